@@ -1,0 +1,437 @@
+"""CPU oracle for the NeuroQuant post-training-quantisation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in `neuroquant_b200/` may import this module; only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
+legs may.  It is a plain PyTorch-CPU (fp32) restatement of the reference's algorithm, written
+as pure functions over explicit tensors (no nn.Module surgery), each citing the reference
+file:line it follows (paths relative to /root/reference).
+
+Pinning: `tests/golden/make_golden.py` imports the UNMODIFIED reference from
+/root/reference (with the three shim modules under `oracle/ref_shims/`) in the build container
+and stores its outputs in `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks every
+function below against those fixtures.  The only un-pinned piece is the third-party
+`hadamard_transform` package (PyPI `hadamard-transform`, version not pinned by the reference,
+absent from /root/reference): restated as the orthonormal Sylvester-ordered Walsh-Hadamard
+transform and checked against `scipy.linalg.hadamard(n)/sqrt(n)`; the ordering of codes along
+the rotated channel axis is therefore "parity unpinned" (weight-space results do not depend on
+it).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+ZETA, GAMMA = 1.1, -0.1  # quantizer.py:274
+
+
+# --------------------------------------------------------------------------------------------
+# Walsh-Hadamard rotation (quant_layer.py:13-22, third-party hadamard_transform at :7,:19)
+# --------------------------------------------------------------------------------------------
+def next_pow2(n: int) -> int:
+    """quant_layer.py:13-14."""
+    return 1 if n == 0 else 2 ** math.ceil(math.log2(n))
+
+
+def fwht_last(x: torch.Tensor) -> torch.Tensor:
+    """Orthonormal Sylvester WHT along the last dim (what quant_layer.py:19 relies on)."""
+    n = x.shape[-1]
+    assert n & (n - 1) == 0
+    y = x.reshape(-1, n).clone()
+    h = 1
+    while h < n:
+        y = y.view(-1, n // (2 * h), 2, h)
+        y = torch.stack((y[:, :, 0] + y[:, :, 1], y[:, :, 0] - y[:, :, 1]), dim=2).reshape(-1, n)
+        h *= 2
+    return (y / math.sqrt(n)).view(x.shape)
+
+
+def hadamard_along_channel(w: torch.Tensor) -> torch.Tensor:
+    """quant_layer.py:16-22: WHT over C_in of a (C_out, C_in, KH, KW) weight."""
+    co, ci, kh, kw = w.shape
+    rows = w.permute(0, 2, 3, 1).reshape(-1, ci)
+    rows = fwht_last(rows)
+    return rows.view(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+
+
+def rotate_weight(w: torch.Tensor) -> torch.Tensor:
+    """quant_layer.py:43-49: zero-pad C_in to a power of two, then rotate."""
+    ci = w.shape[1]
+    pad = next_pow2(ci) - ci
+    return hadamard_along_channel(F.pad(w, (0, 0, 0, 0, 0, pad)))
+
+
+# --------------------------------------------------------------------------------------------
+# Uniform affine quantiser (quantizer.py:76-243)
+# --------------------------------------------------------------------------------------------
+def _scale_max_1(x: torch.Tensor, n_levels: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """quantizer.py:153-168 ('max', asymmetric): python-float min/max -> fp32 tensors."""
+    x_min = min(x.min().item(), 0)
+    x_max = max(x.max().item(), 0)
+    delta = torch.tensor((x_max - x_min) / (n_levels - 1))  # python double -> fp32 tensor
+    delta = torch.max(delta, torch.tensor(1e-8, dtype=torch.float32))
+    zp = (-x_min / delta).round()
+    return delta.to(x.dtype), zp.to(x.dtype)
+
+
+def uaq_init_max(x: torch.Tensor, n_bits: int, channel_wise: bool = True):
+    """quantizer.py:127-152: per-out-channel for 4-D weights, per-tensor for 1-D biases."""
+    n_levels = 2 ** n_bits
+    if channel_wise and x.dim() == 4:
+        pairs = [_scale_max_1(x[c], n_levels) for c in range(x.shape[0])]
+        delta = torch.stack([p[0] for p in pairs]).view(-1, 1, 1, 1)
+        zp = torch.stack([p[1] for p in pairs]).view(-1, 1, 1, 1)
+        return delta, zp
+    d, z = _scale_max_1(x, n_levels)
+    if channel_wise:
+        return d.view(-1), z.view(-1)
+    return d, z
+
+
+def round_ste(x: torch.Tensor) -> torch.Tensor:
+    """quantizer.py:53-57."""
+    return (x.round() - x).detach() + x
+
+
+def uaq_quant(x, delta, zp, n_bits: int):
+    """quantizer.py:117-119.  Returns (codes, dequantised)."""
+    n_levels = 2 ** n_bits
+    codes = torch.clamp(round_ste(x / delta) + zp, 0, n_levels - 1)
+    return codes, (codes - zp) * delta
+
+
+# --------------------------------------------------------------------------------------------
+# AdaRound quantiser (quantizer.py:247-323)
+# --------------------------------------------------------------------------------------------
+def fp16_round(t: torch.Tensor) -> torch.Tensor:
+    """quantizer.py:264-265: delta / zero_point pass through fp16 when AdaRound starts."""
+    return t.detach().half().float()
+
+
+def adaround_init_alpha(x: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
+    """quantizer.py:305-313: alpha s.t. the rectified sigmoid equals the fractional part."""
+    q = x / delta
+    rest = q - torch.floor(q)
+    return -torch.log((ZETA - GAMMA) / (rest - GAMMA) - 1)
+
+
+def soft_targets(alpha: torch.Tensor) -> torch.Tensor:
+    """quantizer.py:302-303."""
+    return torch.clamp(torch.sigmoid(alpha) * (ZETA - GAMMA) + GAMMA, 0, 1)
+
+
+def adaround_quant(x, alpha, delta, zp, n_bits: int, soft: bool):
+    """quantizer.py:288-300 ('learned_hard_sigmoid').  Returns (codes, dequantised)."""
+    n_levels = 2 ** n_bits
+    x_floor = torch.floor(x / delta)
+    x_int = x_floor + (soft_targets(alpha) if soft else (alpha >= 0).float())
+    codes = torch.clamp(x_int + zp, 0, n_levels - 1)
+    return codes, (codes - zp) * delta
+
+
+# --------------------------------------------------------------------------------------------
+# Losses and schedules (quantizer.py:66-73, calib_model.py:16-89, data_utils.py:24-41)
+# --------------------------------------------------------------------------------------------
+def lp_loss(pred, tgt, p: float = 2.0, reduction: str = "none"):
+    if reduction == "none":
+        return (pred - tgt).abs().pow(p).sum(1).mean()
+    return (pred - tgt).abs().pow(p).mean()
+
+
+def round_reg(alpha: torch.Tensor, b: float) -> torch.Tensor:
+    """calib_model.py:44-45 (one tensor, before the `weight` factor)."""
+    return (1 - ((soft_targets(alpha) - 0.5).abs() * 2).pow(b)).sum()
+
+
+class LinearTempDecay:
+    """data_utils.py:24-41."""
+
+    def __init__(self, t_max, rel_start_decay=0.2, start_b=10, end_b=2):
+        self.t_max = t_max
+        self.start_decay = rel_start_decay * t_max
+        self.start_b = start_b
+        self.end_b = end_b
+
+    def __call__(self, t):
+        if t < self.start_decay:
+            return self.start_b
+        rel_t = (t - self.start_decay) / (self.t_max - self.start_decay)
+        return self.end_b + (self.start_b - self.end_b) * max(0.0, 1 - rel_t)
+
+
+def psnr(out: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """utils.py:148-151, per frame."""
+    mse = ((out - gt) ** 2).flatten(1).mean(1)
+    return -10 * torch.log10(mse + 1e-9)
+
+
+# --------------------------------------------------------------------------------------------
+# Decoder description: every decoder stage is conv(k, same) -> shuffle(rh, rw) -> activation
+# (HNeRV.py:29-42,49-71; NeRV.py:23-38,44-65; _layers.py:10-36)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Stage:
+    weight: torch.Tensor  # (C_out, C_in, k, k) reference layout
+    bias: torch.Tensor  # (C_out,)
+    rh: int = 1  # up-shuffle factors (PixelShuffle r, or the stem's fc_h/fc_w fold)
+    rw: int = 1
+    act: str = "none"  # 'none' | 'gelu' | 'tanh' (OutImg: 0.5*tanh+0.5)
+
+    @property
+    def k(self) -> int:
+        return self.weight.shape[-1]
+
+
+def decoder_geometry(cfg: dict, arch: str):
+    """Per-stage (c_in, c_out, k, rh, rw, act) from a reference YAML config."""
+    arch = arch.lower()
+    strides = list(cfg["dec_strides"])
+    geo = []
+    if arch == "hnerv":
+        import numpy as np
+
+        fc = int(np.prod(cfg["enc_strides"]) // np.prod(cfg["dec_strides"]))
+        c = cfg["dec_in_channel"]
+        geo.append((cfg["enc_channel"][-1], c, 1, fc, fc, "none"))  # HNeRV.py:32,57
+    elif arch == "nerv":
+        import numpy as np
+
+        fch = cfg["crop_h"] // int(np.prod(strides))
+        fcw = cfg["crop_w"] // int(np.prod(strides))
+        c = cfg["dec_in_channel"]
+        geo.append((int(cfg["level"] * 2), c * fch * fcw, 1, fch, fcw, "none"))  # NeRV.py:26,51
+    else:
+        raise ValueError(arch)
+    for ks, s in zip(cfg["dec_kernels"], strides):
+        co = int(max(round(c / cfg["channel_reduce"]), cfg["channel_lbound"]))
+        geo.append((c, co * s * s, ks, s, s, cfg["dec_acts"]))
+        c = co
+    geo.append((c, 3, 3, 1, 1, cfg["out_bias"]))
+    return geo
+
+
+def stages_from_state_dict(sd: dict, cfg: dict, arch: str) -> List[Stage]:
+    """Pick decoder/head tensors out of a reference state_dict (keys per SURVEY section 5)."""
+    geo = decoder_geometry(cfg, arch)
+    n_blocks = len(cfg["dec_kernels"])
+    names = ["decoder.0"] + [f"decoder.{i}.conv.0" for i in range(1, n_blocks + 1)] + ["head_layer"]
+    out = []
+    for (ci, co, k, rh, rw, act), nm in zip(geo, names):
+        w, b = sd[nm + ".weight"].detach().float().cpu(), sd[nm + ".bias"].detach().float().cpu()
+        assert tuple(w.shape) == (co, ci, k, k), (nm, tuple(w.shape), (co, ci, k, k))
+        out.append(Stage(w.clone(), b.clone(), rh, rw, act))
+    return out
+
+
+def up_shuffle(x: torch.Tensor, rh: int, rw: int) -> torch.Tensor:
+    """out[n,c,h*rh+i,w*rw+j] = in[n,c*rh*rw+i*rw+j,h,w]  (nn.PixelShuffle for rh==rw;
+    the stem fold of HNeRV.py:57 / NeRV.py:51 in general)."""
+    if rh == 1 and rw == 1:
+        return x
+    n, c, h, w = x.shape
+    return x.view(n, -1, rh, rw, h, w).permute(0, 1, 4, 2, 5, 3).reshape(n, -1, rh * h, rw * w)
+
+
+def apply_act(x: torch.Tensor, act: str) -> torch.Tensor:
+    if act == "none":
+        return x
+    if act == "gelu":
+        return F.gelu(x)  # exact erf, _layers.py:105
+    if act == "tanh":
+        return torch.tanh(x) * 0.5 + 0.5  # _layers.py:13-14
+    if act == "sigmoid":
+        return torch.sigmoid(x)
+    raise ValueError(act)
+
+
+def decode(stages: Sequence[Stage], embed: torch.Tensor,
+           weights: Optional[Sequence[torch.Tensor]] = None,
+           biases: Optional[Sequence[torch.Tensor]] = None,
+           keep: bool = False):
+    """HNeRV.decode / NeRV.decode with (optionally substituted) weights."""
+    x = embed
+    feats = []
+    for i, st in enumerate(stages):
+        w = st.weight if weights is None else weights[i]
+        b = st.bias if biases is None else biases[i]
+        x = F.conv2d(x, w, b, stride=1, padding=st.k // 2)  # quant_layer.py:80
+        x = apply_act(up_shuffle(x, st.rh, st.rw), st.act)
+        if keep:
+            feats.append(x)
+    return (x, feats) if keep else x
+
+
+# --------------------------------------------------------------------------------------------
+# Quantised decoder state (QuantModel / QuantModule bookkeeping, quant_model.py, quant_layer.py)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class QStage:
+    stage: Stage
+    n_bits: int
+    hadamard: bool
+    w_src: torch.Tensor = None  # tensor that is quantised: weight, or rotated+padded weight
+    delta_w: torch.Tensor = None
+    zp_w: torch.Tensor = None
+    delta_b: torch.Tensor = None
+    zp_b: torch.Tensor = None
+    alpha_w: Optional[torch.Tensor] = None
+    alpha_b: Optional[torch.Tensor] = None
+    codes_w: Optional[torch.Tensor] = None  # cache of the last forward (quantizer.py:297)
+    codes_b: Optional[torch.Tensor] = None
+
+
+class QuantDecoder:
+    """Functional stand-in for QuantModel(model, hadamard, {'channel_wise': True, 'max'})."""
+
+    def __init__(self, stages: Sequence[Stage], bits: Sequence[int], hadamard: bool):
+        assert len(bits) == len(stages)
+        self.q: List[QStage] = []
+        for st, nb in zip(stages, bits):
+            assert 2 <= nb <= 8  # quantizer.py:96,237
+            qs = QStage(st, nb, hadamard)
+            qs.w_src = rotate_weight(st.weight) if hadamard else st.weight.clone()
+            self.q.append(qs)
+        self.mode = "uaq"  # 'off' | 'uaq' | 'ada'
+        self.soft_w = False
+        self.soft_b = False
+        self.init_scales()
+
+    @property
+    def stages(self):
+        return [q.stage for q in self.q]
+
+    def avg_bits(self) -> float:
+        """quant_model.py:58-72."""
+        bits = sum(q.n_bits * (q.stage.weight.numel() + q.stage.bias.numel()) for q in self.q)
+        return bits / sum(q.stage.weight.numel() + q.stage.bias.numel() for q in self.q)
+
+    def init_scales(self):
+        """First quantised forward: quantizer.py:112-115 on what quant_layer.py:70-74 feeds it."""
+        for q in self.q:
+            q.delta_w, q.zp_w = uaq_init_max(q.w_src, q.n_bits, True)
+            q.delta_b, q.zp_b = uaq_init_max(q.stage.bias, q.n_bits, True)
+
+    def start_adaround(self):
+        """calib_model.py:169-184 + quantizer.py:259-319."""
+        for q in self.q:
+            q.delta_w, q.zp_w = fp16_round(q.delta_w), fp16_round(q.zp_w)
+            q.delta_b, q.zp_b = fp16_round(q.delta_b), fp16_round(q.zp_b)
+            src = q.w_src if q.hadamard else q.stage.weight  # hadamard_weight | org_weight
+            q.alpha_w = adaround_init_alpha(src, q.delta_w)
+            q.alpha_b = adaround_init_alpha(q.stage.bias, q.delta_b)
+        self.mode, self.soft_w, self.soft_b = "ada", True, True
+
+    def quantised_params(self, q: QStage):
+        """quant_layer.py:67-77: returns the (weight, bias) the conv sees."""
+        if self.mode == "off":
+            return q.stage.weight, q.stage.bias
+        if self.mode == "uaq":
+            q.codes_w, wq = uaq_quant(q.w_src, q.delta_w, q.zp_w, q.n_bits)
+            q.codes_b, bq = uaq_quant(q.stage.bias, q.delta_b, q.zp_b, q.n_bits)
+        else:
+            q.codes_w, wq = adaround_quant(q.w_src, q.alpha_w, q.delta_w, q.zp_w, q.n_bits, self.soft_w)
+            q.codes_b, bq = adaround_quant(q.stage.bias, q.alpha_b, q.delta_b, q.zp_b, q.n_bits, self.soft_b)
+        if q.hadamard:
+            ci = q.stage.weight.shape[1]
+            wq = hadamard_along_channel(wq)[:, :ci]
+        return wq, bq
+
+    def forward(self, embed: torch.Tensor) -> torch.Tensor:
+        ws, bs = zip(*[self.quantised_params(q) for q in self.q])
+        return decode(self.stages, embed, ws, bs)
+
+    def perturbation(self):
+        """quant_layer.py:86-89: org_weight - UAQ(weight) -- never rotated."""
+        out = []
+        for q in self.q:
+            # with --hadamard the scales were fitted on the rotated tensor but are applied to the
+            # plain weight here (reference quirk, quant_layer.py:70 vs :88)
+            _, wq = uaq_quant(q.stage.weight, q.delta_w, q.zp_w, q.n_bits)
+            out.append(q.stage.weight - wq)
+        return out
+
+
+def model_reconstruction(qd: QuantDecoder, cali: torch.Tensor, frames: torch.Tensor,
+                         batches: Sequence[Sequence[int]], iters: int, weight: float = 0.01,
+                         b_range=(20, 2), warmup: float = 0.0, p: float = 2.0, lr: float = 0.0015,
+                         log: Optional[list] = None):
+    """calib_model.py:92-240 with the mini-batch order injected (`batches` = one epoch of index
+    lists; the reference shuffles un-seeded, calibrate_network.py:161)."""
+    n_b = len(batches)
+    # ---- phase 1: step sizes, Adam lr 1e-3 (calib_model.py:120-165)
+    ep1 = int(0.05 * iters / n_b)
+    deltas = []
+    for q in qd.q:
+        q.delta_w = q.delta_w.clone().requires_grad_(True)
+        q.delta_b = q.delta_b.clone().requires_grad_(True)
+        deltas += [q.delta_w, q.delta_b]
+    opt = torch.optim.Adam(deltas, lr=0.001)
+    count = 0
+    for _ in range(ep1):
+        for idx in batches:
+            idx = torch.as_tensor(idx)
+            out = qd.forward(cali[idx])
+            opt.zero_grad()
+            count += 1
+            loss = lp_loss(out, frames[idx], p=p)
+            loss.backward()
+            opt.step()
+            if log is not None:
+                log.append(("delta", count, float(loss), 0.0, 0.0))
+    for q in qd.q:
+        q.delta_w, q.delta_b = q.delta_w.detach(), q.delta_b.detach()
+    # ---- phase 2: rounding variables (calib_model.py:169-226)
+    qd.start_adaround()
+    alphas = []
+    for q in qd.q:
+        q.alpha_w = q.alpha_w.clone().requires_grad_(True)
+        q.alpha_b = q.alpha_b.clone().requires_grad_(True)
+        alphas += [q.alpha_w, q.alpha_b]
+    opt = torch.optim.Adam(alphas, lr=lr)
+    decay = LinearTempDecay(iters, rel_start_decay=warmup, start_b=b_range[0], end_b=b_range[1])
+    loss_start = iters * warmup
+    count = 0
+    for _ in range(int(iters / n_b) - ep1):
+        for idx in batches:
+            idx = torch.as_tensor(idx)
+            out = qd.forward(cali[idx])
+            opt.zero_grad()
+            count += 1
+            rec = lp_loss(out, frames[idx], p=p)
+            b = decay(count)
+            if count < loss_start:
+                b, rnd = 0, torch.zeros(())
+            else:
+                rnd = sum(weight * round_reg(q.alpha_w, b) for q in qd.q)  # bias alpha excluded
+            (rec + rnd).backward()
+            opt.step()
+            if log is not None:
+                log.append(("alpha", count, float(rec), float(rnd), float(b)))
+    for q in qd.q:
+        q.alpha_w, q.alpha_b = q.alpha_w.detach(), q.alpha_b.detach()
+    qd.soft_w = False  # calib_model.py:231-240: only the weight quantiser goes hard
+    return qd
+
+
+# --------------------------------------------------------------------------------------------
+# Omega = dw^T H dw sensitivity (bit_assign.py:57-118,171-203)
+# --------------------------------------------------------------------------------------------
+def omega(stages: Sequence[Stage], vec: Sequence[torch.Tensor], embeds: Sequence[torch.Tensor],
+          frames: Sequence[torch.Tensor]):
+    """Sum over the given batches of v^T H v, H the Hessian of MSE-mean wrt the conv weights.
+    Returns (omega_total, per_layer list)."""
+    ws = [s.weight.clone().requires_grad_(True) for s in stages]
+    bs = [s.bias for s in stages]
+    hv = [torch.zeros_like(w) for w in ws]
+    for e, f in zip(embeds, frames):
+        out = decode(stages, e, ws, bs)
+        loss = F.mse_loss(out, f)
+        g = torch.autograd.grad(loss, ws, create_graph=True)
+        prod = sum((gi * vi).sum() for gi, vi in zip(g, vec))
+        h = torch.autograd.grad(prod, ws)
+        hv = [a + b for a, b in zip(hv, h)]
+    per = [float((h * v).sum()) for h, v in zip(hv, vec)]
+    return sum(per), per
