@@ -1,0 +1,210 @@
+/*
+ * neuroquant_b200.h -- C ABI of libnq_sm100.so, the B200 (sm_100a) kernels behind the NeuroQuant
+ * post-training-quantisation hot path.
+ *
+ * The reference (Eric-qi/NeuroQuant) has no FFI layer: its boundary for this path is the Python API
+ * of quantization/ (quantizer, quant_layer, quant_block, quant_model, calib_model).  Each entry point below names the reference statement(s) it replaces
+ * (paths relative to the reference root).  The library is stateless: the caller (PyTorch host code in
+ * neuroquant_b200/, or any other host) owns every buffer and passes raw DEVICE pointers, explicit
+ * sizes and the CUDA stream (cudaStream_t as void*).  Every function returns 0 on success or a negative
+ * nq_status; nothing throws and nothing synchronises.  All tensors are fp32 unless stated.
+ *
+ * Layouts
+ *   "ref"    weight  (C_out, C_in, KH, KW) contiguous, exactly the reference's nn.Conv2d layout
+ *            (with --hadamard the quantised tensor is (C_out, C_pow2, KH, KW)).
+ *   "packed" weight  Wk[(kh*KW+kw)*cin_p + ci][n']   (GEMM-K rows, GEMM-N contiguous), n' the packed
+ *            output channel: n' = (i*rw + j)*cg + c  for reference channel  c*rh*rw + i*rw + j,
+ *            so that the up-shuffle (nn.PixelShuffle / the stem fold) becomes a contiguous store.
+ *            cin_p, cg are channel counts rounded up to a multiple of 4; pad entries are zero.
+ *   "packedT" Wt[((KH-1-kh)*KW+(KW-1-kw))*nout_p + n'][ci]  the flipped transpose used by dgrad.
+ *   activations      NHWC  x[n][h][w][c_p]  (channels-last, padded channels hold zeros)
+ *   frames           NCHW  (B, 3, H, W) exactly as the reference's dataloader produces them.
+ */
+#ifndef NEUROQUANT_B200_H_
+#define NEUROQUANT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum nq_status {
+  NQ_OK = 0,
+  NQ_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, bits outside 2..8 (quantizer.py:96) */
+  NQ_ERR_BAD_SHAPE = -2,    /* padding / divisibility contract of a layout violated */
+  NQ_ERR_UNSUPPORTED = -3,  /* e.g. rotation length > 256 or not a power of two */
+  NQ_ERR_WORKSPACE = -4,    /* caller-provided workspace too small */
+  NQ_ERR_CUDA = -5          /* a CUDA runtime call / launch failed (see nq_last_cuda_error) */
+} nq_status;
+
+const char* nq_status_string(int status);
+/* cudaError_t of the most recent NQ_ERR_CUDA on the calling thread (0 if none). */
+int nq_last_cuda_error(void);
+/* ABI version; bumped on any signature change. */
+int nq_abi_version(void);
+/* Device properties the host needs for grid sizing: SM count of the current device. */
+int nq_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantisers (quantization/quantizer.py)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* UniformAffineQuantizer.init_quantization_scale, 'max', asymmetric (quantizer.py:127-168), replacing
+ * the per-channel Python loop with .item() syncs (:139-140).  x: rows x row_len (one row per output
+ * channel; rows==1 for the per-tensor bias case, :144-152).  Writes delta[rows], zero_point[rows]. */
+int nq_uaq_init_max(const float* x, int64_t rows, int64_t row_len, int n_bits,
+                    float* delta, float* zero_point, void* stream);
+
+typedef enum nq_round_mode {
+  NQ_ROUND_NEAREST = 0, /* UAQ forward, round-half-even + STE   (quantizer.py:117-119, :53-57) */
+  NQ_ROUND_SOFT = 1,    /* AdaRound floor + h(alpha)           (quantizer.py:288-291, :302-303) */
+  NQ_ROUND_HARD = 2     /* AdaRound floor + [alpha >= 0]        (quantizer.py:292-293) */
+} nq_round_mode;
+
+/* Fake-quantise x (rows x row_len, row r uses delta[r*d_stride], zero_point[r*d_stride]; d_stride 0
+ * broadcasts one scale).  codes (may be NULL) receives clamp(x_int + zp, 0, 2^bits-1) -- the tensor the
+ * reference caches in AdaRoundQuantizer.x_quant (quantizer.py:297); deq (may be NULL) receives
+ * (codes - zp) * delta (quantizer.py:119, :298).  alpha is required for the two AdaRound modes.
+ * reg_sum (may be NULL): *reg_sum += sum(1 - |2 h(alpha) - 1|^reg_b) (calib_model.py:44-45, before the
+ * `weight` factor); the caller zeroes it. */
+int nq_fakequant_fwd(const float* x, const float* alpha, const float* delta, const float* zero_point,
+                     int64_t rows, int64_t row_len, int d_stride, int n_bits, int mode,
+                     float* codes, float* deq, float* reg_sum, float reg_b, void* stream);
+
+/* Backward of the above w.r.t. the learnable of each phase (closed forms verified against autograd of
+ * quantizer.py, see tests):
+ *   NQ_ROUND_NEAREST: d_delta[r] = sum_row g * ((codes - zp) - [in range] * x / delta)     (phase 1)
+ *   NQ_ROUND_SOFT   : d_alpha    = g * delta * [in range] * h'(alpha)  + reg_w * d reg / d alpha (phase 2)
+ * g is the gradient w.r.t. the de-quantised tensor.  reg_w = 0 disables the regulariser term
+ * (calib_model.py:77-78 warm-up, and always for biases, :44).  grad_scale multiplies g first (1/G for the
+ * mean over G data-parallel ranks). */
+int nq_fakequant_bwd(const float* g, const float* x, const float* alpha, const float* delta,
+                     const float* zero_point, int64_t rows, int64_t row_len, int d_stride, int n_bits,
+                     int mode, float grad_scale, float reg_w, float reg_b,
+                     float* d_alpha, float* d_delta, void* stream);
+
+/* AdaRoundQuantizer.init_alpha (quantizer.py:305-313). */
+int nq_adaround_init_alpha(const float* x, const float* delta, int64_t rows, int64_t row_len,
+                           int d_stride, float* alpha, void* stream);
+
+/* torch.optim.Adam single step (defaults: amsgrad off, no weight decay; calib_model.py:134,195) over one
+ * flat tensor; step is 1-based.  Arithmetic order follows torch's single-tensor implementation. */
+int nq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 double lr, double beta1, double beta2, double eps, int step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Walsh-Hadamard rotation (quantization/quant_layer.py:16-22; third-party hadamard_transform)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Orthonormal Sylvester WHT of length n (power of two, <= 256) along a strided axis:
+ * element k of vector v lives at base + (v / inner) * outer_stride + (v % inner) + k * inner, which
+ * covers both "rows of a matrix" (inner = 1, outer_stride = n) and "the C_in axis of a ref-layout
+ * weight" (inner = KH*KW, outer_stride = n*KH*KW).  src == dst is allowed. */
+int nq_fwht(const float* src, float* dst, int64_t n_vectors, int n, int64_t inner,
+            int64_t outer_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight packing between the reference layout and the GEMM layouts
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct nq_conv_desc {
+  int32_t n, h, w;   /* input grid: batch, height, width */
+  int32_t cin;       /* real input channels */
+  int32_t cin_p;     /* padded input channels (multiple of 4) */
+  int32_t ksize;     /* square, odd; stride 1, "same" zero padding (quant_layer.py:33-34) */
+  int32_t cout;      /* real output channels of the conv = c_grp * rh * rw */
+  int32_t rh, rw;    /* up-shuffle factors applied after the conv (1,1 = none) */
+  int32_t c_grp;     /* real channels after the shuffle */
+  int32_t cg;        /* padded channels after the shuffle (multiple of 4) */
+  int32_t act;       /* 0 none, 1 exact-erf GELU (nn.GELU, _layers.py:105) */
+} nq_conv_desc;
+/* derived: nout_p = rh*rw*cg (GEMM N), kdim = ksize*ksize*cin_p (GEMM K) */
+
+/* ref (cout, cin_src, k, k) -> packed Wk [kdim][nout_p] and/or packedT Wt [k*k*nout_p][cin_p]
+ * (either may be NULL); bias_ref (cout) -> bias_packed [nout_p] (either NULL to skip).  cin_src >= cin is
+ * the channel count of the source tensor (C_pow2 after the inverse rotation; extra channels dropped,
+ * quant_layer.py:71 `[:, :self.C]`). */
+int nq_pack_weight(const nq_conv_desc* d, const float* w_ref, int cin_src, const float* bias_ref,
+                   float* wk, float* wt, float* bias_packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder stages (quantization/quant_layer.py:80 F.conv2d; quant_block.py:31-35; models/HNeRV.py:49-71)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* conv(k, same) + bias + up-shuffle(rh, rw) + activation, NHWC.
+ *   x  (n, h, w, cin_p)   wk packed [kdim][nout_p]   bias_packed [nout_p]
+ *   y  (n, h*rh, w*rw, cg) activated output;  z (same shape, may be NULL) pre-activation, kept for
+ *   the backward pass.  Exact fp32 FFMA path (NQ_PREC_FP32). */
+int nq_conv_fwd(const nq_conv_desc* d, const float* x, const float* wk, const float* bias_packed,
+                float* z, float* y, void* stream);
+
+/* Data gradient of the stage, fused with the previous stage's activation derivative and un-shuffle:
+ *   dz      (n, h, w, nout_p)      gradient w.r.t. this stage's conv output (packed channel order)
+ *   wt      packedT weights
+ *   z_prev  (n, h, w, cin_p) or NULL   pre-activation of the previous stage (same grid as x)
+ *   dz_prev (n, h/prev_rh, w/prev_rw, prev_rh*prev_rw*cin_p): gradient w.r.t. the previous stage's conv
+ *           output, i.e. (dx * act'(z_prev)) un-shuffled.  prev_act as nq_conv_desc.act. */
+int nq_conv_dgrad(const nq_conv_desc* d, const float* dz, const float* wt, const float* z_prev,
+                  int prev_rh, int prev_rw, int prev_act, float* dz_prev, void* stream);
+
+/* Weight + bias gradient.  Writes dwk [(kdim + 4)][nout_p]: rows < kdim are dWk in packed layout, row
+ * kdim is the bias gradient (sum of dz over pixels), rows kdim+1.. are zero.  The pixel axis is split
+ * over `splits` CTAs per tile; partials go to `workspace` (>= splits*(kdim+4)*nout_p floats when
+ * splits > 1) and are summed in a fixed order, so the result is run-to-run deterministic. */
+int nq_conv_wgrad(const nq_conv_desc* d, const float* x, const float* dz, float* dwk,
+                  float* workspace, int64_t workspace_floats, int splits, void* stream);
+
+/* packed gradient -> ref layout: dw_ref (cout, cin_dst, k, k) with channels >= cin zero-filled (the
+ * zero pad of quant_layer.py:47 before the rotation), db_ref (cout).  Either output may be NULL. */
+int nq_unpack_wgrad(const nq_conv_desc* d, const float* dwk, int cin_dst, float* dw_ref, float* db_ref,
+                    void* stream);
+
+/* Head: 3x3 conv to 3 channels + OutImg + reconstruction loss (models/HNeRV.py:63-64, _layers.py:10-16,
+ * quantizer.py:66-73), one pass.
+ *   x (n, h, w, cin_p); w_head packed [9*cin_p][4]; bias_head [4]
+ *   out_bias: 0 tanh (0.5*tanh+0.5), 1 sigmoid
+ *   img   (n, 3, h, w) NCHW output frame (may be NULL)
+ *   target (n, 3, h, w) or NULL (decode only).  With a target: *loss_sum += sum_c |img - tgt|^p over all
+ *   pixels (caller zeroes; divide by the GLOBAL pixel count for lp_loss), and dz_head (n, h, w, 4) (may be
+ *   NULL) receives d lp_loss / d(conv output) with the mean taken over `mean_pixels` pixels. */
+int nq_head_fwd_loss(const nq_conv_desc* d, const float* x, const float* w_head, const float* bias_head,
+                     int out_bias, const float* target, float p, float mean_pixels,
+                     float* img, float* loss_sum, float* dz_head, void* stream);
+
+/* Head weight/bias gradient: dwk_head [(9*cin_p + 4)][4] as nq_conv_wgrad; workspace >= blocks*(9*cin_p+4)*4
+ * floats with blocks = nq_head_wgrad_blocks(d). */
+int nq_head_wgrad_blocks(const nq_conv_desc* d);
+int nq_head_wgrad(const nq_conv_desc* d, const float* x, const float* dz_head, float* dwk_head,
+                  float* workspace, int64_t workspace_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout edges and reductions
+ * ------------------------------------------------------------------------------------------------ */
+/* NCHW (n, c, h, w) <-> NHWC (n, h, w, c_p); pad channels are written as zero / ignored. */
+int nq_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream);
+int nq_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream);
+
+/* Activation backward + un-shuffle for a stage whose consumer is outside this library (autograd of
+ * nn.GELU + nn.PixelShuffle, quant_block.py:33-34): dy, z (n, h*rh, w*rw, cg) -> dz (n, h, w, rh*rw*cg). */
+int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int h, int w, int rh, int rw, int cg,
+                         int act, float* dz, void* stream);
+
+/* lp_loss (quantizer.py:66-73) standalone: *loss_sum += sum |pred - tgt|^p; grad (may be NULL) receives
+ * grad_scale * p * |d|^(p-1) * sign(d). */
+int nq_lp_loss(const float* pred, const float* tgt, int64_t numel, float p, float grad_scale,
+               float* loss_sum, float* grad, void* stream);
+
+/* Multi-tensor reductions for bit_assign (bit_assign.py:198-200, :211): out[t] = sum_i a_t[i]*b_t[i]
+ * (mode 0, Omega) or sum_i a_t[i]^2 * b_t[i]^2 (mode 1, diagonal Fisher).  a_ptrs/b_ptrs/sizes are HOST
+ * arrays of n_tensors entries (device pointers inside); out is a device array, overwritten. */
+int nq_multi_dot(const float* const* a_ptrs, const float* const* b_ptrs, const int64_t* sizes,
+                 int n_tensors, int mode, float* out, void* stream);
+
+/* PSNR per frame (utils.py:148-151): psnr[i] = -10 log10(mean((a_i - b_i)^2) + 1e-9), frames of
+ * `frame_numel` elements. */
+int nq_psnr(const float* a, const float* b, int n_frames, int64_t frame_numel, float* psnr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUROQUANT_B200_H_ */

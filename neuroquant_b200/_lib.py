@@ -1,0 +1,197 @@
+"""ctypes binding of libnq_sm100.so (C ABI declared in include/neuroquant_b200.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every wrapper
+refuses non-CUDA tensors.  PyTorch is only the owner of device memory and streams here; pointers and
+sizes cross the boundary as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnq_sm100.so")
+
+
+class NqError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """Mirror of nq_conv_desc."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("n", "h", "w", "cin", "cin_p", "ksize", "cout", "rh", "rw", "c_grp", "cg", "act")]
+
+    @property
+    def nout_p(self):
+        return self.rh * self.rw * self.cg
+
+    @property
+    def kdim(self):
+        return self.ksize * self.ksize * self.cin_p
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise NqError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C neuroquant_b200/csrc`).  neuroquant_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    P, I, L, F, D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    DP = C.POINTER(ConvDesc)
+    sigs = {
+        "nq_status_string": (C.c_char_p, [I]),
+        "nq_last_cuda_error": (I, []),
+        "nq_abi_version": (I, []),
+        "nq_sm_count": (I, []),
+        "nq_uaq_init_max": (I, [P, L, L, I, P, P, P]),
+        "nq_fakequant_fwd": (I, [P, P, P, P, L, L, I, I, I, P, P, P, F, P]),
+        "nq_fakequant_bwd": (I, [P, P, P, P, P, L, L, I, I, I, F, F, F, P, P, P]),
+        "nq_adaround_init_alpha": (I, [P, P, L, L, I, P, P]),
+        "nq_adam_step": (I, [P, P, P, P, L, D, D, D, D, I, P]),
+        "nq_fwht": (I, [P, P, L, I, L, L, P]),
+        "nq_pack_weight": (I, [DP, P, I, P, P, P, P, P]),
+        "nq_conv_fwd": (I, [DP, P, P, P, P, P, P]),
+        "nq_conv_dgrad": (I, [DP, P, P, P, I, I, I, P, P]),
+        "nq_conv_wgrad": (I, [DP, P, P, P, P, L, I, P]),
+        "nq_unpack_wgrad": (I, [DP, P, I, P, P, P]),
+        "nq_head_fwd_loss": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
+        "nq_head_wgrad_blocks": (I, [DP]),
+        "nq_head_wgrad": (I, [DP, P, P, P, P, L, P]),
+        "nq_nchw_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
+        "nq_nhwc_to_nchw": (I, [P, P, I, I, I, I, I, P]),
+        "nq_act_bwd_unshuffle": (I, [P, P, I, I, I, I, I, I, I, P, P]),
+        "nq_lp_loss": (I, [P, P, L, F, F, P, P, P]),
+        "nq_multi_dot": (I, [P, P, P, I, I, P, P]),
+        "nq_psnr": (I, [P, P, I, L, P, P]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library drift: fail loudly
+        fn.restype, fn.argtypes = res, args
+    return lib, tuple(sigs)
+
+
+lib, EXPORTS = _load()
+ABI_VERSION = lib.nq_abi_version()
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib.nq_status_string(status).decode()
+        extra = f" (cudaError {lib.nq_last_cuda_error()})" if status == -5 else ""
+        raise NqError(f"{what}: {msg}{extra}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NqError("neuroquant_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise NqError(f"expected a contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# -------------------------------------------------------------------------------------------------
+# thin typed wrappers (tensor in, tensor out); names follow the C ABI
+# -------------------------------------------------------------------------------------------------
+def rows_of(x: torch.Tensor, channel_wise: bool):
+    """(rows, row_len, d_stride) of the reference's scale broadcasting: one scale per output channel
+    for 4-D weights, one per tensor for 1-D biases (quantizer.py:131-152)."""
+    if channel_wise and x.dim() == 4:
+        return x.shape[0], x.numel() // x.shape[0], 1
+    return 1, x.numel(), 0
+
+
+def uaq_init_max(x, n_bits, channel_wise=True):
+    rows, row_len, _ = rows_of(x, channel_wise)
+    delta = torch.empty(rows, device=x.device, dtype=torch.float32)
+    zp = torch.empty_like(delta)
+    check(lib.nq_uaq_init_max(ptr(x), rows, row_len, n_bits, ptr(delta), ptr(zp), stream()), "nq_uaq_init_max")
+    if x.dim() == 4 and channel_wise:
+        return delta.view(-1, 1, 1, 1), zp.view(-1, 1, 1, 1)
+    return delta.view(-1), zp.view(-1)
+
+
+def fakequant_fwd(x, alpha, delta, zp, n_bits, mode, want_codes=True, want_deq=True, reg_sum=None, reg_b=0.0):
+    rows, row_len, d_stride = (delta.numel(), x.numel() // delta.numel(), 1) if delta.numel() > 1 else (1, x.numel(), 0)
+    codes = torch.empty_like(x) if want_codes else None
+    deq = torch.empty_like(x) if want_deq else None
+    check(lib.nq_fakequant_fwd(ptr(x), ptr(alpha), ptr(delta), ptr(zp), rows, row_len, d_stride, n_bits, mode,
+                               ptr(codes), ptr(deq), ptr(reg_sum), float(reg_b), stream()), "nq_fakequant_fwd")
+    return codes, deq
+
+
+def fakequant_bwd(g, x, alpha, delta, zp, n_bits, mode, grad_scale=1.0, reg_w=0.0, reg_b=0.0, out=None):
+    rows, row_len, d_stride = (delta.numel(), x.numel() // delta.numel(), 1) if delta.numel() > 1 else (1, x.numel(), 0)
+    if mode == 1:
+        d_alpha = out if out is not None else torch.empty_like(x)
+        d_delta = None
+    else:
+        d_alpha = None
+        d_delta = out if out is not None else torch.empty_like(delta)
+    check(lib.nq_fakequant_bwd(ptr(g), ptr(x), ptr(alpha), ptr(delta), ptr(zp), rows, row_len, d_stride, n_bits,
+                               mode, float(grad_scale), float(reg_w), float(reg_b), ptr(d_alpha), ptr(d_delta),
+                               stream()), "nq_fakequant_bwd")
+    return d_alpha if mode == 1 else d_delta
+
+
+def adaround_init_alpha(x, delta):
+    rows, row_len, d_stride = (delta.numel(), x.numel() // delta.numel(), 1) if delta.numel() > 1 else (1, x.numel(), 0)
+    alpha = torch.empty_like(x)
+    check(lib.nq_adaround_init_alpha(ptr(x), ptr(delta), rows, row_len, d_stride, ptr(alpha), stream()),
+          "nq_adaround_init_alpha")
+    return alpha
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(lib.nq_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
+                           eps, step, stream()), "nq_adam_step")
+
+
+def fwht_channel(w: torch.Tensor, out=None):
+    """Orthonormal WHT along dim 1 of a contiguous (C_out, C, KH, KW) tensor."""
+    co, c, kh, kw = w.shape
+    out = torch.empty_like(w) if out is None else out
+    inner = kh * kw
+    check(lib.nq_fwht(ptr(w), ptr(out), co * inner, c, inner, c * inner, stream()), "nq_fwht")
+    return out
+
+
+def fwht_rows(x: torch.Tensor):
+    n = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib.nq_fwht(ptr(x), ptr(out), x.numel() // n, n, 1, n, stream()), "nq_fwht")
+    return out
+
+
+def lp_loss_sum(pred, tgt, p=2.0, grad_scale=0.0, want_grad=False):
+    loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if want_grad else None
+    check(lib.nq_lp_loss(ptr(pred), ptr(tgt), pred.numel(), float(p), float(grad_scale), ptr(loss), ptr(grad),
+                         stream()), "nq_lp_loss")
+    return loss, grad
+
+
+def multi_dot(a_list, b_list, mode=0):
+    n = len(a_list)
+    a_arr = (C.c_void_p * n)(*[ptr(a) for a in a_list])
+    b_arr = (C.c_void_p * n)(*[ptr(b) for b in b_list])
+    s_arr = (C.c_int64 * n)(*[a.numel() for a in a_list])
+    out = torch.empty(n, device=a_list[0].device, dtype=torch.float32)
+    check(lib.nq_multi_dot(a_arr, b_arr, s_arr, n, mode, ptr(out), stream()), "nq_multi_dot")
+    return out
+
+
+def psnr(a, b):
+    n = a.shape[0]
+    out = torch.empty(n, device=a.device, dtype=torch.float32)
+    check(lib.nq_psnr(ptr(a), ptr(b), n, a.numel() // n, ptr(out), stream()), "nq_psnr")
+    return out

@@ -1,0 +1,403 @@
+// Rotation (FWHT), weight packing, layout edges, loss / dot / PSNR reductions, library plumbing.
+#include "nq_common.cuh"
+
+namespace nq {
+
+thread_local int g_last_cuda_error = 0;
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static inline int grid_for(int64_t numel, int block = 256) {
+  int64_t b = (numel + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-shuffle Walsh-Hadamard: one warp per vector, element k = lane + 32*r held in register r of
+// lane `lane` (n <= 256 -> R <= 8).  Butterflies over bits 0-4 are lane exchanges, over bits 5-7 are
+// register exchanges.  Same stage order (h = 1, 2, 4, ...) and operand order (a+b, a-b) as the
+// Sylvester butterfly the reference's hadamard_transform package performs.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) fwht_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                   int64_t n_vectors, int n, int64_t inner,
+                                                   int64_t outer_stride, float norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = warp; v < n_vectors; v += n_warps) {
+    const int64_t base = (v / inner) * outer_stride + (v % inner);
+    float r[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int k = lane + 32 * i;
+      r[i] = (k < n) ? src[base + (int64_t)k * inner] : 0.f;
+    }
+#pragma unroll
+    for (int h = 1; h < 32; h <<= 1) {
+      if (h < n) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float o = __shfl_xor_sync(0xffffffffu, r[i], h);
+          r[i] = (lane & h) ? (o - r[i]) : (r[i] + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int hr = 1; hr < R; hr <<= 1) {
+      if (32 * hr < n) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          if ((i & hr) == 0) {
+            const float a = r[i], b = r[i | hr];
+            r[i] = a + b;
+            r[i | hr] = a - b;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int k = lane + 32 * i;
+      if (k < n) dst[base + (int64_t)k * inner] = __fdiv_rn(r[i], norm);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ref <-> packed weight layouts
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int packed_channel(int co, int rh, int rw, int cg) {
+  const int rr = rh * rw;
+  const int c = co / rr, rem = co - c * rr;
+  return rem * cg + c;
+}
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(nq_conv_desc d, const float* __restrict__ w_ref,
+                                                          int cin_src, const float* __restrict__ bias_ref,
+                                                          float* __restrict__ wk, float* __restrict__ wt,
+                                                          float* __restrict__ bias_packed) {
+  const int kk = d.ksize * d.ksize;
+  const int nout_p = d.rh * d.rw * d.cg;
+  const int64_t total = (int64_t)d.cout * d.cin * kk;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % kk);
+    const int ci = (int)((e / kk) % d.cin);
+    const int co = (int)(e / ((int64_t)kk * d.cin));
+    const float v = w_ref[((int64_t)co * cin_src + ci) * kk + tap];
+    const int np = packed_channel(co, d.rh, d.rw, d.cg);
+    if (wk) wk[((int64_t)tap * d.cin_p + ci) * nout_p + np] = v;
+    if (wt) wt[((int64_t)(kk - 1 - tap) * nout_p + np) * d.cin_p + ci] = v;
+  }
+  if (bias_ref && bias_packed) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < d.cout;
+         e += (int64_t)gridDim.x * blockDim.x)
+      bias_packed[packed_channel((int)e, d.rh, d.rw, d.cg)] = bias_ref[e];
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(nq_conv_desc d, const float* __restrict__ dwk,
+                                                           int cin_dst, float* __restrict__ dw_ref,
+                                                           float* __restrict__ db_ref) {
+  const int kk = d.ksize * d.ksize;
+  const int nout_p = d.rh * d.rw * d.cg;
+  const int64_t kdim = (int64_t)kk * d.cin_p;
+  if (dw_ref) {
+    const int64_t total = (int64_t)d.cout * cin_dst * kk;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+      const int tap = (int)(e % kk);
+      const int ci = (int)((e / kk) % cin_dst);
+      const int co = (int)(e / ((int64_t)kk * cin_dst));
+      float v = 0.f;
+      if (ci < d.cin) v = dwk[((int64_t)tap * d.cin_p + ci) * nout_p + packed_channel(co, d.rh, d.rw, d.cg)];
+      dw_ref[e] = v;
+    }
+  }
+  if (db_ref) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < d.cout;
+         e += (int64_t)gridDim.x * blockDim.x)
+      db_ref[e] = dwk[kdim * nout_p + packed_channel((int)e, d.rh, d.rw, d.cg)];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> NHWC edges (embedding in, debug/feature taps out).  Small tensors; one thread per
+// destination element, destination-coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           int n, int c, int h, int w, int c_p) {
+  const int64_t total = (int64_t)n * h * w * c_p;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % c_p);
+    const int64_t pix = e / c_p;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+    dst[e] = ch < c ? src[(((int64_t)b * c + ch) * h + y) * w + x] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           int n, int c, int h, int w, int c_p) {
+  const int64_t total = (int64_t)n * c * h * w;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(e % w), y = (int)((e / w) % h);
+    const int ch = (int)((e / ((int64_t)w * h)) % c), b = (int)(e / ((int64_t)w * h * c));
+    dst[e] = src[(((int64_t)b * h + y) * w + x) * c_p + ch];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float abs_pow(float a, float p) { return p == 2.0f ? a * a : powf(a, p); }
+
+__global__ void __launch_bounds__(256) lp_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                      int64_t numel, float p, float grad_scale,
+                                                      float* __restrict__ loss_sum, float* __restrict__ grad) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float dlt = pred[e] - tgt[e];
+    const float a = fabsf(dlt);
+    acc += abs_pow(a, p);
+    if (grad) {
+      const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+      grad[e] = grad_scale * (p == 2.0f ? 2.0f * dlt : p * powf(a, p - 1.0f) * sgn);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, acc);
+}
+
+struct DotTable {
+  const float* a[16];
+  const float* b[16];
+  int64_t n[16];
+};
+
+// one CTA column per tensor (blockIdx.y), fixed-order two-level reduction -> deterministic
+__global__ void __launch_bounds__(256) multi_dot_partial_kernel(DotTable t, int mode, float* __restrict__ partial) {
+  __shared__ float red[32];
+  const float* a = t.a[blockIdx.y];
+  const float* b = t.b[blockIdx.y];
+  const int64_t n = t.n[blockIdx.y];
+  float acc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const float x = a[e], y = b[e];
+    acc += mode == 0 ? x * y : (x * x) * (y * y);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(32) multi_dot_final_kernel(const float* __restrict__ partial, int per_tensor,
+                                                             float* __restrict__ out) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < per_tensor; i += 32) acc += partial[blockIdx.x * per_tensor + i];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+// one CTA-group per frame; blockIdx.y = frame.  Two-pass (partials then log) kept in one kernel via
+// atomics on a per-frame accumulator would be non-deterministic; frames are small in number, so use
+// grid.x CTAs per frame + a last-block finaliser.
+__global__ void __launch_bounds__(256) psnr_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           int64_t frame_numel, float* __restrict__ partial) {
+  __shared__ float red[32];
+  const float* pa = a + (int64_t)blockIdx.y * frame_numel;
+  const float* pb = b + (int64_t)blockIdx.y * frame_numel;
+  float acc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < frame_numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float d = pa[e] - pb[e];
+    acc += d * d;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(32) psnr_final_kernel(const float* __restrict__ partial, int per_frame,
+                                                        float inv_numel, float* __restrict__ psnr) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < per_frame; i += 32) acc += partial[blockIdx.x * per_frame + i];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) psnr[blockIdx.x] = -10.0f * log10f(acc * inv_numel + 1e-9f);
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+extern "C" const char* nq_status_string(int status) {
+  switch (status) {
+    case NQ_OK: return "ok";
+    case NQ_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size, or bit-width outside 2..8)";
+    case NQ_ERR_BAD_SHAPE: return "shape violates the layout contract (padding / divisibility)";
+    case NQ_ERR_UNSUPPORTED: return "unsupported configuration";
+    case NQ_ERR_WORKSPACE: return "workspace too small";
+    case NQ_ERR_CUDA: return "CUDA error (see nq_last_cuda_error)";
+    default: return "unknown status";
+  }
+}
+extern "C" int nq_last_cuda_error(void) { return g_last_cuda_error; }
+extern "C" int nq_abi_version(void) { return 1; }
+extern "C" int nq_sm_count(void) { return sm_count(); }
+
+extern "C" int nq_fwht(const float* src, float* dst, int64_t n_vectors, int n, int64_t inner, int64_t outer_stride,
+                       void* stream) {
+  if (!src || !dst || n_vectors <= 0 || inner <= 0) return NQ_ERR_BAD_ARG;
+  if (n < 1 || n > 256 || (n & (n - 1)) != 0) return NQ_ERR_UNSUPPORTED;
+  const float norm = (float)sqrt((double)n);
+  int64_t blocks = (n_vectors + 7) / 8;  // 8 warps per CTA
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = as_stream(stream);
+  if (n <= 32) fwht_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(src, dst, n_vectors, n, inner, outer_stride, norm);
+  else if (n == 64) fwht_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(src, dst, n_vectors, n, inner, outer_stride, norm);
+  else if (n == 128) fwht_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(src, dst, n_vectors, n, inner, outer_stride, norm);
+  else fwht_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(src, dst, n_vectors, n, inner, outer_stride, norm);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+static int check_desc(const nq_conv_desc* d) {
+  if (!d) return NQ_ERR_BAD_ARG;
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->cin <= 0 || d->cout <= 0 || d->rh <= 0 || d->rw <= 0) return NQ_ERR_BAD_ARG;
+  if (d->ksize < 1 || (d->ksize & 1) == 0) return NQ_ERR_BAD_SHAPE;
+  if (d->cin_p < d->cin || (d->cin_p & 3) || d->cg < d->c_grp || (d->cg & 3)) return NQ_ERR_BAD_SHAPE;
+  if (d->cout != d->c_grp * d->rh * d->rw) return NQ_ERR_BAD_SHAPE;
+  if (d->act != 0 && d->act != 1) return NQ_ERR_BAD_ARG;
+  return NQ_OK;
+}
+namespace nq { int check_conv_desc(const nq_conv_desc* d) { return check_desc(d); } }
+
+extern "C" int nq_pack_weight(const nq_conv_desc* d, const float* w_ref, int cin_src, const float* bias_ref,
+                              float* wk, float* wt, float* bias_packed, void* stream) {
+  int st = check_desc(d);
+  if (st) return st;
+  if (!w_ref || cin_src < d->cin) return NQ_ERR_BAD_ARG;
+  const int64_t total = (int64_t)d->cout * d->cin * d->ksize * d->ksize;
+  pack_weight_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(*d, w_ref, cin_src, bias_ref, wk, wt, bias_packed);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_unpack_wgrad(const nq_conv_desc* d, const float* dwk, int cin_dst, float* dw_ref, float* db_ref,
+                               void* stream) {
+  int st = check_desc(d);
+  if (st) return st;
+  if (!dwk || cin_dst < d->cin) return NQ_ERR_BAD_ARG;
+  const int64_t total = (int64_t)d->cout * cin_dst * d->ksize * d->ksize;
+  unpack_wgrad_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(*d, dwk, cin_dst, dw_ref, db_ref);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream) {
+  if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_p < c) return NQ_ERR_BAD_ARG;
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * h * w * c_p), 256, 0, as_stream(stream)>>>(src, dst, n, c, h, w, c_p);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+extern "C" int nq_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream) {
+  if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_p < c) return NQ_ERR_BAD_ARG;
+  nhwc_to_nchw_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, as_stream(stream)>>>(src, dst, n, c, h, w, c_p);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_lp_loss(const float* pred, const float* tgt, int64_t numel, float p, float grad_scale,
+                          float* loss_sum, float* grad, void* stream) {
+  if (!pred || !tgt || !loss_sum || numel <= 0 || !(p > 0.f)) return NQ_ERR_BAD_ARG;
+  lp_loss_kernel<<<grid_for(numel), 256, 0, as_stream(stream)>>>(pred, tgt, numel, p, grad_scale, loss_sum, grad);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+// workspace for the two-level reductions lives in a small per-call device allocation owned by the
+// caller in the general ABI; here the partial buffers are tiny (<= 16 * 148 floats), so they are
+// carved out of the output-adjacent scratch the caller provides via `out` only for the final values.
+// To stay stateless and allocation-free the partials use cudaMallocAsync on the given stream.
+extern "C" int nq_multi_dot(const float* const* a_ptrs, const float* const* b_ptrs, const int64_t* sizes,
+                            int n_tensors, int mode, float* out, void* stream) {
+  if (!a_ptrs || !b_ptrs || !sizes || !out || n_tensors <= 0 || n_tensors > 16) return NQ_ERR_BAD_ARG;
+  if (mode != 0 && mode != 1) return NQ_ERR_BAD_ARG;
+  DotTable t;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!a_ptrs[i] || !b_ptrs[i] || sizes[i] <= 0) return NQ_ERR_BAD_ARG;
+    t.a[i] = a_ptrs[i]; t.b[i] = b_ptrs[i]; t.n[i] = sizes[i];
+  }
+  cudaStream_t s = as_stream(stream);
+  const int per = sm_count();
+  float* partial = nullptr;
+  NQ_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(float) * per * n_tensors, s));
+  multi_dot_partial_kernel<<<dim3(per, n_tensors), 256, 0, s>>>(t, mode, partial);
+  multi_dot_final_kernel<<<n_tensors, 32, 0, s>>>(partial, per, out);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(partial, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return NQ_OK;
+}
+
+extern "C" int nq_psnr(const float* a, const float* b, int n_frames, int64_t frame_numel, float* psnr, void* stream) {
+  if (!a || !b || !psnr || n_frames <= 0 || frame_numel <= 0) return NQ_ERR_BAD_ARG;
+  cudaStream_t s = as_stream(stream);
+  int per = (int)((frame_numel + 256 * 16 - 1) / (256 * 16));
+  if (per > sm_count()) per = sm_count();
+  if (per < 1) per = 1;
+  float* partial = nullptr;
+  NQ_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(float) * per * n_frames, s));
+  psnr_partial_kernel<<<dim3(per, n_frames), 256, 0, s>>>(a, b, frame_numel, partial);
+  psnr_final_kernel<<<n_frames, 32, 0, s>>>(partial, per, 1.0f / (float)frame_numel, psnr);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(partial, s);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return NQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standalone activation-backward + un-shuffle (the tail of a stage whose consumer is not one of our
+// dgrad kernels, e.g. a QuantNeRVBlock called on its own): dz[n,h,w,(i*rw+j)*cg+c] =
+// dy[n,h*rh+i,w*rw+j,c] * act'(z[same]).
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                                int n, int h, int w, int rh, int rw, int cg, int act,
+                                                                float* __restrict__ dz) {
+  const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  const int W2 = w * rw, H2 = h * rh;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cg);
+    const int64_t pix = e / cg;
+    const int x = (int)(pix % W2), y = (int)((pix / W2) % H2), b = (int)(pix / ((int64_t)W2 * H2));
+    float v = dy[e];
+    if (act == 1) v *= gelu_grad_f(z[e]);
+    const int qh = y / rh, si = y - qh * rh, qw = x / rw, sj = x - qw * rw;
+    dz[(((int64_t)b * h + qh) * w + qw) * ((int64_t)rh * rw * cg) + (int64_t)(si * rw + sj) * cg + c] = v;
+  }
+}
+}  // namespace nq
+
+extern "C" int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int h, int w, int rh, int rw, int cg, int act,
+                                    float* dz, void* stream) {
+  if (!dy || !dz || n <= 0 || h <= 0 || w <= 0 || rh <= 0 || rw <= 0 || cg <= 0) return NQ_ERR_BAD_ARG;
+  if (act != 0 && act != 1) return NQ_ERR_BAD_ARG;
+  if (act == 1 && !z) return NQ_ERR_BAD_ARG;
+  const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  act_bwd_unshuffle_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(dy, z, n, h, w, rh, rw, cg, act, dz);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}

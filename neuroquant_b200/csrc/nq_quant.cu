@@ -1,0 +1,271 @@
+// Quantiser kernels: UAQ 'max' scale init, fused fake-quant forward/backward (UAQ-STE, AdaRound
+// soft/hard, rounding regulariser), AdaRound alpha init, Adam.  HBM-bound elementwise work:
+// coalesced 1-D grids, one pass over each operand, reductions by warp shuffle.
+// Reference: quantization/quantizer.py, quantization/calib_model.py:39-47.
+#include "nq_common.cuh"
+
+namespace nq {
+
+// ---------------------------------------------------------------------------------------------
+// quantizer.py:153-168 per row.  delta is formed in double from the fp32 extrema exactly as the
+// reference's python floats do; zero_point = round(reciprocal(delta) * -x_min) because
+// `-x_min / delta` with a python scalar on the left dispatches to Tensor.__rtruediv__.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) uaq_init_max_kernel(const float* __restrict__ x, int64_t row_len,
+                                                           int n_levels, float* __restrict__ delta,
+                                                           float* __restrict__ zp) {
+  __shared__ float smin[8], smax[8];
+  const float* row = x + (int64_t)blockIdx.x * row_len;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = threadIdx.x; i < row_len; i += blockDim.x) {
+    const float v = row[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+    const double x_min = fmin((double)mn, 0.0), x_max = fmax((double)mx, 0.0);
+    float d = (float)((x_max - x_min) / (double)(n_levels - 1));
+    d = fmaxf(d, 1e-8f);
+    const float rcp = __fdiv_rn(1.0f, d);
+    delta[blockIdx.x] = d;
+    zp[blockIdx.x] = rintf(__fmul_rn(rcp, (float)(-x_min)));
+  }
+}
+
+__device__ __forceinline__ float soft_target_raw(float alpha, float& sig) {
+  sig = sigmoid_f(alpha);
+  return __fadd_rn(__fmul_rn(sig, kZeta - kGamma), kGamma);  // two roundings, as torch (no FMA)
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) fakequant_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ delta,
+    const float* __restrict__ zp, int64_t numel, int row_len, int d_stride, float qmax,
+    float* __restrict__ codes, float* __restrict__ deq, float* __restrict__ reg_sum, float reg_b) {
+  __shared__ float red[32];
+  float reg = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = (e / row_len) * d_stride;
+    const float d = delta[r], z = zp[r];
+    const float q = __fdiv_rn(x[e], d);  // true fp32 divide
+    float x_int;
+    if (MODE == NQ_ROUND_NEAREST) {
+      x_int = rintf(q);  // half-to-even == torch.round
+    } else if (MODE == NQ_ROUND_SOFT) {
+      float sig;
+      const float h = fminf(fmaxf(soft_target_raw(alpha[e], sig), 0.f), 1.f);
+      x_int = __fadd_rn(floorf(q), h);
+      if (reg_sum != nullptr) {
+        const float u = fabsf(h - 0.5f) * 2.0f;
+        reg += 1.0f - powf(u, reg_b);
+      }
+    } else {
+      x_int = __fadd_rn(floorf(q), alpha[e] >= 0.f ? 1.f : 0.f);
+    }
+    const float c = fminf(fmaxf(__fadd_rn(x_int, z), 0.f), qmax);
+    if (codes != nullptr) codes[e] = c;
+    if (deq != nullptr) deq[e] = __fmul_rn(__fsub_rn(c, z), d);
+  }
+  if (MODE == NQ_ROUND_SOFT && reg_sum != nullptr) {
+    reg = block_sum(reg, red);
+    if (threadIdx.x == 0) atomicAdd(reg_sum, reg);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, AdaRound soft: elementwise d_alpha
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fakequant_bwd_soft_kernel(
+    const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ alpha,
+    const float* __restrict__ delta, const float* __restrict__ zp, int64_t numel, int row_len,
+    int d_stride, float qmax, float grad_scale, float reg_w, float reg_b, float* __restrict__ d_alpha) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = (e / row_len) * d_stride;
+    const float d = delta[r], z = zp[r];
+    float sig;
+    const float hraw = soft_target_raw(alpha[e], sig);
+    const bool pass_h = (hraw >= 0.f) && (hraw <= 1.f);  // clamp backward is inclusive
+    const float h = fminf(fmaxf(hraw, 0.f), 1.f);
+    const float v = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(x[e], d)), h), z);
+    const bool in_range = (v >= 0.f) && (v <= qmax);
+    float dh = 0.f;
+    if (in_range) dh = g[e] * grad_scale * d;
+    if (reg_w != 0.f) {
+      const float t = h - 0.5f;
+      const float u = fabsf(t) * 2.0f;
+      const float sgn = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f);
+      // d/dh (1 - u^b) = -b u^(b-1) * 2 sign(h - .5)
+      dh += reg_w * (-reg_b * powf(u, reg_b - 1.0f) * 2.0f * sgn);
+    }
+    d_alpha[e] = pass_h ? dh * (kZeta - kGamma) * sig * (1.0f - sig) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, UAQ-STE: per-row d_delta (one CTA per row; rows share a scale only when d_stride == 1,
+// the per-tensor case uses a single CTA over the whole tensor)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fakequant_bwd_delta_kernel(
+    const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ delta,
+    const float* __restrict__ zp, int64_t row_len, float qmax, float grad_scale,
+    float* __restrict__ d_delta) {
+  __shared__ float red[32];
+  const int64_t base = (int64_t)blockIdx.x * row_len;
+  const float d = delta[blockIdx.x], z = zp[blockIdx.x];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < row_len; i += blockDim.x) {
+    const float xv = x[base + i];
+    const float q = __fdiv_rn(xv, d);
+    const float v = __fadd_rn(rintf(q), z);
+    const bool in_range = (v >= 0.f) && (v <= qmax);
+    const float c = fminf(fmaxf(v, 0.f), qmax);
+    acc += g[base + i] * ((c - z) - (in_range ? q : 0.f));
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) d_delta[blockIdx.x] = acc * grad_scale;
+}
+
+__global__ void __launch_bounds__(256) adaround_init_alpha_kernel(
+    const float* __restrict__ x, const float* __restrict__ delta, int64_t numel, int row_len,
+    int d_stride, float* __restrict__ alpha) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float d = delta[(e / row_len) * d_stride];
+    const float q = __fdiv_rn(x[e], d);
+    const float rest = __fsub_rn(q, floorf(q));
+    // -log((zeta - gamma) / (rest - gamma) - 1)
+    const float t = __fsub_rn(__fdiv_rn(kZeta - kGamma, __fsub_rn(rest, kGamma)), 1.0f);
+    alpha[e] = -logf(t);
+  }
+}
+
+// torch.optim.Adam, single-tensor path (torch/optim/adam.py _single_tensor_adam)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                   float one_minus_b1, float b2, float one_minus_b2,
+                                                   float step_size, float bc2_sqrt, float eps) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float gv = g[e];
+    const float mv = m[e] + one_minus_b1 * (gv - m[e]);              // lerp_
+    const float vv = __fadd_rn(__fmul_rn(v[e], b2), __fmul_rn(__fmul_rn(gv, gv), one_minus_b2));
+    m[e] = mv;
+    v[e] = vv;
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), bc2_sqrt), eps);
+    p[e] = p[e] - step_size * __fdiv_rn(mv, denom);
+  }
+}
+
+static inline int grid_for(int64_t numel, int block = 256) {
+  int64_t b = (numel + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 16;  // multiple of the SM count, grid-stride beyond
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+extern "C" int nq_uaq_init_max(const float* x, int64_t rows, int64_t row_len, int n_bits, float* delta,
+                               float* zero_point, void* stream) {
+  if (!x || !delta || !zero_point || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
+  if (n_bits < 2 || n_bits > 8) return NQ_ERR_BAD_ARG;
+  uaq_init_max_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, row_len, 1 << n_bits, delta, zero_point);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_fakequant_fwd(const float* x, const float* alpha, const float* delta, const float* zero_point,
+                                int64_t rows, int64_t row_len, int d_stride, int n_bits, int mode, float* codes,
+                                float* deq, float* reg_sum, float reg_b, void* stream) {
+  if (!x || !delta || !zero_point || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
+  if (n_bits < 2 || n_bits > 8 || (d_stride != 0 && d_stride != 1)) return NQ_ERR_BAD_ARG;
+  if (mode != NQ_ROUND_NEAREST && !alpha) return NQ_ERR_BAD_ARG;
+  if (row_len > 0x7fffffffLL) return NQ_ERR_BAD_SHAPE;
+  const int64_t numel = rows * row_len;
+  const float qmax = (float)((1 << n_bits) - 1);
+  const int grid = grid_for(numel);
+  cudaStream_t s = as_stream(stream);
+  switch (mode) {
+    case NQ_ROUND_NEAREST:
+      fakequant_fwd_kernel<NQ_ROUND_NEAREST><<<grid, 256, 0, s>>>(x, alpha, delta, zero_point, numel, (int)row_len,
+                                                                  d_stride, qmax, codes, deq, nullptr, 0.f);
+      break;
+    case NQ_ROUND_SOFT:
+      fakequant_fwd_kernel<NQ_ROUND_SOFT><<<grid, 256, 0, s>>>(x, alpha, delta, zero_point, numel, (int)row_len,
+                                                               d_stride, qmax, codes, deq, reg_sum, reg_b);
+      break;
+    case NQ_ROUND_HARD:
+      fakequant_fwd_kernel<NQ_ROUND_HARD><<<grid, 256, 0, s>>>(x, alpha, delta, zero_point, numel, (int)row_len,
+                                                               d_stride, qmax, codes, deq, nullptr, 0.f);
+      break;
+    default:
+      return NQ_ERR_BAD_ARG;
+  }
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_fakequant_bwd(const float* g, const float* x, const float* alpha, const float* delta,
+                                const float* zero_point, int64_t rows, int64_t row_len, int d_stride, int n_bits,
+                                int mode, float grad_scale, float reg_w, float reg_b, float* d_alpha,
+                                float* d_delta, void* stream) {
+  if (!g || !x || !delta || !zero_point || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
+  if (n_bits < 2 || n_bits > 8 || (d_stride != 0 && d_stride != 1)) return NQ_ERR_BAD_ARG;
+  if (row_len > 0x7fffffffLL) return NQ_ERR_BAD_SHAPE;
+  const float qmax = (float)((1 << n_bits) - 1);
+  cudaStream_t s = as_stream(stream);
+  if (mode == NQ_ROUND_SOFT) {
+    if (!alpha || !d_alpha) return NQ_ERR_BAD_ARG;
+    const int64_t numel = rows * row_len;
+    fakequant_bwd_soft_kernel<<<grid_for(numel), 256, 0, s>>>(g, x, alpha, delta, zero_point, numel, (int)row_len,
+                                                             d_stride, qmax, grad_scale, reg_w, reg_b, d_alpha);
+  } else if (mode == NQ_ROUND_NEAREST) {
+    if (!d_delta) return NQ_ERR_BAD_ARG;
+    if (d_stride == 1)
+      fakequant_bwd_delta_kernel<<<(unsigned)rows, 256, 0, s>>>(g, x, delta, zero_point, row_len, qmax, grad_scale, d_delta);
+    else  // one shared scale: a single row spanning the tensor
+      fakequant_bwd_delta_kernel<<<1, 256, 0, s>>>(g, x, delta, zero_point, rows * row_len, qmax, grad_scale, d_delta);
+  } else {
+    return NQ_ERR_BAD_ARG;  // hard rounding has no learnable
+  }
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_adaround_init_alpha(const float* x, const float* delta, int64_t rows, int64_t row_len,
+                                      int d_stride, float* alpha, void* stream) {
+  if (!x || !delta || !alpha || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
+  if (d_stride != 0 && d_stride != 1) return NQ_ERR_BAD_ARG;
+  if (row_len > 0x7fffffffLL) return NQ_ERR_BAD_SHAPE;
+  const int64_t numel = rows * row_len;
+  adaround_init_alpha_kernel<<<grid_for(numel), 256, 0, as_stream(stream)>>>(x, delta, numel, (int)row_len, d_stride, alpha);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                            double lr, double beta1, double beta2, double eps, int step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return NQ_ERR_BAD_ARG;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1),
+                                                          (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt,
+                                                          (float)eps);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
