@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the calibration hot path (BASELINE.json metric: AdaRound calibration iterations/s and
+quantised-decode frames/s, HNeRV-3M 1280x640).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+A step is ONE AdaRound (phase-2) calibration iteration -- forward, loss, backward, rounding
+regulariser, Adam -- on a batch of 2 synthetic 1280x640 frames per GPU (frame-sharded data parallel:
+global batch 2*N, one NCCL all-reduce of the flat dW/db buffer per step).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "adaround_calib_iters_per_s"
+UNIT = "it/s (batch-2 iterations; frame-sharded DP processes N of them per step)"
+DEFAULT_BITS = [6, 5, 4, 5, 5, 6, 6]
+HYPER = dict(weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003, iters=21000)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hnerv-bunny-3m")
+    ap.add_argument("--batch", type=int, default=2, help="frames per GPU per iteration")
+    ap.add_argument("--precision", type=int, nargs="+", default=DEFAULT_BITS)
+    ap.add_argument("--hadamard", action="store_true")
+    ap.add_argument("--frames", type=int, default=8, help="synthetic frames resident per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-steps", type=int, default=10)
+    return ap.parse_args()
+
+
+def config_of(args, world):
+    return {"workload": f"{args.workload} 1280x640 AdaRound phase-2 iteration, W-mixed {' '.join(map(str, args.precision))}"
+                        if "bunny" in args.workload else args.workload,
+            "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world, "hadamard": bool(args.hadamard),
+            "parallelism": f"dp{world} (frame-sharded, NCCL all-reduce of dW)" if world > 1 else "single GPU",
+            "l2": "no explicit flush: each step streams >2 GB of activations, far above the 126 MB L2",
+            **{k: v for k, v in HYPER.items()}}
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of calib_model.py on the host cores
+# ------------------------------------------------------------------------------------------------------
+def oracle_iteration_fn(args):
+    """Returns (step_fn, decode_fn, cores): step_fn() runs one AdaRound iteration of the reference
+    algorithm (oracle/nq_oracle.py, pinned to the reference by tests/golden) on CPU."""
+    from oracle import nq_oracle as O
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape, random_decoder
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    arch, cfg = WORKLOADS[args.workload]
+    geoms, params = random_decoder(cfg, arch, 903)
+    stages = [O.Stage(w, b, g.rh, g.rw, g.act) for g, (w, b) in zip(geoms, params)]
+    qd = O.QuantDecoder(stages, args.precision, args.hadamard)
+    qd.start_adaround()
+    alphas = []
+    for q in qd.q:
+        q.alpha_w.requires_grad_(True)
+        q.alpha_b.requires_grad_(True)
+        alphas += [q.alpha_w, q.alpha_b]
+    opt = torch.optim.Adam(alphas, lr=HYPER["lr"])
+    gen = torch.Generator().manual_seed(903)
+    c, h, w = embed_shape(cfg, arch)
+    embed = torch.randn(args.batch, c, h, w, generator=gen)
+    frames = torch.rand(args.batch, 3, cfg["crop_h"], cfg["crop_w"], generator=gen)
+
+    def step():
+        out = qd.forward(embed)
+        opt.zero_grad()
+        rec = O.lp_loss(out, frames, p=HYPER["p"])
+        rnd = sum(HYPER["weight"] * O.round_reg(q.alpha_w, 10.0) for q in qd.q)
+        (rec + rnd).backward()
+        opt.step()
+        return float(rec)
+
+    def decode():
+        with torch.no_grad():
+            return qd.forward(embed)
+
+    return step, decode, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, decode, cores = oracle_iteration_fn(args)
+    for _ in range(min(args.warmup, 1)):  # a CPU iteration is ~3 s; one warm-up is enough to page in
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    sample = f"{args.steps} AdaRound iterations, batch {args.batch}, {args.workload}, oracle port of calib_model.py on {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import neuroquant_b200 as nq
+    from neuroquant_b200.engine import AdamState
+    from neuroquant_b200.workloads import WORKLOADS, conv_flops, embed_shape, random_decoder
+
+    arch, cfg = WORKLOADS[args.workload]
+    geoms, params = random_decoder(cfg, arch, 903)
+    stages = [nq.QuantStage(g, w.cuda(), b.cuda(), nb, args.hadamard) for g, (w, b), nb in zip(geoms, params, args.precision)]
+    eng = nq.DecoderEngine(stages)
+    eng.init_scales()
+    eng.start_adaround()
+    c, h0, w0 = embed_shape(cfg, arch)
+    H, W = cfg["crop_h"], cfg["crop_w"]
+    gen = torch.Generator().manual_seed(903 + rank)
+    F = max(args.frames, args.batch)
+    embeds_h = torch.randn(F, c, h0, w0, generator=gen).pin_memory()
+    frames_h = torch.rand(F, 3, H, W, generator=gen).pin_memory()
+    embeds_d, frames_d = embeds_h.cuda(), frames_h.cuda()
+    params_a = [t_ for s in eng.stages for t_ in (s.alpha_w, s.alpha_b)]
+    opt = AdamState(params_a, lr=HYPER["lr"])
+    B = args.batch
+    mean_pixels = float(B * world * H * W)
+    reg_w, reg_b = HYPER["weight"], 10.0  # mid-schedule temperature: regulariser on, as in 80% of the run
+    stage_ev = []
+
+    def step(i, embed, frames, profile=False):
+        eng.forward(embed, train=True, target=frames, p_norm=HYPER["p"], mean_pixels=mean_pixels, want_img=False)
+        flat = eng.backward()
+        if world > 1:
+            dist.all_reduce(flat)
+        grads = eng.param_grads(1.0, reg_w, reg_b)
+        opt.step([g for pair in grads for g in pair])
+        eng.launches += len(opt.params)
+        eng.invalidate()
+
+    def resident(i):
+        o = (i * B) % (F - B + 1)
+        return embeds_d[o:o + B], frames_d[o:o + B]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms) , t0, t1
+
+    # ---- device-resident throughput
+    for i in range(args.warmup):
+        step(i, *resident(i))
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.launches
+    ms, t0, t1 = timed(lambda i: step(i, *resident(i)), args.steps)
+    launches = eng.launches - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    value = args.steps * world / (ms * 1e-3)
+
+    # ---- per-kernel timing of the convolution launches (CUDA events on the launch stream)
+    kern = eng.kernel_profile(lambda: step(0, *resident(0)), reps=3)
+
+    # ---- end to end: host buffers in, loss out, every step
+    h2d = B * (c * h0 * w0 + 3 * H * W) * 4
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step(i):
+        o = (i * B) % (F - B + 1)
+        embed = embeds_h[o:o + B].cuda(non_blocking=True)
+        frames = frames_h[o:o + B].cuda(non_blocking=True)
+        step(i, embed, frames)
+        loss_host.copy_(eng.last_loss(), non_blocking=False)
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    ms_e, _, _ = timed(e2e_step, args.steps)
+    e2e_val = args.steps * world / (ms_e * 1e-3)
+
+    # ---- quantised decode (hard rounding, weights static -> packed once, Q9)
+    eng.soft_w = False
+    eng.invalidate()
+    eng.forward(embeds_d[:B])
+    for i in range(3):
+        eng.forward(embeds_d[:B], reuse_weights=True)
+    ms_d, _, _ = timed(lambda i: eng.forward(resident(i)[0], reuse_weights=True), args.decode_steps)
+    decode_fps = args.decode_steps * B * world / (ms_d * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops_iter = 3.0 * conv_flops(geoms, h0, w0, B)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    top = kern[0]
+    conv_ms = sum(k["ms"] for k in kern)
+    roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": top["tflops"] / peak_tf, "traffic": None, "ms_per_launch": top["ms"], "flops_per_launch": top["flops"],
+            "share_of_step": top["ms"] / (ms / args.steps),
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+            "conv_kernels_ms": {k["kernel"]: round(k["ms"], 4) for k in kern}, "conv_share_of_step": conv_ms / (ms / args.steps)}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": getattr(eng, "dtype_name", "f32"), "data": "synthetic", "config": config_of(args, world),
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e / args.steps},
+        "decode": {"frames_per_s": decode_fps, "batch": B, "ms_per_batch": ms_d / args.decode_steps,
+                   "gflop_per_frame": conv_flops(geoms, h0, w0, 1) / 1e9},
+        "tflops_effective": flops_iter / (ms / args.steps * 1e-3) / 1e12,
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cstep, cdecode, cores = oracle_iteration_fn(args)
+        cstep()
+        n_s = 3
+        t0 = time.perf_counter()
+        for _ in range(n_s):
+            cstep()
+        dt = time.perf_counter() - t0
+        td = time.perf_counter()
+        cdecode()
+        td = time.perf_counter() - td
+        out["cpu_baseline"] = {"value": n_s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{n_s} AdaRound iterations (batch {B}) after 1 warm-up, same workload; "
+                                         f"decode {B / td:.2f} frames/s on one batch-{B} decode"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,129 @@
+"""Network-wise calibration loop on the decoder engine (reference: quantization/calib_model.py:92-240).
+
+Two Adam phases over a fixed kernel sequence per iteration:
+  phase 1  step sizes delta (UAQ, straight-through rounding), lr 1e-3        calib_model.py:120-165
+  phase 2  rounding variables alpha (AdaRound soft targets), lr = `lr`,
+           + b-annealed rounding regulariser after the warm-up               calib_model.py:169-226
+then the weight quantisers switch to hard rounding (bias quantisers stay soft, :231-240).
+
+Multi-GPU: frames of each global mini-batch are sharded over the ranks of `group`; every rank runs
+the same iteration on its shard and the flat dW/db buffer is summed with ONE NCCL all-reduce before
+the (replica-identical) quantiser Jacobian and Adam.  The loss is normalised by the GLOBAL pixel
+count, so the sum of the per-rank gradients is the gradient of the reference's mean.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Callable, Iterable, List, Optional, Sequence
+
+import torch
+
+from .engine import AdamState, DecoderEngine
+
+
+class LinearTempDecay:
+    """data_utils.py:24-41."""
+
+    def __init__(self, t_max: int, rel_start_decay: float = 0.2, start_b: float = 10, end_b: float = 2):
+        self.t_max = t_max
+        self.start_decay = rel_start_decay * t_max
+        self.start_b = start_b
+        self.end_b = end_b
+
+    def __call__(self, t):
+        if t < self.start_decay:
+            return self.start_b
+        rel_t = (t - self.start_decay) / (self.t_max - self.start_decay)
+        return self.end_b + (self.start_b - self.end_b) * max(0.0, (1 - rel_t))
+
+
+class CalibrationLoop:
+    """One calibration run.  `fetch(idx) -> (embed, frames)` returns this rank's shard of the
+    mini-batch `idx` as device tensors (NCHW)."""
+
+    def __init__(self, engine: DecoderEngine, fetch: Callable, n_batches: int, iters: int, weight: float = 0.01,
+                 b_range=(20, 2), warmup: float = 0.0, p: float = 2.0, lr: float = 0.0015,
+                 group=None, global_batch: Optional[int] = None, log: Optional[list] = None):
+        self.eng, self.fetch, self.n_batches, self.iters = engine, fetch, n_batches, iters
+        self.weight, self.b_range, self.warmup, self.p, self.lr = weight, b_range, warmup, p, lr
+        self.group = group
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+        self.global_batch = global_batch
+        self.log = log
+        self.ep1 = int(0.05 * iters / n_batches)  # calib_model.py:144
+        self.ep2 = int(iters / n_batches) - self.ep1  # calib_model.py:205
+        self.count = 0
+
+    # -- one iteration: forward + loss + backward + (all-reduce) + Jacobian + Adam
+    def iteration(self, idx, opt: AdamState, reg_w: float, reg_b: float, want_log: bool):
+        eng = self.eng
+        embed, frames = self.fetch(idx)
+        n, _, H, W = frames.shape
+        gb = self.global_batch if self.global_batch is not None else n * self.world
+        eng.forward(embed, train=True, target=frames, p_norm=self.p, mean_pixels=float(gb * H * W),
+                    reg_b=reg_b if (reg_w != 0.0 and want_log) else None, want_img=False)
+        flat = eng.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(flat, group=self.group)
+        grads = eng.param_grads(1.0, reg_w, reg_b)
+        opt.step([g for pair in grads for g in pair])
+        eng.launches += len(opt.params)
+        eng.invalidate()
+
+    def run_phase1(self, batches: Callable[[], Iterable]):
+        eng = self.eng
+        eng.mode = "uaq"
+        params = []
+        for s in eng.stages:
+            params += [s.delta_w, s.delta_b]
+        opt = AdamState(params, lr=0.001)  # calib_model.py:134
+        count = 0
+        for _ in range(self.ep1):
+            for idx in batches():
+                count += 1
+                self.iteration(idx, opt, 0.0, 0.0, False)
+                if self.log is not None:
+                    self.log.append(("delta", count, float(self._global_loss()), 0.0, 0.0))
+        return count
+
+    def run_phase2(self, batches: Callable[[], Iterable]):
+        eng = self.eng
+        eng.start_adaround()
+        params = []
+        for s in eng.stages:
+            params += [s.alpha_w, s.alpha_b]
+        opt = AdamState(params, lr=self.lr)
+        decay = LinearTempDecay(self.iters, rel_start_decay=self.warmup, start_b=self.b_range[0], end_b=self.b_range[1])
+        loss_start = self.iters * self.warmup
+        count = 0
+        for _ in range(self.ep2):
+            for idx in batches():
+                count += 1
+                b = decay(count)
+                reg_on = not (count < loss_start)
+                want_log = self.log is not None or count % 500 == 0
+                self.iteration(idx, opt, self.weight if reg_on else 0.0, float(b) if reg_on else 0.0, want_log)
+                if want_log:
+                    rec = float(self._global_loss())
+                    rnd = float(eng.reg_sum) * self.weight if reg_on else 0.0
+                    if self.log is not None:
+                        self.log.append(("alpha", count, rec, rnd, float(b) if reg_on else 0.0))
+                    if count % 500 == 0:  # calib_model.py:86-88
+                        logging.info('Total loss:\t{:.4f} (rec:{:.4f}, round:{:.4f})\tb={:.2f}\tcount={}'.format(
+                            rec + rnd, rec, rnd, b if reg_on else 0, count))
+        eng.soft_w = False  # calib_model.py:231-240 (bias quantisers stay soft)
+        eng.invalidate()
+        return count
+
+    def _global_loss(self) -> torch.Tensor:
+        loss = self.eng.last_loss().clone()
+        if self.world > 1:
+            torch.distributed.all_reduce(loss, group=self.group)
+        return loss
+
+    def run(self, batches: Callable[[], Iterable]):
+        n1 = self.run_phase1(batches)
+        n2 = self.run_phase2(batches)
+        return n1, n2

@@ -1,0 +1,490 @@
+"""Decoder engine: runs a quantised NeRV/HNeRV decoder (forward, loss, backward, Adam) as a fixed
+sequence of libnq_sm100 kernel launches on one CUDA stream.
+
+This is the execution layer under the reference-shaped API in `neuroquant_b200.quantization` /
+`neuroquant_b200.models`.  It replaces, for the decoder only (the encoder is never quantised,
+quant_model.py:28-29):
+
+  * QuantModule.forward                       (quant_layer.py:67-81)
+  * QuantNeRVBlock.forward                    (quant_block.py:31-35)
+  * HNeRV.decode / NeRV.decode + OutImg       (HNeRV.py:49-71, NeRV.py:44-65, _layers.py:10-16)
+  * lp_loss + LossFunction.collect_round_loss (quantizer.py:66-73, calib_model.py:39-47)
+  * autograd of all of the above + torch.optim.Adam.step (calib_model.py:145-165, :206-226)
+
+Data layout in HBM (all fp32 in this revision):
+  activations  NHWC, channels padded to a multiple of 4, pads kept at zero
+  weights      reference layout (C_out, C_in[pow2 if rotated], k, k) for everything the quantiser
+               touches (weight, alpha, delta, zero_point, codes);  "packed" GEMM layouts
+               (include/neuroquant_b200.h) for what the convolutions read
+  gradients    one flat buffer holding every dW (reference layout) and db, so that data-parallel
+               ranks exchange it with a single NCCL all-reduce
+
+There is no PyTorch fallback: every step is a kernel of libnq_sm100.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+ROUND_NEAREST, ROUND_SOFT, ROUND_HARD = 0, 1, 2
+_ACT = {"none": 0, "gelu": 1}
+_HEAD = {"tanh": 0, "sigmoid": 1}
+
+
+def _pad4(c: int) -> int:
+    return (c + 3) // 4 * 4
+
+
+def next_pow2(n: int) -> int:
+    """quant_layer.py:13-14."""
+    return 1 if n == 0 else 1 << (n - 1).bit_length()
+
+
+@dataclass
+class StageGeom:
+    """One decoder stage: conv(k, stride 1, same) -> up-shuffle(rh, rw) -> act."""
+    cin: int
+    cout: int
+    k: int
+    rh: int = 1
+    rw: int = 1
+    act: str = "none"  # 'none' | 'gelu' for hidden stages; 'tanh' | 'sigmoid' for the head
+
+    @property
+    def c_grp(self) -> int:
+        return self.cout // (self.rh * self.rw)
+
+
+def geometry_from_cfg(cfg: dict, arch: str) -> List[StageGeom]:
+    """Stage list of a reference YAML config (HNeRV.py:12-43, NeRV.py:12-38)."""
+    import numpy as np
+
+    arch = arch.lower()
+    strides = list(cfg["dec_strides"])
+    geo: List[StageGeom] = []
+    c = cfg["dec_in_channel"]
+    if arch == "hnerv":
+        fc = int(np.prod(cfg["enc_strides"]) // np.prod(strides))
+        geo.append(StageGeom(cfg["enc_channel"][-1], c, 1, 1, 1, "none"))  # HNeRV.py:32 (fc folds below)
+        if fc != 1:
+            # HNeRV.py:57 folds (fc_h, fc_w) out of the channel axis of the stem output
+            if c % (fc * fc):
+                raise ValueError("dec_in_channel must be divisible by fc^2")
+            geo[0] = StageGeom(cfg["enc_channel"][-1], c, 1, fc, fc, "none")
+            c = c // (fc * fc)
+    elif arch == "nerv":
+        fch = cfg["crop_h"] // int(np.prod(strides))
+        fcw = cfg["crop_w"] // int(np.prod(strides))
+        geo.append(StageGeom(int(cfg["level"] * 2), c * fch * fcw, 1, fch, fcw, "none"))  # NeRV.py:26,51
+    else:
+        raise ValueError(f"unsupported arch {arch!r} (quant_model.py:13 supports NeRV and HNeRV)")
+    if cfg.get("dec_norm", "none") != "none":
+        raise NotImplementedError("QuantNeRVBlock drops the norm layer (quant_block.py:27-29); only dec_norm: none")
+    if cfg["dec_acts"] not in _ACT:
+        raise NotImplementedError(f"dec_acts={cfg['dec_acts']!r}: only 'gelu'/'none' have fused epilogues")
+    for ks, s in zip(cfg["dec_kernels"], strides):
+        co = int(max(round(c / cfg["channel_reduce"]), cfg["channel_lbound"]))
+        geo.append(StageGeom(c, co * s * s, ks, s, s, cfg["dec_acts"]))
+        c = co
+    if cfg["out_bias"] not in _HEAD:
+        raise NotImplementedError(f"out_bias={cfg['out_bias']!r}: only tanh / sigmoid heads")
+    geo.append(StageGeom(c, 3, 3, 1, 1, cfg["out_bias"]))
+    return geo
+
+
+class QuantStage:
+    """Device state of one QuantModule: weights, quantiser parameters, rounding variables.
+
+    Tensors are shared by reference with the API objects (QuantModule / quantizers) that expose
+    them under the reference's attribute names; the engine never copies them.
+    """
+
+    def __init__(self, geom: StageGeom, weight: torch.Tensor, bias: torch.Tensor, n_bits: int = 8,
+                 hadamard: bool = False):
+        assert tuple(weight.shape) == (geom.cout, geom.cin, geom.k, geom.k), (tuple(weight.shape), geom)
+        self.geom = geom
+        self.weight = weight.detach().contiguous().float()  # org_weight (quant_layer.py:41)
+        self.bias = bias.detach().contiguous().float()
+        self.hadamard = bool(hadamard)
+        self.n_bits = int(n_bits)
+        self.cin_src = next_pow2(geom.cin) if hadamard else geom.cin
+        if hadamard:  # quant_layer.py:43-49
+            padded = torch.zeros(geom.cout, self.cin_src, geom.k, geom.k, device=weight.device, dtype=torch.float32)
+            padded[:, :geom.cin] = self.weight
+            self.w_src = L.fwht_channel(padded)  # hadamard_weight
+        else:
+            self.w_src = self.weight
+        self.delta_w = self.zp_w = self.delta_b = self.zp_b = None
+        self.alpha_w = self.alpha_b = None
+        self.codes_w = torch.empty_like(self.w_src)  # x_quant cache (quantizer.py:297)
+        self.codes_b = torch.empty_like(self.bias)
+
+    def set_bits(self, n_bits: int):
+        if not 2 <= n_bits <= 8:
+            raise AssertionError("bitwidth not supported")  # quantizer.py:96,237
+        self.n_bits = int(n_bits)
+
+    def init_scales(self):
+        """UniformAffineQuantizer.init_quantization_scale('max', channel_wise) (quantizer.py:127-168)."""
+        self.delta_w, self.zp_w = L.uaq_init_max(self.w_src, self.n_bits, True)
+        self.delta_b, self.zp_b = L.uaq_init_max(self.bias, self.n_bits, True)
+
+    def start_adaround(self):
+        """AdaRoundQuantizer.__init__ (quantizer.py:259-319): fp16-rounded scales, alpha from the
+        fractional part of w_src / delta."""
+        self.delta_w = self.delta_w.detach().half().float().contiguous()
+        self.zp_w = self.zp_w.detach().half().float().contiguous()
+        self.delta_b = self.delta_b.detach().half().float().contiguous()
+        self.zp_b = self.zp_b.detach().half().float().contiguous()
+        self.alpha_w = L.adaround_init_alpha(self.w_src, self.delta_w)
+        self.alpha_b = L.adaround_init_alpha(self.bias, self.delta_b)
+
+
+class _Plan:
+    """Buffers of one (batch, grid) shape."""
+
+    def __init__(self, eng: "DecoderEngine", n: int, h0: int, w0: int, train: bool):
+        dev = eng.device
+        self.n, self.h0, self.w0, self.train = n, h0, w0, train
+        self.desc: List[L.ConvDesc] = []
+        self.x: List[torch.Tensor] = []  # stage inputs (x[i+1] is stage i's activated output)
+        self.z: List[Optional[torch.Tensor]] = []  # pre-activations (train only, act != none)
+        self.dz: List[Optional[torch.Tensor]] = []
+        h, w = h0, w0
+        cin_p = _pad4(eng.geoms[0].cin)
+        self.x.append(torch.zeros(n, h, w, cin_p, device=dev))
+        for i, g in enumerate(eng.geoms):
+            head = i == len(eng.geoms) - 1
+            cg = 4 if head else _pad4(g.c_grp)
+            d = L.ConvDesc(n, h, w, g.cin, cin_p, g.k, g.cout, g.rh, g.rw, g.c_grp, cg, 0 if head else _ACT[g.act])
+            self.desc.append(d)
+            if train:
+                self.dz.append(torch.empty(n, h, w, d.nout_p, device=dev))
+            if head:
+                break
+            h, w = h * g.rh, w * g.rw
+            self.x.append(torch.empty(n, h, w, cg, device=dev))
+            self.z.append(torch.empty(n, h, w, cg, device=dev) if (train and g.act != "none") else None)
+            cin_p = cg
+        self.H, self.W = h, w
+        self.img = torch.empty(n, 3, h, w, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+
+
+class DecoderEngine:
+    """Executes a list of QuantStage on one device.  mode: 'off' | 'uaq' | 'ada'."""
+
+    def __init__(self, stages: Sequence[QuantStage]):
+        self.stages = list(stages)
+        self.geoms = [s.geom for s in self.stages]
+        for g in self.geoms[:-1]:
+            if g.act not in _ACT:
+                raise NotImplementedError(f"activation {g.act!r}")
+        hg = self.geoms[-1]
+        if (hg.k, hg.cout, hg.rh, hg.rw) != (3, 3, 1, 1) or hg.act not in _HEAD:
+            raise NotImplementedError("head must be a 3x3 conv to 3 channels with tanh/sigmoid OutImg")
+        self.device = self.stages[0].weight.device
+        if self.device.type != "cuda":
+            raise L.NqError("DecoderEngine needs CUDA tensors (no CPU fallback)")
+        self.mode = "uaq"
+        self.soft_w = False
+        self.soft_b = False
+        self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
+        self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
+        self._weights_valid = False
+        self._wt_valid = False
+        self.reg_sum = torch.zeros(1, device=self.device)
+        self._grad = None
+        self.sm = L.lib.nq_sm_count()
+        self.launches = 0  # kernels launched through the C ABI (bench.py reports it)
+        self._prof = None  # list of (name, flops, start_event, stop_event) while kernel_profile() runs
+        self.dtype_name = "f32"
+
+    # ------------------------------------------------------------------ profiling
+    def _run(self, name: str, d, fn, *args) -> int:
+        """Launch one convolution-class kernel; under kernel_profile() bracket it with CUDA events on
+        the launch stream.  d: the stage's ConvDesc (for the algorithmic FLOP count 2*M*N*K)."""
+        if self._prof is None:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = fn(*args)
+        e1.record()
+        flops = 2.0 * d.n * d.h * d.w * d.cout * d.cin * d.ksize * d.ksize
+        self._prof.append((name, flops, e0, e1))
+        return st
+
+    def kernel_profile(self, step_fn, reps: int = 3):
+        """Per-kernel device time of the convolution launches of `step_fn` (CUDA events on the launch
+        stream, averaged over `reps` runs).  Returns a list of dicts sorted by total time."""
+        step_fn()
+        torch.cuda.synchronize()
+        self._prof = []
+        for _ in range(reps):
+            step_fn()
+        torch.cuda.synchronize()
+        rows, self._prof = self._prof, None
+        agg = {}
+        for name, flops, e0, e1 in rows:
+            a = agg.setdefault(name, [0.0, 0, flops])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+        out = [{"kernel": k, "ms": v[0] / v[1], "flops": v[2], "tflops": v[2] / (v[0] / v[1] * 1e-3) / 1e12}
+               for k, v in agg.items()]
+        out.sort(key=lambda r: -r["ms"])
+        return out
+
+    # ------------------------------------------------------------------ bookkeeping
+    def invalidate(self):
+        """Call after any change to weights / quantiser state (Q9: cached packed weights stay legal
+        only while nothing changed)."""
+        self._weights_valid = False
+        self._wt_valid = False
+
+    def avg_bits(self) -> float:
+        """quant_model.py:58-72."""
+        num = sum(s.n_bits * (s.weight.numel() + s.bias.numel()) for s in self.stages)
+        return num / sum(s.weight.numel() + s.bias.numel() for s in self.stages)
+
+    def set_bitwidth(self, bits: Sequence[int]) -> float:
+        for s, b in zip(self.stages, bits):
+            s.set_bits(b)
+        self.invalidate()
+        return self.avg_bits()
+
+    def init_scales(self):
+        for s in self.stages:
+            s.init_scales()
+            self.launches += 2
+        self.invalidate()
+
+    def start_adaround(self):
+        for s in self.stages:
+            s.start_adaround()
+            self.launches += 2
+        self.mode, self.soft_w, self.soft_b = "ada", True, True
+        self.invalidate()
+
+    def plan(self, n: int, h0: int, w0: int, train: bool) -> _Plan:
+        key = (n, h0, w0, train)
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, n, h0, w0, train)
+        return self._plans[key]
+
+    def _alloc_packed(self, p: _Plan):
+        if self._packed is not None:
+            return
+        self._packed = []
+        for s, d in zip(self.stages, p.desc):
+            wk = torch.zeros(d.kdim, d.nout_p, device=self.device)
+            wt = torch.zeros(d.ksize * d.ksize * d.nout_p, d.cin_p, device=self.device)
+            bp = torch.zeros(d.nout_p, device=self.device)
+            deq_w = torch.empty_like(s.w_src)
+            deq_b = torch.empty_like(s.bias)
+            self._packed.append((wk, wt, bp, deq_w, deq_b))
+
+    # ------------------------------------------------------------------ weights
+    def prepare_weights(self, p: _Plan, need_wt: bool, reg_b: Optional[float] = None):
+        """Fake-quantise every stage's weight and bias and pack them for the convolutions
+        (quant_layer.py:68-78).  reg_b: also accumulate sum(1 - |2h-1|^b) over the WEIGHT alphas into
+        self.reg_sum (calib_model.py:39-47; bias alphas are excluded there)."""
+        self._alloc_packed(p)
+        st = L.stream()
+        if reg_b is not None:
+            self.reg_sum.zero_()
+        for s, d, (wk, wt, bp, deq_w, deq_b) in zip(self.stages, p.desc, self._packed):
+            if self.mode == "off":
+                w_for_conv, b_for_conv, cin_src = s.weight, s.bias, s.geom.cin
+            else:
+                if self.mode == "uaq":
+                    mw = mb = ROUND_NEAREST
+                else:
+                    mw = ROUND_SOFT if self.soft_w else ROUND_HARD
+                    mb = ROUND_SOFT if self.soft_b else ROUND_HARD
+                self._fq(s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, mw, s.codes_w, deq_w,
+                         self.reg_sum if (reg_b is not None and mw == ROUND_SOFT) else None, reg_b or 0.0)
+                self._fq(s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, mb, s.codes_b, deq_b, None, 0.0)
+                if s.hadamard:  # quant_layer.py:71: rotate back, keep the first C_in channels
+                    L.fwht_channel(deq_w, out=deq_w)
+                    self.launches += 1
+                w_for_conv, b_for_conv, cin_src = deq_w, deq_b, s.cin_src
+            L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(w_for_conv), cin_src, L.ptr(b_for_conv), L.ptr(wk),
+                                         L.ptr(wt) if need_wt else None, L.ptr(bp), st), "nq_pack_weight")
+            self.launches += 1
+        self._weights_valid = True
+        self._wt_valid = need_wt
+
+    def _fq(self, x, alpha, delta, zp, n_bits, mode, codes, deq, reg_sum, reg_b):
+        rows, row_len, d_stride = (delta.numel(), x.numel() // delta.numel(), 1) if delta.numel() > 1 else (1, x.numel(), 0)
+        L.check(L.lib.nq_fakequant_fwd(L.ptr(x), L.ptr(alpha) if mode != ROUND_NEAREST else None, L.ptr(delta),
+                                       L.ptr(zp), rows, row_len, d_stride, n_bits, mode, L.ptr(codes), L.ptr(deq),
+                                       L.ptr(reg_sum), float(reg_b), L.stream()), "nq_fakequant_fwd")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, embed: torch.Tensor, *, train: bool = False, target: Optional[torch.Tensor] = None,
+                p_norm: float = 2.0, mean_pixels: Optional[float] = None, reuse_weights: bool = False,
+                reg_b: Optional[float] = None, want_img: bool = True) -> torch.Tensor:
+        """embed: (n, C0, h0, w0) NCHW as the reference's decode() takes it.  Returns the (n, 3, H, W)
+        frame.  With `target` the loss sum is accumulated into plan.loss (read via last_loss())."""
+        n, c0, h0, w0 = embed.shape
+        if c0 != self.geoms[0].cin:
+            raise L.NqError(f"embedding has {c0} channels, decoder stem expects {self.geoms[0].cin}")
+        p = self.plan(n, h0, w0, train)
+        self._last_plan = p
+        st = L.stream()
+        if not (reuse_weights and self._weights_valid and (self._wt_valid or not train)):
+            self.prepare_weights(p, need_wt=train, reg_b=reg_b)
+        embed = embed.detach().contiguous().float()
+        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(embed), L.ptr(p.x[0]), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_nhwc")
+        self.launches += 1
+        last = len(self.stages) - 1
+        for i in range(last):
+            wk, _, bp, _, _ = self._packed[i]
+            z = p.z[i] if train else None
+            L.check(self._run(f"conv_fwd[{i}]", p.desc[i], L.lib.nq_conv_fwd, C.byref(p.desc[i]), L.ptr(p.x[i]), L.ptr(wk),
+                              L.ptr(bp), L.ptr(z), L.ptr(p.x[i + 1]), st), "nq_conv_fwd")
+            self.launches += 1
+        wk, _, bp, _, _ = self._packed[last]
+        if target is not None:
+            target = target.detach().contiguous().float()
+            if tuple(target.shape) != (n, 3, p.H, p.W):
+                raise L.NqError(f"target shape {tuple(target.shape)} != {(n, 3, p.H, p.W)}")
+            p.loss.zero_()
+            mp = float(mean_pixels if mean_pixels is not None else n * p.H * p.W)
+        else:
+            mp = 1.0
+        L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss, C.byref(p.desc[last]), L.ptr(p.x[last]), L.ptr(wk), L.ptr(bp),
+                                       _HEAD[self.geoms[last].act], L.ptr(target), float(p_norm), mp,
+                                       L.ptr(p.img) if (want_img or target is None) else None,
+                                       L.ptr(p.loss) if target is not None else None,
+                                       L.ptr(p.dz[last]) if (train and target is not None) else None, st), "nq_head_fwd_loss")
+        self.launches += 1
+        self._mean_pixels = mp
+        return p.img
+
+    def last_loss(self) -> torch.Tensor:
+        """lp_loss of the last forward-with-target: sum / mean_pixels (device scalar, no sync)."""
+        return self._last_plan.loss / self._mean_pixels
+
+    # ------------------------------------------------------------------ backward
+    def _grad_buffers(self):
+        if self._grad is None:
+            sizes = []
+            for s in self.stages:
+                sizes += [s.w_src.numel(), s.bias.numel()]
+            flat = torch.zeros(sum(sizes), device=self.device)
+            views, o = [], 0
+            for s in self.stages:
+                nw, nb = s.w_src.numel(), s.bias.numel()
+                views.append((flat[o:o + nw].view_as(s.w_src), flat[o + nw:o + nw + nb]))
+                o += nw + nb
+            self._grad = (flat, views)
+        return self._grad
+
+    def _wgrad_splits(self, d: L.ConvDesc) -> int:
+        rows = d.kdim + 4
+        n = d.nout_p
+        bn = 64 if (n <= 64 or 0 < n % 128 <= 64) else 128
+        tiles = ((rows + 127) // 128) * ((n + bn - 1) // bn)
+        pix = d.n * d.h * d.w
+        s = max(1, min((4 * self.sm + tiles - 1) // tiles, pix // 64))
+        return int(s)
+
+    def backward(self) -> torch.Tensor:
+        """Back-propagate the loss of the last train-mode forward down to dL/d(dequantised weight) and
+        dL/d(dequantised bias) in reference layout (rotated domain when --hadamard).  Returns the flat
+        gradient buffer (all stages, W then b), ready for an all-reduce."""
+        p = self._last_plan
+        assert p.train and self._wt_valid
+        st = L.stream()
+        flat, views = self._grad_buffers()
+        last = len(self.stages) - 1
+        if not hasattr(p, "dwk"):
+            p.dwk, p.ws = [], []
+            for i, d in enumerate(p.desc):
+                p.dwk.append(torch.empty(d.kdim + 4, d.nout_p, device=self.device))
+                if i == last:
+                    blocks = L.lib.nq_head_wgrad_blocks(C.byref(d))
+                    p.ws.append((torch.empty(blocks * (d.kdim + 4) * 4, device=self.device), 0))
+                else:
+                    sp = self._wgrad_splits(d)
+                    p.ws.append((torch.empty(sp * (d.kdim + 4) * d.nout_p, device=self.device) if sp > 1 else None, sp))
+        for i in range(last, -1, -1):
+            d = p.desc[i]
+            _, wt, _, _, _ = self._packed[i]
+            ws, sp = p.ws[i]
+            if i == last:
+                L.check(self._run("head_wgrad", d, L.lib.nq_head_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]), L.ptr(p.dwk[i]),
+                                  L.ptr(ws), ws.numel(), st), "nq_head_wgrad")
+                self.launches += 2
+            else:
+                L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_conv_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]),
+                                  L.ptr(p.dwk[i]), L.ptr(ws), ws.numel() if ws is not None else 0, sp, st), "nq_conv_wgrad")
+                self.launches += 2 if sp > 1 else 1
+            if i > 0:
+                g_prev = self.geoms[i - 1]
+                L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
+                                  L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st), "nq_conv_dgrad")
+                self.launches += 1
+            s = self.stages[i]
+            gw, gb = views[i]
+            L.check(L.lib.nq_unpack_wgrad(C.byref(d), L.ptr(p.dwk[i]), s.cin_src, L.ptr(gw), L.ptr(gb), st), "nq_unpack_wgrad")
+            self.launches += 1
+        return flat
+
+    def param_grads(self, grad_scale: float = 1.0, reg_w: float = 0.0, reg_b: float = 0.0):
+        """Chain the (possibly all-reduced) weight gradients through the rotation and the quantiser
+        Jacobian.  Returns per stage (g_w, g_b): d_alpha (mode 'ada', soft) or d_delta (mode 'uaq').
+        reg_w / reg_b add the rounding regulariser's gradient on the WEIGHT alphas only."""
+        flat, views = self._grad_buffers()
+        out = []
+        if not hasattr(self, "_pg"):
+            self._pg = {}
+        for i, s in enumerate(self.stages):
+            gw, gb = views[i]
+            if s.hadamard:  # transpose of the (symmetric, orthonormal) rotation is the rotation
+                L.fwht_channel(gw, out=gw)
+                self.launches += 1
+            if self.mode == "ada":
+                key = ("a", i)
+                if key not in self._pg:
+                    self._pg[key] = (torch.empty_like(s.alpha_w), torch.empty_like(s.alpha_b))
+                da_w, da_b = self._pg[key]
+                L.fakequant_bwd(gw, s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, ROUND_SOFT, grad_scale, reg_w, reg_b, out=da_w)
+                L.fakequant_bwd(gb, s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, ROUND_SOFT, grad_scale, 0.0, 0.0, out=da_b)
+                out.append((da_w, da_b))
+            elif self.mode == "uaq":
+                key = ("d", i)
+                if key not in self._pg:
+                    self._pg[key] = (torch.empty_like(s.delta_w), torch.empty_like(s.delta_b))
+                dd_w, dd_b = self._pg[key]
+                L.fakequant_bwd(gw, s.w_src, None, s.delta_w, s.zp_w, s.n_bits, ROUND_NEAREST, grad_scale, out=dd_w)
+                L.fakequant_bwd(gb, s.bias, None, s.delta_b, s.zp_b, s.n_bits, ROUND_NEAREST, grad_scale, out=dd_b)
+                out.append((dd_w, dd_b))
+            else:
+                raise L.NqError("param_grads needs quantisation on")
+            self.launches += 2
+        return out
+
+
+class AdamState:
+    """torch.optim.Adam defaults (calib_model.py:134,195) over a list of tensors, one fused kernel each."""
+
+    def __init__(self, params: Sequence[torch.Tensor], lr: float):
+        self.params = list(params)
+        self.lr = float(lr)
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.t = 0
+
+    def step(self, grads: Sequence[torch.Tensor]) -> int:
+        self.t += 1
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            L.adam_step(p, g, m, v, self.lr, self.t)
+        return len(self.params)

@@ -1,0 +1,61 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/neuroquant_b200.h declares (no compute calls -- there is no GPU here), error strings exist,
+and the product package never imports the oracle."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "neuroquant_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from neuroquant_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in the header but not exported"
+    assert set(syms) == set(_lib.EXPORTS), set(syms) ^ set(_lib.EXPORTS)
+    assert _lib.ABI_VERSION == raw.nq_abi_version()
+    for code in (0, -1, -2, -3, -4, -5):
+        assert _lib.lib.nq_status_string(code)
+
+
+def test_cpu_tensors_are_rejected():
+    import pytest
+    import torch
+    from neuroquant_b200 import _lib
+    with pytest.raises(_lib.NqError):
+        _lib.ptr(torch.zeros(3))
+    with pytest.raises(_lib.NqError):
+        _lib.uaq_init_max(torch.zeros(2, 2, 1, 1), 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "neuroquant_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+def test_host_logic_geometry_and_schedule():
+    import neuroquant_b200 as nq
+    from neuroquant_b200.workloads import WORKLOADS, conv_flops, embed_shape
+    arch, cfg = WORKLOADS["hnerv-bunny-3m"]
+    geo = nq.geometry_from_cfg(cfg, arch)
+    assert [(g.cout, g.cin, g.k) for g in geo] == [(92, 16, 1), (1925, 92, 1), (1024, 77, 3), (848, 64, 5), (176, 53, 5),
+                                                   (148, 44, 5), (3, 37, 3)]
+    assert abs(conv_flops(geo, *embed_shape(cfg, arch)[1:], n=2) / 1e9 - 202.34) < 0.01
+    arch, cfg = WORKLOADS["nerv-bunny-3m"]
+    geo = nq.geometry_from_cfg(cfg, arch)
+    assert (geo[0].cout, geo[0].rh, geo[0].rw) == (1160, 2, 4)
+    td = nq.LinearTempDecay(21000, rel_start_decay=0.2, start_b=20, end_b=2)
+    assert f"{td(4500):.2f}" == "19.68" and f"{td(19500):.2f}" == "3.61"  # reference log lines

@@ -1,0 +1,301 @@
+"""GPU parity tests (run with -m gpu on a B200): every kernel behind the C ABI against the CPU oracle
+(oracle/nq_oracle.py) and the golden fixtures produced by the unmodified reference.
+
+Bars: bit-exact for integer work (hard / nearest codes, zero points, de-quantised values that are
+products of exact integers and scales); fp32 tolerances stated per test for everything that goes
+through transcendental functions (GPU expf/logf/erff differ from the CPU's by <= 2 ulp) or through
+differently-ordered fp32 sums.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nq_oracle as O
+from tests.helpers import CASES, case_stages, load, t
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nq():
+    import neuroquant_b200 as pkg
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return pkg
+
+
+def dev(x):
+    return x.cuda().contiguous()
+
+
+# ------------------------------------------------------------------------------------------ quantisers
+@pytest.mark.parametrize("bits", [2, 3, 4, 6, 8])
+@pytest.mark.parametrize("name", ["w", "b"])
+def test_uaq_kernels_golden(nq, bits, name):
+    L = nq._lib
+    g = load("quantizer_kats")
+    x = dev(t(g[name]))
+    delta, zp = L.uaq_init_max(x, bits, True)
+    assert np.array_equal(delta.cpu().numpy(), g[f"uaq{bits}_{name}_delta"])  # bit-exact scales
+    assert np.array_equal(zp.cpu().numpy(), g[f"uaq{bits}_{name}_zp"])
+    codes, deq = L.fakequant_fwd(x, None, delta, zp, bits, 0)
+    assert np.array_equal(deq.cpu().numpy(), g[f"uaq{bits}_{name}_deq"])  # bit-exact
+    want_codes, _ = O.uaq_quant(t(g[name]), t(g[f"uaq{bits}_{name}_delta"]), t(g[f"uaq{bits}_{name}_zp"]), bits)
+    assert torch.equal(codes.cpu(), want_codes)
+    r = dev(t(g[f"uaq{bits}_{name}_r"]))
+    dd = L.fakequant_bwd(r, x, None, delta, zp, bits, 0)
+    want = g[f"uaq{bits}_{name}_ddelta"]
+    # per-row sums in a different order: fp32 tolerance relative to the row's magnitude
+    scale = np.abs(want).max() + 1e-6
+    assert np.abs(dd.cpu().numpy().reshape(want.shape) - want).max() <= 2e-5 * scale + 1e-5
+
+
+@pytest.mark.parametrize("bits", [2, 4, 6, 8])
+@pytest.mark.parametrize("name", ["w", "b"])
+def test_adaround_kernels_golden(nq, bits, name):
+    L = nq._lib
+    g = load("quantizer_kats")
+    x = dev(t(g[f"ada{bits}_{name}_x"]))
+    delta, zp = dev(t(g[f"ada{bits}_{name}_delta"])), dev(t(g[f"ada{bits}_{name}_zp"]))
+    a0 = L.adaround_init_alpha(x, delta)
+    assert np.allclose(a0.cpu().numpy(), g[f"ada{bits}_{name}_alpha0"], rtol=2e-6, atol=2e-6)  # logf ulp
+    alpha = dev(t(g[f"ada{bits}_{name}_alpha"]))
+    # hard rounding: integer codes, bit-exact (the deliverable)
+    codes, deq = L.fakequant_fwd(x, alpha, delta, zp, bits, 2)
+    assert np.array_equal(codes.cpu().numpy(), g[f"ada{bits}_{name}_hard_codes"])
+    assert np.array_equal(deq.cpu().numpy(), g[f"ada{bits}_{name}_hard_deq"])
+    # soft rounding: sigmoid through expf -> 1e-6
+    reg = torch.zeros(1, device="cuda")
+    codes, deq = L.fakequant_fwd(x, alpha, delta, zp, bits, 1, reg_sum=reg, reg_b=7.5)
+    assert np.allclose(codes.cpu().numpy(), g[f"ada{bits}_{name}_soft_codes"], rtol=0, atol=2e-6 * 2 ** bits)
+    assert np.allclose(deq.cpu().numpy(), g[f"ada{bits}_{name}_soft_deq"], rtol=1e-6, atol=1e-6)
+    assert float(reg) == pytest.approx(float(g[f"ada{bits}_{name}_reg_b7.5"]), rel=1e-5)
+    r = dev(t(g[f"uaq{bits}_{name}_r"]))
+    da = L.fakequant_bwd(r, x, alpha, delta, zp, bits, 1, 1.0, 0.01, 7.5)
+    want = g[f"ada{bits}_{name}_dalpha"]
+    assert np.allclose(da.cpu().numpy(), want, rtol=2e-5, atol=1e-7)
+
+
+def test_fakequant_big_random_bit_exact(nq):
+    """A weight-sized tensor (HNeRV stage 3: 848 x 64 x 5 x 5): nearest and hard codes bit-exact."""
+    L = nq._lib
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(848, 64, 5, 5, generator=g) * 0.05
+    for bits in (4, 6):
+        d, z = O.uaq_init_max(w, bits, True)
+        dg, zg = L.uaq_init_max(dev(w), bits, True)
+        assert torch.equal(dg.cpu(), d) and torch.equal(zg.cpu(), z)
+        codes, deq = L.fakequant_fwd(dev(w), None, dg, zg, bits, 0)
+        wc, wd = O.uaq_quant(w, d, z, bits)
+        assert torch.equal(codes.cpu(), wc) and torch.equal(deq.cpu(), wd)
+        d16, z16 = O.fp16_round(d), O.fp16_round(z)
+        alpha = torch.randn(w.shape, generator=g) * 3
+        codes, deq = L.fakequant_fwd(dev(w), dev(alpha), dev(d16), dev(z16), bits, 2)
+        wc, wd = O.adaround_quant(w, alpha, d16, z16, bits, soft=False)
+        assert torch.equal(codes.cpu(), wc) and torch.equal(deq.cpu(), wd)
+
+
+def test_fakequant_rejects_bad_args(nq):
+    L = nq._lib
+    x = torch.zeros(4, 4, 1, 1, device="cuda")
+    d = torch.ones(4, 1, 1, 1, device="cuda")
+    with pytest.raises(L.NqError):
+        L.fakequant_fwd(x, None, d, d, 9, 0)  # assert 2 <= n_bits <= 8 (quantizer.py:96)
+    with pytest.raises(L.NqError):
+        L.fakequant_fwd(x, None, d, d, 4, 1)  # AdaRound needs alpha
+    with pytest.raises(L.NqError):
+        L.fakequant_fwd(x.cpu(), None, d, d, 4, 0)  # no CPU fallback
+
+
+@pytest.mark.parametrize("n", [1, 2, 16, 32, 64, 128, 256])
+def test_fwht_rows(nq, n):
+    L = nq._lib
+    x = torch.randn(77, n, generator=torch.Generator().manual_seed(n))
+    got = L.fwht_rows(dev(x)).cpu()
+    want = O.fwht_last(x)
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
+    from scipy.linalg import hadamard
+    ref = x.double() @ t(hadamard(n).astype(np.float64)) / math.sqrt(n)
+    assert torch.allclose(got.double(), ref, atol=1e-5)
+
+
+def test_fwht_channel_golden_and_involution(nq):
+    L = nq._lib
+    g = load("quantizer_kats")
+    got = L.fwht_channel(dev(t(g["had_in"])))
+    assert np.allclose(got.cpu().numpy(), g["had_out"], rtol=1e-6, atol=1e-6)
+    x = torch.randn(2, 8, 4, 4)
+    assert (L.fwht_channel(L.fwht_channel(dev(x))).cpu() - x).abs().max() < 1e-6  # quant_layer.py:94-100
+    with pytest.raises(L.NqError):
+        L.fwht_rows(torch.zeros(3, 24, device="cuda"))  # not a power of two
+    with pytest.raises(L.NqError):
+        L.fwht_rows(torch.zeros(3, 512, device="cuda"))  # > 256
+
+
+def test_adam_matches_torch(nq):
+    L = nq._lib
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.randn(1000, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=0.003)
+    p, m, v = dev(p0.clone()), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+    for step in range(1, 6):
+        gr = torch.randn(1000, generator=g)
+        p_ref.grad = gr.clone()
+        opt.step()
+        L.adam_step(p, dev(gr), m, v, 0.003, step)
+    assert torch.allclose(p.cpu(), p_ref.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_loss_psnr_dot(nq):
+    L = nq._lib
+    g = load("quantizer_kats")
+    pr, tg = t(g["lp_pred"]), t(g["lp_tgt"])
+    n_mean = pr.shape[0] * pr.shape[2] * pr.shape[3]
+    for p, key in ((2.0, "lp_p2"), (2.4, "lp_p24")):
+        s, grad = L.lp_loss_sum(dev(pr), dev(tg), p, 1.0 / n_mean, want_grad=True)
+        assert float(s) / n_mean == pytest.approx(float(g[key]), rel=2e-6)
+        pa = pr.clone().requires_grad_(True)
+        O.lp_loss(pa, tg, p).backward()
+        assert torch.allclose(grad.cpu(), pa.grad, rtol=1e-5, atol=1e-8)
+    a, b = torch.rand(3, 3, 20, 30), torch.rand(3, 3, 20, 30)
+    assert torch.allclose(L.psnr(dev(a), dev(b)).cpu(), O.psnr(a, b), rtol=1e-6)
+    xs = [torch.randn(n) for n in (5, 1000, 70001)]
+    ys = [torch.randn(n) for n in (5, 1000, 70001)]
+    got = L.multi_dot([dev(x) for x in xs], [dev(y) for y in ys], 0).cpu()
+    want = torch.stack([(x.double() * y.double()).sum() for x, y in zip(xs, ys)]).float()
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-3)
+    got = L.multi_dot([dev(x) for x in xs], [dev(y) for y in ys], 1).cpu()
+    want = torch.stack([((x.double() * y.double()) ** 2).sum() for x, y in zip(xs, ys)]).float()
+    assert torch.allclose(got, want, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ decoder engine
+def make_engine(nq, tag, mode="uaq"):
+    g, arch, cfg, stages = case_stages(tag)
+    geoms = nq.geometry_from_cfg(cfg, arch)
+    had = bool(g["hadamard"])
+    qs = [nq.QuantStage(gm, dev(st.weight), dev(st.bias), int(b), had) for gm, st, b in zip(geoms, stages, g["bits"].tolist())]
+    eng = nq.DecoderEngine(qs)
+    eng.mode = mode
+    return g, arch, cfg, stages, eng
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_decode_golden(nq, tag):
+    """FP decode and nearest-rounded quantised decode against the reference's outputs; scales and
+    perturbation-free codes bit-exact."""
+    g, arch, cfg, stages, eng = make_engine(nq, tag, "off")
+    cali = dev(t(g["cali"]))
+    out = eng.forward(cali[:2]).cpu()
+    assert np.abs(out.numpy() - g["fp_out"]).max() < 1e-5
+    eng.mode = "uaq"
+    eng.init_scales()
+    assert eng.avg_bits() == float(g["avg_bits"])
+    for i, s in enumerate(eng.stages):
+        assert np.array_equal(s.delta_w.cpu().numpy(), g[f"init/{i}/delta_w"])
+        assert np.array_equal(s.zp_w.cpu().numpy(), g[f"init/{i}/zp_w"])
+        assert np.array_equal(s.delta_b.cpu().numpy(), g[f"init/{i}/delta_b"])
+        assert np.array_equal(s.zp_b.cpu().numpy(), g[f"init/{i}/zp_b"])
+    out = eng.forward(cali[:2]).cpu()
+    assert np.abs(out.numpy() - g["uaq_out"]).max() < 1e-5
+    # codes of the last forward (quant_model.py:74-80) against the oracle, bit-exact
+    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]))
+    with torch.no_grad():
+        qd.forward(t(g["cali"])[:2])
+    for s, q in zip(eng.stages, qd.q):
+        if not bool(g["hadamard"]):  # rotated inputs differ by fp32 rounding of the WHT -> ties may flip
+            assert torch.equal(s.codes_w.cpu(), q.codes_w)
+        else:
+            assert (s.codes_w.cpu() != q.codes_w).float().mean() < 1e-3
+        assert torch.equal(s.codes_b.cpu(), q.codes_b)
+
+
+def oracle_grads(stages, g, soft, batch=slice(0, 2)):
+    """Oracle: loss gradients w.r.t. alpha (soft AdaRound) or delta (UAQ) on the first two frames."""
+    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]))
+    cali, frames = t(g["cali"]), t(g["frames"])
+    if soft:
+        qd.start_adaround()
+        leaves = []
+        for q in qd.q:
+            q.alpha_w.requires_grad_(True)
+            q.alpha_b.requires_grad_(True)
+            leaves += [q.alpha_w, q.alpha_b]
+    else:
+        leaves = []
+        for q in qd.q:
+            q.delta_w = q.delta_w.clone().requires_grad_(True)
+            q.delta_b = q.delta_b.clone().requires_grad_(True)
+            leaves += [q.delta_w, q.delta_b]
+    out = qd.forward(cali[batch])
+    rec = O.lp_loss(out, frames[batch], 2.0)
+    reg = sum(0.01 * O.round_reg(q.alpha_w, 7.5) for q in qd.q) if soft else 0.0
+    (rec + reg).backward()
+    return qd, out.detach(), float(rec), [x.grad for x in leaves]
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("soft", [True, False])
+def test_backward_matches_oracle_autograd(nq, tag, soft):
+    """forward + loss + backward + quantiser Jacobian vs autograd of the oracle.  Tolerance: 2e-4 of
+    each tensor's gradient scale (fp32 sums in a different order through 7 convolutions)."""
+    g, arch, cfg, stages, eng = make_engine(nq, tag, "uaq")
+    eng.init_scales()
+    qd, want_out, want_rec, want = oracle_grads(stages, g, soft)
+    if soft:
+        eng.start_adaround()
+    cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
+    out = eng.forward(cali[:2], train=True, target=frames[:2], p_norm=2.0, reg_b=7.5 if soft else None)
+    assert (out.cpu() - want_out).abs().max() < 2e-5
+    assert float(eng.last_loss()) == pytest.approx(want_rec, rel=1e-5)
+    eng.backward()
+    got = eng.param_grads(1.0, 0.01 if soft else 0.0, 7.5 if soft else 0.0)
+    got = [x for pair in got for x in pair]
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        a = a.cpu().reshape(b.shape)
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= 2e-4 * scale + 1e-9, (i, (a - b).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_calibration_golden(nq, tag):
+    """80 iterations (4 step-size + 76 AdaRound) in the reference's injected batch order: same
+    acceptance as the oracle's own pin (tests/test_oracle_golden.py::test_calibration_golden)."""
+    g, arch, cfg, stages, eng = make_engine(nq, tag, "uaq")
+    eng.init_scales()
+    cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
+    order = g["order"].tolist()
+    log = []
+
+    def fetch(idx):
+        idx = torch.as_tensor(idx, device="cuda")
+        return cali[idx], frames[idx]
+
+    loop = nq.CalibrationLoop(eng, fetch, len(order), iters=80, weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0,
+                              lr=0.003, log=log)
+    loop.run(lambda: order)
+    traj = g["traj"]
+    assert len(log) == len(traj)
+    got_total = np.array([r[2] + r[3] for r in log])
+    assert np.allclose(got_total[:10], traj[:10, 1], rtol=2e-5, atol=1e-7)
+    assert np.allclose(got_total, traj[:, 1], rtol=5e-3, atol=1e-6)
+    out = eng.forward(cali[:2]).cpu()
+    assert np.abs(out.numpy() - g["calib_out"]).max() < 5e-3
+    assert np.abs(O.psnr(out, t(g["frames"])[:2]).numpy() - g["calib_psnr"]).max() < 0.01
+    n_diff = n_tot = 0
+    for i, s in enumerate(eng.stages):
+        far = np.abs(s.alpha_w.cpu().numpy() - g[f"final/{i}/alpha_w"]) > 1e-3
+        assert far.mean() < 0.02
+        assert np.allclose(s.delta_w.cpu().numpy(), g[f"final/{i}/delta_w"], rtol=2e-3)
+        cw = s.codes_w.cpu()
+        n_diff += int((cw.numpy() != g[f"final/{i}/codes_w"]).sum())
+        n_tot += cw.numel()
+        assert torch.equal(cw, cw.round())  # hard codes are integers
+        assert np.allclose(s.codes_b.cpu().numpy(), g[f"final/{i}/codes_b"], atol=5e-2)  # biases stay soft (Q3)
+        # identical V and scales -> bit-exact codes: re-derive on the oracle from OUR alpha/delta
+        wc, _ = O.adaround_quant(s.w_src.cpu(), s.alpha_w.cpu(), s.delta_w.cpu(), s.zp_w.cpu(), s.n_bits, soft=False)
+        assert torch.equal(cw, wc)
+    assert n_diff / n_tot < 5e-3
