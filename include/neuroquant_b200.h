@@ -178,6 +178,46 @@ int nq_head_wgrad(const nq_conv_desc* d, const float* x, const float* dz_head, f
                   float* workspace, int64_t workspace_floats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 / TMEM) convolution path: same contract as nq_conv_fwd / nq_conv_dgrad, bf16
+ * operands split hi + lo so that products carry 16 mantissa bits, fp32 accumulation in TMEM.
+ * Channel contract: cin_p and rh*rw*cg must be multiples of 16.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct nq_tc_plan {
+  int32_t dir;                 /* 0 forward, 1 data gradient */
+  int32_t C, N;                /* GEMM-K channels per tap, GEMM-N columns */
+  int32_t NT, KC, SBC;         /* N tile, channels per activation unit, channels per weight stage */
+  int32_t a_planes, b_planes;  /* bf16 planes of the activation / weight operand (1 = hi, 2 = hi + lo) */
+  int32_t PW, PH, CGS;         /* halo tile width, height (pixels); channel-group stride (bytes) */
+  int32_t a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages, smem_bytes;
+  int32_t tiles_x, tiles_y, tiles_n, total_tiles;
+  int64_t wpk_bytes;           /* size of the packed weight buffer the caller allocates */
+} nq_tc_plan;
+
+/* Tiling / staging plan of one stage and direction; pure host arithmetic. */
+int nq_tc_plan_conv(const nq_conv_desc* d, int dir, int a_planes, int b_planes, nq_tc_plan* plan);
+
+/* ref-layout weights (cout, cin_src, k, k) -> bf16 stage order of `plan` (wpk: plan->wpk_bytes bytes).
+ * zero_point (may be NULL) is subtracted per output channel first: passing the quantiser's codes
+ * (quantizer.py:297) and zero point packs the INTEGER weights code - zp, exact in one bf16 plane for
+ * n_bits <= 8; the per-channel step size then goes to nq_tc_pack_epilogue / the conv epilogue. */
+int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* plan, const float* w_ref, int cin_src,
+                      const float* zero_point, int zp_stride, void* wpk, void* stream);
+
+/* Per-column epilogue vectors in packed channel order: scale_packed[n'] = delta[co * d_stride] (1 when
+ * delta is NULL or n' is a pad column), bias_packed[n'] = bias_ref[co] (0 for pads). */
+int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, int d_stride, const float* bias_ref,
+                        float* scale_packed, float* bias_packed, void* stream);
+
+/* y = act(shuffle(conv(x) * scale + bias)); arguments as nq_conv_fwd (scale_packed may be NULL). */
+int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* plan, const float* x, const void* wpk,
+                   const float* scale_packed, const float* bias_packed, float* z, float* y, void* stream);
+
+/* dz_prev = unshuffle(conv_transpose(dz) * act'(z_prev)); arguments as nq_conv_dgrad, wpk_t packed with a
+ * dir = 1 plan from the DE-QUANTISED weights. */
+int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* plan, const float* dz, const void* wpk_t,
+                     const float* z_prev, int prev_rh, int prev_rw, int prev_act, float* dz_prev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Layout edges and reductions
  * ------------------------------------------------------------------------------------------------ */
 /* NCHW (n, c, h, w) <-> NHWC (n, h, w, c_p); pad channels are written as zero / ignored. */

@@ -33,6 +33,14 @@ class ConvDesc(C.Structure):
         return self.ksize * self.ksize * self.cin_p
 
 
+class TcPlan(C.Structure):
+    """Mirror of nq_tc_plan."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("dir", "C", "N", "NT", "KC", "SBC", "a_planes", "b_planes", "PW", "PH", "CGS", "a_plane_bytes",
+                 "a_buf_bytes", "b_stage_bytes", "n_bstages", "smem_bytes", "tiles_x", "tiles_y", "tiles_n",
+                 "total_tiles")] + [("wpk_bytes", C.c_int64)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise NqError(
@@ -41,6 +49,7 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     P, I, L, F, D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     DP = C.POINTER(ConvDesc)
+    TP = C.POINTER(TcPlan)
     sigs = {
         "nq_status_string": (C.c_char_p, [I]),
         "nq_last_cuda_error": (I, []),
@@ -60,6 +69,11 @@ def _load():
         "nq_head_fwd_loss": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_head_wgrad_blocks": (I, [DP]),
         "nq_head_wgrad": (I, [DP, P, P, P, P, L, P]),
+        "nq_tc_plan_conv": (I, [DP, I, I, I, TP]),
+        "nq_tc_pack_weight": (I, [DP, TP, P, I, P, I, P, P]),
+        "nq_tc_pack_epilogue": (I, [DP, P, I, P, P, P, P]),
+        "nq_tc_conv_fwd": (I, [DP, TP, P, P, P, P, P, P, P]),
+        "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P]),
         "nq_nchw_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
         "nq_nhwc_to_nchw": (I, [P, P, I, I, I, I, I, P]),
         "nq_act_bwd_unshuffle": (I, [P, P, I, I, I, I, I, I, I, P, P]),

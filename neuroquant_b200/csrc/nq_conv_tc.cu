@@ -1,0 +1,639 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a: forward (bias + per-channel scale + up-shuffle +
+// exact-erf GELU fused in the epilogue) and data gradient (GELU' + un-shuffle fused), one kernel template.
+// Replaces F.conv2d (quant_layer.py:80) + nn.PixelShuffle + nn.GELU (quant_block.py:31-35) and the
+// dgrad half of their autograd.
+//
+// Formulation ("halo tile" implicit GEMM, no im2col buffer, no per-tap re-load):
+//   out[m][n] = sum_{tap, c} In[pix(m) + tap][c] * B[tap][c][n]          m = pixel, n = output channel
+//   * a CTA owns a 16x8-pixel output tile (GEMM-M = 128) and one N tile (<= 256 columns)
+//   * the (16+k-1) x (8+k-1) input halo of the tile is staged ONCE in shared memory as bf16, in the
+//     canonical no-swizzle K-major core-matrix order  [channel-group of 8][halo pixel][8 channels]
+//     (16 B per pixel and group).  For a fixed tap the 128 A rows are then a strided view of that
+//     buffer -- 8 consecutive x are 8 consecutive 16-byte rows (one core matrix), tile rows are
+//     PW*16 bytes apart (the descriptor's SBO), the next 8 channels are CGS bytes away (its LBO) --
+//     so every tap is just a different descriptor start address: k*k-fold reuse out of shared memory.
+//   * B (weights) streams through a ring of stages with cp.async.bulk (TMA bulk copy) + mbarrier
+//     complete_tx; it is pre-packed by nq_tc_pack_weight in exactly the order the MMA consumes it.
+//   * accumulators live in TMEM (2 x 256 fp32 columns, double buffered so the epilogue of tile i
+//     overlaps the MMAs of tile i+1); one elected thread issues tcgen05.mma.kind::f16.
+//   * fp32 accuracy from bf16 tensor cores: activations are split x = hi + lo (two bf16 planes, 16
+//     mantissa bits), weights either are exact in one bf16 plane (integer codes - zero_point, |v| <= 255,
+//     per-channel scale applied in the epilogue) or are split as well; the product is accumulated as
+//     hi*hi + lo*hi + hi*lo in fp32.
+//
+// Warp roles (384 threads): warp 0 weight-stage producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (TMEM -> registers -> global), warps 8-11 activation loaders (fp32 -> bf16 hi/lo).
+#include <cuda_bf16.h>
+
+#include "nq_common.cuh"
+
+namespace nq {
+
+constexpr int TC_THREADS = 384;
+constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
+constexpr int TC_MAX_BSTAGES = 8;
+
+struct TcParams {
+  const float* in;       // (n, h, w, C) fp32 NHWC
+  const uint8_t* wpk;    // packed bf16 weight stages
+  const float* scale;    // [N] per-column scale (fwd) or null
+  const float* bias;     // [N] (fwd) or null
+  const float* zprev;    // dgrad: (n, h, w, N) pre-activation of the previous stage, or null
+  float* out_z;          // fwd: pre-activation (may be null)
+  float* out_y;          // fwd: activated output; dgrad: dz_prev
+  int n, h, w, C;        // input grid and GEMM-K channels (C % 16 == 0)
+  int ks, pad;
+  int N, NT;             // GEMM N (multiple of 16) and its tile
+  int KC, SBC;           // channels per A unit / per B stage (multiples of 16, SBC | KC, SBC | C)
+  int a_planes, b_planes;
+  int epi;               // 0 forward, 1 dgrad
+  int rh, rw, cg, act;   // fwd: up-shuffle of this stage's output; dgrad: previous stage's (un-shuffle)
+  int tiles_x, tiles_y, tiles_n, total_tiles;
+  int PW, PH, CGS;       // halo width/height (pixels), channel-group stride (bytes)
+  int a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start >> 4, [16,30) leading-dim byte offset >> 4 (between the two 16-byte K chunks of one MMA),
+// [32,46) stride-dim byte offset >> 4 (between 8-row groups), [46,48) version = 1, [61,64) layout 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits in two bf16 planes
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float r[8];
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    r[2 * i] = x[2 * i] - __bfloat162float(h0);
+    r[2 * i + 1] = x[2 * i + 1] - __bfloat162float(h1);
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = pack_bf16x2(r[2 * i], r[2 * i + 1]);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+struct TileCoord {
+  int img, y0, x0, n0, nt;  // image, tile origin (pixels), first column, columns in this N tile
+};
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
+  TileCoord c;
+  const int tn = t % p.tiles_n;
+  int tm = t / p.tiles_n;
+  const int tx = tm % p.tiles_x;
+  tm /= p.tiles_x;
+  const int ty = tm % p.tiles_y;
+  c.img = tm / p.tiles_y;
+  c.y0 = ty * TILE_H;
+  c.x0 = tx * TILE_W;
+  c.n0 = tn * p.NT;
+  c.nt = min(p.NT, p.N - c.n0);
+  return c;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [0,256): barriers + tmem pointer; then A buffers, then B stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar0 = smem_u32(bars);
+  // barrier indices
+  const uint32_t A_FULL = bar0 + 0 * 8, A_EMPTY = bar0 + 2 * 8, T_FULL = bar0 + 4 * 8, T_EMPTY = bar0 + 6 * 8;
+  const uint32_t B_FULL = bar0 + 8 * 8, B_EMPTY = bar0 + (8 + TC_MAX_BSTAGES) * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (8 + 2 * TC_MAX_BSTAGES) * 8);
+  const uint32_t a_base = smem_u32(smem + 256);
+  const uint32_t b_base = a_base + 2 * p.a_buf_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(A_FULL + i * 8, 4);
+      mbar_init(A_EMPTY + i * 8, 1);
+      mbar_init(T_FULL + i * 8, 1);
+      mbar_init(T_EMPTY + i * 8, 4);
+    }
+    for (int i = 0; i < p.n_bstages; ++i) {
+      mbar_init(B_FULL + i * 8, 1);
+      mbar_init(B_EMPTY + i * 8, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.ks * p.ks;
+  const int ncb = (p.C + p.KC - 1) / p.KC;
+
+  if (warp == 0) {
+    // ===================== weight-stage producer (TMA bulk copies) =====================
+    if (lane == 0) {
+      const int nsb_full = p.KC / p.SBC;
+      const int stages_per_ntile = (p.C / p.SBC) * taps;
+      const size_t ntile_stride = (size_t)stages_per_ntile * p.NT * p.SBC * 2 * p.b_planes;
+      uint32_t sc = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t);
+        const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * 2 * p.b_planes;
+        const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride;
+        for (int cb = 0; cb < ncb; ++cb) {
+          const int nsb = min(nsb_full, (p.C - cb * p.KC) / p.SBC);
+          for (int tap = 0; tap < taps; ++tap)
+            for (int sb = 0; sb < nsb; ++sb, ++sc) {
+              const uint32_t s = sc % p.n_bstages, ph = (sc / p.n_bstages) & 1;
+              mbar_wait(B_EMPTY + s * 8, ph ^ 1);
+              mbar_arrive_expect_tx(B_FULL + s * 8, stage_bytes);
+              bulk_g2s(b_base + s * p.b_stage_bytes, src, stage_bytes, B_FULL + s * 8);
+              src += stage_bytes;
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t sc = 0, uc = 0, tcnt = 0;
+      const int nsb_full = p.KC / p.SBC;
+      const uint32_t a_sbo = p.PW * 16;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcnt) {
+        const TileCoord tc = tile_coord(p, t);
+        const uint32_t acc = tcnt & 1;
+        mbar_wait(T_EMPTY + acc * 8, ((tcnt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t idesc = make_idesc(tc.nt);
+        const uint32_t b_lbo = tc.nt * 16;
+        const uint32_t b_plane_bytes = tc.nt * p.SBC * 2;
+        uint32_t accum = 0;
+        for (int cb = 0; cb < ncb; ++cb, ++uc) {
+          const uint32_t abuf = uc & 1;
+          mbar_wait(A_FULL + abuf * 8, (uc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_buf = a_base + abuf * p.a_buf_bytes;
+          const int nsb = min(nsb_full, (p.C - cb * p.KC) / p.SBC);
+          for (int tap = 0; tap < taps; ++tap) {
+            const uint32_t a_tap = a_buf + (uint32_t)((tap / p.ks) * p.PW + (tap % p.ks)) * 16;
+            for (int sb = 0; sb < nsb; ++sb, ++sc) {
+              const uint32_t s = sc % p.n_bstages, ph = (sc / p.n_bstages) & 1;
+              mbar_wait(B_FULL + s * 8, ph);
+              tc_fence_after();
+              const uint32_t b_st = b_base + s * p.b_stage_bytes;
+              for (int j = 0; j < p.SBC / 16; ++j) {
+                const uint32_t a_addr = a_tap + (uint32_t)(sb * (p.SBC / 8) + 2 * j) * p.CGS;
+                const uint32_t b_addr = b_st + (uint32_t)(2 * j) * b_lbo;
+                const uint64_t a_hi = make_desc(a_addr, p.CGS, a_sbo);
+                const uint64_t b_hi = make_desc(b_addr, b_lbo, 128);
+                umma_bf16(d_tmem, a_hi, b_hi, idesc, accum);
+                accum = 1;
+                if (p.a_planes == 2) umma_bf16(d_tmem, make_desc(a_addr + p.a_plane_bytes, p.CGS, a_sbo), b_hi, idesc, 1);
+                if (p.b_planes == 2) umma_bf16(d_tmem, a_hi, make_desc(b_addr + b_plane_bytes, b_lbo, 128), idesc, 1);
+              }
+              umma_commit(B_EMPTY + s * 8);  // stage free once these MMAs have read it
+            }
+          }
+          umma_commit(A_EMPTY + abuf * 8);
+        }
+        umma_commit(T_FULL + acc * 8);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== activation loaders: fp32 NHWC -> bf16 hi/lo halo tile =====================
+    const int ltid = threadIdx.x - 8 * 32;
+    const int npix = p.PW * p.PH;
+    uint32_t uc = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(p, t);
+      const float* img = p.in + (size_t)tc.img * p.h * p.w * p.C;
+      for (int cb = 0; cb < ncb; ++cb, ++uc) {
+        const uint32_t abuf = uc & 1;
+        const int c0 = cb * p.KC;
+        const int ncg = min(p.KC, p.C - c0) >> 3;
+        mbar_wait(A_EMPTY + abuf * 8, ((uc >> 1) & 1) ^ 1);
+        uint8_t* dst = smem + 256 + (size_t)abuf * p.a_buf_bytes;
+        const int tasks = npix * ncg;
+        for (int i0 = ltid; i0 < tasks; i0 += 128 * 4) {
+          float4 va[4], vb[4];
+          int off[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 128;
+            va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            off[u] = -1;
+            if (i < tasks) {
+              const int pix = i / ncg, cgi = i - pix * ncg;
+              const int py = pix / p.PW, px = pix - py * p.PW;
+              const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
+              off[u] = cgi * p.CGS + pix * 16;
+              if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
+                const float4* src = reinterpret_cast<const float4*>(img + ((size_t)gy * p.w + gx) * p.C + c0 + cgi * 8);
+                va[u] = __ldg(src);
+                vb[u] = __ldg(src + 1);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (off[u] >= 0) {
+              uint4 hi, lo;
+              split8(va[u], vb[u], hi, lo);
+              *reinterpret_cast<uint4*>(dst + off[u]) = hi;
+              if (p.a_planes == 2) *reinterpret_cast<uint4*>(dst + p.a_plane_bytes + off[u]) = lo;
+            }
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(A_FULL + abuf * 8);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int ly = m >> 3, lx = m & 7;
+    uint32_t tcnt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcnt) {
+      const TileCoord tc = tile_coord(p, t);
+      const uint32_t acc = tcnt & 1;
+      const int y = tc.y0 + ly, x = tc.x0 + lx;
+      const bool valid = y < p.h && x < p.w;
+      mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      // per-row output bases
+      size_t row_base = 0;   // fwd: pixel (y*rh, x*rw) of the shuffled grid; dgrad: un-shuffled destination
+      size_t zrow = 0;
+      if (p.epi == 0) {
+        row_base = (((size_t)tc.img * (p.h * p.rh) + (size_t)y * p.rh) * (p.w * p.rw) + (size_t)x * p.rw) * p.cg;
+      } else {
+        const int qh = y / p.rh, si = y - qh * p.rh, qw = x / p.rw, sj = x - qw * p.rw;
+        row_base = (((size_t)tc.img * (p.h / p.rh) + qh) * (p.w / p.rw) + qw) * ((size_t)p.rh * p.rw * p.N) +
+                   (size_t)(si * p.rw + sj) * p.N;
+        zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.N;
+      }
+      // running (group, channel) of column n for the forward shuffle: n = grp * cg + c
+      int grp = 0, c = 0;
+      if (p.epi == 0) {
+        grp = tc.n0 / p.cg;
+        c = tc.n0 - grp * p.cg;
+      }
+      for (int c0 = 0; c0 < tc.nt; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int n = tc.n0 + c0 + qd * 4;
+          float4 r = make_float4(__uint_as_float(v[qd * 4 + 0]), __uint_as_float(v[qd * 4 + 1]),
+                                 __uint_as_float(v[qd * 4 + 2]), __uint_as_float(v[qd * 4 + 3]));
+          if (p.epi == 0) {
+            if (p.scale) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+              r.x *= s.x; r.y *= s.y; r.z *= s.z; r.w *= s.w;
+            }
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+            }
+            const int si = grp / p.rw, sj = grp - si * p.rw;
+            const size_t o = row_base + ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
+            if (valid) {
+              if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
+              if (p.act == 1) { r.x = gelu_f(r.x); r.y = gelu_f(r.y); r.z = gelu_f(r.z); r.w = gelu_f(r.w); }
+              *reinterpret_cast<float4*>(p.out_y + o) = r;
+            }
+            c += 4;
+            if (c >= p.cg) { c -= p.cg; ++grp; }
+          } else {
+            if (valid) {
+              if (p.zprev && p.act == 1) {
+                const float4 z = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow + n));
+                r.x *= gelu_grad_f(z.x); r.y *= gelu_grad_f(z.y); r.z *= gelu_grad_f(z.z); r.w *= gelu_grad_f(z.w);
+              }
+              *reinterpret_cast<float4*>(p.out_y + row_base + n) = r;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing into the stage order above
+//   stage layout: [plane][k-group of 8][n in tile][8 k-channels] bf16
+//   n tile t: stages cb-major, then tap, then sub-block; every stage of tile t has nt(t) columns
+// ------------------------------------------------------------------------------------------------
+struct TcPackParams {
+  const float* w;     // reference layout (cout, cin_src, k, k): codes, or de-quantised weights
+  const float* zp;    // per-cout zero point subtracted from w (integer-domain forward), or null
+  int zp_stride;      // 1: per output channel, 0: one value
+  uint8_t* out;
+  int cout, cin, cin_src, ks;
+  int rh, rw, c_grp, cg;  // packed output-channel order (up-shuffle groups)
+  int dir;                // 0 forward (K = input channels, N = packed output channels), 1 dgrad (swapped, flipped)
+  int C, N, NT, KC, SBC, b_planes;
+};
+
+__device__ __forceinline__ int unpack_cout(int np, int rh, int rw, int c_grp, int cg) {
+  // packed n' = (i*rw + j)*cg + c  ->  reference channel c*rh*rw + i*rw + j   (-1 for a pad column)
+  const int grp = np / cg, c = np - grp * cg;
+  if (c >= c_grp || grp >= rh * rw) return -1;
+  return c * rh * rw + grp;
+}
+
+__global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackParams q) {
+  const int taps = q.ks * q.ks;
+  const int tiles_n = (q.N + q.NT - 1) / q.NT;
+  const int stages_per_ntile = (q.C / q.SBC) * taps;
+  const int nsb_full = q.KC / q.SBC;
+  const int g_per_stage = q.SBC / 8;
+  // one thread per (n tile, stage, k-group, column): both planes
+  const long long per_tile_full = (long long)stages_per_ntile * g_per_stage * q.NT;
+  const long long total = per_tile_full * tiles_n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int tn = (int)(e / per_tile_full);
+    long long r = e - (long long)tn * per_tile_full;
+    const int nt = min(q.NT, q.N - tn * q.NT);
+    const int nn = (int)(r % q.NT);
+    r /= q.NT;
+    if (nn >= nt) continue;
+    const int g = (int)(r % g_per_stage);
+    const int s = (int)(r / g_per_stage);
+    // stage -> (cb, tap, sb)
+    const int full_block_stages = taps * nsb_full;
+    int cb = s / full_block_stages;
+    int rem = s - cb * full_block_stages;
+    const int ncb_full = q.C / q.KC;
+    int nsb = nsb_full;
+    if (cb >= ncb_full) {
+      cb = ncb_full;
+      rem = s - ncb_full * full_block_stages;
+      nsb = (q.C - ncb_full * q.KC) / q.SBC;
+    }
+    const int tap = rem / nsb, sb = rem - tap * nsb;
+    const int k0 = cb * q.KC + sb * q.SBC + g * 8;  // first K channel of this chunk
+    const int n = tn * q.NT + nn;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + i;
+      int co, ci, t;
+      if (q.dir == 0) {
+        co = unpack_cout(n, q.rh, q.rw, q.c_grp, q.cg);
+        ci = k;
+        t = tap;
+      } else {
+        co = unpack_cout(k, q.rh, q.rw, q.c_grp, q.cg);
+        ci = n;
+        t = taps - 1 - tap;
+      }
+      float x = 0.f;
+      if (co >= 0 && co < q.cout && ci < q.cin) {
+        x = q.w[((size_t)co * q.cin_src + ci) * taps + t];
+        if (q.zp) x -= q.zp[co * q.zp_stride];
+      }
+      v[i] = x;
+    }
+    uint4 hi, lo;
+    split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+    const size_t stage_bytes = (size_t)nt * q.SBC * 2 * q.b_planes;
+    const size_t ntile_stride = (size_t)stages_per_ntile * q.NT * q.SBC * 2 * q.b_planes;
+    uint8_t* st = q.out + (size_t)tn * ntile_stride + (size_t)s * stage_bytes;
+    const size_t o = ((size_t)g * nt + nn) * 16;
+    *reinterpret_cast<uint4*>(st + o) = hi;
+    if (q.b_planes == 2) *reinterpret_cast<uint4*>(st + (size_t)nt * q.SBC * 2 + o) = lo;
+  }
+}
+
+// per-column epilogue vectors in packed order: scale[n] = delta[co] (or 1), bias[n] = b[co] (or 0)
+__global__ void __launch_bounds__(256) tc_pack_vec_kernel(const float* __restrict__ delta, int d_stride,
+                                                          const float* __restrict__ bias, int cout, int rh, int rw,
+                                                          int c_grp, int cg, int N, float* __restrict__ scale_out,
+                                                          float* __restrict__ bias_out) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const int co = unpack_cout(n, rh, rw, c_grp, cg);
+    const bool ok = co >= 0 && co < cout;
+    if (scale_out) scale_out[n] = (ok && delta) ? delta[co * d_stride] : 1.0f;
+    if (bias_out) bias_out[n] = (ok && bias) ? bias[co] : 0.0f;
+  }
+}
+
+int check_conv_desc(const nq_conv_desc* d);
+
+static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes, nq_tc_plan* pl) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || (dir != 0 && dir != 1) || a_planes < 1 || a_planes > 2 || b_planes < 1 || b_planes > 2) return NQ_ERR_BAD_ARG;
+  const int nout_p = d->rh * d->rw * d->cg;
+  const int C = dir == 0 ? d->cin_p : nout_p;
+  const int N = dir == 0 ? nout_p : d->cin_p;
+  if (C % 16 || N % 16 || d->ksize > 7) return NQ_ERR_BAD_SHAPE;
+  pl->dir = dir;
+  pl->C = C;
+  pl->N = N;
+  pl->a_planes = a_planes;
+  pl->b_planes = b_planes;
+  pl->NT = N < 256 ? N : 256;
+  // B stage: the largest channel count of {64,48,32,16} that divides C and keeps a stage <= 24 KB
+  int sbc = 16;
+  const int cand[4] = {64, 48, 32, 16};
+  for (int i = 0; i < 4; ++i)
+    if (C % cand[i] == 0 && pl->NT * cand[i] * 2 * b_planes <= 24 * 1024) { sbc = cand[i]; break; }
+  pl->SBC = sbc;
+  pl->KC = sbc * (64 / sbc > 0 ? 64 / sbc : 1);  // largest multiple of SBC <= 64 (48 stays 48)
+  if (pl->KC > C) pl->KC = C;
+  pl->PW = TILE_W + d->ksize - 1;
+  pl->PH = TILE_H + d->ksize - 1;
+  int npix = pl->PW * pl->PH;
+  int cgs16 = npix;  // channel-group stride in 16-byte units, forced to 1 mod 8 (conflict-free loader stores)
+  while (cgs16 % 8 != 1) ++cgs16;
+  pl->CGS = cgs16 * 16;
+  pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
+  pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
+  pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes;
+  const int budget = 227 * 1024 - 256 - 2 * pl->a_buf_bytes;
+  int nst = budget / pl->b_stage_bytes;
+  if (nst > TC_MAX_BSTAGES) nst = TC_MAX_BSTAGES;
+  if (nst < 2) return NQ_ERR_UNSUPPORTED;
+  pl->n_bstages = nst;
+  pl->smem_bytes = 256 + 2 * pl->a_buf_bytes + nst * pl->b_stage_bytes;
+  pl->tiles_x = (d->w + TILE_W - 1) / TILE_W;
+  pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
+  pl->tiles_n = (N + pl->NT - 1) / pl->NT;
+  pl->total_tiles = pl->tiles_x * pl->tiles_y * d->n * pl->tiles_n;
+  const int taps = d->ksize * d->ksize;
+  // bytes of the packed weight buffer: full-width stages for all but the last N tile
+  const long long stages = (long long)(C / sbc) * taps;
+  const int last_nt = N - (pl->tiles_n - 1) * pl->NT;
+  pl->wpk_bytes = stages * sbc * 2 * b_planes * ((long long)(pl->tiles_n - 1) * pl->NT + last_nt);
+  return NQ_OK;
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+extern "C" int nq_tc_plan_conv(const nq_conv_desc* d, int dir, int a_planes, int b_planes, nq_tc_plan* plan) {
+  return fill_plan(d, dir, a_planes, b_planes, plan);
+}
+
+extern "C" int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* pl, const float* w_ref, int cin_src,
+                                 const float* zero_point, int zp_stride, void* wpk, void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || !w_ref || !wpk || cin_src < d->cin) return NQ_ERR_BAD_ARG;
+  TcPackParams q{};
+  q.w = w_ref; q.zp = zero_point; q.zp_stride = zp_stride; q.out = reinterpret_cast<uint8_t*>(wpk);
+  q.cout = d->cout; q.cin = d->cin; q.cin_src = cin_src; q.ks = d->ksize;
+  q.rh = d->rh; q.rw = d->rw; q.c_grp = d->c_grp; q.cg = d->cg;
+  q.dir = pl->dir; q.C = pl->C; q.N = pl->N; q.NT = pl->NT; q.KC = pl->KC; q.SBC = pl->SBC; q.b_planes = pl->b_planes;
+  const long long total = (long long)(pl->C / pl->SBC) * d->ksize * d->ksize * (pl->SBC / 8) * pl->NT * pl->tiles_n;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  tc_pack_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(q);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, int d_stride, const float* bias_ref,
+                                   float* scale_packed, float* bias_packed, void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  const int N = d->rh * d->rw * d->cg;
+  tc_pack_vec_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(delta, d_stride, bias_ref, d->cout, d->rh, d->rw,
+                                                                     d->c_grp, d->cg, N, scale_packed, bias_packed);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, cudaStream_t s) {
+  p.n = d->n; p.h = d->h; p.w = d->w; p.C = pl->C; p.ks = d->ksize; p.pad = d->ksize / 2;
+  p.N = pl->N; p.NT = pl->NT; p.KC = pl->KC; p.SBC = pl->SBC; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
+  p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_n = pl->tiles_n; p.total_tiles = pl->total_tiles;
+  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS;
+  p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
+  p.n_bstages = pl->n_bstages;
+  NQ_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int grid = pl->total_tiles < sm_count() ? pl->total_tiles : sm_count();
+  conv_tc_kernel<<<grid, TC_THREADS, pl->smem_bytes, s>>>(p);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* pl, const float* x, const void* wpk,
+                              const float* scale_packed, const float* bias_packed, float* z, float* y, void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || pl->dir != 0 || !x || !wpk || !y) return NQ_ERR_BAD_ARG;
+  TcParams p{};
+  p.in = x; p.wpk = reinterpret_cast<const uint8_t*>(wpk); p.scale = scale_packed; p.bias = bias_packed;
+  p.zprev = nullptr; p.out_z = z; p.out_y = y; p.epi = 0;
+  p.rh = d->rh; p.rw = d->rw; p.cg = d->cg; p.act = d->act;
+  return launch_tc(d, pl, p, as_stream(stream));
+}
+
+extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, const float* dz, const void* wpk_t,
+                                const float* z_prev, int prev_rh, int prev_rw, int prev_act, float* dz_prev,
+                                void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || pl->dir != 1 || !dz || !wpk_t || !dz_prev || prev_rh <= 0 || prev_rw <= 0) return NQ_ERR_BAD_ARG;
+  if (d->h % prev_rh || d->w % prev_rw) return NQ_ERR_BAD_SHAPE;
+  if (prev_act != 0 && prev_act != 1) return NQ_ERR_BAD_ARG;
+  TcParams p{};
+  p.in = dz; p.wpk = reinterpret_cast<const uint8_t*>(wpk_t); p.scale = nullptr; p.bias = nullptr;
+  p.zprev = z_prev; p.out_z = nullptr; p.out_y = dz_prev; p.epi = 1;
+  p.rh = prev_rh; p.rw = prev_rw; p.cg = d->cin_p; p.act = prev_act;
+  return launch_tc(d, pl, p, as_stream(stream));
+}

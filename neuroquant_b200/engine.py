@@ -24,6 +24,7 @@ There is no PyTorch fallback: every step is a kernel of libnq_sm100.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -36,8 +37,12 @@ _ACT = {"none": 0, "gelu": 1}
 _HEAD = {"tanh": 0, "sigmoid": 1}
 
 
+def _pad(c: int, m: int) -> int:
+    return (c + m - 1) // m * m
+
+
 def _pad4(c: int) -> int:
-    return (c + 3) // 4 * 4
+    return _pad(c, 4)
 
 
 def next_pow2(n: int) -> int:
@@ -156,11 +161,15 @@ class _Plan:
         self.z: List[Optional[torch.Tensor]] = []  # pre-activations (train only, act != none)
         self.dz: List[Optional[torch.Tensor]] = []
         h, w = h0, w0
-        cin_p = _pad4(eng.geoms[0].cin)
+        # channel padding: 16 for the input of a tensor-core stage (two 8-channel bf16 chunks per MMA),
+        # 8 for the head's input (fp32 float4 pairs), 4 on the SIMT path
+        last = len(eng.geoms) - 1
+        in_pad = [(16 if eng.use_tc else 4) if i < last else (8 if eng.use_tc else 4) for i in range(last + 1)]
+        cin_p = _pad(eng.geoms[0].cin, in_pad[0])
         self.x.append(torch.zeros(n, h, w, cin_p, device=dev))
         for i, g in enumerate(eng.geoms):
-            head = i == len(eng.geoms) - 1
-            cg = 4 if head else _pad4(g.c_grp)
+            head = i == last
+            cg = 4 if head else _pad(g.c_grp, in_pad[i + 1])
             d = L.ConvDesc(n, h, w, g.cin, cin_p, g.k, g.cout, g.rh, g.rw, g.c_grp, cg, 0 if head else _ACT[g.act])
             self.desc.append(d)
             if train:
@@ -174,6 +183,20 @@ class _Plan:
         self.H, self.W = h, w
         self.img = torch.empty(n, 3, h, w, device=dev)
         self.loss = torch.zeros(1, device=dev)
+        # tensor-core plans: forward with 1 or 2 weight planes, data gradient
+        self.tc_fwd = {}
+        self.tc_dgrad = []
+        if eng.use_tc:
+            for i in range(last):
+                for bpl in (1, 2):
+                    pl = L.TcPlan()
+                    L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[i]), 0, eng.fwd_a_planes, bpl, C.byref(pl)), "nq_tc_plan_conv")
+                    self.tc_fwd[(i, bpl)] = pl
+                pl = L.TcPlan()
+                if train and i > 0:
+                    L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[i]), 1, eng.bwd_a_planes, eng.bwd_b_planes, C.byref(pl)),
+                            "nq_tc_plan_conv")
+                self.tc_dgrad.append(pl)
 
 
 class DecoderEngine:
@@ -194,6 +217,13 @@ class DecoderEngine:
         self.mode = "uaq"
         self.soft_w = False
         self.soft_b = False
+        # Convolution path: tcgen05 tensor cores (default) or the exact-fp32 FFMA kernels (NQ_CONV=simt).
+        # Both are CUDA kernels of libnq_sm100.so; neither is a fallback for a missing library.
+        self.use_tc = os.environ.get("NQ_CONV", "tc").lower() != "simt"
+        # bf16 planes per operand (1 = hi only, 2 = hi + lo): forward activations, backward gradients/weights
+        self.fwd_a_planes = int(os.environ.get("NQ_FWD_A_PLANES", "2"))
+        self.bwd_a_planes = int(os.environ.get("NQ_BWD_A_PLANES", "2"))
+        self.bwd_b_planes = int(os.environ.get("NQ_BWD_B_PLANES", "2"))
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
         self._weights_valid = False
@@ -203,7 +233,7 @@ class DecoderEngine:
         self.sm = L.lib.nq_sm_count()
         self.launches = 0  # kernels launched through the C ABI (bench.py reports it)
         self._prof = None  # list of (name, flops, start_event, stop_event) while kernel_profile() runs
-        self.dtype_name = "f32"
+        self.dtype_name = "bf16x2 split operands, fp32 accumulate (tcgen05)" if self.use_tc else "f32"
 
     # ------------------------------------------------------------------ profiling
     def _run(self, name: str, d, fn, *args) -> int:
@@ -280,13 +310,29 @@ class DecoderEngine:
         if self._packed is not None:
             return
         self._packed = []
-        for s, d in zip(self.stages, p.desc):
-            wk = torch.zeros(d.kdim, d.nout_p, device=self.device)
-            wt = torch.zeros(d.ksize * d.ksize * d.nout_p, d.cin_p, device=self.device)
+        self._tcw = []  # per non-head stage: (wpk_fwd bytes, wpk_dgrad bytes, scale_packed)
+        last = len(self.stages) - 1
+        for i, (s, d) in enumerate(zip(self.stages, p.desc)):
+            tc = self.use_tc and i < last
+            wk = None if tc else torch.zeros(d.kdim, d.nout_p, device=self.device)
+            wt = None if tc else torch.zeros(d.ksize * d.ksize * d.nout_p, d.cin_p, device=self.device)
             bp = torch.zeros(d.nout_p, device=self.device)
             deq_w = torch.empty_like(s.w_src)
             deq_b = torch.empty_like(s.bias)
             self._packed.append((wk, wt, bp, deq_w, deq_b))
+            if tc:
+                nb_f = p.tc_fwd[(i, 2)].wpk_bytes
+                # the dgrad buffer is sized from a worst-case (2-plane) plan so that eval-only plans can share it
+                pl = L.TcPlan()
+                nb_d = 0
+                if i > 0:
+                    L.check(L.lib.nq_tc_plan_conv(C.byref(d), 1, 2, 2, C.byref(pl)), "nq_tc_plan_conv")
+                    nb_d = pl.wpk_bytes
+                self._tcw.append((torch.zeros(nb_f, dtype=torch.uint8, device=self.device),
+                                  torch.zeros(max(nb_d, 16), dtype=torch.uint8, device=self.device),
+                                  torch.ones(d.nout_p, device=self.device)))
+            else:
+                self._tcw.append(None)
 
     # ------------------------------------------------------------------ weights
     def prepare_weights(self, p: _Plan, need_wt: bool, reg_b: Optional[float] = None):
@@ -297,7 +343,9 @@ class DecoderEngine:
         st = L.stream()
         if reg_b is not None:
             self.reg_sum.zero_()
-        for s, d, (wk, wt, bp, deq_w, deq_b) in zip(self.stages, p.desc, self._packed):
+        if not hasattr(self, "_fwd_bpl"):
+            self._fwd_bpl = [2] * len(self.stages)
+        for i, (s, d, (wk, wt, bp, deq_w, deq_b)) in enumerate(zip(self.stages, p.desc, self._packed)):
             if self.mode == "off":
                 w_for_conv, b_for_conv, cin_src = s.weight, s.bias, s.geom.cin
             else:
@@ -313,9 +361,36 @@ class DecoderEngine:
                     L.fwht_channel(deq_w, out=deq_w)
                     self.launches += 1
                 w_for_conv, b_for_conv, cin_src = deq_w, deq_b, s.cin_src
-            L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(w_for_conv), cin_src, L.ptr(b_for_conv), L.ptr(wk),
-                                         L.ptr(wt) if need_wt else None, L.ptr(bp), st), "nq_pack_weight")
-            self.launches += 1
+            if self._tcw[i] is None:
+                L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(w_for_conv), cin_src, L.ptr(b_for_conv), L.ptr(wk),
+                                             L.ptr(wt) if need_wt else None, L.ptr(bp), st), "nq_pack_weight")
+                self.launches += 1
+                continue
+            wpk_f, wpk_d, scale_p = self._tcw[i]
+            # forward operand: integer weights (codes - zero_point), exact in ONE bf16 plane, whenever the
+            # codes are integers and are what the conv multiplies (no rotation in between); the step size
+            # is applied per output channel in the epilogue.  Otherwise the de-quantised fp32 weights,
+            # split into two bf16 planes.
+            integer = self.mode != "off" and not s.hadamard
+            exact1 = integer and (self.mode == "uaq" or not self.soft_w)
+            bpl = 1 if exact1 else 2
+            self._fwd_bpl[i] = bpl
+            if integer:
+                ds = 1 if s.delta_w.numel() > 1 else 0
+                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_fwd[(i, bpl)]), L.ptr(s.codes_w), s.cin_src,
+                                                L.ptr(s.zp_w), ds, wpk_f.data_ptr(), st), "nq_tc_pack_weight")
+                L.check(L.lib.nq_tc_pack_epilogue(C.byref(d), L.ptr(s.delta_w), ds, L.ptr(b_for_conv), L.ptr(scale_p), L.ptr(bp), st),
+                        "nq_tc_pack_epilogue")
+            else:
+                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_fwd[(i, bpl)]), L.ptr(w_for_conv), cin_src,
+                                                None, 0, wpk_f.data_ptr(), st), "nq_tc_pack_weight")
+                L.check(L.lib.nq_tc_pack_epilogue(C.byref(d), None, 0, L.ptr(b_for_conv), L.ptr(scale_p), L.ptr(bp), st),
+                        "nq_tc_pack_epilogue")
+            self.launches += 2
+            if need_wt and i > 0:
+                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_dgrad[i]), L.ptr(w_for_conv), cin_src, None, 0,
+                                                wpk_d.data_ptr(), st), "nq_tc_pack_weight")
+                self.launches += 1
         self._weights_valid = True
         self._wt_valid = need_wt
 
@@ -347,8 +422,14 @@ class DecoderEngine:
         for i in range(last):
             wk, _, bp, _, _ = self._packed[i]
             z = p.z[i] if train else None
-            L.check(self._run(f"conv_fwd[{i}]", p.desc[i], L.lib.nq_conv_fwd, C.byref(p.desc[i]), L.ptr(p.x[i]), L.ptr(wk),
-                              L.ptr(bp), L.ptr(z), L.ptr(p.x[i + 1]), st), "nq_conv_fwd")
+            if self._tcw[i] is None:
+                L.check(self._run(f"conv_fwd[{i}]", p.desc[i], L.lib.nq_conv_fwd, C.byref(p.desc[i]), L.ptr(p.x[i]), L.ptr(wk),
+                                  L.ptr(bp), L.ptr(z), L.ptr(p.x[i + 1]), st), "nq_conv_fwd")
+            else:
+                wpk_f, _, scale_p = self._tcw[i]
+                L.check(self._run(f"conv_fwd[{i}]", p.desc[i], L.lib.nq_tc_conv_fwd, C.byref(p.desc[i]),
+                                  C.byref(p.tc_fwd[(i, self._fwd_bpl[i])]), L.ptr(p.x[i]), wpk_f.data_ptr(), L.ptr(scale_p),
+                                  L.ptr(bp), L.ptr(z), L.ptr(p.x[i + 1]), st), "nq_tc_conv_fwd")
             self.launches += 1
         wk, _, bp, _, _ = self._packed[last]
         if target is not None:
@@ -429,8 +510,14 @@ class DecoderEngine:
                 self.launches += 2 if sp > 1 else 1
             if i > 0:
                 g_prev = self.geoms[i - 1]
-                L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
-                                  L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st), "nq_conv_dgrad")
+                if self._tcw[i] is None:
+                    L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
+                                      L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st),
+                            "nq_conv_dgrad")
+                else:
+                    L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(p.tc_dgrad[i]),
+                                      L.ptr(p.dz[i]), self._tcw[i][1].data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw,
+                                      _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st), "nq_tc_conv_dgrad")
                 self.launches += 1
             s = self.stages[i]
             gw, gb = views[i]

@@ -174,6 +174,13 @@ def test_loss_psnr_dot(nq):
 
 
 # ------------------------------------------------------------------------------------------ decoder engine
+@pytest.fixture(params=["tc", "simt"])
+def conv_path(request, monkeypatch):
+    """Both convolution paths of the library: tcgen05 tensor cores (default) and exact-fp32 FFMA."""
+    monkeypatch.setenv("NQ_CONV", request.param)
+    return request.param
+
+
 def make_engine(nq, tag, mode="uaq"):
     g, arch, cfg, stages = case_stages(tag)
     geoms = nq.geometry_from_cfg(cfg, arch)
@@ -185,10 +192,11 @@ def make_engine(nq, tag, mode="uaq"):
 
 
 @pytest.mark.parametrize("tag", list(CASES))
-def test_decode_golden(nq, tag):
+def test_decode_golden(nq, tag, conv_path):
     """FP decode and nearest-rounded quantised decode against the reference's outputs; scales and
     perturbation-free codes bit-exact."""
     g, arch, cfg, stages, eng = make_engine(nq, tag, "off")
+    assert eng.use_tc == (conv_path == "tc")
     cali = dev(t(g["cali"]))
     out = eng.forward(cali[:2]).cpu()
     assert np.abs(out.numpy() - g["fp_out"]).max() < 1e-5
@@ -240,7 +248,7 @@ def oracle_grads(stages, g, soft, batch=slice(0, 2)):
 
 @pytest.mark.parametrize("tag", list(CASES))
 @pytest.mark.parametrize("soft", [True, False])
-def test_backward_matches_oracle_autograd(nq, tag, soft):
+def test_backward_matches_oracle_autograd(nq, tag, soft, conv_path):
     """forward + loss + backward + quantiser Jacobian vs autograd of the oracle.  Tolerance: 2e-4 of
     each tensor's gradient scale (fp32 sums in a different order through 7 convolutions)."""
     g, arch, cfg, stages, eng = make_engine(nq, tag, "uaq")
@@ -265,7 +273,7 @@ def test_backward_matches_oracle_autograd(nq, tag, soft):
 
 
 @pytest.mark.parametrize("tag", list(CASES))
-def test_calibration_golden(nq, tag):
+def test_calibration_golden(nq, tag, conv_path):
     """80 iterations (4 step-size + 76 AdaRound) in the reference's injected batch order: same
     acceptance as the oracle's own pin (tests/test_oracle_golden.py::test_calibration_golden)."""
     g, arch, cfg, stages, eng = make_engine(nq, tag, "uaq")
