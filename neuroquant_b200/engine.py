@@ -150,6 +150,27 @@ class QuantStage:
         self.alpha_b = L.adaround_init_alpha(self.bias, self.delta_b)
 
 
+def stage_descs(geoms: Sequence[StageGeom], n: int, h0: int, w0: int, use_tc: bool) -> List[L.ConvDesc]:
+    """nq_conv_desc of every stage for a batch of n embeddings on an h0 x w0 grid.  Channel padding:
+    16 for the input of a tensor-core stage (two 8-channel bf16 chunks per MMA), 8 for the head's input
+    (pairs of fp32 float4), 4 on the FFMA path; a tensor-core stage's GEMM-N (rh*rw*cg) must be a
+    multiple of 16 as well."""
+    last = len(geoms) - 1
+    in_pad = [(16 if use_tc else 4) if i < last else (8 if use_tc else 4) for i in range(last + 1)]
+    out = []
+    h, w = h0, w0
+    cin_p = _pad(geoms[0].cin, in_pad[0])
+    for i, g in enumerate(geoms):
+        head = i == last
+        cg = 4 if head else _pad(g.c_grp, in_pad[i + 1])
+        if use_tc and not head and (g.rh * g.rw * cg) % 16:
+            cg = _pad(g.c_grp, 16)
+        out.append(L.ConvDesc(n, h, w, g.cin, cin_p, g.k, g.cout, g.rh, g.rw, g.c_grp, cg, 0 if head else _ACT[g.act]))
+        h, w = h * g.rh, w * g.rw
+        cin_p = cg
+    return out
+
+
 class _Plan:
     """Buffers of one (batch, grid) shape."""
 
@@ -160,26 +181,18 @@ class _Plan:
         self.x: List[torch.Tensor] = []  # stage inputs (x[i+1] is stage i's activated output)
         self.z: List[Optional[torch.Tensor]] = []  # pre-activations (train only, act != none)
         self.dz: List[Optional[torch.Tensor]] = []
-        h, w = h0, w0
-        # channel padding: 16 for the input of a tensor-core stage (two 8-channel bf16 chunks per MMA),
-        # 8 for the head's input (fp32 float4 pairs), 4 on the SIMT path
         last = len(eng.geoms) - 1
-        in_pad = [(16 if eng.use_tc else 4) if i < last else (8 if eng.use_tc else 4) for i in range(last + 1)]
-        cin_p = _pad(eng.geoms[0].cin, in_pad[0])
-        self.x.append(torch.zeros(n, h, w, cin_p, device=dev))
-        for i, g in enumerate(eng.geoms):
-            head = i == last
-            cg = 4 if head else _pad(g.c_grp, in_pad[i + 1])
-            d = L.ConvDesc(n, h, w, g.cin, cin_p, g.k, g.cout, g.rh, g.rw, g.c_grp, cg, 0 if head else _ACT[g.act])
-            self.desc.append(d)
+        self.desc = stage_descs(eng.geoms, n, h0, w0, eng.use_tc)
+        self.x.append(torch.zeros(n, h0, w0, self.desc[0].cin_p, device=dev))
+        h, w = h0, w0
+        for i, (g, d) in enumerate(zip(eng.geoms, self.desc)):
             if train:
                 self.dz.append(torch.empty(n, h, w, d.nout_p, device=dev))
-            if head:
+            if i == last:
                 break
             h, w = h * g.rh, w * g.rw
-            self.x.append(torch.empty(n, h, w, cg, device=dev))
-            self.z.append(torch.empty(n, h, w, cg, device=dev) if (train and g.act != "none") else None)
-            cin_p = cg
+            self.x.append(torch.empty(n, h, w, d.cg, device=dev))
+            self.z.append(torch.empty(n, h, w, d.cg, device=dev) if (train and g.act != "none") else None)
         self.H, self.W = h, w
         self.img = torch.empty(n, 3, h, w, device=dev)
         self.loss = torch.zeros(1, device=dev)

@@ -59,3 +59,33 @@ def test_host_logic_geometry_and_schedule():
     assert (geo[0].cout, geo[0].rh, geo[0].rw) == (1160, 2, 4)
     td = nq.LinearTempDecay(21000, rel_start_decay=0.2, start_b=20, end_b=2)
     assert f"{td(4500):.2f}" == "19.68" and f"{td(19500):.2f}" == "3.61"  # reference log lines
+
+
+def test_tc_plans_fit_for_every_workload():
+    """nq_tc_plan_conv is pure host arithmetic: every stage of every named workload (and the tiny
+    golden nets) gets a tensor-core plan within the 227 KB shared-memory budget, >= 2 weight stages."""
+    import ctypes as C
+    import neuroquant_b200 as nq
+    from neuroquant_b200 import _lib as L
+    from neuroquant_b200.engine import stage_descs
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape
+    from tests.helpers import CASES
+    cases = [(a, c, embed_shape(c, a)) for a, c in WORKLOADS.values()]
+    cases += [(a, c, (None, 2, 4) if a == "hnerv" else (None, 1, 1)) for a, c in CASES.values()]
+    for arch, cfg, (_, h0, w0) in cases:
+        geo = nq.geometry_from_cfg(cfg, arch)
+        descs = stage_descs(geo, 2, h0, w0, True)
+        for i, d in enumerate(descs[:-1]):
+            assert d.cin_p % 16 == 0 and d.nout_p % 16 == 0
+            for direction, ap, bp in ((0, 2, 1), (0, 2, 2), (1, 2, 2), (1, 1, 1)):
+                if direction == 1 and i == 0:
+                    continue
+                pl = L.TcPlan()
+                st = L.lib.nq_tc_plan_conv(C.byref(d), direction, ap, bp, C.byref(pl))
+                assert st == 0, (arch, i, direction, st)
+                assert pl.smem_bytes <= 227 * 1024 and pl.n_bstages >= 2
+                assert pl.C % pl.SBC == 0 and pl.KC % pl.SBC == 0 and pl.SBC % 16 == 0
+                assert pl.NT % 16 == 0 and pl.NT <= 256 and pl.N % 16 == 0
+                assert pl.total_tiles == pl.tiles_x * pl.tiles_y * pl.tiles_n * 2
+                assert (pl.CGS // 16) % 8 == 1 and pl.CGS >= pl.PW * pl.PH * 16
+        assert descs[-1].cin_p % 4 == 0
