@@ -217,6 +217,19 @@ int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* plan, const float* x
 int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* plan, const float* dz, const void* wpk_t,
                      const float* z_prev, int prev_rh, int prev_rw, int prev_act, float* dz_prev, void* stream);
 
+/* Weight + bias gradient on the tensor cores; output contract identical to nq_conv_wgrad (dwk
+ * [(kdim + 4)][nout_p], bias gradient in row kdim).  cin_p % 8 == 0, rh*rw*cg % 16 == 0. */
+typedef struct nq_tc_wgrad_plan {
+  int32_t C, N, a_planes, b_planes;
+  int32_t ncg, G, MB, NC, nsplits, TR;
+  int32_t CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf, smem_bytes;
+  int32_t tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
+  int64_t workspace_floats;    /* partial-gradient workspace the caller provides */
+} nq_tc_wgrad_plan;
+int nq_tc_plan_wgrad(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc_wgrad_plan* plan);
+int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* plan, const float* x, const float* dz,
+                     float* dwk, float* workspace, int64_t workspace_floats, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Layout edges and reductions
  * ------------------------------------------------------------------------------------------------ */

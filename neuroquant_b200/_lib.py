@@ -41,6 +41,14 @@ class TcPlan(C.Structure):
                  "total_tiles")] + [("wpk_bytes", C.c_int64)]
 
 
+class TcWgradPlan(C.Structure):
+    """Mirror of nq_tc_wgrad_plan."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("C", "N", "a_planes", "b_planes", "ncg", "G", "MB", "NC", "nsplits", "TR", "CGS_A", "CGS_B",
+                 "a_plane_bytes", "b_plane_bytes", "buf_bytes", "nbuf", "smem_bytes", "tiles_x", "tiles_y",
+                 "tiles_total", "psplits", "tiles_per_split")] + [("workspace_floats", C.c_int64)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise NqError(
@@ -74,6 +82,8 @@ def _load():
         "nq_tc_pack_epilogue": (I, [DP, P, I, P, P, P, P]),
         "nq_tc_conv_fwd": (I, [DP, TP, P, P, P, P, P, P, P]),
         "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P]),
+        "nq_tc_plan_wgrad": (I, [DP, I, I, C.POINTER(TcWgradPlan)]),
+        "nq_tc_conv_wgrad": (I, [DP, C.POINTER(TcWgradPlan), P, P, P, P, L, P]),
         "nq_nchw_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
         "nq_nhwc_to_nchw": (I, [P, P, I, I, I, I, I, P]),
         "nq_act_bwd_unshuffle": (I, [P, P, I, I, I, I, I, I, I, P, P]),

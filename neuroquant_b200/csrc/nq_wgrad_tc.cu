@@ -1,0 +1,376 @@
+// tcgen05 / TMEM weight (+ bias) gradient of a stride-1 "same" convolution, NHWC fp32 in, fp32 out.
+// Replaces the wgrad half of autograd(F.conv2d) (quant_layer.py:80) inside the calibration loop
+// (calib_model.py:160-162, :221-223).
+//
+//   dW[(kh,kw)][ci][n'] = sum_pixels X[pixel + (kh,kw)][ci] * dZ[pixel][n']        (+ db[n'] = sum dZ)
+//
+// The reduction runs over pixels, so pixels are the MMA K dimension and both operands are "MN-major"
+// (channels contiguous) -- which NHWC gives for free: an 8-channel group of 8 consecutive x positions is
+// exactly one 128-byte no-swizzle core matrix.  Mapping:
+//   * a CTA owns one kernel row kh, one slice of the output channels n' and a contiguous range of
+//     16-pixel-wide x TR-row pixel tiles; its accumulators stay in TMEM for the whole range
+//     (persistent split-K), then are written once as a partial dW and summed in a fixed order
+//   * A (GEMM M) = shifted input: rows (kw, channel group, 8 channels).  The ks horizontal shifts are
+//     materialised as ks copies of the 16-pixel row segment in shared memory ([kw][group][row][x][8]),
+//     which makes the 8-row groups uniformly strided, so M = 128 covers 16 (kw, group) pairs per MMA
+//   * one extra A group holds the constant 1 in channel 0: its accumulator row is the bias gradient
+//   * B (GEMM N) = dZ tile [group][row][x][8]; K = 16 pixels = one row segment per MMA
+//   * operands are bf16 hi (+ lo) planes of the fp32 tensors, accumulation fp32
+#include <cuda_bf16.h>
+
+#include "nq_common.cuh"
+
+namespace nq {
+
+constexpr int WG_THREADS = 384;
+constexpr int WG_TW = 16;  // pixels per MMA K step
+
+struct WgParams {
+  const float* x;   // (n, h, w, C)
+  const float* dz;  // (n, h, w, N)
+  float* ws;        // [psplits][(ks*ks*C + 4)][N] partial gradients (bias row at ks*ks*C)
+  int n, h, w, C, N, ks, pad;
+  int ncg, G, MB;   // channel groups, (kw, group) pairs, 128-row blocks
+  int NC, nsplits;  // output columns per CTA
+  int TR;           // tile rows
+  int tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
+  int a_planes, b_planes;
+  int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
+};
+
+// ---- PTX helpers (same conventions as nq_conv_tc.cu) ----
+__device__ __forceinline__ uint32_t wsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void wbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void wbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t wdesc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void wmma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void wcommit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void wsplit8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t bar0 = wsmem_u32(smem);
+  const uint32_t FULL = bar0, EMPTY = bar0 + 4 * 8, DONE = bar0 + 8 * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 9 * 8);
+  uint8_t* bufs = smem + 128;
+  const uint32_t buf0 = wsmem_u32(bufs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // block -> (pixel split, column split, kernel row)
+  int b = blockIdx.x;
+  const int kh = b % p.ks;
+  b /= p.ks;
+  const int nsplit = b % p.nsplits;
+  const int psplit = b / p.nsplits;
+  const int n0 = nsplit * p.NC;
+  const int nc = min(p.NC, p.N - n0);
+  const int t_begin = psplit * p.tiles_per_split;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nbuf; ++i) {
+      wbar_init(FULL + i * 8, 8);
+      wbar_init(EMPTY + i * 8, 1);
+    }
+    wbar_init(DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // constant part of every A buffer: the "ones" group (bias gradient) and zeroed tail groups
+  {
+    const int tail_groups = p.MB * 16 - p.G;  // >= 1
+    const int per_group16 = p.TR * WG_TW;     // 16-byte units per group
+    for (int bi = 0; bi < p.nbuf; ++bi)
+      for (int pl = 0; pl < p.a_planes; ++pl) {
+        uint8_t* base = bufs + (size_t)bi * p.buf_bytes + (size_t)pl * p.a_plane_bytes;
+        for (int i = threadIdx.x; i < tail_groups * per_group16; i += WG_THREADS) {
+          const int g = p.G + i / per_group16, u = i % per_group16;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (g == p.G && pl == 0) v.x = 0x3F80u;  // bf16 1.0 in channel 0
+          *reinterpret_cast<uint4*>(base + (size_t)g * p.CGS_A + (size_t)u * 16) = v;
+        }
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128, N = nc
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      uint32_t it = 0, accum = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const uint32_t bi = it % p.nbuf, ph = (it / p.nbuf) & 1;
+        wbar_wait(FULL + bi * 8, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_buf = buf0 + bi * p.buf_bytes;
+        const uint32_t b_buf = a_buf + p.a_planes * p.a_plane_bytes;
+        for (int r = 0; r < p.TR; ++r) {
+          const uint64_t b_hi = wdesc(b_buf + r * (WG_TW * 16), 128, p.CGS_B);
+          const uint64_t b_lo = wdesc(b_buf + p.b_plane_bytes + r * (WG_TW * 16), 128, p.CGS_B);
+          for (int mb = 0; mb < p.MB; ++mb) {
+            const uint32_t a_addr = a_buf + mb * 16 * p.CGS_A + r * (WG_TW * 16);
+            const uint64_t a_hi = wdesc(a_addr, 128, p.CGS_A);
+            const uint32_t d = tmem_base + mb * p.NC;
+            wmma(d, a_hi, b_hi, idesc, accum);
+            if (p.a_planes == 2) wmma(d, wdesc(a_addr + p.a_plane_bytes, 128, p.CGS_A), b_hi, idesc, 1);
+            if (p.b_planes == 2) wmma(d, a_hi, b_lo, idesc, 1);
+          }
+          accum = 1;
+        }
+        wcommit(EMPTY + bi * 8);
+      }
+      wcommit(DONE);
+    }
+  } else if (warp >= 4) {
+    // ===================== loaders (8 warps): fp32 NHWC -> bf16 planes =====================
+    const int ltid = threadIdx.x - 4 * 32;
+    const int span = WG_TW + p.ks - 1;  // source pixels per row that feed the ks shifted copies
+    const int a_tasks = p.TR * span * p.ncg;
+    const int ncg_b = nc >> 3;
+    const int b_tasks = p.TR * WG_TW * ncg_b;
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t bi = it % p.nbuf, ph = (it / p.nbuf) & 1;
+      int tt = t;
+      const int tx = tt % p.tiles_x;
+      tt /= p.tiles_x;
+      const int ty = tt % p.tiles_y;
+      const int img = tt / p.tiles_y;
+      const int y0 = ty * p.TR, x0 = tx * WG_TW;
+      wbar_wait(EMPTY + bi * 8, ph ^ 1);
+      uint8_t* a_dst = bufs + (size_t)bi * p.buf_bytes;
+      uint8_t* b_dst = a_dst + (size_t)p.a_planes * p.a_plane_bytes;
+      // ---- shifted input copies
+      for (int i = ltid; i < a_tasks; i += 256) {
+        const int cg = i % p.ncg;
+        const int pj = i / p.ncg;
+        const int j = pj % span, r = pj / span;
+        const int gy = y0 + r + kh - p.pad, gx = x0 + j - p.pad;
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && (y0 + r) < p.h) {
+          const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)img * p.h + gy) * p.w + gx) * p.C + cg * 8);
+          va = __ldg(src);
+          vb = __ldg(src + 1);
+        }
+        uint4 hi, lo;
+        wsplit8(va, vb, hi, lo);
+        // source pixel j lands at x = j - kw of copy kw
+        for (int kw = 0; kw < p.ks; ++kw) {
+          const int xl = j - kw;
+          if ((unsigned)xl < (unsigned)WG_TW) {
+            const size_t o = (size_t)(kw * p.ncg + cg) * p.CGS_A + (size_t)(r * WG_TW + xl) * 16;
+            *reinterpret_cast<uint4*>(a_dst + o) = hi;
+            if (p.a_planes == 2) *reinterpret_cast<uint4*>(a_dst + p.a_plane_bytes + o) = lo;
+          }
+        }
+      }
+      // ---- output-gradient tile
+      for (int i = ltid; i < b_tasks; i += 256) {
+        const int cg = i % ncg_b;
+        const int pj = i / ncg_b;
+        const int xl = pj % WG_TW, r = pj / WG_TW;
+        const int gy = y0 + r, gx = x0 + xl;
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        if (gy < p.h && gx < p.w) {
+          const float4* src = reinterpret_cast<const float4*>(p.dz + (((size_t)img * p.h + gy) * p.w + gx) * p.N + n0 + cg * 8);
+          va = __ldg(src);
+          vb = __ldg(src + 1);
+        }
+        uint4 hi, lo;
+        wsplit8(va, vb, hi, lo);
+        const size_t o = (size_t)cg * p.CGS_B + (size_t)(r * WG_TW + xl) * 16;
+        *reinterpret_cast<uint4*>(b_dst + o) = hi;
+        if (p.b_planes == 2) *reinterpret_cast<uint4*>(b_dst + p.b_plane_bytes + o) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) wbar_arrive(FULL + bi * 8);
+    }
+    // ===================== epilogue (warps 4-7): TMEM -> partial dW =====================
+    if (warp < 8) {
+      wbar_wait(DONE, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3;
+      const int rows_total = p.ks * p.ks * p.C + 4;
+      float* out = p.ws + (size_t)psplit * rows_total * p.N;
+      const bool have_work = t_end > t_begin;
+      for (int mb = 0; mb < p.MB; ++mb) {
+        const int row = mb * 128 + q * 32 + lane;  // (kw, group, channel)
+        const int g = row >> 3, ch = row & 7;
+        int orow = -1;
+        if (g < p.G) {
+          const int kw = g / p.ncg, cg = g - kw * p.ncg;
+          orow = (kh * p.ks + kw) * p.C + cg * 8 + ch;
+        } else if (g == p.G && ch < 4 && kh == 0) {
+          orow = p.ks * p.ks * p.C + ch;  // bias gradient row (+ 3 zero rows)
+        }
+        const uint32_t taddr = tmem_base + mb * p.NC + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < nc; c0 += 16) {
+          uint32_t v[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr + c0)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (orow >= 0) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)orow * p.N + n0 + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              dst[k] = have_work ? make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                               __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256) wg_reduce_kernel(const float* __restrict__ ws, int64_t numel4, int splits,
+                                                        float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel4; e += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = reinterpret_cast<const float4*>(ws)[e];
+    for (int k = 1; k < splits; ++k) {
+      const float4 v = reinterpret_cast<const float4*>(ws)[(int64_t)k * numel4 + e];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[e] = s;
+  }
+}
+
+int check_conv_desc(const nq_conv_desc* d);
+
+static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc_wgrad_plan* pl) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || a_planes < 1 || a_planes > 2 || b_planes < 1 || b_planes > 2) return NQ_ERR_BAD_ARG;
+  const int C = d->cin_p, N = d->rh * d->rw * d->cg;
+  if (C % 8 || N % 16 || d->ksize > 7) return NQ_ERR_BAD_SHAPE;
+  pl->C = C; pl->N = N; pl->a_planes = a_planes; pl->b_planes = b_planes;
+  pl->ncg = C / 8;
+  pl->G = d->ksize * pl->ncg;
+  pl->MB = (pl->G + 1 + 15) / 16;
+  if (pl->MB > 4) return NQ_ERR_UNSUPPORTED;  // C * ks > 504: more accumulator rows than one CTA's TMEM pass
+  int nc = (512 / pl->MB) / 16 * 16;
+  if (nc > 256) nc = 256;
+  if (nc > N) nc = N;
+  pl->NC = nc;
+  pl->nsplits = (N + nc - 1) / nc;
+  pl->TR = 4;
+  const int per_group = pl->TR * WG_TW * 16;  // bytes
+  pl->CGS_A = per_group + 16;                 // +16: conflict-free loader stores across groups
+  pl->CGS_B = per_group + 16;
+  pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
+  pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
+  pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
+  int nbuf = (227 * 1024 - 128) / pl->buf_bytes;
+  if (nbuf > 4) nbuf = 4;
+  if (nbuf < 2) return NQ_ERR_UNSUPPORTED;
+  pl->nbuf = nbuf;
+  pl->smem_bytes = 128 + nbuf * pl->buf_bytes;
+  pl->tiles_x = (d->w + WG_TW - 1) / WG_TW;
+  pl->tiles_y = (d->h + pl->TR - 1) / pl->TR;
+  pl->tiles_total = pl->tiles_x * pl->tiles_y * d->n;
+  int ps = sm_count() / (d->ksize * pl->nsplits);
+  if (ps < 1) ps = 1;
+  if (ps > pl->tiles_total) ps = pl->tiles_total;
+  pl->tiles_per_split = (pl->tiles_total + ps - 1) / ps;
+  pl->psplits = (pl->tiles_total + pl->tiles_per_split - 1) / pl->tiles_per_split;
+  pl->workspace_floats = (int64_t)pl->psplits * (d->ksize * d->ksize * C + 4) * N;
+  return NQ_OK;
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+extern "C" int nq_tc_plan_wgrad(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc_wgrad_plan* plan) {
+  return fill_wg_plan(d, a_planes, b_planes, plan);
+}
+
+extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* pl, const float* x, const float* dz,
+                                float* dwk, float* workspace, int64_t workspace_floats, void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || !x || !dz || !dwk || !workspace) return NQ_ERR_BAD_ARG;
+  if (workspace_floats < pl->workspace_floats) return NQ_ERR_WORKSPACE;
+  WgParams p{};
+  p.x = x; p.dz = dz; p.ws = workspace;
+  p.n = d->n; p.h = d->h; p.w = d->w; p.C = pl->C; p.N = pl->N; p.ks = d->ksize; p.pad = d->ksize / 2;
+  p.ncg = pl->ncg; p.G = pl->G; p.MB = pl->MB; p.NC = pl->NC; p.nsplits = pl->nsplits; p.TR = pl->TR;
+  p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_total = pl->tiles_total; p.psplits = pl->psplits;
+  p.tiles_per_split = pl->tiles_per_split; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
+  p.CGS_A = pl->CGS_A; p.CGS_B = pl->CGS_B; p.a_plane_bytes = pl->a_plane_bytes; p.b_plane_bytes = pl->b_plane_bytes;
+  p.buf_bytes = pl->buf_bytes; p.nbuf = pl->nbuf;
+  cudaStream_t s = as_stream(stream);
+  NQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int grid = pl->psplits * pl->nsplits * d->ksize;
+  wgrad_tc_kernel<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
+  NQ_LAUNCH_CHECK();
+  const int64_t n4 = (int64_t)(d->ksize * d->ksize * pl->C + 4) * pl->N / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  wg_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(workspace, n4, pl->psplits, dwk);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}

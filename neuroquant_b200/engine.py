@@ -237,6 +237,7 @@ class DecoderEngine:
         self.fwd_a_planes = int(os.environ.get("NQ_FWD_A_PLANES", "2"))
         self.bwd_a_planes = int(os.environ.get("NQ_BWD_A_PLANES", "2"))
         self.bwd_b_planes = int(os.environ.get("NQ_BWD_B_PLANES", "2"))
+        self.wgrad_tc = os.environ.get("NQ_WGRAD", "tc").lower() != "simt"
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
         self._weights_valid = False
@@ -481,6 +482,11 @@ class DecoderEngine:
             self._grad = (flat, views)
         return self._grad
 
+    def _wg_plan(self, d: L.ConvDesc):
+        pl = L.TcWgradPlan()
+        st = L.lib.nq_tc_plan_wgrad(C.byref(d), self.bwd_a_planes, self.bwd_b_planes, C.byref(pl))
+        return pl if st == 0 else None
+
     def _wgrad_splits(self, d: L.ConvDesc) -> int:
         rows = d.kdim + 4
         n = d.nout_p
@@ -506,6 +512,9 @@ class DecoderEngine:
                 if i == last:
                     blocks = L.lib.nq_head_wgrad_blocks(C.byref(d))
                     p.ws.append((torch.empty(blocks * (d.kdim + 4) * 4, device=self.device), 0))
+                elif self.use_tc and self.wgrad_tc and d.n * d.h * d.w >= 256 and self._wg_plan(d) is not None:
+                    pl = self._wg_plan(d)
+                    p.ws.append((torch.empty(pl.workspace_floats, device=self.device), pl))
                 else:
                     sp = self._wgrad_splits(d)
                     p.ws.append((torch.empty(sp * (d.kdim + 4) * d.nout_p, device=self.device) if sp > 1 else None, sp))
@@ -516,6 +525,10 @@ class DecoderEngine:
             if i == last:
                 L.check(self._run("head_wgrad", d, L.lib.nq_head_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]), L.ptr(p.dwk[i]),
                                   L.ptr(ws), ws.numel(), st), "nq_head_wgrad")
+                self.launches += 2
+            elif isinstance(sp, L.TcWgradPlan):
+                L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_tc_conv_wgrad, C.byref(d), C.byref(sp), L.ptr(p.x[i]),
+                                  L.ptr(p.dz[i]), L.ptr(p.dwk[i]), L.ptr(ws), ws.numel(), st), "nq_tc_conv_wgrad")
                 self.launches += 2
             else:
                 L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_conv_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]),

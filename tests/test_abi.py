@@ -89,3 +89,11 @@ def test_tc_plans_fit_for_every_workload():
                 assert pl.total_tiles == pl.tiles_x * pl.tiles_y * pl.tiles_n * 2
                 assert (pl.CGS // 16) % 8 == 1 and pl.CGS >= pl.PW * pl.PH * 16
         assert descs[-1].cin_p % 4 == 0
+        for i, d in enumerate(descs[:-1]):
+            for ap, bp in ((1, 1), (2, 2)):
+                wp = L.TcWgradPlan()
+                st = L.lib.nq_tc_plan_wgrad(C.byref(d), ap, bp, C.byref(wp))
+                assert st == 0, (arch, i, st)
+                assert wp.MB * wp.NC <= 512 and wp.NC % 16 == 0 and wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2
+                assert wp.G + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
+                assert wp.psplits * wp.nsplits * d.ksize <= max(148, wp.nsplits * d.ksize)
