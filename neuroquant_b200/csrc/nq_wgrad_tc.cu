@@ -316,16 +316,21 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   if (nc > N) nc = N;
   pl->NC = nc;
   pl->nsplits = (N + nc - 1) / nc;
-  pl->TR = 4;
-  const int per_group = pl->TR * WG_TW * 16;  // bytes
-  pl->CGS_A = per_group + 16;                 // +16: conflict-free loader stores across groups
-  pl->CGS_B = per_group + 16;
-  pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
-  pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
-  pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
-  int nbuf = (227 * 1024 - 128) / pl->buf_bytes;
-  if (nbuf > 4) nbuf = 4;
+  // tile rows: as many as leave room for >= 2 pipeline buffers
+  int tr = 4, nbuf = 0;
+  for (; tr >= 1; tr >>= 1) {
+    const int per_group = tr * WG_TW * 16;  // bytes
+    pl->CGS_A = per_group + 16;             // +16: conflict-free loader stores across groups
+    pl->CGS_B = per_group + 16;
+    pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
+    pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
+    pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
+    nbuf = (227 * 1024 - 128) / pl->buf_bytes;
+    if (nbuf >= 2) break;
+  }
   if (nbuf < 2) return NQ_ERR_UNSUPPORTED;
+  if (nbuf > 4) nbuf = 4;
+  pl->TR = tr;
   pl->nbuf = nbuf;
   pl->smem_bytes = 128 + nbuf * pl->buf_bytes;
   pl->tiles_x = (d->w + WG_TW - 1) / WG_TW;

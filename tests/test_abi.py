@@ -93,6 +93,8 @@ def test_tc_plans_fit_for_every_workload():
             for ap, bp in ((1, 1), (2, 2)):
                 wp = L.TcWgradPlan()
                 st = L.lib.nq_tc_plan_wgrad(C.byref(d), ap, bp, C.byref(wp))
+                if st == -3 and d.cin_p * d.ksize > 504:
+                    continue  # wide 12M-class stages: more accumulator rows than one TMEM pass -> FFMA wgrad kernel
                 assert st == 0, (arch, i, st)
                 assert wp.MB * wp.NC <= 512 and wp.NC % 16 == 0 and wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2
                 assert wp.G + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
