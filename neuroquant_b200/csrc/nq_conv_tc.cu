@@ -51,6 +51,8 @@ struct TcParams {
   int tiles_x, tiles_y, tiles_n, total_tiles;
   int PW, PH, CGS;       // halo width/height (pixels), channel-group stride (bytes)
   int a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages;
+  int cs;                // CTAs per cluster sharing every weight stage by TMA multicast (1, 2 or 4)
+  int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -88,6 +90,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -148,11 +170,17 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
 // ------------------------------------------------------------------------------------------------
 struct TileCoord {
   int img, y0, x0, n0, nt;  // image, tile origin (pixels), first column, columns in this N tile
+  bool real;                // false: padding slot of a cluster group (runs the pipeline, touches no pixels)
 };
-__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
+// Tile slots are ordered pixel-tile fastest within an N tile, padded so that the cs CTAs of a cluster
+// always work on the same N tile (they share its weight stages by multicast).
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, int rank) {
   TileCoord c;
-  const int tn = t % p.tiles_n;
-  int tm = t / p.tiles_n;
+  const int slot = group * p.cs + rank;
+  const int tn = slot / p.tiles_m_pad;
+  int tm = slot - tn * p.tiles_m_pad;
+  c.real = tm < p.tiles_m;
+  if (!c.real) tm = 0;
   const int tx = tm % p.tiles_x;
   tm /= p.tiles_x;
   const int ty = tm % p.tiles_y;
@@ -177,6 +205,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t b_base = a_base + 2 * p.a_buf_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = p.cs > 1 ? (int)cluster_rank() : 0;
+  const int cluster_id = blockIdx.x / p.cs, n_clusters = gridDim.x / p.cs;
+  const uint16_t mc_mask = (uint16_t)((1u << p.cs) - 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -187,7 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < p.n_bstages; ++i) {
       mbar_init(B_FULL + i * 8, 1);
-      mbar_init(B_EMPTY + i * 8, 1);
+      mbar_init(B_EMPTY + i * 8, p.cs);  // every CTA of the cluster must have consumed the slot
     }
     fence_barrier_init();
   }
@@ -198,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -211,9 +243,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int stages_per_ntile = (p.C / p.SBC) * taps;
       const size_t ntile_stride = (size_t)stages_per_ntile * p.NT * p.SBC * 2 * p.b_planes;
       uint32_t sc = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t);
+      for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
+        const TileCoord tc = tile_coord(p, t, rank);
         const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * 2 * p.b_planes;
+        const uint32_t part = stage_bytes / p.cs;
         const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride;
         for (int cb = 0; cb < ncb; ++cb) {
           const int nsb = min(nsb_full, (p.C - cb * p.KC) / p.SBC);
@@ -222,7 +255,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t s = sc % p.n_bstages, ph = (sc / p.n_bstages) & 1;
               mbar_wait(B_EMPTY + s * 8, ph ^ 1);
               mbar_arrive_expect_tx(B_FULL + s * 8, stage_bytes);
-              bulk_g2s(b_base + s * p.b_stage_bytes, src, stage_bytes, B_FULL + s * 8);
+              if (p.cs == 1)
+                bulk_g2s(b_base + s * p.b_stage_bytes, src, stage_bytes, B_FULL + s * 8);
+              else  // this CTA fetches its 1/cs of the stage and multicasts it to every CTA of the cluster
+                bulk_g2s_mc(b_base + s * p.b_stage_bytes + rank * part, src + rank * part, part, B_FULL + s * 8, mc_mask);
               src += stage_bytes;
             }
         }
@@ -234,8 +270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t sc = 0, uc = 0, tcnt = 0;
       const int nsb_full = p.KC / p.SBC;
       const uint32_t a_sbo = p.PW * 16;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcnt) {
-        const TileCoord tc = tile_coord(p, t);
+      for (int t = cluster_id; t < p.total_groups; t += n_clusters, ++tcnt) {
+        const TileCoord tc = tile_coord(p, t, rank);
         const uint32_t acc = tcnt & 1;
         mbar_wait(T_EMPTY + acc * 8, ((tcnt >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -267,7 +303,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (p.a_planes == 2) umma_bf16(d_tmem, make_desc(a_addr + p.a_plane_bytes, p.CGS, a_sbo), b_hi, idesc, 1);
                 if (p.b_planes == 2) umma_bf16(d_tmem, a_hi, make_desc(b_addr + b_plane_bytes, b_lbo, 128), idesc, 1);
               }
-              umma_commit(B_EMPTY + s * 8);  // stage free once these MMAs have read it
+              // stage free once these MMAs have read it -- signalled to every CTA that multicasts into it
+              if (p.cs == 1) umma_commit(B_EMPTY + s * 8);
+              else umma_commit_mc(B_EMPTY + s * 8, mc_mask);
             }
           }
           umma_commit(A_EMPTY + abuf * 8);
@@ -280,8 +318,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int ltid = threadIdx.x - 8 * 32;
     const int npix = p.PW * p.PH;
     uint32_t uc = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc = tile_coord(p, t);
+    for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
+      const TileCoord tc = tile_coord(p, t, rank);
       const float* img = p.in + (size_t)tc.img * p.h * p.w * p.C;
       for (int cb = 0; cb < ncb; ++cb, ++uc) {
         const uint32_t abuf = uc & 1;
@@ -299,11 +337,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             off[u] = -1;
             if (i < tasks) {
-              const int pix = i / ncg, cgi = i - pix * ncg;
+              // pixel fastest: the 8 threads of a 16-byte store phase fill 8 consecutive 16-byte rows
+              const int cgi = i / npix, pix = i - cgi * npix;
               const int py = pix / p.PW, px = pix - py * p.PW;
               const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
               off[u] = cgi * p.CGS + pix * 16;
-              if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
+              if (tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
                 const float4* src = reinterpret_cast<const float4*>(img + ((size_t)gy * p.w + gx) * p.C + c0 + cgi * 8);
                 va[u] = __ldg(src);
                 vb[u] = __ldg(src + 1);
@@ -331,11 +370,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int m = q * 32 + lane;
     const int ly = m >> 3, lx = m & 7;
     uint32_t tcnt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcnt) {
-      const TileCoord tc = tile_coord(p, t);
+    for (int t = cluster_id; t < p.total_groups; t += n_clusters, ++tcnt) {
+      const TileCoord tc = tile_coord(p, t, rank);
       const uint32_t acc = tcnt & 1;
       const int y = tc.y0 + ly, x = tc.x0 + lx;
-      const bool valid = y < p.h && x < p.w;
+      const bool valid = tc.real && y < p.h && x < p.w;
       mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
@@ -402,6 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -556,6 +596,9 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   const long long stages = (long long)(C / sbc) * taps;
   const int last_nt = N - (pl->tiles_n - 1) * pl->NT;
   pl->wpk_bytes = stages * sbc * 2 * b_planes * ((long long)(pl->tiles_n - 1) * pl->NT + last_nt);
+  // weight-stream sharing: 2 CTAs per cluster pack all 148 SMs (74 TPCs); every stage splits evenly
+  // (nt * SBC * 2 * planes is a multiple of 512 bytes)
+  pl->cluster = 2;
   return NQ_OK;
 }
 
@@ -605,9 +648,28 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   NQ_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  int grid = pl->total_tiles < sm_count() ? pl->total_tiles : sm_count();
-  conv_tc_kernel<<<grid, TC_THREADS, pl->smem_bytes, s>>>(p);
-  NQ_LAUNCH_CHECK();
+  // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
+  int cs = pl->cluster;
+  p.tiles_m = pl->tiles_x * pl->tiles_y * d->n;
+  if (cs < 1 || p.tiles_m < 2 * cs) cs = 1;
+  p.cs = cs;
+  p.tiles_m_pad = (p.tiles_m + cs - 1) / cs * cs;
+  p.total_groups = p.tiles_m_pad / cs * pl->tiles_n;
+  int n_clusters = sm_count() / cs;
+  if (n_clusters > p.total_groups) n_clusters = p.total_groups;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(n_clusters * cs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, p));
   return NQ_OK;
 }
 

@@ -191,47 +191,76 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
       uint8_t* a_dst = bufs + (size_t)bi * p.buf_bytes;
       uint8_t* b_dst = a_dst + (size_t)p.a_planes * p.a_plane_bytes;
+      // Task order: pixel fastest, so that the 8 threads of a 16-byte store phase write 8 consecutive
+      // 16-byte rows of one core matrix (conflict free); loads are issued 4 deep before any store.
       // ---- shifted input copies
-      for (int i = ltid; i < a_tasks; i += 256) {
-        const int cg = i % p.ncg;
-        const int pj = i / p.ncg;
-        const int j = pj % span, r = pj / span;
-        const int gy = y0 + r + kh - p.pad, gx = x0 + j - p.pad;
-        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-        if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && (y0 + r) < p.h) {
-          const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)img * p.h + gy) * p.w + gx) * p.C + cg * 8);
-          va = __ldg(src);
-          vb = __ldg(src + 1);
+      for (int i0 = ltid; i0 < a_tasks; i0 += 256 * 4) {
+        float4 va[4], vb[4];
+        int jj[4], rr[4], cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          jj[u] = -1;
+          if (i < a_tasks) {
+            const int j = i % span;
+            const int rc = i / span;
+            const int r = rc % p.TR, cg = rc / p.TR;
+            jj[u] = j; rr[u] = r; cc[u] = cg;
+            const int gy = y0 + r + kh - p.pad, gx = x0 + j - p.pad;
+            if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && (y0 + r) < p.h) {
+              const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)img * p.h + gy) * p.w + gx) * p.C + cg * 8);
+              va[u] = __ldg(src);
+              vb[u] = __ldg(src + 1);
+            }
+          }
         }
-        uint4 hi, lo;
-        wsplit8(va, vb, hi, lo);
-        // source pixel j lands at x = j - kw of copy kw
-        for (int kw = 0; kw < p.ks; ++kw) {
-          const int xl = j - kw;
-          if ((unsigned)xl < (unsigned)WG_TW) {
-            const size_t o = (size_t)(kw * p.ncg + cg) * p.CGS_A + (size_t)(r * WG_TW + xl) * 16;
-            *reinterpret_cast<uint4*>(a_dst + o) = hi;
-            if (p.a_planes == 2) *reinterpret_cast<uint4*>(a_dst + p.a_plane_bytes + o) = lo;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (jj[u] < 0) continue;
+          uint4 hi, lo;
+          wsplit8(va[u], vb[u], hi, lo);
+          // source pixel j lands at x = j - kw of copy kw
+          for (int kw = 0; kw < p.ks; ++kw) {
+            const int xl = jj[u] - kw;
+            if ((unsigned)xl < (unsigned)WG_TW) {
+              const size_t o = (size_t)(kw * p.ncg + cc[u]) * p.CGS_A + (size_t)(rr[u] * WG_TW + xl) * 16;
+              *reinterpret_cast<uint4*>(a_dst + o) = hi;
+              if (p.a_planes == 2) *reinterpret_cast<uint4*>(a_dst + p.a_plane_bytes + o) = lo;
+            }
           }
         }
       }
       // ---- output-gradient tile
-      for (int i = ltid; i < b_tasks; i += 256) {
-        const int cg = i % ncg_b;
-        const int pj = i / ncg_b;
-        const int xl = pj % WG_TW, r = pj / WG_TW;
-        const int gy = y0 + r, gx = x0 + xl;
-        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-        if (gy < p.h && gx < p.w) {
-          const float4* src = reinterpret_cast<const float4*>(p.dz + (((size_t)img * p.h + gy) * p.w + gx) * p.N + n0 + cg * 8);
-          va = __ldg(src);
-          vb = __ldg(src + 1);
+      for (int i0 = ltid; i0 < b_tasks; i0 += 256 * 4) {
+        float4 va[4], vb[4];
+        int oo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          oo[u] = -1;
+          if (i < b_tasks) {
+            const int xl = i % WG_TW;
+            const int rc = i / WG_TW;
+            const int r = rc % p.TR, cg = rc / p.TR;
+            oo[u] = cg * p.CGS_B + (r * WG_TW + xl) * 16;
+            const int gy = y0 + r, gx = x0 + xl;
+            if (gy < p.h && gx < p.w) {
+              const float4* src = reinterpret_cast<const float4*>(p.dz + (((size_t)img * p.h + gy) * p.w + gx) * p.N + n0 + cg * 8);
+              va[u] = __ldg(src);
+              vb[u] = __ldg(src + 1);
+            }
+          }
         }
-        uint4 hi, lo;
-        wsplit8(va, vb, hi, lo);
-        const size_t o = (size_t)cg * p.CGS_B + (size_t)(r * WG_TW + xl) * 16;
-        *reinterpret_cast<uint4*>(b_dst + o) = hi;
-        if (p.b_planes == 2) *reinterpret_cast<uint4*>(b_dst + p.b_plane_bytes + o) = lo;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (oo[u] < 0) continue;
+          uint4 hi, lo;
+          wsplit8(va[u], vb[u], hi, lo);
+          *reinterpret_cast<uint4*>(b_dst + oo[u]) = hi;
+          if (p.b_planes == 2) *reinterpret_cast<uint4*>(b_dst + p.b_plane_bytes + oo[u]) = lo;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();

@@ -204,11 +204,13 @@ class _Plan:
                 for bpl in (1, 2):
                     pl = L.TcPlan()
                     L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[i]), 0, eng.fwd_a_planes, bpl, C.byref(pl)), "nq_tc_plan_conv")
+                    pl.cluster = eng.cluster
                     self.tc_fwd[(i, bpl)] = pl
                 pl = L.TcPlan()
                 if train and i > 0:
                     L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[i]), 1, eng.bwd_a_planes, eng.bwd_b_planes, C.byref(pl)),
                             "nq_tc_plan_conv")
+                    pl.cluster = eng.cluster
                 self.tc_dgrad.append(pl)
 
 
@@ -238,6 +240,7 @@ class DecoderEngine:
         self.bwd_a_planes = int(os.environ.get("NQ_BWD_A_PLANES", "2"))
         self.bwd_b_planes = int(os.environ.get("NQ_BWD_B_PLANES", "2"))
         self.wgrad_tc = os.environ.get("NQ_WGRAD", "tc").lower() != "simt"
+        self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
         self._weights_valid = False
