@@ -68,6 +68,31 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// Branch-free GELU / GELU' for the tensor-core epilogues.  Phi(x) = 0.5 erfc(-x/sqrt2) from the
+// Abramowitz-Stegun 7.1.26 rational (|abs err| <= 1.5e-7 on erfc), evaluated on |x| and mirrored so
+// that the small tail is never formed by cancellation; GELU' reuses the same exponential.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  e = __expf(-u * u);  // = exp(-x^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;  // 0.5 erfc(|x|/sqrt2)
+  cdf = x < 0.f ? half_erfc : 1.0f - half_erfc;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 __device__ __forceinline__ float sigmoid_f(float a) { return 1.0f / (1.0f + expf(-a)); }
 
 }  // namespace nq

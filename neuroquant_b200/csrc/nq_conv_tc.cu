@@ -21,15 +21,15 @@
 //     per-channel scale applied in the epilogue) or are split as well; the product is accumulated as
 //     hi*hi + lo*hi + hi*lo in fp32.
 //
-// Warp roles (384 threads): warp 0 weight-stage producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (TMEM -> registers -> global), warps 8-11 activation loaders (fp32 -> bf16 hi/lo).
+// Warp roles (512 threads): warp 0 weight-stage producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-11 epilogue (TMEM -> registers -> global), warps 12-15 activation loaders (fp32 -> bf16 hi/lo).
 #include <cuda_bf16.h>
 
 #include "nq_common.cuh"
 
 namespace nq {
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 512;
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 8;
 
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(A_FULL + i * 8, 4);
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
-      mbar_init(T_EMPTY + i * 8, 4);
+      mbar_init(T_EMPTY + i * 8, 8);
     }
     for (int i = 0; i < p.n_bstages; ++i) {
       mbar_init(B_FULL + i * 8, 1);
@@ -313,9 +313,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         umma_commit(T_FULL + acc * 8);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ===================== activation loaders: fp32 NHWC -> bf16 hi/lo halo tile =====================
-    const int ltid = threadIdx.x - 8 * 32;
+    const int ltid = threadIdx.x - 12 * 32;
     const int npix = p.PW * p.PH;
     uint32_t uc = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
@@ -365,8 +365,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue: TMEM -> registers -> global (8 warps) =====================
+    // Two warps per TMEM lane quarter; they take alternate 16-column chunks.  Per chunk: the global
+    // operands (scale / bias, or z of the previous stage) are requested BEFORE waiting on the TMEM load.
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int ly = m >> 3, lx = m & 7;
     uint32_t tcnt = 0;
@@ -378,7 +381,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      // per-row output bases
       size_t row_base = 0;   // fwd: pixel (y*rh, x*rw) of the shuffled grid; dgrad: un-shuffled destination
       size_t zrow = 0;
       if (p.epi == 0) {
@@ -389,47 +391,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                    (size_t)(si * p.rw + sj) * p.N;
         zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.N;
       }
-      // running (group, channel) of column n for the forward shuffle: n = grp * cg + c
-      int grp = 0, c = 0;
-      if (p.epi == 0) {
-        grp = tc.n0 / p.cg;
-        c = tc.n0 - grp * p.cg;
-      }
-      for (int c0 = 0; c0 < tc.nt; c0 += 16) {
+      for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
+        const int nb = tc.n0 + c0;
+        float4 g0[4], g1[4];  // fwd: scale, bias; dgrad: z of the previous stage
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          g0[qd] = make_float4(1.f, 1.f, 1.f, 1.f);
+          g1[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.epi == 0) {
+            if (p.scale) g0[qd] = __ldg(reinterpret_cast<const float4*>(p.scale + nb + qd * 4));
+            if (p.bias) g1[qd] = __ldg(reinterpret_cast<const float4*>(p.bias + nb + qd * 4));
+          } else if (valid && p.zprev && p.act == 1) {
+            g0[qd] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow + nb + qd * 4));
+          }
+        }
+        // (group, channel) of column nb for the forward shuffle: n = grp * cg + c
+        int grp = 0, c = 0;
+        if (p.epi == 0) {
+          grp = nb / p.cg;
+          c = nb - grp * p.cg;
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const int n = tc.n0 + c0 + qd * 4;
           float4 r = make_float4(__uint_as_float(v[qd * 4 + 0]), __uint_as_float(v[qd * 4 + 1]),
                                  __uint_as_float(v[qd * 4 + 2]), __uint_as_float(v[qd * 4 + 3]));
           if (p.epi == 0) {
-            if (p.scale) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-              r.x *= s.x; r.y *= s.y; r.z *= s.z; r.w *= s.w;
-            }
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-            }
+            r.x = fmaf(r.x, g0[qd].x, g1[qd].x); r.y = fmaf(r.y, g0[qd].y, g1[qd].y);
+            r.z = fmaf(r.z, g0[qd].z, g1[qd].z); r.w = fmaf(r.w, g0[qd].w, g1[qd].w);
             const int si = grp / p.rw, sj = grp - si * p.rw;
             const size_t o = row_base + ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
             if (valid) {
               if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
-              if (p.act == 1) { r.x = gelu_f(r.x); r.y = gelu_f(r.y); r.z = gelu_f(r.z); r.w = gelu_f(r.w); }
+              if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
               *reinterpret_cast<float4*>(p.out_y + o) = r;
             }
             c += 4;
             if (c >= p.cg) { c -= p.cg; ++grp; }
-          } else {
-            if (valid) {
-              if (p.zprev && p.act == 1) {
-                const float4 z = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow + n));
-                r.x *= gelu_grad_f(z.x); r.y *= gelu_grad_f(z.y); r.z *= gelu_grad_f(z.z); r.w *= gelu_grad_f(z.w);
-              }
-              *reinterpret_cast<float4*>(p.out_y + row_base + n) = r;
+          } else if (valid) {
+            if (p.zprev && p.act == 1) {
+              r.x *= gelu_grad_fast(g0[qd].x); r.y *= gelu_grad_fast(g0[qd].y);
+              r.z *= gelu_grad_fast(g0[qd].z); r.w *= gelu_grad_fast(g0[qd].w);
             }
+            *reinterpret_cast<float4*>(p.out_y + row_base + nb + qd * 4) = r;
           }
         }
       }
