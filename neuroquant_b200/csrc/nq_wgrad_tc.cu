@@ -70,6 +70,19 @@ __device__ __forceinline__ void wmma(uint32_t tmem_d, uint64_t a_desc, uint64_t 
       "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void wmma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void wcommit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     wbar_init(DONE, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 10) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -142,29 +155,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 1) {
-    // ===================== MMA issuer =====================
+  if (warp == 9) {
+    // ===================== MMA issuer (highest warp id of its scheduler partition) =====================
     if (lane == 0) {
       // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128, N = nc
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_hi32 = ((uint32_t)p.CGS_A >> 4) | (1u << 14), b_hi32 = ((uint32_t)p.CGS_B >> 4) | (1u << 14);
+      const uint32_t lbo_bits = (128u >> 4) << 16;
+      const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)p.b_plane_bytes >> 4;
+      const uint32_t mb_step16 = (uint32_t)(16 * p.CGS_A) >> 4, row16 = (WG_TW * 16) >> 4;
+      const bool a2 = p.a_planes == 2, b2 = p.b_planes == 2;
       uint32_t it = 0, accum = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const uint32_t bi = it % p.nbuf, ph = (it / p.nbuf) & 1;
         wbar_wait(FULL + bi * 8, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_buf = buf0 + bi * p.buf_bytes;
-        const uint32_t b_buf = a_buf + p.a_planes * p.a_plane_bytes;
+        const uint32_t a16 = ((a_buf & 0x3FFFFu) >> 4) | lbo_bits;
+        const uint32_t b16 = (((a_buf + p.a_planes * p.a_plane_bytes) & 0x3FFFFu) >> 4) | lbo_bits;
         for (int r = 0; r < p.TR; ++r) {
-          const uint64_t b_hi = wdesc(b_buf + r * (WG_TW * 16), 128, p.CGS_B);
-          const uint64_t b_lo = wdesc(b_buf + p.b_plane_bytes + r * (WG_TW * 16), 128, p.CGS_B);
+          const uint32_t b_lo = b16 + r * row16;
+          uint32_t a_lo = a16 + r * row16;
           for (int mb = 0; mb < p.MB; ++mb) {
-            const uint32_t a_addr = a_buf + mb * 16 * p.CGS_A + r * (WG_TW * 16);
-            const uint64_t a_hi = wdesc(a_addr, 128, p.CGS_A);
             const uint32_t d = tmem_base + mb * p.NC;
-            wmma(d, a_hi, b_hi, idesc, accum);
-            if (p.a_planes == 2) wmma(d, wdesc(a_addr + p.a_plane_bytes, 128, p.CGS_A), b_hi, idesc, 1);
-            if (p.b_planes == 2) wmma(d, a_hi, b_lo, idesc, 1);
+            wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
+            if (a2) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+            if (b2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+            a_lo += mb_step16;
           }
           accum = 1;
         }
@@ -172,9 +190,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
       wcommit(DONE);
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===================== loaders (8 warps): fp32 NHWC -> bf16 planes =====================
-    const int ltid = threadIdx.x - 4 * 32;
+    const int ltid = threadIdx.x;
     const int span = WG_TW + p.ks - 1;  // source pixels per row that feed the ks shifted copies
     const int a_tasks = p.TR * span * p.ncg;
     const int ncg_b = nc >> 3;
@@ -266,8 +284,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) wbar_arrive(FULL + bi * 8);
     }
-    // ===================== epilogue (warps 4-7): TMEM -> partial dW =====================
-    if (warp < 8) {
+    // ===================== epilogue (warps 0-3): TMEM -> partial dW =====================
+    if (warp < 4) {
       wbar_wait(DONE, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3;
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 10) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
