@@ -83,6 +83,17 @@ __device__ __forceinline__ void wmma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t 
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ bool welect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void wcommit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -156,40 +167,45 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 9) {
-    // ===================== MMA issuer (highest warp id of its scheduler partition) =====================
-    if (lane == 0) {
-      // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128, N = nc
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_hi32 = ((uint32_t)p.CGS_A >> 4) | (1u << 14), b_hi32 = ((uint32_t)p.CGS_B >> 4) | (1u << 14);
-      const uint32_t lbo_bits = (128u >> 4) << 16;
-      const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)p.b_plane_bytes >> 4;
-      const uint32_t mb_step16 = (uint32_t)(16 * p.CGS_A) >> 4, row16 = (WG_TW * 16) >> 4;
-      const bool a2 = p.a_planes == 2, b2 = p.b_planes == 2;
-      uint32_t it = 0, accum = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const uint32_t bi = it % p.nbuf, ph = (it / p.nbuf) & 1;
-        wbar_wait(FULL + bi * 8, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_buf = buf0 + bi * p.buf_bytes;
-        const uint32_t a16 = ((a_buf & 0x3FFFFu) >> 4) | lbo_bits;
-        const uint32_t b16 = (((a_buf + p.a_planes * p.a_plane_bytes) & 0x3FFFFu) >> 4) | lbo_bits;
-        for (int r = 0; r < p.TR; ++r) {
-          const uint32_t b_lo = b16 + r * row16;
-          uint32_t a_lo = a16 + r * row16;
-          for (int mb = 0; mb < p.MB; ++mb) {
-            const uint32_t d = tmem_base + mb * p.NC;
+    // ===================== MMA issuer =====================
+    // Highest warp id of its scheduler partition; warp-uniform loop with an elect.sync leader so that the
+    // descriptors stay in uniform registers (see nq_conv_tc.cu).
+    const bool leader = welect_one();
+    // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128, N = nc
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi32 = ((uint32_t)p.CGS_A >> 4) | (1u << 14), b_hi32 = ((uint32_t)p.CGS_B >> 4) | (1u << 14);
+    const uint32_t lbo_bits = (128u >> 4) << 16;
+    const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)p.b_plane_bytes >> 4;
+    const uint32_t mb_step16 = (uint32_t)(16 * p.CGS_A) >> 4, row16 = (WG_TW * 16) >> 4;
+    const int passes = (p.a_planes == 2 ? 1 : 0) | (p.b_planes == 2 ? 2 : 0);
+    uint32_t accum = 0, bi = 0, ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      wbar_wait(FULL + bi * 8, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_buf = buf0 + bi * p.buf_bytes;
+      const uint32_t a16 = ((a_buf & 0x3FFFFu) >> 4) | lbo_bits;
+      const uint32_t b16 = (((a_buf + p.a_planes * p.a_plane_bytes) & 0x3FFFFu) >> 4) | lbo_bits;
+      for (int r = 0; r < p.TR; ++r) {
+        const uint32_t b_lo = b16 + r * row16;
+        uint32_t a_lo = a16 + r * row16;
+        uint32_t d = tmem_base;
+#pragma unroll 1
+        for (int mb = 0; mb < p.MB; ++mb) {
+          if (leader) {
             wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
-            if (a2) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
-            if (b2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
-            a_lo += mb_step16;
+            if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+            if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
           }
-          accum = 1;
+          a_lo += mb_step16;
+          d += p.NC;
         }
-        wcommit(EMPTY + bi * 8);
+        accum = 1;
       }
-      wcommit(DONE);
+      if (leader) wcommit(EMPTY + bi * 8);
+      if (++bi == (uint32_t)p.nbuf) { bi = 0; ph ^= 1; }
     }
+    if (leader) wcommit(DONE);
   } else if (warp < 8) {
     // ===================== loaders (8 warps): fp32 NHWC -> bf16 planes =====================
     const int ltid = threadIdx.x;
@@ -197,9 +213,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int a_tasks = p.TR * span * p.ncg;
     const int ncg_b = nc >> 3;
     const int b_tasks = p.TR * WG_TW * ncg_b;
-    uint32_t it = 0;
-    for (int t = t_begin; t < t_end; ++t, ++it) {
-      const uint32_t bi = it % p.nbuf, ph = (it / p.nbuf) & 1;
+    uint32_t bi = 0, ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
       int tt = t;
       const int tx = tt % p.tiles_x;
       tt /= p.tiles_x;
@@ -283,6 +298,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) wbar_arrive(FULL + bi * 8);
+      if (++bi == (uint32_t)p.nbuf) { bi = 0; ph ^= 1; }
     }
     // ===================== epilogue (warps 0-3): TMEM -> partial dW =====================
     if (warp < 4) {
