@@ -22,7 +22,8 @@
 
 namespace nq {
 
-constexpr int WG_THREADS = 384;
+constexpr int WG_THREADS = 640;
+constexpr int WG_LOADERS = 512;  // warps 0-15
 constexpr int WG_TW = 16;  // pixels per MMA K step
 
 struct WgParams {
@@ -134,13 +135,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nbuf; ++i) {
-      wbar_init(FULL + i * 8, 8);
+      wbar_init(FULL + i * 8, WG_LOADERS / 32);
       wbar_init(EMPTY + i * 8, 1);
     }
     wbar_init(DONE, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 10) {
+  if (warp == 18) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
+  if (warp == 17) {
     // ===================== MMA issuer =====================
     // Highest warp id of its scheduler partition; warp-uniform loop with an elect.sync leader so that the
     // descriptors stay in uniform registers (see nq_conv_tc.cu).
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (++bi == (uint32_t)p.nbuf) { bi = 0; ph ^= 1; }
     }
     if (leader) wcommit(DONE);
-  } else if (warp < 8) {
-    // ===================== loaders (8 warps): fp32 NHWC -> bf16 planes =====================
+  } else if (warp < WG_LOADERS / 32) {
+    // ===================== loaders (16 warps): fp32 NHWC -> bf16 planes =====================
     const int ltid = threadIdx.x;
     const int span = WG_TW + p.ks - 1;  // source pixels per row that feed the ks shifted copies
     const int a_tasks = p.TR * span * p.ncg;
@@ -227,12 +228,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       // Task order: pixel fastest, so that the 8 threads of a 16-byte store phase write 8 consecutive
       // 16-byte rows of one core matrix (conflict free); loads are issued 4 deep before any store.
       // ---- shifted input copies
-      for (int i0 = ltid; i0 < a_tasks; i0 += 256 * 4) {
+      for (int i0 = ltid; i0 < a_tasks; i0 += WG_LOADERS * 4) {
         float4 va[4], vb[4];
         int jj[4], rr[4], cc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 256;
+          const int i = i0 + u * WG_LOADERS;
           va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           jj[u] = -1;
           if (i < a_tasks) {
@@ -265,12 +266,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
       }
       // ---- output-gradient tile
-      for (int i0 = ltid; i0 < b_tasks; i0 += 256 * 4) {
+      for (int i0 = ltid; i0 < b_tasks; i0 += WG_LOADERS * 4) {
         float4 va[4], vb[4];
         int oo[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 256;
+          const int i = i0 + u * WG_LOADERS;
           va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           oo[u] = -1;
           if (i < b_tasks) {
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 10) {
+  if (warp == 18) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
