@@ -233,6 +233,21 @@ int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* plan, const 
                      float* dwk, float* workspace, int64_t workspace_floats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Omega = dw^T H dw (methods/bit_assign.py:57-118,171-203) by second-order FORWARD propagation:
+ * every stage carries (y, y', y'') = value and first/second directional derivative along the weight
+ * perturbation; the convolutions are the forward kernels above applied to y, y', y'' with the weights
+ * w or the perturbation v; these two kernels are the elementwise chain rule and the MSE head.
+ * ------------------------------------------------------------------------------------------------ */
+/* z' = zd1 + zd2, z'' = zdd1 + 2*zdd2 (any of the four may be NULL = 0); act as nq_conv_desc.act.
+ * y = f(z), yd = f'(z) z', ydd = f''(z) z'^2 + f'(z) z''. */
+int nq_jet_act(const float* z, const float* zd1, const float* zd2, const float* zdd1, const float* zdd2,
+               int64_t numel, int act, float* y, float* yd, float* ydd, void* stream);
+/* Head pre-activations (n, h, w, 4) NHWC, target (n, 3, h, w): *omega_acc += d^2/d eps^2 of
+ * nn.MSELoss(OutImg(z), target) (mean over n*3*h*w).  omega_acc is a device double the caller zeroes. */
+int nq_jet_head(const float* z, const float* zd1, const float* zd2, const float* zdd1, const float* zdd2,
+                const float* target, int n, int h, int w, int out_bias, double* omega_acc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Layout edges and reductions
  * ------------------------------------------------------------------------------------------------ */
 /* NCHW (n, c, h, w) <-> NHWC (n, h, w, c_p); pad channels are written as zero / ignored. */

@@ -1,0 +1,133 @@
+"""Sensitivity criteria of bit_assign on the decoder engine (reference: methods/bit_assign.py:57-217).
+
+omega        Omega = sum_batches v^T H_b v, H_b the Hessian of nn.MSELoss(decode(x_b), frame_b) w.r.t. the
+             conv weights, v = W - Q(W).  The reference forms H v by a double backward pass; here
+             v^T H v = d^2/d eps^2 L(w + eps v)|_0 is propagated FORWARD as a second-order jet
+             (y, y', y'') through the decoder: 5 forward convolutions per stage on the tensor-core kernel
+             (y*w, y'*w, y*v, y''*w, y'*v), the elementwise chain rule (nq_jet_act) and the MSE head
+             (nq_jet_head).  No backward pass, no graph.  The per-layer split of Omega that the reference
+             also logs needs the full H v and is not produced.
+fisher_diag  sum_l sum (v_l^2 * g_l^2) with g the gradient accumulated over the batches: one engine
+             forward/backward per batch and one fused multi-tensor reduction (nq_multi_dot).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import List, Sequence
+
+import torch
+
+from . import _lib as L
+from .engine import DecoderEngine, _ACT, _HEAD
+
+
+class OmegaEvaluator:
+    def __init__(self, engine: DecoderEngine):
+        if engine.mode != "off":
+            raise L.NqError("Omega is defined on the full-precision decoder (engine.mode == 'off')")
+        self.eng = engine
+        self.acc = torch.zeros(1, dtype=torch.float64, device=engine.device)
+        self._v = None
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ direction
+    def set_direction(self, vecs: Sequence[torch.Tensor], n: int, h0: int, w0: int):
+        """vecs: one (C_out, C_in, k, k) perturbation per stage (QuantModel.get_perturbation())."""
+        eng = self.eng
+        p = eng.plan(n, h0, w0, False)
+        eng.prepare_weights(p, need_wt=False)
+        st = L.stream()
+        self._v = []
+        last = len(eng.stages) - 1
+        for i, (s, d, v) in enumerate(zip(eng.stages, p.desc, vecs)):
+            v = v.detach().contiguous().float()
+            assert v.shape == s.weight.shape
+            if eng._tcw[i] is not None:
+                pl = p.tc_fwd[(i, 2)]
+                buf = torch.zeros(pl.wpk_bytes, dtype=torch.uint8, device=eng.device)
+                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(pl), L.ptr(v), s.geom.cin, None, 0, buf.data_ptr(), st),
+                        "nq_tc_pack_weight")
+            else:
+                buf = torch.zeros(d.kdim, d.nout_p, device=eng.device)
+                L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(v), s.geom.cin, None, L.ptr(buf), None, None, st), "nq_pack_weight")
+            self._v.append(buf)
+        self._zero_bias = [torch.zeros(d.nout_p, device=eng.device) for d in p.desc]
+
+    def _conv(self, p, i, x, use_v: bool, with_bias: bool, out):
+        eng = self.eng
+        d = copy.copy(p.desc[i])
+        d.act = 0
+        st = L.stream()
+        wk, _, bp, _, _ = eng._packed[i]
+        if eng._tcw[i] is not None:
+            w = self._v[i].data_ptr() if use_v else eng._tcw[i][0].data_ptr()
+            L.check(L.lib.nq_tc_conv_fwd(C.byref(d), C.byref(p.tc_fwd[(i, 2)]), L.ptr(x), w, None, L.ptr(bp) if with_bias else None,
+                                         None, L.ptr(out), st), "nq_tc_conv_fwd")
+        else:
+            w = self._v[i] if use_v else wk
+            L.check(L.lib.nq_conv_fwd(C.byref(d), L.ptr(x), L.ptr(w), L.ptr(bp if with_bias else self._zero_bias[i]), None,
+                                      L.ptr(out), st), "nq_conv_fwd")
+        eng.launches += 1
+
+    # ------------------------------------------------------------------ one batch
+    def add_batch(self, embed: torch.Tensor, target: torch.Tensor):
+        eng = self.eng
+        n, c0, h0, w0 = embed.shape
+        p = eng.plan(n, h0, w0, False)
+        key = (n, h0, w0)
+        if key not in self._bufs:
+            bufs = []
+            for x in p.x[1:]:
+                bufs.append({k: torch.empty_like(x) for k in ("z", "zd1", "zd2", "zdd1", "zdd2", "y", "yd", "ydd")})
+            hd = p.desc[-1]
+            bufs.append({k: torch.empty(n, hd.h, hd.w, 4, device=eng.device) for k in ("z", "zd1", "zd2", "zdd1", "zdd2")})
+            self._bufs[key] = bufs
+        bufs = self._bufs[key]
+        st = L.stream()
+        embed = embed.detach().contiguous().float()
+        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(embed), L.ptr(p.x[0]), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_nhwc")
+        x, xd, xdd = p.x[0], None, None
+        last = len(eng.stages) - 1
+        for i in range(last + 1):
+            b = bufs[i]
+            self._conv(p, i, x, False, True, b["z"])
+            self._conv(p, i, x, True, False, b["zd2"])
+            zd1 = zdd1 = zdd2 = None
+            if xd is not None:
+                self._conv(p, i, xd, False, False, b["zd1"])
+                self._conv(p, i, xd, True, False, b["zdd2"])
+                zd1, zdd2 = b["zd1"], b["zdd2"]
+            if xdd is not None:
+                self._conv(p, i, xdd, False, False, b["zdd1"])
+                zdd1 = b["zdd1"]
+            if i < last:
+                L.check(L.lib.nq_jet_act(L.ptr(b["z"]), L.ptr(zd1), L.ptr(b["zd2"]), L.ptr(zdd1), L.ptr(zdd2), b["z"].numel(),
+                                         _ACT[eng.geoms[i].act], L.ptr(b["y"]), L.ptr(b["yd"]), L.ptr(b["ydd"]), st), "nq_jet_act")
+                x, xd, xdd = b["y"], b["yd"], b["ydd"]
+            else:
+                tgt = target.detach().contiguous().float()
+                L.check(L.lib.nq_jet_head(L.ptr(b["z"]), L.ptr(zd1), L.ptr(b["zd2"]), L.ptr(zdd1), L.ptr(zdd2), L.ptr(tgt), n,
+                                          p.H, p.W, _HEAD[eng.geoms[last].act], self.acc.data_ptr(), st), "nq_jet_head")
+            eng.launches += 1
+
+    def value(self) -> float:
+        return float(self.acc)
+
+
+def fisher_diag(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches) -> float:
+    """bit_assign.py:122-168, :205-214: gradients of the MSE-mean loss accumulated over the batches,
+    then sum v^2 g^2."""
+    if engine.mode != "off":
+        raise L.NqError("fisher_diag is defined on the full-precision decoder")
+    total = None
+    for embed, target in batches:
+        n, _, H, W = target.shape
+        engine.forward(embed, train=True, target=target, p_norm=2.0, mean_pixels=float(3 * n * H * W), want_img=False)
+        flat = engine.backward()
+        total = flat.clone() if total is None else total + flat
+    engine._grad[0].copy_(total)
+    _, views = engine._grad_buffers()
+    g = [gw.contiguous() for gw, _ in views]
+    v = [x.detach().contiguous().float() for x in vecs]
+    return float(L.multi_dot(v, g, 1).sum())

@@ -143,3 +143,40 @@ def test_model_reconstruction_and_checkpoint(tag, tmp_path):
     assert "model.head_layer.bias_quantizer.alpha" in keys
     out2, _, _ = q2(cali[:2])
     assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("tag", ["tiny_hnerv", "tiny_hnerv_had", "tiny_nerv"])
+def test_omega_golden(tag):
+    """Omega of the reference (double-backward HVP over 4 batches of 2 frames) vs the forward-jet kernels."""
+    from neuroquant_b200.quantization import QuantModel
+    from neuroquant_b200.runner import DecoderRunner
+    from neuroquant_b200.sensitivity import OmegaEvaluator, fisher_diag
+    import copy
+    g, arch, cfg, model = build_model(tag)
+    cali, frames = t(g["cali"]).cuda(), t(g["frames"]).cuda()
+    if arch == "hnerv":
+        cali = cali / 3.0  # make_golden stored 3x the embeddings bit_assign re-encodes (see tests/test_oracle_golden.py)
+    qnn = QuantModel(copy.deepcopy(model), hadamard=bool(g["hadamard"]),
+                     weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"}).cuda()
+    qnn.set_bitwidth(g["bits"].tolist())
+    qnn.set_quant_state(True)
+    qnn(t(g["cali"]).cuda()[:2])
+    vec = qnn.get_perturbation()
+    runner = DecoderRunner.of(model)
+    runner.sync()
+    ev = OmegaEvaluator(runner.engine)
+    ev.set_direction(vec, 2, cali.shape[2], cali.shape[3])
+    for i in range(0, 8, 2):
+        ev.add_batch(cali[i:i + 2], frames[i:i + 2])
+    assert ev.value() == pytest.approx(float(g["omega"]), rel=5e-3, abs=1e-12)
+    # fisher_diag against autograd of the oracle
+    _, _, _, stages = __import__("tests.helpers", fromlist=["case_stages"]).case_stages(tag)
+    ws = [s.weight.clone().requires_grad_(True) for s in stages]
+    tot = [torch.zeros_like(w) for w in ws]
+    for i in range(0, 8, 2):
+        out = O.decode(stages, cali[i:i + 2].cpu(), ws, [s.bias for s in stages])
+        gr = torch.autograd.grad(torch.nn.functional.mse_loss(out, frames[i:i + 2].cpu()), ws)
+        tot = [a + b for a, b in zip(tot, gr)]
+    want = sum(float((v.cpu() ** 2 * gg ** 2).sum()) for v, gg in zip(vec, tot))
+    got = fisher_diag(runner.engine, vec, [(cali[i:i + 2], frames[i:i + 2]) for i in range(0, 8, 2)])
+    assert got == pytest.approx(want, rel=2e-3)
