@@ -1,0 +1,152 @@
+"""Mixed-precision bit assignment by sensitivity score (reference: methods/bit_assign.py): same flags,
+same two-candidate tables and log lines; the candidates are farmed out one per GPU under torchrun and
+the scores gathered.
+
+    python -m neuroquant_b200.methods.bit_assign --config ... --arch hnerv --data_path bunny --vid Bunny \\
+        --batch_size 2 --channel_wise --init max --mode omega --ckpt epoch300.pth
+"""
+import argparse
+import copy
+import logging
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+from ..parallel import candidates_of_rank, gather_scores
+from ..quantization import QuantModel
+from ..runner import DecoderRunner
+from ..sensitivity import OmegaEvaluator, fisher_diag
+from ..utils import data_split, get_config, setup_logger, worker_init_fn
+from ..videosets import VideoDataSet
+from .common import build_model, evaluate, init_distributed
+
+# toy examples of the reference (bit_assign.py:28-36)
+hnerv_candidate = {"candidate1": [2, 3, 4, 6, 4, 4, 2], "candidate2": [6, 5, 4, 5, 5, 6, 6]}
+nerv_candidate = {"candidate1": [5, 6, 3, 4, 5, 4, 3], "candidate2": [6, 5, 5, 6, 7, 6, 7]}
+
+
+def sensitivity_criterion(mode, arch, net, qnn, dataloader, use_cuda=True, max_batches=10):
+    """bit_assign.py:171-217.  `net` is the full-precision model, `qnn` the QuantModel whose perturbation
+    W - Q(W) is scored; the first 10 batches of `dataloader` are used (:115-117)."""
+    vec = qnn.get_perturbation()
+    runner = DecoderRunner.of(net)
+    for l in runner.layers:
+        if hasattr(l, "set_quant_state"):
+            l.set_quant_state(False)
+    runner.sync()
+    device = next(net.parameters()).device
+    batches = []
+    with torch.no_grad():
+        for i, sample in enumerate(dataloader):
+            img = sample["img"].to(device)
+            embed = net.encode(img) if arch == "hnerv" else net.encode(sample["norm_idx"].to(device))
+            batches.append((embed, img))
+            if len(batches) >= max_batches:
+                break
+    if mode == "omega":
+        ev = OmegaEvaluator(runner.engine)
+        n, _, h0, w0 = batches[0][0].shape
+        for embed, img in batches:
+            if embed.shape[0] != n:  # a ragged last batch gets its own plan
+                n = embed.shape[0]
+            ev.set_direction(vec, embed.shape[0], h0, w0) if ev._v is None or embed.shape[0] != n else None
+            ev.add_batch(embed, img)
+        return torch.tensor(ev.value())
+    if mode == "fisher_diag":
+        return torch.tensor(fisher_diag(runner.engine, vec, batches))
+    raise ValueError("Not implemented sensitivity criteria: {}".format(mode))
+
+
+def assign(args, cfg):
+    rank, world, _ = init_distributed()
+    device = "cuda"
+    full_dataset = VideoDataSet(cfg, args)
+    gen = torch.Generator()
+    gen.manual_seed(args.seed)
+    loader = torch.utils.data.DataLoader(full_dataset, batch_size=args.batch_size, shuffle=True, num_workers=cfg["workers"],
+                                         pin_memory=True, drop_last=False, worker_init_fn=worker_init_fn, generator=gen)
+    args.final_size = full_dataset.final_size
+    args.full_data_length = len(full_dataset)
+    split = [int(x) for x in args.data_split.split("_")]
+    _, args.val_ind_list = data_split(list(range(args.full_data_length)), split, False, 0)
+    model = build_model(args, cfg).to(device)
+    args.outf = os.path.join(args.outf, f"Encoder_{round(args.encoder_param, 2)}M_Decoder_{round(args.decoder_param, 2)}M_"
+                                        f"Total_{round(args.total_param, 2)}M")
+    args.outf = os.path.join(args.outf, "sensitivity-{}_{}-init_batch{}_CW".format(args.mode, args.init, args.batch_size))
+    if rank == 0:
+        os.makedirs(args.outf, exist_ok=True)
+        setup_logger(args.outf + "/" + time.strftime("%Y%m%d_%H%M%S") + ".log")
+    assert args.ckpt != "None"
+    model.load_state_dict(torch.load(args.ckpt, map_location="cpu"), strict=False)
+    model.to(device)
+    logging.info("=======================Full-precision model========================")
+    _, _, embedding_list = evaluate(model, loader, args, cfg)
+    cali_data = torch.cat(embedding_list, dim=0)
+    candidate_dict = hnerv_candidate if args.arch == "hnerv" else nerv_candidate
+    names = list(candidate_dict)
+    local = []
+    for ci in candidates_of_rank(len(names), rank, world):
+        bits = candidate_dict[names[ci]]
+        wq_params = {"n_bits": 8, "channel_wise": args.channel_wise, "scale_method": args.init}
+        qnn = QuantModel(model=copy.deepcopy(model), hadamard=args.hadamard, weight_quant_params=wq_params).to(device)
+        qnn.eval()
+        avg_bits = float(qnn.set_bitwidth(bits))
+        qnn.set_quant_state(True)
+        _ = qnn(cali_data[:args.batch_size].to(device))
+        logging.info(f"[{names[ci]}: {bits}] Average Quantization Bit-Width:\t{avg_bits:.4f}")
+        score = sensitivity_criterion(args.mode, args.arch, copy.deepcopy(model), qnn, loader, use_cuda=True).item()
+        logging.info(f"[{names[ci]}: {bits}] The {args.mode} sensitivity score =\t{score:.3e}")
+        local.append((ci, score))
+    scores = gather_scores(local, len(names))
+    best = int(np.argmin(scores))
+    logging.info("=" * 60)
+    logging.info(f"Best Candidate: {names[best]}")
+    logging.info(f"Bit Configuration: {candidate_dict[names[best]]}")
+    logging.info(f"Minimum Score: {scores[best]:.4e}")
+    logging.info("=" * 60)
+    return names[best], candidate_dict[names[best]], scores[best]
+
+
+def parse_args(argv):
+    p = argparse.ArgumentParser(description="running parameters", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("--seed", default=903, type=int)
+    p.add_argument("--outf", default="unify")
+    p.add_argument("--config", type=str)
+    p.add_argument("--arch", type=str)
+    p.add_argument("-p", "--print-freq", default=50, type=int)
+    p.add_argument("--data_path", type=str)
+    p.add_argument("--vid", type=str)
+    p.add_argument("--data_split", type=str, default="1_1_1")
+    p.add_argument("--batch_size", default=12, type=int)
+    p.add_argument("--hadamard", action="store_true")
+    p.add_argument("--channel_wise", action="store_true")
+    p.add_argument("--init", default="max", type=str, choices=["max", "mse", "gaussian", "l1", "l2"])
+    p.add_argument("--mode", default="omega", type=str, choices=["omega", "fisher_diag"])
+    p.add_argument("--ckpt", default="None", type=str)
+    return p.parse_args(argv)
+
+
+def seed_all(seed=903):
+    random.seed(seed)
+    np.random.seed(seed)
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
+def main(argv):
+    seed_all()
+    args = parse_args(argv)
+    cfg = get_config(args.config)
+    args.outf = os.path.join("results", args.outf)
+    args.exp_id = f"{args.vid}_e{cfg['epoch']}_b{cfg['batch_size']}_lr{cfg['learning_rate']}_{cfg['loss']}"
+    args.outf = os.path.join(args.outf, args.exp_id)
+    assign(args, cfg)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

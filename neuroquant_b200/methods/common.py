@@ -1,0 +1,84 @@
+"""Shared pieces of the two command lines: model construction, evaluation, distributed setup."""
+import logging
+import os
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from ..models import HNeRV, NeRV
+from ..parallel import frame_range_of_rank, world_info
+from ..utils import RoundTensor, psnr_fn_batch
+
+
+def init_distributed():
+    """torchrun sets RANK / LOCAL_RANK / WORLD_SIZE: one process per GPU over NCCL.  Additive to the
+    reference, which is single-GPU."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("neuroquant_b200 needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world_info()
+
+
+def build_model(args, cfg):
+    """calibrate_network.py:168-186 / bit_assign.py:286-300: model + the parameter counts used in the
+    output directory name."""
+    if args.arch == "hnerv":
+        model = HNeRV(cfg)
+        enc = sum(p.data.nelement() for p in model.encoder.parameters()) / 1e6
+        dec = sum(p.data.nelement() for p in model.decoder.parameters()) / 1e6
+        embed = float(cfg["enc_channel"][-1]) / np.prod(cfg["enc_strides"]) ** 2 * args.final_size * args.full_data_length
+        total = dec + embed / 1e6
+    elif args.arch == "nerv":
+        model = NeRV(cfg)
+        enc, embed = 0.0, 0.0
+        dec = sum(p.data.nelement() for p in model.decoder.parameters()) / 1e6
+        total = dec
+    else:
+        raise ValueError("model arch wrong!")
+    args.encoder_param, args.decoder_param, args.total_param = enc, dec, total
+    return model
+
+
+@torch.no_grad()
+def evaluate(model, full_dataloader, args, cfg, dump_vis=False):
+    """calibrate_network.py:82-145: decode every frame, PSNR per frame (device kernel), FPS from the
+    per-call decode time.  MS-SSIM is not computed (eval cosmetic); the log line prints
+    PSNR and FPS in the reference's format.  Under torch.distributed every rank decodes a contiguous
+    range of frames (decode sharding) and the metrics are gathered."""
+    rank, world, group = world_info()
+    model.eval()
+    device = next(model.parameters()).device
+    embeds, psnrs, idxs, dec_times = [], [], [], []
+    n_batches = len(full_dataloader)
+    lo, hi = frame_range_of_rank(n_batches, rank, world)
+    for i, sample in enumerate(full_dataloader):
+        img, norm_idx, img_idx = sample["img"].to(device), sample["norm_idx"].to(device), sample["idx"].to(device)
+        embed = model.encode(img) if args.arch == "hnerv" else model.encode(norm_idx)
+        embeds.append(embed)
+        if not (lo <= i < hi):
+            continue
+        img_out, _, dec_time = model.decode(embed)
+        dec_times.append(dec_time)
+        psnrs.append(psnr_fn_batch([img_out], img)[0])
+        idxs.append(img_idx.cpu())
+        if (i - lo) % args.print_freq == 0 or i == hi - 1:
+            fps = cfg["batch_size"] / (sum(dec_times) / len(dec_times))
+            logging.info("[{}], Eval at Step [{}/{}], FPS {}, PSNR {}".format(
+                datetime.now().strftime("%Y/%m/%d %H:%M:%S"), i + 1, n_batches, round(fps, 1),
+                RoundTensor(torch.cat(psnrs).mean().view(1), 2)))
+    psnr = torch.cat(psnrs) if psnrs else torch.zeros(0)
+    if world > 1:
+        bucket = [None] * world
+        torch.distributed.all_gather_object(bucket, (psnr, sum(dec_times), len(dec_times)), group=group)
+        psnr = torch.cat([b[0] for b in bucket])
+        args.fps = cfg["batch_size"] * sum(b[2] for b in bucket) / max(1e-12, sum(b[1] for b in bucket)) * world
+    else:
+        args.fps = cfg["batch_size"] / (sum(dec_times) / max(1, len(dec_times)))
+    model.train()
+    h, w = img.shape[-2:]
+    return [psnr.mean().view(1)], (h, w), embeds
