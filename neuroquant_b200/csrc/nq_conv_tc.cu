@@ -21,7 +21,7 @@
 //     per-channel scale applied in the epilogue) or are split as well; the product is accumulated as
 //     hi*hi + lo*hi + hi*lo in fp32.
 //
-// Warp roles (512 threads): warps 0-7 epilogue (TMEM -> registers -> global), warps 8-11 activation loaders
+// Warp roles (512 threads): warps 0-3 epilogue (TMEM -> registers -> global), warps 4-11 activation loaders
 // (fp32 -> bf16 hi/lo), warp 12 weight-stage producer, warp 13 MMA issuer, warp 14 TMEM allocator.
 #include <cuda_bf16.h>
 
@@ -30,6 +30,7 @@
 namespace nq {
 
 constexpr int TC_THREADS = 512;
+constexpr int TC_LOADERS = 256;  // warps 4-11
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 8;
 
@@ -239,10 +240,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(A_FULL + i * 8, 4);
+      mbar_init(A_FULL + i * 8, TC_LOADERS / 32);
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
-      mbar_init(T_EMPTY + i * 8, 8);
+      mbar_init(T_EMPTY + i * 8, 4);
     }
     for (int i = 0; i < p.n_bstages; ++i) {
       mbar_init(B_FULL + i * 8, 1);
@@ -386,9 +387,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       if (leader) umma_commit(T_FULL + acc * 8);
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== activation loaders: fp32 NHWC -> bf16 hi/lo halo tile =====================
-    const int ltid = threadIdx.x - 8 * 32;
+    const int ltid = threadIdx.x - 4 * 32;
     const int npix = p.PW * p.PH;
     uint32_t uc = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
@@ -401,12 +402,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         mbar_wait(A_EMPTY + abuf * 8, ((uc >> 1) & 1) ^ 1);
         uint8_t* dst = smem + 256 + (size_t)abuf * p.a_buf_bytes;
         const int tasks = npix * ncg;
-        for (int i0 = ltid; i0 < tasks; i0 += 128 * 4) {
+        for (int i0 = ltid; i0 < tasks; i0 += TC_LOADERS * 4) {
           float4 va[4], vb[4];
           int off[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 128;
+            const int i = i0 + u * TC_LOADERS;
             va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             off[u] = -1;
             if (i < tasks) {
@@ -437,12 +438,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) mbar_arrive(A_FULL + abuf * 8);
       }
     }
-  } else if (warp < 8) {
-    // ===================== epilogue: TMEM -> registers -> global (8 warps) =====================
-    // Two warps per TMEM lane quarter; they take alternate 16-column chunks.  Per chunk: the global
+  } else if (warp < 4) {
+    // ===================== epilogue: TMEM -> registers -> global (4 warps) =====================
+    // One warp per TMEM lane quarter.  Per 16-column chunk: the global
     // operands (scale / bias, or z of the previous stage) are requested BEFORE waiting on the TMEM load.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = warp >> 2;
+    const int half = 0;
     const int m = q * 32 + lane;
     const int ly = m >> 3, lx = m & 7;
     uint32_t tcnt = 0;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                    (size_t)(si * p.rw + sj) * p.N;
         zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.N;
       }
-      for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
+      for (int c0 = half * 16; c0 < tc.nt; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         const int nb = tc.n0 + c0;
