@@ -21,16 +21,16 @@
 //     per-channel scale applied in the epilogue) or are split as well; the product is accumulated as
 //     hi*hi + lo*hi + hi*lo in fp32.
 //
-// Warp roles (512 threads): warps 0-3 epilogue (TMEM -> registers -> global), warps 4-11 activation loaders
-// (fp32 -> bf16 hi/lo), warp 12 weight-stage producer, warp 13 MMA issuer, warp 14 TMEM allocator.
+// Warp roles (640 threads): warps 0-7 epilogue (TMEM -> registers -> global), warps 8-15 activation loaders
+// (fp32 -> bf16 hi/lo), warp 16 weight-stage producer, warp 17 MMA issuer, warp 18 TMEM allocator.
 #include <cuda_bf16.h>
 
 #include "nq_common.cuh"
 
 namespace nq {
 
-constexpr int TC_THREADS = 512;
-constexpr int TC_LOADERS = 256;  // warps 4-11
+constexpr int TC_THREADS = 640;
+constexpr int TC_LOADERS = 256;  // warps 8-15
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 8;
 
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(A_FULL + i * 8, TC_LOADERS / 32);
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
-      mbar_init(T_EMPTY + i * 8, 4);
+      mbar_init(T_EMPTY + i * 8, 8);
     }
     for (int i = 0; i < p.n_bstages; ++i) {
       mbar_init(B_FULL + i * 8, 1);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     fence_barrier_init();
   }
-  if (warp == 14) {
+  if (warp == 18) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int taps = p.ks * p.ks;
   const int ncb = (p.C + p.KC - 1) / p.KC;
 
-  if (warp == 12) {
+  if (warp == 16) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
     if (lane == 0) {
       const int nsb_full = p.KC / p.SBC;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == 17) {
     // ===================== MMA issuer =====================
     // The issue loop is the critical path of the kernel: one MMA has to leave every ~nt/2 cycles.  All 32
     // lanes run the (warp-uniform) loop so that the address arithmetic stays on the uniform datapath; lane 0
@@ -387,9 +387,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       if (leader) umma_commit(T_FULL + acc * 8);
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 8 && warp < 16) {
     // ===================== activation loaders: fp32 NHWC -> bf16 hi/lo halo tile =====================
-    const int ltid = threadIdx.x - 4 * 32;
+    const int ltid = threadIdx.x - 8 * 32;
     const int npix = p.PW * p.PH;
     uint32_t uc = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
@@ -438,12 +438,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) mbar_arrive(A_FULL + abuf * 8);
       }
     }
-  } else if (warp < 4) {
-    // ===================== epilogue: TMEM -> registers -> global (4 warps) =====================
-    // One warp per TMEM lane quarter.  Per 16-column chunk: the global
+  } else if (warp < 8) {
+    // ===================== epilogue: TMEM -> registers -> global (8 warps) =====================
+    // Two warps per TMEM lane quarter; they take alternate 16-column chunks.  Per chunk: the global
     // operands (scale / bias, or z of the previous stage) are requested BEFORE waiting on the TMEM load.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = 0;
+    const int half = warp >> 2;
     const int m = q * 32 + lane;
     const int ly = m >> 3, lx = m & 7;
     uint32_t tcnt = 0;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                    (size_t)(si * p.rw + sj) * p.N;
         zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.N;
       }
-      for (int c0 = half * 16; c0 < tc.nt; c0 += 16) {
+      for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         const int nb = tc.n0 + c0;
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / signal its barriers
-  if (warp == 14) {
+  if (warp == 18) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -644,20 +644,34 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->a_planes = a_planes;
   pl->b_planes = b_planes;
   pl->NT = N < 256 ? N : 256;
-  // B stage: the largest channel count of {64,48,32,16} that divides C and keeps a stage <= 24 KB
-  int sbc = 16;
-  const int cand[4] = {64, 48, 32, 16};
-  for (int i = 0; i < 4; ++i)
-    if (C % cand[i] == 0 && pl->NT * cand[i] * 2 * b_planes <= 24 * 1024) { sbc = cand[i]; break; }
-  pl->SBC = sbc;
-  pl->KC = sbc * (64 / sbc > 0 ? 64 / sbc : 1);  // largest multiple of SBC <= 64 (48 stays 48)
-  if (pl->KC > C) pl->KC = C;
   pl->PW = TILE_W + d->ksize - 1;
   pl->PH = TILE_H + d->ksize - 1;
   int npix = pl->PW * pl->PH;
-  int cgs16 = npix;  // channel-group stride in 16-byte units, forced to 1 mod 8 (conflict-free loader stores)
+  int cgs16 = npix;  // channel-group stride in 16-byte units, forced to 1 mod 8
   while (cgs16 % 8 != 1) ++cgs16;
   pl->CGS = cgs16 * 16;
+  // Weight stage = SBC channels of one tap; activation unit = KC channels of the halo tile.  Big stages
+  // amortise the per-stage barrier round trips of the producer and issuer threads (a 6 KB stage is only
+  // ~270 MMA cycles), so take the largest SBC (multiple of 16 dividing C) whose stage is <= 32 KB and that
+  // leaves room for two activation buffers and >= 3 weight stages in the 227 KB of shared memory.
+  int best = 0;
+  for (int sbc = (C < 128 ? C : 128) / 16 * 16; sbc >= 16; sbc -= 16) {
+    if (C % sbc) continue;
+    const int stage = pl->NT * sbc * 2 * b_planes;
+    if (stage > 32 * 1024 && sbc > 16) continue;
+    int kc = sbc >= 64 ? sbc : sbc * (64 / sbc);
+    if (kc > C) kc = C;
+    const int a_buf = pl->CGS * (kc / 8) * a_planes;
+    const int budget = 227 * 1024 - 256 - 2 * a_buf;
+    if (budget < 3 * stage) continue;
+    best = sbc;
+    break;
+  }
+  if (!best) return NQ_ERR_UNSUPPORTED;
+  const int sbc = best;
+  pl->SBC = sbc;
+  pl->KC = sbc >= 64 ? sbc : sbc * (64 / sbc);
+  if (pl->KC > C) pl->KC = C;
   pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
   pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
   pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes;
