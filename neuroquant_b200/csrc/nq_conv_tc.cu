@@ -52,6 +52,8 @@ struct TcParams {
   int tiles_x, tiles_y, tiles_n, total_tiles;
   int PW, PH, CGS;       // halo width/height (pixels), channel-group stride (bytes)
   int a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages;
+  int in_stride, c_valid;  // channels per pixel stored in `in` (<= C) : channels >= c_valid are read as zero
+  int n_store;           // dgrad: columns actually stored / row stride of zprev and out (<= N, N padded to 16)
   int cs;                // CTAs per cluster sharing every weight stage by TMA multicast (1, 2 or 4)
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
 };
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t uc = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
-      const float* img = p.in + (size_t)tc.img * p.h * p.w * p.C;
+      const float* img = p.in + (size_t)tc.img * p.h * p.w * p.in_stride;
       for (int cb = 0; cb < ncb; ++cb, ++uc) {
         const uint32_t abuf = uc & 1;
         const int c0 = cb * p.KC;
@@ -417,9 +419,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
               off[u] = cgi * p.CGS + pix * 16;
               if (tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
-                const float4* src = reinterpret_cast<const float4*>(img + ((size_t)gy * p.w + gx) * p.C + c0 + cgi * 8);
-                va[u] = __ldg(src);
-                vb[u] = __ldg(src + 1);
+                const int ch = c0 + cgi * 8;
+                const float4* src = reinterpret_cast<const float4*>(img + ((size_t)gy * p.w + gx) * p.in_stride + ch);
+                if (ch < p.c_valid) va[u] = __ldg(src);
+                if (ch + 4 < p.c_valid) vb[u] = __ldg(src + 1);
               }
             }
           }
@@ -461,9 +464,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         row_base = (((size_t)tc.img * (p.h * p.rh) + (size_t)y * p.rh) * (p.w * p.rw) + (size_t)x * p.rw) * p.cg;
       } else {
         const int qh = y / p.rh, si = y - qh * p.rh, qw = x / p.rw, sj = x - qw * p.rw;
-        row_base = (((size_t)tc.img * (p.h / p.rh) + qh) * (p.w / p.rw) + qw) * ((size_t)p.rh * p.rw * p.N) +
-                   (size_t)(si * p.rw + sj) * p.N;
-        zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.N;
+        row_base = (((size_t)tc.img * (p.h / p.rh) + qh) * (p.w / p.rw) + qw) * ((size_t)p.rh * p.rw * p.n_store) +
+                   (size_t)(si * p.rw + sj) * p.n_store;
+        zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.n_store;
       }
       for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (p.epi == 0) {
             if (p.scale) g0[qd] = __ldg(reinterpret_cast<const float4*>(p.scale + nb + qd * 4));
             if (p.bias) g1[qd] = __ldg(reinterpret_cast<const float4*>(p.bias + nb + qd * 4));
-          } else if (valid && p.zprev && p.act == 1) {
+          } else if (valid && p.zprev && p.act == 1 && nb + qd * 4 < p.n_store) {
             g0[qd] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow + nb + qd * 4));
           }
         }
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             c += 4;
             if (c >= p.cg) { c -= p.cg; ++grp; }
-          } else if (valid) {
+          } else if (valid && nb + qd * 4 < p.n_store) {
             if (p.zprev && p.act == 1) {
               r.x *= gelu_grad_fast(g0[qd].x); r.y *= gelu_grad_fast(g0[qd].y);
               r.z *= gelu_grad_fast(g0[qd].z); r.w *= gelu_grad_fast(g0[qd].w);
@@ -635,8 +638,12 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   if (st) return st;
   if (!pl || (dir != 0 && dir != 1) || a_planes < 1 || a_planes > 2 || b_planes < 1 || b_planes > 2) return NQ_ERR_BAD_ARG;
   const int nout_p = d->rh * d->rw * d->cg;
-  const int C = dir == 0 ? d->cin_p : nout_p;
-  const int N = dir == 0 ? nout_p : d->cin_p;
+  int C = dir == 0 ? d->cin_p : nout_p;
+  int N = dir == 0 ? nout_p : d->cin_p;
+  if (dir == 1) {  // data gradient: both GEMM dims may be padded to 16 (zero weights / unread columns)
+    C = (C + 15) / 16 * 16;
+    N = (N + 15) / 16 * 16;
+  }
   if (C % 16 || N % 16 || d->ksize > 7) return NQ_ERR_BAD_SHAPE;
   pl->dir = dir;
   pl->C = C;
@@ -736,6 +743,8 @@ extern "C" int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, in
 
 static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, cudaStream_t s) {
   p.n = d->n; p.h = d->h; p.w = d->w; p.C = pl->C; p.ks = d->ksize; p.pad = d->ksize / 2;
+  if (p.in_stride == 0) { p.in_stride = pl->C; p.c_valid = pl->C; }
+  if (p.n_store == 0) p.n_store = pl->N;
   p.N = pl->N; p.NT = pl->NT; p.KC = pl->KC; p.SBC = pl->SBC; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_n = pl->tiles_n; p.total_tiles = pl->total_tiles;
   p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS;
@@ -791,5 +800,8 @@ extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, con
   p.in = dz; p.wpk = reinterpret_cast<const uint8_t*>(wpk_t); p.scale = nullptr; p.bias = nullptr;
   p.zprev = z_prev; p.out_z = nullptr; p.out_y = dz_prev; p.epi = 1;
   p.rh = prev_rh; p.rw = prev_rw; p.cg = d->cin_p; p.act = prev_act;
+  p.in_stride = d->rh * d->rw * d->cg;  // dz as stored: nout_p channels per pixel
+  p.c_valid = p.in_stride;
+  p.n_store = d->cin_p;
   return launch_tc(d, pl, p, as_stream(stream));
 }

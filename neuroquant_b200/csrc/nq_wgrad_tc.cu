@@ -37,6 +37,7 @@ struct WgParams {
   int tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
   int a_planes, b_planes;
   int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
+  int dz_stride, n_valid;  // channels per pixel stored in dz (<= N); columns >= n_valid are zero
 };
 
 // ---- PTX helpers (same conventions as nq_conv_tc.cu) ----
@@ -281,9 +282,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             oo[u] = cg * p.CGS_B + (r * WG_TW + xl) * 16;
             const int gy = y0 + r, gx = x0 + xl;
             if (gy < p.h && gx < p.w) {
-              const float4* src = reinterpret_cast<const float4*>(p.dz + (((size_t)img * p.h + gy) * p.w + gx) * p.N + n0 + cg * 8);
-              va[u] = __ldg(src);
-              vb[u] = __ldg(src + 1);
+              const int ch = n0 + cg * 8;
+              const float4* src = reinterpret_cast<const float4*>(p.dz + (((size_t)img * p.h + gy) * p.w + gx) * p.dz_stride + ch);
+              if (ch < p.n_valid) va[u] = __ldg(src);
+              if (ch + 4 < p.n_valid) vb[u] = __ldg(src + 1);
             }
           }
         }
@@ -368,8 +370,9 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   int st = check_conv_desc(d);
   if (st) return st;
   if (!pl || a_planes < 1 || a_planes > 2 || b_planes < 1 || b_planes > 2) return NQ_ERR_BAD_ARG;
-  const int C = d->cin_p, N = d->rh * d->rw * d->cg;
-  if (C % 8 || N % 16 || d->ksize > 7) return NQ_ERR_BAD_SHAPE;
+  const int C = d->cin_p;
+  const int N = (d->rh * d->rw * d->cg + 15) / 16 * 16;  // padded columns are zero-filled by the loader
+  if (C % 8 || d->ksize > 7) return NQ_ERR_BAD_SHAPE;
   pl->C = C; pl->N = N; pl->a_planes = a_planes; pl->b_planes = b_planes;
   pl->ncg = C / 8;
   pl->G = d->ksize * pl->ncg;
@@ -431,6 +434,8 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.tiles_per_split = pl->tiles_per_split; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.CGS_A = pl->CGS_A; p.CGS_B = pl->CGS_B; p.a_plane_bytes = pl->a_plane_bytes; p.b_plane_bytes = pl->b_plane_bytes;
   p.buf_bytes = pl->buf_bytes; p.nbuf = pl->nbuf;
+  p.dz_stride = d->rh * d->rw * d->cg;
+  p.n_valid = p.dz_stride;
   cudaStream_t s = as_stream(stream);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int grid = pl->psplits * pl->nsplits * d->ksize;

@@ -212,6 +212,13 @@ class _Plan:
                             "nq_tc_plan_conv")
                     pl.cluster = eng.cluster
                 self.tc_dgrad.append(pl)
+            self.tc_head_dgrad = None
+            if train and last > 0:
+                pl = L.TcPlan()
+                L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[last]), 1, eng.bwd_a_planes, eng.bwd_b_planes, C.byref(pl)),
+                        "nq_tc_plan_conv")
+                pl.cluster = eng.cluster
+                self.tc_head_dgrad = pl
 
 
 class DecoderEngine:
@@ -350,6 +357,11 @@ class DecoderEngine:
                                   torch.ones(d.nout_p, device=self.device)))
             else:
                 self._tcw.append(None)
+        self._head_dgrad = None
+        if self.use_tc and last > 0:
+            pl = L.TcPlan()
+            L.check(L.lib.nq_tc_plan_conv(C.byref(p.desc[last]), 1, 2, 2, C.byref(pl)), "nq_tc_plan_conv")
+            self._head_dgrad = torch.zeros(pl.wpk_bytes, dtype=torch.uint8, device=self.device)
 
     # ------------------------------------------------------------------ weights
     def prepare_weights(self, p: _Plan, need_wt: bool, reg_b: Optional[float] = None):
@@ -379,9 +391,14 @@ class DecoderEngine:
                     self.launches += 1
                 w_for_conv, b_for_conv, cin_src = deq_w, deq_b, s.cin_src
             if self._tcw[i] is None:
+                head_tc = need_wt and self._head_dgrad is not None and i == len(self.stages) - 1 and p.tc_head_dgrad is not None
                 L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(w_for_conv), cin_src, L.ptr(b_for_conv), L.ptr(wk),
-                                             L.ptr(wt) if need_wt else None, L.ptr(bp), st), "nq_pack_weight")
+                                             L.ptr(wt) if (need_wt and not head_tc) else None, L.ptr(bp), st), "nq_pack_weight")
                 self.launches += 1
+                if head_tc:
+                    L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_head_dgrad), L.ptr(w_for_conv), cin_src, None, 0,
+                                                    self._head_dgrad.data_ptr(), st), "nq_tc_pack_weight")
+                    self.launches += 1
                 continue
             wpk_f, wpk_d, scale_p = self._tcw[i]
             # forward operand: integer weights (codes - zero_point), exact in ONE bf16 plane, whenever the
@@ -511,8 +528,13 @@ class DecoderEngine:
         if not hasattr(p, "dwk"):
             p.dwk, p.ws = [], []
             for i, d in enumerate(p.desc):
-                p.dwk.append(torch.empty(d.kdim + 4, d.nout_p, device=self.device))
-                if i == last:
+                head_tc = i == last and self.use_tc and self.wgrad_tc and self._wg_plan(d) is not None
+                p.dwk.append(torch.empty(d.kdim + 4, 16 if head_tc else d.nout_p, device=self.device))
+                if head_tc:  # head weight gradient on the tensor cores: 3 output channels padded to N = 16
+                    pl = self._wg_plan(d)
+                    p.ws.append((torch.empty(pl.workspace_floats, device=self.device), pl))
+                    p.head_desc16 = L.ConvDesc(d.n, d.h, d.w, d.cin, d.cin_p, d.ksize, d.cout, 1, 1, d.c_grp, 16, 0)
+                elif i == last:
                     blocks = L.lib.nq_head_wgrad_blocks(C.byref(d))
                     p.ws.append((torch.empty(blocks * (d.kdim + 4) * 4, device=self.device), 0))
                 elif self.use_tc and self.wgrad_tc and d.n * d.h * d.w >= 256 and self._wg_plan(d) is not None:
@@ -525,7 +547,7 @@ class DecoderEngine:
             d = p.desc[i]
             _, wt, _, _, _ = self._packed[i]
             ws, sp = p.ws[i]
-            if i == last:
+            if i == last and not isinstance(sp, L.TcWgradPlan):
                 L.check(self._run("head_wgrad", d, L.lib.nq_head_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]), L.ptr(p.dwk[i]),
                                   L.ptr(ws), ws.numel(), st), "nq_head_wgrad")
                 self.launches += 2
@@ -539,7 +561,11 @@ class DecoderEngine:
                 self.launches += 2 if sp > 1 else 1
             if i > 0:
                 g_prev = self.geoms[i - 1]
-                if self._tcw[i] is None:
+                if i == last and self._head_dgrad is not None:
+                    L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(p.tc_head_dgrad),
+                                      L.ptr(p.dz[i]), self._head_dgrad.data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw,
+                                      _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st), "nq_tc_conv_dgrad")
+                elif self._tcw[i] is None:
                     L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
                                       L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st),
                             "nq_conv_dgrad")
@@ -550,7 +576,8 @@ class DecoderEngine:
                 self.launches += 1
             s = self.stages[i]
             gw, gb = views[i]
-            L.check(L.lib.nq_unpack_wgrad(C.byref(d), L.ptr(p.dwk[i]), s.cin_src, L.ptr(gw), L.ptr(gb), st), "nq_unpack_wgrad")
+            du = p.head_desc16 if (i == last and isinstance(sp, L.TcWgradPlan)) else d
+            L.check(L.lib.nq_unpack_wgrad(C.byref(du), L.ptr(p.dwk[i]), s.cin_src, L.ptr(gw), L.ptr(gb), st), "nq_unpack_wgrad")
             self.launches += 1
         return flat
 
