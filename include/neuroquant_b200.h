@@ -171,6 +171,12 @@ int nq_head_fwd_loss(const nq_conv_desc* d, const float* x, const float* w_head,
                      int out_bias, const float* target, float p, float mean_pixels,
                      float* img, float* loss_sum, float* dz_head, void* stream);
 
+/* Same with the split-bf16 tensors of the tensor-core engine: x_split (n, h, w, cin_p) planes in,
+ * dz_head_split (n, h, w, 8) planes out (3 real channels + 5 zeros = one 16-byte chunk per pixel and plane). */
+int nq_head_fwd_loss_split(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                           int out_bias, const float* target, float p, float mean_pixels,
+                           float* img, float* loss_sum, void* dz_head_split, void* stream);
+
 /* Head weight/bias gradient: dwk_head [(9*cin_p + 4)][4] as nq_conv_wgrad; workspace >= blocks*(9*cin_p+4)*4
  * floats with blocks = nq_head_wgrad_blocks(d). */
 int nq_head_wgrad_blocks(const nq_conv_desc* d);
@@ -180,7 +186,7 @@ int nq_head_wgrad(const nq_conv_desc* d, const float* x, const float* dz_head, f
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM) convolution path: same contract as nq_conv_fwd / nq_conv_dgrad, bf16
  * operands split hi + lo so that products carry 16 mantissa bits, fp32 accumulation in TMEM.
- * Channel contract: cin_p and rh*rw*cg must be multiples of 16.
+ * Channel contract: cin_p a multiple of 8; GEMM dims are padded to 16 internally (zero channels / unwritten columns).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct nq_tc_plan {
   int32_t dir;                 /* 0 forward, 1 data gradient */
@@ -210,14 +216,28 @@ int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* plan, const float
 int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, int d_stride, const float* bias_ref,
                         float* scale_packed, float* bias_packed, void* stream);
 
-/* y = act(shuffle(conv(x) * scale + bias)); arguments as nq_conv_fwd (scale_packed may be NULL). */
-int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* plan, const float* x, const void* wpk,
-                   const float* scale_packed, const float* bias_packed, float* z, float* y, void* stream);
+/* "split-bf16" storage: a tensor-core stage reads and writes its activations / gradients as TWO bf16
+ * planes, hi = bf16(v) and lo = bf16(v - hi), plane 0 then plane 1, each NHWC with the padded channel
+ * count of the fp32 layout (same bytes as fp32, 16 mantissa bits).  The producing epilogue converts once;
+ * consumers copy 16-byte chunks asynchronously.  Pre-activations (z) stay fp32. */
 
-/* dz_prev = unshuffle(conv_transpose(dz) * act'(z_prev)); arguments as nq_conv_dgrad, wpk_t packed with a
- * dir = 1 plan from the DE-QUANTISED weights. */
-int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* plan, const float* dz, const void* wpk_t,
-                     const float* z_prev, int prev_rh, int prev_rw, int prev_act, float* dz_prev, void* stream);
+/* y = act(shuffle(conv(x) * scale + bias)).  x_split (n, h, w, cin_p) and y_split (n, h*rh, w*rw, cg) are
+ * split-bf16; z (fp32, same shape as y) receives the pre-activation.  Either output may be NULL (not both);
+ * scale_packed / bias_packed may be NULL. */
+int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* plan, const void* x_split, const void* wpk,
+                   const float* scale_packed, const float* bias_packed, float* z, void* y_split, void* stream);
+
+/* dz_prev = unshuffle(conv_transpose(dz) * act'(z_prev)).  dz_split (n, h, w, nout_p rounded up to 8) and
+ * dz_prev_split (n, h/prev_rh, w/prev_rw, prev_rh*prev_rw*cin_p) are split-bf16, z_prev fp32; wpk_t is
+ * packed with a dir = 1 plan from the DE-QUANTISED weights. */
+int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* plan, const void* dz_split, const void* wpk_t,
+                     const float* z_prev, int prev_rh, int prev_rw, int prev_act, void* dz_prev_split, void* stream);
+
+/* Edges of the split-bf16 domain.  NCHW fp32 (n, c, h, w) <-> split NHWC (n, h, w, c_p); flat fp32 <-> split. */
+int nq_nchw_to_split(const float* src, void* dst_split, int n, int c, int h, int w, int c_p, void* stream);
+int nq_split_to_nchw(const void* src_split, float* dst, int n, int c, int h, int w, int c_p, void* stream);
+int nq_f32_to_split(const float* src, void* dst_split, int64_t numel, void* stream);
+int nq_split_to_f32(const void* src_split, float* dst, int64_t numel, void* stream);
 
 /* Weight + bias gradient on the tensor cores; output contract identical to nq_conv_wgrad (dwk
  * [(kdim + 4)][nout_p], bias gradient in row kdim).  cin_p % 8 == 0, rh*rw*cg % 16 == 0. */
@@ -229,7 +249,8 @@ typedef struct nq_tc_wgrad_plan {
   int64_t workspace_floats;    /* partial-gradient workspace the caller provides */
 } nq_tc_wgrad_plan;
 int nq_tc_plan_wgrad(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc_wgrad_plan* plan);
-int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* plan, const float* x, const float* dz,
+/* x_split (n, h, w, cin_p) and dz_split (n, h, w, nout_p rounded up to 8) are split-bf16. */
+int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* plan, const void* x_split, const void* dz_split,
                      float* dwk, float* workspace, int64_t workspace_floats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -241,7 +262,8 @@ int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* plan, const 
 /* z' = zd1 + zd2, z'' = zdd1 + 2*zdd2 (any of the four may be NULL = 0); act as nq_conv_desc.act.
  * y = f(z), yd = f'(z) z', ydd = f''(z) z'^2 + f'(z) z''. */
 int nq_jet_act(const float* z, const float* zd1, const float* zd2, const float* zdd1, const float* zdd2,
-               int64_t numel, int act, float* y, float* yd, float* ydd, void* stream);
+               int64_t numel, int act, void* y, void* yd, void* ydd, int split_out, void* stream);
+/* split_out = 1: y, yd, ydd are written as split-bf16 (2 * numel bf16 each) for the tensor-core convolutions. */
 /* Head pre-activations (n, h, w, 4) NHWC, target (n, 3, h, w): *omega_acc += d^2/d eps^2 of
  * nn.MSELoss(OutImg(z), target) (mean over n*3*h*w).  omega_acc is a device double the caller zeroes. */
 int nq_jet_head(const float* z, const float* zd1, const float* zd2, const float* zdd1, const float* zdd2,

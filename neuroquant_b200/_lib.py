@@ -84,8 +84,13 @@ def _load():
         "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P]),
         "nq_tc_plan_wgrad": (I, [DP, I, I, C.POINTER(TcWgradPlan)]),
         "nq_tc_conv_wgrad": (I, [DP, C.POINTER(TcWgradPlan), P, P, P, P, L, P]),
-        "nq_jet_act": (I, [P, P, P, P, P, L, I, P, P, P, P]),
+        "nq_jet_act": (I, [P, P, P, P, P, L, I, P, P, P, I, P]),
+        "nq_head_fwd_loss_split": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_jet_head": (I, [P, P, P, P, P, P, I, I, I, I, P, P]),
+        "nq_nchw_to_split": (I, [P, P, I, I, I, I, I, P]),
+        "nq_split_to_nchw": (I, [P, P, I, I, I, I, I, P]),
+        "nq_f32_to_split": (I, [P, P, L, P]),
+        "nq_split_to_f32": (I, [P, P, L, P]),
         "nq_nchw_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
         "nq_nhwc_to_nchw": (I, [P, P, I, I, I, I, I, P]),
         "nq_act_bwd_unshuffle": (I, [P, P, I, I, I, I, I, I, I, P, P]),

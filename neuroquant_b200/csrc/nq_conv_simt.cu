@@ -317,7 +317,18 @@ struct HeadParams {
   float* img; float* loss_sum; float* dz;
   int n, h, w_, C, out_bias;
   float p, inv_mean;
+  // split-bf16 variants (tensor-core engine): input planes (hi, lo) of (n, h, w, C) bf16; gradient planes of
+  // (n, h, w, 8) bf16 (3 real channels + zeros: one 16-byte chunk per pixel for the cp.async consumers)
+  const uint16_t* x_hi; const uint16_t* x_lo;
+  uint16_t* dz_hi; uint16_t* dz_lo;
 };
+
+__device__ __forceinline__ float bf16_bits_to_f(uint32_t b) { return __uint_as_float(b << 16); }
+__device__ __forceinline__ uint16_t f_to_bf16_bits(float v) {  // round to nearest even
+  uint32_t u = __float_as_uint(v);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
 
 __global__ void __launch_bounds__(HT_H * HT_W) head_fwd_loss_kernel(const HeadParams q) {
   __shared__ __align__(16) float xs[(HT_H + 2) * (HT_W + 2) * H_PS];
@@ -344,8 +355,18 @@ __global__ void __launch_bounds__(HT_H * HT_W) head_fwd_loss_kernel(const HeadPa
       const int sx = pix % (HT_W + 2), sy = pix / (HT_W + 2);
       const int gx = x0 + sx - 1, gy = y0 + sy - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c4 < c4n && (unsigned)gx < (unsigned)q.w_ && (unsigned)gy < (unsigned)q.h)
-        v = ldg4(q.x + ((int64_t)(bn * q.h + gy) * q.w_ + gx) * q.C + c0 + c4 * 4);
+      if (c4 < c4n && (unsigned)gx < (unsigned)q.w_ && (unsigned)gy < (unsigned)q.h) {
+        const int64_t o = ((int64_t)(bn * q.h + gy) * q.w_ + gx) * q.C + c0 + c4 * 4;
+        if (q.x_hi) {
+          const uint2 hb = __ldg(reinterpret_cast<const uint2*>(q.x_hi + o)), lb = __ldg(reinterpret_cast<const uint2*>(q.x_lo + o));
+          v.x = bf16_bits_to_f(hb.x & 0xFFFFu) + bf16_bits_to_f(lb.x & 0xFFFFu);
+          v.y = bf16_bits_to_f(hb.x >> 16) + bf16_bits_to_f(lb.x >> 16);
+          v.z = bf16_bits_to_f(hb.y & 0xFFFFu) + bf16_bits_to_f(lb.y & 0xFFFFu);
+          v.w = bf16_bits_to_f(hb.y >> 16) + bf16_bits_to_f(lb.y >> 16);
+        } else {
+          v = ldg4(q.x + o);
+        }
+      }
       *reinterpret_cast<float4*>(&xs[pix * H_PS + c4 * 4]) = v;
     }
     for (int i = tid; i < 9 * H_CH; i += HT_H * HT_W) {
@@ -405,6 +426,17 @@ __global__ void __launch_bounds__(HT_H * HT_W) head_fwd_loss_kernel(const HeadPa
       }
     }
     if (q.dz) *reinterpret_cast<float4*>(q.dz + ((int64_t)(bn * q.h + py) * q.w_ + px) * 4) = make_float4(g[0], g[1], g[2], 0.f);
+    if (q.dz_hi) {
+      uint16_t hb[3], lb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        hb[c] = f_to_bf16_bits(g[c]);
+        lb[c] = f_to_bf16_bits(g[c] - bf16_bits_to_f(hb[c]));
+      }
+      const int64_t o = ((int64_t)(bn * q.h + py) * q.w_ + px) * 8;
+      *reinterpret_cast<uint4*>(q.dz_hi + o) = make_uint4((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), hb[2], 0u, 0u);
+      *reinterpret_cast<uint4*>(q.dz_lo + o) = make_uint4((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), lb[2], 0u, 0u);
+    }
   }
   if (q.target && q.loss_sum) {
     loss = block_sum(loss, red);
@@ -612,6 +644,31 @@ extern "C" int nq_head_fwd_loss(const nq_conv_desc* d, const float* x, const flo
   if (!target && !img) return NQ_ERR_BAD_ARG;
   HeadParams q{};
   q.x = x; q.w = w_head; q.bias = bias_head; q.target = target; q.img = img; q.loss_sum = loss_sum; q.dz = dz_head;
+  q.n = d->n; q.h = d->h; q.w_ = d->w; q.C = d->cin_p; q.out_bias = out_bias; q.p = p;
+  q.inv_mean = target ? 1.0f / mean_pixels : 0.f;
+  const int64_t blocks = cdiv(d->w, HT_W) * cdiv(d->h, HT_H) * d->n;
+  head_fwd_loss_kernel<<<(unsigned)blocks, HT_H * HT_W, 0, as_stream(stream)>>>(q);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_head_fwd_loss_split(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                                      int out_bias, const float* target, float p, float mean_pixels, float* img,
+                                      float* loss_sum, void* dz_head_split, void* stream) {
+  int st = check_head(d);
+  if (st) return st;
+  if (!x_split || !w_head || !bias_head) return NQ_ERR_BAD_ARG;
+  if (out_bias != 0 && out_bias != 1) return NQ_ERR_UNSUPPORTED;
+  if (target && (!(p > 0.f) || !(mean_pixels > 0.f))) return NQ_ERR_BAD_ARG;
+  if (!target && !img) return NQ_ERR_BAD_ARG;
+  if (d->cin_p % 8) return NQ_ERR_BAD_SHAPE;
+  HeadParams q{};
+  const int64_t pix = (int64_t)d->n * d->h * d->w;
+  q.x = nullptr; q.w = w_head; q.bias = bias_head; q.target = target; q.img = img; q.loss_sum = loss_sum; q.dz = nullptr;
+  q.x_hi = reinterpret_cast<const uint16_t*>(x_split);
+  q.x_lo = q.x_hi + pix * d->cin_p;
+  q.dz_hi = reinterpret_cast<uint16_t*>(dz_head_split);
+  q.dz_lo = q.dz_hi ? q.dz_hi + pix * 8 : nullptr;
   q.n = d->n; q.h = d->h; q.w_ = d->w; q.C = d->cin_p; q.out_bias = out_bias; q.p = p;
   q.inv_mean = target ? 1.0f / mean_pixels : 0.f;
   const int64_t blocks = cdiv(d->w, HT_W) * cdiv(d->h, HT_H) * d->n;

@@ -20,6 +20,11 @@
 //     mantissa bits), weights either are exact in one bf16 plane (integer codes - zero_point, |v| <= 255,
 //     per-channel scale applied in the epilogue) or are split as well; the product is accumulated as
 //     hi*hi + lo*hi + hi*lo in fp32.
+//   * activations and gradients LIVE in HBM in that split form ("split-bf16": plane 0 = hi, plane 1 = lo,
+//     each NHWC bf16; same bytes as fp32): the producing epilogue converts once, every consumer (forward
+//     and wgrad of the next stage, dgrad and wgrad of this one) copies 16-byte chunks with cp.async --
+//     no conversion, no register staging, the copies of a whole halo tile are in flight at once and
+//     complete on an mbarrier (cp.async.mbarrier.arrive.noinc).
 //
 // Warp roles (640 threads): warps 0-7 epilogue (TMEM -> registers -> global), warps 8-15 activation loaders
 // (fp32 -> bf16 hi/lo), warp 16 weight-stage producer, warp 17 MMA issuer, warp 18 TMEM allocator.
@@ -35,13 +40,15 @@ constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 8;
 
 struct TcParams {
-  const float* in;       // (n, h, w, C) fp32 NHWC
+  const uint8_t* in;     // split-bf16 input: plane 0 (hi) then plane 1 (lo), each (n, h, w, in_stride) bf16
+  size_t in_plane_bytes;
   const uint8_t* wpk;    // packed bf16 weight stages
   const float* scale;    // [N] per-column scale (fwd) or null
   const float* bias;     // [N] (fwd) or null
-  const float* zprev;    // dgrad: (n, h, w, N) pre-activation of the previous stage, or null
-  float* out_z;          // fwd: pre-activation (may be null)
-  float* out_y;          // fwd: activated output; dgrad: dz_prev
+  const float* zprev;    // dgrad: (n, h, w, n_store) fp32 pre-activation of the previous stage, or null
+  float* out_z;          // fwd: fp32 pre-activation (may be null)
+  uint8_t* out_y;        // split-bf16 output (fwd: activated output, may be null; dgrad: dz_prev)
+  size_t out_plane_bytes;
   int n, h, w, C;        // input grid and GEMM-K channels (C % 16 == 0)
   int ks, pad;
   int N, NT;             // GEMM N (multiple of 16) and its tile
@@ -128,6 +135,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills (halo outside the image)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all of this thread's prior cp.async have landed (does not bump the pending count)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
@@ -196,6 +211,19 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// four consecutive channels of element index `o` -> hi and lo bf16 planes (8 bytes each)
+__device__ __forceinline__ void store_split4(uint8_t* base, size_t plane_bytes, size_t o, const float4& r) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(r.x), h1 = __float2bfloat16_rn(r.y), h2 = __float2bfloat16_rn(r.z),
+                      h3 = __float2bfloat16_rn(r.w);
+  uint2 hi, lo;
+  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lo.x = pack_bf16x2(r.x - __bfloat162float(h0), r.y - __bfloat162float(h1));
+  lo.y = pack_bf16x2(r.z - __bfloat162float(h2), r.w - __bfloat162float(h3));
+  *reinterpret_cast<uint2*>(base + o * 2) = hi;
+  *reinterpret_cast<uint2*>(base + plane_bytes + o * 2) = lo;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -242,7 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(A_FULL + i * 8, TC_LOADERS / 32);
+      mbar_init(A_FULL + i * 8, TC_LOADERS);  // one deferred arrival per loader thread
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
       mbar_init(T_EMPTY + i * 8, 8);
@@ -328,6 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int cb = 0; cb < ncb; ++cb, ++uc) {
         const uint32_t abuf = uc & 1;
         mbar_wait(A_FULL + abuf * 8, (uc >> 1) & 1);
+        fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
         tc_fence_after();
         const uint32_t a_buf16 = (((a_base + abuf * p.a_buf_bytes) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
         const int nsb = min(nsb_full, (p.C - cb * p.KC) / p.SBC);
@@ -390,55 +419,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (leader) umma_commit(T_FULL + acc * 8);
     }
   } else if (warp >= 8 && warp < 16) {
-    // ===================== activation loaders: fp32 NHWC -> bf16 hi/lo halo tile =====================
+    // ===================== activation loaders: split-bf16 NHWC -> halo tile, 16-byte cp.async =====================
     const int ltid = threadIdx.x - 8 * 32;
     const int npix = p.PW * p.PH;
     uint32_t uc = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
-      const float* img = p.in + (size_t)tc.img * p.h * p.w * p.in_stride;
+      const uint8_t* img = p.in + (size_t)tc.img * p.h * p.w * p.in_stride * 2;
       for (int cb = 0; cb < ncb; ++cb, ++uc) {
         const uint32_t abuf = uc & 1;
         const int c0 = cb * p.KC;
         const int ncg = min(p.KC, p.C - c0) >> 3;
         mbar_wait(A_EMPTY + abuf * 8, ((uc >> 1) & 1) ^ 1);
-        uint8_t* dst = smem + 256 + (size_t)abuf * p.a_buf_bytes;
+        const uint32_t dst = a_base + abuf * p.a_buf_bytes;
         const int tasks = npix * ncg;
-        for (int i0 = ltid; i0 < tasks; i0 += TC_LOADERS * 4) {
-          float4 va[4], vb[4];
-          int off[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * TC_LOADERS;
-            va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            off[u] = -1;
-            if (i < tasks) {
-              // pixel fastest: the 8 threads of a 16-byte store phase fill 8 consecutive 16-byte rows
-              const int cgi = i / npix, pix = i - cgi * npix;
-              const int py = pix / p.PW, px = pix - py * p.PW;
-              const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
-              off[u] = cgi * p.CGS + pix * 16;
-              if (tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
-                const int ch = c0 + cgi * 8;
-                const float4* src = reinterpret_cast<const float4*>(img + ((size_t)gy * p.w + gx) * p.in_stride + ch);
-                if (ch < p.c_valid) va[u] = __ldg(src);
-                if (ch + 4 < p.c_valid) vb[u] = __ldg(src + 1);
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (off[u] >= 0) {
-              uint4 hi, lo;
-              split8(va[u], vb[u], hi, lo);
-              *reinterpret_cast<uint4*>(dst + off[u]) = hi;
-              if (p.a_planes == 2) *reinterpret_cast<uint4*>(dst + p.a_plane_bytes + off[u]) = lo;
-            }
-          }
+        // pixel fastest: consecutive threads fill consecutive 16-byte rows of one channel group
+        int cgi = ltid / npix, pix = ltid - cgi * npix;
+        for (int i = ltid; i < tasks; i += TC_LOADERS) {
+          const int py = pix / p.PW, px = pix - py * p.PW;
+          const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
+          const int ch = c0 + cgi * 8;
+          const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
+          const uint8_t* src = ok ? img + (((size_t)gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
+          const uint32_t d = dst + cgi * p.CGS + pix * 16;
+          cp_async16(d, src, ok ? 16u : 0u);
+          if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
+          pix += TC_LOADERS;
+          while (pix >= npix) { pix -= npix; ++cgi; }
         }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(A_FULL + abuf * 8);
+        cp_async_arrive(A_FULL + abuf * 8);
       }
     }
   } else if (warp < 8) {
@@ -478,8 +487,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           g0[qd] = make_float4(1.f, 1.f, 1.f, 1.f);
           g1[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.epi == 0) {
-            if (p.scale) g0[qd] = __ldg(reinterpret_cast<const float4*>(p.scale + nb + qd * 4));
-            if (p.bias) g1[qd] = __ldg(reinterpret_cast<const float4*>(p.bias + nb + qd * 4));
+            if (nb + qd * 4 < p.n_store) {
+              if (p.scale) g0[qd] = __ldg(reinterpret_cast<const float4*>(p.scale + nb + qd * 4));
+              if (p.bias) g1[qd] = __ldg(reinterpret_cast<const float4*>(p.bias + nb + qd * 4));
+            }
           } else if (valid && p.zprev && p.act == 1 && nb + qd * 4 < p.n_store) {
             g0[qd] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow + nb + qd * 4));
           }
@@ -500,10 +511,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             r.z = fmaf(r.z, g0[qd].z, g1[qd].z); r.w = fmaf(r.w, g0[qd].w, g1[qd].w);
             const int si = grp / p.rw, sj = grp - si * p.rw;
             const size_t o = row_base + ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
-            if (valid) {
+            if (valid && nb + qd * 4 < p.n_store) {
               if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
-              if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
-              *reinterpret_cast<float4*>(p.out_y + o) = r;
+              if (p.out_y) {
+                if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
+                store_split4(p.out_y, p.out_plane_bytes, o, r);
+              }
             }
             c += 4;
             if (c >= p.cg) { c -= p.cg; ++grp; }
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               r.x *= gelu_grad_fast(g0[qd].x); r.y *= gelu_grad_fast(g0[qd].y);
               r.z *= gelu_grad_fast(g0[qd].z); r.w *= gelu_grad_fast(g0[qd].w);
             }
-            *reinterpret_cast<float4*>(p.out_y + row_base + nb + qd * 4) = r;
+            store_split4(p.out_y, p.out_plane_bytes, row_base + nb + qd * 4, r);
           }
         }
       }
@@ -640,10 +653,10 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   const int nout_p = d->rh * d->rw * d->cg;
   int C = dir == 0 ? d->cin_p : nout_p;
   int N = dir == 0 ? nout_p : d->cin_p;
-  if (dir == 1) {  // data gradient: both GEMM dims may be padded to 16 (zero weights / unread columns)
-    C = (C + 15) / 16 * 16;
-    N = (N + 15) / 16 * 16;
-  }
+  // both GEMM dims may be padded to 16: channels >= the stored count are read as zero (c_valid), columns
+  // >= the stored count are not written (n_store)
+  C = (C + 15) / 16 * 16;
+  N = (N + 15) / 16 * 16;
   if (C % 16 || N % 16 || d->ksize > 7) return NQ_ERR_BAD_SHAPE;
   pl->dir = dir;
   pl->C = C;
@@ -776,32 +789,123 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   return NQ_OK;
 }
 
-extern "C" int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* pl, const float* x, const void* wpk,
-                              const float* scale_packed, const float* bias_packed, float* z, float* y, void* stream) {
+extern "C" int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* pl, const void* x_split, const void* wpk,
+                              const float* scale_packed, const float* bias_packed, float* z, void* y_split,
+                              void* stream) {
   int st = check_conv_desc(d);
   if (st) return st;
-  if (!pl || pl->dir != 0 || !x || !wpk || !y) return NQ_ERR_BAD_ARG;
+  if (!pl || pl->dir != 0 || !x_split || !wpk || (!y_split && !z)) return NQ_ERR_BAD_ARG;
   TcParams p{};
-  p.in = x; p.wpk = reinterpret_cast<const uint8_t*>(wpk); p.scale = scale_packed; p.bias = bias_packed;
-  p.zprev = nullptr; p.out_z = z; p.out_y = y; p.epi = 0;
+  p.in = reinterpret_cast<const uint8_t*>(x_split);
+  p.in_plane_bytes = (size_t)d->n * d->h * d->w * d->cin_p * 2;
+  p.in_stride = d->cin_p; p.c_valid = d->cin_p;
+  p.wpk = reinterpret_cast<const uint8_t*>(wpk); p.scale = scale_packed; p.bias = bias_packed;
+  p.zprev = nullptr; p.out_z = z; p.out_y = reinterpret_cast<uint8_t*>(y_split); p.epi = 0;
+  p.out_plane_bytes = (size_t)d->n * d->h * d->rh * d->w * d->rw * d->cg * 2;
+  p.n_store = d->rh * d->rw * d->cg;
   p.rh = d->rh; p.rw = d->rw; p.cg = d->cg; p.act = d->act;
   return launch_tc(d, pl, p, as_stream(stream));
 }
 
-extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, const float* dz, const void* wpk_t,
-                                const float* z_prev, int prev_rh, int prev_rw, int prev_act, float* dz_prev,
+extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, const void* dz_split, const void* wpk_t,
+                                const float* z_prev, int prev_rh, int prev_rw, int prev_act, void* dz_prev_split,
                                 void* stream) {
   int st = check_conv_desc(d);
   if (st) return st;
-  if (!pl || pl->dir != 1 || !dz || !wpk_t || !dz_prev || prev_rh <= 0 || prev_rw <= 0) return NQ_ERR_BAD_ARG;
+  if (!pl || pl->dir != 1 || !dz_split || !wpk_t || !dz_prev_split || prev_rh <= 0 || prev_rw <= 0) return NQ_ERR_BAD_ARG;
   if (d->h % prev_rh || d->w % prev_rw) return NQ_ERR_BAD_SHAPE;
   if (prev_act != 0 && prev_act != 1) return NQ_ERR_BAD_ARG;
   TcParams p{};
-  p.in = dz; p.wpk = reinterpret_cast<const uint8_t*>(wpk_t); p.scale = nullptr; p.bias = nullptr;
-  p.zprev = z_prev; p.out_z = nullptr; p.out_y = dz_prev; p.epi = 1;
+  const int nout_p = d->rh * d->rw * d->cg;
+  const int dz_ch = (nout_p + 7) / 8 * 8;  // channels per pixel as stored (the head's 4 are stored as 8)
+  p.in = reinterpret_cast<const uint8_t*>(dz_split);
+  p.in_plane_bytes = (size_t)d->n * d->h * d->w * dz_ch * 2;
+  p.in_stride = dz_ch; p.c_valid = dz_ch;
+  p.wpk = reinterpret_cast<const uint8_t*>(wpk_t); p.scale = nullptr; p.bias = nullptr;
+  p.zprev = z_prev; p.out_z = nullptr; p.out_y = reinterpret_cast<uint8_t*>(dz_prev_split); p.epi = 1;
+  p.out_plane_bytes = (size_t)d->n * d->h * d->w * d->cin_p * 2;
   p.rh = prev_rh; p.rw = prev_rw; p.cg = d->cin_p; p.act = prev_act;
-  p.in_stride = d->rh * d->rw * d->cg;  // dz as stored: nout_p channels per pixel
-  p.c_valid = p.in_stride;
   p.n_store = d->cin_p;
   return launch_tc(d, pl, p, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-bf16 edges: fp32 <-> (hi, lo) planes
+// ------------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst,
+                                                            int n, int c, int h, int w, int c_p) {
+  const int64_t total = (int64_t)n * h * w * c_p;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dst);
+  __nv_bfloat16* lo = hi + total;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % c_p);
+    const int64_t pix = e / c_p;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+    const float v = ch < c ? src[(((int64_t)b * c + ch) * h + y) * w + x] : 0.f;
+    const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+    hi[e] = hv;
+    lo[e] = __float2bfloat16_rn(v - __bfloat162float(hv));
+  }
+}
+__global__ void __launch_bounds__(256) split_to_nchw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int n,
+                                                            int c, int h, int w, int c_p) {
+  const int64_t total = (int64_t)n * c * h * w;
+  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(src);
+  const __nv_bfloat16* lo = hi + (int64_t)n * h * w * c_p;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(e % w), y = (int)((e / w) % h);
+    const int ch = (int)((e / ((int64_t)w * h)) % c), b = (int)(e / ((int64_t)w * h * c));
+    const int64_t o = (((int64_t)b * h + y) * w + x) * c_p + ch;
+    dst[e] = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+  }
+}
+__global__ void __launch_bounds__(256) f32_to_split_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t numel) {
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dst);
+  __nv_bfloat16* lo = hi + numel;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (int64_t)gridDim.x * blockDim.x) {
+    const float v = src[e];
+    const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+    hi[e] = hv;
+    lo[e] = __float2bfloat16_rn(v - __bfloat162float(hv));
+  }
+}
+__global__ void __launch_bounds__(256) split_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t numel) {
+  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(src);
+  const __nv_bfloat16* lo = hi + numel;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (int64_t)gridDim.x * blockDim.x)
+    dst[e] = __bfloat162float(hi[e]) + __bfloat162float(lo[e]);
+}
+static inline unsigned split_grid(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+}  // namespace nq
+
+extern "C" int nq_nchw_to_split(const float* src, void* dst, int n, int c, int h, int w, int c_p, void* stream) {
+  if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_p < c) return NQ_ERR_BAD_ARG;
+  nchw_to_split_kernel<<<split_grid((int64_t)n * h * w * c_p), 256, 0, as_stream(stream)>>>(
+      src, reinterpret_cast<uint8_t*>(dst), n, c, h, w, c_p);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+extern "C" int nq_split_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int c_p, void* stream) {
+  if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_p < c) return NQ_ERR_BAD_ARG;
+  split_to_nchw_kernel<<<split_grid((int64_t)n * c * h * w), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint8_t*>(src), dst, n, c, h, w, c_p);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+extern "C" int nq_f32_to_split(const float* src, void* dst, int64_t numel, void* stream) {
+  if (!src || !dst || numel <= 0) return NQ_ERR_BAD_ARG;
+  f32_to_split_kernel<<<split_grid(numel), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<uint8_t*>(dst), numel);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+extern "C" int nq_split_to_f32(const void* src, float* dst, int64_t numel, void* stream) {
+  if (!src || !dst || numel <= 0) return NQ_ERR_BAD_ARG;
+  split_to_f32_kernel<<<split_grid(numel), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(src), dst, numel);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
 }

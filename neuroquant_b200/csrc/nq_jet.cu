@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) jet_act_kernel(const float* __restrict__ 
                                                       const float* __restrict__ zd2, const float* __restrict__ zdd1,
                                                       const float* __restrict__ zdd2, int64_t numel, int act,
                                                       float* __restrict__ y, float* __restrict__ yd,
-                                                      float* __restrict__ ydd) {
+                                                      float* __restrict__ ydd, int split) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (int64_t)gridDim.x * blockDim.x) {
     const float x = z[e];
     const float d1 = (zd1 ? zd1[e] : 0.f) + (zd2 ? zd2[e] : 0.f);
@@ -27,9 +27,27 @@ __global__ void __launch_bounds__(256) jet_act_kernel(const float* __restrict__ 
       f1 = cdf + x * pdf;
       f2 = pdf * (2.0f - x * x);
     }
-    y[e] = f0;
-    yd[e] = f1 * d1;
-    ydd[e] = f2 * d1 * d1 + f1 * d2;
+    const float o0 = f0, o1 = f1 * d1, o2 = f2 * d1 * d1 + f1 * d2;
+    if (!split) {
+      y[e] = o0;
+      yd[e] = o1;
+      ydd[e] = o2;
+    } else {  // split-bf16 planes (hi at [0, numel), lo at [numel, 2 numel)) for the tensor-core convolutions
+      const float vals[3] = {o0, o1, o2};
+      float* outs[3] = {y, yd, ydd};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        uint16_t* hp = reinterpret_cast<uint16_t*>(outs[k]);
+        uint32_t u = __float_as_uint(vals[k]);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        const uint16_t hb = (uint16_t)(u >> 16);
+        const float rem = vals[k] - __uint_as_float((uint32_t)hb << 16);
+        uint32_t u2 = __float_as_uint(rem);
+        u2 += 0x7FFFu + ((u2 >> 16) & 1u);
+        hp[e] = hb;
+        hp[numel + e] = (uint16_t)(u2 >> 16);
+      }
+    }
   }
 }
 
@@ -82,12 +100,14 @@ __global__ void __launch_bounds__(256) jet_head_kernel(const float* __restrict__
 using namespace nq;
 
 extern "C" int nq_jet_act(const float* z, const float* zd1, const float* zd2, const float* zdd1, const float* zdd2,
-                          int64_t numel, int act, float* y, float* yd, float* ydd, void* stream) {
+                          int64_t numel, int act, void* y, void* yd, void* ydd, int split_out, void* stream) {
   if (!z || !y || !yd || !ydd || numel <= 0 || (act != 0 && act != 1)) return NQ_ERR_BAD_ARG;
   int64_t blocks = (numel + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  jet_act_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(z, zd1, zd2, zdd1, zdd2, numel, act, y, yd, ydd);
+  jet_act_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(z, zd1, zd2, zdd1, zdd2, numel, act,
+                                                                  reinterpret_cast<float*>(y), reinterpret_cast<float*>(yd),
+                                                                  reinterpret_cast<float*>(ydd), split_out);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

@@ -27,8 +27,9 @@ constexpr int WG_LOADERS = 512;  // warps 0-15
 constexpr int WG_TW = 16;  // pixels per MMA K step
 
 struct WgParams {
-  const float* x;   // (n, h, w, C)
-  const float* dz;  // (n, h, w, N)
+  const uint8_t* x;   // split-bf16 (hi plane, lo plane), each (n, h, w, C) bf16
+  const uint8_t* dz;  // split-bf16, each (n, h, w, dz_stride) bf16
+  size_t x_plane_bytes, dz_plane_bytes;
   float* ws;        // [psplits][(ks*ks*C + 4)][N] partial gradients (bias row at ks*ks*C)
   int n, h, w, C, N, ks, pad;
   int ncg, G, MB;   // channel groups, (kw, group) pairs, 128-row blocks
@@ -85,6 +86,12 @@ __device__ __forceinline__ void wmma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t 
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void wcp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void wcp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool welect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nbuf; ++i) {
-      wbar_init(FULL + i * 8, WG_LOADERS / 32);
+      wbar_init(FULL + i * 8, WG_LOADERS);  // one deferred cp.async arrival per loader thread
       wbar_init(EMPTY + i * 8, 1);
     }
     wbar_init(DONE, 1);
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     uint32_t accum = 0, bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       wbar_wait(FULL + bi * 8, ph);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) -> MMA (async proxy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_buf = buf0 + bi * p.buf_bytes;
       const uint32_t a16 = ((a_buf & 0x3FFFFu) >> 4) | lbo_bits;
@@ -211,8 +219,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else if (warp < WG_LOADERS / 32) {
     // ===================== loaders (16 warps): fp32 NHWC -> bf16 planes =====================
     const int ltid = threadIdx.x;
-    const int span = WG_TW + p.ks - 1;  // source pixels per row that feed the ks shifted copies
-    const int a_tasks = p.TR * span * p.ncg;
+    const int a_copies = p.ks * p.ncg * p.TR * WG_TW;  // 16-byte chunks of the ks shifted copies
     const int ncg_b = nc >> 3;
     const int b_tasks = p.TR * WG_TW * ncg_b;
     uint32_t bi = 0, ph = 0;
@@ -224,83 +231,39 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int img = tt / p.tiles_y;
       const int y0 = ty * p.TR, x0 = tx * WG_TW;
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
-      uint8_t* a_dst = bufs + (size_t)bi * p.buf_bytes;
-      uint8_t* b_dst = a_dst + (size_t)p.a_planes * p.a_plane_bytes;
-      // Task order: pixel fastest, so that the 8 threads of a 16-byte store phase write 8 consecutive
-      // 16-byte rows of one core matrix (conflict free); loads are issued 4 deep before any store.
-      // ---- shifted input copies
-      for (int i0 = ltid; i0 < a_tasks; i0 += WG_LOADERS * 4) {
-        float4 va[4], vb[4];
-        int jj[4], rr[4], cc[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * WG_LOADERS;
-          va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          jj[u] = -1;
-          if (i < a_tasks) {
-            const int j = i % span;
-            const int rc = i / span;
-            const int r = rc % p.TR, cg = rc / p.TR;
-            jj[u] = j; rr[u] = r; cc[u] = cg;
-            const int gy = y0 + r + kh - p.pad, gx = x0 + j - p.pad;
-            if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && (y0 + r) < p.h) {
-              const float4* src = reinterpret_cast<const float4*>(p.x + (((size_t)img * p.h + gy) * p.w + gx) * p.C + cg * 8);
-              va[u] = __ldg(src);
-              vb[u] = __ldg(src + 1);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (jj[u] < 0) continue;
-          uint4 hi, lo;
-          wsplit8(va[u], vb[u], hi, lo);
-          // source pixel j lands at x = j - kw of copy kw
-          for (int kw = 0; kw < p.ks; ++kw) {
-            const int xl = jj[u] - kw;
-            if ((unsigned)xl < (unsigned)WG_TW) {
-              const size_t o = (size_t)(kw * p.ncg + cc[u]) * p.CGS_A + (size_t)(rr[u] * WG_TW + xl) * 16;
-              *reinterpret_cast<uint4*>(a_dst + o) = hi;
-              if (p.a_planes == 2) *reinterpret_cast<uint4*>(a_dst + p.a_plane_bytes + o) = lo;
-            }
-          }
-        }
+      const uint32_t a_dst = buf0 + bi * p.buf_bytes;
+      const uint32_t b_dst = a_dst + p.a_planes * p.a_plane_bytes;
+      // ---- shifted input copies: copy kw, row r, x holds source pixel x + kw - pad; pixel fastest so that the
+      //      16-byte chunks of a warp are consecutive in shared memory
+      const uint8_t* ximg = p.x + (size_t)img * p.h * p.w * p.C * 2;
+      for (int i = ltid; i < a_copies; i += WG_LOADERS) {
+        const int xl = i % WG_TW;
+        int rem = i / WG_TW;
+        const int r = rem % p.TR;
+        rem /= p.TR;
+        const int cg = rem % p.ncg, kw = rem / p.ncg;
+        const int gy = y0 + r + kh - p.pad, gx = x0 + xl + kw - p.pad;
+        const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && (y0 + r) < p.h;
+        const uint8_t* src = ok ? ximg + (((size_t)gy * p.w + gx) * p.C + cg * 8) * 2 : p.x;
+        const uint32_t d = a_dst + (uint32_t)(kw * p.ncg + cg) * p.CGS_A + (uint32_t)(r * WG_TW + xl) * 16;
+        wcp_async16(d, src, ok ? 16u : 0u);
+        if (p.a_planes == 2) wcp_async16(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
       }
       // ---- output-gradient tile
-      for (int i0 = ltid; i0 < b_tasks; i0 += WG_LOADERS * 4) {
-        float4 va[4], vb[4];
-        int oo[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * WG_LOADERS;
-          va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          oo[u] = -1;
-          if (i < b_tasks) {
-            const int xl = i % WG_TW;
-            const int rc = i / WG_TW;
-            const int r = rc % p.TR, cg = rc / p.TR;
-            oo[u] = cg * p.CGS_B + (r * WG_TW + xl) * 16;
-            const int gy = y0 + r, gx = x0 + xl;
-            if (gy < p.h && gx < p.w) {
-              const int ch = n0 + cg * 8;
-              const float4* src = reinterpret_cast<const float4*>(p.dz + (((size_t)img * p.h + gy) * p.w + gx) * p.dz_stride + ch);
-              if (ch < p.n_valid) va[u] = __ldg(src);
-              if (ch + 4 < p.n_valid) vb[u] = __ldg(src + 1);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (oo[u] < 0) continue;
-          uint4 hi, lo;
-          wsplit8(va[u], vb[u], hi, lo);
-          *reinterpret_cast<uint4*>(b_dst + oo[u]) = hi;
-          if (p.b_planes == 2) *reinterpret_cast<uint4*>(b_dst + p.b_plane_bytes + oo[u]) = lo;
-        }
+      const uint8_t* zimg = p.dz + (size_t)img * p.h * p.w * p.dz_stride * 2;
+      for (int i = ltid; i < b_tasks; i += WG_LOADERS) {
+        const int xl = i % WG_TW;
+        const int rc = i / WG_TW;
+        const int r = rc % p.TR, cg = rc / p.TR;
+        const int gy = y0 + r, gx = x0 + xl;
+        const int ch = n0 + cg * 8;
+        const bool ok = gy < p.h && gx < p.w && ch < p.n_valid;
+        const uint8_t* src = ok ? zimg + (((size_t)gy * p.w + gx) * p.dz_stride + ch) * 2 : p.dz;
+        const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B + (uint32_t)(r * WG_TW + xl) * 16;
+        wcp_async16(d, src, ok ? 16u : 0u);
+        if (p.b_planes == 2) wcp_async16(d + p.b_plane_bytes, src + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) wbar_arrive(FULL + bi * 8);
+      wcp_async_arrive(FULL + bi * 8);
       if (++bi == (uint32_t)p.nbuf) { bi = 0; ph ^= 1; }
     }
     // ===================== epilogue (warps 0-3): TMEM -> partial dW =====================
@@ -420,8 +383,10 @@ extern "C" int nq_tc_plan_wgrad(const nq_conv_desc* d, int a_planes, int b_plane
   return fill_wg_plan(d, a_planes, b_planes, plan);
 }
 
-extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* pl, const float* x, const float* dz,
+extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* pl, const void* x_split, const void* dz_split,
                                 float* dwk, float* workspace, int64_t workspace_floats, void* stream) {
+  const uint8_t* x = reinterpret_cast<const uint8_t*>(x_split);
+  const uint8_t* dz = reinterpret_cast<const uint8_t*>(dz_split);
   int st = check_conv_desc(d);
   if (st) return st;
   if (!pl || !x || !dz || !dwk || !workspace) return NQ_ERR_BAD_ARG;
@@ -434,8 +399,10 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.tiles_per_split = pl->tiles_per_split; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.CGS_A = pl->CGS_A; p.CGS_B = pl->CGS_B; p.a_plane_bytes = pl->a_plane_bytes; p.b_plane_bytes = pl->b_plane_bytes;
   p.buf_bytes = pl->buf_bytes; p.nbuf = pl->nbuf;
-  p.dz_stride = d->rh * d->rw * d->cg;
+  p.dz_stride = (d->rh * d->rw * d->cg + 7) / 8 * 8;  // channels per pixel as stored (the head's 4 are stored as 8)
   p.n_valid = p.dz_stride;
+  p.x_plane_bytes = (size_t)d->n * d->h * d->w * pl->C * 2;
+  p.dz_plane_bytes = (size_t)d->n * d->h * d->w * p.dz_stride * 2;
   cudaStream_t s = as_stream(stream);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int grid = pl->psplits * pl->nsplits * d->ksize;
