@@ -183,15 +183,22 @@ class _Plan:
         self.dz: List[Optional[torch.Tensor]] = []
         last = len(eng.geoms) - 1
         self.desc = stage_descs(eng.geoms, n, h0, w0, eng.use_tc)
-        self.x.append(torch.zeros(n, h0, w0, self.desc[0].cin_p, device=dev))
+
+        def act_buf(*shape):
+            # tensor-core engine: "split-bf16" storage (hi plane, lo plane; same bytes as fp32); FFMA engine: fp32
+            if eng.use_tc:
+                return torch.zeros((2,) + shape, device=dev, dtype=torch.bfloat16)
+            return torch.zeros(shape, device=dev)
+
+        self.x.append(act_buf(n, h0, w0, self.desc[0].cin_p))
         h, w = h0, w0
         for i, (g, d) in enumerate(zip(eng.geoms, self.desc)):
             if train:
-                self.dz.append(torch.empty(n, h, w, d.nout_p, device=dev))
+                self.dz.append(act_buf(n, h, w, _pad(d.nout_p, 8) if eng.use_tc else d.nout_p))
             if i == last:
                 break
             h, w = h * g.rh, w * g.rw
-            self.x.append(torch.empty(n, h, w, d.cg, device=dev))
+            self.x.append(act_buf(n, h, w, d.cg))
             self.z.append(torch.empty(n, h, w, d.cg, device=dev) if (train and g.act != "none") else None)
         self.H, self.W = h, w
         self.img = torch.empty(n, 3, h, w, device=dev)
@@ -450,7 +457,10 @@ class DecoderEngine:
         if not (reuse_weights and self._weights_valid and (self._wt_valid or not train)):
             self.prepare_weights(p, need_wt=train, reg_b=reg_b)
         embed = embed.detach().contiguous().float()
-        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(embed), L.ptr(p.x[0]), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_nhwc")
+        if self.use_tc:
+            L.check(L.lib.nq_nchw_to_split(L.ptr(embed), p.x[0].data_ptr(), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_split")
+        else:
+            L.check(L.lib.nq_nchw_to_nhwc(L.ptr(embed), L.ptr(p.x[0]), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_nhwc")
         self.launches += 1
         last = len(self.stages) - 1
         for i in range(last):
@@ -462,8 +472,8 @@ class DecoderEngine:
             else:
                 wpk_f, _, scale_p = self._tcw[i]
                 L.check(self._run(f"conv_fwd[{i}]", p.desc[i], L.lib.nq_tc_conv_fwd, C.byref(p.desc[i]),
-                                  C.byref(p.tc_fwd[(i, self._fwd_bpl[i])]), L.ptr(p.x[i]), wpk_f.data_ptr(), L.ptr(scale_p),
-                                  L.ptr(bp), L.ptr(z), L.ptr(p.x[i + 1]), st), "nq_tc_conv_fwd")
+                                  C.byref(p.tc_fwd[(i, self._fwd_bpl[i])]), p.x[i].data_ptr(), wpk_f.data_ptr(), L.ptr(scale_p),
+                                  L.ptr(bp), L.ptr(z), p.x[i + 1].data_ptr(), st), "nq_tc_conv_fwd")
             self.launches += 1
         wk, _, bp, _, _ = self._packed[last]
         if target is not None:
@@ -474,11 +484,19 @@ class DecoderEngine:
             mp = float(mean_pixels if mean_pixels is not None else n * p.H * p.W)
         else:
             mp = 1.0
-        L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss, C.byref(p.desc[last]), L.ptr(p.x[last]), L.ptr(wk), L.ptr(bp),
-                                       _HEAD[self.geoms[last].act], L.ptr(target), float(p_norm), mp,
-                                       L.ptr(p.img) if (want_img or target is None) else None,
-                                       L.ptr(p.loss) if target is not None else None,
-                                       L.ptr(p.dz[last]) if (train and target is not None) else None, st), "nq_head_fwd_loss")
+        want_dz = train and target is not None
+        if self.use_tc:
+            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss_split, C.byref(p.desc[last]),
+                              p.x[last].data_ptr(), L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target),
+                              float(p_norm), mp, L.ptr(p.img) if (want_img or target is None) else None,
+                              L.ptr(p.loss) if target is not None else None,
+                              p.dz[last].data_ptr() if want_dz else None, st), "nq_head_fwd_loss_split")
+        else:
+            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss, C.byref(p.desc[last]), L.ptr(p.x[last]),
+                              L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target), float(p_norm), mp,
+                              L.ptr(p.img) if (want_img or target is None) else None,
+                              L.ptr(p.loss) if target is not None else None,
+                              L.ptr(p.dz[last]) if want_dz else None, st), "nq_head_fwd_loss")
         self.launches += 1
         self._mean_pixels = mp
         return p.img
@@ -527,33 +545,39 @@ class DecoderEngine:
         last = len(self.stages) - 1
         if not hasattr(p, "dwk"):
             p.dwk, p.ws = [], []
+            p.head_desc16 = None
             for i, d in enumerate(p.desc):
-                head_tc = i == last and self.use_tc and self.wgrad_tc and self._wg_plan(d) is not None
-                p.dwk.append(torch.empty(d.kdim + 4, 16 if head_tc else d.nout_p, device=self.device))
-                if head_tc:  # head weight gradient on the tensor cores: 3 output channels padded to N = 16
+                if self.use_tc:
+                    # every stage's weight gradient on the tensor cores (the head's 3 output channels are
+                    # padded to N = 16; its dz is stored with 8 channels)
                     pl = self._wg_plan(d)
+                    if pl is None:
+                        raise NotImplementedError(
+                            f"stage {i}: cin_p * k = {d.cin_p * d.ksize} > 504 accumulator rows -- no tensor-core wgrad plan "
+                            "(12M-class decoders); train such models with NQ_CONV=simt")
+                    p.dwk.append(torch.empty(d.kdim + 4, pl.N, device=self.device))
                     p.ws.append((torch.empty(pl.workspace_floats, device=self.device), pl))
-                    p.head_desc16 = L.ConvDesc(d.n, d.h, d.w, d.cin, d.cin_p, d.ksize, d.cout, 1, 1, d.c_grp, 16, 0)
+                    if i == last:
+                        p.head_desc16 = L.ConvDesc(d.n, d.h, d.w, d.cin, d.cin_p, d.ksize, d.cout, 1, 1, d.c_grp, pl.N, 0)
                 elif i == last:
+                    p.dwk.append(torch.empty(d.kdim + 4, d.nout_p, device=self.device))
                     blocks = L.lib.nq_head_wgrad_blocks(C.byref(d))
                     p.ws.append((torch.empty(blocks * (d.kdim + 4) * 4, device=self.device), 0))
-                elif self.use_tc and self.wgrad_tc and d.n * d.h * d.w >= 256 and self._wg_plan(d) is not None:
-                    pl = self._wg_plan(d)
-                    p.ws.append((torch.empty(pl.workspace_floats, device=self.device), pl))
                 else:
+                    p.dwk.append(torch.empty(d.kdim + 4, d.nout_p, device=self.device))
                     sp = self._wgrad_splits(d)
                     p.ws.append((torch.empty(sp * (d.kdim + 4) * d.nout_p, device=self.device) if sp > 1 else None, sp))
         for i in range(last, -1, -1):
             d = p.desc[i]
             _, wt, _, _, _ = self._packed[i]
             ws, sp = p.ws[i]
-            if i == last and not isinstance(sp, L.TcWgradPlan):
+            if isinstance(sp, L.TcWgradPlan):
+                L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_tc_conv_wgrad, C.byref(d), C.byref(sp), p.x[i].data_ptr(),
+                                  p.dz[i].data_ptr(), L.ptr(p.dwk[i]), L.ptr(ws), ws.numel(), st), "nq_tc_conv_wgrad")
+                self.launches += 2
+            elif i == last:
                 L.check(self._run("head_wgrad", d, L.lib.nq_head_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]), L.ptr(p.dwk[i]),
                                   L.ptr(ws), ws.numel(), st), "nq_head_wgrad")
-                self.launches += 2
-            elif isinstance(sp, L.TcWgradPlan):
-                L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_tc_conv_wgrad, C.byref(d), C.byref(sp), L.ptr(p.x[i]),
-                                  L.ptr(p.dz[i]), L.ptr(p.dwk[i]), L.ptr(ws), ws.numel(), st), "nq_tc_conv_wgrad")
                 self.launches += 2
             else:
                 L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_conv_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]),
@@ -561,22 +585,19 @@ class DecoderEngine:
                 self.launches += 2 if sp > 1 else 1
             if i > 0:
                 g_prev = self.geoms[i - 1]
-                if i == last and self._head_dgrad is not None:
-                    L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(p.tc_head_dgrad),
-                                      L.ptr(p.dz[i]), self._head_dgrad.data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw,
-                                      _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st), "nq_tc_conv_dgrad")
-                elif self._tcw[i] is None:
+                if self.use_tc:
+                    pl, wpk = (p.tc_head_dgrad, self._head_dgrad) if i == last else (p.tc_dgrad[i], self._tcw[i][1])
+                    L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(pl), p.dz[i].data_ptr(),
+                                      wpk.data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act],
+                                      p.dz[i - 1].data_ptr(), st), "nq_tc_conv_dgrad")
+                else:
                     L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
                                       L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st),
                             "nq_conv_dgrad")
-                else:
-                    L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(p.tc_dgrad[i]),
-                                      L.ptr(p.dz[i]), self._tcw[i][1].data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw,
-                                      _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st), "nq_tc_conv_dgrad")
                 self.launches += 1
             s = self.stages[i]
             gw, gb = views[i]
-            du = p.head_desc16 if (i == last and isinstance(sp, L.TcWgradPlan)) else d
+            du = p.head_desc16 if (i == last and p.head_desc16 is not None) else d
             L.check(L.lib.nq_unpack_wgrad(C.byref(du), L.ptr(p.dwk[i]), s.cin_src, L.ptr(gw), L.ptr(gb), st), "nq_unpack_wgrad")
             self.launches += 1
         return flat

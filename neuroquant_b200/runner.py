@@ -182,9 +182,12 @@ class DecoderRunner:
         p = self.engine._last_plan
         out = []
         for x, d in zip(p.x[1:], p.desc):
-            n, h, w, cp = x.shape
+            n, h, w, cp = x.shape[-4:]
             c = d.c_grp
             t = torch.empty(n, c, h, w, device=x.device)
-            L.check(L.lib.nq_nhwc_to_nchw(L.ptr(x), L.ptr(t), n, c, h, w, cp, L.stream()), "nq_nhwc_to_nchw")
+            if self.engine.use_tc:  # split-bf16 planes -> fp32 NCHW
+                L.check(L.lib.nq_split_to_nchw(x.data_ptr(), L.ptr(t), n, c, h, w, cp, L.stream()), "nq_split_to_nchw")
+            else:
+                L.check(L.lib.nq_nhwc_to_nchw(L.ptr(x), L.ptr(t), n, c, h, w, cp, L.stream()), "nq_nhwc_to_nchw")
             out.append(t)
         return out

@@ -38,34 +38,46 @@ class OmegaEvaluator:
         p = eng.plan(n, h0, w0, False)
         eng.prepare_weights(p, need_wt=False)
         st = L.stream()
-        self._v = []
+        self._v, self._w, self._plans = [], [], []
         last = len(eng.stages) - 1
         for i, (s, d, v) in enumerate(zip(eng.stages, p.desc, vecs)):
             v = v.detach().contiguous().float()
             assert v.shape == s.weight.shape
-            if eng._tcw[i] is not None:
-                pl = p.tc_fwd[(i, 2)]
-                buf = torch.zeros(pl.wpk_bytes, dtype=torch.uint8, device=eng.device)
-                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(pl), L.ptr(v), s.geom.cin, None, 0, buf.data_ptr(), st),
-                        "nq_tc_pack_weight")
+            if eng.use_tc:
+                # every stage, the head included (its 3 columns padded to 16), runs on the tensor-core forward kernel
+                pl = p.tc_fwd[(i, 2)] if i < last else L.TcPlan()
+                if i == last:
+                    L.check(L.lib.nq_tc_plan_conv(C.byref(d), 0, eng.fwd_a_planes, 2, C.byref(pl)), "nq_tc_plan_conv")
+                    pl.cluster = eng.cluster
+                bufs = []
+                for src in (s.weight, v):
+                    buf = torch.zeros(pl.wpk_bytes, dtype=torch.uint8, device=eng.device)
+                    L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(pl), L.ptr(src), s.geom.cin, None, 0, buf.data_ptr(), st),
+                            "nq_tc_pack_weight")
+                    bufs.append(buf)
+                self._plans.append(pl)
+                self._w.append(bufs[0])
+                self._v.append(bufs[1])
             else:
                 buf = torch.zeros(d.kdim, d.nout_p, device=eng.device)
                 L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(v), s.geom.cin, None, L.ptr(buf), None, None, st), "nq_pack_weight")
-            self._v.append(buf)
+                self._plans.append(None)
+                self._w.append(eng._packed[i][0])
+                self._v.append(buf)
         self._zero_bias = [torch.zeros(d.nout_p, device=eng.device) for d in p.desc]
 
     def _conv(self, p, i, x, use_v: bool, with_bias: bool, out):
+        """out (fp32 pre-activation, shuffled grid) = conv(x; w or v) [+ bias]."""
         eng = self.eng
         d = copy.copy(p.desc[i])
         d.act = 0
         st = L.stream()
-        wk, _, bp, _, _ = eng._packed[i]
-        if eng._tcw[i] is not None:
-            w = self._v[i].data_ptr() if use_v else eng._tcw[i][0].data_ptr()
-            L.check(L.lib.nq_tc_conv_fwd(C.byref(d), C.byref(p.tc_fwd[(i, 2)]), L.ptr(x), w, None, L.ptr(bp) if with_bias else None,
-                                         None, L.ptr(out), st), "nq_tc_conv_fwd")
+        bp = eng._packed[i][2]
+        w = self._v[i] if use_v else self._w[i]
+        if eng.use_tc:
+            L.check(L.lib.nq_tc_conv_fwd(C.byref(d), C.byref(self._plans[i]), x.data_ptr(), w.data_ptr(), None,
+                                         L.ptr(bp) if with_bias else None, L.ptr(out), None, st), "nq_tc_conv_fwd")
         else:
-            w = self._v[i] if use_v else wk
             L.check(L.lib.nq_conv_fwd(C.byref(d), L.ptr(x), L.ptr(w), L.ptr(bp if with_bias else self._zero_bias[i]), None,
                                       L.ptr(out), st), "nq_conv_fwd")
         eng.launches += 1
@@ -78,15 +90,22 @@ class OmegaEvaluator:
         key = (n, h0, w0)
         if key not in self._bufs:
             bufs = []
-            for x in p.x[1:]:
-                bufs.append({k: torch.empty_like(x) for k in ("z", "zd1", "zd2", "zdd1", "zdd2", "y", "yd", "ydd")})
+            for x, d in zip(p.x[1:], p.desc):
+                shape = (n, d.h * d.rh, d.w * d.rw, d.cg)
+                b = {k: torch.empty(shape, device=eng.device) for k in ("z", "zd1", "zd2", "zdd1", "zdd2")}
+                for k in ("y", "yd", "ydd"):  # inputs of the next stage: split-bf16 on the tensor-core engine
+                    b[k] = torch.empty_like(x)
+                bufs.append(b)
             hd = p.desc[-1]
             bufs.append({k: torch.empty(n, hd.h, hd.w, 4, device=eng.device) for k in ("z", "zd1", "zd2", "zdd1", "zdd2")})
             self._bufs[key] = bufs
         bufs = self._bufs[key]
         st = L.stream()
         embed = embed.detach().contiguous().float()
-        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(embed), L.ptr(p.x[0]), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_nhwc")
+        if eng.use_tc:
+            L.check(L.lib.nq_nchw_to_split(L.ptr(embed), p.x[0].data_ptr(), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_split")
+        else:
+            L.check(L.lib.nq_nchw_to_nhwc(L.ptr(embed), L.ptr(p.x[0]), n, c0, h0, w0, p.desc[0].cin_p, st), "nq_nchw_to_nhwc")
         x, xd, xdd = p.x[0], None, None
         last = len(eng.stages) - 1
         for i in range(last + 1):
@@ -103,7 +122,8 @@ class OmegaEvaluator:
                 zdd1 = b["zdd1"]
             if i < last:
                 L.check(L.lib.nq_jet_act(L.ptr(b["z"]), L.ptr(zd1), L.ptr(b["zd2"]), L.ptr(zdd1), L.ptr(zdd2), b["z"].numel(),
-                                         _ACT[eng.geoms[i].act], L.ptr(b["y"]), L.ptr(b["yd"]), L.ptr(b["ydd"]), st), "nq_jet_act")
+                                         _ACT[eng.geoms[i].act], b["y"].data_ptr(), b["yd"].data_ptr(), b["ydd"].data_ptr(),
+                                         1 if eng.use_tc else 0, st), "nq_jet_act")
                 x, xd, xdd = b["y"], b["yd"], b["ydd"]
             else:
                 tgt = target.detach().contiguous().float()
