@@ -219,9 +219,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else if (warp < WG_LOADERS / 32) {
     // ===================== loaders (16 warps): fp32 NHWC -> bf16 planes =====================
     const int ltid = threadIdx.x;
-    const int a_copies = p.ks * p.ncg * p.TR * WG_TW;  // 16-byte chunks of the ks shifted copies
+    // Each thread owns one pixel slot (row r, column xl) of the tile and walks the (kw, channel-group) pairs with
+    // incremental addresses: no integer division in the copy loops (they were issue bound on index arithmetic).
+    const int slots = p.TR * WG_TW;  // 64, 32 or 16: power of two
+    const int slot = ltid & (slots - 1);
+    const int grp = ltid / slots, ngrp = WG_LOADERS / slots;
+    const int r = slot / WG_TW, xl = slot % WG_TW;
+    const int G = p.ks * p.ncg;
     const int ncg_b = nc >> 3;
-    const int b_tasks = p.TR * WG_TW * ncg_b;
     uint32_t bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       int tt = t;
@@ -231,37 +236,38 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int img = tt / p.tiles_y;
       const int y0 = ty * p.TR, x0 = tx * WG_TW;
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
-      const uint32_t a_dst = buf0 + bi * p.buf_bytes;
-      const uint32_t b_dst = a_dst + p.a_planes * p.a_plane_bytes;
-      // ---- shifted input copies: copy kw, row r, x holds source pixel x + kw - pad; pixel fastest so that the
-      //      16-byte chunks of a warp are consecutive in shared memory
-      const uint8_t* ximg = p.x + (size_t)img * p.h * p.w * p.C * 2;
-      for (int i = ltid; i < a_copies; i += WG_LOADERS) {
-        const int xl = i % WG_TW;
-        int rem = i / WG_TW;
-        const int r = rem % p.TR;
-        rem /= p.TR;
-        const int cg = rem % p.ncg, kw = rem / p.ncg;
-        const int gy = y0 + r + kh - p.pad, gx = x0 + xl + kw - p.pad;
-        const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && (y0 + r) < p.h;
-        const uint8_t* src = ok ? ximg + (((size_t)gy * p.w + gx) * p.C + cg * 8) * 2 : p.x;
-        const uint32_t d = a_dst + (uint32_t)(kw * p.ncg + cg) * p.CGS_A + (uint32_t)(r * WG_TW + xl) * 16;
-        wcp_async16(d, src, ok ? 16u : 0u);
-        if (p.a_planes == 2) wcp_async16(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
+      const uint32_t a_dst = buf0 + bi * p.buf_bytes + slot * 16;
+      const uint32_t b_dst = buf0 + bi * p.buf_bytes + p.a_planes * p.a_plane_bytes + slot * 16;
+      const int oy = y0 + r, ox = x0 + xl;  // this thread's output pixel
+      // ---- shifted input copies: copy kw holds source pixel (oy + kh - pad, ox + kw - pad)
+      {
+        const int gy = oy + kh - p.pad;
+        const bool row_ok = (unsigned)gy < (unsigned)p.h && oy < p.h;
+        const uint8_t* xrow = p.x + (((size_t)img * p.h + (row_ok ? gy : 0)) * p.w) * p.C * 2;
+        int kw = 0, cg = grp;
+        while (cg >= p.ncg) { cg -= p.ncg; ++kw; }
+        for (int g = grp; g < G; g += ngrp) {
+          const int gx = ox + kw - p.pad;
+          const bool ok = row_ok && (unsigned)gx < (unsigned)p.w;
+          const uint8_t* src = ok ? xrow + ((size_t)gx * p.C + cg * 8) * 2 : p.x;
+          const uint32_t d = a_dst + (uint32_t)g * p.CGS_A;
+          wcp_async16(d, src, ok ? 16u : 0u);
+          if (p.a_planes == 2) wcp_async16(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
+          cg += ngrp;
+          while (cg >= p.ncg) { cg -= p.ncg; ++kw; }
+        }
       }
       // ---- output-gradient tile
-      const uint8_t* zimg = p.dz + (size_t)img * p.h * p.w * p.dz_stride * 2;
-      for (int i = ltid; i < b_tasks; i += WG_LOADERS) {
-        const int xl = i % WG_TW;
-        const int rc = i / WG_TW;
-        const int r = rc % p.TR, cg = rc / p.TR;
-        const int gy = y0 + r, gx = x0 + xl;
-        const int ch = n0 + cg * 8;
-        const bool ok = gy < p.h && gx < p.w && ch < p.n_valid;
-        const uint8_t* src = ok ? zimg + (((size_t)gy * p.w + gx) * p.dz_stride + ch) * 2 : p.dz;
-        const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B + (uint32_t)(r * WG_TW + xl) * 16;
-        wcp_async16(d, src, ok ? 16u : 0u);
-        if (p.b_planes == 2) wcp_async16(d + p.b_plane_bytes, src + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
+      {
+        const bool pix_ok = oy < p.h && ox < p.w;
+        const uint8_t* zpix = p.dz + ((((size_t)img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0) * 2;
+        for (int cg = grp; cg < ncg_b; cg += ngrp) {
+          const bool ok = pix_ok && (n0 + cg * 8) < p.n_valid;
+          const uint8_t* src = ok ? zpix + cg * 16 : p.dz;
+          const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B;
+          wcp_async16(d, src, ok ? 16u : 0u);
+          if (p.b_planes == 2) wcp_async16(d + p.b_plane_bytes, src + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
+        }
       }
       wcp_async_arrive(FULL + bi * 8);
       if (++bi == (uint32_t)p.nbuf) { bi = 0; ph ^= 1; }
