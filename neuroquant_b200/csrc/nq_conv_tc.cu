@@ -432,20 +432,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int ncg = min(p.KC, p.C - c0) >> 3;
         mbar_wait(A_EMPTY + abuf * 8, ((uc >> 1) & 1) ^ 1);
         const uint32_t dst = a_base + abuf * p.a_buf_bytes;
-        const int tasks = npix * ncg;
-        // pixel fastest: consecutive threads fill consecutive 16-byte rows of one channel group
-        int cgi = ltid / npix, pix = ltid - cgi * npix;
-        for (int i = ltid; i < tasks; i += TC_LOADERS) {
-          const int py = pix / p.PW, px = pix - py * p.PW;
-          const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
-          const int ch = c0 + cgi * 8;
-          const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
-          const uint8_t* src = ok ? img + (((size_t)gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
-          const uint32_t d = dst + cgi * p.CGS + pix * 16;
-          cp_async16(d, src, ok ? 16u : 0u);
-          if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
-          pix += TC_LOADERS;
-          while (pix >= npix) { pix -= npix; ++cgi; }
+        // lanes 2k / 2k+1 copy the two 16-byte halves (adjacent channel groups) of one 32-byte sector of the
+        // same pixel; consecutive lane pairs take consecutive pixels
+        const int npair = (ncg + 1) >> 1;
+        const int tasks = npix * npair;
+        const int cgp = ltid & 1;
+        int j = ltid >> 1;
+        int cpi = j / npix, pix = j - cpi * npix;
+        for (; j < tasks; j += TC_LOADERS / 2) {
+          const int cgi = 2 * cpi + cgp;
+          if (cgi < ncg) {
+            const int py = pix / p.PW, px = pix - py * p.PW;
+            const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
+            const int ch = c0 + cgi * 8;
+            const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
+            const uint8_t* src = ok ? img + (((size_t)gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
+            const uint32_t d = dst + cgi * p.CGS + pix * 16;
+            cp_async16(d, src, ok ? 16u : 0u);
+            if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
+          }
+          pix += TC_LOADERS / 2;
+          while (pix >= npix) { pix -= npix; ++cpi; }
         }
         cp_async_arrive(A_FULL + abuf * 8);
       }
@@ -667,8 +674,8 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->PW = TILE_W + d->ksize - 1;
   pl->PH = TILE_H + d->ksize - 1;
   int npix = pl->PW * pl->PH;
-  int cgs16 = npix;  // channel-group stride in 16-byte units, forced to 1 mod 8
-  while (cgs16 % 8 != 1) ++cgs16;
+  int cgs16 = npix;  // channel-group stride in 16-byte units, forced to 4 mod 8 (conflict-free lane-pair stores)
+  while (cgs16 % 8 != 4) ++cgs16;
   pl->CGS = cgs16 * 16;
   // Weight stage = SBC channels of one tap; activation unit = KC channels of the halo tile.  Big stages
   // amortise the per-stage barrier round trips of the producer and issuer threads (a 6 KB stage is only

@@ -89,6 +89,9 @@ __device__ __forceinline__ void wmma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t 
 __device__ __forceinline__ void wcp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void wcp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void wcp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -219,13 +222,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else if (warp < WG_LOADERS / 32) {
     // ===================== loaders (16 warps): fp32 NHWC -> bf16 planes =====================
     const int ltid = threadIdx.x;
-    // Each thread owns one pixel slot (row r, column xl) of the tile and walks the (kw, channel-group) pairs with
-    // incremental addresses: no integer division in the copy loops (they were issue bound on index arithmetic).
+    // Each thread owns one pixel slot (row r, column xl) of the tile and one parity of the channel groups:
+    // lanes 2k and 2k+1 copy the two 16-byte halves of the same 32-byte sector (full sector efficiency on the
+    // L2 -> SM path, which bounds this kernel), and walk the (kw, group pair) list with incremental addresses.
     const int slots = p.TR * WG_TW;  // 64, 32 or 16: power of two
-    const int slot = ltid & (slots - 1);
-    const int grp = ltid / slots, ngrp = WG_LOADERS / slots;
+    const int cgp = ltid & 1;
+    const int slot = (ltid >> 1) & (slots - 1);
+    const int grp = ltid / (2 * slots), ngrp = WG_LOADERS / (2 * slots);
     const int r = slot / WG_TW, xl = slot % WG_TW;
-    const int G = p.ks * p.ncg;
+    const int npair = (p.ncg + 1) >> 1;
+    const int Q = p.ks * npair;
     const int ncg_b = nc >> 3;
     uint32_t bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
@@ -239,29 +245,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t a_dst = buf0 + bi * p.buf_bytes + slot * 16;
       const uint32_t b_dst = buf0 + bi * p.buf_bytes + p.a_planes * p.a_plane_bytes + slot * 16;
       const int oy = y0 + r, ox = x0 + xl;  // this thread's output pixel
-      // ---- shifted input copies: copy kw holds source pixel (oy + kh - pad, ox + kw - pad)
+      // ---- shifted input copies: copy kw holds source pixel (oy + kh - pad, ox + kw - pad); the kw copies of
+      //      one source sector come from L1 (cp.async.ca)
       {
         const int gy = oy + kh - p.pad;
         const bool row_ok = (unsigned)gy < (unsigned)p.h && oy < p.h;
         const uint8_t* xrow = p.x + (((size_t)img * p.h + (row_ok ? gy : 0)) * p.w) * p.C * 2;
-        int kw = 0, cg = grp;
-        while (cg >= p.ncg) { cg -= p.ncg; ++kw; }
-        for (int g = grp; g < G; g += ngrp) {
-          const int gx = ox + kw - p.pad;
-          const bool ok = row_ok && (unsigned)gx < (unsigned)p.w;
-          const uint8_t* src = ok ? xrow + ((size_t)gx * p.C + cg * 8) * 2 : p.x;
-          const uint32_t d = a_dst + (uint32_t)g * p.CGS_A;
-          wcp_async16(d, src, ok ? 16u : 0u);
-          if (p.a_planes == 2) wcp_async16(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
-          cg += ngrp;
-          while (cg >= p.ncg) { cg -= p.ncg; ++kw; }
+        int kw = 0, cpi = grp;
+        while (cpi >= npair) { cpi -= npair; ++kw; }
+        for (int q = grp; q < Q; q += ngrp) {
+          const int cg = 2 * cpi + cgp;
+          if (cg < p.ncg) {
+            const int gx = ox + kw - p.pad;
+            const bool ok = row_ok && (unsigned)gx < (unsigned)p.w;
+            const uint8_t* src = ok ? xrow + ((size_t)gx * p.C + cg * 8) * 2 : p.x;
+            const uint32_t d = a_dst + (uint32_t)(kw * p.ncg + cg) * p.CGS_A;
+            wcp_async16_ca(d, src, ok ? 16u : 0u);
+            if (p.a_planes == 2) wcp_async16_ca(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
+          }
+          cpi += ngrp;
+          while (cpi >= npair) { cpi -= npair; ++kw; }
         }
       }
       // ---- output-gradient tile
       {
         const bool pix_ok = oy < p.h && ox < p.w;
         const uint8_t* zpix = p.dz + ((((size_t)img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0) * 2;
-        for (int cg = grp; cg < ncg_b; cg += ngrp) {
+        for (int cg = 2 * grp + cgp; cg < ncg_b; cg += 2 * ngrp) {
           const bool ok = pix_ok && (n0 + cg * 8) < p.n_valid;
           const uint8_t* src = ok ? zpix + cg * 16 : p.dz;
           const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B;
@@ -356,8 +366,8 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   int tr = 4, nbuf = 0;
   for (; tr >= 1; tr >>= 1) {
     const int per_group = tr * WG_TW * 16;  // bytes
-    pl->CGS_A = per_group + 16;             // +16: conflict-free loader stores across groups
-    pl->CGS_B = per_group + 16;
+    pl->CGS_A = per_group + 64;             // +64: lane pairs (same pixel, adjacent groups) store conflict free
+    pl->CGS_B = per_group + 64;
     pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
     pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
     pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;

@@ -87,7 +87,7 @@ def test_tc_plans_fit_for_every_workload():
                 assert pl.C % pl.SBC == 0 and pl.KC % pl.SBC == 0 and pl.SBC % 16 == 0
                 assert pl.NT % 16 == 0 and pl.NT <= 256 and pl.N % 16 == 0
                 assert pl.total_tiles == pl.tiles_x * pl.tiles_y * pl.tiles_n * 2
-                assert (pl.CGS // 16) % 8 == 1 and pl.CGS >= pl.PW * pl.PH * 16
+                assert (pl.CGS // 16) % 8 == 4 and pl.CGS >= pl.PW * pl.PH * 16
         assert descs[-1].cin_p % 4 == 0
         for i, d in enumerate(descs[:-1]):
             for ap, bp in ((1, 1), (2, 2)):
