@@ -7,9 +7,12 @@
 // The reduction runs over pixels, so pixels are the MMA K dimension and both operands are "MN-major"
 // (channels contiguous) -- which NHWC gives for free: an 8-channel group of 8 consecutive x positions is
 // exactly one 128-byte no-swizzle core matrix.  Mapping:
-//   * a CTA owns one kernel row kh, one slice of the output channels n' and a contiguous range of
-//     16-pixel-wide x TR-row pixel tiles; its accumulators stay in TMEM for the whole range
-//     (persistent split-K), then are written once as a partial dW and summed in a fixed order
+//   * a CTA owns a group of consecutive kernel rows kh, one slice of the output channels n' and a contiguous
+//     range of 16-pixel-wide x TR-row pixel tiles; its accumulators (one per kh and 128-row block, side by
+//     side in the 512 TMEM columns) stay in TMEM for the whole range (persistent split-K), then are written
+//     once as a partial dW and summed in a fixed order.  Grouping kernel rows lets one staged tile of dZ and of
+//     the shifted inputs feed several kh (the kh shift is a row offset in the descriptor): the L2 -> SM traffic,
+//     which bounds this kernel, drops by the group size
 //   * A (GEMM M) = shifted input: rows (kw, channel group, 8 channels).  The ks horizontal shifts are
 //     materialised as ks copies of the 16-pixel row segment in shared memory ([kw][group][row][x][8]),
 //     which makes the 8-row groups uniformly strided, so M = 128 covers 16 (kw, group) pairs per MMA
@@ -17,6 +20,8 @@
 //   * B (GEMM N) = dZ tile [group][row][x][8]; K = 16 pixels = one row segment per MMA
 //   * operands are bf16 hi (+ lo) planes of the fp32 tensors, accumulation fp32
 #include <cuda_bf16.h>
+
+#include <stdlib.h>
 
 #include "nq_common.cuh"
 
@@ -35,6 +40,7 @@ struct WgParams {
   int ncg, G, MB;   // channel groups, (kw, group) pairs, 128-row blocks
   int NC, nsplits;  // output columns per CTA
   int TR;           // tile rows
+  int nkh, khg, AR; // kernel rows per CTA, number of kernel-row groups, staged input rows (TR + nkh - 1)
   int tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
   int a_planes, b_planes;
   int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
@@ -133,10 +139,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t buf0 = wsmem_u32(bufs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // block -> (pixel split, column split, kernel row)
+  // block -> (pixel split, column split, kernel-row group)
   int b = blockIdx.x;
-  const int kh = b % p.ks;
-  b /= p.ks;
+  const int kh0 = (b % p.khg) * p.nkh;
+  const int nkh = min(p.nkh, p.ks - kh0);
+  b /= p.khg;
   const int nsplit = b % p.nsplits;
   const int psplit = b / p.nsplits;
   const int n0 = nsplit * p.NC;
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   // constant part of every A buffer: the "ones" group (bias gradient) and zeroed tail groups
   {
     const int tail_groups = p.MB * 16 - p.G;  // >= 1
-    const int per_group16 = p.TR * WG_TW;     // 16-byte units per group
+    const int per_group16 = p.AR * WG_TW;     // 16-byte units per group
     for (int bi = 0; bi < p.nbuf; ++bi)
       for (int pl = 0; pl < p.a_planes; ++pl) {
         uint8_t* base = bufs + (size_t)bi * p.buf_bytes + (size_t)pl * p.a_plane_bytes;
@@ -201,17 +208,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t b16 = (((a_buf + p.a_planes * p.a_plane_bytes) & 0x3FFFFu) >> 4) | lbo_bits;
       for (int r = 0; r < p.TR; ++r) {
         const uint32_t b_lo = b16 + r * row16;
-        uint32_t a_lo = a16 + r * row16;
         uint32_t d = tmem_base;
+        for (int khl = 0; khl < nkh; ++khl) {
+          uint32_t a_lo = a16 + (r + khl) * row16;  // the kh shift is a row offset into the staged input rows
 #pragma unroll 1
-        for (int mb = 0; mb < p.MB; ++mb) {
-          if (leader) {
-            wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
-            if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
-            if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+          for (int mb = 0; mb < p.MB; ++mb) {
+            if (leader) {
+              wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
+              if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+              if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+            }
+            a_lo += mb_step16;
+            d += p.NC;
           }
-          a_lo += mb_step16;
-          d += p.NC;
         }
         accum = 1;
       }
@@ -222,17 +231,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else if (warp < WG_LOADERS / 32) {
     // ===================== loaders (16 warps): fp32 NHWC -> bf16 planes =====================
     const int ltid = threadIdx.x;
-    // Each thread owns one pixel slot (row r, column xl) of the tile and one parity of the channel groups:
-    // lanes 2k and 2k+1 copy the two 16-byte halves of the same 32-byte sector (full sector efficiency on the
-    // L2 -> SM path, which bounds this kernel), and walk the (kw, group pair) list with incremental addresses.
-    const int slots = p.TR * WG_TW;  // 64, 32 or 16: power of two
+    // Lanes 2k and 2k+1 copy the two 16-byte halves (adjacent channel groups) of one 32-byte sector: full sector
+    // efficiency on the L2 -> SM path, which bounds this kernel.  All index walking is incremental (no division).
     const int cgp = ltid & 1;
-    const int slot = (ltid >> 1) & (slots - 1);
-    const int grp = ltid / (2 * slots), ngrp = WG_LOADERS / (2 * slots);
-    const int r = slot / WG_TW, xl = slot % WG_TW;
+    const int xl = (ltid >> 1) & (WG_TW - 1);
+    const int lgrp = ltid >> 5, nlgrp = WG_LOADERS >> 5;  // 16 pixels x 2 parities per warp
     const int npair = (p.ncg + 1) >> 1;
-    const int Q = p.ks * npair;
+    const int QA = p.AR * p.ks * npair;                   // (input row, kw, group pair) items, pair fastest
+    const int slots = p.TR * WG_TW;
     const int ncg_b = nc >> 3;
+    // output-gradient tile: thread -> (pixel slot, parity), walks group pairs
+    const int bslot = (ltid >> 1) & (slots - 1);
+    const int bgrp = ltid / (2 * slots), nbgrp = WG_LOADERS / (2 * slots);
+    const int br = bslot / WG_TW, bxl = bslot % WG_TW;
     uint32_t bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       int tt = t;
@@ -242,36 +253,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int img = tt / p.tiles_y;
       const int y0 = ty * p.TR, x0 = tx * WG_TW;
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
-      const uint32_t a_dst = buf0 + bi * p.buf_bytes + slot * 16;
-      const uint32_t b_dst = buf0 + bi * p.buf_bytes + p.a_planes * p.a_plane_bytes + slot * 16;
-      const int oy = y0 + r, ox = x0 + xl;  // this thread's output pixel
-      // ---- shifted input copies: copy kw holds source pixel (oy + kh - pad, ox + kw - pad); the kw copies of
-      //      one source sector come from L1 (cp.async.ca)
+      const uint32_t a_dst = buf0 + bi * p.buf_bytes + xl * 16;
+      const uint32_t b_dst = buf0 + bi * p.buf_bytes + p.a_planes * p.a_plane_bytes + bslot * 16;
+      // ---- shifted input copies: staged row ar holds image row y0 + ar + kh0 - pad; copy kw holds source column
+      //      x0 + xl + kw - pad; the kw copies of one source sector come from L1 (cp.async.ca)
       {
-        const int gy = oy + kh - p.pad;
-        const bool row_ok = (unsigned)gy < (unsigned)p.h && oy < p.h;
-        const uint8_t* xrow = p.x + (((size_t)img * p.h + (row_ok ? gy : 0)) * p.w) * p.C * 2;
-        int kw = 0, cpi = grp;
-        while (cpi >= npair) { cpi -= npair; ++kw; }
-        for (int q = grp; q < Q; q += ngrp) {
+        int cpi = lgrp, kw = 0, ar = 0;
+        while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
+        for (int q = lgrp; q < QA; q += nlgrp) {
           const int cg = 2 * cpi + cgp;
           if (cg < p.ncg) {
-            const int gx = ox + kw - p.pad;
-            const bool ok = row_ok && (unsigned)gx < (unsigned)p.w;
-            const uint8_t* src = ok ? xrow + ((size_t)gx * p.C + cg * 8) * 2 : p.x;
-            const uint32_t d = a_dst + (uint32_t)(kw * p.ncg + cg) * p.CGS_A;
+            const int gy = y0 + ar + kh0 - p.pad, gx = x0 + xl + kw - p.pad;
+            const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
+            const uint8_t* src = ok ? p.x + ((((size_t)img * p.h + gy) * p.w + gx) * p.C + cg * 8) * 2 : p.x;
+            const uint32_t d = a_dst + (uint32_t)(kw * p.ncg + cg) * p.CGS_A + (uint32_t)ar * (WG_TW * 16);
             wcp_async16_ca(d, src, ok ? 16u : 0u);
             if (p.a_planes == 2) wcp_async16_ca(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
           }
-          cpi += ngrp;
-          while (cpi >= npair) { cpi -= npair; ++kw; }
+          cpi += nlgrp;
+          while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
         }
       }
       // ---- output-gradient tile
       {
+        const int oy = y0 + br, ox = x0 + bxl;
         const bool pix_ok = oy < p.h && ox < p.w;
         const uint8_t* zpix = p.dz + ((((size_t)img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0) * 2;
-        for (int cg = 2 * grp + cgp; cg < ncg_b; cg += 2 * ngrp) {
+        for (int cg = 2 * bgrp + cgp; cg < ncg_b; cg += 2 * nbgrp) {
           const bool ok = pix_ok && (n0 + cg * 8) < p.n_valid;
           const uint8_t* src = ok ? zpix + cg * 16 : p.dz;
           const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B;
@@ -290,36 +298,38 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int rows_total = p.ks * p.ks * p.C + 4;
       float* out = p.ws + (size_t)psplit * rows_total * p.N;
       const bool have_work = t_end > t_begin;
-      for (int mb = 0; mb < p.MB; ++mb) {
-        const int row = mb * 128 + q * 32 + lane;  // (kw, group, channel)
-        const int g = row >> 3, ch = row & 7;
-        int orow = -1;
-        if (g < p.G) {
-          const int kw = g / p.ncg, cg = g - kw * p.ncg;
-          orow = (kh * p.ks + kw) * p.C + cg * 8 + ch;
-        } else if (g == p.G && ch < 4 && kh == 0) {
-          orow = p.ks * p.ks * p.C + ch;  // bias gradient row (+ 3 zero rows)
-        }
-        const uint32_t taddr = tmem_base + mb * p.NC + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < nc; c0 += 16) {
-          uint32_t v[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(taddr + c0)
-              : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (orow >= 0) {
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)orow * p.N + n0 + c0);
+      for (int khl = 0; khl < nkh; ++khl)
+        for (int mb = 0; mb < p.MB; ++mb) {
+          const int kh = kh0 + khl;
+          const int row = mb * 128 + q * 32 + lane;  // (kw, group, channel)
+          const int g = row >> 3, ch = row & 7;
+          int orow = -1;
+          if (g < p.G) {
+            const int kw = g / p.ncg, cg = g - kw * p.ncg;
+            orow = (kh * p.ks + kw) * p.C + cg * 8 + ch;
+          } else if (g == p.G && ch < 4 && kh == 0) {
+            orow = p.ks * p.ks * p.C + ch;  // bias gradient row (+ 3 zero rows)
+          }
+          const uint32_t taddr = tmem_base + (khl * p.MB + mb) * p.NC + ((uint32_t)(q * 32) << 16);
+          for (int c0 = 0; c0 < nc; c0 += 16) {
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr + c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (orow >= 0) {
+              float4* dst = reinterpret_cast<float4*>(out + (size_t)orow * p.N + n0 + c0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              dst[k] = have_work ? make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
-                                               __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int k = 0; k < 4; ++k)
+                dst[k] = have_work ? make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                                 __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
-      }
     }
   }
 
@@ -357,17 +367,48 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   pl->G = d->ksize * pl->ncg;
   pl->MB = (pl->G + 1 + 15) / 16;
   if (pl->MB > 4) return NQ_ERR_UNSUPPORTED;  // C * ks > 504: more accumulator rows than one CTA's TMEM pass
-  int nc = (512 / pl->MB) / 16 * 16;
-  if (nc > 256) nc = 256;
-  if (nc > N) nc = N;
+  // Choose (kernel rows per CTA, columns per CTA): nkh * MB * NC <= 512 TMEM columns.  Model: the kernel is bound
+  // by the larger of its MMA time (A read from shared memory binds narrow N: ~max(NC/2, 32 + NC/6) cycles per
+  // MMA) and its L2 -> SM traffic (dZ once per kernel-row group, the input once per column slice and group).
+  const double P = (double)d->n * d->h * d->w;
+  double best_cost = 1e300;
+  int best_nkh = 1, best_nc = 16;
+  for (int nkh = 1; nkh <= d->ksize; ++nkh) {
+    int nc = (512 / (nkh * pl->MB)) / 16 * 16;
+    if (nc > 256) nc = 256;
+    if (nc > N) nc = N;
+    if (nc < 16) continue;
+    const int nsp = (N + nc - 1) / nc;
+    const int khg = (d->ksize + nkh - 1) / nkh;
+    const double per_mma = nc * 0.5 > 32.0 + nc / 6.0 ? nc * 0.5 : 32.0 + nc / 6.0;
+    const int passes = 1 + (a_planes == 2) + (b_planes == 2);
+    const double mma = P / 16.0 * d->ksize * pl->MB * nsp * passes * per_mma / 148.0;
+    const double in_rows = (4.0 + nkh - 1) / 4.0;
+    const double bytes = P * 2.0 * (b_planes * (double)N * khg + a_planes * (double)C * nsp * khg * in_rows);
+    const double traffic = bytes / (32.0 * 148.0);  // ~32 B/clk/SM sustained on this access pattern
+    const double cost = mma > traffic ? mma : traffic;
+    if (cost < best_cost) { best_cost = cost; best_nkh = nkh; best_nc = nc; }
+  }
+  if (const char* e = getenv("NQ_WG_NKH")) {  // tuning override: kernel rows per CTA
+    int v = atoi(e);
+    if (v >= 1 && v <= d->ksize) {
+      int c = (512 / (v * pl->MB)) / 16 * 16;
+      if (c > 256) c = 256;
+      if (c > N) c = N;
+      if (c >= 16) { best_nkh = v; best_nc = c; }
+    }
+  }
+  int nc = best_nc;
+  pl->nkh = best_nkh;
+  pl->khg = (d->ksize + best_nkh - 1) / best_nkh;
   pl->NC = nc;
   pl->nsplits = (N + nc - 1) / nc;
   // tile rows: as many as leave room for >= 2 pipeline buffers
   int tr = 4, nbuf = 0;
   for (; tr >= 1; tr >>= 1) {
-    const int per_group = tr * WG_TW * 16;  // bytes
-    pl->CGS_A = per_group + 64;             // +64: lane pairs (same pixel, adjacent groups) store conflict free
-    pl->CGS_B = per_group + 64;
+    pl->AR = tr + pl->nkh - 1;
+    pl->CGS_A = pl->AR * WG_TW * 16 + 64;   // +64: lane pairs (same pixel, adjacent groups) store conflict free
+    pl->CGS_B = tr * WG_TW * 16 + 64;
     pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
     pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
     pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
@@ -382,7 +423,7 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   pl->tiles_x = (d->w + WG_TW - 1) / WG_TW;
   pl->tiles_y = (d->h + pl->TR - 1) / pl->TR;
   pl->tiles_total = pl->tiles_x * pl->tiles_y * d->n;
-  int ps = sm_count() / (d->ksize * pl->nsplits);
+  int ps = sm_count() / (pl->khg * pl->nsplits);
   if (ps < 1) ps = 1;
   if (ps > pl->tiles_total) ps = pl->tiles_total;
   pl->tiles_per_split = (pl->tiles_total + ps - 1) / ps;
@@ -411,6 +452,7 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.x = x; p.dz = dz; p.ws = workspace;
   p.n = d->n; p.h = d->h; p.w = d->w; p.C = pl->C; p.N = pl->N; p.ks = d->ksize; p.pad = d->ksize / 2;
   p.ncg = pl->ncg; p.G = pl->G; p.MB = pl->MB; p.NC = pl->NC; p.nsplits = pl->nsplits; p.TR = pl->TR;
+  p.nkh = pl->nkh; p.khg = pl->khg; p.AR = pl->AR;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_total = pl->tiles_total; p.psplits = pl->psplits;
   p.tiles_per_split = pl->tiles_per_split; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.CGS_A = pl->CGS_A; p.CGS_B = pl->CGS_B; p.a_plane_bytes = pl->a_plane_bytes; p.b_plane_bytes = pl->b_plane_bytes;
@@ -421,7 +463,7 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.dz_plane_bytes = (size_t)d->n * d->h * d->w * p.dz_stride * 2;
   cudaStream_t s = as_stream(stream);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  const int grid = pl->psplits * pl->nsplits * d->ksize;
+  const int grid = pl->psplits * pl->nsplits * pl->khg;
   wgrad_tc_kernel<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
   NQ_LAUNCH_CHECK();
   const int64_t n4 = (int64_t)(d->ksize * d->ksize * pl->C + 4) * pl->N / 4;

@@ -96,6 +96,7 @@ def test_tc_plans_fit_for_every_workload():
                 if st == -3 and d.cin_p * d.ksize > 504:
                     continue  # wide 12M-class stages: more accumulator rows than one TMEM pass -> FFMA wgrad kernel
                 assert st == 0, (arch, i, st)
-                assert wp.MB * wp.NC <= 512 and wp.NC % 16 == 0 and wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2
+                assert wp.nkh * wp.MB * wp.NC <= 512 and wp.NC % 16 == 0 and wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2
+                assert wp.khg * wp.nkh >= d.ksize and wp.AR == wp.TR + wp.nkh - 1
                 assert wp.G + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
-                assert wp.psplits * wp.nsplits * d.ksize <= max(148, wp.nsplits * d.ksize)
+                assert wp.psplits * wp.nsplits * wp.khg <= max(148, wp.nsplits * wp.khg)
