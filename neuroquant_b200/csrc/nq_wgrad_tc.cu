@@ -398,28 +398,36 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
       if (c >= 16) { best_nkh = v; best_nc = c; }
     }
   }
-  int nc = best_nc;
-  pl->nkh = best_nkh;
-  pl->khg = (d->ksize + best_nkh - 1) / best_nkh;
-  pl->NC = nc;
-  pl->nsplits = (N + nc - 1) / nc;
-  // tile rows: as many as leave room for >= 2 pipeline buffers
-  int tr = 4, nbuf = 0;
-  for (; tr >= 1; tr >>= 1) {
-    pl->AR = tr + pl->nkh - 1;
-    pl->CGS_A = pl->AR * WG_TW * 16 + 64;   // +64: lane pairs (same pixel, adjacent groups) store conflict free
-    pl->CGS_B = tr * WG_TW * 16 + 64;
-    pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
-    pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
-    pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
-    nbuf = (227 * 1024 - 128) / pl->buf_bytes;
-    if (nbuf >= 2) break;
+  // shared-memory fit: tile rows as many as leave room for >= 2 pipeline buffers
+  auto fit = [&](int nkh, int nc) -> bool {
+    pl->nkh = nkh;
+    pl->khg = (d->ksize + nkh - 1) / nkh;
+    pl->NC = nc;
+    pl->nsplits = (N + nc - 1) / nc;
+    int nbuf = 0, tr = 4;
+    for (; tr >= 1; tr >>= 1) {
+      pl->AR = tr + nkh - 1;
+      pl->CGS_A = pl->AR * WG_TW * 16 + 64;  // +64: lane pairs (same pixel, adjacent groups) store conflict free
+      pl->CGS_B = tr * WG_TW * 16 + 64;
+      pl->a_plane_bytes = pl->MB * 16 * pl->CGS_A;
+      pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
+      pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
+      nbuf = (227 * 1024 - 128) / pl->buf_bytes;
+      if (nbuf >= 2) break;
+    }
+    if (nbuf < 2) return false;
+    pl->TR = tr;
+    pl->nbuf = nbuf > 4 ? 4 : nbuf;
+    pl->smem_bytes = 128 + pl->nbuf * pl->buf_bytes;
+    return true;
+  };
+  if (!fit(best_nkh, best_nc)) {
+    // fall back to one kernel row per CTA with the widest column slice
+    int c = (512 / pl->MB) / 16 * 16;
+    if (c > 256) c = 256;
+    if (c > N) c = N;
+    if (!fit(1, c)) return NQ_ERR_UNSUPPORTED;
   }
-  if (nbuf < 2) return NQ_ERR_UNSUPPORTED;
-  if (nbuf > 4) nbuf = 4;
-  pl->TR = tr;
-  pl->nbuf = nbuf;
-  pl->smem_bytes = 128 + nbuf * pl->buf_bytes;
   pl->tiles_x = (d->w + WG_TW - 1) / WG_TW;
   pl->tiles_y = (d->h + pl->TR - 1) / pl->TR;
   pl->tiles_total = pl->tiles_x * pl->tiles_y * d->n;
