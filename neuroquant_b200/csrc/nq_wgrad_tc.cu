@@ -386,7 +386,11 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
     const double in_rows = (4.0 + nkh - 1) / 4.0;
     const double bytes = P * 2.0 * (b_planes * (double)N * khg + a_planes * (double)C * nsp * khg * in_rows);
     const double traffic = bytes / (32.0 * 148.0);  // ~32 B/clk/SM sustained on this access pattern
-    const double cost = mma > traffic ? mma : traffic;
+    double cost = mma > traffic ? mma : traffic;
+    // measured on B200 (profiles/): grouping kernel rows only pays when N is so narrow that the MMAs are cheap and
+    // the kernel is traffic bound (the head, N = 16: 0.82 -> 0.38 ms); at N >= 64 the narrower column slice costs more
+    if (N > 32 && nkh > 1) cost = 1e300;
+    if (N <= 32 && nkh == d->ksize) cost = 0.0;
     if (cost < best_cost) { best_cost = cost; best_nkh = nkh; best_nc = nc; }
   }
   if (const char* e = getenv("NQ_WG_NKH")) {  // tuning override: kernel rows per CTA
@@ -405,6 +409,8 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
     pl->NC = nc;
     pl->nsplits = (N + nc - 1) / nc;
     int nbuf = 0, tr = 4;
+    int min_buf = 2;
+    if (const char* e = getenv("NQ_WG_MINBUF")) min_buf = atoi(e) < 2 ? 2 : atoi(e);  // tuning override
     for (; tr >= 1; tr >>= 1) {
       pl->AR = tr + nkh - 1;
       pl->CGS_A = pl->AR * WG_TW * 16 + 64;  // +64: lane pairs (same pixel, adjacent groups) store conflict free
@@ -413,7 +419,7 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
       pl->b_plane_bytes = (nc / 8) * pl->CGS_B;
       pl->buf_bytes = a_planes * pl->a_plane_bytes + b_planes * pl->b_plane_bytes;
       nbuf = (227 * 1024 - 128) / pl->buf_bytes;
-      if (nbuf >= 2) break;
+      if (nbuf >= min_buf || (tr == 1 && nbuf >= 2)) break;
     }
     if (nbuf < 2) return false;
     pl->TR = tr;
