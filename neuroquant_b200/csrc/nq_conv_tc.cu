@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(A_FULL + i * 8, TC_LOADERS / 32);  // one arrival per loader warp
+      mbar_init(A_FULL + i * 8, TC_LOADERS);  // one deferred arrival per loader thread
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
       mbar_init(T_EMPTY + i * 8, 8);
@@ -422,9 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ===================== activation loaders: split-bf16 NHWC -> halo tile, 16-byte cp.async =====================
     const int ltid = threadIdx.x - 8 * 32;
     const int npix = p.PW * p.PH;
-    // completion: one cp.async group per unit, one unit kept in flight per thread, one barrier arrival per warp
     uint32_t uc = 0;
-    int prev_buf = -1;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
       const uint8_t* img = p.in + (size_t)tc.img * p.h * p.w * p.in_stride * 2;
@@ -456,19 +454,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           pix += TC_LOADERS / 2;
           while (pix >= npix) { pix -= npix; ++cpi; }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (prev_buf >= 0) {
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(A_FULL + prev_buf * 8);
-        }
-        prev_buf = (int)abuf;
+        cp_async_arrive(A_FULL + abuf * 8);
       }
-    }
-    if (prev_buf >= 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(A_FULL + prev_buf * 8);
     }
   } else if (warp < 8) {
     // ===================== epilogue: TMEM -> registers -> global (8 warps) =====================

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nbuf; ++i) {
-      wbar_init(FULL + i * 8, WG_LOADERS / 32);  // one arrival per loader warp
+      wbar_init(FULL + i * 8, WG_LOADERS);  // one deferred cp.async arrival per loader thread
       wbar_init(EMPTY + i * 8, 1);
     }
     wbar_init(DONE, 1);
@@ -244,10 +244,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int bslot = (ltid >> 1) & (slots - 1);
     const int bgrp = ltid / (2 * slots), nbgrp = WG_LOADERS / (2 * slots);
     const int br = bslot / WG_TW, bxl = bslot % WG_TW;
-    // Completion: every thread commits one cp.async group per tile and keeps ONE tile in flight
-    // (cp.async.wait_group 1); when its previous group has landed the warp arrives once on that buffer's barrier
-    // (16 arrivals per tile instead of one deferred arrival per thread: the barrier traffic was a fixed cost per tile)
-    uint32_t bi = 0, ph = 0, prev_bi = 0;
+    uint32_t bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       int tt = t;
       const int tx = tt % p.tiles_x;
@@ -290,19 +287,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           if (p.b_planes == 2) wcp_async16(d + p.b_plane_bytes, src + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (t > t_begin) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) wbar_arrive(FULL + prev_bi * 8);
-      }
-      prev_bi = bi;
+      wcp_async_arrive(FULL + bi * 8);
       if (++bi == (uint32_t)p.nbuf) { bi = 0; ph ^= 1; }
-    }
-    if (t_end > t_begin) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) wbar_arrive(FULL + prev_bi * 8);
     }
     // ===================== epilogue (warps 0-3): TMEM -> partial dW =====================
     if (warp < 4) {
