@@ -38,6 +38,8 @@ constexpr int TC_THREADS = 640;
 constexpr int TC_LOADERS = 256;  // warps 8-15
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 8;
+constexpr int EPI_ROW = 20;            // floats per staged epilogue row (16 + 4 pad: conflict-free 16-byte accesses)
+constexpr int EPI_STAGE_BYTES = 8 * 32 * EPI_ROW * 4;  // 8 epilogue warps
 
 struct TcParams {
   const uint8_t* in;     // split-bf16 input: plane 0 (hi) then plane 1 (lo), each (n, h, w, in_stride) bf16
@@ -61,6 +63,7 @@ struct TcParams {
   int a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages;
   int in_stride, c_valid;  // channels per pixel stored in `in` (<= C) : channels >= c_valid are read as zero
   int n_store;           // dgrad: columns actually stored / row stride of zprev and out (<= N, N padded to 16)
+  int epi_stage_off;     // byte offset of the epilogue staging tiles in shared memory
   int cs;                // CTAs per cluster sharing every weight stage by TMA multicast (1, 2 or 4)
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
 };
@@ -458,83 +461,87 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else if (warp < 8) {
-    // ===================== epilogue: TMEM -> registers -> global (8 warps) =====================
-    // Two warps per TMEM lane quarter; they take alternate 16-column chunks.  Per chunk: the global
-    // operands (scale / bias, or z of the previous stage) are requested BEFORE waiting on the TMEM load.
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> global (8 warps) =====================
+    // Two warps per TMEM lane quarter; they take alternate 16-column chunks.  tcgen05.ld hands every lane one
+    // ROW (pixel) of the chunk; storing from that layout touches 32 different sectors per instruction with 8-16
+    // useful bytes each.  The chunk is therefore transposed through a per-warp staging tile so that 4 lanes hold
+    // the 16 consecutive channels of one pixel: every store (and the z / scale / bias load) then moves whole
+    // 32-byte sectors.
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int half = warp >> 2;
-    const int m = q * 32 + lane;
-    const int ly = m >> 3, lx = m & 7;
+    float* stg = reinterpret_cast<float*>(smem + p.epi_stage_off) + warp * (32 * EPI_ROW);
+    const int qd = lane & 3;         // 4-channel quad of the chunk this lane stores
+    const int rsub = lane >> 2;      // row (pixel) within each group of 8 rows
     uint32_t tcnt = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters, ++tcnt) {
       const TileCoord tc = tile_coord(p, t, rank);
       const uint32_t acc = tcnt & 1;
-      const int y = tc.y0 + ly, x = tc.x0 + lx;
-      const bool valid = tc.real && y < p.h && x < p.w;
+      // the four pixels (one per 8-row group) this lane stores: m = q*32 + it*8 + rsub, tile row m>>3 = q*4 + it
+      size_t row_base[4], zrow[4];
+      bool valid[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int y = tc.y0 + q * 4 + it, x = tc.x0 + rsub;
+        valid[it] = tc.real && y < p.h && x < p.w;
+        if (p.epi == 0) {
+          row_base[it] = (((size_t)tc.img * (p.h * p.rh) + (size_t)y * p.rh) * (p.w * p.rw) + (size_t)x * p.rw) * p.cg;
+          zrow[it] = 0;
+        } else {
+          const int qh = y / p.rh, si = y - qh * p.rh, qw = x / p.rw, sj = x - qw * p.rw;
+          row_base[it] = (((size_t)tc.img * (p.h / p.rh) + qh) * (p.w / p.rw) + qw) * ((size_t)p.rh * p.rw * p.n_store) +
+                         (size_t)(si * p.rw + sj) * p.n_store;
+          zrow[it] = (((size_t)tc.img * p.h + y) * p.w + x) * p.n_store;
+        }
+      }
       mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      size_t row_base = 0;   // fwd: pixel (y*rh, x*rw) of the shuffled grid; dgrad: un-shuffled destination
-      size_t zrow = 0;
-      if (p.epi == 0) {
-        row_base = (((size_t)tc.img * (p.h * p.rh) + (size_t)y * p.rh) * (p.w * p.rw) + (size_t)x * p.rw) * p.cg;
-      } else {
-        const int qh = y / p.rh, si = y - qh * p.rh, qw = x / p.rw, sj = x - qw * p.rw;
-        row_base = (((size_t)tc.img * (p.h / p.rh) + qh) * (p.w / p.rw) + qw) * ((size_t)p.rh * p.rw * p.n_store) +
-                   (size_t)(si * p.rw + sj) * p.n_store;
-        zrow = (((size_t)tc.img * p.h + y) * p.w + x) * p.n_store;
-      }
       for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
-        const int nb = tc.n0 + c0;
-        float4 g0[4], g1[4];  // fwd: scale, bias; dgrad: z of the previous stage
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          g0[qd] = make_float4(1.f, 1.f, 1.f, 1.f);
-          g1[qd] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.epi == 0) {
-            if (nb + qd * 4 < p.n_store) {
-              if (p.scale) g0[qd] = __ldg(reinterpret_cast<const float4*>(p.scale + nb + qd * 4));
-              if (p.bias) g1[qd] = __ldg(reinterpret_cast<const float4*>(p.bias + nb + qd * 4));
-            }
-          } else if (valid && p.zprev && p.act == 1 && nb + qd * 4 < p.n_store) {
-            g0[qd] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow + nb + qd * 4));
-          }
-        }
-        // (group, channel) of column nb for the forward shuffle: n = grp * cg + c
-        int grp = 0, c = 0;
-        if (p.epi == 0) {
-          grp = nb / p.cg;
-          c = nb - grp * p.cg;
+        const int n = tc.n0 + c0 + qd * 4;  // first of this lane's 4 columns
+        const bool col_ok = n < p.n_store;
+        float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        size_t col_off = (size_t)n;  // dgrad: plain column; fwd: (group, channel) of the shuffle
+        if (p.epi == 0 && col_ok) {
+          if (p.scale) g0 = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+          if (p.bias) g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const int grp = n / p.cg, c = n - grp * p.cg;
+          const int si = grp / p.rw, sj = grp - si * p.rw;
+          col_off = ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
         }
         tmem_ld_wait();
+        {  // own row -> staging tile (row stride EPI_ROW floats keeps the 16-byte stores conflict free)
+          float4* rowp = reinterpret_cast<float4*>(stg + lane * EPI_ROW);
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          float4 r = make_float4(__uint_as_float(v[qd * 4 + 0]), __uint_as_float(v[qd * 4 + 1]),
-                                 __uint_as_float(v[qd * 4 + 2]), __uint_as_float(v[qd * 4 + 3]));
+          for (int k = 0; k < 4; ++k)
+            rowp[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                                  __uint_as_float(v[4 * k + 3]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float4 r = *reinterpret_cast<const float4*>(stg + (it * 8 + rsub) * EPI_ROW + qd * 4);
+          if (!(valid[it] && col_ok)) continue;
           if (p.epi == 0) {
-            r.x = fmaf(r.x, g0[qd].x, g1[qd].x); r.y = fmaf(r.y, g0[qd].y, g1[qd].y);
-            r.z = fmaf(r.z, g0[qd].z, g1[qd].z); r.w = fmaf(r.w, g0[qd].w, g1[qd].w);
-            const int si = grp / p.rw, sj = grp - si * p.rw;
-            const size_t o = row_base + ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
-            if (valid && nb + qd * 4 < p.n_store) {
-              if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
-              if (p.out_y) {
-                if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
-                store_split4(p.out_y, p.out_plane_bytes, o, r);
-              }
+            r.x = fmaf(r.x, g0.x, g1.x); r.y = fmaf(r.y, g0.y, g1.y);
+            r.z = fmaf(r.z, g0.z, g1.z); r.w = fmaf(r.w, g0.w, g1.w);
+            const size_t o = row_base[it] + col_off;
+            if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
+            if (p.out_y) {
+              if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
+              store_split4(p.out_y, p.out_plane_bytes, o, r);
             }
-            c += 4;
-            if (c >= p.cg) { c -= p.cg; ++grp; }
-          } else if (valid && nb + qd * 4 < p.n_store) {
+          } else {
             if (p.zprev && p.act == 1) {
-              r.x *= gelu_grad_fast(g0[qd].x); r.y *= gelu_grad_fast(g0[qd].y);
-              r.z *= gelu_grad_fast(g0[qd].z); r.w *= gelu_grad_fast(g0[qd].w);
+              const float4 z = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
+              r.x *= gelu_grad_fast(z.x); r.y *= gelu_grad_fast(z.y);
+              r.z *= gelu_grad_fast(z.z); r.w *= gelu_grad_fast(z.w);
             }
-            store_split4(p.out_y, p.out_plane_bytes, row_base + nb + qd * 4, r);
+            store_split4(p.out_y, p.out_plane_bytes, row_base[it] + n, r);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -689,7 +696,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
     int kc = sbc >= 64 ? sbc : sbc * (64 / sbc);
     if (kc > C) kc = C;
     const int a_buf = pl->CGS * (kc / 8) * a_planes;
-    const int budget = 227 * 1024 - 256 - 2 * a_buf;
+    const int budget = 227 * 1024 - 256 - EPI_STAGE_BYTES - 2 * a_buf;
     if (budget < 3 * stage) continue;
     best = sbc;
     break;
@@ -702,12 +709,12 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
   pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
   pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes;
-  const int budget = 227 * 1024 - 256 - 2 * pl->a_buf_bytes;
+  const int budget = 227 * 1024 - 256 - EPI_STAGE_BYTES - 2 * pl->a_buf_bytes;
   int nst = budget / pl->b_stage_bytes;
   if (nst > TC_MAX_BSTAGES) nst = TC_MAX_BSTAGES;
   if (nst < 2) return NQ_ERR_UNSUPPORTED;
   pl->n_bstages = nst;
-  pl->smem_bytes = 256 + 2 * pl->a_buf_bytes + nst * pl->b_stage_bytes;
+  pl->smem_bytes = 256 + 2 * pl->a_buf_bytes + nst * pl->b_stage_bytes + EPI_STAGE_BYTES;
   pl->tiles_x = (d->w + TILE_W - 1) / TILE_W;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
@@ -770,6 +777,7 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
+  p.epi_stage_off = 256 + 2 * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
   NQ_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
   int cs = pl->cluster;
