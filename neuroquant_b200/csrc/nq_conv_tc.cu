@@ -510,6 +510,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int si = grp / p.rw, sj = grp - si * p.rw;
           col_off = ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
         }
+        float4 zv[4];  // dgrad: z of the previous stage for this lane's 4 pixels, requested before the TMEM wait
+        if (p.epi == 1) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            zv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.zprev && p.act == 1 && valid[it] && col_ok)
+              zv[it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
+          }
+        }
         tmem_ld_wait();
         {  // own row -> staging tile (row stride EPI_ROW floats keeps the 16-byte stores conflict free)
           float4* rowp = reinterpret_cast<float4*>(stg + lane * EPI_ROW);
@@ -534,9 +543,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           } else {
             if (p.zprev && p.act == 1) {
-              const float4 z = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
-              r.x *= gelu_grad_fast(z.x); r.y *= gelu_grad_fast(z.y);
-              r.z *= gelu_grad_fast(z.z); r.w *= gelu_grad_fast(z.w);
+              r.x *= gelu_grad_fast(zv[it].x); r.y *= gelu_grad_fast(zv[it].y);
+              r.z *= gelu_grad_fast(zv[it].z); r.w *= gelu_grad_fast(zv[it].w);
             }
             store_split4(p.out_y, p.out_plane_bytes, row_base[it] + n, r);
           }
