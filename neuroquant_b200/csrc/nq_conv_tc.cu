@@ -493,26 +493,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           zrow[it] = (((size_t)tc.img * p.h + y) * p.w + x) * p.n_store;
         }
       }
-      // dgrad: z of the previous stage does not depend on the MMAs -- request it for this warp's first two chunks
-      // BEFORE waiting for the accumulator, so its DRAM latency overlaps the tile's MMAs
-      float4 zpre[2][4];
-      if (p.epi == 1) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int n = tc.n0 + half * 16 + k * 32 + qd * 4;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            zpre[k][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.zprev && p.act == 1 && valid[it] && half * 16 + k * 32 < tc.nt && n < p.n_store)
-              zpre[k][it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
-          }
-        }
-      }
       mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      int chunk = 0;
-      for (int c0 = half * 16; c0 < tc.nt; c0 += 32, ++chunk) {
+      for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         const int n = tc.n0 + c0 + qd * 4;  // first of this lane's 4 columns
@@ -530,13 +514,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (p.epi == 1) {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            if (chunk == 0) zv[it] = zpre[0][it];
-            else if (chunk == 1) zv[it] = zpre[1][it];
-            else {
-              zv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.zprev && p.act == 1 && valid[it] && col_ok)
-                zv[it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
-            }
+            zv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.zprev && p.act == 1 && valid[it] && col_ok)
+              zv[it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
           }
         }
         tmem_ld_wait();
