@@ -244,6 +244,39 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int bslot = (ltid >> 1) & (slots - 1);
     const int bgrp = ltid / (2 * slots), nbgrp = WG_LOADERS / (2 * slots);
     const int br = bslot / WG_TW, bxl = bslot % WG_TW;
+    // The (input row, kw, group) items a thread copies are the same for every tile: decode them ONCE into
+    // registers (source offset relative to the tile origin, destination offset, dy, dx); the per-tile work is then
+    // a bounds test and two adds per copy.  (The decode loop per tile made this kernel issue bound.)
+    constexpr int MAXI = 8;
+    int a_so[MAXI], a_do[MAXI], a_dyx[MAXI];  // source element offset, destination byte offset, (dy << 16) | (dx & 0xffff)
+    int na = 0;
+    bool a_table = true;
+    {
+      int cpi = lgrp, kw = 0, ar = 0;
+      while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
+      for (int q = lgrp; q < QA; q += nlgrp) {
+        const int cg = 2 * cpi + cgp;
+        if (cg < p.ncg) {
+          if (na < MAXI) {
+            const int dy = ar + kh0 - p.pad, dx = xl + kw - p.pad;
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k)
+              if (k == na) {
+                a_so[k] = (dy * p.w + dx) * p.C + cg * 8;
+                a_do[k] = (kw * p.ncg + cg) * p.CGS_A + ar * (WG_TW * 16) + xl * 16;
+                a_dyx[k] = (dy << 16) | (dx & 0xffff);
+              }
+            ++na;
+          } else {
+            a_table = false;  // more items than registers: generic path below
+          }
+        }
+        cpi += nlgrp;
+        while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
+      }
+    }
+    const uint16_t* xh = reinterpret_cast<const uint16_t*>(p.x);
+    const uint16_t* zh = reinterpret_cast<const uint16_t*>(p.dz);
     uint32_t bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       int tt = t;
@@ -253,11 +286,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int img = tt / p.tiles_y;
       const int y0 = ty * p.TR, x0 = tx * WG_TW;
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
-      const uint32_t a_dst = buf0 + bi * p.buf_bytes + xl * 16;
-      const uint32_t b_dst = buf0 + bi * p.buf_bytes + p.a_planes * p.a_plane_bytes + bslot * 16;
+      const uint32_t buf = buf0 + bi * p.buf_bytes;
       // ---- shifted input copies: staged row ar holds image row y0 + ar + kh0 - pad; copy kw holds source column
       //      x0 + xl + kw - pad; the kw copies of one source sector come from L1 (cp.async.ca)
-      {
+      if (a_table) {
+        const uint16_t* origin = xh + (((size_t)img * p.h + y0) * p.w + x0) * p.C;
+#pragma unroll
+        for (int k = 0; k < MAXI; ++k) {
+          if (k < na) {
+            const int gy = y0 + (a_dyx[k] >> 16), gx = x0 + (int)(int16_t)(a_dyx[k] & 0xffff);
+            const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
+            const uint16_t* src = ok ? origin + a_so[k] : xh;
+            const uint32_t d = buf + (uint32_t)a_do[k];
+            wcp_async16_ca(d, src, ok ? 16u : 0u);
+            if (p.a_planes == 2)
+              wcp_async16_ca(d + p.a_plane_bytes, reinterpret_cast<const uint8_t*>(src) + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
+          }
+        }
+      } else {
+        const uint32_t a_dst = buf + xl * 16;
         int cpi = lgrp, kw = 0, ar = 0;
         while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
         for (int q = lgrp; q < QA; q += nlgrp) {
@@ -276,15 +323,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
       // ---- output-gradient tile
       {
+        const uint32_t b_dst = buf + p.a_planes * p.a_plane_bytes + bslot * 16;
         const int oy = y0 + br, ox = x0 + bxl;
         const bool pix_ok = oy < p.h && ox < p.w;
-        const uint8_t* zpix = p.dz + ((((size_t)img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0) * 2;
+        const uint16_t* zpix = zh + (((size_t)img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0;
+#pragma unroll 2
         for (int cg = 2 * bgrp + cgp; cg < ncg_b; cg += 2 * nbgrp) {
           const bool ok = pix_ok && (n0 + cg * 8) < p.n_valid;
-          const uint8_t* src = ok ? zpix + cg * 16 : p.dz;
+          const uint16_t* src = ok ? zpix + cg * 8 : zh;
           const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B;
           wcp_async16(d, src, ok ? 16u : 0u);
-          if (p.b_planes == 2) wcp_async16(d + p.b_plane_bytes, src + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
+          if (p.b_planes == 2)
+            wcp_async16(d + p.b_plane_bytes, reinterpret_cast<const uint8_t*>(src) + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
         }
       }
       wcp_async_arrive(FULL + bi * 8);
