@@ -254,6 +254,9 @@ class DecoderEngine:
         self.bwd_a_planes = int(os.environ.get("NQ_BWD_A_PLANES", "2"))
         self.bwd_b_planes = int(os.environ.get("NQ_BWD_B_PLANES", "2"))
         self.wgrad_tc = os.environ.get("NQ_WGRAD", "tc").lower() != "simt"
+        # weight-gradient operand planes (input activations, output gradients): default = the backward setting
+        self.wg_a_planes = int(os.environ.get("NQ_WG_A_PLANES", str(self.bwd_a_planes)))
+        self.wg_b_planes = int(os.environ.get("NQ_WG_B_PLANES", str(self.bwd_b_planes)))
         self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
@@ -522,7 +525,7 @@ class DecoderEngine:
 
     def _wg_plan(self, d: L.ConvDesc):
         pl = L.TcWgradPlan()
-        st = L.lib.nq_tc_plan_wgrad(C.byref(d), self.bwd_a_planes, self.bwd_b_planes, C.byref(pl))
+        st = L.lib.nq_tc_plan_wgrad(C.byref(d), self.wg_a_planes, self.wg_b_planes, C.byref(pl))
         return pl if st == 0 else None
 
     def _wgrad_splits(self, d: L.ConvDesc) -> int:
