@@ -51,6 +51,7 @@ def config_of(args, world):
             "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world, "hadamard": bool(args.hadamard),
             "parallelism": f"dp{world} (frame-sharded, NCCL all-reduce of dW)" if world > 1 else "single GPU",
             "l2": "no explicit flush: each step streams >2 GB of activations, far above the 126 MB L2",
+            "launch": "CUDA graph replay of the iteration (1 GPU) / eager launches around the NCCL all-reduce (N > 1)",
             **{k: v for k, v in HYPER.items()}}
 
 
@@ -202,7 +203,18 @@ def run_b200(args):
     reg_w, reg_b = HYPER["weight"], 10.0  # mid-schedule temperature: regulariser on, as in 80% of the run
     stage_ev = []
 
-    def step(i, embed, frames, profile=False):
+    from neuroquant_b200.calibration import GraphedStep
+    use_graph = world == 1 and os.environ.get("NQ_GRAPH", "1") != "0"
+    graphed = {}
+
+    def step(i, embed, frames, eager=False):
+        """One AdaRound iteration exactly as CalibrationLoop.iteration runs it: on one GPU the kernel sequence is
+        captured once as a CUDA graph and replayed; data-parallel runs launch it eagerly around the all-reduce."""
+        if use_graph and not eager:
+            if "g" not in graphed:
+                graphed["g"] = GraphedStep(eng, opt, embed, frames, HYPER["p"], mean_pixels)
+            graphed["g"].run(embed, frames, reg_w, reg_b)
+            return
         eng.forward(embed, train=True, target=frames, p_norm=HYPER["p"], mean_pixels=mean_pixels, want_img=False)
         flat = eng.backward()
         if world > 1:
@@ -249,7 +261,7 @@ def run_b200(args):
     value = args.steps * world / (ms * 1e-3)
 
     # ---- per-kernel timing of the convolution launches (CUDA events on the launch stream)
-    kern = eng.kernel_profile(lambda: step(0, *resident(0)), reps=3)
+    kern = eng.kernel_profile(lambda: step(0, *resident(0), eager=True), reps=3)
 
     # ---- end to end: host buffers in, loss out, every step
     h2d = B * (c * h0 * w0 + 3 * H * W) * 4

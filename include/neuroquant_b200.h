@@ -93,6 +93,15 @@ int nq_adaround_init_alpha(const float* x, const float* delta, int64_t rows, int
 int nq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                  double lr, double beta1, double beta2, double eps, int step, void* stream);
 
+/* CUDA-graph variants of the two calls whose scalars change every iteration: hyper_dev is a device array
+ * {reg_w, reg_b, lr / (1 - beta1^t), sqrt(1 - beta2^t)} that the host refreshes (one 16-byte copy) before each
+ * replay of the captured iteration.  use_reg = 0 ignores the regulariser entries (bias quantisers). */
+int nq_fakequant_bwd_soft_dev(const float* g, const float* x, const float* alpha, const float* delta,
+                              const float* zero_point, int64_t rows, int64_t row_len, int d_stride, int n_bits,
+                              float grad_scale, int use_reg, const float* hyper_dev, float* d_alpha, void* stream);
+int nq_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     double beta1, double beta2, double eps, const float* hyper_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Walsh-Hadamard rotation (quantization/quant_layer.py:16-22; third-party hadamard_transform)
  * ------------------------------------------------------------------------------------------------ */

@@ -69,6 +69,8 @@ def _load():
         "nq_fakequant_bwd": (I, [P, P, P, P, P, L, L, I, I, I, F, F, F, P, P, P]),
         "nq_adaround_init_alpha": (I, [P, P, L, L, I, P, P]),
         "nq_adam_step": (I, [P, P, P, P, L, D, D, D, D, I, P]),
+        "nq_fakequant_bwd_soft_dev": (I, [P, P, P, P, P, L, L, I, I, F, I, P, P, P]),
+        "nq_adam_step_dev": (I, [P, P, P, P, L, D, D, D, P, P]),
         "nq_fwht": (I, [P, P, L, I, L, L, P]),
         "nq_pack_weight": (I, [DP, P, I, P, P, P, P, P]),
         "nq_conv_fwd": (I, [DP, P, P, P, P, P, P]),

@@ -14,6 +14,7 @@ count, so the sum of the per-rank gradients is the gradient of the reference's m
 from __future__ import annotations
 
 import logging
+import os
 from typing import Callable, Iterable, List, Optional, Sequence
 
 import torch
@@ -37,6 +38,55 @@ class LinearTempDecay:
         return self.end_b + (self.start_b - self.end_b) * max(0.0, (1 - rel_t))
 
 
+class GraphedStep:
+    """One calibration iteration (forward, loss, backward, quantiser Jacobian, Adam) captured ONCE as a CUDA graph
+    and replayed: ~100 kernel launches become one graph launch.  Inputs are copied into static buffers; the four
+    scalars that change per iteration go through a 16-byte device array (nq_*_dev kernels).  Single-GPU AdaRound
+    phase only; the eager path stays for iterations that log and for data-parallel runs."""
+
+    def __init__(self, eng: DecoderEngine, opt: AdamState, embed: torch.Tensor, frames: torch.Tensor, p_norm: float,
+                 mean_pixels: float):
+        self.eng, self.opt, self.p_norm, self.mean_pixels = eng, opt, p_norm, mean_pixels
+        self.embed = torch.empty_like(embed)
+        self.frames = torch.empty_like(frames)
+        self.hyper = torch.zeros(4, device=embed.device)
+        self.hyper_host = torch.zeros(4).pin_memory()
+        self.graph = None
+        self.launches_per_replay = 0
+
+    def _body(self):
+        eng = self.eng
+        eng.forward(self.embed, train=True, target=self.frames, p_norm=self.p_norm, mean_pixels=self.mean_pixels, want_img=False)
+        eng.backward()
+        grads = eng.param_grads(1.0, hyper=self.hyper)
+        self.opt.step_dev([g for pair in grads for g in pair], self.hyper)
+        eng.launches += len(self.opt.params)
+
+    def run(self, embed, frames, reg_w: float, reg_b: float):
+        self.embed.copy_(embed)
+        self.frames.copy_(frames)
+        step_size, bc2_sqrt = self.opt.hyper_of_next_step()
+        self.hyper_host[0], self.hyper_host[1], self.hyper_host[2], self.hyper_host[3] = reg_w, reg_b, step_size, bc2_sqrt
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        if self.graph is None:
+            l0 = self.eng.launches
+            self._body()  # eager once: allocates every lazily-created buffer, and is this iteration's real work
+            self.launches_per_replay = self.eng.launches - l0
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            saved = [t.clone() for t in self.opt.params + self.opt.m + self.opt.v]  # capture must not advance the state
+            with torch.cuda.graph(g):
+                self._body()
+            self.eng.launches -= self.launches_per_replay  # launches issued during capture do not execute
+            for t, s in zip(self.opt.params + self.opt.m + self.opt.v, saved):
+                t.copy_(s)
+            self.graph = g
+        else:
+            self.graph.replay()
+            self.eng.launches += self.launches_per_replay
+        self.eng.invalidate()
+
+
 class CalibrationLoop:
     """One calibration run.  `fetch(idx) -> (embed, frames)` returns this rank's shard of the
     mini-batch `idx` as device tensors (NCHW)."""
@@ -52,6 +102,8 @@ class CalibrationLoop:
             self.world = torch.distributed.get_world_size(group)
         self.global_batch = global_batch
         self.log = log
+        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and self.world == 1
+        self._graphed = {}
         self.ep1 = int(0.05 * iters / n_batches)  # calib_model.py:144
         self.ep2 = int(iters / n_batches) - self.ep1  # calib_model.py:205
         self.count = 0
@@ -62,6 +114,13 @@ class CalibrationLoop:
         embed, frames = self.fetch(idx)
         n, _, H, W = frames.shape
         gb = self.global_batch if self.global_batch is not None else n * self.world
+        if self.use_graph and eng.mode == "ada" and not want_log:
+            key = (tuple(embed.shape), tuple(frames.shape), id(opt))
+            gs = self._graphed.get(key)
+            if gs is None:
+                gs = self._graphed[key] = GraphedStep(eng, opt, embed, frames, self.p, float(gb * H * W))
+            gs.run(embed, frames, reg_w, reg_b)
+            return
         eng.forward(embed, train=True, target=frames, p_norm=self.p, mean_pixels=float(gb * H * W),
                     reg_b=reg_b if (reg_w != 0.0 and want_log) else None, want_img=False)
         flat = eng.backward()

@@ -88,7 +88,12 @@ __global__ void __launch_bounds__(256) fakequant_fwd_kernel(
 __global__ void __launch_bounds__(256) fakequant_bwd_soft_kernel(
     const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ alpha,
     const float* __restrict__ delta, const float* __restrict__ zp, int64_t numel, int row_len,
-    int d_stride, float qmax, float grad_scale, float reg_w, float reg_b, float* __restrict__ d_alpha) {
+    int d_stride, float qmax, float grad_scale, float reg_w, float reg_b, float* __restrict__ d_alpha,
+    const float* __restrict__ hyper) {
+  if (hyper != nullptr) {  // CUDA-graph replay: the schedule values live in device memory
+    reg_w = hyper[0];
+    reg_b = hyper[1];
+  }
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = (e / row_len) * d_stride;
@@ -154,7 +159,12 @@ __global__ void __launch_bounds__(256) adaround_init_alpha_kernel(
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    float one_minus_b1, float b2, float one_minus_b2,
-                                                   float step_size, float bc2_sqrt, float eps) {
+                                                   float step_size, float bc2_sqrt, float eps,
+                                                   const float* __restrict__ hyper) {
+  if (hyper != nullptr) {
+    step_size = hyper[2];
+    bc2_sqrt = hyper[3];
+  }
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
     const float gv = g[e];
@@ -231,7 +241,7 @@ extern "C" int nq_fakequant_bwd(const float* g, const float* x, const float* alp
     if (!alpha || !d_alpha) return NQ_ERR_BAD_ARG;
     const int64_t numel = rows * row_len;
     fakequant_bwd_soft_kernel<<<grid_for(numel), 256, 0, s>>>(g, x, alpha, delta, zero_point, numel, (int)row_len,
-                                                             d_stride, qmax, grad_scale, reg_w, reg_b, d_alpha);
+                                                             d_stride, qmax, grad_scale, reg_w, reg_b, d_alpha, nullptr);
   } else if (mode == NQ_ROUND_NEAREST) {
     if (!d_delta) return NQ_ERR_BAD_ARG;
     if (d_stride == 1)
@@ -265,7 +275,37 @@ extern "C" int nq_adam_step(float* param, const float* grad, float* exp_avg, flo
   const float bc2_sqrt = (float)sqrt(bc2);
   adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1),
                                                           (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt,
-                                                          (float)eps);
+                                                          (float)eps, nullptr);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+// Variants for CUDA-graph capture of the calibration iteration: the per-iteration scalars (regulariser weight and
+// temperature, Adam's bias-corrected step size and sqrt(1 - beta2^t)) are read from hyper_dev[0..3] at run time.
+extern "C" int nq_fakequant_bwd_soft_dev(const float* g, const float* x, const float* alpha, const float* delta,
+                                         const float* zero_point, int64_t rows, int64_t row_len, int d_stride,
+                                         int n_bits, float grad_scale, int use_reg, const float* hyper_dev,
+                                         float* d_alpha, void* stream) {
+  if (!g || !x || !alpha || !delta || !zero_point || !d_alpha || !hyper_dev || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
+  if (n_bits < 2 || n_bits > 8 || (d_stride != 0 && d_stride != 1)) return NQ_ERR_BAD_ARG;
+  if (row_len > 0x7fffffffLL) return NQ_ERR_BAD_SHAPE;
+  const int64_t numel = rows * row_len;
+  const float qmax = (float)((1 << n_bits) - 1);
+  if (use_reg)
+    fakequant_bwd_soft_kernel<<<grid_for(numel), 256, 0, as_stream(stream)>>>(g, x, alpha, delta, zero_point, numel, (int)row_len,
+                                                                             d_stride, qmax, grad_scale, 0.f, 0.f, d_alpha, hyper_dev);
+  else
+    fakequant_bwd_soft_kernel<<<grid_for(numel), 256, 0, as_stream(stream)>>>(g, x, alpha, delta, zero_point, numel, (int)row_len,
+                                                                             d_stride, qmax, grad_scale, 0.f, 0.f, d_alpha, nullptr);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                double beta1, double beta2, double eps, const float* hyper_dev, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper_dev || n <= 0) return NQ_ERR_BAD_ARG;
+  adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1),
+                                                          (float)beta2, (float)(1.0 - beta2), 0.f, 1.f, (float)eps, hyper_dev);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

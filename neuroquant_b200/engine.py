@@ -605,10 +605,11 @@ class DecoderEngine:
             self.launches += 1
         return flat
 
-    def param_grads(self, grad_scale: float = 1.0, reg_w: float = 0.0, reg_b: float = 0.0):
+    def param_grads(self, grad_scale: float = 1.0, reg_w: float = 0.0, reg_b: float = 0.0, hyper: Optional[torch.Tensor] = None):
         """Chain the (possibly all-reduced) weight gradients through the rotation and the quantiser
         Jacobian.  Returns per stage (g_w, g_b): d_alpha (mode 'ada', soft) or d_delta (mode 'uaq').
-        reg_w / reg_b add the rounding regulariser's gradient on the WEIGHT alphas only."""
+        reg_w / reg_b add the rounding regulariser's gradient on the WEIGHT alphas only; with `hyper` (device
+        array {reg_w, reg_b, ...}) they are read on the device instead (CUDA-graph replay)."""
         flat, views = self._grad_buffers()
         out = []
         if not hasattr(self, "_pg"):
@@ -623,8 +624,16 @@ class DecoderEngine:
                 if key not in self._pg:
                     self._pg[key] = (torch.empty_like(s.alpha_w), torch.empty_like(s.alpha_b))
                 da_w, da_b = self._pg[key]
-                L.fakequant_bwd(gw, s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, ROUND_SOFT, grad_scale, reg_w, reg_b, out=da_w)
-                L.fakequant_bwd(gb, s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, ROUND_SOFT, grad_scale, 0.0, 0.0, out=da_b)
+                if hyper is None:
+                    L.fakequant_bwd(gw, s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, ROUND_SOFT, grad_scale, reg_w, reg_b, out=da_w)
+                    L.fakequant_bwd(gb, s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, ROUND_SOFT, grad_scale, 0.0, 0.0, out=da_b)
+                else:
+                    for g_, x_, a_, d_, z_, o_, use_reg in ((gw, s.w_src, s.alpha_w, s.delta_w, s.zp_w, da_w, 1),
+                                                            (gb, s.bias, s.alpha_b, s.delta_b, s.zp_b, da_b, 0)):
+                        rows, row_len, ds = (d_.numel(), x_.numel() // d_.numel(), 1) if d_.numel() > 1 else (1, x_.numel(), 0)
+                        L.check(L.lib.nq_fakequant_bwd_soft_dev(L.ptr(g_), L.ptr(x_), L.ptr(a_), L.ptr(d_), L.ptr(z_), rows, row_len,
+                                                                ds, s.n_bits, float(grad_scale), use_reg, L.ptr(hyper), L.ptr(o_),
+                                                                L.stream()), "nq_fakequant_bwd_soft_dev")
                 out.append((da_w, da_b))
             elif self.mode == "uaq":
                 key = ("d", i)
@@ -654,4 +663,16 @@ class AdamState:
         self.t += 1
         for p, g, m, v in zip(self.params, grads, self.m, self.v):
             L.adam_step(p, g, m, v, self.lr, self.t)
+        return len(self.params)
+
+    def hyper_of_next_step(self, beta1=0.9, beta2=0.999):
+        """(lr / (1 - beta1^t), sqrt(1 - beta2^t)) of the step about to be taken; advances t."""
+        self.t += 1
+        return self.lr / (1.0 - beta1 ** self.t), (1.0 - beta2 ** self.t) ** 0.5
+
+    def step_dev(self, grads: Sequence[torch.Tensor], hyper: torch.Tensor, beta1=0.9, beta2=0.999, eps=1e-8) -> int:
+        """Adam step whose step size / bias correction come from the device array `hyper` (entries 2, 3)."""
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            L.check(L.lib.nq_adam_step_dev(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), beta1, beta2, eps, L.ptr(hyper),
+                                           L.stream()), "nq_adam_step_dev")
         return len(self.params)

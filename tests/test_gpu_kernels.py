@@ -319,3 +319,28 @@ def test_calibration_golden(nq, tag, conv_path):
     assert a_far / a_tot < 0.5, (a_far, a_tot, n_diff, n_tot)
     assert d_far / d_tot < 0.08, (d_far, d_tot)
     assert n_diff / n_tot < 1e-2, (n_diff, n_tot)
+
+
+def test_graph_replay_equals_eager(nq, monkeypatch):
+    """The CUDA-graph replay of the AdaRound iteration (calibration.GraphedStep) is the same kernel sequence as the
+    eager one: identical alpha after 30 iterations, bit for bit."""
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NQ_GRAPH", flag)
+        g, arch, cfg, stages, eng = make_engine(nq, "tiny_hnerv", "uaq")
+        eng.init_scales()
+        cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
+        order = g["order"].tolist()
+
+        def fetch(idx):
+            idx = torch.as_tensor(idx, device="cuda")
+            return cali[idx], frames[idx]
+
+        loop = nq.CalibrationLoop(eng, fetch, len(order), iters=40, weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003)
+        assert loop.use_graph == (flag == "1")
+        loop.run(lambda: order)
+        res[flag] = [s.alpha_w.clone() for s in eng.stages] + [s.alpha_b.clone() for s in eng.stages]
+        if flag == "1":
+            assert loop._graphed, "graph path was not taken"
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
