@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=8, help="synthetic frames resident per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-steps", type=int, default=10)
+    ap.add_argument("--mode", default="calib", choices=["calib", "decode"],
+                    help="decode: quantised-decode throughput only (any workload, e.g. hnerv-1080p-12m)")
     return ap.parse_args()
 
 
@@ -190,6 +192,8 @@ def run_b200(args):
     eng.init_scales()
     eng.start_adaround()
     c, h0, w0 = embed_shape(cfg, arch)
+    if args.mode == "decode":
+        return run_decode_only(args, eng, cfg, arch, geoms, world, rank, local)
     H, W = cfg["crop_h"], cfg["crop_w"]
     gen = torch.Generator().manual_seed(903 + rank)
     F = max(args.frames, args.batch)
@@ -345,6 +349,50 @@ def run_b200(args):
                                "sample": f"{n_s} AdaRound iterations (batch {B}) after 1 warm-up, same workload; "
                                          f"decode {B / td:.2f} frames/s on one batch-{B} decode"}
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_decode_only(args, eng, cfg, arch, geoms, world, rank, local):
+    """Quantised decode (hard AdaRound rounding, weights packed once -- SURVEY Q9) of synthetic embeddings; frames are
+    sharded across ranks with no collective on the data path."""
+    import torch.distributed as dist
+    from neuroquant_b200.workloads import conv_flops, embed_shape
+
+    c, h0, w0 = embed_shape(cfg, arch)
+    B = args.batch
+    gen = torch.Generator().manual_seed(903 + rank)
+    embeds = torch.randn(max(args.frames, B), c, h0, w0, generator=gen).cuda()
+    eng.soft_w = False
+    eng.invalidate()
+    eng.forward(embeds[:B])
+    for _ in range(max(args.warmup, 3)):
+        eng.forward(embeds[:B], reuse_weights=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    e0.record()
+    for i in range(args.steps):
+        o = (i * B) % (embeds.shape[0] - B + 1)
+        eng.forward(embeds[o:o + B], reuse_weights=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms = float(ms)
+    if rank == 0:
+        fps = args.steps * B * world / (ms * 1e-3)
+        gf = conv_flops(geoms, h0, w0, 1) / 1e9
+        print(json.dumps({"metric": "quantized_decode_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": eng.dtype_name,
+                          "data": "synthetic", "config": {"workload": args.workload + " quantised decode", "batch": B},
+                          "gpu_launches": eng.launches - l0, "gflop_per_frame": gf,
+                          "tflops_effective": fps * gf / 1e3}))
     if world > 1:
         dist.destroy_process_group()
 
