@@ -236,6 +236,13 @@ int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, int d_stride,
 int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* plan, const void* x_split, const void* wpk,
                    const float* scale_packed, const float* bias_packed, float* z, void* y_split, void* stream);
 
+/* Head on the tensor cores: nq_head_fwd_loss_split's contract (3x3 conv to 3 channels + OutImg + loss sum + dL/dz)
+ * with the convolution as an N = 16 (3 real columns) tcgen05 GEMM; wpk / scale / bias packed as for any stage
+ * with a dir = 0 plan of the head's descriptor. */
+int nq_tc_head_fwd_loss(const nq_conv_desc* d, const nq_tc_plan* plan, const void* x_split, const void* wpk,
+                        const float* scale_packed, const float* bias_packed, int out_bias, const float* target,
+                        float p, float mean_pixels, float* img, float* loss_sum, void* dz_head_split, void* stream);
+
 /* dz_prev = unshuffle(conv_transpose(dz) * act'(z_prev)).  dz_split (n, h, w, nout_p rounded up to 8) and
  * dz_prev_split (n, h/prev_rh, w/prev_rw, prev_rh*prev_rw*cin_p) are split-bf16, z_prev fp32; wpk_t is
  * packed with a dir = 1 plan from the DE-QUANTISED weights. */

@@ -85,6 +85,7 @@ def _load():
         "nq_tc_pack_epilogue": (I, [DP, P, I, P, P, P, P]),
         "nq_tc_conv_fwd": (I, [DP, TP, P, P, P, P, P, P, P]),
         "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P]),
+        "nq_tc_head_fwd_loss": (I, [DP, TP, P, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_tc_plan_wgrad": (I, [DP, I, I, C.POINTER(TcWgradPlan)]),
         "nq_tc_conv_wgrad": (I, [DP, C.POINTER(TcWgradPlan), P, P, P, P, L, P]),
         "nq_jet_act": (I, [P, P, P, P, P, L, I, P, P, P, I, P]),

@@ -56,7 +56,10 @@ struct TcParams {
   int N, NT;             // GEMM N (multiple of 16) and its tile
   int KC, SBC;           // channels per A unit / per B stage (multiples of 16, SBC | KC, SBC | C)
   int a_planes, b_planes;
-  int epi;               // 0 forward, 1 dgrad
+  int epi;               // 0 forward, 1 dgrad, 2 head (forward + OutImg + loss + dL/dz)
+  // head epilogue (epi == 2)
+  const float* head_target; float* head_img; float* head_loss; uint8_t* head_dz;
+  float head_p, head_inv_mean; int head_out_bias;
   int rh, rw, cg, act;   // fwd: up-shuffle of this stage's output; dgrad: previous stage's (un-shuffle)
   int tiles_x, tiles_y, tiles_n, total_tiles;
   int PW, PH, CGS;       // halo width/height (pixels), channel-group stride (bytes)
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int qd = lane & 3;         // 4-channel quad of the chunk this lane stores
     const int rsub = lane >> 2;      // row (pixel) within each group of 8 rows
     uint32_t tcnt = 0;
+    float head_loss_acc = 0.f;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters, ++tcnt) {
       const TileCoord tc = tile_coord(p, t, rank);
       const uint32_t acc = tcnt & 1;
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const bool col_ok = n < p.n_store;
         float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = make_float4(0.f, 0.f, 0.f, 0.f);
         size_t col_off = (size_t)n;  // dgrad: plain column; fwd: (group, channel) of the shuffle
-        if (p.epi == 0 && col_ok) {
+        if (p.epi != 1 && col_ok) {
           if (p.scale) g0 = __ldg(reinterpret_cast<const float4*>(p.scale + n));
           if (p.bias) g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
           const int grp = n / p.cg, c = n - grp * p.cg;
@@ -541,12 +545,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
               store_split4(p.out_y, p.out_plane_bytes, o, r);
             }
-          } else {
+          } else if (p.epi == 1) {
             if (p.zprev && p.act == 1) {
               r.x *= gelu_grad_fast(zv[it].x); r.y *= gelu_grad_fast(zv[it].y);
               r.z *= gelu_grad_fast(zv[it].z); r.w *= gelu_grad_fast(zv[it].w);
             }
             store_split4(p.out_y, p.out_plane_bytes, row_base[it] + n, r);
+          } else if (qd == 0) {
+            // head: OutImg (models/_layers.py:10-16) + lp_loss partial sum (quantizer.py:66-73) + dL/dz, 3 channels
+            const float vals[3] = {fmaf(r.x, g0.x, g1.x), fmaf(r.y, g0.y, g1.y), fmaf(r.z, g0.z, g1.z)};
+            const int y = tc.y0 + q * 4 + it, x = tc.x0 + rsub;
+            const size_t plane = (size_t)p.h * p.w;
+            const size_t o = (size_t)tc.img * 3 * plane + (size_t)y * p.w + x;
+            float gr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float outv, dout;
+              if (p.head_out_bias == 0) {
+                const float th = tanhf(vals[c]);
+                outv = th * 0.5f + 0.5f;
+                dout = 0.5f * (1.0f - th * th);
+              } else {
+                outv = sigmoid_f(vals[c]);
+                dout = outv * (1.0f - outv);
+              }
+              if (p.head_img) p.head_img[o + c * plane] = outv;
+              if (p.head_target) {
+                const float dlt = outv - __ldg(p.head_target + o + c * plane);
+                const float a = fabsf(dlt);
+                if (p.head_p == 2.0f) {
+                  head_loss_acc += dlt * dlt;
+                  gr[c] = 2.0f * dlt * p.head_inv_mean * dout;
+                } else {
+                  head_loss_acc += powf(a, p.head_p);
+                  const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+                  gr[c] = p.head_p * powf(a, p.head_p - 1.0f) * sgn * p.head_inv_mean * dout;
+                }
+              }
+            }
+            if (p.head_dz) {  // (n, h, w, 8) split-bf16 planes: 3 real channels + zeros
+              uint32_t hb[3], lb[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const __nv_bfloat16 hv = __float2bfloat16_rn(gr[c]);
+                hb[c] = __bfloat16_as_ushort(hv);
+                lb[c] = __bfloat16_as_ushort(__float2bfloat16_rn(gr[c] - __bfloat162float(hv)));
+              }
+              const size_t px = (((size_t)tc.img * p.h + y) * p.w + x) * 16;  // 8 channels * 2 bytes
+              *reinterpret_cast<uint4*>(p.head_dz + px) = make_uint4(hb[0] | (hb[1] << 16), hb[2], 0u, 0u);
+              *reinterpret_cast<uint4*>(p.head_dz + p.out_plane_bytes + px) = make_uint4(lb[0] | (lb[1] << 16), lb[2], 0u, 0u);
+            }
           }
         }
         __syncwarp();
@@ -554,6 +602,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
+    }
+    if (p.epi == 2 && p.head_loss != nullptr) {
+      head_loss_acc = warp_sum(head_loss_acc);
+      if (lane == 0 && head_loss_acc != 0.f) atomicAdd(p.head_loss, head_loss_acc);
     }
   }
 
@@ -827,6 +879,31 @@ extern "C" int nq_tc_conv_fwd(const nq_conv_desc* d, const nq_tc_plan* pl, const
   p.out_plane_bytes = (size_t)d->n * d->h * d->rh * d->w * d->rw * d->cg * 2;
   p.n_store = d->rh * d->rw * d->cg;
   p.rh = d->rh; p.rw = d->rw; p.cg = d->cg; p.act = d->act;
+  return launch_tc(d, pl, p, as_stream(stream));
+}
+
+extern "C" int nq_tc_head_fwd_loss(const nq_conv_desc* d, const nq_tc_plan* pl, const void* x_split, const void* wpk,
+                                   const float* scale_packed, const float* bias_packed, int out_bias,
+                                   const float* target, float p_norm, float mean_pixels, float* img, float* loss_sum,
+                                   void* dz_head_split, void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (!pl || pl->dir != 0 || !x_split || !wpk || !bias_packed) return NQ_ERR_BAD_ARG;
+  if (d->ksize != 3 || d->rh != 1 || d->rw != 1 || d->cout != 3 || d->cg != 4) return NQ_ERR_BAD_SHAPE;
+  if (out_bias != 0 && out_bias != 1) return NQ_ERR_UNSUPPORTED;
+  if (target && (!(p_norm > 0.f) || !(mean_pixels > 0.f))) return NQ_ERR_BAD_ARG;
+  if (!target && !img) return NQ_ERR_BAD_ARG;
+  TcParams p{};
+  p.in = reinterpret_cast<const uint8_t*>(x_split);
+  p.in_plane_bytes = (size_t)d->n * d->h * d->w * d->cin_p * 2;
+  p.in_stride = d->cin_p; p.c_valid = d->cin_p;
+  p.wpk = reinterpret_cast<const uint8_t*>(wpk); p.scale = scale_packed; p.bias = bias_packed;
+  p.epi = 2; p.n_store = 4;
+  p.rh = 1; p.rw = 1; p.cg = 4; p.act = 0;
+  p.head_target = target; p.head_img = img; p.head_loss = target ? loss_sum : nullptr;
+  p.head_dz = target ? reinterpret_cast<uint8_t*>(dz_head_split) : nullptr;
+  p.out_plane_bytes = (size_t)d->n * d->h * d->w * 8 * 2;  // plane stride of dz_head_split
+  p.head_p = p_norm; p.head_inv_mean = target ? 1.0f / mean_pixels : 0.f; p.head_out_bias = out_bias;
   return launch_tc(d, pl, p, as_stream(stream));
 }
 

@@ -207,7 +207,7 @@ class _Plan:
         self.tc_fwd = {}
         self.tc_dgrad = []
         if eng.use_tc:
-            for i in range(last):
+            for i in range(last + 1):  # the head too: N = 3 real columns padded to 16
                 for bpl in (1, 2):
                     pl = L.TcPlan()
                     L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[i]), 0, eng.fwd_a_planes, bpl, C.byref(pl)), "nq_tc_plan_conv")
@@ -219,13 +219,7 @@ class _Plan:
                             "nq_tc_plan_conv")
                     pl.cluster = eng.cluster
                 self.tc_dgrad.append(pl)
-            self.tc_head_dgrad = None
-            if train and last > 0:
-                pl = L.TcPlan()
-                L.check(L.lib.nq_tc_plan_conv(C.byref(self.desc[last]), 1, eng.bwd_a_planes, eng.bwd_b_planes, C.byref(pl)),
-                        "nq_tc_plan_conv")
-                pl.cluster = eng.cluster
-                self.tc_head_dgrad = pl
+            self.tc_head_dgrad = self.tc_dgrad[last] if train and last > 0 else None
 
 
 class DecoderEngine:
@@ -347,7 +341,7 @@ class DecoderEngine:
         self._tcw = []  # per non-head stage: (wpk_fwd bytes, wpk_dgrad bytes, scale_packed)
         last = len(self.stages) - 1
         for i, (s, d) in enumerate(zip(self.stages, p.desc)):
-            tc = self.use_tc and i < last
+            tc = self.use_tc
             wk = None if tc else torch.zeros(d.kdim, d.nout_p, device=self.device)
             wt = None if tc else torch.zeros(d.ksize * d.ksize * d.nout_p, d.cin_p, device=self.device)
             bp = torch.zeros(d.nout_p, device=self.device)
@@ -367,11 +361,7 @@ class DecoderEngine:
                                   torch.ones(d.nout_p, device=self.device)))
             else:
                 self._tcw.append(None)
-        self._head_dgrad = None
-        if self.use_tc and last > 0:
-            pl = L.TcPlan()
-            L.check(L.lib.nq_tc_plan_conv(C.byref(p.desc[last]), 1, 2, 2, C.byref(pl)), "nq_tc_plan_conv")
-            self._head_dgrad = torch.zeros(pl.wpk_bytes, dtype=torch.uint8, device=self.device)
+        self._head_dgrad = self._tcw[last][1] if (self.use_tc and last > 0) else None
 
     # ------------------------------------------------------------------ weights
     def prepare_weights(self, p: _Plan, need_wt: bool, reg_b: Optional[float] = None):
@@ -401,14 +391,9 @@ class DecoderEngine:
                     self.launches += 1
                 w_for_conv, b_for_conv, cin_src = deq_w, deq_b, s.cin_src
             if self._tcw[i] is None:
-                head_tc = need_wt and self._head_dgrad is not None and i == len(self.stages) - 1 and p.tc_head_dgrad is not None
                 L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(w_for_conv), cin_src, L.ptr(b_for_conv), L.ptr(wk),
-                                             L.ptr(wt) if (need_wt and not head_tc) else None, L.ptr(bp), st), "nq_pack_weight")
+                                             L.ptr(wt) if need_wt else None, L.ptr(bp), st), "nq_pack_weight")
                 self.launches += 1
-                if head_tc:
-                    L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_head_dgrad), L.ptr(w_for_conv), cin_src, None, 0,
-                                                    self._head_dgrad.data_ptr(), st), "nq_tc_pack_weight")
-                    self.launches += 1
                 continue
             wpk_f, wpk_d, scale_p = self._tcw[i]
             # forward operand: integer weights (codes - zero_point), exact in ONE bf16 plane, whenever the
@@ -489,11 +474,13 @@ class DecoderEngine:
             mp = 1.0
         want_dz = train and target is not None
         if self.use_tc:
-            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss_split, C.byref(p.desc[last]),
-                              p.x[last].data_ptr(), L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target),
-                              float(p_norm), mp, L.ptr(p.img) if (want_img or target is None) else None,
+            wpk_f, _, scale_p = self._tcw[last]
+            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_tc_head_fwd_loss, C.byref(p.desc[last]),
+                              C.byref(p.tc_fwd[(last, self._fwd_bpl[last])]), p.x[last].data_ptr(), wpk_f.data_ptr(),
+                              L.ptr(scale_p), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target), float(p_norm), mp,
+                              L.ptr(p.img) if (want_img or target is None) else None,
                               L.ptr(p.loss) if target is not None else None,
-                              p.dz[last].data_ptr() if want_dz else None, st), "nq_head_fwd_loss_split")
+                              p.dz[last].data_ptr() if want_dz else None, st), "nq_tc_head_fwd_loss")
         else:
             L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss, C.byref(p.desc[last]), L.ptr(p.x[last]),
                               L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target), float(p_norm), mp,
