@@ -497,6 +497,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           zrow[it] = (((size_t)tc.img * p.h + y) * p.w + x) * p.n_store;
         }
       }
+      if (p.epi == 2) {
+        // head: every lane keeps its own accumulator row = one pixel, 3 real columns: OutImg (models/_layers.py:10-16)
+        // + lp_loss partial sum (quantizer.py:66-73) + dL/dz.  The target is requested before the accumulator wait.
+        const int m = q * 32 + lane;
+        const int y = tc.y0 + (m >> 3), x = tc.x0 + (m & 7);
+        const bool ok = tc.real && y < p.h && x < p.w && half == 0;
+        const size_t plane = (size_t)p.h * p.w;
+        const size_t o = (size_t)tc.img * 3 * plane + (size_t)y * p.w + x;
+        float tg[3] = {0.f, 0.f, 0.f};
+        if (ok && p.head_target) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tg[c] = __ldg(p.head_target + o + c * plane);
+        }
+        mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
+        tc_fence_after();
+        if (half == 0) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (ok) {
+            float gr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float val = __uint_as_float(v[c]);
+              if (p.scale) val *= __ldg(p.scale + c);
+              val += __ldg(p.bias + c);
+              float outv, dout;
+              if (p.head_out_bias == 0) {
+                const float th = tanhf(val);
+                outv = th * 0.5f + 0.5f;
+                dout = 0.5f * (1.0f - th * th);
+              } else {
+                outv = sigmoid_f(val);
+                dout = outv * (1.0f - outv);
+              }
+              if (p.head_img) p.head_img[o + c * plane] = outv;
+              if (p.head_target) {
+                const float dlt = outv - tg[c];
+                const float a = fabsf(dlt);
+                if (p.head_p == 2.0f) {
+                  head_loss_acc += dlt * dlt;
+                  gr[c] = 2.0f * dlt * p.head_inv_mean * dout;
+                } else {
+                  head_loss_acc += powf(a, p.head_p);
+                  const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+                  gr[c] = p.head_p * powf(a, p.head_p - 1.0f) * sgn * p.head_inv_mean * dout;
+                }
+              }
+            }
+            if (p.head_dz) {  // (n, h, w, 8) split-bf16 planes: 3 real channels + zeros
+              uint32_t hb[3], lb[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const __nv_bfloat16 hv = __float2bfloat16_rn(gr[c]);
+                hb[c] = __bfloat16_as_ushort(hv);
+                lb[c] = __bfloat16_as_ushort(__float2bfloat16_rn(gr[c] - __bfloat162float(hv)));
+              }
+              const size_t px = (((size_t)tc.img * p.h + y) * p.w + x) * 16;  // 8 channels * 2 bytes
+              *reinterpret_cast<uint4*>(p.head_dz + px) = make_uint4(hb[0] | (hb[1] << 16), hb[2], 0u, 0u);
+              *reinterpret_cast<uint4*>(p.head_dz + p.out_plane_bytes + px) = make_uint4(lb[0] | (lb[1] << 16), lb[2], 0u, 0u);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
+        continue;
+      }
       mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
@@ -551,50 +619,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               r.z *= gelu_grad_fast(zv[it].z); r.w *= gelu_grad_fast(zv[it].w);
             }
             store_split4(p.out_y, p.out_plane_bytes, row_base[it] + n, r);
-          } else if (qd == 0) {
-            // head: OutImg (models/_layers.py:10-16) + lp_loss partial sum (quantizer.py:66-73) + dL/dz, 3 channels
-            const float vals[3] = {fmaf(r.x, g0.x, g1.x), fmaf(r.y, g0.y, g1.y), fmaf(r.z, g0.z, g1.z)};
-            const int y = tc.y0 + q * 4 + it, x = tc.x0 + rsub;
-            const size_t plane = (size_t)p.h * p.w;
-            const size_t o = (size_t)tc.img * 3 * plane + (size_t)y * p.w + x;
-            float gr[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float outv, dout;
-              if (p.head_out_bias == 0) {
-                const float th = tanhf(vals[c]);
-                outv = th * 0.5f + 0.5f;
-                dout = 0.5f * (1.0f - th * th);
-              } else {
-                outv = sigmoid_f(vals[c]);
-                dout = outv * (1.0f - outv);
-              }
-              if (p.head_img) p.head_img[o + c * plane] = outv;
-              if (p.head_target) {
-                const float dlt = outv - __ldg(p.head_target + o + c * plane);
-                const float a = fabsf(dlt);
-                if (p.head_p == 2.0f) {
-                  head_loss_acc += dlt * dlt;
-                  gr[c] = 2.0f * dlt * p.head_inv_mean * dout;
-                } else {
-                  head_loss_acc += powf(a, p.head_p);
-                  const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
-                  gr[c] = p.head_p * powf(a, p.head_p - 1.0f) * sgn * p.head_inv_mean * dout;
-                }
-              }
-            }
-            if (p.head_dz) {  // (n, h, w, 8) split-bf16 planes: 3 real channels + zeros
-              uint32_t hb[3], lb[3];
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const __nv_bfloat16 hv = __float2bfloat16_rn(gr[c]);
-                hb[c] = __bfloat16_as_ushort(hv);
-                lb[c] = __bfloat16_as_ushort(__float2bfloat16_rn(gr[c] - __bfloat162float(hv)));
-              }
-              const size_t px = (((size_t)tc.img * p.h + y) * p.w + x) * 16;  // 8 channels * 2 bytes
-              *reinterpret_cast<uint4*>(p.head_dz + px) = make_uint4(hb[0] | (hb[1] << 16), hb[2], 0u, 0u);
-              *reinterpret_cast<uint4*>(p.head_dz + p.out_plane_bytes + px) = make_uint4(lb[0] | (lb[1] << 16), lb[2], 0u, 0u);
-            }
           }
         }
         __syncwarp();
