@@ -251,6 +251,9 @@ class DecoderEngine:
         # weight-gradient operand planes (input activations, output gradients): default = the backward setting
         self.wg_a_planes = int(os.environ.get("NQ_WG_A_PLANES", str(self.bwd_a_planes)))
         self.wg_b_planes = int(os.environ.get("NQ_WG_B_PLANES", str(self.bwd_b_planes)))
+        # head forward: the HBM-bound FFMA kernel (default, measured faster: 0.27 vs 0.36 ms at 2 x 640 x 1280) or
+        # the tensor-core kernel with the OutImg/loss epilogue (NQ_HEAD=tc)
+        self.head_tc = os.environ.get("NQ_HEAD", "simt").lower() == "tc"
         self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
@@ -342,7 +345,8 @@ class DecoderEngine:
         last = len(self.stages) - 1
         for i, (s, d) in enumerate(zip(self.stages, p.desc)):
             tc = self.use_tc
-            wk = None if tc else torch.zeros(d.kdim, d.nout_p, device=self.device)
+            head_simt_fwd = tc and i == last and not self.head_tc
+            wk = None if (tc and not head_simt_fwd) else torch.zeros(d.kdim, d.nout_p, device=self.device)
             wt = None if tc else torch.zeros(d.ksize * d.ksize * d.nout_p, d.cin_p, device=self.device)
             bp = torch.zeros(d.nout_p, device=self.device)
             deq_w = torch.empty_like(s.w_src)
@@ -396,6 +400,16 @@ class DecoderEngine:
                 self.launches += 1
                 continue
             wpk_f, wpk_d, scale_p = self._tcw[i]
+            if i == len(self.stages) - 1 and not self.head_tc:
+                # head forward on the FFMA kernel: fp32 packed weights; its data gradient still runs on the tensor cores
+                L.check(L.lib.nq_pack_weight(C.byref(d), L.ptr(w_for_conv), cin_src, L.ptr(b_for_conv), L.ptr(wk), None, L.ptr(bp), st),
+                        "nq_pack_weight")
+                self.launches += 1
+                if need_wt and i > 0:
+                    L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_dgrad[i]), L.ptr(w_for_conv), cin_src, None, 0,
+                                                    wpk_d.data_ptr(), st), "nq_tc_pack_weight")
+                    self.launches += 1
+                continue
             # forward operand: integer weights (codes - zero_point), exact in ONE bf16 plane, whenever the
             # codes are integers and are what the conv multiplies (no rotation in between); the step size
             # is applied per output channel in the epilogue.  Otherwise the de-quantised fp32 weights,
@@ -473,7 +487,13 @@ class DecoderEngine:
         else:
             mp = 1.0
         want_dz = train and target is not None
-        if self.use_tc:
+        if self.use_tc and not self.head_tc:
+            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss_split, C.byref(p.desc[last]),
+                              p.x[last].data_ptr(), L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target),
+                              float(p_norm), mp, L.ptr(p.img) if (want_img or target is None) else None,
+                              L.ptr(p.loss) if target is not None else None,
+                              p.dz[last].data_ptr() if want_dz else None, st), "nq_head_fwd_loss_split")
+        elif self.use_tc:
             wpk_f, _, scale_p = self._tcw[last]
             L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_tc_head_fwd_loss, C.byref(p.desc[last]),
                               C.byref(p.tc_fwd[(last, self._fwd_bpl[last])]), p.x[last].data_ptr(), wpk_f.data_ptr(),

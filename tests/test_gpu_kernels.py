@@ -344,3 +344,25 @@ def test_graph_replay_equals_eager(nq, monkeypatch):
             assert loop._graphed, "graph path was not taken"
     for a, b in zip(res["1"], res["0"]):
         assert torch.equal(a, b)
+
+
+def test_tensor_core_head_variant(nq, monkeypatch):
+    """NQ_HEAD=tc: the head's forward + OutImg + loss + dL/dz as a tcgen05 GEMM epilogue gives the same frames,
+    loss and gradients as the default HBM-bound FFMA head."""
+    outs = {}
+    for mode in ("simt", "tc"):
+        monkeypatch.setenv("NQ_HEAD", mode)
+        g, arch, cfg, stages, eng = make_engine(nq, "tiny_hnerv", "uaq")
+        assert eng.head_tc == (mode == "tc")
+        eng.init_scales()
+        eng.start_adaround()
+        cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
+        img = eng.forward(cali[:2], train=True, target=frames[:2]).clone()
+        loss = float(eng.last_loss())
+        eng.backward()
+        grads = [x.clone() for pair in eng.param_grads() for x in pair]
+        outs[mode] = (img, loss, grads)
+    assert (outs["tc"][0] - outs["simt"][0]).abs().max() < 2e-6
+    assert outs["tc"][1] == pytest.approx(outs["simt"][1], rel=1e-5)
+    for a, b in zip(outs["tc"][2], outs["simt"][2]):
+        assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-10
