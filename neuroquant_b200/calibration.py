@@ -42,11 +42,13 @@ class GraphedStep:
     """One calibration iteration (forward, loss, backward, quantiser Jacobian, Adam) captured ONCE as a CUDA graph
     and replayed: ~100 kernel launches become one graph launch.  Inputs are copied into static buffers; the four
     scalars that change per iteration go through a 16-byte device array (nq_*_dev kernels).  Single-GPU AdaRound
-    phase only; the eager path stays for iterations that log and for data-parallel runs."""
+    phase; the eager path stays for iterations that log.  Under data parallelism the all-reduce of the flat
+    gradient buffer is part of the captured graph (NQ_GRAPH_DP=0 keeps those runs eager)."""
 
     def __init__(self, eng: DecoderEngine, opt: AdamState, embed: torch.Tensor, frames: torch.Tensor, p_norm: float,
-                 mean_pixels: float):
+                 mean_pixels: float, group=None, world: int = 1):
         self.eng, self.opt, self.p_norm, self.mean_pixels = eng, opt, p_norm, mean_pixels
+        self.group, self.world = group, world
         self.embed = torch.empty_like(embed)
         self.frames = torch.empty_like(frames)
         self.hyper = torch.zeros(4, device=embed.device)
@@ -57,7 +59,9 @@ class GraphedStep:
     def _body(self):
         eng = self.eng
         eng.forward(self.embed, train=True, target=self.frames, p_norm=self.p_norm, mean_pixels=self.mean_pixels, want_img=False)
-        eng.backward()
+        flat = eng.backward()
+        if self.world > 1:  # the NCCL all-reduce is captured into the graph with the kernels around it
+            torch.distributed.all_reduce(flat, group=self.group)
         grads = eng.param_grads(1.0, hyper=self.hyper)
         self.opt.step_dev([g for pair in grads for g in pair], self.hyper)
         eng.launches += len(self.opt.params)
@@ -102,7 +106,7 @@ class CalibrationLoop:
             self.world = torch.distributed.get_world_size(group)
         self.global_batch = global_batch
         self.log = log
-        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and self.world == 1
+        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (self.world == 1 or os.environ.get("NQ_GRAPH_DP", "1") != "0")
         self._graphed = {}
         self.ep1 = int(0.05 * iters / n_batches)  # calib_model.py:144
         self.ep2 = int(iters / n_batches) - self.ep1  # calib_model.py:205
@@ -118,7 +122,7 @@ class CalibrationLoop:
             key = (tuple(embed.shape), tuple(frames.shape), id(opt))
             gs = self._graphed.get(key)
             if gs is None:
-                gs = self._graphed[key] = GraphedStep(eng, opt, embed, frames, self.p, float(gb * H * W))
+                gs = self._graphed[key] = GraphedStep(eng, opt, embed, frames, self.p, float(gb * H * W), self.group, self.world)
             gs.run(embed, frames, reg_w, reg_b)
             return
         eng.forward(embed, train=True, target=frames, p_norm=self.p, mean_pixels=float(gb * H * W),
