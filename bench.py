@@ -53,7 +53,7 @@ def config_of(args, world):
             "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world, "hadamard": bool(args.hadamard),
             "parallelism": f"dp{world} (frame-sharded, NCCL all-reduce of dW)" if world > 1 else "single GPU",
             "l2": "no explicit flush: each step streams >2 GB of activations, far above the 126 MB L2",
-            "launch": "CUDA graph replay of the iteration (the NCCL all-reduce is captured with it when N > 1)",
+            "launch": "CUDA graph replay of the iteration on 1 GPU; eager launches around the NCCL all-reduce when N > 1",
             **{k: v for k, v in HYPER.items()}}
 
 
@@ -208,7 +208,7 @@ def run_b200(args):
     stage_ev = []
 
     from neuroquant_b200.calibration import GraphedStep
-    use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (world == 1 or os.environ.get("NQ_GRAPH_DP", "1") != "0")
+    use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0")
     graphed = {}
 
     def step(i, embed, frames, eager=False):

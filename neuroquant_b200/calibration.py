@@ -42,8 +42,8 @@ class GraphedStep:
     """One calibration iteration (forward, loss, backward, quantiser Jacobian, Adam) captured ONCE as a CUDA graph
     and replayed: ~100 kernel launches become one graph launch.  Inputs are copied into static buffers; the four
     scalars that change per iteration go through a 16-byte device array (nq_*_dev kernels).  Single-GPU AdaRound
-    phase; the eager path stays for iterations that log.  Under data parallelism the all-reduce of the flat
-    gradient buffer is part of the captured graph (NQ_GRAPH_DP=0 keeps those runs eager)."""
+    phase; the eager path stays for iterations that log and, by default, for data-parallel runs (capturing the NCCL
+    all-reduce into the graph hung on the test box: opt-in with NQ_GRAPH_DP=1)."""
 
     def __init__(self, eng: DecoderEngine, opt: AdamState, embed: torch.Tensor, frames: torch.Tensor, p_norm: float,
                  mean_pixels: float, group=None, world: int = 1):
@@ -106,7 +106,7 @@ class CalibrationLoop:
             self.world = torch.distributed.get_world_size(group)
         self.global_batch = global_batch
         self.log = log
-        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (self.world == 1 or os.environ.get("NQ_GRAPH_DP", "1") != "0")
+        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (self.world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0")
         self._graphed = {}
         self.ep1 = int(0.05 * iters / n_batches)  # calib_model.py:144
         self.ep2 = int(iters / n_batches) - self.ep1  # calib_model.py:205
