@@ -21,6 +21,7 @@
 //   * operands are bf16 hi (+ lo) planes of the fp32 tensors, accumulation fp32
 #include <cuda_bf16.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "nq_common.cuh"
@@ -41,6 +42,7 @@ struct WgParams {
   int NC, nsplits;  // output columns per CTA
   int TR;           // tile rows
   int nkh, khg, AR; // kernel rows per CTA, number of kernel-row groups, staged input rows (TR + nkh - 1)
+  int msplit, ncg_c; // channel-group slices of the input (GEMM-M split across CTAs), groups per slice
   int tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
   int a_planes, b_planes;
   int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
@@ -145,7 +147,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const int nkh = min(p.nkh, p.ks - kh0);
   b /= p.khg;
   const int nsplit = b % p.nsplits;
-  const int psplit = b / p.nsplits;
+  b /= p.nsplits;
+  const int cg0 = (b % p.msplit) * p.ncg_c;            // first input channel group of this CTA
+  const int ncg_c = min(p.ncg_c, p.ncg - cg0);         // its channel groups
+  const int Gc = p.ks * ncg_c;                         // its (kw, group) pairs
+  const int psplit = b / p.msplit;
   const int n0 = nsplit * p.NC;
   const int nc = min(p.NC, p.N - n0);
   const int t_begin = psplit * p.tiles_per_split;
@@ -166,15 +172,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   }
   // constant part of every A buffer: the "ones" group (bias gradient) and zeroed tail groups
   {
-    const int tail_groups = p.MB * 16 - p.G;  // >= 1
+    const int tail_groups = p.MB * 16 - Gc;  // >= 1
     const int per_group16 = p.AR * WG_TW;     // 16-byte units per group
     for (int bi = 0; bi < p.nbuf; ++bi)
       for (int pl = 0; pl < p.a_planes; ++pl) {
         uint8_t* base = bufs + (size_t)bi * p.buf_bytes + (size_t)pl * p.a_plane_bytes;
         for (int i = threadIdx.x; i < tail_groups * per_group16; i += WG_THREADS) {
-          const int g = p.G + i / per_group16, u = i % per_group16;
+          const int g = Gc + i / per_group16, u = i % per_group16;
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (g == p.G && pl == 0) v.x = 0x3F80u;  // bf16 1.0 in channel 0
+          if (g == Gc && pl == 0) v.x = 0x3F80u;  // bf16 1.0 in channel 0
           *reinterpret_cast<uint4*>(base + (size_t)g * p.CGS_A + (size_t)u * 16) = v;
         }
       }
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int cgp = ltid & 1;
     const int xl = (ltid >> 1) & (WG_TW - 1);
     const int lgrp = ltid >> 5, nlgrp = WG_LOADERS >> 5;  // 16 pixels x 2 parities per warp
-    const int npair = (p.ncg + 1) >> 1;
+    const int npair = (ncg_c + 1) >> 1;
     const int QA = p.AR * p.ks * npair;                   // (input row, kw, group pair) items, pair fastest
     const int slots = p.TR * WG_TW;
     const int ncg_b = nc >> 3;
@@ -256,14 +262,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
       for (int q = lgrp; q < QA; q += nlgrp) {
         const int cg = 2 * cpi + cgp;
-        if (cg < p.ncg) {
+        if (cg < ncg_c) {
           if (na < MAXI) {
             const int dy = ar + kh0 - p.pad, dx = xl + kw - p.pad;
 #pragma unroll
             for (int k = 0; k < MAXI; ++k)
               if (k == na) {
-                a_so[k] = (dy * p.w + dx) * p.C + cg * 8;
-                a_do[k] = (kw * p.ncg + cg) * p.CGS_A + ar * (WG_TW * 16) + xl * 16;
+                a_so[k] = (dy * p.w + dx) * p.C + (cg0 + cg) * 8;
+                a_do[k] = (kw * ncg_c + cg) * p.CGS_A + ar * (WG_TW * 16) + xl * 16;
                 a_dyx[k] = (dy << 16) | (dx & 0xffff);
               }
             ++na;
@@ -309,11 +315,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
         for (int q = lgrp; q < QA; q += nlgrp) {
           const int cg = 2 * cpi + cgp;
-          if (cg < p.ncg) {
+          if (cg < ncg_c) {
             const int gy = y0 + ar + kh0 - p.pad, gx = x0 + xl + kw - p.pad;
             const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
-            const uint8_t* src = ok ? p.x + ((((size_t)img * p.h + gy) * p.w + gx) * p.C + cg * 8) * 2 : p.x;
-            const uint32_t d = a_dst + (uint32_t)(kw * p.ncg + cg) * p.CGS_A + (uint32_t)ar * (WG_TW * 16);
+            const uint8_t* src = ok ? p.x + ((((size_t)img * p.h + gy) * p.w + gx) * p.C + (cg0 + cg) * 8) * 2 : p.x;
+            const uint32_t d = a_dst + (uint32_t)(kw * ncg_c + cg) * p.CGS_A + (uint32_t)ar * (WG_TW * 16);
             wcp_async16_ca(d, src, ok ? 16u : 0u);
             if (p.a_planes == 2) wcp_async16_ca(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
           }
@@ -354,10 +360,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           const int row = mb * 128 + q * 32 + lane;  // (kw, group, channel)
           const int g = row >> 3, ch = row & 7;
           int orow = -1;
-          if (g < p.G) {
-            const int kw = g / p.ncg, cg = g - kw * p.ncg;
-            orow = (kh * p.ks + kw) * p.C + cg * 8 + ch;
-          } else if (g == p.G && ch < 4 && kh == 0) {
+          if (g < Gc) {
+            const int kw = g / ncg_c, cg = g - kw * ncg_c;
+            orow = (kh * p.ks + kw) * p.C + (cg0 + cg) * 8 + ch;
+          } else if (g == Gc && ch < 4 && kh == 0 && cg0 == 0) {
             orow = p.ks * p.ks * p.C + ch;  // bias gradient row (+ 3 zero rows)
           }
           const uint32_t taddr = tmem_base + (khl * p.MB + mb) * p.NC + ((uint32_t)(q * 32) << 16);
@@ -415,43 +421,52 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   pl->C = C; pl->N = N; pl->a_planes = a_planes; pl->b_planes = b_planes;
   pl->ncg = C / 8;
   pl->G = d->ksize * pl->ncg;
-  pl->MB = (pl->G + 1 + 15) / 16;
-  if (pl->MB > 4) return NQ_ERR_UNSUPPORTED;  // C * ks > 504: more accumulator rows than one CTA's TMEM pass
-  // Choose (kernel rows per CTA, columns per CTA): nkh * MB * NC <= 512 TMEM columns.  Model: the kernel is bound
-  // by the larger of its MMA time (A read from shared memory binds narrow N: ~max(NC/2, 32 + NC/6) cycles per
-  // MMA) and its L2 -> SM traffic (dZ once per kernel-row group, the input once per column slice and group).
+  // Choose (input-channel slices msplit, kernel rows per CTA nkh, columns per CTA NC) with
+  // nkh * MB * NC <= 512 TMEM columns, MB = 128-row blocks of one slice's (kw, group) pairs (+ the bias group).
+  // Cost model fitted to the B200 measurements in profiles/: the kernel is bound by the larger of
+  //   MMA time     ~ max(NC/2, 40 + NC/8) cycles per MMA (the A read from shared memory binds narrow N), and
+  //   L2->SM time  ~ 1.8 x algorithmic bytes / 5.5 TB/s, where dZ is read once per (slice, kernel-row group) and
+  //                  the input once per (column slice, kernel-row group) with (TR + nkh - 1) / TR row overlap.
   const double P = (double)d->n * d->h * d->w;
+  const int passes = 1 + (a_planes == 2) + (b_planes == 2);
   double best_cost = 1e300;
-  int best_nkh = 1, best_nc = 16;
-  for (int nkh = 1; nkh <= d->ksize; ++nkh) {
-    int nc = (512 / (nkh * pl->MB)) / 16 * 16;
-    if (nc > 256) nc = 256;
-    if (nc > N) nc = N;
-    if (nc < 16) continue;
-    const int nsp = (N + nc - 1) / nc;
-    const int khg = (d->ksize + nkh - 1) / nkh;
-    const double per_mma = nc * 0.5 > 32.0 + nc / 6.0 ? nc * 0.5 : 32.0 + nc / 6.0;
-    const int passes = 1 + (a_planes == 2) + (b_planes == 2);
-    const double mma = P / 16.0 * d->ksize * pl->MB * nsp * passes * per_mma / 148.0;
-    const double in_rows = (4.0 + nkh - 1) / 4.0;
-    const double bytes = P * 2.0 * (b_planes * (double)N * khg + a_planes * (double)C * nsp * khg * in_rows);
-    const double traffic = bytes / (32.0 * 148.0);  // ~32 B/clk/SM sustained on this access pattern
-    double cost = mma > traffic ? mma : traffic;
-    // measured on B200 (profiles/): grouping kernel rows only pays when N is so narrow that the MMAs are cheap and
-    // the kernel is traffic bound (the head, N = 16: 0.82 -> 0.38 ms); at N >= 64 the narrower column slice costs more
-    if (N > 32 && nkh > 1) cost = 1e300;
-    if (N <= 32 && nkh == d->ksize) cost = 0.0;
-    if (cost < best_cost) { best_cost = cost; best_nkh = nkh; best_nc = nc; }
-  }
-  if (const char* e = getenv("NQ_WG_NKH")) {  // tuning override: kernel rows per CTA
-    int v = atoi(e);
-    if (v >= 1 && v <= d->ksize) {
-      int c = (512 / (v * pl->MB)) / 16 * 16;
-      if (c > 256) c = 256;
-      if (c > N) c = N;
-      if (c >= 16) { best_nkh = v; best_nc = c; }
+  int best_nkh = 0, best_nc = 0, best_ms = 1;
+  for (int ms = 1; ms <= pl->ncg && ms <= 8; ++ms) {
+    const int ncg_c = (pl->ncg + ms - 1) / ms;
+    if ((ms - 1) * ncg_c >= pl->ncg) continue;  // empty last slice
+    const int mb = (d->ksize * ncg_c + 1 + 15) / 16;
+    if (mb > 4) continue;
+    for (int nkh = 1; nkh <= d->ksize; ++nkh) {
+      int nc = (512 / (nkh * mb)) / 16 * 16;
+      if (nc > 256) nc = 256;
+      if (nc > N) nc = N;
+      if (nc < 16) continue;
+      const int nsp = (N + nc - 1) / nc;
+      const int khg = (d->ksize + nkh - 1) / nkh;
+      const double cyc = nc * 0.5 > 40.0 + nc / 8.0 ? nc * 0.5 : 40.0 + nc / 8.0;
+      const double mma = P / 16.0 * d->ksize * mb * ms * nsp * passes * cyc / (148.0 * 1.9e9);
+      const double bytes = P * 2.0 * (b_planes * (double)N * ms * khg + a_planes * (double)C * nsp * khg * (4.0 + nkh - 1) / 4.0);
+      const double traffic = 1.8 * bytes / 5.5e12;
+      const double ctas = (double)ms * nsp * khg;
+      double cost = (mma > traffic ? mma : traffic) + 2e-6 * ctas;  // mild preference for fewer CTA types
+      if (cost < best_cost) { best_cost = cost; best_nkh = nkh; best_nc = nc; best_ms = ms; }
     }
   }
+  if (!best_nkh) return NQ_ERR_UNSUPPORTED;  // C * ks too large for one TMEM pass even with 8 slices
+  if (const char* e = getenv("NQ_WG_CFG")) {  // tuning override "msplit,nkh"
+    int ms = 0, nkh = 0;
+    if (sscanf(e, "%d,%d", &ms, &nkh) == 2 && ms >= 1 && ms <= pl->ncg && nkh >= 1 && nkh <= d->ksize) {
+      const int ncg_c = (pl->ncg + ms - 1) / ms;
+      const int mb = (d->ksize * ncg_c + 1 + 15) / 16;
+      int c = mb <= 4 ? (512 / (nkh * mb)) / 16 * 16 : 0;
+      if (c > 256) c = 256;
+      if (c > N) c = N;
+      if (c >= 16 && (ms - 1) * ncg_c < pl->ncg) { best_ms = ms; best_nkh = nkh; best_nc = c; }
+    }
+  }
+  pl->msplit = best_ms;
+  pl->ncg_c = (pl->ncg + best_ms - 1) / best_ms;
+  pl->MB = (d->ksize * pl->ncg_c + 1 + 15) / 16;
   // shared-memory fit: tile rows as many as leave room for >= 2 pipeline buffers
   auto fit = [&](int nkh, int nc) -> bool {
     pl->nkh = nkh;
@@ -487,7 +502,7 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
   pl->tiles_x = (d->w + WG_TW - 1) / WG_TW;
   pl->tiles_y = (d->h + pl->TR - 1) / pl->TR;
   pl->tiles_total = pl->tiles_x * pl->tiles_y * d->n;
-  int ps = sm_count() / (pl->khg * pl->nsplits);
+  int ps = sm_count() / (pl->khg * pl->nsplits * pl->msplit);
   if (ps < 1) ps = 1;
   if (ps > pl->tiles_total) ps = pl->tiles_total;
   pl->tiles_per_split = (pl->tiles_total + ps - 1) / ps;
@@ -516,7 +531,7 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.x = x; p.dz = dz; p.ws = workspace;
   p.n = d->n; p.h = d->h; p.w = d->w; p.C = pl->C; p.N = pl->N; p.ks = d->ksize; p.pad = d->ksize / 2;
   p.ncg = pl->ncg; p.G = pl->G; p.MB = pl->MB; p.NC = pl->NC; p.nsplits = pl->nsplits; p.TR = pl->TR;
-  p.nkh = pl->nkh; p.khg = pl->khg; p.AR = pl->AR;
+  p.nkh = pl->nkh; p.khg = pl->khg; p.AR = pl->AR; p.msplit = pl->msplit; p.ncg_c = pl->ncg_c;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_total = pl->tiles_total; p.psplits = pl->psplits;
   p.tiles_per_split = pl->tiles_per_split; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.CGS_A = pl->CGS_A; p.CGS_B = pl->CGS_B; p.a_plane_bytes = pl->a_plane_bytes; p.b_plane_bytes = pl->b_plane_bytes;
@@ -527,7 +542,7 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.dz_plane_bytes = (size_t)d->n * d->h * d->w * p.dz_stride * 2;
   cudaStream_t s = as_stream(stream);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  const int grid = pl->psplits * pl->nsplits * pl->khg;
+  const int grid = pl->psplits * pl->msplit * pl->nsplits * pl->khg;
   wgrad_tc_kernel<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
   NQ_LAUNCH_CHECK();
   const int64_t n4 = (int64_t)(d->ksize * d->ksize * pl->C + 4) * pl->N / 4;

@@ -98,5 +98,6 @@ def test_tc_plans_fit_for_every_workload():
                 assert st == 0, (arch, i, st)
                 assert wp.nkh * wp.MB * wp.NC <= 512 and wp.NC % 16 == 0 and wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2
                 assert wp.khg * wp.nkh >= d.ksize and wp.AR == wp.TR + wp.nkh - 1
-                assert wp.G + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
-                assert wp.psplits * wp.nsplits * wp.khg <= max(148, wp.nsplits * wp.khg)
+                assert d.ksize * wp.ncg_c + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
+                assert wp.msplit * wp.ncg_c >= wp.ncg and (wp.msplit - 1) * wp.ncg_c < wp.ncg
+                assert wp.psplits * wp.nsplits * wp.khg * wp.msplit <= max(148, wp.nsplits * wp.khg * wp.msplit)
