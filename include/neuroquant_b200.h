@@ -125,7 +125,9 @@ typedef struct nq_conv_desc {
   int32_t rh, rw;    /* up-shuffle factors applied after the conv (1,1 = none) */
   int32_t c_grp;     /* real channels after the shuffle */
   int32_t cg;        /* padded channels after the shuffle (multiple of 4) */
-  int32_t act;       /* 0 none, 1 exact-erf GELU (nn.GELU, _layers.py:105) */
+  int32_t act;       /* 0 none, 1 exact-erf GELU (nn.GELU, _layers.py:105), 2 the same GELU with the `z` buffer
+                        holding GELU'(pre-activation) instead of the pre-activation: what autograd's backward of
+                        nn.GELU needs, evaluated once in the forward epilogue next to GELU itself */
 } nq_conv_desc;
 /* derived: nout_p = rh*rw*cg (GEMM N), kdim = ksize*ksize*cin_p (GEMM K) */
 
@@ -150,7 +152,8 @@ int nq_conv_fwd(const nq_conv_desc* d, const float* x, const float* wk, const fl
 /* Data gradient of the stage, fused with the previous stage's activation derivative and un-shuffle:
  *   dz      (n, h, w, nout_p)      gradient w.r.t. this stage's conv output (packed channel order)
  *   wt      packedT weights
- *   z_prev  (n, h, w, cin_p) or NULL   pre-activation of the previous stage (same grid as x)
+ *   z_prev  (n, h, w, cin_p) or NULL   pre-activation of the previous stage (same grid as x); with prev_act 2
+ *           the derivative GELU'(pre-activation) that the forward kernel saved under act 2
  *   dz_prev (n, h/prev_rh, w/prev_rw, prev_rh*prev_rw*cin_p): gradient w.r.t. the previous stage's conv
  *           output, i.e. (dx * act'(z_prev)) un-shuffled.  prev_act as nq_conv_desc.act. */
 int nq_conv_dgrad(const nq_conv_desc* d, const float* dz, const float* wt, const float* z_prev,

@@ -147,14 +147,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_igemm_kernel(const IgemmPara
         const int grp = col / p.cg, c = col - grp * p.cg;
         const int si = grp / p.rw, sj = grp - si * p.rw;
         const int64_t o = (((int64_t)pn * (p.h * p.rh) + (ph * p.rh + si)) * (p.w * p.rw) + (pw * p.rw + sj)) * p.cg + c;
-        if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = v;
-        if (p.act == 1) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+        if (p.out_z) {  // act 2: keep GELU'(z) for the backward pass instead of z
+          const float4 zs = p.act == 2 ? make_float4(gelu_grad_f(v.x), gelu_grad_f(v.y), gelu_grad_f(v.z), gelu_grad_f(v.w)) : v;
+          *reinterpret_cast<float4*>(p.out_z + o) = zs;
+        }
+        if (p.act != 0) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
         *reinterpret_cast<float4*>(p.out_y + o) = v;
       } else {
         if (p.zprev) {
           const float4 z = ldg4(p.zprev + (int64_t)m * p.N + col);
           if (p.act == 1) {
             v.x *= gelu_grad_f(z.x); v.y *= gelu_grad_f(z.y); v.z *= gelu_grad_f(z.z); v.w *= gelu_grad_f(z.w);
+          } else if (p.act == 2) {  // z_prev already holds the derivative
+            v.x *= z.x; v.y *= z.y; v.z *= z.z; v.w *= z.w;
           }
         }
         const int qh = ph / p.rh, si = ph - qh * p.rh;
@@ -580,7 +585,7 @@ extern "C" int nq_conv_dgrad(const nq_conv_desc* d, const float* dz, const float
   if (st) return st;
   if (!dz || !wt || !dz_prev || prev_rh <= 0 || prev_rw <= 0) return NQ_ERR_BAD_ARG;
   if (d->h % prev_rh || d->w % prev_rw) return NQ_ERR_BAD_SHAPE;
-  if (prev_act != 0 && prev_act != 1) return NQ_ERR_BAD_ARG;
+  if (prev_act < 0 || prev_act > 2) return NQ_ERR_BAD_ARG;
   IgemmParams p{};
   p.in = dz; p.wmat = wt; p.bias = nullptr; p.zprev = z_prev; p.out_z = nullptr; p.out_y = dz_prev;
   p.n = d->n; p.h = d->h; p.w = d->w; p.C = d->rh * d->rw * d->cg; p.ks = d->ksize; p.pad = d->ksize / 2;

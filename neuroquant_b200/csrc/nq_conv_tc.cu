@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             zv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.zprev && p.act == 1 && valid[it] && col_ok)
+            if (p.zprev && p.act != 0 && valid[it] && col_ok)
               zv[it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
           }
         }
@@ -608,15 +608,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             r.x = fmaf(r.x, g0.x, g1.x); r.y = fmaf(r.y, g0.y, g1.y);
             r.z = fmaf(r.z, g0.z, g1.z); r.w = fmaf(r.w, g0.w, g1.w);
             const size_t o = row_base[it] + col_off;
-            if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
-            if (p.out_y) {
-              if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
-              store_split4(p.out_y, p.out_plane_bytes, o, r);
+            if (p.act == 2) {  // GELU, keeping GELU'(z) for the backward pass in place of z (one exponential for both)
+              float4 g;
+              gelu_both_fast(r.x, r.x, g.x); gelu_both_fast(r.y, r.y, g.y);
+              gelu_both_fast(r.z, r.z, g.z); gelu_both_fast(r.w, r.w, g.w);
+              if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = g;
+              if (p.out_y) store_split4(p.out_y, p.out_plane_bytes, o, r);
+            } else {
+              if (p.out_z) *reinterpret_cast<float4*>(p.out_z + o) = r;
+              if (p.out_y) {
+                if (p.act == 1) { r.x = gelu_fast(r.x); r.y = gelu_fast(r.y); r.z = gelu_fast(r.z); r.w = gelu_fast(r.w); }
+                store_split4(p.out_y, p.out_plane_bytes, o, r);
+              }
             }
           } else if (p.epi == 1) {
             if (p.zprev && p.act == 1) {
               r.x *= gelu_grad_fast(zv[it].x); r.y *= gelu_grad_fast(zv[it].y);
               r.z *= gelu_grad_fast(zv[it].z); r.w *= gelu_grad_fast(zv[it].w);
+            } else if (p.zprev && p.act == 2) {  // z_prev holds GELU'(z) already
+              r.x *= zv[it].x; r.y *= zv[it].y; r.z *= zv[it].z; r.w *= zv[it].w;
             }
             store_split4(p.out_y, p.out_plane_bytes, row_base[it] + n, r);
           }
@@ -938,7 +948,7 @@ extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, con
   if (st) return st;
   if (!pl || pl->dir != 1 || !dz_split || !wpk_t || !dz_prev_split || prev_rh <= 0 || prev_rw <= 0) return NQ_ERR_BAD_ARG;
   if (d->h % prev_rh || d->w % prev_rw) return NQ_ERR_BAD_SHAPE;
-  if (prev_act != 0 && prev_act != 1) return NQ_ERR_BAD_ARG;
+  if (prev_act < 0 || prev_act > 2) return NQ_ERR_BAD_ARG;
   TcParams p{};
   const int nout_p = d->rh * d->rw * d->cg;
   const int dz_ch = (nout_p + 7) / 8 * 8;  // channels per pixel as stored (the head's 4 are stored as 8)

@@ -279,7 +279,7 @@ static int check_desc(const nq_conv_desc* d) {
   if (d->ksize < 1 || (d->ksize & 1) == 0) return NQ_ERR_BAD_SHAPE;
   if (d->cin_p < d->cin || (d->cin_p & 3) || d->cg < d->c_grp || (d->cg & 3)) return NQ_ERR_BAD_SHAPE;
   if (d->cout != d->c_grp * d->rh * d->rw) return NQ_ERR_BAD_SHAPE;
-  if (d->act != 0 && d->act != 1) return NQ_ERR_BAD_ARG;
+  if (d->act < 0 || d->act > 2) return NQ_ERR_BAD_ARG;
   return NQ_OK;
 }
 namespace nq { int check_conv_desc(const nq_conv_desc* d) { return check_desc(d); } }
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const float* __r
     const int x = (int)(pix % W2), y = (int)((pix / W2) % H2), b = (int)(pix / ((int64_t)W2 * H2));
     float v = dy[e];
     if (act == 1) v *= gelu_grad_f(z[e]);
+    else if (act == 2) v *= z[e];
     const int qh = y / rh, si = y - qh * rh, qw = x / rw, sj = x - qw * rw;
     dz[(((int64_t)b * h + qh) * w + qw) * ((int64_t)rh * rw * cg) + (int64_t)(si * rw + sj) * cg + c] = v;
   }
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const float* __r
 extern "C" int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int h, int w, int rh, int rw, int cg, int act,
                                     float* dz, void* stream) {
   if (!dy || !dz || n <= 0 || h <= 0 || w <= 0 || rh <= 0 || rw <= 0 || cg <= 0) return NQ_ERR_BAD_ARG;
-  if (act != 0 && act != 1) return NQ_ERR_BAD_ARG;
-  if (act == 1 && !z) return NQ_ERR_BAD_ARG;
+  if (act < 0 || act > 2) return NQ_ERR_BAD_ARG;
+  if (act != 0 && !z) return NQ_ERR_BAD_ARG;
   const int64_t total = (int64_t)n * h * rh * w * rw * cg;
   act_bwd_unshuffle_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(dy, z, n, h, w, rh, rw, cg, act, dz);
   NQ_LAUNCH_CHECK();

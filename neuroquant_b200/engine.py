@@ -34,6 +34,7 @@ from . import _lib as L
 
 ROUND_NEAREST, ROUND_SOFT, ROUND_HARD = 0, 1, 2
 _ACT = {"none": 0, "gelu": 1}
+_ACT_SAVED_GRAD = 2  # nq_conv_desc.act: GELU whose z buffer holds the derivative
 _HEAD = {"tanh": 0, "sigmoid": 1}
 
 
@@ -179,10 +180,16 @@ class _Plan:
         self.n, self.h0, self.w0, self.train = n, h0, w0, train
         self.desc: List[L.ConvDesc] = []
         self.x: List[torch.Tensor] = []  # stage inputs (x[i+1] is stage i's activated output)
-        self.z: List[Optional[torch.Tensor]] = []  # pre-activations (train only, act != none)
+        self.z: List[Optional[torch.Tensor]] = []  # what backward needs of the pre-activation: GELU'(z) (train only)
         self.dz: List[Optional[torch.Tensor]] = []
         last = len(eng.geoms) - 1
         self.desc = stage_descs(eng.geoms, n, h0, w0, eng.use_tc)
+        if train and os.environ.get("NQ_SAVE_ACT_GRAD", "1") != "0":
+            # act 2: the forward epilogue evaluates GELU' next to GELU (one exponential for both) and keeps it in the
+            # z buffer; dgrad then multiplies instead of re-evaluating erfc / exp per element.
+            for d in self.desc:
+                if d.act == _ACT["gelu"]:
+                    d.act = _ACT_SAVED_GRAD
 
         def act_buf(*shape):
             # tensor-core engine: "split-bf16" storage (hi plane, lo plane; same bytes as fp32); FFMA engine: fp32
@@ -598,11 +605,11 @@ class DecoderEngine:
                 if self.use_tc:
                     pl, wpk = (p.tc_head_dgrad, self._head_dgrad) if i == last else (p.tc_dgrad[i], self._tcw[i][1])
                     L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(pl), p.dz[i].data_ptr(),
-                                      wpk.data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act],
+                                      wpk.data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, p.desc[i - 1].act,
                                       p.dz[i - 1].data_ptr(), st), "nq_tc_conv_dgrad")
                 else:
                     L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
-                                      L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, _ACT[g_prev.act], L.ptr(p.dz[i - 1]), st),
+                                      L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, p.desc[i - 1].act, L.ptr(p.dz[i - 1]), st),
                             "nq_conv_dgrad")
                 self.launches += 1
             s = self.stages[i]

@@ -366,3 +366,23 @@ def test_tensor_core_head_variant(nq, monkeypatch):
     assert outs["tc"][1] == pytest.approx(outs["simt"][1], rel=1e-5)
     for a, b in zip(outs["tc"][2], outs["simt"][2]):
         assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-10
+
+
+def test_saved_activation_derivative_equals_recomputed(nq, monkeypatch, conv_path):
+    """nq_conv_desc.act = 2 (forward keeps GELU'(z) in the z buffer, dgrad multiplies) against act = 1 (forward keeps
+    z, dgrad re-evaluates GELU'): same frames, and the same gradients up to fp32 rounding of one product."""
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NQ_SAVE_ACT_GRAD", flag)
+        g, arch, cfg, stages, eng = make_engine(nq, "tiny_hnerv", "uaq")
+        eng.init_scales()
+        eng.start_adaround()
+        cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
+        img = eng.forward(cali[:2], train=True, target=frames[:2]).clone()
+        acts = [d.act for d in eng._last_plan.desc]
+        assert (2 in acts) == (flag == "1") and (1 in acts) == (flag == "0")
+        eng.backward()
+        outs[flag] = (img, [x.clone() for pair in eng.param_grads() for x in pair])
+    assert torch.equal(outs["1"][0], outs["0"][0])
+    for a, b in zip(outs["1"][1], outs["0"][1]):
+        assert (a - b).abs().max() <= 1e-5 * b.abs().max() + 1e-12
