@@ -29,6 +29,7 @@
 // Warp roles (640 threads): warps 0-7 epilogue (TMEM -> registers -> global), warps 8-15 activation loaders
 // (fp32 -> bf16 hi/lo), warp 16 weight-stage producer, warp 17 MMA issuer, warp 18 TMEM allocator.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "nq_common.cuh"
 
@@ -37,7 +38,8 @@ namespace nq {
 constexpr int TC_THREADS = 640;
 constexpr int TC_LOADERS = 256;  // warps 8-15
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
-constexpr int TC_MAX_BSTAGES = 8;
+constexpr int TC_MAX_BSTAGES = 16;
+constexpr int TC_HDR_BYTES = 512;     // barriers (8 + 2 * TC_MAX_BSTAGES) + TMEM pointer
 constexpr int EPI_ROW = 20;            // floats per staged epilogue row (16 + 4 pad: conflict-free 16-byte accesses)
 constexpr int EPI_STAGE_BYTES = 8 * 32 * EPI_ROW * 4;  // 8 epilogue warps
 
@@ -69,6 +71,7 @@ struct TcParams {
   int epi_stage_off;     // byte offset of the epilogue staging tiles in shared memory
   int cs;                // CTAs per cluster sharing every weight stage by TMA multicast (1, 2 or 4)
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
+  int mt;                // 16x8 pixel tiles (side by side in x) per CTA step: they share every weight stage (NT <= 256 / mt)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -251,7 +254,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, in
   const int ty = tm % p.tiles_y;
   c.img = tm / p.tiles_y;
   c.y0 = ty * TILE_H;
-  c.x0 = tx * TILE_W;
+  c.x0 = tx * TILE_W * p.mt;
   c.n0 = tn * p.NT;
   c.nt = min(p.NT, p.N - c.n0);
   return c;
@@ -259,14 +262,14 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, in
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // [0,256): barriers + tmem pointer; then A buffers, then B stages
+  // [0, TC_HDR_BYTES): barriers + tmem pointer; then A buffers, then B stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
   // barrier indices
   const uint32_t A_FULL = bar0 + 0 * 8, A_EMPTY = bar0 + 2 * 8, T_FULL = bar0 + 4 * 8, T_EMPTY = bar0 + 6 * 8;
   const uint32_t B_FULL = bar0 + 8 * 8, B_EMPTY = bar0 + (8 + TC_MAX_BSTAGES) * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (8 + 2 * TC_MAX_BSTAGES) * 8);
-  const uint32_t a_base = smem_u32(smem + 256);
+  const uint32_t a_base = smem_u32(smem + TC_HDR_BYTES);
   const uint32_t b_base = a_base + 2 * p.a_buf_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -354,6 +357,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(T_EMPTY + acc * 8, ((tcnt >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
+      const uint32_t d_tmem1 = d_tmem + 128;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
+      const bool two = p.mt == 2;
       const uint32_t idesc = make_idesc(tc.nt);
       const uint32_t b_lbo16 = (uint32_t)tc.nt;  // nt * 16 bytes >> 4
       const uint32_t b_plane16 = (uint32_t)(tc.nt * p.SBC * 2) >> 4;
@@ -383,6 +388,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   umma_bf16_w(d_tmem, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
                   umma_bf16_w(d_tmem, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
                   umma_bf16_w(d_tmem, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+                  if (two) {
+                    umma_bf16_w(d_tmem1, a_lo + 8, a_hi32, b_lo, b_hi32, idesc, accum);
+                    umma_bf16_w(d_tmem1, a_lo + 8 + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                    umma_bf16_w(d_tmem1, a_lo + 8, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+                  }
                 }
                 accum = 1;
                 a_lo += a_step16;
@@ -394,6 +404,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (leader) {
                   umma_bf16_w(d_tmem, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
                   umma_bf16_w(d_tmem, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                  if (two) {
+                    umma_bf16_w(d_tmem1, a_lo + 8, a_hi32, b_lo, b_hi32, idesc, accum);
+                    umma_bf16_w(d_tmem1, a_lo + 8 + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                  }
                 }
                 accum = 1;
                 a_lo += a_step16;
@@ -405,6 +419,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (leader) {
                   umma_bf16_w(d_tmem, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
                   if (passes == 2) umma_bf16_w(d_tmem, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+                  if (two) {
+                    umma_bf16_w(d_tmem1, a_lo + 8, a_hi32, b_lo, b_hi32, idesc, accum);
+                    if (passes == 2) umma_bf16_w(d_tmem1, a_lo + 8, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+                  }
                 }
                 accum = 1;
                 a_lo += a_step16;
@@ -483,9 +501,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // the four pixels (one per 8-row group) this lane stores: m = q*32 + it*8 + rsub, tile row m>>3 = q*4 + it
       size_t row_base[4], zrow[4];
       bool valid[4];
+      int sub = 0;  // pixel tile of the step (0 .. mt-1)
+    next_sub:
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int y = tc.y0 + q * 4 + it, x = tc.x0 + rsub;
+        const int y = tc.y0 + q * 4 + it, x = tc.x0 + sub * TILE_W + rsub;
         valid[it] = tc.real && y < p.h && x < p.w;
         if (p.epi == 0) {
           row_base[it] = (((size_t)tc.img * (p.h * p.rh) + (size_t)y * p.rh) * (p.w * p.rw) + (size_t)x * p.rw) * p.cg;
@@ -567,7 +587,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * 256 + sub * 128 + ((uint32_t)(q * 32) << 16);
       for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
@@ -633,6 +653,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         __syncwarp();
       }
+      if (++sub < p.mt) goto next_sub;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
@@ -772,7 +793,21 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->a_planes = a_planes;
   pl->b_planes = b_planes;
   pl->NT = N < 256 ? N : 256;
-  pl->PW = TILE_W + d->ksize - 1;
+  // Two pixel tiles per CTA step (side by side in x, one 16x16 halo) when the weight stream would otherwise bind:
+  // every weight stage then feeds 2x the MMAs, halving the L2 -> SM weight traffic per pixel (conv_dgrad[5] of
+  // HNeRV-3M re-streams 768 KB of weights per 128-pixel tile).  Needs both accumulators in one 256-column TMEM half
+  // and enough tile pairs to fill the machine.
+  {
+    const long long w_tile_bytes = (long long)d->ksize * d->ksize * C * pl->NT * 2 * b_planes;
+    const long long pairs = (long long)((d->w + 2 * TILE_W - 1) / (2 * TILE_W)) * ((d->h + TILE_H - 1) / TILE_H) * d->n;
+    pl->mt = (pl->NT <= 128 && w_tile_bytes >= 64 * 1024 && pairs >= 2LL * sm_count()) ? 2 : 1;
+    if (const char* e = getenv("NQ_TC_MT")) {  // tuning override
+      const int v = atoi(e);
+      if (v == 1 || (v == 2 && pl->NT <= 128)) pl->mt = v;
+    }
+  }
+  const int tile_w = TILE_W * pl->mt;
+  pl->PW = tile_w + d->ksize - 1;
   pl->PH = TILE_H + d->ksize - 1;
   int npix = pl->PW * pl->PH;
   int cgs16 = npix;  // channel-group stride in 16-byte units, forced to 4 mod 8 (conflict-free lane-pair stores)
@@ -782,34 +817,36 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   // amortise the per-stage barrier round trips of the producer and issuer threads (a 6 KB stage is only
   // ~270 MMA cycles), so take the largest SBC (multiple of 16 dividing C) whose stage is <= 32 KB and that
   // leaves room for two activation buffers and >= 3 weight stages in the 227 KB of shared memory.
-  int best = 0;
-  for (int sbc = (C < 128 ? C : 128) / 16 * 16; sbc >= 16; sbc -= 16) {
+  int best = 0, best_kc = 0;
+  for (int sbc = (C < 128 ? C : 128) / 16 * 16; sbc >= 16 && !best; sbc -= 16) {
     if (C % sbc) continue;
     const int stage = pl->NT * sbc * 2 * b_planes;
     if (stage > 32 * 1024 && sbc > 16) continue;
-    int kc = sbc >= 64 ? sbc : sbc * (64 / sbc);
-    if (kc > C) kc = C;
-    const int a_buf = pl->CGS * (kc / 8) * a_planes;
-    const int budget = 227 * 1024 - 256 - EPI_STAGE_BYTES - 2 * a_buf;
-    if (budget < 3 * stage) continue;
-    best = sbc;
-    break;
+    // activation unit: ~64 channels (a multiple of the stage), fewer when the (16x16-pixel) halo is large
+    for (int kc = sbc >= 64 ? sbc : sbc * (64 / sbc); kc >= sbc; kc -= sbc) {
+      const int kcc = kc > C ? C : kc;
+      const int a_buf = pl->CGS * (kcc / 8) * a_planes;
+      const int budget = 227 * 1024 - TC_HDR_BYTES - EPI_STAGE_BYTES - 2 * a_buf;
+      if (budget < 3 * stage) continue;
+      best = sbc;
+      best_kc = kcc;
+      break;
+    }
   }
   if (!best) return NQ_ERR_UNSUPPORTED;
   const int sbc = best;
   pl->SBC = sbc;
-  pl->KC = sbc >= 64 ? sbc : sbc * (64 / sbc);
-  if (pl->KC > C) pl->KC = C;
+  pl->KC = best_kc;
   pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
   pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
   pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes;
-  const int budget = 227 * 1024 - 256 - EPI_STAGE_BYTES - 2 * pl->a_buf_bytes;
+  const int budget = 227 * 1024 - TC_HDR_BYTES - EPI_STAGE_BYTES - 2 * pl->a_buf_bytes;
   int nst = budget / pl->b_stage_bytes;
   if (nst > TC_MAX_BSTAGES) nst = TC_MAX_BSTAGES;
   if (nst < 2) return NQ_ERR_UNSUPPORTED;
   pl->n_bstages = nst;
-  pl->smem_bytes = 256 + 2 * pl->a_buf_bytes + nst * pl->b_stage_bytes + EPI_STAGE_BYTES;
-  pl->tiles_x = (d->w + TILE_W - 1) / TILE_W;
+  pl->smem_bytes = TC_HDR_BYTES + 2 * pl->a_buf_bytes + nst * pl->b_stage_bytes + EPI_STAGE_BYTES;
+  pl->tiles_x = (d->w + tile_w - 1) / tile_w;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
   pl->total_tiles = pl->tiles_x * pl->tiles_y * d->n * pl->tiles_n;
@@ -868,10 +905,11 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if (p.n_store == 0) p.n_store = pl->N;
   p.N = pl->N; p.NT = pl->NT; p.KC = pl->KC; p.SBC = pl->SBC; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_n = pl->tiles_n; p.total_tiles = pl->total_tiles;
-  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS;
+  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS; p.mt = pl->mt;
+  if (p.mt < 1 || p.mt > 2 || (p.mt == 2 && (pl->NT > 128 || p.epi == 2))) return NQ_ERR_BAD_ARG;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
-  p.epi_stage_off = 256 + 2 * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
+  p.epi_stage_off = TC_HDR_BYTES + 2 * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
   NQ_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
   int cs = pl->cluster;
