@@ -71,6 +71,8 @@ struct TcParams {
   int epi_stage_off;     // byte offset of the epilogue staging tiles in shared memory
   int cs;                // CTAs per cluster sharing every weight stage by TMA multicast (1, 2 or 4)
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
+  int bcat;              // weight stage stores the planes side by side per k-group ([k-group][plane][n][8]): A_hi x [B_hi | B_lo]
+                         // is ONE MMA of 2 * nt columns (hi*hi in columns [0, nt), hi*lo in [nt, 2 nt)) + A_lo x B_hi
   int mt;                // 16x8 pixel tiles (side by side in x) per CTA step: they share every weight stage (NT <= 256 / mt)
 };
 
@@ -260,6 +262,8 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, in
   return c;
 }
 
+// MT / BCAT are compile-time copies of TcParams::mt / bcat: the common (1, 0) variant carries none of their code.
+template <int MT, int BCAT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // [0, TC_HDR_BYTES): barriers + tmem pointer; then A buffers, then B stages
@@ -358,9 +362,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
       const uint32_t d_tmem1 = d_tmem + 128;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
-      const bool two = p.mt == 2;
+      constexpr bool two = MT == 2;
       const uint32_t idesc = make_idesc(tc.nt);
-      const uint32_t b_lbo16 = (uint32_t)tc.nt;  // nt * 16 bytes >> 4
+      const uint32_t idesc2 = make_idesc(2 * tc.nt);  // bcat: both weight planes as one operand
+      const uint32_t b_lbo16 = (uint32_t)tc.nt << BCAT;  // k-group stride: nt (or 2 nt) * 16 bytes >> 4
       const uint32_t b_plane16 = (uint32_t)(tc.nt * p.SBC * 2) >> 4;
       const uint32_t b_step16 = 2 * b_lbo16;
       uint32_t accum = 0;
@@ -381,7 +386,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             uint32_t b_lo = (((b_base + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
             // uniform loops; only the MMA itself is predicated on the leader lane, so that ptxas keeps the
             // descriptors in uniform registers instead of broadcasting them per instruction
-            if (passes == 3) {
+            if (BCAT) {
+              // 2 MMAs per k16 instead of 3: the A tile (4 KB of shared-memory reads per MMA, the binding resource
+              // at narrow N) is fetched twice, not three times
+#pragma unroll 1
+              for (int j = 0; j < k16_per_stage; ++j) {
+                if (leader) {
+                  umma_bf16_w(d_tmem, a_lo, a_hi32, b_lo, b_hi32, idesc2, accum);
+                  umma_bf16_w(d_tmem, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                  if (two) {
+                    umma_bf16_w(d_tmem1, a_lo + 8, a_hi32, b_lo, b_hi32, idesc2, accum);
+                    umma_bf16_w(d_tmem1, a_lo + 8 + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                  }
+                }
+                accum = 1;
+                a_lo += a_step16;
+                b_lo += b_step16;
+              }
+            } else if (passes == 3) {
 #pragma unroll 1
               for (int j = 0; j < k16_per_stage; ++j) {
                 if (leader) {
@@ -591,6 +613,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
+        if (BCAT) {  // hi*lo partial sums live nt columns further
+          uint32_t v2[16];
+          tmem_ld16(taddr + tc.nt + c0, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(v2[k]));
+        }
         const int n = tc.n0 + c0 + qd * 4;  // first of this lane's 4 columns
         const bool col_ok = n < p.n_store;
         float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -653,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         __syncwarp();
       }
-      if (++sub < p.mt) goto next_sub;
+      if (MT > 1 && ++sub < MT) goto next_sub;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
@@ -686,7 +715,7 @@ struct TcPackParams {
   int cout, cin, cin_src, ks;
   int rh, rw, c_grp, cg;  // packed output-channel order (up-shuffle groups)
   int dir;                // 0 forward (K = input channels, N = packed output channels), 1 dgrad (swapped, flipped)
-  int C, N, NT, KC, SBC, b_planes;
+  int C, N, NT, KC, SBC, b_planes, bcat;
 };
 
 __device__ __forceinline__ int unpack_cout(int np, int rh, int rw, int c_grp, int cg) {
@@ -754,9 +783,15 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackParams q) {
     const size_t stage_bytes = (size_t)nt * q.SBC * 2 * q.b_planes;
     const size_t ntile_stride = (size_t)stages_per_ntile * q.NT * q.SBC * 2 * q.b_planes;
     uint8_t* st = q.out + (size_t)tn * ntile_stride + (size_t)s * stage_bytes;
-    const size_t o = ((size_t)g * nt + nn) * 16;
-    *reinterpret_cast<uint4*>(st + o) = hi;
-    if (q.b_planes == 2) *reinterpret_cast<uint4*>(st + (size_t)nt * q.SBC * 2 + o) = lo;
+    if (q.bcat) {  // [k-group][plane][n][8]
+      const size_t o = ((size_t)g * 2 * nt + nn) * 16;
+      *reinterpret_cast<uint4*>(st + o) = hi;
+      *reinterpret_cast<uint4*>(st + o + (size_t)nt * 16) = lo;
+    } else {  // [plane][k-group][n][8]
+      const size_t o = ((size_t)g * nt + nn) * 16;
+      *reinterpret_cast<uint4*>(st + o) = hi;
+      if (q.b_planes == 2) *reinterpret_cast<uint4*>(st + (size_t)nt * q.SBC * 2 + o) = lo;
+    }
   }
 }
 
@@ -806,6 +841,15 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
       if (v == 1 || (v == 2 && pl->NT <= 128)) pl->mt = v;
     }
   }
+  // Planes side by side (see TcParams::bcat) when both operands are split, the doubled tile fits the accumulator
+  // slot (256 columns, 128 per pixel tile when mt == 2) and K is long enough to amortise the second TMEM read of
+  // the epilogue.
+  pl->bcat = (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256 && d->ksize * d->ksize * C >= 512) ? 1 : 0;
+  if (const char* e = getenv("NQ_TC_BCAT")) {  // tuning override
+    if (atoi(e) == 0) pl->bcat = 0;
+    else if (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256) pl->bcat = 1;
+  }
+  pl->reserved = 0;
   const int tile_w = TILE_W * pl->mt;
   pl->PW = tile_w + d->ksize - 1;
   pl->PH = TILE_H + d->ksize - 1;
@@ -878,7 +922,7 @@ extern "C" int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* pl, co
   q.w = w_ref; q.zp = zero_point; q.zp_stride = zp_stride; q.out = reinterpret_cast<uint8_t*>(wpk);
   q.cout = d->cout; q.cin = d->cin; q.cin_src = cin_src; q.ks = d->ksize;
   q.rh = d->rh; q.rw = d->rw; q.c_grp = d->c_grp; q.cg = d->cg;
-  q.dir = pl->dir; q.C = pl->C; q.N = pl->N; q.NT = pl->NT; q.KC = pl->KC; q.SBC = pl->SBC; q.b_planes = pl->b_planes;
+  q.dir = pl->dir; q.C = pl->C; q.N = pl->N; q.NT = pl->NT; q.KC = pl->KC; q.SBC = pl->SBC; q.b_planes = pl->b_planes; q.bcat = pl->bcat;
   const long long total = (long long)(pl->C / pl->SBC) * d->ksize * d->ksize * (pl->SBC / 8) * pl->NT * pl->tiles_n;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
@@ -905,12 +949,15 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if (p.n_store == 0) p.n_store = pl->N;
   p.N = pl->N; p.NT = pl->NT; p.KC = pl->KC; p.SBC = pl->SBC; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_n = pl->tiles_n; p.total_tiles = pl->total_tiles;
-  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS; p.mt = pl->mt;
+  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS; p.mt = pl->mt; p.bcat = pl->bcat;
   if (p.mt < 1 || p.mt > 2 || (p.mt == 2 && (pl->NT > 128 || p.epi == 2))) return NQ_ERR_BAD_ARG;
+  if (p.bcat && (p.epi == 2 || pl->a_planes != 2 || pl->b_planes != 2 || 2 * pl->NT * pl->mt > 256)) return NQ_ERR_BAD_ARG;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   p.epi_stage_off = TC_HDR_BYTES + 2 * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
-  NQ_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  void (*kern)(const TcParams) = p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1> : conv_tc_kernel<2, 0>)
+                                            : (p.bcat ? conv_tc_kernel<1, 1> : conv_tc_kernel<1, 0>);
+  NQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
   int cs = pl->cluster;
   p.tiles_m = pl->tiles_x * pl->tiles_y * d->n;
@@ -932,7 +979,7 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, p));
+  NQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   return NQ_OK;
 }
 
