@@ -103,6 +103,47 @@ int nq_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp
                      double beta1, double beta2, double eps, const float* hyper_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-tensor launches.  A decoder has 2 quantisers per stage (weight, bias) of 12 .. 1.6 M elements; one
+ * launch per tensor is launch-latency bound.  These entry points take a HOST array of per-tensor tasks (device
+ * pointers inside) and process up to NQ_MULTI_MAX tensors per kernel launch; element arithmetic is the
+ * single-tensor kernels', value for value.
+ * ------------------------------------------------------------------------------------------------ */
+#define NQ_MULTI_MAX 16
+
+typedef struct nq_fq_task {    /* one nq_fakequant_fwd call */
+  const float* x;
+  const float* alpha;          /* may be NULL for NQ_ROUND_NEAREST */
+  const float* delta;
+  const float* zero_point;
+  float* codes;                /* may be NULL */
+  float* deq;                  /* may be NULL */
+  int64_t rows, row_len;
+  int32_t channel_wise;        /* 1: delta / zero_point per row, 0: one value */
+  int32_t n_bits, mode;        /* nq_round_mode */
+  int32_t want_reg;            /* 1: this tensor's soft targets add sum(1 - |2h - 1|^reg_b) to *reg_sum */
+} nq_fq_task;
+int nq_fakequant_fwd_multi(const nq_fq_task* tasks, int n_tasks, float* reg_sum, float reg_b, void* stream);
+
+typedef struct nq_ada_task {   /* nq_fakequant_bwd_soft_dev + nq_adam_step_dev of one AdaRound quantiser */
+  const float* g;              /* dLoss / d(de-quantised tensor) */
+  const float* x;              /* the tensor being quantised */
+  float* alpha;                /* rounding variables V: the Adam parameter, updated in place */
+  const float* delta;
+  const float* zero_point;
+  float* exp_avg;              /* Adam state */
+  float* exp_avg_sq;
+  int64_t rows, row_len;
+  int32_t channel_wise, n_bits;
+  int32_t use_reg;             /* 1: add the rounding regulariser's gradient (weights), 0: not (biases) */
+  int32_t reserved;
+} nq_ada_task;
+/* alpha <- Adam(alpha, d(loss + reg)/d alpha) for every task in one pass (calib_model.py:213-218: loss.backward();
+ * optimizer.step()); hyper_dev as in nq_fakequant_bwd_soft_dev / nq_adam_step_dev. */
+int nq_adaround_step_multi(const nq_ada_task* tasks, int n_tasks, float grad_scale, double beta1, double beta2, double eps,
+                           const float* hyper_dev, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
  * Walsh-Hadamard rotation (quantization/quant_layer.py:16-22; third-party hadamard_transform)
  * ------------------------------------------------------------------------------------------------ */
 

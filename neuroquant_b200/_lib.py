@@ -50,6 +50,23 @@ class TcWgradPlan(C.Structure):
                  "tiles_total", "psplits", "tiles_per_split")] + [("workspace_floats", C.c_int64)]
 
 
+class FqTask(C.Structure):
+    """Mirror of nq_fq_task."""
+    _fields_ = [(n, C.c_void_p) for n in ("x", "alpha", "delta", "zero_point", "codes", "deq")] + \
+               [("rows", C.c_int64), ("row_len", C.c_int64)] + \
+               [(n, C.c_int32) for n in ("channel_wise", "n_bits", "mode", "want_reg")]
+
+
+class AdaTask(C.Structure):
+    """Mirror of nq_ada_task."""
+    _fields_ = [(n, C.c_void_p) for n in ("g", "x", "alpha", "delta", "zero_point", "exp_avg", "exp_avg_sq")] + \
+               [("rows", C.c_int64), ("row_len", C.c_int64)] + \
+               [(n, C.c_int32) for n in ("channel_wise", "n_bits", "use_reg", "reserved")]
+
+
+MULTI_MAX = 16
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise NqError(
@@ -71,6 +88,8 @@ def _load():
         "nq_adam_step": (I, [P, P, P, P, L, D, D, D, D, I, P]),
         "nq_fakequant_bwd_soft_dev": (I, [P, P, P, P, P, L, L, I, I, F, I, P, P, P]),
         "nq_adam_step_dev": (I, [P, P, P, P, L, D, D, D, P, P]),
+        "nq_fakequant_fwd_multi": (I, [C.POINTER(FqTask), I, P, F, P]),
+        "nq_adaround_step_multi": (I, [C.POINTER(AdaTask), I, F, D, D, D, P, P]),
         "nq_fwht": (I, [P, P, L, I, L, L, P]),
         "nq_pack_weight": (I, [DP, P, I, P, P, P, P, P]),
         "nq_conv_fwd": (I, [DP, P, P, P, P, P, P]),

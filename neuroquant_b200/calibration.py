@@ -19,7 +19,7 @@ from typing import Callable, Iterable, List, Optional, Sequence
 
 import torch
 
-from .engine import AdamState, DecoderEngine
+from .engine import AdamState, DecoderEngine, adaround_step_multi
 
 
 class LinearTempDecay:
@@ -62,9 +62,7 @@ class GraphedStep:
         flat = eng.backward()
         if self.world > 1:  # the NCCL all-reduce is captured into the graph with the kernels around it
             torch.distributed.all_reduce(flat, group=self.group)
-        grads = eng.param_grads(1.0, hyper=self.hyper)
-        self.opt.step_dev([g for pair in grads for g in pair], self.hyper)
-        eng.launches += len(self.opt.params)
+        adaround_step_multi(eng, self.opt, self.hyper)  # quantiser Jacobian + Adam for all 14 tensors: one launch
 
     def run(self, embed, frames, reg_w: float, reg_b: float):
         self.embed.copy_(embed)

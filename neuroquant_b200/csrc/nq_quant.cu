@@ -46,6 +46,28 @@ __device__ __forceinline__ float soft_target_raw(float alpha, float& sig) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// one element of the fake-quantiser forward: returns the code, writes the rounding-regulariser term
+template <int MODE>
+__device__ __forceinline__ float fq_fwd_elem(float xv, float av, float d, float z, float qmax, bool want_reg, float reg_b,
+                                             float& reg) {
+  const float q = __fdiv_rn(xv, d);  // true fp32 divide
+  float x_int;
+  if (MODE == NQ_ROUND_NEAREST) {
+    x_int = rintf(q);  // half-to-even == torch.round
+  } else if (MODE == NQ_ROUND_SOFT) {
+    float sig;
+    const float h = fminf(fmaxf(soft_target_raw(av, sig), 0.f), 1.f);
+    x_int = __fadd_rn(floorf(q), h);
+    if (want_reg) {
+      const float u = fabsf(h - 0.5f) * 2.0f;
+      reg += 1.0f - powf(u, reg_b);
+    }
+  } else {
+    x_int = __fadd_rn(floorf(q), av >= 0.f ? 1.f : 0.f);
+  }
+  return fminf(fmaxf(__fadd_rn(x_int, z), 0.f), qmax);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) fakequant_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ delta,
@@ -57,22 +79,7 @@ __global__ void __launch_bounds__(256) fakequant_fwd_kernel(
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = (e / row_len) * d_stride;
     const float d = delta[r], z = zp[r];
-    const float q = __fdiv_rn(x[e], d);  // true fp32 divide
-    float x_int;
-    if (MODE == NQ_ROUND_NEAREST) {
-      x_int = rintf(q);  // half-to-even == torch.round
-    } else if (MODE == NQ_ROUND_SOFT) {
-      float sig;
-      const float h = fminf(fmaxf(soft_target_raw(alpha[e], sig), 0.f), 1.f);
-      x_int = __fadd_rn(floorf(q), h);
-      if (reg_sum != nullptr) {
-        const float u = fabsf(h - 0.5f) * 2.0f;
-        reg += 1.0f - powf(u, reg_b);
-      }
-    } else {
-      x_int = __fadd_rn(floorf(q), alpha[e] >= 0.f ? 1.f : 0.f);
-    }
-    const float c = fminf(fmaxf(__fadd_rn(x_int, z), 0.f), qmax);
+    const float c = fq_fwd_elem<MODE>(x[e], MODE == NQ_ROUND_NEAREST ? 0.f : alpha[e], d, z, qmax, reg_sum != nullptr, reg_b, reg);
     if (codes != nullptr) codes[e] = c;
     if (deq != nullptr) deq[e] = __fmul_rn(__fsub_rn(c, z), d);
   }
@@ -85,6 +92,39 @@ __global__ void __launch_bounds__(256) fakequant_fwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // backward, AdaRound soft: elementwise d_alpha
 // ---------------------------------------------------------------------------------------------
+// one element of d(loss + regulariser)/d(alpha); the last product is an explicit rounding so that fusing the
+// consumer (Adam) behind it cannot change the value
+__device__ __forceinline__ float fq_bwd_soft_elem(float gv, float xv, float av, float d, float z, float qmax, float grad_scale,
+                                                  float reg_w, float reg_b) {
+  float sig;
+  const float hraw = soft_target_raw(av, sig);
+  const bool pass_h = (hraw >= 0.f) && (hraw <= 1.f);  // clamp backward is inclusive
+  const float h = fminf(fmaxf(hraw, 0.f), 1.f);
+  const float v = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(xv, d)), h), z);
+  const bool in_range = (v >= 0.f) && (v <= qmax);
+  float dh = 0.f;
+  if (in_range) dh = gv * grad_scale * d;
+  if (reg_w != 0.f) {
+    const float t = h - 0.5f;
+    const float u = fabsf(t) * 2.0f;
+    const float sgn = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f);
+    // d/dh (1 - u^b) = -b u^(b-1) * 2 sign(h - .5)
+    dh += reg_w * (-reg_b * powf(u, reg_b - 1.0f) * 2.0f * sgn);
+  }
+  return pass_h ? __fmul_rn(dh * (kZeta - kGamma) * sig, 1.0f - sig) : 0.f;
+}
+
+// torch.optim.Adam, single-tensor path (torch/optim/adam.py _single_tensor_adam), one element
+__device__ __forceinline__ void adam_elem(float& pv, float gv, float& mv_io, float& vv_io, float one_minus_b1, float b2,
+                                          float one_minus_b2, float step_size, float bc2_sqrt, float eps) {
+  const float mv = mv_io + one_minus_b1 * (gv - mv_io);  // lerp_
+  const float vv = __fadd_rn(__fmul_rn(vv_io, b2), __fmul_rn(__fmul_rn(gv, gv), one_minus_b2));
+  mv_io = mv;
+  vv_io = vv;
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), bc2_sqrt), eps);
+  pv = pv - step_size * __fdiv_rn(mv, denom);
+}
+
 __global__ void __launch_bounds__(256) fakequant_bwd_soft_kernel(
     const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ alpha,
     const float* __restrict__ delta, const float* __restrict__ zp, int64_t numel, int row_len,
@@ -97,23 +137,7 @@ __global__ void __launch_bounds__(256) fakequant_bwd_soft_kernel(
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = (e / row_len) * d_stride;
-    const float d = delta[r], z = zp[r];
-    float sig;
-    const float hraw = soft_target_raw(alpha[e], sig);
-    const bool pass_h = (hraw >= 0.f) && (hraw <= 1.f);  // clamp backward is inclusive
-    const float h = fminf(fmaxf(hraw, 0.f), 1.f);
-    const float v = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(x[e], d)), h), z);
-    const bool in_range = (v >= 0.f) && (v <= qmax);
-    float dh = 0.f;
-    if (in_range) dh = g[e] * grad_scale * d;
-    if (reg_w != 0.f) {
-      const float t = h - 0.5f;
-      const float u = fabsf(t) * 2.0f;
-      const float sgn = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f);
-      // d/dh (1 - u^b) = -b u^(b-1) * 2 sign(h - .5)
-      dh += reg_w * (-reg_b * powf(u, reg_b - 1.0f) * 2.0f * sgn);
-    }
-    d_alpha[e] = pass_h ? dh * (kZeta - kGamma) * sig * (1.0f - sig) : 0.f;
+    d_alpha[e] = fq_bwd_soft_elem(g[e], x[e], alpha[e], delta[r], zp[r], qmax, grad_scale, reg_w, reg_b);
   }
 }
 
@@ -155,7 +179,6 @@ __global__ void __launch_bounds__(256) adaround_init_alpha_kernel(
   }
 }
 
-// torch.optim.Adam, single-tensor path (torch/optim/adam.py _single_tensor_adam)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    float one_minus_b1, float b2, float one_minus_b2,
@@ -167,13 +190,89 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
-    const float gv = g[e];
-    const float mv = m[e] + one_minus_b1 * (gv - m[e]);              // lerp_
-    const float vv = __fadd_rn(__fmul_rn(v[e], b2), __fmul_rn(__fmul_rn(gv, gv), one_minus_b2));
+    float pv = p[e], mv = m[e], vv = v[e];
+    adam_elem(pv, g[e], mv, vv, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
     m[e] = mv;
     v[e] = vv;
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), bc2_sqrt), eps);
-    p[e] = p[e] - step_size * __fdiv_rn(mv, denom);
+    p[e] = pv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor launches: the decoder has 7 stages x (weight, bias) quantisers of 12 .. 1.6 M elements; one launch
+// each is launch-latency bound (4-5 us per kernel for < 1 us of work).  A block owns MULTI_CHUNK consecutive
+// elements of one tensor; the block -> tensor table travels in the kernel parameters.
+// ---------------------------------------------------------------------------------------------
+constexpr int MULTI_CHUNK = 2048;  // elements per block (256 threads x 8)
+
+struct FqMulti {
+  nq_fq_task t[NQ_MULTI_MAX];
+  int blk_start[NQ_MULTI_MAX + 1];
+  int n;
+  float* reg_sum;
+  float reg_b;
+};
+struct AdaMulti {
+  nq_ada_task t[NQ_MULTI_MAX];
+  int blk_start[NQ_MULTI_MAX + 1];
+  int n;
+  float grad_scale, one_minus_b1, b2, one_minus_b2, eps;
+  const float* hyper;
+};
+
+template <typename M>
+__device__ __forceinline__ int multi_task_of_block(const M& m, int blk) {
+  int t = 0;
+  while (t + 1 < m.n && blk >= m.blk_start[t + 1]) ++t;
+  return t;
+}
+
+__global__ void __launch_bounds__(256) fakequant_fwd_multi_kernel(const __grid_constant__ FqMulti m) {
+  __shared__ float red[32];
+  const int ti = multi_task_of_block(m, blockIdx.x);
+  const nq_fq_task& t = m.t[ti];
+  const int64_t numel = t.rows * t.row_len;
+  const int64_t e0 = (int64_t)(blockIdx.x - m.blk_start[ti]) * MULTI_CHUNK;
+  const int64_t e1 = e0 + MULTI_CHUNK < numel ? e0 + MULTI_CHUNK : numel;
+  const float qmax = (float)((1 << t.n_bits) - 1);
+  const bool want_reg = t.want_reg && m.reg_sum != nullptr && t.mode == NQ_ROUND_SOFT;
+  float reg = 0.f;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int64_t r = t.channel_wise ? e / t.row_len : 0;
+    const float d = t.delta[r], z = t.zero_point[r];
+    const float xv = t.x[e];
+    float c;
+    if (t.mode == NQ_ROUND_NEAREST) c = fq_fwd_elem<NQ_ROUND_NEAREST>(xv, 0.f, d, z, qmax, false, 0.f, reg);
+    else if (t.mode == NQ_ROUND_SOFT) c = fq_fwd_elem<NQ_ROUND_SOFT>(xv, t.alpha[e], d, z, qmax, want_reg, m.reg_b, reg);
+    else c = fq_fwd_elem<NQ_ROUND_HARD>(xv, t.alpha[e], d, z, qmax, false, 0.f, reg);
+    if (t.codes != nullptr) t.codes[e] = c;
+    if (t.deq != nullptr) t.deq[e] = __fmul_rn(__fsub_rn(c, z), d);
+  }
+  if (want_reg) {  // block-uniform
+    reg = block_sum(reg, red);
+    if (threadIdx.x == 0) atomicAdd(m.reg_sum, reg);
+  }
+}
+
+// d_alpha (fakequant_bwd_soft_kernel) and the Adam update of alpha (adam_kernel) in one pass: d_alpha never
+// leaves the registers.  Same element functions as the single-tensor kernels: identical values.
+__global__ void __launch_bounds__(256) adaround_step_multi_kernel(const __grid_constant__ AdaMulti m) {
+  const int ti = multi_task_of_block(m, blockIdx.x);
+  const nq_ada_task& t = m.t[ti];
+  const int64_t numel = t.rows * t.row_len;
+  const int64_t e0 = (int64_t)(blockIdx.x - m.blk_start[ti]) * MULTI_CHUNK;
+  const int64_t e1 = e0 + MULTI_CHUNK < numel ? e0 + MULTI_CHUNK : numel;
+  const float qmax = (float)((1 << t.n_bits) - 1);
+  const float reg_w = t.use_reg ? m.hyper[0] : 0.f, reg_b = t.use_reg ? m.hyper[1] : 0.f;
+  const float step_size = m.hyper[2], bc2_sqrt = m.hyper[3];
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int64_t r = t.channel_wise ? e / t.row_len : 0;
+    float av = t.alpha[e], mv = t.exp_avg[e], vv = t.exp_avg_sq[e];
+    const float gv = fq_bwd_soft_elem(t.g[e], t.x[e], av, t.delta[r], t.zero_point[r], qmax, m.grad_scale, reg_w, reg_b);
+    adam_elem(av, gv, mv, vv, m.one_minus_b1, m.b2, m.one_minus_b2, step_size, bc2_sqrt, m.eps);
+    t.exp_avg[e] = mv;
+    t.exp_avg_sq[e] = vv;
+    t.alpha[e] = av;
   }
 }
 
@@ -307,5 +406,59 @@ extern "C" int nq_adam_step_dev(float* param, const float* grad, float* exp_avg,
   adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1),
                                                           (float)beta2, (float)(1.0 - beta2), 0.f, 1.f, (float)eps, hyper_dev);
   NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_fakequant_fwd_multi(const nq_fq_task* tasks, int n_tasks, float* reg_sum, float reg_b, void* stream) {
+  if (!tasks || n_tasks <= 0) return NQ_ERR_BAD_ARG;
+  for (int i0 = 0; i0 < n_tasks; i0 += NQ_MULTI_MAX) {
+    FqMulti m{};
+    m.n = n_tasks - i0 < NQ_MULTI_MAX ? n_tasks - i0 : NQ_MULTI_MAX;
+    m.reg_sum = reg_sum;
+    m.reg_b = reg_b;
+    int blocks = 0;
+    for (int i = 0; i < m.n; ++i) {
+      const nq_fq_task& t = tasks[i0 + i];
+      if (!t.x || !t.delta || !t.zero_point || t.rows <= 0 || t.row_len <= 0) return NQ_ERR_BAD_ARG;
+      if (t.n_bits < 2 || t.n_bits > 8 || t.mode < NQ_ROUND_NEAREST || t.mode > NQ_ROUND_HARD) return NQ_ERR_BAD_ARG;
+      if (t.mode != NQ_ROUND_NEAREST && !t.alpha) return NQ_ERR_BAD_ARG;
+      if (t.row_len > 0x7fffffffLL) return NQ_ERR_BAD_SHAPE;
+      m.t[i] = t;
+      m.blk_start[i] = blocks;
+      blocks += (int)((t.rows * t.row_len + MULTI_CHUNK - 1) / MULTI_CHUNK);
+    }
+    m.blk_start[m.n] = blocks;
+    fakequant_fwd_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(m);
+    NQ_LAUNCH_CHECK();
+  }
+  return NQ_OK;
+}
+
+extern "C" int nq_adaround_step_multi(const nq_ada_task* tasks, int n_tasks, float grad_scale, double beta1, double beta2,
+                                      double eps, const float* hyper_dev, void* stream) {
+  if (!tasks || n_tasks <= 0 || !hyper_dev) return NQ_ERR_BAD_ARG;
+  for (int i0 = 0; i0 < n_tasks; i0 += NQ_MULTI_MAX) {
+    AdaMulti m{};
+    m.n = n_tasks - i0 < NQ_MULTI_MAX ? n_tasks - i0 : NQ_MULTI_MAX;
+    m.grad_scale = grad_scale;
+    m.one_minus_b1 = (float)(1.0 - beta1);
+    m.b2 = (float)beta2;
+    m.one_minus_b2 = (float)(1.0 - beta2);
+    m.eps = (float)eps;
+    m.hyper = hyper_dev;
+    int blocks = 0;
+    for (int i = 0; i < m.n; ++i) {
+      const nq_ada_task& t = tasks[i0 + i];
+      if (!t.g || !t.x || !t.alpha || !t.delta || !t.zero_point || !t.exp_avg || !t.exp_avg_sq) return NQ_ERR_BAD_ARG;
+      if (t.rows <= 0 || t.row_len <= 0 || t.n_bits < 2 || t.n_bits > 8) return NQ_ERR_BAD_ARG;
+      if (t.row_len > 0x7fffffffLL) return NQ_ERR_BAD_SHAPE;
+      m.t[i] = t;
+      m.blk_start[i] = blocks;
+      blocks += (int)((t.rows * t.row_len + MULTI_CHUNK - 1) / MULTI_CHUNK);
+    }
+    m.blk_start[m.n] = blocks;
+    adaround_step_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(m);
+    NQ_LAUNCH_CHECK();
+  }
   return NQ_OK;
 }

@@ -385,18 +385,26 @@ class DecoderEngine:
             self.reg_sum.zero_()
         if not hasattr(self, "_fwd_bpl"):
             self._fwd_bpl = [2] * len(self.stages)
+        if self.mode != "off":
+            # every weight and bias quantiser of the decoder in one multi-tensor launch
+            if self.mode == "uaq":
+                mw = mb = ROUND_NEAREST
+            else:
+                mw = ROUND_SOFT if self.soft_w else ROUND_HARD
+                mb = ROUND_SOFT if self.soft_b else ROUND_HARD
+            tasks = []
+            for s, (_, _, _, deq_w, deq_b) in zip(self.stages, self._packed):
+                tasks.append(self._fq_task(s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, mw, s.codes_w, deq_w,
+                                           reg_b is not None and mw == ROUND_SOFT))
+                tasks.append(self._fq_task(s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, mb, s.codes_b, deq_b, False))
+            arr = (L.FqTask * len(tasks))(*tasks)
+            L.check(L.lib.nq_fakequant_fwd_multi(arr, len(tasks), L.ptr(self.reg_sum) if reg_b is not None else None,
+                                                 float(reg_b or 0.0), st), "nq_fakequant_fwd_multi")
+            self.launches += (len(tasks) + L.MULTI_MAX - 1) // L.MULTI_MAX
         for i, (s, d, (wk, wt, bp, deq_w, deq_b)) in enumerate(zip(self.stages, p.desc, self._packed)):
             if self.mode == "off":
                 w_for_conv, b_for_conv, cin_src = s.weight, s.bias, s.geom.cin
             else:
-                if self.mode == "uaq":
-                    mw = mb = ROUND_NEAREST
-                else:
-                    mw = ROUND_SOFT if self.soft_w else ROUND_HARD
-                    mb = ROUND_SOFT if self.soft_b else ROUND_HARD
-                self._fq(s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, mw, s.codes_w, deq_w,
-                         self.reg_sum if (reg_b is not None and mw == ROUND_SOFT) else None, reg_b or 0.0)
-                self._fq(s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, mb, s.codes_b, deq_b, None, 0.0)
                 if s.hadamard:  # quant_layer.py:71: rotate back, keep the first C_in channels
                     L.fwht_channel(deq_w, out=deq_w)
                     self.launches += 1
@@ -443,6 +451,13 @@ class DecoderEngine:
                 self.launches += 1
         self._weights_valid = True
         self._wt_valid = need_wt
+
+    @staticmethod
+    def _fq_task(x, alpha, delta, zp, n_bits, mode, codes, deq, want_reg) -> "L.FqTask":
+        cw = delta.numel() > 1
+        rows, row_len = (delta.numel(), x.numel() // delta.numel()) if cw else (1, x.numel())
+        return L.FqTask(L.ptr(x), L.ptr(alpha) if mode != ROUND_NEAREST else None, L.ptr(delta), L.ptr(zp), L.ptr(codes),
+                        L.ptr(deq), rows, row_len, int(cw), n_bits, mode, int(bool(want_reg)))
 
     def _fq(self, x, alpha, delta, zp, n_bits, mode, codes, deq, reg_sum, reg_b):
         rows, row_len, d_stride = (delta.numel(), x.numel() // delta.numel(), 1) if delta.numel() > 1 else (1, x.numel(), 0)
@@ -661,6 +676,35 @@ class DecoderEngine:
                 raise L.NqError("param_grads needs quantisation on")
             self.launches += 2
         return out
+
+
+def adaround_step_multi(eng: "DecoderEngine", opt: "AdamState", hyper: torch.Tensor, grad_scale: float = 1.0,
+                        beta1=0.9, beta2=0.999, eps=1e-8) -> int:
+    """d(loss + regulariser)/d alpha and Adam's update of alpha for every quantiser of the decoder in ONE launch
+    (the graph-replayed form of param_grads() + AdamState.step_dev()).  `opt.params` must be the engine's
+    [alpha_w, alpha_b] per stage, in order (CalibrationLoop.run_phase2)."""
+    _, views = eng._grad_buffers()
+    tasks = []
+    k = 0
+    for i, s in enumerate(eng.stages):
+        gw, gb = views[i]
+        if s.hadamard:  # transpose of the (symmetric, orthonormal) rotation is the rotation
+            L.fwht_channel(gw, out=gw)
+            eng.launches += 1
+        for g_, x_, a_, d_, z_, use_reg in ((gw, s.w_src, s.alpha_w, s.delta_w, s.zp_w, 1), (gb, s.bias, s.alpha_b, s.delta_b, s.zp_b, 0)):
+            if opt.params[k] is not a_:
+                raise L.NqError("adaround_step_multi: optimiser parameters are not the engine's alpha tensors")
+            cw = d_.numel() > 1
+            rows, row_len = (d_.numel(), x_.numel() // d_.numel()) if cw else (1, x_.numel())
+            tasks.append(L.AdaTask(L.ptr(g_), L.ptr(x_), L.ptr(a_), L.ptr(d_), L.ptr(z_), L.ptr(opt.m[k]), L.ptr(opt.v[k]),
+                                   rows, row_len, int(cw), s.n_bits, use_reg, 0))
+            k += 1
+    arr = (L.AdaTask * len(tasks))(*tasks)
+    L.check(L.lib.nq_adaround_step_multi(arr, len(tasks), float(grad_scale), beta1, beta2, eps, L.ptr(hyper), L.stream()),
+            "nq_adaround_step_multi")
+    n = (len(tasks) + L.MULTI_MAX - 1) // L.MULTI_MAX
+    eng.launches += n
+    return n
 
 
 class AdamState:

@@ -386,3 +386,51 @@ def test_saved_activation_derivative_equals_recomputed(nq, monkeypatch, conv_pat
     assert torch.equal(outs["1"][0], outs["0"][0])
     for a, b in zip(outs["1"][1], outs["0"][1]):
         assert (a - b).abs().max() <= 1e-5 * b.abs().max() + 1e-12
+
+
+def test_multi_tensor_quantiser_launches_equal_single_tensor(nq):
+    """nq_fakequant_fwd_multi and nq_adaround_step_multi against the single-tensor entry points they batch:
+    bit-identical outputs on ragged sizes (a 3-element bias, a tensor that is not a multiple of the block chunk,
+    per-tensor and channel-wise scales, 20 tensors = two launches)."""
+    import ctypes as C
+    L = nq._lib
+    torch.manual_seed(5)
+    shapes = [(3,), (16, 3, 3, 3), (7, 300), (64, 48, 5, 5), (1, 2049), (5,), (33, 7)] * 3
+    shapes = shapes[:20]
+    hyper = dev(torch.tensor([0.01, 7.5, 0.003 / (1 - 0.9 ** 3), (1 - 0.999 ** 3) ** 0.5]))
+    single, multi, fq_tasks, ada_tasks, keep = [], [], [], [], []
+    for k, shp in enumerate(shapes):
+        x = dev(torch.randn(shp))
+        cw = len(shp) > 1 and k % 2 == 0
+        bits = 2 + k % 7
+        rows, row_len = (shp[0], x.numel() // shp[0]) if cw else (1, x.numel())
+        delta = dev(torch.rand(rows) * 0.05 + 0.01)
+        zp = dev(torch.randint(0, 2 ** bits, (rows,)).float())
+        alpha = dev(torch.randn(shp))
+        g = dev(torch.randn(shp))
+        mode = k % 3  # nq_round_mode: nearest, soft, hard
+        # single-tensor reference
+        c1, d1 = torch.empty_like(x), torch.empty_like(x)
+        L.check(L.lib.nq_fakequant_fwd(L.ptr(x), L.ptr(alpha), L.ptr(delta), L.ptr(zp), rows, row_len, int(cw), bits, mode,
+                                       L.ptr(c1), L.ptr(d1), None, 0.0, L.stream()))
+        a1, m1, v1 = alpha.clone(), dev(torch.rand(shp) * 1e-3), dev(torch.rand(shp) * 1e-6)
+        a2, m2, v2 = a1.clone(), m1.clone(), v1.clone()
+        da = torch.empty_like(x)
+        L.check(L.lib.nq_fakequant_bwd_soft_dev(L.ptr(g), L.ptr(x), L.ptr(a1), L.ptr(delta), L.ptr(zp), rows, row_len, int(cw), bits,
+                                                1.0, k % 2, L.ptr(hyper), L.ptr(da), L.stream()))
+        L.check(L.lib.nq_adam_step_dev(L.ptr(a1), L.ptr(da), L.ptr(m1), L.ptr(v1), x.numel(), 0.9, 0.999, 1e-8, L.ptr(hyper), L.stream()))
+        single.append((c1, d1, a1, m1, v1))
+        c2, d2 = torch.empty_like(x), torch.empty_like(x)
+        fq_tasks.append(L.FqTask(L.ptr(x), L.ptr(alpha), L.ptr(delta), L.ptr(zp), L.ptr(c2), L.ptr(d2), rows, row_len, int(cw), bits, mode, 0))
+        ada_tasks.append(L.AdaTask(L.ptr(g), L.ptr(x), L.ptr(a2), L.ptr(delta), L.ptr(zp), L.ptr(m2), L.ptr(v2), rows, row_len, int(cw),
+                                   bits, k % 2, 0))
+        multi.append((c2, d2, a2, m2, v2))
+        keep.append((x, delta, zp, alpha, g))
+    L.check(L.lib.nq_fakequant_fwd_multi((L.FqTask * len(fq_tasks))(*fq_tasks), len(fq_tasks), None, 0.0, L.stream()))
+    L.check(L.lib.nq_adaround_step_multi((L.AdaTask * len(ada_tasks))(*ada_tasks), len(ada_tasks), 1.0, 0.9, 0.999, 1e-8,
+                                         L.ptr(hyper), L.stream()))
+    torch.cuda.synchronize()
+    for s_, m_ in zip(single, multi):
+        for a, b in zip(s_, m_):
+            assert torch.equal(a, b)
+    assert L.lib.nq_fakequant_fwd_multi(None, 3, None, 0.0, L.stream()) != 0
