@@ -252,7 +252,8 @@ typedef struct nq_tc_plan {
   int32_t cluster;             /* CTAs per cluster sharing each weight stage by TMA multicast (caller may set 1, 2, 4) */
   int32_t mt;                  /* 16x8 pixel tiles per CTA step sharing each weight stage (1, or 2 when NT <= 128) */
   int32_t bcat;                /* 1: weight planes packed side by side per k-group, 2 MMAs per K step instead of 3 */
-  int32_t reserved;
+  int32_t n_abuf, n_acc;       /* ring depths: activation buffers in shared memory, accumulator slots in TMEM */
+  int32_t acc_stride;          /* TMEM columns per accumulator slot */
   int64_t wpk_bytes;           /* size of the packed weight buffer the caller allocates */
 } nq_tc_plan;
 

@@ -39,7 +39,8 @@ constexpr int TC_THREADS = 640;
 constexpr int TC_LOADERS = 256;  // warps 8-15
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 16;
-constexpr int TC_HDR_BYTES = 512;     // barriers (8 + 2 * TC_MAX_BSTAGES) + TMEM pointer
+constexpr int TC_MAX_RING = 8;        // activation buffers / TMEM accumulator slots
+constexpr int TC_HDR_BYTES = 1024;    // barriers (4 * TC_MAX_RING + 2 * TC_MAX_BSTAGES) + TMEM pointer
 constexpr int EPI_ROW = 20;            // floats per staged epilogue row (16 + 4 pad: conflict-free 16-byte accesses)
 constexpr int EPI_STAGE_BYTES = 8 * 32 * EPI_ROW * 4;  // 8 epilogue warps
 
@@ -71,6 +72,8 @@ struct TcParams {
   int epi_stage_off;     // byte offset of the epilogue staging tiles in shared memory
   int cs;                // CTAs per cluster sharing every weight stage by TMA multicast (1, 2 or 4)
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
+  int n_abuf, n_acc;     // activation buffers in shared memory, accumulator slots in TMEM (rings, 2 .. TC_MAX_RING)
+  int acc_stride, sub_stride;  // TMEM columns per accumulator slot / between the pixel tiles of a slot
   int bcat;              // weight stage stores the planes side by side per k-group ([k-group][plane][n][8]): A_hi x [B_hi | B_lo]
                          // is ONE MMA of 2 * nt columns (hi*hi in columns [0, nt), hi*lo in [nt, 2 nt)) + A_lo x B_hi
   int mt;                // 16x8 pixel tiles (side by side in x) per CTA step: they share every weight stage (NT <= 256 / mt)
@@ -270,11 +273,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
   // barrier indices
-  const uint32_t A_FULL = bar0 + 0 * 8, A_EMPTY = bar0 + 2 * 8, T_FULL = bar0 + 4 * 8, T_EMPTY = bar0 + 6 * 8;
-  const uint32_t B_FULL = bar0 + 8 * 8, B_EMPTY = bar0 + (8 + TC_MAX_BSTAGES) * 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (8 + 2 * TC_MAX_BSTAGES) * 8);
+  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + TC_MAX_RING * 8, T_FULL = bar0 + 2 * TC_MAX_RING * 8,
+                 T_EMPTY = bar0 + 3 * TC_MAX_RING * 8;
+  const uint32_t B_FULL = bar0 + 4 * TC_MAX_RING * 8, B_EMPTY = B_FULL + TC_MAX_BSTAGES * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (4 * TC_MAX_RING + 2 * TC_MAX_BSTAGES) * 8);
   const uint32_t a_base = smem_u32(smem + TC_HDR_BYTES);
-  const uint32_t b_base = a_base + 2 * p.a_buf_bytes;
+  const uint32_t b_base = a_base + p.n_abuf * p.a_buf_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = p.cs > 1 ? (int)cluster_rank() : 0;
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint16_t mc_mask = (uint16_t)((1u << p.cs) - 1);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < TC_MAX_RING; ++i) {
       mbar_init(A_FULL + i * 8, TC_LOADERS);  // one deferred arrival per loader thread
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // alone issues.  Descriptors differ only in their 14-bit start-address field: 32-bit adds per MMA.
     // This warp has the highest id of its scheduler partition (the arbiter favours high ids).
     const bool leader = elect_one();
-    uint32_t uc = 0, tcnt = 0;
+    uint32_t abuf = 0, aph = 0, acc = 0, tph = 0;  // activation-buffer / accumulator ring positions and phases
     uint32_t bs = 0, bph = 0;  // weight-stage ring position and phase
     const int nsb_full = p.KC / p.SBC;
     const uint32_t a_hi32 = ((uint32_t)(p.PW * 16) >> 4) | (1u << 14);  // SBO, descriptor version 1
@@ -355,13 +359,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int k16_per_stage = p.SBC / 16;
     const uint32_t row_skip16 = (uint32_t)(p.PW - p.ks + 1);
     const int passes = (p.a_planes == 2 ? 1 : 0) | (p.b_planes == 2 ? 2 : 0);
-    for (int t = cluster_id; t < p.total_groups; t += n_clusters, ++tcnt) {
+    for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
-      const uint32_t acc = tcnt & 1;
-      mbar_wait(T_EMPTY + acc * 8, ((tcnt >> 1) & 1) ^ 1);
+      mbar_wait(T_EMPTY + acc * 8, tph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
-      const uint32_t d_tmem1 = d_tmem + 128;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
+      const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+      const uint32_t d_tmem1 = d_tmem + p.sub_stride;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
       constexpr bool two = MT == 2;
       const uint32_t idesc = make_idesc(tc.nt);
       const uint32_t idesc2 = make_idesc(2 * tc.nt);  // bcat: both weight planes as one operand
@@ -369,9 +372,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t b_plane16 = (uint32_t)(tc.nt * p.SBC * 2) >> 4;
       const uint32_t b_step16 = 2 * b_lbo16;
       uint32_t accum = 0;
-      for (int cb = 0; cb < ncb; ++cb, ++uc) {
-        const uint32_t abuf = uc & 1;
-        mbar_wait(A_FULL + abuf * 8, (uc >> 1) & 1);
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(A_FULL + abuf * 8, aph);
         fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
         tc_fence_after();
         const uint32_t a_buf16 = (((a_base + abuf * p.a_buf_bytes) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
@@ -461,22 +463,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (++kw == p.ks) { kw = 0; a_tap += row_skip16; } else { ++a_tap; }
         }
         if (leader) umma_commit(A_EMPTY + abuf * 8);
+        if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
       }
       if (leader) umma_commit(T_FULL + acc * 8);
+      if (++acc == (uint32_t)p.n_acc) { acc = 0; tph ^= 1; }
     }
   } else if (warp >= 8 && warp < 16) {
     // ===================== activation loaders: split-bf16 NHWC -> halo tile, 16-byte cp.async =====================
     const int ltid = threadIdx.x - 8 * 32;
     const int npix = p.PW * p.PH;
-    uint32_t uc = 0;
+    uint32_t abuf = 0, aph = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
       const uint8_t* img = p.in + (size_t)tc.img * p.h * p.w * p.in_stride * 2;
-      for (int cb = 0; cb < ncb; ++cb, ++uc) {
-        const uint32_t abuf = uc & 1;
+      for (int cb = 0; cb < ncb; ++cb) {
         const int c0 = cb * p.KC;
         const int ncg = min(p.KC, p.C - c0) >> 3;
-        mbar_wait(A_EMPTY + abuf * 8, ((uc >> 1) & 1) ^ 1);
+        mbar_wait(A_EMPTY + abuf * 8, aph ^ 1);
         const uint32_t dst = a_base + abuf * p.a_buf_bytes;
         // lanes 2k / 2k+1 copy the two 16-byte halves (adjacent channel groups) of one 32-byte sector of the
         // same pixel; consecutive lane pairs take consecutive pixels
@@ -501,6 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           while (pix >= npix) { pix -= npix; ++cpi; }
         }
         cp_async_arrive(A_FULL + abuf * 8);
+        if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
       }
     }
   } else if (warp < 8) {
@@ -515,11 +519,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float* stg = reinterpret_cast<float*>(smem + p.epi_stage_off) + warp * (32 * EPI_ROW);
     const int qd = lane & 3;         // 4-channel quad of the chunk this lane stores
     const int rsub = lane >> 2;      // row (pixel) within each group of 8 rows
-    uint32_t tcnt = 0;
+    uint32_t acc_next = 0, tph_next = 0;
     float head_loss_acc = 0.f;
-    for (int t = cluster_id; t < p.total_groups; t += n_clusters, ++tcnt) {
+    for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
-      const uint32_t acc = tcnt & 1;
+      const uint32_t acc = acc_next, tph = tph_next;
+      if (++acc_next == (uint32_t)p.n_acc) { acc_next = 0; tph_next ^= 1; }
       // the four pixels (one per 8-row group) this lane stores: m = q*32 + it*8 + rsub, tile row m>>3 = q*4 + it
       size_t row_base[4], zrow[4];
       bool valid[4];
@@ -552,11 +557,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int c = 0; c < 3; ++c) tg[c] = __ldg(p.head_target + o + c * plane);
         }
-        mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
+        mbar_wait(T_FULL + acc * 8, tph);
         tc_fence_after();
         if (half == 0) {
           uint32_t v[16];
-          tmem_ld16(tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld16(tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
           if (ok) {
             float gr[3] = {0.f, 0.f, 0.f};
@@ -607,9 +612,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
         continue;
       }
-      mbar_wait(T_FULL + acc * 8, (tcnt >> 1) & 1);
+      mbar_wait(T_FULL + acc * 8, tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + sub * 128 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * p.acc_stride + sub * p.sub_stride + ((uint32_t)(q * 32) << 16);
       for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
@@ -849,7 +854,6 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
     if (atoi(e) == 0) pl->bcat = 0;
     else if (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256) pl->bcat = 1;
   }
-  pl->reserved = 0;
   const int tile_w = TILE_W * pl->mt;
   pl->PW = tile_w + d->ksize - 1;
   pl->PH = TILE_H + d->ksize - 1;
@@ -884,12 +888,36 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
   pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
   pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes;
-  const int budget = 227 * 1024 - TC_HDR_BYTES - EPI_STAGE_BYTES - 2 * pl->a_buf_bytes;
+  // Ring depths: as many activation buffers (<= 8) as fit next to ~48 KB of weight stages, and as many accumulator
+  // slots as the 512 TMEM columns hold, so that several short-K tiles can be in flight.
+  const int total = 227 * 1024 - TC_HDR_BYTES - EPI_STAGE_BYTES;
+  int nst_min = 48 * 1024 / pl->b_stage_bytes;
+  if (nst_min < 3) nst_min = 3;
+  if (nst_min > TC_MAX_BSTAGES) nst_min = TC_MAX_BSTAGES;
+  int n_abuf = (total - nst_min * pl->b_stage_bytes) / pl->a_buf_bytes;
+  if (n_abuf > TC_MAX_RING) n_abuf = TC_MAX_RING;
+  if (n_abuf < 2) n_abuf = 2;
+  if (const char* e = getenv("NQ_TC_ABUF")) {  // tuning override
+    const int v = atoi(e);
+    if (v >= 2 && v <= TC_MAX_RING && total - v * pl->a_buf_bytes >= 2 * pl->b_stage_bytes) n_abuf = v;
+  }
+  pl->n_abuf = n_abuf;
+  const int budget = total - n_abuf * pl->a_buf_bytes;
   int nst = budget / pl->b_stage_bytes;
   if (nst > TC_MAX_BSTAGES) nst = TC_MAX_BSTAGES;
   if (nst < 2) return NQ_ERR_UNSUPPORTED;
   pl->n_bstages = nst;
-  pl->smem_bytes = TC_HDR_BYTES + 2 * pl->a_buf_bytes + nst * pl->b_stage_bytes + EPI_STAGE_BYTES;
+  pl->smem_bytes = TC_HDR_BYTES + n_abuf * pl->a_buf_bytes + nst * pl->b_stage_bytes + EPI_STAGE_BYTES;
+  int sub_cols = pl->NT * (pl->bcat ? 2 : 1), sub_stride = 32;
+  while (sub_stride < sub_cols) sub_stride *= 2;
+  pl->acc_stride = sub_stride * pl->mt;
+  pl->n_acc = 512 / pl->acc_stride;
+  if (pl->n_acc > TC_MAX_RING) pl->n_acc = TC_MAX_RING;
+  if (const char* e = getenv("NQ_TC_NACC")) {  // tuning override
+    const int v = atoi(e);
+    if (v >= 2 && v <= pl->n_acc) pl->n_acc = v;
+  }
+  if (pl->n_acc < 2) return NQ_ERR_UNSUPPORTED;
   pl->tiles_x = (d->w + tile_w - 1) / tile_w;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
@@ -950,11 +978,15 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.N = pl->N; p.NT = pl->NT; p.KC = pl->KC; p.SBC = pl->SBC; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_n = pl->tiles_n; p.total_tiles = pl->total_tiles;
   p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS; p.mt = pl->mt; p.bcat = pl->bcat;
+  p.n_abuf = pl->n_abuf; p.n_acc = pl->n_acc; p.acc_stride = pl->acc_stride; p.sub_stride = pl->acc_stride / pl->mt;
+  if (p.n_abuf < 2 || p.n_abuf > TC_MAX_RING || p.n_acc < 2 || p.n_acc > TC_MAX_RING || p.n_acc * p.acc_stride > 512 ||
+      p.sub_stride < pl->NT * (pl->bcat ? 2 : 1))
+    return NQ_ERR_BAD_ARG;
   if (p.mt < 1 || p.mt > 2 || (p.mt == 2 && (pl->NT > 128 || p.epi == 2))) return NQ_ERR_BAD_ARG;
   if (p.bcat && (p.epi == 2 || pl->a_planes != 2 || pl->b_planes != 2 || 2 * pl->NT * pl->mt > 256)) return NQ_ERR_BAD_ARG;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
-  p.epi_stage_off = TC_HDR_BYTES + 2 * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
+  p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
   void (*kern)(const TcParams) = p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1> : conv_tc_kernel<2, 0>)
                                             : (p.bcat ? conv_tc_kernel<1, 1> : conv_tc_kernel<1, 0>);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -101,3 +101,31 @@ def test_tc_plans_fit_for_every_workload():
                 assert d.ksize * wp.ncg_c + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
                 assert wp.msplit * wp.ncg_c >= wp.ncg and (wp.msplit - 1) * wp.ncg_c < wp.ncg
                 assert wp.psplits * wp.nsplits * wp.khg * wp.msplit <= max(148, wp.nsplits * wp.khg * wp.msplit)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """Every struct the Python side mirrors has the size and trailing-field offset the C header gives it
+    (compiled here with gcc: the header is plain C)."""
+    import ctypes as C
+    import subprocess
+    from neuroquant_b200 import _lib as L
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "neuroquant_b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu\\n", sizeof(nq_conv_desc), offsetof(nq_conv_desc, act));\n'
+        '  printf("%zu %zu\\n", sizeof(nq_tc_plan), offsetof(nq_tc_plan, wpk_bytes));\n'
+        '  printf("%zu %zu\\n", sizeof(nq_tc_wgrad_plan), offsetof(nq_tc_wgrad_plan, workspace_floats));\n'
+        '  printf("%zu %zu\\n", sizeof(nq_fq_task), offsetof(nq_fq_task, want_reg));\n'
+        '  printf("%zu %zu\\n", sizeof(nq_ada_task), offsetof(nq_ada_task, use_reg));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [tuple(int(v) for v in ln.split()) for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()]
+    want = [(C.sizeof(L.ConvDesc), L.ConvDesc.act.offset),
+            (C.sizeof(L.TcPlan), L.TcPlan.wpk_bytes.offset),
+            (C.sizeof(L.TcWgradPlan), L.TcWgradPlan.workspace_floats.offset),
+            (C.sizeof(L.FqTask), L.FqTask.want_reg.offset),
+            (C.sizeof(L.AdaTask), L.AdaTask.use_reg.offset)]
+    assert got == want
