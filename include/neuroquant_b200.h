@@ -254,6 +254,8 @@ typedef struct nq_tc_plan {
   int32_t bcat;                /* 1: weight planes packed side by side per k-group, 2 MMAs per K step instead of 3 */
   int32_t n_abuf, n_acc;       /* ring depths: activation buffers in shared memory, accumulator slots in TMEM */
   int32_t acc_stride;          /* TMEM columns per accumulator slot */
+  int32_t n_epi;               /* epilogue warps (8 or 12 of the 16 worker warps; the rest load activations) */
+  int32_t resident;            /* 1: all weight stages of a tile fit the ring; loaded once per CTA */
   int64_t wpk_bytes;           /* size of the packed weight buffer the caller allocates */
 } nq_tc_plan;
 

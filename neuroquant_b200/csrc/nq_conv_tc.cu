@@ -26,7 +26,8 @@
 //     no conversion, no register staging, the copies of a whole halo tile are in flight at once and
 //     complete on an mbarrier (cp.async.mbarrier.arrive.noinc).
 //
-// Warp roles (640 threads): warps 0-7 epilogue (TMEM -> registers -> global), warps 8-15 activation loaders
+// Warp roles (640 threads): warps 0..n_epi-1 epilogue (TMEM -> registers -> global; n_epi = 8, or 12 for short-K
+// stages whose epilogue is the longest role), warps n_epi..15 activation loaders
 // (fp32 -> bf16 hi/lo), warp 16 weight-stage producer, warp 17 MMA issuer, warp 18 TMEM allocator.
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -36,13 +37,13 @@
 namespace nq {
 
 constexpr int TC_THREADS = 640;
-constexpr int TC_LOADERS = 256;  // warps 8-15
+constexpr int TC_WORK_WARPS = 16;  // warps 0-15: n_epi epilogue warps (8 or 12), the rest load activations
 constexpr int TILE_H = 16, TILE_W = 8;  // 128 output pixels per tile (GEMM M)
 constexpr int TC_MAX_BSTAGES = 16;
 constexpr int TC_MAX_RING = 8;        // activation buffers / TMEM accumulator slots
 constexpr int TC_HDR_BYTES = 1024;    // barriers (4 * TC_MAX_RING + 2 * TC_MAX_BSTAGES) + TMEM pointer
 constexpr int EPI_ROW = 20;            // floats per staged epilogue row (16 + 4 pad: conflict-free 16-byte accesses)
-constexpr int EPI_STAGE_BYTES = 8 * 32 * EPI_ROW * 4;  // 8 epilogue warps
+constexpr int EPI_STAGE_BYTES = 12 * 32 * EPI_ROW * 4;  // up to 12 epilogue warps
 
 struct TcParams {
   const uint8_t* in;     // split-bf16 input: plane 0 (hi) then plane 1 (lo), each (n, h, w, in_stride) bf16
@@ -74,6 +75,8 @@ struct TcParams {
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
   int n_abuf, n_acc;     // activation buffers in shared memory, accumulator slots in TMEM (rings, 2 .. TC_MAX_RING)
   int acc_stride, sub_stride;  // TMEM columns per accumulator slot / between the pixel tiles of a slot
+  int resident;          // 1: all weight stages of a tile fit the ring and stay there: loaded once per CTA, never released
+  int n_epi;             // epilogue warps (8, or 12 for short-K stages whose epilogue binds); loaders = 16 - n_epi warps
   int bcat;              // weight stage stores the planes side by side per k-group ([k-group][plane][n][8]): A_hi x [B_hi | B_lo]
                          // is ONE MMA of 2 * nt columns (hi*hi in columns [0, nt), hi*lo in [nt, 2 nt)) + A_lo x B_hi
   int mt;                // 16x8 pixel tiles (side by side in x) per CTA step: they share every weight stage (NT <= 256 / mt)
@@ -265,8 +268,9 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, in
   return c;
 }
 
-// MT / BCAT are compile-time copies of TcParams::mt / bcat: the common (1, 0) variant carries none of their code.
-template <int MT, int BCAT>
+// MT / BCAT / RES are compile-time copies of TcParams::mt / bcat / resident: the common (1, 0, 0) variant carries
+// none of their code.
+template <int MT, int BCAT, int RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // [0, TC_HDR_BYTES): barriers + tmem pointer; then A buffers, then B stages
@@ -287,10 +291,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_MAX_RING; ++i) {
-      mbar_init(A_FULL + i * 8, TC_LOADERS);  // one deferred arrival per loader thread
+      mbar_init(A_FULL + i * 8, (TC_WORK_WARPS - p.n_epi) * 32);  // one deferred arrival per loader thread
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
-      mbar_init(T_EMPTY + i * 8, 8);
+      mbar_init(T_EMPTY + i * 8, p.n_epi);
     }
     for (int i = 0; i < p.n_bstages; ++i) {
       mbar_init(B_FULL + i * 8, 1);
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               src += stage_bytes;
             }
         }
+        if (RES) break;  // the ring now holds every stage of the (single) N tile for the rest of the kernel
       }
     }
   } else if (warp == 17) {
@@ -363,6 +368,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const TileCoord tc = tile_coord(p, t, rank);
       mbar_wait(T_EMPTY + acc * 8, tph ^ 1);
       tc_fence_after();
+      if (RES) bs = 0;  // stage i of the tile lives in ring slot i
+      const bool b_wait = !RES || t == cluster_id;
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       const uint32_t d_tmem1 = d_tmem + p.sub_stride;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
       constexpr bool two = MT == 2;
@@ -383,8 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int tap = 0; tap < taps; ++tap) {
           uint32_t a_lo = a_tap;
           for (int sb = 0; sb < nsb; ++sb) {
-            mbar_wait(B_FULL + bs * 8, bph);
-            tc_fence_after();
+            if (b_wait) {
+              mbar_wait(B_FULL + bs * 8, bph);
+              tc_fence_after();
+            }
             uint32_t b_lo = (((b_base + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
             // uniform loops; only the MMA itself is predicated on the leader lane, so that ptxas keeps the
             // descriptors in uniform registers instead of broadcasting them per instruction
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             }
             // stage free once these MMAs have read it -- signalled to every CTA that multicasts into it
-            if (leader) {
+            if (leader && !RES) {
               if (p.cs == 1) umma_commit(B_EMPTY + bs * 8);
               else umma_commit_mc(B_EMPTY + bs * 8, mc_mask);
             }
@@ -468,9 +477,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (leader) umma_commit(T_FULL + acc * 8);
       if (++acc == (uint32_t)p.n_acc) { acc = 0; tph ^= 1; }
     }
-  } else if (warp >= 8 && warp < 16) {
+  } else if (warp >= p.n_epi && warp < TC_WORK_WARPS) {
     // ===================== activation loaders: split-bf16 NHWC -> halo tile, 16-byte cp.async =====================
-    const int ltid = threadIdx.x - 8 * 32;
+    const int ltid = threadIdx.x - p.n_epi * 32;
+    const int nload = (TC_WORK_WARPS - p.n_epi) * 32;
     const int npix = p.PW * p.PH;
     uint32_t abuf = 0, aph = 0;
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int cgp = ltid & 1;
         int j = ltid >> 1;
         int cpi = j / npix, pix = j - cpi * npix;
-        for (; j < tasks; j += TC_LOADERS / 2) {
+        for (; j < tasks; j += nload / 2) {
           const int cgi = 2 * cpi + cgp;
           if (cgi < ncg) {
             const int py = pix / p.PW, px = pix - py * p.PW;
@@ -500,14 +510,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             cp_async16(d, src, ok ? 16u : 0u);
             if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
           }
-          pix += TC_LOADERS / 2;
+          pix += nload / 2;
           while (pix >= npix) { pix -= npix; ++cpi; }
         }
         cp_async_arrive(A_FULL + abuf * 8);
         if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < p.n_epi) {
     // ===================== epilogue: TMEM -> registers -> smem transpose -> global (8 warps) =====================
     // Two warps per TMEM lane quarter; they take alternate 16-column chunks.  tcgen05.ld hands every lane one
     // ROW (pixel) of the chunk; storing from that layout touches 32 different sectors per instruction with 8-16
@@ -615,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(T_FULL + acc * 8, tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + sub * p.sub_stride + ((uint32_t)(q * 32) << 16);
-      for (int c0 = half * 16; c0 < tc.nt; c0 += 32) {
+      for (int c0 = half * 16; c0 < tc.nt; c0 += (p.n_epi >> 2) * 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         if (BCAT) {  // hi*lo partial sums live nt columns further
@@ -918,6 +928,15 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
     if (v >= 2 && v <= pl->n_acc) pl->n_acc = v;
   }
   if (pl->n_acc < 2) return NQ_ERR_UNSUPPORTED;
+  // Short K (the head's dgrad: 9 taps x 16 channels): ~1000 MMA cycles per tile against an epilogue of ~3 chunks
+  // x 150 dependent instructions per warp -- give the epilogue 12 of the 16 worker warps, the loaders 4.
+  pl->n_epi = (d->ksize * d->ksize * C <= 1024 && pl->NT >= 48) ? 12 : 8;
+  if (const char* e = getenv("NQ_TC_NEPI")) {  // tuning override
+    const int v = atoi(e);
+    if (v == 8 || v == 12) pl->n_epi = v;
+  }
+  // Weights that fit the ring whole (the head: 9 stages of 3 KB) are loaded once per CTA and stay resident.
+  pl->resident = (N <= pl->NT && pl->mt == 1 && !pl->bcat && (C / sbc) * d->ksize * d->ksize <= pl->n_bstages) ? 1 : 0;
   pl->tiles_x = (d->w + tile_w - 1) / tile_w;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
@@ -977,7 +996,8 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if (p.n_store == 0) p.n_store = pl->N;
   p.N = pl->N; p.NT = pl->NT; p.KC = pl->KC; p.SBC = pl->SBC; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_n = pl->tiles_n; p.total_tiles = pl->total_tiles;
-  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS; p.mt = pl->mt; p.bcat = pl->bcat;
+  p.PW = pl->PW; p.PH = pl->PH; p.CGS = pl->CGS; p.mt = pl->mt; p.bcat = pl->bcat; p.n_epi = pl->n_epi;
+  if (p.n_epi != 8 && p.n_epi != 12) return NQ_ERR_BAD_ARG;
   p.n_abuf = pl->n_abuf; p.n_acc = pl->n_acc; p.acc_stride = pl->acc_stride; p.sub_stride = pl->acc_stride / pl->mt;
   if (p.n_abuf < 2 || p.n_abuf > TC_MAX_RING || p.n_acc < 2 || p.n_acc > TC_MAX_RING || p.n_acc * p.acc_stride > 512 ||
       p.sub_stride < pl->NT * (pl->bcat ? 2 : 1))
@@ -987,11 +1007,17 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
-  void (*kern)(const TcParams) = p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1> : conv_tc_kernel<2, 0>)
-                                            : (p.bcat ? conv_tc_kernel<1, 1> : conv_tc_kernel<1, 0>);
+  p.resident = pl->resident;
+  void (*kern)(const TcParams) = p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1, 0> : conv_tc_kernel<2, 0, 0>)
+                                 : p.bcat  ? conv_tc_kernel<1, 1, 0>
+                                           : (p.resident ? conv_tc_kernel<1, 0, 1> : conv_tc_kernel<1, 0, 0>);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
   int cs = pl->cluster;
+  if (p.resident) {
+    if (pl->tiles_n != 1 || pl->mt != 1 || pl->bcat || (pl->C / pl->SBC) * d->ksize * d->ksize > pl->n_bstages) return NQ_ERR_BAD_ARG;
+    cs = 1;  // nothing left to share: every CTA loads its own copy once
+  }
   p.tiles_m = pl->tiles_x * pl->tiles_y * d->n;
   if (cs < 1 || p.tiles_m < 2 * cs) cs = 1;
   p.cs = cs;
