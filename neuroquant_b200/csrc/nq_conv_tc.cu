@@ -45,6 +45,19 @@ constexpr int TC_HDR_BYTES = 1024;    // barriers (4 * TC_MAX_RING + 2 * TC_MAX_
 constexpr int EPI_ROW = 20;            // floats per staged epilogue row (16 + 4 pad: conflict-free 16-byte accesses)
 constexpr int EPI_STAGE_BYTES = 12 * 32 * EPI_ROW * 4;  // up to 12 epilogue warps
 
+// Division by a kernel-invariant divisor as one multiply-high: m = floor(2^32 / d) + 1 gives the exact quotient
+// for every x with x * d < 2^32 (all uses below: tile and pixel indices, d <= a few hundred).
+struct FastDiv {
+  uint32_t m, d;
+};
+__host__ __device__ __forceinline__ FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.m = d > 1 ? (uint32_t)((1ull << 32) / (uint32_t)d) + 1u : 0u;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int x, FastDiv f) { return f.d == 1u ? x : (int)__umulhi((uint32_t)x, f.m); }
+
 struct TcParams {
   const uint8_t* in;     // split-bf16 input: plane 0 (hi) then plane 1 (lo), each (n, h, w, in_stride) bf16
   size_t in_plane_bytes;
@@ -75,6 +88,10 @@ struct TcParams {
   int tiles_m, tiles_m_pad, total_groups;  // pixel tiles per N tile, padded to a multiple of cs; tile groups
   int n_abuf, n_acc;     // activation buffers in shared memory, accumulator slots in TMEM (rings, 2 .. TC_MAX_RING)
   int acc_stride, sub_stride;  // TMEM columns per accumulator slot / between the pixel tiles of a slot
+  FastDiv fd_tiles_x, fd_tiles_y, fd_rh, fd_rw, fd_PW, fd_npix, fd_cg;
+  int out_h, out_w, quad_stride;  // output grid (fwd: h*rh, w*rw; dgrad: h/rh, w/rw) and dgrad's floats per output pixel
+  int dbg;               // timing experiments only (NQ_TC_DBG bit mask; results are wrong when set): 1 no z loads,
+                         // 2 no epilogue stores, 4 no activation copies, 8 no MMAs
   int resident;          // 1: all weight stages of a tile fit the ring and stay there: loaded once per CTA, never released
   int n_epi;             // epilogue warps (8, or 12 for short-K stages whose epilogue binds); loaders = 16 - n_epi warps
   int bcat;              // weight stage stores the planes side by side per k-group ([k-group][plane][n][8]): A_hi x [B_hi | B_lo]
@@ -257,10 +274,10 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, in
   int tm = slot - tn * p.tiles_m_pad;
   c.real = tm < p.tiles_m;
   if (!c.real) tm = 0;
-  const int tx = tm % p.tiles_x;
-  tm /= p.tiles_x;
-  const int ty = tm % p.tiles_y;
-  c.img = tm / p.tiles_y;
+  const int tmx = fdiv(tm, p.fd_tiles_x);
+  const int tx = tm - tmx * p.tiles_x;
+  c.img = fdiv(tmx, p.fd_tiles_y);
+  const int ty = tmx - c.img * p.tiles_y;
   c.y0 = ty * TILE_H;
   c.x0 = tx * TILE_W * p.mt;
   c.n0 = tn * p.NT;
@@ -379,6 +396,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t b_plane16 = (uint32_t)(tc.nt * p.SBC * 2) >> 4;
       const uint32_t b_step16 = 2 * b_lbo16;
       uint32_t accum = 0;
+      if (RES) {
+        // Resident weights (ks <= 3, one activation unit, one stage per tap): the whole tile is a fully unrolled
+        // sequence of MMAs whose descriptors are INDEPENDENT adds off two bases.  The generic loops below carry
+        // their descriptors through dependent uniform-datapath adds, ~10 cycles per instruction for this lone
+        // warp: ~250 cycles per MMA on the head's 27-MMA tiles, far above the MMAs themselves.
+        mbar_wait(A_FULL + abuf * 8, aph);
+        fence_proxy_async();
+        tc_fence_after();
+        if (b_wait) {
+          for (int s2 = 0; s2 < taps; ++s2) mbar_wait(B_FULL + s2 * 8, 0);
+          tc_fence_after();
+        }
+        const uint32_t a0 = (((a_base + abuf * p.a_buf_bytes) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
+        const uint32_t b0 = ((b_base & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+        const uint32_t stage16 = (uint32_t)p.b_stage_bytes >> 4;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          if (kh >= p.ks) break;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            if (kw >= p.ks) break;
+            const uint32_t at = a0 + (uint32_t)(kh * p.PW + kw);
+            const uint32_t bt = b0 + (uint32_t)(kh * p.ks + kw) * stage16;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              if (j >= k16_per_stage) break;
+              const uint32_t aj = at + j * a_step16, bj = bt + j * b_step16;
+              if (leader && !(p.dbg & 8)) {
+                umma_bf16_w(d_tmem, aj, a_hi32, bj, b_hi32, idesc, (kh | kw | j) ? 1u : 0u);
+                if (passes & 1) umma_bf16_w(d_tmem, aj + a_plane16, a_hi32, bj, b_hi32, idesc, 1);
+                if (passes & 2) umma_bf16_w(d_tmem, aj, a_hi32, bj + b_plane16, b_hi32, idesc, 1);
+              }
+            }
+          }
+        }
+        if (leader) umma_commit(A_EMPTY + abuf * 8);
+        if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
+      } else
       for (int cb = 0; cb < ncb; ++cb) {
         mbar_wait(A_FULL + abuf * 8, aph);
         fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
@@ -497,18 +552,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int tasks = npix * npair;
         const int cgp = ltid & 1;
         int j = ltid >> 1;
-        int cpi = j / npix, pix = j - cpi * npix;
-        for (; j < tasks; j += nload / 2) {
+        int cpi = fdiv(j, p.fd_npix), pix = j - cpi * npix;
+        for (; j < tasks && !(p.dbg & 32); j += nload / 2) {
           const int cgi = 2 * cpi + cgp;
           if (cgi < ncg) {
-            const int py = pix / p.PW, px = pix - py * p.PW;
+            const int py = fdiv(pix, p.fd_PW), px = pix - py * p.PW;
             const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
             const int ch = c0 + cgi * 8;
             const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
             const uint8_t* src = ok ? img + (((size_t)gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
             const uint32_t d = dst + cgi * p.CGS + pix * 16;
-            cp_async16(d, src, ok ? 16u : 0u);
-            if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
+            if (!(p.dbg & 4)) {
+              cp_async16(d, src, ok ? 16u : 0u);
+              if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
+            }
           }
           pix += nload / 2;
           while (pix >= npix) { pix -= npix; ++cpi; }
@@ -544,14 +601,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int it = 0; it < 4; ++it) {
         const int y = tc.y0 + q * 4 + it, x = tc.x0 + sub * TILE_W + rsub;
         valid[it] = tc.real && y < p.h && x < p.w;
+        // pixel indices fit 32 bits (checked at launch); one 64-bit multiply per offset
         if (p.epi == 0) {
-          row_base[it] = (((size_t)tc.img * (p.h * p.rh) + (size_t)y * p.rh) * (p.w * p.rw) + (size_t)x * p.rw) * p.cg;
+          row_base[it] = (size_t)((tc.img * p.out_h + y * p.rh) * p.out_w + x * p.rw) * (size_t)p.cg;
           zrow[it] = 0;
         } else {
-          const int qh = y / p.rh, si = y - qh * p.rh, qw = x / p.rw, sj = x - qw * p.rw;
-          row_base[it] = (((size_t)tc.img * (p.h / p.rh) + qh) * (p.w / p.rw) + qw) * ((size_t)p.rh * p.rw * p.n_store) +
-                         (size_t)(si * p.rw + sj) * p.n_store;
-          zrow[it] = (((size_t)tc.img * p.h + y) * p.w + x) * p.n_store;
+          const int qh = fdiv(y, p.fd_rh), si = y - qh * p.rh, qw = fdiv(x, p.fd_rw), sj = x - qw * p.rw;
+          row_base[it] = (size_t)((tc.img * p.out_h + qh) * p.out_w + qw) * (size_t)p.quad_stride + (size_t)((si * p.rw + sj) * p.n_store);
+          zrow[it] = (size_t)((tc.img * p.h + y) * p.w + x) * (size_t)p.n_store;
         }
       }
       if (p.epi == 2) {
@@ -625,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(T_FULL + acc * 8, tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + sub * p.sub_stride + ((uint32_t)(q * 32) << 16);
-      for (int c0 = half * 16; c0 < tc.nt; c0 += (p.n_epi >> 2) * 16) {
+      for (int c0 = half * 16; c0 < tc.nt && !(p.dbg & 16); c0 += (p.n_epi >> 2) * 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         if (BCAT) {  // hi*lo partial sums live nt columns further
@@ -642,8 +699,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (p.epi != 1 && col_ok) {
           if (p.scale) g0 = __ldg(reinterpret_cast<const float4*>(p.scale + n));
           if (p.bias) g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          const int grp = n / p.cg, c = n - grp * p.cg;
-          const int si = grp / p.rw, sj = grp - si * p.rw;
+          const int grp = fdiv(n, p.fd_cg), c = n - grp * p.cg;
+          const int si = fdiv(grp, p.fd_rw), sj = grp - si * p.rw;
           col_off = ((size_t)si * (p.w * p.rw) + sj) * p.cg + c;
         }
         float4 zv[4];  // dgrad: z of the previous stage for this lane's 4 pixels, requested before the TMEM wait
@@ -651,7 +708,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             zv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.zprev && p.act != 0 && valid[it] && col_ok)
+            if (p.zprev && p.act != 0 && valid[it] && col_ok && !(p.dbg & 1))
               zv[it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
           }
         }
@@ -667,7 +724,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float4 r = *reinterpret_cast<const float4*>(stg + (it * 8 + rsub) * EPI_ROW + qd * 4);
-          if (!(valid[it] && col_ok)) continue;
+          if (!(valid[it] && col_ok) || (p.dbg & 2)) continue;
           if (p.epi == 0) {
             r.x = fmaf(r.x, g0.x, g1.x); r.y = fmaf(r.y, g0.y, g1.y);
             r.z = fmaf(r.z, g0.z, g1.z); r.w = fmaf(r.w, g0.w, g1.w);
@@ -936,7 +993,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
     if (v == 8 || v == 12) pl->n_epi = v;
   }
   // Weights that fit the ring whole (the head: 9 stages of 3 KB) are loaded once per CTA and stay resident.
-  pl->resident = (N <= pl->NT && pl->mt == 1 && !pl->bcat && (C / sbc) * d->ksize * d->ksize <= pl->n_bstages) ? 1 : 0;
+  pl->resident = (N <= pl->NT && pl->mt == 1 && !pl->bcat && d->ksize <= 3 && pl->KC == C && sbc == C && sbc <= 96 && (C / sbc) * d->ksize * d->ksize <= pl->n_bstages) ? 1 : 0;
   pl->tiles_x = (d->w + tile_w - 1) / tile_w;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
@@ -1007,7 +1064,14 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
+  if (p.epi == 1) { p.out_h = p.h / p.rh; p.out_w = p.w / p.rw; p.quad_stride = p.rh * p.rw * p.n_store; }
+  else { p.out_h = p.h * p.rh; p.out_w = p.w * p.rw; p.quad_stride = 0; }
+  if ((long long)p.n * p.out_h * p.out_w >= (1LL << 31) || (long long)p.n * p.h * p.w >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
   p.resident = pl->resident;
+  { static const int dbg = getenv("NQ_TC_DBG") ? atoi(getenv("NQ_TC_DBG")) : 0; p.dbg = dbg; }
+  p.fd_tiles_x = make_fastdiv(pl->tiles_x); p.fd_tiles_y = make_fastdiv(pl->tiles_y);
+  p.fd_rh = make_fastdiv(p.rh); p.fd_rw = make_fastdiv(p.rw); p.fd_PW = make_fastdiv(pl->PW);
+  p.fd_npix = make_fastdiv(pl->PW * pl->PH); p.fd_cg = make_fastdiv(p.cg);
   void (*kern)(const TcParams) = p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1, 0> : conv_tc_kernel<2, 0, 0>)
                                  : p.bcat  ? conv_tc_kernel<1, 1, 0>
                                            : (p.resident ? conv_tc_kernel<1, 0, 1> : conv_tc_kernel<1, 0, 0>);
@@ -1015,7 +1079,9 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
   int cs = pl->cluster;
   if (p.resident) {
-    if (pl->tiles_n != 1 || pl->mt != 1 || pl->bcat || (pl->C / pl->SBC) * d->ksize * d->ksize > pl->n_bstages) return NQ_ERR_BAD_ARG;
+    if (pl->tiles_n != 1 || pl->mt != 1 || pl->bcat || d->ksize > 3 || pl->KC != pl->C || pl->SBC != pl->C || pl->SBC > 96 ||
+        d->ksize * d->ksize > pl->n_bstages)
+      return NQ_ERR_BAD_ARG;
     cs = 1;  // nothing left to share: every CTA loads its own copy once
   }
   p.tiles_m = pl->tiles_x * pl->tiles_y * d->n;
