@@ -89,6 +89,7 @@ struct TcParams {
   int n_abuf, n_acc;     // activation buffers in shared memory, accumulator slots in TMEM (rings, 2 .. TC_MAX_RING)
   int acc_stride, sub_stride;  // TMEM columns per accumulator slot / between the pixel tiles of a slot
   FastDiv fd_tiles_x, fd_tiles_y, fd_rh, fd_rw, fd_PW, fd_npix, fd_cg;
+  int nsb_last;          // weight stages of the last (possibly partial) activation unit
   int out_h, out_w, quad_stride;  // output grid (fwd: h*rh, w*rw; dgrad: h/rh, w/rw) and dgrad's floats per output pixel
   int dbg;               // timing experiments only (NQ_TC_DBG bit mask; results are wrong when set): 1 no z loads,
                          // 2 no epilogue stores, 4 no activation copies, 8 no MMAs
@@ -270,7 +271,7 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, int rank) {
   TileCoord c;
   const int slot = group * p.cs + rank;
-  const int tn = slot / p.tiles_m_pad;
+  const int tn = p.tiles_n == 1 ? 0 : slot / p.tiles_m_pad;
   int tm = slot - tn * p.tiles_m_pad;
   c.real = tm < p.tiles_m;
   if (!c.real) tm = 0;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t part = stage_bytes / p.cs;
         const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride;
         for (int cb = 0; cb < ncb; ++cb) {
-          const int nsb = min(nsb_full, (p.C - cb * p.KC) / p.SBC);
+          const int nsb = cb == ncb - 1 ? p.nsb_last : nsb_full;
           for (int tap = 0; tap < taps; ++tap)
             for (int sb = 0; sb < nsb; ++sb, ++sc) {
               const uint32_t s = bs, ph = bph;
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
         tc_fence_after();
         const uint32_t a_buf16 = (((a_base + abuf * p.a_buf_bytes) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
-        const int nsb = min(nsb_full, (p.C - cb * p.KC) / p.SBC);
+        const int nsb = cb == ncb - 1 ? p.nsb_last : nsb_full;
         uint32_t a_tap = a_buf16;  // + (kh * PW + kw) 16-byte rows
         int kw = 0;
         for (int tap = 0; tap < taps; ++tap) {
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int gy = tc.y0 + py - p.pad, gx = tc.x0 + px - p.pad;
             const int ch = c0 + cgi * 8;
             const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
-            const uint8_t* src = ok ? img + (((size_t)gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
+            const uint8_t* src = ok ? img + ((size_t)(gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
             const uint32_t d = dst + cgi * p.CGS + pix * 16;
             if (!(p.dbg & 4)) {
               cp_async16(d, src, ok ? 16u : 0u);
@@ -1067,6 +1068,7 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if (p.epi == 1) { p.out_h = p.h / p.rh; p.out_w = p.w / p.rw; p.quad_stride = p.rh * p.rw * p.n_store; }
   else { p.out_h = p.h * p.rh; p.out_w = p.w * p.rw; p.quad_stride = 0; }
   if ((long long)p.n * p.out_h * p.out_w >= (1LL << 31) || (long long)p.n * p.h * p.w >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
+  p.nsb_last = (pl->C - ((pl->C + pl->KC - 1) / pl->KC - 1) * pl->KC) / pl->SBC;
   p.resident = pl->resident;
   { static const int dbg = getenv("NQ_TC_DBG") ? atoi(getenv("NQ_TC_DBG")) : 0; p.dbg = dbg; }
   p.fd_tiles_x = make_fastdiv(pl->tiles_x); p.fd_tiles_y = make_fastdiv(pl->tiles_y);

@@ -284,19 +284,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(p.x);
     const uint16_t* zh = reinterpret_cast<const uint16_t*>(p.dz);
     uint32_t bi = 0, ph = 0;
+    // tiles are consecutive: decode the first one, then step (no per-tile divisions; 32-bit pixel indices)
+    int tx = t_begin % p.tiles_x, ty = (t_begin / p.tiles_x) % p.tiles_y, img_next = t_begin / (p.tiles_x * p.tiles_y);
     for (int t = t_begin; t < t_end; ++t) {
-      int tt = t;
-      const int tx = tt % p.tiles_x;
-      tt /= p.tiles_x;
-      const int ty = tt % p.tiles_y;
-      const int img = tt / p.tiles_y;
-      const int y0 = ty * p.TR, x0 = tx * WG_TW;
+      const int y0 = ty * p.TR, x0 = tx * WG_TW, img = img_next;
+      if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img_next; } }
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
       const uint32_t buf = buf0 + bi * p.buf_bytes;
       // ---- shifted input copies: staged row ar holds image row y0 + ar + kh0 - pad; copy kw holds source column
       //      x0 + xl + kw - pad; the kw copies of one source sector come from L1 (cp.async.ca)
       if (a_table) {
-        const uint16_t* origin = xh + (((size_t)img * p.h + y0) * p.w + x0) * p.C;
+        const uint16_t* origin = xh + (ptrdiff_t)((img * p.h + y0) * p.w + x0) * p.C;
 #pragma unroll
         for (int k = 0; k < MAXI; ++k) {
           if (k < na) {
@@ -318,7 +316,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           if (cg < ncg_c) {
             const int gy = y0 + ar + kh0 - p.pad, gx = x0 + xl + kw - p.pad;
             const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
-            const uint8_t* src = ok ? p.x + ((((size_t)img * p.h + gy) * p.w + gx) * p.C + (cg0 + cg) * 8) * 2 : p.x;
+            const uint8_t* src = ok ? p.x + ((size_t)((img * p.h + gy) * p.w + gx) * p.C + (cg0 + cg) * 8) * 2 : p.x;
             const uint32_t d = a_dst + (uint32_t)(kw * ncg_c + cg) * p.CGS_A + (uint32_t)ar * (WG_TW * 16);
             wcp_async16_ca(d, src, ok ? 16u : 0u);
             if (p.a_planes == 2) wcp_async16_ca(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
@@ -332,7 +330,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         const uint32_t b_dst = buf + p.a_planes * p.a_plane_bytes + bslot * 16;
         const int oy = y0 + br, ox = x0 + bxl;
         const bool pix_ok = oy < p.h && ox < p.w;
-        const uint16_t* zpix = zh + (((size_t)img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0;
+        const uint16_t* zpix = zh + (size_t)((img * p.h + (pix_ok ? oy : 0)) * p.w + (pix_ok ? ox : 0)) * p.dz_stride + n0;
 #pragma unroll 2
         for (int cg = 2 * bgrp + cgp; cg < ncg_b; cg += 2 * nbgrp) {
           const bool ok = pix_ok && (n0 + cg * 8) < p.n_valid;
