@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t d = dst + cgi * p.CGS + pix * 16;
             if (!(p.dbg & 4)) {
               cp_async16(d, src, ok ? 16u : 0u);
-              if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + (ok ? p.in_plane_bytes : 0), ok ? 16u : 0u);
+              if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + p.in_plane_bytes, ok ? 16u : 0u);  // plane 1 of the dummy address is valid
             }
           }
           pix += nload / 2;

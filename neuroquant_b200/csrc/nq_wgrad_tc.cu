@@ -212,6 +212,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t a_buf = buf0 + bi * p.buf_bytes;
       const uint32_t a16 = ((a_buf & 0x3FFFFu) >> 4) | lbo_bits;
       const uint32_t b16 = (((a_buf + p.a_planes * p.a_plane_bytes) & 0x3FFFFu) >> 4) | lbo_bits;
+      if (p.MB == 1) {
+        // One 128-row block: fully unrolled, every descriptor an independent add off the buffer base.  The loop nest
+        // below carries them through dependent uniform-datapath adds, which binds the narrow-N plans (the head:
+        // 36 MMAs of N = 16 per tile, ~100 cycles of issue each).
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r >= p.TR) break;
+#pragma unroll
+          for (int khl = 0; khl < 7; ++khl) {
+            if (khl >= nkh) break;
+            const uint32_t a_lo = a16 + (r + khl) * row16, b_lo = b16 + r * row16, d = tmem_base + khl * p.NC;
+            if (leader) {
+              wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, r == 0 ? accum : 1u);
+              if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+              if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+            }
+          }
+        }
+        accum = 1;
+      } else
       for (int r = 0; r < p.TR; ++r) {
         const uint32_t b_lo = b16 + r * row16;
         uint32_t d = tmem_base;
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const uint32_t d = buf + (uint32_t)a_do[k];
             wcp_async16_ca(d, src, ok ? 16u : 0u);
             if (p.a_planes == 2)
-              wcp_async16_ca(d + p.a_plane_bytes, reinterpret_cast<const uint8_t*>(src) + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
+              wcp_async16_ca(d + p.a_plane_bytes, reinterpret_cast<const uint8_t*>(src) + p.x_plane_bytes, ok ? 16u : 0u);  // plane 1 of the dummy address is valid too
           }
         }
       } else {
@@ -319,7 +339,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const uint8_t* src = ok ? p.x + ((size_t)((img * p.h + gy) * p.w + gx) * p.C + (cg0 + cg) * 8) * 2 : p.x;
             const uint32_t d = a_dst + (uint32_t)(kw * ncg_c + cg) * p.CGS_A + (uint32_t)ar * (WG_TW * 16);
             wcp_async16_ca(d, src, ok ? 16u : 0u);
-            if (p.a_planes == 2) wcp_async16_ca(d + p.a_plane_bytes, src + (ok ? p.x_plane_bytes : 0), ok ? 16u : 0u);
+            if (p.a_planes == 2) wcp_async16_ca(d + p.a_plane_bytes, src + p.x_plane_bytes, ok ? 16u : 0u);
           }
           cpi += nlgrp;
           while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
@@ -338,7 +358,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           const uint32_t d = b_dst + (uint32_t)cg * p.CGS_B;
           wcp_async16(d, src, ok ? 16u : 0u);
           if (p.b_planes == 2)
-            wcp_async16(d + p.b_plane_bytes, reinterpret_cast<const uint8_t*>(src) + (ok ? p.dz_plane_bytes : 0), ok ? 16u : 0u);
+            wcp_async16(d + p.b_plane_bytes, reinterpret_cast<const uint8_t*>(src) + p.dz_plane_bytes, ok ? 16u : 0u);
         }
       }
       wcp_async_arrive(FULL + bi * 8);
