@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnq_sm100.so")
+# NQ_LIB_PATH: load another build of the same library (A/B timing of kernel variants); default is the in-tree build
+LIB_PATH = os.environ.get("NQ_LIB_PATH") or os.path.join(_HERE, "libnq_sm100.so")
 
 
 class NqError(RuntimeError):

@@ -450,195 +450,13 @@ __global__ void __launch_bounds__(HT_H * HT_W) head_fwd_loss_kernel(const HeadPa
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Head forward, register blocked.  The one-pixel-per-thread kernel above issues 10 shared-memory loads per 24
-// FMAs and is bound by the shared-memory pipe (0.27 ms for 3.5 GFLOP at 1280x640x2).  Here a thread owns 2 rows x
-// 4 consecutive pixels (24 accumulators); the input tile lives in shared memory CHANNEL-PLANAR, so a lane's four
-// pixels of one row are one aligned 16-byte load and the two neighbours come from the adjacent lanes by shuffle
-// (the tile's halo columns by one predicated scalar load): per channel 4 vector loads + 9 broadcast weight loads
-// feed 216 FMAs.  Tile 8 x 128 pixels, 4 warps (one per row pair), 8 channels per chunk (44 KB: 4 CTAs per SM).
-// ---------------------------------------------------------------------------------------------
-constexpr int HF_TH = 8, HF_TW = 128, HF_CH = 8, HF_THREADS = 128, HF_BATCH = 4;
-constexpr int HF_RP = HF_TW + 8;              // row pitch (floats): [3] left halo, [4, 4 + TW) tile, [4 + TW] right halo
-constexpr int HF_PLANE = (HF_TH + 2) * HF_RP;  // floats per channel plane
-constexpr int HF_SMEM = (HF_CH * HF_PLANE + 9 * HF_CH * 4) * 4;
-
-__global__ void __launch_bounds__(HF_THREADS) head_fwd_loss_rb_kernel(const HeadParams q) {
-  extern __shared__ __align__(16) float hsm[];
-  float* xs = hsm;                      // [HF_CH][HF_TH + 2][HF_RP]
-  float* ws = hsm + HF_CH * HF_PLANE;   // [9][HF_CH][4]
-  __shared__ float red[32];
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  const int tiles_w = (q.w_ + HF_TW - 1) / HF_TW, tiles_h = (q.h + HF_TH - 1) / HF_TH;
-  int b = blockIdx.x;
-  const int tw = b % tiles_w; b /= tiles_w;
-  const int th = b % tiles_h;
-  const int bn = b / tiles_h;
-  const int x0 = tw * HF_TW, y0 = th * HF_TH;
-
-  float acc[2][4][3];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[r][i][0] = acc[r][i][1] = acc[r][i][2] = 0.f;
-
-  for (int c0 = 0; c0 < q.C; c0 += HF_CH) {
-    const int cw = min(HF_CH, q.C - c0);  // multiple of 4
-    __syncthreads();
-    // stage the halo tile: one item = one pixel, all channels of the chunk (whole 32-byte sectors per plane).
-    // Items go in batches of HF_BATCH with every global load of the batch issued before the first conversion:
-    // only 4 warps per CTA, so the memory-level parallelism has to come from each thread.
-    for (int i0 = tid; i0 < (HF_TH + 2) * (HF_TW + 2); i0 += HF_THREADS * HF_BATCH) {
-      uint4 raw[HF_BATCH][2];  // split-bf16: hi, lo of the 8 channels; fp32: channels 0-3, 4-7
-      int soff[HF_BATCH];
-#pragma unroll
-      for (int k = 0; k < HF_BATCH; ++k) {
-        const int i = i0 + k * HF_THREADS;
-        const int sy = i / (HF_TW + 2), sx = i - sy * (HF_TW + 2);
-        const int gx = x0 + sx - 1, gy = y0 + sy - 1;
-        const bool ok = i < (HF_TH + 2) * (HF_TW + 2) && (unsigned)gx < (unsigned)q.w_ && (unsigned)gy < (unsigned)q.h;
-        soff[k] = i < (HF_TH + 2) * (HF_TW + 2) ? sy * HF_RP + sx + 3 : -1;
-        const int64_t o = ((int64_t)(bn * q.h + (ok ? gy : 0)) * q.w_ + (ok ? gx : 0)) * q.C + c0;
-        raw[k][0] = raw[k][1] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) {
-          if (q.x_hi) {
-            raw[k][0] = __ldg(reinterpret_cast<const uint4*>(q.x_hi + o));
-            raw[k][1] = __ldg(reinterpret_cast<const uint4*>(q.x_lo + o));
-          } else {
-            raw[k][0] = __ldg(reinterpret_cast<const uint4*>(q.x + o));
-            if (cw > 4) raw[k][1] = __ldg(reinterpret_cast<const uint4*>(q.x + o + 4));
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < HF_BATCH; ++k) {
-        if (soff[k] < 0) continue;
-        float* dst = xs + soff[k];
-        if (q.x_hi) {
-          const uint32_t hb[4] = {raw[k][0].x, raw[k][0].y, raw[k][0].z, raw[k][0].w};
-          const uint32_t lb[4] = {raw[k][1].x, raw[k][1].y, raw[k][1].z, raw[k][1].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            dst[(2 * e) * HF_PLANE] = bf16_bits_to_f(hb[e] & 0xFFFFu) + bf16_bits_to_f(lb[e] & 0xFFFFu);
-            dst[(2 * e + 1) * HF_PLANE] = bf16_bits_to_f(hb[e] >> 16) + bf16_bits_to_f(lb[e] >> 16);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            dst[(4 * j + 0) * HF_PLANE] = __uint_as_float(raw[k][j].x);
-            dst[(4 * j + 1) * HF_PLANE] = __uint_as_float(raw[k][j].y);
-            dst[(4 * j + 2) * HF_PLANE] = __uint_as_float(raw[k][j].z);
-            dst[(4 * j + 3) * HF_PLANE] = __uint_as_float(raw[k][j].w);
-          }
-        }
-      }
-    }
-    for (int i = tid; i < 9 * cw; i += HF_THREADS) {
-      const int tap = i / cw, c = i - tap * cw;
-      *reinterpret_cast<float4*>(&ws[(tap * HF_CH + c) * 4]) = ldg4(q.w + ((int64_t)tap * q.C + c0 + c) * 4);
-    }
-    __syncthreads();
-    for (int c = 0; c < cw; ++c) {
-      const float* xp = xs + c * HF_PLANE + (2 * wp) * HF_RP + 4 + 4 * lane;
-      float xr[4][6];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(xp + r * HF_RP);
-        float l = __shfl_up_sync(0xffffffffu, v.w, 1), rr = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 0 || lane == 31) {  // the tile's own halo columns: one predicated load serves both edge lanes
-          const float e = xp[r * HF_RP + (lane == 0 ? -1 : 4)];
-          if (lane == 0) l = e; else rr = e;
-        }
-        xr[r][0] = l; xr[r][1] = v.x; xr[r][2] = v.y; xr[r][3] = v.z; xr[r][4] = v.w; xr[r][5] = rr;
-      }
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float4 wv = *reinterpret_cast<const float4*>(&ws[((kh * 3 + kw) * HF_CH + c) * 4]);
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float xv = xr[r + kh][i + kw];
-              acc[r][i][0] = fmaf(xv, wv.x, acc[r][i][0]);
-              acc[r][i][1] = fmaf(xv, wv.y, acc[r][i][1]);
-              acc[r][i][2] = fmaf(xv, wv.z, acc[r][i][2]);
-            }
-        }
-    }
-  }
-
-  float loss = 0.f;
-  const int64_t plane = (int64_t)q.h * q.w_;
-  const float b0 = q.bias[0], b1 = q.bias[1], b2 = q.bias[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int py = y0 + 2 * wp + r;
-    if (py >= q.h) continue;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int px = x0 + 4 * lane + i;
-      if (px >= q.w_) continue;
-      const float v[3] = {acc[r][i][0] + b0, acc[r][i][1] + b1, acc[r][i][2] + b2};
-      float g[3] = {0.f, 0.f, 0.f};
-      const int64_t o = (int64_t)bn * 3 * plane + (int64_t)py * q.w_ + px;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float outv, dout;
-        if (q.out_bias == 0) {
-          const float t = tanhf(v[c]);
-          outv = t * 0.5f + 0.5f;
-          dout = 0.5f * (1.0f - t * t);
-        } else {
-          outv = sigmoid_f(v[c]);
-          dout = outv * (1.0f - outv);
-        }
-        if (q.img) q.img[o + c * plane] = outv;
-        if (q.target) {
-          const float dlt = outv - __ldg(q.target + o + c * plane);
-          const float a = fabsf(dlt);
-          if (q.p == 2.0f) {
-            loss += dlt * dlt;
-            g[c] = 2.0f * dlt * q.inv_mean * dout;
-          } else {
-            loss += powf(a, q.p);
-            const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
-            g[c] = q.p * powf(a, q.p - 1.0f) * sgn * q.inv_mean * dout;
-          }
-        }
-      }
-      const int64_t pix = (int64_t)(bn * q.h + py) * q.w_ + px;
-      if (q.dz) *reinterpret_cast<float4*>(q.dz + pix * 4) = make_float4(g[0], g[1], g[2], 0.f);
-      if (q.dz_hi) {
-        uint16_t hb[3], lb[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          hb[c] = f_to_bf16_bits(g[c]);
-          lb[c] = f_to_bf16_bits(g[c] - bf16_bits_to_f(hb[c]));
-        }
-        *reinterpret_cast<uint4*>(q.dz_hi + pix * 8) = make_uint4((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), hb[2], 0u, 0u);
-        *reinterpret_cast<uint4*>(q.dz_lo + pix * 8) = make_uint4((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), lb[2], 0u, 0u);
-      }
-    }
-  }
-  if (q.target && q.loss_sum) {
-    loss = block_sum(loss, red);
-    if (tid == 0) atomicAdd(q.loss_sum, loss);
-  }
-}
-
 static inline int64_t hcdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// (A register-blocked variant -- 2 x 4 pixels per thread over a channel-planar shared-memory tile -- was measured at
+// 0.31 ms against 0.27 ms for this kernel at 1280x640x2: with 44 KB of staging per CTA its synchronous tile loads are
+// exposed, and the head's input arrives as split-bf16 NHWC, which needs a converting transpose.  Not kept.)
 static int launch_head_fwd(const HeadParams& q, cudaStream_t s) {
-  static const bool v1 = getenv("NQ_HEAD_V1") != nullptr;  // A/B switch: the one-pixel-per-thread kernel
-  if (v1) {
-    const int64_t blocks = hcdiv(q.w_, HT_W) * hcdiv(q.h, HT_H) * q.n;
-    head_fwd_loss_kernel<<<(unsigned)blocks, HT_H * HT_W, 0, s>>>(q);
-  } else {
-    NQ_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_loss_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM));
-    const int64_t blocks = hcdiv(q.w_, HF_TW) * hcdiv(q.h, HF_TH) * q.n;
-    head_fwd_loss_rb_kernel<<<(unsigned)blocks, HF_THREADS, HF_SMEM, s>>>(q);
-  }
+  const int64_t blocks = hcdiv(q.w_, HT_W) * hcdiv(q.h, HT_H) * q.n;
+  head_fwd_loss_kernel<<<(unsigned)blocks, HT_H * HT_W, 0, s>>>(q);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

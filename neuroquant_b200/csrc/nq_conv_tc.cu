@@ -91,8 +91,6 @@ struct TcParams {
   FastDiv fd_tiles_x, fd_tiles_y, fd_rh, fd_rw, fd_PW, fd_npix, fd_cg;
   int nsb_last;          // weight stages of the last (possibly partial) activation unit
   int out_h, out_w, quad_stride;  // output grid (fwd: h*rh, w*rw; dgrad: h/rh, w/rw) and dgrad's floats per output pixel
-  int dbg;               // timing experiments only (NQ_TC_DBG bit mask; results are wrong when set): 1 no z loads,
-                         // 2 no epilogue stores, 4 no activation copies, 8 no MMAs
   int resident;          // 1: all weight stages of a tile fit the ring and stay there: loaded once per CTA, never released
   int n_epi;             // epilogue warps (8, or 12 for short-K stages whose epilogue binds); loaders = 16 - n_epi warps
   int bcat;              // weight stage stores the planes side by side per k-group ([k-group][plane][n][8]): A_hi x [B_hi | B_lo]
@@ -424,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int j = 0; j < 6; ++j) {
               if (j >= k16_per_stage) break;
               const uint32_t aj = at + j * a_step16, bj = bt + j * b_step16;
-              if (leader && !(p.dbg & 8)) {
+              if (leader) {
                 umma_bf16_w(d_tmem, aj, a_hi32, bj, b_hi32, idesc, (kh | kw | j) ? 1u : 0u);
                 if (passes & 1) umma_bf16_w(d_tmem, aj + a_plane16, a_hi32, bj, b_hi32, idesc, 1);
                 if (passes & 2) umma_bf16_w(d_tmem, aj, a_hi32, bj + b_plane16, b_hi32, idesc, 1);
@@ -554,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int cgp = ltid & 1;
         int j = ltid >> 1;
         int cpi = fdiv(j, p.fd_npix), pix = j - cpi * npix;
-        for (; j < tasks && !(p.dbg & 32); j += nload / 2) {
+        for (; j < tasks; j += nload / 2) {
           const int cgi = 2 * cpi + cgp;
           if (cgi < ncg) {
             const int py = fdiv(pix, p.fd_PW), px = pix - py * p.PW;
@@ -563,10 +561,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
             const uint8_t* src = ok ? img + ((size_t)(gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
             const uint32_t d = dst + cgi * p.CGS + pix * 16;
-            if (!(p.dbg & 4)) {
-              cp_async16(d, src, ok ? 16u : 0u);
-              if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + p.in_plane_bytes, ok ? 16u : 0u);  // plane 1 of the dummy address is valid
-            }
+            cp_async16(d, src, ok ? 16u : 0u);
+            if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + p.in_plane_bytes, ok ? 16u : 0u);  // plane 1 of the dummy address is valid
           }
           pix += nload / 2;
           while (pix >= npix) { pix -= npix; ++cpi; }
@@ -683,7 +679,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(T_FULL + acc * 8, tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + sub * p.sub_stride + ((uint32_t)(q * 32) << 16);
-      for (int c0 = half * 16; c0 < tc.nt && !(p.dbg & 16); c0 += (p.n_epi >> 2) * 16) {
+      for (int c0 = half * 16; c0 < tc.nt; c0 += (p.n_epi >> 2) * 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         if (BCAT) {  // hi*lo partial sums live nt columns further
@@ -709,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             zv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.zprev && p.act != 0 && valid[it] && col_ok && !(p.dbg & 1))
+            if (p.zprev && p.act != 0 && valid[it] && col_ok)
               zv[it] = __ldg(reinterpret_cast<const float4*>(p.zprev + zrow[it] + n));
           }
         }
@@ -725,7 +721,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float4 r = *reinterpret_cast<const float4*>(stg + (it * 8 + rsub) * EPI_ROW + qd * 4);
-          if (!(valid[it] && col_ok) || (p.dbg & 2)) continue;
+          if (!(valid[it] && col_ok)) continue;
           if (p.epi == 0) {
             r.x = fmaf(r.x, g0.x, g1.x); r.y = fmaf(r.y, g0.y, g1.y);
             r.z = fmaf(r.z, g0.z, g1.z); r.w = fmaf(r.w, g0.w, g1.w);
@@ -1070,7 +1066,6 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if ((long long)p.n * p.out_h * p.out_w >= (1LL << 31) || (long long)p.n * p.h * p.w >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
   p.nsb_last = (pl->C - ((pl->C + pl->KC - 1) / pl->KC - 1) * pl->KC) / pl->SBC;
   p.resident = pl->resident;
-  { static const int dbg = getenv("NQ_TC_DBG") ? atoi(getenv("NQ_TC_DBG")) : 0; p.dbg = dbg; }
   p.fd_tiles_x = make_fastdiv(pl->tiles_x); p.fd_tiles_y = make_fastdiv(pl->tiles_y);
   p.fd_rh = make_fastdiv(p.rh); p.fd_rw = make_fastdiv(p.rw); p.fd_PW = make_fastdiv(pl->PW);
   p.fd_npix = make_fastdiv(pl->PW * pl->PH); p.fd_cg = make_fastdiv(p.cg);
