@@ -308,7 +308,7 @@ def run_b200(args):
     conv_ms = sum(k["ms"] for k in kern)
     traffic = None
     try:  # dram__bytes_read + dram__bytes_write of this launch from the committed `ncu --set full` capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01g_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01l_traffic.json")))
         if args.workload == "hnerv-bunny-3m" and B == 2:
             traffic = tr.get(top["kernel"])
     except OSError:
