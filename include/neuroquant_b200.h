@@ -321,6 +321,20 @@ int nq_tc_plan_wgrad(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc_wg
 int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* plan, const void* x_split, const void* dz_split,
                      float* dwk, float* workspace, int64_t workspace_floats, void* stream);
 
+/* One launch that finishes the weight gradients of several stages: the fixed-order sum over each stage's
+ * pixel-split partials (what nq_tc_conv_wgrad does itself when dwk != NULL) fused with nq_unpack_wgrad.  Call
+ * nq_tc_conv_wgrad with dwk = NULL for those stages.  d is the descriptor the wgrad plan was made for; channels
+ * cin .. cin_dst of dw_ref (the zero pad of a rotated layer, quant_layer.py:66) are written as zeros. */
+typedef struct nq_wgrad_finish_task {
+  const nq_conv_desc* d;
+  const float* workspace;   /* (plan->psplits, k*k*cin_p + 4, plan->N) */
+  float* dw_ref;            /* (cout, cin_dst, k, k) or NULL */
+  float* db_ref;            /* (cout) or NULL */
+  int32_t psplits, n_cols;  /* plan->psplits, plan->N */
+  int32_t cin_dst, reserved;
+} nq_wgrad_finish_task;
+int nq_tc_wgrad_finish_multi(const nq_wgrad_finish_task* tasks, int n_tasks, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Omega = dw^T H dw (methods/bit_assign.py:57-118,171-203) by second-order FORWARD propagation:
  * every stage carries (y, y', y'') = value and first/second directional derivative along the weight

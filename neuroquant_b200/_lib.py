@@ -65,6 +65,12 @@ class AdaTask(C.Structure):
                [(n, C.c_int32) for n in ("channel_wise", "n_bits", "use_reg", "reserved")]
 
 
+class WgFinishTask(C.Structure):
+    """Mirror of nq_wgrad_finish_task."""
+    _fields_ = [("d", C.POINTER(ConvDesc)), ("workspace", C.c_void_p), ("dw_ref", C.c_void_p), ("db_ref", C.c_void_p),
+                ("psplits", C.c_int32), ("n_cols", C.c_int32), ("cin_dst", C.c_int32), ("reserved", C.c_int32)]
+
+
 MULTI_MAX = 16
 
 
@@ -108,6 +114,7 @@ def _load():
         "nq_tc_head_fwd_loss": (I, [DP, TP, P, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_tc_plan_wgrad": (I, [DP, I, I, C.POINTER(TcWgradPlan)]),
         "nq_tc_conv_wgrad": (I, [DP, C.POINTER(TcWgradPlan), P, P, P, P, L, P]),
+        "nq_tc_wgrad_finish_multi": (I, [C.POINTER(WgFinishTask), I, P]),
         "nq_jet_act": (I, [P, P, P, P, P, L, I, P, P, P, I, P]),
         "nq_head_fwd_loss_split": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_jet_head": (I, [P, P, P, P, P, P, I, I, I, I, P, P]),

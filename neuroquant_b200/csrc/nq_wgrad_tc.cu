@@ -427,6 +427,63 @@ __global__ void __launch_bounds__(256) wg_reduce_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Finish of all stages' weight gradients in one launch: fixed-order sum of the pixel-split partials (read
+// coalesced, in packed order) and scatter into the reference layout (cout, cin_dst, k, k) + bias gradient.
+// Replaces 7 x (wg_reduce_kernel + unpack_wgrad_kernel): 14 launches of 7-10 us each on 0.1 .. 30 MB.
+// ---------------------------------------------------------------------------------------------
+struct WgFinishItem {
+  const float* ws;
+  float* dw_ref;
+  float* db_ref;
+  int psplits, N, rows_total;      // partial buffers, columns per row, rows (k*k*cin_p + 4)
+  int kk, cin, cin_p, cin_dst, cout, rr, cg;
+  int n4, pad_elems;               // float4 per partial; elements of the zero-filled channel pad (cin..cin_dst)
+};
+struct WgFinishMulti {
+  WgFinishItem t[NQ_MULTI_MAX];
+  int blk_start[NQ_MULTI_MAX + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) wg_finish_multi_kernel(const __grid_constant__ WgFinishMulti m) {
+  int ti = 0;
+  while (ti + 1 < m.n && (int)blockIdx.x >= m.blk_start[ti + 1]) ++ti;
+  const WgFinishItem& t = m.t[ti];
+  const int e = (blockIdx.x - m.blk_start[ti]) * 256 + threadIdx.x;
+  if (e < t.pad_elems) {  // channels cin .. cin_dst of the (rotated-weight) layout carry no gradient
+    const int per_co = (t.cin_dst - t.cin) * t.kk;
+    const int co = e / per_co, r = e - co * per_co;
+    t.dw_ref[((size_t)co * t.cin_dst + t.cin) * t.kk + r] = 0.f;
+  }
+  if (e >= t.n4) return;
+  const float4* w4 = reinterpret_cast<const float4*>(t.ws);
+  float4 s = w4[e];
+  for (int k = 1; k < t.psplits; ++k) {
+    const float4 v = w4[(size_t)k * t.n4 + e];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const int n4_per_row = t.N >> 2;
+  const int row = e / n4_per_row, col0 = (e - row * n4_per_row) * 4;
+  const int kdim = t.kk * t.cin_p;
+  if (row > kdim) return;  // the 3 zero rows after the bias row
+  const int tap = row / t.cin_p, ci = row - tap * t.cin_p;
+  if (row < kdim && ci >= t.cin) return;
+  const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int np = col0 + j;
+    const int grp = np / t.cg, c = np - grp * t.cg;
+    const int co = c * t.rr + grp;
+    if (grp >= t.rr || co >= t.cout) continue;
+    if (row == kdim) {
+      if (t.db_ref) t.db_ref[co] = v[j];
+    } else if (t.dw_ref) {
+      t.dw_ref[((size_t)co * t.cin_dst + ci) * t.kk + tap] = v[j];
+    }
+  }
+}
+
 int check_conv_desc(const nq_conv_desc* d);
 
 static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc_wgrad_plan* pl) {
@@ -543,7 +600,7 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   const uint8_t* dz = reinterpret_cast<const uint8_t*>(dz_split);
   int st = check_conv_desc(d);
   if (st) return st;
-  if (!pl || !x || !dz || !dwk || !workspace) return NQ_ERR_BAD_ARG;
+  if (!pl || !x || !dz || !workspace) return NQ_ERR_BAD_ARG;  // dwk NULL: the caller finishes with nq_tc_wgrad_finish_multi
   if (workspace_floats < pl->workspace_floats) return NQ_ERR_WORKSPACE;
   WgParams p{};
   p.x = x; p.dz = dz; p.ws = workspace;
@@ -563,10 +620,45 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   const int grid = pl->psplits * pl->msplit * pl->nsplits * pl->khg;
   wgrad_tc_kernel<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
   NQ_LAUNCH_CHECK();
+  if (!dwk) return NQ_OK;
   const int64_t n4 = (int64_t)(d->ksize * d->ksize * pl->C + 4) * pl->N / 4;
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   wg_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(workspace, n4, pl->psplits, dwk);
   NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_tc_wgrad_finish_multi(const nq_wgrad_finish_task* tasks, int n_tasks, void* stream) {
+  if (!tasks || n_tasks <= 0) return NQ_ERR_BAD_ARG;
+  for (int i0 = 0; i0 < n_tasks; i0 += NQ_MULTI_MAX) {
+    WgFinishMulti m{};
+    m.n = n_tasks - i0 < NQ_MULTI_MAX ? n_tasks - i0 : NQ_MULTI_MAX;
+    int blocks = 0;
+    for (int i = 0; i < m.n; ++i) {
+      const nq_wgrad_finish_task& t = tasks[i0 + i];
+      if (!t.d || !t.workspace || t.psplits <= 0 || t.n_cols <= 0 || t.n_cols % 4) return NQ_ERR_BAD_ARG;
+      const int st = check_conv_desc(t.d);
+      if (st) return st;
+      const nq_conv_desc* d = t.d;
+      if (t.cin_dst < d->cin || d->rh * d->rw * d->cg > t.n_cols) return NQ_ERR_BAD_ARG;
+      WgFinishItem& w = m.t[i];
+      w.ws = t.workspace; w.dw_ref = t.dw_ref; w.db_ref = t.db_ref;
+      w.psplits = t.psplits; w.N = t.n_cols;
+      w.kk = d->ksize * d->ksize; w.cin = d->cin; w.cin_p = d->cin_p; w.cin_dst = t.cin_dst; w.cout = d->cout;
+      w.rr = d->rh * d->rw; w.cg = d->cg;
+      w.rows_total = w.kk * d->cin_p + 4;
+      const long long n4 = (long long)w.rows_total * t.n_cols / 4;
+      const long long pad = t.dw_ref ? (long long)d->cout * (t.cin_dst - d->cin) * w.kk : 0;
+      if (n4 >= (1LL << 31) || pad >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
+      w.n4 = (int)n4; w.pad_elems = (int)pad;
+      m.blk_start[i] = blocks;
+      const long long work = n4 > pad ? n4 : pad;
+      blocks += (int)((work + 255) / 256);
+    }
+    m.blk_start[m.n] = blocks;
+    wg_finish_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(m);
+    NQ_LAUNCH_CHECK();
+  }
   return NQ_OK;
 }

@@ -599,14 +599,20 @@ class DecoderEngine:
                     p.dwk.append(torch.empty(d.kdim + 4, d.nout_p, device=self.device))
                     sp = self._wgrad_splits(d)
                     p.ws.append((torch.empty(sp * (d.kdim + 4) * d.nout_p, device=self.device) if sp > 1 else None, sp))
+        finish = []
         for i in range(last, -1, -1):
             d = p.desc[i]
             _, wt, _, _, _ = self._packed[i]
             ws, sp = p.ws[i]
             if isinstance(sp, L.TcWgradPlan):
+                # partial sums only (dwk = NULL): one multi-stage launch after the loop reduces and unpacks them all
                 L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_tc_conv_wgrad, C.byref(d), C.byref(sp), p.x[i].data_ptr(),
-                                  p.dz[i].data_ptr(), L.ptr(p.dwk[i]), L.ptr(ws), ws.numel(), st), "nq_tc_conv_wgrad")
-                self.launches += 2
+                                  p.dz[i].data_ptr(), None, L.ptr(ws), ws.numel(), st), "nq_tc_conv_wgrad")
+                self.launches += 1
+                du = p.head_desc16 if (i == last and p.head_desc16 is not None) else d
+                gw_, gb_ = views[i]
+                finish.append(L.WgFinishTask(C.pointer(du), L.ptr(ws), L.ptr(gw_), L.ptr(gb_), sp.psplits, sp.N,
+                                             self.stages[i].cin_src, 0))
             elif i == last:
                 L.check(self._run("head_wgrad", d, L.lib.nq_head_wgrad, C.byref(d), L.ptr(p.x[i]), L.ptr(p.dz[i]), L.ptr(p.dwk[i]),
                                   L.ptr(ws), ws.numel(), st), "nq_head_wgrad")
@@ -629,9 +635,13 @@ class DecoderEngine:
                 self.launches += 1
             s = self.stages[i]
             gw, gb = views[i]
-            du = p.head_desc16 if (i == last and p.head_desc16 is not None) else d
-            L.check(L.lib.nq_unpack_wgrad(C.byref(du), L.ptr(p.dwk[i]), s.cin_src, L.ptr(gw), L.ptr(gb), st), "nq_unpack_wgrad")
-            self.launches += 1
+            if not isinstance(sp, L.TcWgradPlan):
+                L.check(L.lib.nq_unpack_wgrad(C.byref(d), L.ptr(p.dwk[i]), s.cin_src, L.ptr(gw), L.ptr(gb), st), "nq_unpack_wgrad")
+                self.launches += 1
+        if finish:
+            arr = (L.WgFinishTask * len(finish))(*finish)
+            L.check(L.lib.nq_tc_wgrad_finish_multi(arr, len(finish), st), "nq_tc_wgrad_finish_multi")
+            self.launches += (len(finish) + L.MULTI_MAX - 1) // L.MULTI_MAX
         return flat
 
     def param_grads(self, grad_scale: float = 1.0, reg_w: float = 0.0, reg_b: float = 0.0, hyper: Optional[torch.Tensor] = None):
