@@ -274,6 +274,18 @@ int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* plan, const float
 int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, int d_stride, const float* bias_ref,
                         float* scale_packed, float* bias_packed, void* stream);
 
+/* Several nq_tc_pack_weight (wpk != NULL) and / or nq_tc_pack_epilogue (scale_packed or bias_packed != NULL) calls
+ * of the same or different stages in one launch: the weights of a calibration iteration are re-packed for every
+ * stage and direction after each optimiser step, 19 launches of 3-8 us otherwise. */
+typedef struct nq_tc_pack_task {
+  const nq_conv_desc* d;
+  const nq_tc_plan* plan;      /* may be NULL when wpk is NULL */
+  const float* w_ref; const float* zero_point; void* wpk;
+  const float* delta; const float* bias_ref; float* scale_packed; float* bias_packed;
+  int32_t cin_src, zp_stride, d_stride, reserved;
+} nq_tc_pack_task;
+int nq_tc_pack_multi(const nq_tc_pack_task* tasks, int n_tasks, void* stream);
+
 /* "split-bf16" storage: a tensor-core stage reads and writes its activations / gradients as TWO bf16
  * planes, hi = bf16(v) and lo = bf16(v - hi), plane 0 then plane 1, each NHWC with the padded channel
  * count of the fp32 layout (same bytes as fp32, 16 mantissa bits).  The producing epilogue converts once;

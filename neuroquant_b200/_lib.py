@@ -71,6 +71,13 @@ class WgFinishTask(C.Structure):
                 ("psplits", C.c_int32), ("n_cols", C.c_int32), ("cin_dst", C.c_int32), ("reserved", C.c_int32)]
 
 
+class TcPackTask(C.Structure):
+    """Mirror of nq_tc_pack_task."""
+    _fields_ = [("d", C.POINTER(ConvDesc)), ("plan", C.POINTER(TcPlan)), ("w_ref", C.c_void_p), ("zero_point", C.c_void_p),
+                ("wpk", C.c_void_p), ("delta", C.c_void_p), ("bias_ref", C.c_void_p), ("scale_packed", C.c_void_p),
+                ("bias_packed", C.c_void_p)] + [(n, C.c_int32) for n in ("cin_src", "zp_stride", "d_stride", "reserved")]
+
+
 MULTI_MAX = 16
 
 
@@ -109,6 +116,7 @@ def _load():
         "nq_tc_plan_conv": (I, [DP, I, I, I, TP]),
         "nq_tc_pack_weight": (I, [DP, TP, P, I, P, I, P, P]),
         "nq_tc_pack_epilogue": (I, [DP, P, I, P, P, P, P]),
+        "nq_tc_pack_multi": (I, [C.POINTER(TcPackTask), I, P]),
         "nq_tc_conv_fwd": (I, [DP, TP, P, P, P, P, P, P, P]),
         "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P]),
         "nq_tc_head_fwd_loss": (I, [DP, TP, P, P, P, P, I, P, F, F, P, P, P, P]),

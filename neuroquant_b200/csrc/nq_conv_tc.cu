@@ -794,7 +794,7 @@ __device__ __forceinline__ int unpack_cout(int np, int rh, int rw, int c_grp, in
   return c * rh * rw + grp;
 }
 
-__global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackParams q) {
+__device__ __forceinline__ void tc_pack_body(const TcPackParams& q, long long e_first, long long e_step) {
   const int taps = q.ks * q.ks;
   const int tiles_n = (q.N + q.NT - 1) / q.NT;
   const int stages_per_ntile = (q.C / q.SBC) * taps;
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackParams q) {
   // one thread per (n tile, stage, k-group, column): both planes
   const long long per_tile_full = (long long)stages_per_ntile * g_per_stage * q.NT;
   const long long total = per_tile_full * tiles_n;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+  for (long long e = e_first; e < total; e += e_step) {
     const int tn = (int)(e / per_tile_full);
     long long r = e - (long long)tn * per_tile_full;
     const int nt = min(q.NT, q.N - tn * q.NT);
@@ -864,17 +864,42 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackParams q) {
   }
 }
 
+__global__ void __launch_bounds__(256) tc_pack_kernel(const TcPackParams q) {
+  tc_pack_body(q, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// Several packs (every stage's forward and data-gradient operand, plus the per-column epilogue vectors) in one
+// launch: a block belongs to one task and strides over that task's elements with the task's own block count.
+struct TcPackVec {
+  const float* delta; const float* bias; float* scale_out; float* bias_out;
+  int d_stride, cout, rh, rw, c_grp, cg, N;
+};
+struct TcPackMulti {
+  TcPackParams t[NQ_MULTI_MAX];
+  TcPackVec v[NQ_MULTI_MAX];   // v[i].N == 0: task i packs no vectors
+  int blk_start[NQ_MULTI_MAX + 1];
+  int n;
+};
+__device__ __forceinline__ void tc_pack_vec_body(const TcPackVec& v, int first, int step);
+
 // per-column epilogue vectors in packed order: scale[n] = delta[co] (or 1), bias[n] = b[co] (or 0)
-__global__ void __launch_bounds__(256) tc_pack_vec_kernel(const float* __restrict__ delta, int d_stride,
-                                                          const float* __restrict__ bias, int cout, int rh, int rw,
-                                                          int c_grp, int cg, int N, float* __restrict__ scale_out,
-                                                          float* __restrict__ bias_out) {
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-    const int co = unpack_cout(n, rh, rw, c_grp, cg);
-    const bool ok = co >= 0 && co < cout;
-    if (scale_out) scale_out[n] = (ok && delta) ? delta[co * d_stride] : 1.0f;
-    if (bias_out) bias_out[n] = (ok && bias) ? bias[co] : 0.0f;
+__device__ __forceinline__ void tc_pack_vec_body(const TcPackVec& v, int first, int step) {
+  for (int n = first; n < v.N; n += step) {
+    const int co = unpack_cout(n, v.rh, v.rw, v.c_grp, v.cg);
+    const bool ok = co >= 0 && co < v.cout;
+    if (v.scale_out) v.scale_out[n] = (ok && v.delta) ? v.delta[co * v.d_stride] : 1.0f;
+    if (v.bias_out) v.bias_out[n] = (ok && v.bias) ? v.bias[co] : 0.0f;
   }
+}
+__global__ void __launch_bounds__(256) tc_pack_vec_kernel(const TcPackVec v) {
+  tc_pack_vec_body(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(256) tc_pack_multi_kernel(const __grid_constant__ TcPackMulti m) {
+  int ti = 0;
+  while (ti + 1 < m.n && (int)blockIdx.x >= m.blk_start[ti + 1]) ++ti;
+  const int lb = blockIdx.x - m.blk_start[ti], nb = m.blk_start[ti + 1] - m.blk_start[ti];
+  if (m.t[ti].out != nullptr) tc_pack_body(m.t[ti], (long long)lb * blockDim.x + threadIdx.x, (long long)nb * blockDim.x);
+  if (m.v[ti].N > 0 && lb == 0) tc_pack_vec_body(m.v[ti], threadIdx.x, blockDim.x);
 }
 
 int check_conv_desc(const nq_conv_desc* d);
@@ -1014,22 +1039,67 @@ extern "C" int nq_tc_plan_conv(const nq_conv_desc* d, int dir, int a_planes, int
   return fill_plan(d, dir, a_planes, b_planes, plan);
 }
 
-extern "C" int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* pl, const float* w_ref, int cin_src,
-                                 const float* zero_point, int zp_stride, void* wpk, void* stream) {
+static int fill_pack(const nq_conv_desc* d, const nq_tc_plan* pl, const float* w_ref, int cin_src, const float* zero_point,
+                     int zp_stride, void* wpk, TcPackParams& q, long long& blocks) {
   int st = check_conv_desc(d);
   if (st) return st;
   if (!pl || !w_ref || !wpk || cin_src < d->cin) return NQ_ERR_BAD_ARG;
-  TcPackParams q{};
   q.w = w_ref; q.zp = zero_point; q.zp_stride = zp_stride; q.out = reinterpret_cast<uint8_t*>(wpk);
   q.cout = d->cout; q.cin = d->cin; q.cin_src = cin_src; q.ks = d->ksize;
   q.rh = d->rh; q.rw = d->rw; q.c_grp = d->c_grp; q.cg = d->cg;
   q.dir = pl->dir; q.C = pl->C; q.N = pl->N; q.NT = pl->NT; q.KC = pl->KC; q.SBC = pl->SBC; q.b_planes = pl->b_planes; q.bcat = pl->bcat;
   const long long total = (long long)(pl->C / pl->SBC) * d->ksize * d->ksize * (pl->SBC / 8) * pl->NT * pl->tiles_n;
-  long long blocks = (total + 255) / 256;
+  blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  return NQ_OK;
+}
+
+extern "C" int nq_tc_pack_weight(const nq_conv_desc* d, const nq_tc_plan* pl, const float* w_ref, int cin_src,
+                                 const float* zero_point, int zp_stride, void* wpk, void* stream) {
+  TcPackParams q{};
+  long long blocks = 0;
+  const int st = fill_pack(d, pl, w_ref, cin_src, zero_point, zp_stride, wpk, q, blocks);
+  if (st) return st;
   tc_pack_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(q);
   NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_tc_pack_multi(const nq_tc_pack_task* tasks, int n_tasks, void* stream) {
+  if (!tasks || n_tasks <= 0) return NQ_ERR_BAD_ARG;
+  for (int i0 = 0; i0 < n_tasks; i0 += NQ_MULTI_MAX) {
+    TcPackMulti m{};
+    m.n = n_tasks - i0 < NQ_MULTI_MAX ? n_tasks - i0 : NQ_MULTI_MAX;
+    int blocks = 0;
+    for (int i = 0; i < m.n; ++i) {
+      const nq_tc_pack_task& t = tasks[i0 + i];
+      if (!t.d) return NQ_ERR_BAD_ARG;
+      long long nb = 0;
+      if (t.wpk) {
+        const int st = fill_pack(t.d, t.plan, t.w_ref, t.cin_src, t.zero_point, t.zp_stride, t.wpk, m.t[i], nb);
+        if (st) return st;
+      } else {
+        const int st = check_conv_desc(t.d);
+        if (st) return st;
+      }
+      if (t.scale_packed || t.bias_packed) {
+        const nq_conv_desc* d = t.d;
+        m.v[i] = TcPackVec{t.delta, t.bias_ref, t.scale_packed, t.bias_packed, t.d_stride, d->cout, d->rh, d->rw, d->c_grp, d->cg,
+                           d->rh * d->rw * d->cg};
+        if (nb < 1) nb = 1;
+      }
+      if (nb < 1) return NQ_ERR_BAD_ARG;  // a task with nothing to do
+      // cap the share of one task so that 16 tasks stay within a few waves
+      const long long cap = (long long)sm_count() * 4;
+      if (nb > cap) nb = cap;
+      m.blk_start[i] = blocks;
+      blocks += (int)nb;
+    }
+    m.blk_start[m.n] = blocks;
+    tc_pack_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(m);
+    NQ_LAUNCH_CHECK();
+  }
   return NQ_OK;
 }
 
@@ -1038,8 +1108,8 @@ extern "C" int nq_tc_pack_epilogue(const nq_conv_desc* d, const float* delta, in
   int st = check_conv_desc(d);
   if (st) return st;
   const int N = d->rh * d->rw * d->cg;
-  tc_pack_vec_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(delta, d_stride, bias_ref, d->cout, d->rh, d->rw,
-                                                                     d->c_grp, d->cg, N, scale_packed, bias_packed);
+  TcPackVec v{delta, bias_ref, scale_packed, bias_packed, d_stride, d->cout, d->rh, d->rw, d->c_grp, d->cg, N};
+  tc_pack_vec_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(v);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

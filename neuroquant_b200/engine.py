@@ -401,6 +401,7 @@ class DecoderEngine:
             L.check(L.lib.nq_fakequant_fwd_multi(arr, len(tasks), L.ptr(self.reg_sum) if reg_b is not None else None,
                                                  float(reg_b or 0.0), st), "nq_fakequant_fwd_multi")
             self.launches += (len(tasks) + L.MULTI_MAX - 1) // L.MULTI_MAX
+        packs = []
         for i, (s, d, (wk, wt, bp, deq_w, deq_b)) in enumerate(zip(self.stages, p.desc, self._packed)):
             if self.mode == "off":
                 w_for_conv, b_for_conv, cin_src = s.weight, s.bias, s.geom.cin
@@ -421,9 +422,8 @@ class DecoderEngine:
                         "nq_pack_weight")
                 self.launches += 1
                 if need_wt and i > 0:
-                    L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_dgrad[i]), L.ptr(w_for_conv), cin_src, None, 0,
-                                                    wpk_d.data_ptr(), st), "nq_tc_pack_weight")
-                    self.launches += 1
+                    packs.append(L.TcPackTask(C.pointer(d), C.pointer(p.tc_dgrad[i]), L.ptr(w_for_conv), None, wpk_d.data_ptr(),
+                                              None, None, None, None, cin_src, 0, 0, 0))
                 continue
             # forward operand: integer weights (codes - zero_point), exact in ONE bf16 plane, whenever the
             # codes are integers and are what the conv multiplies (no rotation in between); the step size
@@ -433,22 +433,22 @@ class DecoderEngine:
             exact1 = integer and (self.mode == "uaq" or not self.soft_w)
             bpl = 1 if exact1 else 2
             self._fwd_bpl[i] = bpl
+            # forward operand + per-column epilogue vectors: one task; data-gradient operand: another; all stages'
+            # tasks go out in one multi-pack launch below
             if integer:
                 ds = 1 if s.delta_w.numel() > 1 else 0
-                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_fwd[(i, bpl)]), L.ptr(s.codes_w), s.cin_src,
-                                                L.ptr(s.zp_w), ds, wpk_f.data_ptr(), st), "nq_tc_pack_weight")
-                L.check(L.lib.nq_tc_pack_epilogue(C.byref(d), L.ptr(s.delta_w), ds, L.ptr(b_for_conv), L.ptr(scale_p), L.ptr(bp), st),
-                        "nq_tc_pack_epilogue")
+                packs.append(L.TcPackTask(C.pointer(d), C.pointer(p.tc_fwd[(i, bpl)]), L.ptr(s.codes_w), L.ptr(s.zp_w), wpk_f.data_ptr(),
+                                          L.ptr(s.delta_w), L.ptr(b_for_conv), L.ptr(scale_p), L.ptr(bp), s.cin_src, ds, ds, 0))
             else:
-                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_fwd[(i, bpl)]), L.ptr(w_for_conv), cin_src,
-                                                None, 0, wpk_f.data_ptr(), st), "nq_tc_pack_weight")
-                L.check(L.lib.nq_tc_pack_epilogue(C.byref(d), None, 0, L.ptr(b_for_conv), L.ptr(scale_p), L.ptr(bp), st),
-                        "nq_tc_pack_epilogue")
-            self.launches += 2
+                packs.append(L.TcPackTask(C.pointer(d), C.pointer(p.tc_fwd[(i, bpl)]), L.ptr(w_for_conv), None, wpk_f.data_ptr(),
+                                          None, L.ptr(b_for_conv), L.ptr(scale_p), L.ptr(bp), cin_src, 0, 0, 0))
             if need_wt and i > 0:
-                L.check(L.lib.nq_tc_pack_weight(C.byref(d), C.byref(p.tc_dgrad[i]), L.ptr(w_for_conv), cin_src, None, 0,
-                                                wpk_d.data_ptr(), st), "nq_tc_pack_weight")
-                self.launches += 1
+                packs.append(L.TcPackTask(C.pointer(d), C.pointer(p.tc_dgrad[i]), L.ptr(w_for_conv), None, wpk_d.data_ptr(),
+                                          None, None, None, None, cin_src, 0, 0, 0))
+        if packs:
+            arr = (L.TcPackTask * len(packs))(*packs)
+            L.check(L.lib.nq_tc_pack_multi(arr, len(packs), st), "nq_tc_pack_multi")
+            self.launches += (len(packs) + L.MULTI_MAX - 1) // L.MULTI_MAX
         self._weights_valid = True
         self._wt_valid = need_wt
 

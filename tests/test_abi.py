@@ -119,6 +119,7 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
         '  printf("%zu %zu\\n", sizeof(nq_fq_task), offsetof(nq_fq_task, want_reg));\n'
         '  printf("%zu %zu\\n", sizeof(nq_ada_task), offsetof(nq_ada_task, use_reg));\n'
         '  printf("%zu %zu\\n", sizeof(nq_wgrad_finish_task), offsetof(nq_wgrad_finish_task, cin_dst));\n'
+        '  printf("%zu %zu\\n", sizeof(nq_tc_pack_task), offsetof(nq_tc_pack_task, cin_src));\n'
         '  return 0;\n}\n')
     exe = tmp_path / "layout"
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
@@ -129,5 +130,6 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
             (C.sizeof(L.TcWgradPlan), L.TcWgradPlan.workspace_floats.offset),
             (C.sizeof(L.FqTask), L.FqTask.want_reg.offset),
             (C.sizeof(L.AdaTask), L.AdaTask.use_reg.offset),
-            (C.sizeof(L.WgFinishTask), L.WgFinishTask.cin_dst.offset)]
+            (C.sizeof(L.WgFinishTask), L.WgFinishTask.cin_dst.offset),
+            (C.sizeof(L.TcPackTask), L.TcPackTask.cin_src.offset)]
     assert got == want
