@@ -450,13 +450,327 @@ __global__ void __launch_bounds__(HT_H * HT_W) head_fwd_loss_kernel(const HeadPa
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head forward, 4 pixels per thread.  The kernel above issues 16 shared-memory wavefronts (2 input float4 + 8
+// broadcast weight float4) per 24 FMAs and is bound by the shared-memory pipe (92 % busy, 0.27 ms).  Here a thread
+// owns a 4-row strip of one column: the 8 weight loads of a (tap, channel quad) feed 4 pixels, and the 6 input rows
+// of a strip are loaded once per kernel column -- 72 wavefronts per 288 FMAs, balanced with the FMA pipe.
+// Same staging (pixel-major, 8-channel chunks), same per-pixel epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr int HV_TW = 32, HV_TH = 32, HV_THREADS = 256;  // thread = (column lx, strip ly of 4 rows)
+constexpr int HV_SMEM = ((HV_TH + 2) * (HV_TW + 2) * H_PS + 9 * H_CH * 4) * 4;
+
+__global__ void __launch_bounds__(HV_THREADS) head_fwd_loss_strip_kernel(const HeadParams q) {
+  extern __shared__ __align__(16) float hsm[];
+  float* xs = hsm;                                         // [(HV_TH + 2)][(HV_TW + 2)][H_PS]
+  float* ws = hsm + (HV_TH + 2) * (HV_TW + 2) * H_PS;      // [9][H_CH][4]
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const int lx = tid % HV_TW, ly = tid / HV_TW;
+  const int tiles_w = (q.w_ + HV_TW - 1) / HV_TW, tiles_h = (q.h + HV_TH - 1) / HV_TH;
+  int b = blockIdx.x;
+  const int tw = b % tiles_w; b /= tiles_w;
+  const int th = b % tiles_h;
+  const int bn = b / tiles_h;
+  const int x0 = tw * HV_TW, y0 = th * HV_TH;
+
+  float acc[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+
+  for (int c0 = 0; c0 < q.C; c0 += H_CH) {
+    const int cw = min(H_CH, q.C - c0);  // 8 or 4
+    const int c4n = cw >> 2;
+    __syncthreads();
+#pragma unroll 3
+    for (int i = tid; i < (HV_TH + 2) * (HV_TW + 2) * 2; i += HV_THREADS) {
+      const int c4 = i & 1, pix = i >> 1;
+      const int sy = pix / (HV_TW + 2), sx = pix - sy * (HV_TW + 2);
+      const int gx = x0 + sx - 1, gy = y0 + sy - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < c4n && (unsigned)gx < (unsigned)q.w_ && (unsigned)gy < (unsigned)q.h) {
+        const int64_t o = (int64_t)((bn * q.h + gy) * q.w_ + gx) * q.C + c0 + c4 * 4;
+        if (q.x_hi) {
+          const uint2 hb = __ldg(reinterpret_cast<const uint2*>(q.x_hi + o)), lb = __ldg(reinterpret_cast<const uint2*>(q.x_lo + o));
+          v.x = bf16_bits_to_f(hb.x & 0xFFFFu) + bf16_bits_to_f(lb.x & 0xFFFFu);
+          v.y = bf16_bits_to_f(hb.x >> 16) + bf16_bits_to_f(lb.x >> 16);
+          v.z = bf16_bits_to_f(hb.y & 0xFFFFu) + bf16_bits_to_f(lb.y & 0xFFFFu);
+          v.w = bf16_bits_to_f(hb.y >> 16) + bf16_bits_to_f(lb.y >> 16);
+        } else {
+          v = ldg4(q.x + o);
+        }
+      }
+      *reinterpret_cast<float4*>(&xs[pix * H_PS + c4 * 4]) = v;
+    }
+    for (int i = tid; i < 9 * H_CH; i += HV_THREADS) {
+      const int tap = i / H_CH, c = i % H_CH;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < cw) v = ldg4(q.w + ((int64_t)tap * q.C + c0 + c) * 4);
+      *reinterpret_cast<float4*>(&ws[i * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const float* xcol = &xs[((4 * ly) * (HV_TW + 2) + (lx + kw)) * H_PS];
+#pragma unroll
+      for (int c4 = 0; c4 < 2; ++c4) {
+        float4 xv[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) xv[r] = *reinterpret_cast<const float4*>(xcol + r * (HV_TW + 2) * H_PS + c4 * 4);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float* wp = &ws[((kh * 3 + kw) * H_CH + c4 * 4) * 4];
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4),
+                       w2 = *reinterpret_cast<const float4*>(wp + 8), w3 = *reinterpret_cast<const float4*>(wp + 12);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 x = xv[i + kh];
+            acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]); acc[i][2] = fmaf(x.x, w0.z, acc[i][2]);
+            acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]); acc[i][2] = fmaf(x.y, w1.z, acc[i][2]);
+            acc[i][0] = fmaf(x.z, w2.x, acc[i][0]); acc[i][1] = fmaf(x.z, w2.y, acc[i][1]); acc[i][2] = fmaf(x.z, w2.z, acc[i][2]);
+            acc[i][0] = fmaf(x.w, w3.x, acc[i][0]); acc[i][1] = fmaf(x.w, w3.y, acc[i][1]); acc[i][2] = fmaf(x.w, w3.z, acc[i][2]);
+          }
+        }
+      }
+    }
+  }
+
+  float loss = 0.f;
+  const int px = x0 + lx;
+  const int64_t plane = (int64_t)q.h * q.w_;
+  const float b0 = q.bias[0], b1 = q.bias[1], b2 = q.bias[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int py = y0 + 4 * ly + i;
+    if (px >= q.w_ || py >= q.h) continue;
+    const float v[3] = {acc[i][0] + b0, acc[i][1] + b1, acc[i][2] + b2};
+    float g[3] = {0.f, 0.f, 0.f};
+    const int64_t o = (int64_t)bn * 3 * plane + (int64_t)py * q.w_ + px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float outv, dout;
+      if (q.out_bias == 0) {
+        const float t = tanhf(v[c]);
+        outv = t * 0.5f + 0.5f;
+        dout = 0.5f * (1.0f - t * t);
+      } else {
+        outv = sigmoid_f(v[c]);
+        dout = outv * (1.0f - outv);
+      }
+      if (q.img) q.img[o + c * plane] = outv;
+      if (q.target) {
+        const float dlt = outv - __ldg(q.target + o + c * plane);
+        const float a = fabsf(dlt);
+        if (q.p == 2.0f) {
+          loss += dlt * dlt;
+          g[c] = 2.0f * dlt * q.inv_mean * dout;
+        } else {
+          loss += powf(a, q.p);
+          const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+          g[c] = q.p * powf(a, q.p - 1.0f) * sgn * q.inv_mean * dout;
+        }
+      }
+    }
+    const int64_t pix = (int64_t)(bn * q.h + py) * q.w_ + px;
+    if (q.dz) *reinterpret_cast<float4*>(q.dz + pix * 4) = make_float4(g[0], g[1], g[2], 0.f);
+    if (q.dz_hi) {
+      uint16_t hb[3], lb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        hb[c] = f_to_bf16_bits(g[c]);
+        lb[c] = f_to_bf16_bits(g[c] - bf16_bits_to_f(hb[c]));
+      }
+      *reinterpret_cast<uint4*>(q.dz_hi + pix * 8) = make_uint4((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), hb[2], 0u, 0u);
+      *reinterpret_cast<uint4*>(q.dz_lo + pix * 8) = make_uint4((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), lb[2], 0u, 0u);
+    }
+  }
+  if (q.target && q.loss_sum) {
+    loss = block_sum(loss, red);
+    if (tid == 0) atomicAdd(q.loss_sum, loss);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head forward for the split-bf16 engine, asynchronous.  Both kernels above stage every 8-channel chunk
+// synchronously (global -> registers -> convert -> shared, two block barriers per chunk) and sit at ~0.26 ms whatever
+// their inner loop does: neither DRAM (19 %) nor the FMA pipe is busy, the loads are simply exposed.  Here persistent
+// CTAs stream the RAW bf16 planes with cp.async through a 4-deep ring of (tile, chunk) items, the hi + lo sum is
+// formed in registers when a pixel is read, and all weights stay resident: no staging pass, one barrier per item.
+// Thread mapping and inner loop as head_fwd_loss_strip_kernel (4-row strip of one column).
+// ---------------------------------------------------------------------------------------------
+constexpr int HA_TW = 32, HA_TH = 32, HA_THREADS = 256, HA_STAGES = 4;
+constexpr int HA_NPIX = (HA_TH + 2) * (HA_TW + 2);
+constexpr int HA_STAGE_BYTES = HA_NPIX * 16 * 2;  // hi plane + lo plane, 8 channels (16 bytes) per pixel each
+constexpr int HA_MAXC = 64;
+
+__device__ __forceinline__ void ha_cp16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(HA_THREADS, 1) head_fwd_loss_async_kernel(const HeadParams q) {
+  extern __shared__ __align__(16) uint8_t hraw[];
+  float* ws = reinterpret_cast<float*>(hraw + HA_STAGES * HA_STAGE_BYTES);  // [9][C][4] all channels, loaded once
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const int lx = tid % HA_TW, ly = tid / HA_TW;
+  const int tiles_w = (q.w_ + HA_TW - 1) / HA_TW, tiles_h = (q.h + HA_TH - 1) / HA_TH;
+  const int tiles = tiles_w * tiles_h * q.n;
+  const int nch = q.C / 8;  // 8-channel chunks per tile (C % 8 == 0 on this path)
+  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int items = my_tiles * nch;
+  const uint32_t raw0 = (uint32_t)__cvta_generic_to_shared(hraw);
+
+  for (int i = tid; i < 9 * q.C; i += HA_THREADS) *reinterpret_cast<float4*>(&ws[i * 4]) = ldg4(q.w + (int64_t)i * 4);
+
+  auto issue = [&](int item) {  // one (tile, chunk) item -> ring slot item % HA_STAGES
+    if (item < items) {
+      const int t = blockIdx.x + (item / nch) * gridDim.x, c0 = (item % nch) * 8;
+      const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, bn = t / (tiles_w * tiles_h);
+      const int x0 = tw * HA_TW, y0 = th * HA_TH;
+      const uint32_t dst = raw0 + (item % HA_STAGES) * HA_STAGE_BYTES;
+      for (int pix = tid; pix < HA_NPIX; pix += HA_THREADS) {
+        const int sy = pix / (HA_TW + 2), sx = pix - sy * (HA_TW + 2);
+        const int gx = x0 + sx - 1, gy = y0 + sy - 1;
+        const bool ok = (unsigned)gx < (unsigned)q.w_ && (unsigned)gy < (unsigned)q.h;
+        const int64_t o = ok ? (int64_t)((bn * q.h + gy) * q.w_ + gx) * q.C + c0 : 0;
+        ha_cp16(dst + pix * 16, q.x_hi + o, ok ? 16u : 0u);
+        ha_cp16(dst + HA_NPIX * 16 + pix * 16, q.x_lo + o, ok ? 16u : 0u);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (empty groups keep the wait counts uniform)
+  };
+
+#pragma unroll
+  for (int k = 0; k < HA_STAGES - 1; ++k) issue(k);
+
+  float acc[4][3];
+  float loss = 0.f;
+  const int64_t plane = (int64_t)q.h * q.w_;
+  for (int item = 0; item < items; ++item) {
+    const int ch = item % nch;
+    if (ch == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(HA_STAGES - 2) : "memory");
+    __syncthreads();               // item's data visible to all; everyone is done with the slot refilled next
+    issue(item + HA_STAGES - 1);
+    const uint8_t* hi = hraw + (item % HA_STAGES) * HA_STAGE_BYTES;
+    const uint8_t* lo = hi + HA_NPIX * 16;
+    const float* wc = ws + ch * 8 * 4;  // weights of this chunk: ws[(tap * C + ch * 8 + c) * 4]
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int p0 = (4 * ly) * (HA_TW + 2) + lx + kw;
+      float xv[6][8];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const uint4 h = *reinterpret_cast<const uint4*>(hi + (p0 + r * (HA_TW + 2)) * 16);
+        const uint4 l = *reinterpret_cast<const uint4*>(lo + (p0 + r * (HA_TW + 2)) * 16);
+        xv[r][0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+        xv[r][1] = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
+        xv[r][2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+        xv[r][3] = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
+        xv[r][4] = __uint_as_float(h.z << 16) + __uint_as_float(l.z << 16);
+        xv[r][5] = __uint_as_float(h.z & 0xFFFF0000u) + __uint_as_float(l.z & 0xFFFF0000u);
+        xv[r][6] = __uint_as_float(h.w << 16) + __uint_as_float(l.w << 16);
+        xv[r][7] = __uint_as_float(h.w & 0xFFFF0000u) + __uint_as_float(l.w & 0xFFFF0000u);
+      }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const float* wp = wc + (kh * 3 + kw) * q.C * 4;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp + c * 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][0] = fmaf(xv[i + kh][c], wv.x, acc[i][0]);
+            acc[i][1] = fmaf(xv[i + kh][c], wv.y, acc[i][1]);
+            acc[i][2] = fmaf(xv[i + kh][c], wv.z, acc[i][2]);
+          }
+        }
+      }
+    }
+    if (ch != nch - 1) continue;
+    // ---- per-pixel epilogue of the finished tile (OutImg + loss + dL/dz), as in the kernels above
+    const int t = blockIdx.x + (item / nch) * gridDim.x;
+    const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, bn = t / (tiles_w * tiles_h);
+    const int px = tw * HA_TW + lx;
+    const float b0 = q.bias[0], b1 = q.bias[1], b2 = q.bias[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int py = th * HA_TH + 4 * ly + i;
+      if (px >= q.w_ || py >= q.h) continue;
+      const float v[3] = {acc[i][0] + b0, acc[i][1] + b1, acc[i][2] + b2};
+      float g[3] = {0.f, 0.f, 0.f};
+      const int64_t o = (int64_t)bn * 3 * plane + (int64_t)py * q.w_ + px;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float outv, dout;
+        if (q.out_bias == 0) {
+          const float tt = tanhf(v[c]);
+          outv = tt * 0.5f + 0.5f;
+          dout = 0.5f * (1.0f - tt * tt);
+        } else {
+          outv = sigmoid_f(v[c]);
+          dout = outv * (1.0f - outv);
+        }
+        if (q.img) q.img[o + c * plane] = outv;
+        if (q.target) {
+          const float dlt = outv - __ldg(q.target + o + c * plane);
+          const float a = fabsf(dlt);
+          if (q.p == 2.0f) {
+            loss += dlt * dlt;
+            g[c] = 2.0f * dlt * q.inv_mean * dout;
+          } else {
+            loss += powf(a, q.p);
+            const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+            g[c] = q.p * powf(a, q.p - 1.0f) * sgn * q.inv_mean * dout;
+          }
+        }
+      }
+      if (q.dz_hi) {
+        const int64_t pix = (int64_t)(bn * q.h + py) * q.w_ + px;
+        uint16_t hb[3], lb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          hb[c] = f_to_bf16_bits(g[c]);
+          lb[c] = f_to_bf16_bits(g[c] - bf16_bits_to_f(hb[c]));
+        }
+        *reinterpret_cast<uint4*>(q.dz_hi + pix * 8) = make_uint4((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), hb[2], 0u, 0u);
+        *reinterpret_cast<uint4*>(q.dz_lo + pix * 8) = make_uint4((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), lb[2], 0u, 0u);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (q.target && q.loss_sum) {
+    loss = block_sum(loss, red);
+    if (tid == 0) atomicAdd(q.loss_sum, loss);
+  }
+}
+
 static inline int64_t hcdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // (A register-blocked variant -- 2 x 4 pixels per thread over a channel-planar shared-memory tile -- was measured at
 // 0.31 ms against 0.27 ms for this kernel at 1280x640x2: with 44 KB of staging per CTA its synchronous tile loads are
 // exposed, and the head's input arrives as split-bf16 NHWC, which needs a converting transpose.  Not kept.)
 static int launch_head_fwd(const HeadParams& q, cudaStream_t s) {
-  const int64_t blocks = hcdiv(q.w_, HT_W) * hcdiv(q.h, HT_H) * q.n;
-  head_fwd_loss_kernel<<<(unsigned)blocks, HT_H * HT_W, 0, s>>>(q);
+  static const bool v1 = getenv("NQ_HEAD_V1") != nullptr;  // A/B switch: the one-pixel-per-thread kernel
+  static const bool v2 = getenv("NQ_HEAD_V2") != nullptr;  // A/B switch: the synchronous 4-row-strip kernel
+  if (v1) {
+    const int64_t blocks = hcdiv(q.w_, HT_W) * hcdiv(q.h, HT_H) * q.n;
+    head_fwd_loss_kernel<<<(unsigned)blocks, HT_H * HT_W, 0, s>>>(q);
+  } else if (q.x_hi && !q.target && !v2 && q.C % 8 == 0 && q.C <= HA_MAXC) {
+    // decode (no target): the asynchronous kernel; with the loss epilogue its 8 warps per SM cannot hide the target
+    // loads and gradient stores, and the synchronous strip kernel below is faster (0.26 vs 0.29 ms at 1280x640x2)
+    const int smem = HA_STAGES * HA_STAGE_BYTES + 9 * q.C * 16;
+    NQ_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_loss_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t tiles = hcdiv(q.w_, HA_TW) * hcdiv(q.h, HA_TH) * q.n;
+    const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+    head_fwd_loss_async_kernel<<<(unsigned)grid, HA_THREADS, smem, s>>>(q);
+  } else {
+    NQ_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_loss_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HV_SMEM));
+    const int64_t blocks = hcdiv(q.w_, HV_TW) * hcdiv(q.h, HV_TH) * q.n;
+    head_fwd_loss_strip_kernel<<<(unsigned)blocks, HV_THREADS, HV_SMEM, s>>>(q);
+  }
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }
