@@ -323,7 +323,7 @@ typedef struct nq_tc_wgrad_plan {
   int32_t ncg, G, MB, NC, nsplits, TR;
   int32_t nkh, khg, AR;        /* kernel rows per CTA, kernel-row groups, staged input rows */
   int32_t msplit, ncg_c;       /* input channel-group slices (GEMM-M split across CTAs), groups per slice */
-  int32_t reserved;
+  int32_t bcat;                /* 1: both dZ planes as one MMA operand (2 MMAs per pixel step instead of 3) */
   int32_t CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf, smem_bytes;
   int32_t tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
   int64_t workspace_floats;    /* partial-gradient workspace the caller provides */

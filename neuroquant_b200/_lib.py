@@ -45,7 +45,7 @@ class TcPlan(C.Structure):
 class TcWgradPlan(C.Structure):
     """Mirror of nq_tc_wgrad_plan."""
     _fields_ = [(n, C.c_int32) for n in
-                ("C", "N", "a_planes", "b_planes", "ncg", "G", "MB", "NC", "nsplits", "TR", "nkh", "khg", "AR", "msplit", "ncg_c", "reserved",
+                ("C", "N", "a_planes", "b_planes", "ncg", "G", "MB", "NC", "nsplits", "TR", "nkh", "khg", "AR", "msplit", "ncg_c", "bcat",
                  "CGS_A", "CGS_B",
                  "a_plane_bytes", "b_plane_bytes", "buf_bytes", "nbuf", "smem_bytes", "tiles_x", "tiles_y",
                  "tiles_total", "psplits", "tiles_per_split")] + [("workspace_floats", C.c_int64)]

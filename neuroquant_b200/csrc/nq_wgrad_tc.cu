@@ -43,6 +43,7 @@ struct WgParams {
   int TR;           // tile rows
   int nkh, khg, AR; // kernel rows per CTA, number of kernel-row groups, staged input rows (TR + nkh - 1)
   int msplit, ncg_c; // channel-group slices of the input (GEMM-M split across CTAs), groups per slice
+  int bcat;          // the two dZ planes (adjacent in the column-group dimension of a buffer) as ONE operand of 2 NC columns
   int tiles_x, tiles_y, tiles_total, psplits, tiles_per_split;
   int a_planes, b_planes;
   int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
@@ -199,6 +200,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128, N = nc
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * nc) >> 3) << 17);  // N = 2 nc
+    const uint32_t acc_cols = (uint32_t)p.NC << p.bcat;
     const uint32_t a_hi32 = ((uint32_t)p.CGS_A >> 4) | (1u << 14), b_hi32 = ((uint32_t)p.CGS_B >> 4) | (1u << 14);
     const uint32_t lbo_bits = (128u >> 4) << 16;
     const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)p.b_plane_bytes >> 4;
@@ -222,11 +225,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
           for (int khl = 0; khl < 7; ++khl) {
             if (khl >= nkh) break;
-            const uint32_t a_lo = a16 + (r + khl) * row16, b_lo = b16 + r * row16, d = tmem_base + khl * p.NC;
+            const uint32_t a_lo = a16 + (r + khl) * row16, b_lo = b16 + r * row16, d = tmem_base + khl * acc_cols;
             if (leader) {
-              wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, r == 0 ? accum : 1u);
-              if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
-              if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+              if (p.bcat) {  // x_hi * [dz_hi | dz_lo] in one MMA of 2 NC columns, then x_lo * dz_hi: 2 A-tile reads, not 3
+                wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc2, r == 0 ? accum : 1u);
+                wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+              } else {
+                wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, r == 0 ? accum : 1u);
+                if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+              }
             }
           }
         }
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
               if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
             }
             a_lo += mb_step16;
-            d += p.NC;
+            d += acc_cols;
           }
         }
         accum = 1;
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           } else if (g == Gc && ch < 4 && kh == 0 && cg0 == 0) {
             orow = p.ks * p.ks * p.C + ch;  // bias gradient row (+ 3 zero rows)
           }
-          const uint32_t taddr = tmem_base + (khl * p.MB + mb) * p.NC + ((uint32_t)(q * 32) << 16);
+          const uint32_t taddr = tmem_base + (khl * p.MB + mb) * (p.NC << p.bcat) + ((uint32_t)(q * 32) << 16);
           for (int c0 = 0; c0 < nc; c0 += 16) {
             uint32_t v[16];
             asm volatile(
@@ -394,6 +402,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 : "r"(taddr + c0)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (p.bcat) {  // + the x_hi * dz_lo partial sums, NC columns further
+              uint32_t v2[16];
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                  : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+                    "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15])
+                  : "r"(taddr + p.NC + c0)
+                  : "memory");
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(v2[k]));
+            }
             if (orow >= 0) {
               float4* dst = reinterpret_cast<float4*>(out + (size_t)orow * p.N + n0 + c0);
 #pragma unroll
@@ -574,6 +594,9 @@ static int fill_wg_plan(const nq_conv_desc* d, int a_planes, int b_planes, nq_tc
     if (c > N) c = N;
     if (!fit(1, c)) return NQ_ERR_UNSUPPORTED;
   }
+  // dZ planes as one operand (see WgParams::bcat): single 128-row block, one column slice, accumulators still fit
+  pl->bcat = (a_planes == 2 && b_planes == 2 && pl->MB == 1 && pl->nsplits == 1 && pl->NC <= 128 && 2 * pl->nkh * pl->NC <= 512) ? 1 : 0;  // one MMA takes N <= 256
+  if (const char* e = getenv("NQ_WG_BCAT")) { if (atoi(e) == 0) pl->bcat = 0; }  // tuning override
   pl->tiles_x = (d->w + WG_TW - 1) / WG_TW;
   pl->tiles_y = (d->h + pl->TR - 1) / pl->TR;
   pl->tiles_total = pl->tiles_x * pl->tiles_y * d->n;
@@ -606,7 +629,10 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.x = x; p.dz = dz; p.ws = workspace;
   p.n = d->n; p.h = d->h; p.w = d->w; p.C = pl->C; p.N = pl->N; p.ks = d->ksize; p.pad = d->ksize / 2;
   p.ncg = pl->ncg; p.G = pl->G; p.MB = pl->MB; p.NC = pl->NC; p.nsplits = pl->nsplits; p.TR = pl->TR;
-  p.nkh = pl->nkh; p.khg = pl->khg; p.AR = pl->AR; p.msplit = pl->msplit; p.ncg_c = pl->ncg_c;
+  p.nkh = pl->nkh; p.khg = pl->khg; p.AR = pl->AR; p.msplit = pl->msplit; p.ncg_c = pl->ncg_c; p.bcat = pl->bcat;
+  if (p.bcat && (pl->MB != 1 || pl->nsplits != 1 || pl->a_planes != 2 || pl->b_planes != 2 || 2 * pl->nkh * pl->NC > 512 || pl->NC > 128 ||
+                 pl->b_plane_bytes != (pl->NC / 8) * pl->CGS_B))
+    return NQ_ERR_BAD_ARG;
   p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.tiles_total = pl->tiles_total; p.psplits = pl->psplits;
   p.tiles_per_split = pl->tiles_per_split; p.a_planes = pl->a_planes; p.b_planes = pl->b_planes;
   p.CGS_A = pl->CGS_A; p.CGS_B = pl->CGS_B; p.a_plane_bytes = pl->a_plane_bytes; p.b_plane_bytes = pl->b_plane_bytes;

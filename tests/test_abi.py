@@ -88,6 +88,15 @@ def test_tc_plans_fit_for_every_workload():
                 assert pl.NT % 16 == 0 and pl.NT <= 256 and pl.N % 16 == 0
                 assert pl.total_tiles == pl.tiles_x * pl.tiles_y * pl.tiles_n * 2
                 assert (pl.CGS // 16) % 8 == 4 and pl.CGS >= pl.PW * pl.PH * 16
+                # hardware shape limits of the variants the plan may pick: one MMA takes N <= 256, 512 TMEM columns
+                cols = pl.NT * (2 if pl.bcat else 1)
+                assert cols <= 256 and pl.mt in (1, 2) and pl.acc_stride >= cols * pl.mt and pl.n_acc * pl.acc_stride <= 512
+                assert 2 <= pl.n_abuf <= 8 and 2 <= pl.n_acc <= 8 and pl.n_epi in (8, 12) and pl.n_bstages <= 16
+                assert pl.smem_bytes >= 1024 + pl.n_abuf * pl.a_buf_bytes + pl.n_bstages * pl.b_stage_bytes
+                if pl.bcat:
+                    assert ap == 2 and bp == 2
+                if pl.resident:
+                    assert pl.tiles_n == 1 and pl.mt == 1 and not pl.bcat and d.ksize * d.ksize <= pl.n_bstages
         assert descs[-1].cin_p % 4 == 0
         for i, d in enumerate(descs[:-1]):
             for ap, bp in ((1, 1), (2, 2)):
@@ -96,7 +105,11 @@ def test_tc_plans_fit_for_every_workload():
                 if st == -3 and d.cin_p * d.ksize > 504:
                     continue  # wide 12M-class stages: more accumulator rows than one TMEM pass -> FFMA wgrad kernel
                 assert st == 0, (arch, i, st)
-                assert wp.nkh * wp.MB * wp.NC <= 512 and wp.NC % 16 == 0 and wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2
+                assert wp.nkh * wp.MB * wp.NC * (2 if wp.bcat else 1) <= 512 and wp.NC % 16 == 0
+                assert wp.smem_bytes <= 227 * 1024 and wp.nbuf >= 2 and wp.NC <= 256
+                if wp.bcat:  # both dZ planes as one MMA operand: N = 2 NC <= 256, single block, single column slice
+                    assert wp.NC <= 128 and wp.MB == 1 and wp.nsplits == 1 and ap == 2 and bp == 2
+                    assert wp.b_plane_bytes == (wp.NC // 8) * wp.CGS_B
                 assert wp.khg * wp.nkh >= d.ksize and wp.AR == wp.TR + wp.nkh - 1
                 assert d.ksize * wp.ncg_c + 1 <= wp.MB * 16 and wp.psplits * wp.tiles_per_split >= wp.tiles_total
                 assert wp.msplit * wp.ncg_c >= wp.ncg and (wp.msplit - 1) * wp.ncg_c < wp.ncg
