@@ -256,7 +256,10 @@ typedef struct nq_tc_plan {
   int32_t acc_stride;          /* TMEM columns per accumulator slot */
   int32_t n_epi;               /* epilogue warps (8 or 12 of the 16 worker warps; the rest load activations) */
   int32_t resident;            /* 1: all weight stages of a tile fit the ring; loaded once per CTA */
+  int32_t ksplit;              /* data gradient: CTAs sharing the K range of one tile (1 = off; the caller may set 1) */
+  int32_t reserved;
   int64_t wpk_bytes;           /* size of the packed weight buffer the caller allocates */
+  int64_t workspace_floats;    /* fp32 partial sums nq_tc_conv_dgrad needs when ksplit > 1 */
 } nq_tc_plan;
 
 /* Tiling / staging plan of one stage and direction; pure host arithmetic. */
@@ -305,10 +308,11 @@ int nq_tc_head_fwd_loss(const nq_conv_desc* d, const nq_tc_plan* plan, const voi
                         float p, float mean_pixels, float* img, float* loss_sum, void* dz_head_split, void* stream);
 
 /* dz_prev = unshuffle(conv_transpose(dz) * act'(z_prev)).  dz_split (n, h, w, nout_p rounded up to 8) and
- * dz_prev_split (n, h/prev_rh, w/prev_rw, prev_rh*prev_rw*cin_p) are split-bf16, z_prev fp32; wpk_t is
+ * dz_prev_split (n, h/prev_rh, w/prev_rw, prev_rh*prev_rw*cin_p) are split-bf16, z_prev fp32; workspace
+ * (plan->workspace_floats floats, may be NULL when plan->ksplit == 1) holds the split-K partial sums; wpk_t is
  * packed with a dir = 1 plan from the DE-QUANTISED weights. */
 int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* plan, const void* dz_split, const void* wpk_t,
-                     const float* z_prev, int prev_rh, int prev_rw, int prev_act, void* dz_prev_split, void* stream);
+                     const float* z_prev, int prev_rh, int prev_rw, int prev_act, void* dz_prev_split, float* workspace, int64_t workspace_floats, void* stream);
 
 /* Edges of the split-bf16 domain.  NCHW fp32 (n, c, h, w) <-> split NHWC (n, h, w, c_p); flat fp32 <-> split. */
 int nq_nchw_to_split(const float* src, void* dst_split, int n, int c, int h, int w, int c_p, void* stream);

@@ -39,7 +39,7 @@ class TcPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("dir", "C", "N", "NT", "KC", "SBC", "a_planes", "b_planes", "PW", "PH", "CGS", "a_plane_bytes",
                  "a_buf_bytes", "b_stage_bytes", "n_bstages", "smem_bytes", "tiles_x", "tiles_y", "tiles_n",
-                 "total_tiles", "cluster", "mt", "bcat", "n_abuf", "n_acc", "acc_stride", "n_epi", "resident")] + [("wpk_bytes", C.c_int64)]
+                 "total_tiles", "cluster", "mt", "bcat", "n_abuf", "n_acc", "acc_stride", "n_epi", "resident", "ksplit", "reserved")] + [("wpk_bytes", C.c_int64), ("workspace_floats", C.c_int64)]
 
 
 class TcWgradPlan(C.Structure):
@@ -118,7 +118,7 @@ def _load():
         "nq_tc_pack_epilogue": (I, [DP, P, I, P, P, P, P]),
         "nq_tc_pack_multi": (I, [C.POINTER(TcPackTask), I, P]),
         "nq_tc_conv_fwd": (I, [DP, TP, P, P, P, P, P, P, P]),
-        "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P]),
+        "nq_tc_conv_dgrad": (I, [DP, TP, P, P, P, I, I, I, P, P, L, P]),
         "nq_tc_head_fwd_loss": (I, [DP, TP, P, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_tc_plan_wgrad": (I, [DP, I, I, C.POINTER(TcWgradPlan)]),
         "nq_tc_conv_wgrad": (I, [DP, C.POINTER(TcWgradPlan), P, P, P, P, L, P]),

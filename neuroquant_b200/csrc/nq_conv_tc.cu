@@ -89,6 +89,9 @@ struct TcParams {
   int n_abuf, n_acc;     // activation buffers in shared memory, accumulator slots in TMEM (rings, 2 .. TC_MAX_RING)
   int acc_stride, sub_stride;  // TMEM columns per accumulator slot / between the pixel tiles of a slot
   FastDiv fd_tiles_x, fd_tiles_y, fd_rh, fd_rw, fd_PW, fd_npix, fd_cg;
+  int ksplit, cb_per_split, ncb;  // split-K over activation units (channel blocks): units per split, units in total
+  float* part;           // epi 3: fp32 partial sums (ksplit, n, h, w, n_store); the finish kernel applies the epilogue
+  size_t part_stride;    // floats per partial
   int nsb_last;          // weight stages of the last (possibly partial) activation unit
   int out_h, out_w, quad_stride;  // output grid (fwd: h*rh, w*rw; dgrad: h/rh, w/rw) and dgrad's floats per output pixel
   int resident;          // 1: all weight stages of a tile fit the ring and stay there: loaded once per CTA, never released
@@ -263,14 +266,26 @@ __device__ __forceinline__ void store_split4(uint8_t* base, size_t plane_bytes, 
 struct TileCoord {
   int img, y0, x0, n0, nt;  // image, tile origin (pixels), first column, columns in this N tile
   bool real;                // false: padding slot of a cluster group (runs the pipeline, touches no pixels)
+  int cb0, cb1, ksp;        // activation units [cb0, cb1) of this slot and its split index (split-K)
 };
 // Tile slots are ordered pixel-tile fastest within an N tile, padded so that the cs CTAs of a cluster
 // always work on the same N tile (they share its weight stages by multicast).
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, int rank) {
   TileCoord c;
   const int slot = group * p.cs + rank;
-  const int tn = p.tiles_n == 1 ? 0 : slot / p.tiles_m_pad;
-  int tm = slot - tn * p.tiles_m_pad;
+  int tn, tm;
+  if (p.ksplit == 1) {
+    tn = p.tiles_n == 1 ? 0 : slot / p.tiles_m_pad;
+    tm = slot - tn * p.tiles_m_pad;
+    c.cb0 = 0; c.cb1 = p.ncb; c.ksp = 0;
+  } else {  // slots: pixel tile fastest, then K split, then N tile
+    const int tnk = slot / p.tiles_m_pad;
+    tm = slot - tnk * p.tiles_m_pad;
+    tn = tnk / p.ksplit;
+    c.ksp = tnk - tn * p.ksplit;
+    c.cb0 = c.ksp * p.cb_per_split;
+    c.cb1 = min(p.ncb, c.cb0 + p.cb_per_split);
+  }
   c.real = tm < p.tiles_m;
   if (!c.real) tm = 0;
   const int tmx = fdiv(tm, p.fd_tiles_x);
@@ -343,8 +358,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const TileCoord tc = tile_coord(p, t, rank);
         const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * 2 * p.b_planes;
         const uint32_t part = stage_bytes / p.cs;
-        const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride;
-        for (int cb = 0; cb < ncb; ++cb) {
+        const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride + (size_t)tc.cb0 * taps * nsb_full * stage_bytes;
+        for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
           const int nsb = cb == ncb - 1 ? p.nsb_last : nsb_full;
           for (int tap = 0; tap < taps; ++tap)
             for (int sb = 0; sb < nsb; ++sb, ++sc) {
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (leader) umma_commit(A_EMPTY + abuf * 8);
         if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
       } else
-      for (int cb = 0; cb < ncb; ++cb) {
+      for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
         mbar_wait(A_FULL + abuf * 8, aph);
         fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
         tc_fence_after();
@@ -540,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
       const uint8_t* img = p.in + (size_t)tc.img * p.h * p.w * p.in_stride * 2;
-      for (int cb = 0; cb < ncb; ++cb) {
+      for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
         const int c0 = cb * p.KC;
         const int ncg = min(p.KC, p.C - c0) >> 3;
         mbar_wait(A_EMPTY + abuf * 8, aph ^ 1);
@@ -747,6 +762,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               r.x *= zv[it].x; r.y *= zv[it].y; r.z *= zv[it].z; r.w *= zv[it].w;
             }
             store_split4(p.out_y, p.out_plane_bytes, row_base[it] + n, r);
+          } else if (p.epi == 3) {  // split-K partial: raw sums in the input grid's own order, finished by dgrad_finish_kernel
+            *reinterpret_cast<float4*>(p.part + (size_t)tc.ksp * p.part_stride + zrow[it] + n) = r;
           }
         }
         __syncwarp();
@@ -1019,6 +1036,8 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->tiles_x = (d->w + tile_w - 1) / tile_w;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
+  pl->ksplit = 1;
+  pl->workspace_floats = 0;
   pl->total_tiles = pl->tiles_x * pl->tiles_y * d->n * pl->tiles_n;
   const int taps = d->ksize * d->ksize;
   // bytes of the packed weight buffer: full-width stages for all but the last N tile
@@ -1028,6 +1047,22 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   // weight-stream sharing: 2 CTAs per cluster pack all 148 SMs (74 TPCs); every stage splits evenly
   // (nt * SBC * 2 * planes is a multiple of 512 bytes)
   pl->cluster = 2;
+  // split-K (data gradient only): when the tiles cannot fill half the SMs, deal the activation units to several CTAs
+  if (dir == 1 && !pl->resident) {
+    const int ncb = (C + pl->KC - 1) / pl->KC;
+    const int slots = pl->total_tiles;
+    int ks = slots * 2 <= sm_count() ? sm_count() / slots : 1;
+    if (ks > ncb) ks = ncb;
+    if (const char* e = getenv("NQ_TC_KSPLIT")) {  // tuning override (0: off)
+      const int v = atoi(e);
+      if (v <= 1) ks = 1; else if (v <= ncb) ks = v;
+    }
+    if (ks > 1) {
+      const int per = (ncb + ks - 1) / ks;
+      pl->ksplit = (ncb + per - 1) / per;
+      pl->workspace_floats = (long long)pl->ksplit * d->n * d->h * d->w * d->cin_p;
+    }
+  }
   return NQ_OK;
 }
 
@@ -1131,7 +1166,7 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
-  if (p.epi == 1) { p.out_h = p.h / p.rh; p.out_w = p.w / p.rw; p.quad_stride = p.rh * p.rw * p.n_store; }
+  if (p.epi == 1 || p.epi == 3) { p.out_h = p.h / p.rh; p.out_w = p.w / p.rw; p.quad_stride = p.rh * p.rw * p.n_store; }
   else { p.out_h = p.h * p.rh; p.out_w = p.w * p.rw; p.quad_stride = 0; }
   if ((long long)p.n * p.out_h * p.out_w >= (1LL << 31) || (long long)p.n * p.h * p.w >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
   p.nsb_last = (pl->C - ((pl->C + pl->KC - 1) / pl->KC - 1) * pl->KC) / pl->SBC;
@@ -1155,7 +1190,9 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if (cs < 1 || p.tiles_m < 2 * cs) cs = 1;
   p.cs = cs;
   p.tiles_m_pad = (p.tiles_m + cs - 1) / cs * cs;
-  p.total_groups = p.tiles_m_pad / cs * pl->tiles_n;
+  p.ncb = (pl->C + pl->KC - 1) / pl->KC;
+  if (p.ksplit < 1) { p.ksplit = 1; p.cb_per_split = p.ncb; }
+  p.total_groups = p.tiles_m_pad / cs * pl->tiles_n * p.ksplit;
   int n_clusters = sm_count() / cs;
   if (n_clusters > p.total_groups) n_clusters = p.total_groups;
   cudaLaunchConfig_t cfg{};
@@ -1217,9 +1254,51 @@ extern "C" int nq_tc_head_fwd_loss(const nq_conv_desc* d, const nq_tc_plan* pl, 
   return launch_tc(d, pl, p, as_stream(stream));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-K data gradient.  The deep stages have few pixels (HNeRV-3M stage 3: 40 x 80 x 2 = 50 tiles for 148 SMs,
+// stage 2: 6 tiles) and a long K (9-25 taps x 1024 channels): every CTA would stream the whole weight tensor.
+// With plan->ksplit > 1 the activation units (channel blocks) of a tile are dealt to ksplit CTAs that write raw fp32
+// partial sums; this kernel adds them in a fixed order and applies the epilogue (activation derivative, un-shuffle,
+// split-bf16 store).
+// ------------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) dgrad_finish_kernel(const float* __restrict__ part, int ksplit, size_t part_stride,
+                                                           const float* __restrict__ zprev, int act, int n, int h, int w,
+                                                           int n_store, int rh, int rw, uint8_t* __restrict__ out,
+                                                           size_t out_plane_bytes) {
+  const int c4n = n_store >> 2;
+  const int64_t total4 = (int64_t)n * h * w * c4n;
+  const int hq = h / rh, wq = w / rw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = e / c4n;
+    const int c = (int)(e - pix * c4n) * 4;
+    const float4* p4 = reinterpret_cast<const float4*>(part + pix * n_store + c);
+    float4 r = *p4;
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (size_t)k * part_stride + pix * n_store + c);
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    if (zprev != nullptr && act != 0) {
+      const float4 z = __ldg(reinterpret_cast<const float4*>(zprev + pix * n_store + c));
+      if (act == 1) {
+        r.x *= gelu_grad_fast(z.x); r.y *= gelu_grad_fast(z.y); r.z *= gelu_grad_fast(z.z); r.w *= gelu_grad_fast(z.w);
+      } else {
+        r.x *= z.x; r.y *= z.y; r.z *= z.z; r.w *= z.w;
+      }
+    }
+    const int x = (int)(pix % w);
+    const int64_t t = pix / w;
+    const int y = (int)(t % h), img = (int)(t / h);
+    const int qh = y / rh, si = y - qh * rh, qw = x / rw, sj = x - qw * rw;
+    const size_t o = ((size_t)(img * hq + qh) * wq + qw) * ((size_t)rh * rw * n_store) + (size_t)(si * rw + sj) * n_store + c;
+    store_split4(out, out_plane_bytes, o, r);
+  }
+}
+}  // namespace nq
+
 extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, const void* dz_split, const void* wpk_t,
                                 const float* z_prev, int prev_rh, int prev_rw, int prev_act, void* dz_prev_split,
-                                void* stream) {
+                                float* workspace, int64_t workspace_floats, void* stream) {
   int st = check_conv_desc(d);
   if (st) return st;
   if (!pl || pl->dir != 1 || !dz_split || !wpk_t || !dz_prev_split || prev_rh <= 0 || prev_rw <= 0) return NQ_ERR_BAD_ARG;
@@ -1236,6 +1315,25 @@ extern "C" int nq_tc_conv_dgrad(const nq_conv_desc* d, const nq_tc_plan* pl, con
   p.out_plane_bytes = (size_t)d->n * d->h * d->w * d->cin_p * 2;
   p.rh = prev_rh; p.rw = prev_rw; p.cg = d->cin_p; p.act = prev_act;
   p.n_store = d->cin_p;
+  if (pl->ksplit > 1) {  // split-K: raw partial sums, then one finishing pass
+    if (!workspace || workspace_floats < pl->workspace_floats) return NQ_ERR_WORKSPACE;
+    const size_t per = (size_t)d->n * d->h * d->w * d->cin_p;
+    p.epi = 3; p.zprev = nullptr; p.out_y = nullptr;
+    p.part = workspace; p.part_stride = per;
+    p.ksplit = pl->ksplit;
+    p.cb_per_split = ((pl->C + pl->KC - 1) / pl->KC + pl->ksplit - 1) / pl->ksplit;
+    st = launch_tc(d, pl, p, as_stream(stream));
+    if (st) return st;
+    const int64_t total4 = (int64_t)per / 4;
+    int64_t blocks = (total4 + 255) / 256;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    dgrad_finish_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(workspace, pl->ksplit, per, z_prev, prev_act, d->n, d->h, d->w,
+                                                                        d->cin_p, prev_rh, prev_rw,
+                                                                        reinterpret_cast<uint8_t*>(dz_prev_split),
+                                                                        (size_t)d->n * d->h * d->w * d->cin_p * 2);
+    NQ_LAUNCH_CHECK();
+    return NQ_OK;
+  }
   return launch_tc(d, pl, p, as_stream(stream));
 }
 

@@ -625,9 +625,14 @@ class DecoderEngine:
                 g_prev = self.geoms[i - 1]
                 if self.use_tc:
                     pl, wpk = (p.tc_head_dgrad, self._head_dgrad) if i == last else (p.tc_dgrad[i], self._tcw[i][1])
+                    if pl.ksplit > 1 and (not hasattr(p, "dgrad_ws") or p.dgrad_ws.numel() < pl.workspace_floats):
+                        p.dgrad_ws = torch.empty(int(pl.workspace_floats), device=self.device)  # shared by the split-K stages
+                    dws = p.dgrad_ws if pl.ksplit > 1 else None
                     L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_tc_conv_dgrad, C.byref(d), C.byref(pl), p.dz[i].data_ptr(),
                                       wpk.data_ptr(), L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, p.desc[i - 1].act,
-                                      p.dz[i - 1].data_ptr(), st), "nq_tc_conv_dgrad")
+                                      p.dz[i - 1].data_ptr(), L.ptr(dws), dws.numel() if dws is not None else 0, st),
+                            "nq_tc_conv_dgrad")
+                    self.launches += 1 if pl.ksplit > 1 else 0
                 else:
                     L.check(self._run(f"conv_dgrad[{i}]", d, L.lib.nq_conv_dgrad, C.byref(d), L.ptr(p.dz[i]), L.ptr(wt),
                                       L.ptr(p.z[i - 1]), g_prev.rh, g_prev.rw, p.desc[i - 1].act, L.ptr(p.dz[i - 1]), st),
