@@ -271,16 +271,36 @@ def run_b200(args):
     h2d = B * (c * h0 * w0 + 3 * H * W) * 4
     loss_host = torch.zeros(1).pin_memory()
 
-    def e2e_step(i):
+    # Inputs start in pinned HOST memory every step and the loss goes back to the host every step.  The package's
+    # HostBatchPipe keeps one batch in flight: the PCIe copy of batch i+1 runs on a side stream under the kernels of
+    # batch i, and the 4-byte loss read-back is asynchronous (all of it completes inside the timed region, which ends
+    # with a device synchronise).
+    from neuroquant_b200.calibration import HostBatchPipe
+    pipe = HostBatchPipe((B, c, h0, w0), (B, 3, H, W))
+    loss_ring = torch.zeros(4).pin_memory()
+
+    def host_batch(i):
         o = (i * B) % (F - B + 1)
-        embed = embeds_h[o:o + B].cuda(non_blocking=True)
-        frames = frames_h[o:o + B].cuda(non_blocking=True)
+        return embeds_h[o:o + B], frames_h[o:o + B]
+
+    def e2e_step(i):
+        if pipe.head == pipe.tail:       # first step of a run: nothing prefetched yet
+            pipe.put(*host_batch(i))
+        embed, frames = pipe.get()
+        pipe.put(*host_batch(i + 1))     # next batch's copy overlaps this step's kernels
         step(i, embed, frames)
-        loss_host.copy_(eng.last_loss(), non_blocking=False)
+        loss_ring[i % 4:i % 4 + 1].copy_(eng.last_loss().view(1), non_blocking=True)
+
+    def e2e_drain():
+        if pipe.head > pipe.tail:        # the batch prefetched by the last step is never used
+            pipe.get()
+        pipe.release()
 
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
+    e2e_drain()
     ms_e, _, _ = timed(e2e_step, args.steps)
+    e2e_drain()
     e2e_val = args.steps * world / (ms_e * 1e-3)
 
     # ---- quantised decode (hard rounding, weights static -> packed once, Q9)

@@ -89,6 +89,56 @@ class GraphedStep:
         self.eng.invalidate()
 
 
+class HostBatchPipe:
+    """Double-buffered host -> device input pipe for calibration batches that live in (pinned) host memory.
+
+    `put(embed_h, frames_h)` starts the copy of the NEXT batch on a side stream; `get()` makes the compute stream
+    wait for the oldest pending batch and returns its device tensors.  With one batch in flight the PCIe copy of
+    batch k+1 (19.7 MB for two 1280x640 frames) runs under the kernels of batch k instead of in front of them.
+    A slot is refilled only after the compute stream has consumed it (event recorded by `get()` of the next batch or
+    by `release()`)."""
+
+    def __init__(self, embed_shape, frames_shape, device="cuda", depth: int = 2):
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [(torch.empty(embed_shape, device=device), torch.empty(frames_shape, device=device)) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [None] * depth  # event after which the slot may be overwritten
+        self.head = self.tail = 0   # next slot to fill / next slot to hand out
+        self.depth = depth
+        self._last = None
+
+    def put(self, embed_h: torch.Tensor, frames_h: torch.Tensor):
+        if self.head - self.tail >= self.depth:
+            raise RuntimeError("HostBatchPipe: all slots are pending; call get() first")
+        k = self.head % self.depth
+        e, f = self.slots[k]
+        with torch.cuda.stream(self.stream):
+            if self.free[k] is not None:
+                self.stream.wait_event(self.free[k])
+            e.copy_(embed_h, non_blocking=True)
+            f.copy_(frames_h, non_blocking=True)
+            self.ready[k].record(self.stream)
+        self.head += 1
+
+    def get(self):
+        if self.tail >= self.head:
+            raise RuntimeError("HostBatchPipe: nothing pending; call put() first")
+        self.release()
+        k = self.tail % self.depth
+        torch.cuda.current_stream().wait_event(self.ready[k])
+        self.tail += 1
+        self._last = k
+        return self.slots[k]
+
+    def release(self):
+        """Mark the batch handed out last as consumed by everything enqueued on the compute stream so far."""
+        if self._last is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.free[self._last] = ev
+            self._last = None
+
+
 class CalibrationLoop:
     """One calibration run.  `fetch(idx) -> (embed, frames)` returns this rank's shard of the
     mini-batch `idx` as device tensors (NCHW)."""

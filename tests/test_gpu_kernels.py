@@ -434,3 +434,24 @@ def test_multi_tensor_quantiser_launches_equal_single_tensor(nq):
         for a, b in zip(s_, m_):
             assert torch.equal(a, b)
     assert L.lib.nq_fakequant_fwd_multi(None, 3, None, 0.0, L.stream()) != 0
+
+
+def test_host_batch_pipe_orders_and_reuses_slots(nq):
+    """HostBatchPipe hands batches out in the order they were put, from pinned host memory, and may be refilled
+    while the previous batch is still being consumed (two slots)."""
+    from neuroquant_b200.calibration import HostBatchPipe
+    pipe = HostBatchPipe((2, 3, 4, 5), (2, 3, 8, 8))
+    host = [(torch.full((2, 3, 4, 5), float(k)).pin_memory(), torch.full((2, 3, 8, 8), float(-k)).pin_memory()) for k in range(7)]
+    pipe.put(*host[0])
+    acc = torch.zeros((), device="cuda")
+    for k in range(7):
+        e, f = pipe.get()
+        if k + 1 < 7:
+            pipe.put(*host[k + 1])
+        acc = acc + e.sum() * 1000 + f.sum()      # consumer work enqueued on the compute stream
+        assert torch.equal(e.cpu(), host[k][0]) and torch.equal(f.cpu(), host[k][1])
+    pipe.release()
+    want = sum(k * 120 * 1000 - k * 384 for k in range(7))
+    assert float(acc) == want
+    with pytest.raises(RuntimeError):
+        pipe.get()
