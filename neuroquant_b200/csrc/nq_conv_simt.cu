@@ -778,7 +778,7 @@ static int launch_head_fwd(const HeadParams& q, cudaStream_t s) {
 // Head weight gradient.  Persistent CTAs loop over pixel tiles; inside a tile the 9*8 (tap, channel)
 // pairs of a chunk (+1 bias slot) are spread over three thread groups that split the tile rows;
 // per-CTA partials are then summed in a fixed order.
-constexpr int HW_MAXCHUNK = 8;   // supports C <= 64 (head inputs are 24..37 channels in all configs)
+constexpr int HW_MAXCHUNK = 16;  // supports C <= 128 (head inputs: 24..40 channels in the 3M configs, 112 in the 12M one)
 constexpr int HW_SLOTS = 9 * H_CH + 1;
 
 struct HeadWgradParams {

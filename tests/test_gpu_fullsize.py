@@ -1,0 +1,64 @@
+"""Full-size parity on the GPU: the tensor-core engine against the exact-fp32 FFMA engine of the same library on the
+workloads the benchmark is quoted on.
+
+The tiny golden fixtures pin both engines to the reference (tests/test_gpu_kernels.py); they do not reach the plan
+variants that only large stages select (input-channel slicing and 5 kernel rows per CTA in wgrad, two pixel tiles per
+step, side-by-side weight planes, split-K data gradients, resident head weights).  Here the two independent
+implementations must agree at the benchmark's own sizes: same frames, same loss, same gradient for every weight and bias
+(forward, data gradient and weight gradient of every stage enter the flat gradient)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# workload, batch, hadamard: the metric's configuration, the NeRV counterpart, a rotated run, a 12M-class 1080p decoder
+# last column: gradient tolerance as a fraction of the tensor's largest entry.  Split-bf16 products carry 16 mantissa
+# bits; the rest is the fp32 summation order over 0.8-2 M pixels (and up to 7000-term dot products at 12M), which
+# differs between the two engines.
+RUNS = [("hnerv-bunny-3m", 2, False, 2e-4), ("nerv-bunny-3m", 2, False, 2e-4), ("hnerv-bunny-3m", 1, True, 2e-4),
+        ("hnerv-1080p-12m", 1, False, 1e-3)]
+
+
+def _run(monkeypatch, conv, workload, batch, hadamard):
+    monkeypatch.setenv("NQ_CONV", conv)
+    import neuroquant_b200 as nq
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape, random_decoder
+    arch, cfg = WORKLOADS[workload]
+    geoms, params = random_decoder(cfg, arch, 903)
+    bits = [6, 5, 4, 5, 5, 6, 6]
+    stages = [nq.QuantStage(g, w.cuda(), b.cuda(), nb, hadamard) for g, (w, b), nb in zip(geoms, params, bits)]
+    eng = nq.DecoderEngine(stages)
+    assert eng.use_tc == (conv == "tc")
+    eng.init_scales()
+    eng.start_adaround()
+    c, h0, w0 = embed_shape(cfg, arch)
+    gen = torch.Generator().manual_seed(17)
+    embed = torch.randn(batch, c, h0, w0, generator=gen).cuda()
+    frames = torch.rand(batch, 3, cfg["crop_h"], cfg["crop_w"], generator=gen).cuda()
+    img = eng.forward(embed, train=True, target=frames, p_norm=2.0).clone()
+    loss = float(eng.last_loss())
+    flat = eng.backward().clone()
+    views = [(gw.clone(), gb.clone()) for gw, gb in eng._grad_buffers()[1]]
+    # quantised decode with hard rounding (the deliverable): integer weights, one bf16 plane on the tensor cores
+    eng.soft_w = False
+    eng.invalidate()
+    dec = eng.forward(embed).clone()
+    del eng
+    torch.cuda.empty_cache()
+    return img, loss, flat, views, dec
+
+
+@pytest.mark.parametrize("workload,batch,hadamard,gtol", RUNS)
+def test_tensor_core_engine_matches_fp32_engine_at_full_size(monkeypatch, workload, batch, hadamard, gtol):
+    tc = _run(monkeypatch, "tc", workload, batch, hadamard)
+    ff = _run(monkeypatch, "simt", workload, batch, hadamard)
+    # frames: BASELINE north_star asks for 1e-3 max-abs against the reference; the two engines agree far below that
+    assert (tc[0] - ff[0]).abs().max() < 2e-5
+    assert (tc[4] - ff[4]).abs().max() < 2e-5
+    assert tc[1] == pytest.approx(ff[1], rel=1e-5)
+    # gradients, per tensor: max |diff| <= gtol * the tensor's largest entry
+    for i, ((gw_t, gb_t), (gw_f, gb_f)) in enumerate(zip(tc[3], ff[3])):
+        for name, a, b in (("dW", gw_t, gw_f), ("db", gb_t, gb_f)):
+            tol = gtol * float(b.abs().max()) + 1e-12
+            assert float((a - b).abs().max()) <= tol, (workload, i, name, float((a - b).abs().max()), tol)
+    assert torch.isfinite(tc[2]).all()
