@@ -53,7 +53,7 @@ def config_of(args, world):
             "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world, "hadamard": bool(args.hadamard),
             "parallelism": f"dp{world} (frame-sharded, NCCL all-reduce of dW)" if world > 1 else "single GPU",
             "l2": "no explicit flush: each step streams >2 GB of activations, far above the 126 MB L2",
-            "launch": "CUDA graph replay of the iteration on 1 GPU; eager launches around the NCCL all-reduce when N > 1",
+            "launch": "CUDA graph replay of the iteration on 1 GPU; the same fused launch sequence issued eagerly around the NCCL all-reduce when N > 1",
             **{k: v for k, v in HYPER.items()}}
 
 
@@ -208,7 +208,8 @@ def run_b200(args):
     stage_ev = []
 
     from neuroquant_b200.calibration import GraphedStep
-    use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0")
+    use_graph = os.environ.get("NQ_GRAPH", "1") != "0"
+    capture = world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0"
     graphed = {}
 
     def step(i, embed, frames, eager=False):
@@ -216,7 +217,7 @@ def run_b200(args):
         captured once as a CUDA graph and replayed; data-parallel runs launch it eagerly around the all-reduce."""
         if use_graph and not eager:
             if "g" not in graphed:
-                graphed["g"] = GraphedStep(eng, opt, embed, frames, HYPER["p"], mean_pixels, None, world)
+                graphed["g"] = GraphedStep(eng, opt, embed, frames, HYPER["p"], mean_pixels, None, world, capture=capture)
             graphed["g"].run(embed, frames, reg_w, reg_b)
             return
         eng.forward(embed, train=True, target=frames, p_norm=HYPER["p"], mean_pixels=mean_pixels, want_img=False)

@@ -46,13 +46,17 @@ class GraphedStep:
     all-reduce into the graph hung on the test box: opt-in with NQ_GRAPH_DP=1)."""
 
     def __init__(self, eng: DecoderEngine, opt: AdamState, embed: torch.Tensor, frames: torch.Tensor, p_norm: float,
-                 mean_pixels: float, group=None, world: int = 1):
+                 mean_pixels: float, group=None, world: int = 1, capture: bool = True):
         self.eng, self.opt, self.p_norm, self.mean_pixels = eng, opt, p_norm, mean_pixels
         self.group, self.world = group, world
+        self.capture = capture  # False: the same fused kernel sequence launched eagerly (data-parallel default)
         self.embed = torch.empty_like(embed)
         self.frames = torch.empty_like(frames)
         self.hyper = torch.zeros(4, device=embed.device)
-        self.hyper_host = torch.zeros(4).pin_memory()
+        # the host runs ahead of the device: a ring of pinned staging buffers, each reused only after its copy is done
+        self.hyper_host = [torch.zeros(4).pin_memory() for _ in range(8)]
+        self.hyper_done = [None] * 8
+        self.n_run = 0
         self.graph = None
         self.launches_per_replay = 0
 
@@ -68,9 +72,19 @@ class GraphedStep:
         self.embed.copy_(embed)
         self.frames.copy_(frames)
         step_size, bc2_sqrt = self.opt.hyper_of_next_step()
-        self.hyper_host[0], self.hyper_host[1], self.hyper_host[2], self.hyper_host[3] = reg_w, reg_b, step_size, bc2_sqrt
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
-        if self.graph is None:
+        k = self.n_run % len(self.hyper_host)
+        self.n_run += 1
+        if self.hyper_done[k] is not None:
+            self.hyper_done[k].synchronize()
+        hh = self.hyper_host[k]
+        hh[0], hh[1], hh[2], hh[3] = reg_w, reg_b, step_size, bc2_sqrt
+        self.hyper.copy_(hh, non_blocking=True)
+        if self.hyper_done[k] is None:
+            self.hyper_done[k] = torch.cuda.Event()
+        self.hyper_done[k].record()
+        if not self.capture:
+            self._body()
+        elif self.graph is None:
             l0 = self.eng.launches
             self._body()  # eager once: allocates every lazily-created buffer, and is this iteration's real work
             self.launches_per_replay = self.eng.launches - l0
@@ -154,7 +168,10 @@ class CalibrationLoop:
             self.world = torch.distributed.get_world_size(group)
         self.global_batch = global_batch
         self.log = log
-        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0" and (self.world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0")
+        # one GPU: CUDA-graph replay; data parallel: the same fused sequence launched eagerly around the NCCL all-reduce
+        # (capturing the all-reduce hung on the test box: opt-in with NQ_GRAPH_DP=1); NQ_GRAPH=0: per-tensor eager path
+        self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0"
+        self.capture = self.world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0"
         self._graphed = {}
         self.ep1 = int(0.05 * iters / n_batches)  # calib_model.py:144
         self.ep2 = int(iters / n_batches) - self.ep1  # calib_model.py:205
@@ -170,7 +187,8 @@ class CalibrationLoop:
             key = (tuple(embed.shape), tuple(frames.shape), id(opt))
             gs = self._graphed.get(key)
             if gs is None:
-                gs = self._graphed[key] = GraphedStep(eng, opt, embed, frames, self.p, float(gb * H * W), self.group, self.world)
+                gs = self._graphed[key] = GraphedStep(eng, opt, embed, frames, self.p, float(gb * H * W), self.group, self.world,
+                                                      capture=self.capture)
             gs.run(embed, frames, reg_w, reg_b)
             return
         eng.forward(embed, train=True, target=frames, p_norm=self.p, mean_pixels=float(gb * H * W),
