@@ -417,6 +417,84 @@ def model_reconstruction(qd: QuantDecoder, cali: torch.Tensor, frames: torch.Ten
 
 
 # --------------------------------------------------------------------------------------------
+# Block-wise reconstruction (calib_block.py:91-183, data_utils.py:45-86,146-196)
+# --------------------------------------------------------------------------------------------
+def block_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, asym: bool, cache_bs: int = 10):
+    """save_inp_oup_data(model, block, cali_data, asym, batch_size=10, input_prob=True) for the block that is stage k:
+    (input the optimisation sees, full-precision input, full-precision output) over the calibration set; the last
+    cali.size(0) % 10 samples are dropped as in data_utils.py:67.  With asym the input comes from a pass with EVERY
+    layer quantised in its current state (GetLayerInpOut.__call__, data_utils.py:172-180)."""
+    n = int(cali.size(0) / cache_bs) * cache_bs
+    inps, syms, outs = [], [], []
+    mode = qd.mode
+    for i in range(0, n, cache_bs):
+        e = cali[i:i + cache_bs]
+        qd.mode = "off"
+        with torch.no_grad():
+            _, feats = decode(qd.stages, e, keep=True)
+        x_fp = e if k == 0 else feats[k - 1]
+        syms.append(x_fp)
+        outs.append(feats[k])
+        if asym:
+            qd.mode = mode
+            with torch.no_grad():
+                ws, bs = zip(*[qd.quantised_params(q) for q in qd.q])
+                _, fq = decode(qd.stages, e, ws, bs, keep=True)
+            inps.append(e if k == 0 else fq[k - 1])
+        else:
+            inps.append(x_fp)
+    qd.mode = mode
+    return torch.cat(inps), torch.cat(syms), torch.cat(outs)
+
+
+def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: Sequence[Sequence[int]], iters: int,
+                         weight: float = 0.01, asym: bool = False, b_range=(20, 2), warmup: float = 0.0,
+                         input_prob: float = 1.0, p: float = 2.0, lr: float = 0.0015,
+                         masks: Optional[Sequence[torch.Tensor]] = None, log: Optional[list] = None):
+    """calib_block.py:91-183, opt_mode 'mse', for the block that is decoder stage k, with the reference's random draws
+    injected: idx_seq[i] = torch.randperm(N)[:batch_size] of iteration i, masks[i] = its torch.rand_like (QDrop).
+    Only this stage's quantisers become AdaRound (fp16-rounded scales, quantizer.py:264-265); both its weight and bias
+    quantisers end hard-rounded (calib_block.py:180-183, unlike the network-wise variant)."""
+    q = qd.q[k]
+    if q.hadamard:
+        raise NotImplementedError("the reference's block_reconstruction cannot run with hadamard=True (calib_block.py:125)")
+    st = q.stage
+    # AdaRoundQuantizer(uaq, weight_tensor=org_weight / bias): calib_block.py:123-130
+    q.delta_w, q.zp_w = fp16_round(q.delta_w), fp16_round(q.zp_w)
+    q.delta_b, q.zp_b = fp16_round(q.delta_b), fp16_round(q.zp_b)
+    alpha_w = adaround_init_alpha(st.weight, q.delta_w).requires_grad_(True)
+    alpha_b = adaround_init_alpha(st.bias, q.delta_b).requires_grad_(True)
+    opt = torch.optim.Adam([alpha_w, alpha_b], lr=lr)
+    decay = LinearTempDecay(iters, rel_start_decay=warmup, start_b=b_range[0], end_b=b_range[1])
+    loss_start = iters * warmup
+    # the cache is taken AFTER the block's quantisers were swapped (calib_block.py:151), but predecessors only matter
+    q.alpha_w, q.alpha_b = alpha_w.detach(), alpha_b.detach()
+    inp, sym, out_fp = block_cache(qd, k, cali, asym)
+    for it in range(iters):
+        idx = torch.as_tensor(idx_seq[it])
+        cur_inp, cur_sym, cur_out = inp[idx], sym[idx], out_fp[idx]
+        if input_prob < 1.0:
+            cur_inp = torch.where(masks[it] < input_prob, cur_inp, cur_sym)
+        opt.zero_grad()
+        _, wq = adaround_quant(st.weight, alpha_w, q.delta_w, q.zp_w, q.n_bits, True)
+        _, bq = adaround_quant(st.bias, alpha_b, q.delta_b, q.zp_b, q.n_bits, True)
+        y = apply_act(up_shuffle(F.conv2d(cur_inp, wq, bq, stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
+        count = it + 1
+        rec = lp_loss(y, cur_out, p=p)
+        b = decay(count)
+        if count < loss_start:
+            b, rnd = 0, torch.zeros(())
+        else:
+            rnd = weight * round_reg(alpha_w, b)
+        (rec + rnd).backward()
+        opt.step()
+        if log is not None:
+            log.append((count, float(rec + rnd), float(rec), float(rnd)))
+    q.alpha_w, q.alpha_b = alpha_w.detach(), alpha_b.detach()
+    return inp, sym, out_fp
+
+
+# --------------------------------------------------------------------------------------------
 # Omega = dw^T H dw sensitivity (bit_assign.py:57-118,171-203)
 # --------------------------------------------------------------------------------------------
 def omega(stages: Sequence[Stage], vec: Sequence[torch.Tensor], embeds: Sequence[torch.Tensor],

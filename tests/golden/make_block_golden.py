@@ -1,0 +1,111 @@
+"""Golden fixtures for block-wise reconstruction from the UNMODIFIED reference.
+
+Run in the build container only:   python tests/golden/make_block_golden.py
+Writes tests/golden/block_*.npz.  The reference's block_reconstruction (calib_block.py:91-183) draws its mini-batches
+with an unseeded torch.randperm and its QDrop masks with torch.rand_like; both are recorded here (the functions are
+wrapped for the duration of the call) so that the oracle and the CUDA path can replay the same draws.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shims"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, HERE)
+
+import models  # noqa: E402  (reference)
+import quantization  # noqa: E402  (reference)
+import quantization.calib_block as cb  # noqa: E402
+from quantization.quant_layer import QuantModule  # noqa: E402
+from make_golden import TINY_HNERV, TINY_NERV, npy  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters=60, n_frames=20, bsz=2):
+    torch.manual_seed(903)
+    model = (models.HNeRV if arch == "hnerv" else models.NeRV)(cfg)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "encoder" not in n and p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+    g = torch.Generator().manual_seed(11)
+    frames = torch.rand(n_frames, 3, cfg["crop_h"], cfg["crop_w"], generator=g)
+    with torch.no_grad():
+        cali = model.encode(frames) * 3.0 if arch == "hnerv" else model.encode(torch.arange(n_frames).float() / n_frames)
+    out = {"cali": npy(cali), "bits": np.array(bits), "hadamard": np.array(hadamard), "block_idx": np.array(block_idx),
+           "asym": np.array(asym), "input_prob": np.array(input_prob), "iters": np.array(iters), "bsz": np.array(bsz)}
+    for k, v in model.state_dict().items():
+        if "encoder" not in k:
+            out["sd/" + k] = npy(v)
+    qnn = quantization.QuantModel(model=model, hadamard=hadamard,
+                                  weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"})
+    qnn.set_bitwidth(bits)
+    qnn.eval()
+    qnn.set_quant_state(True)
+    with torch.no_grad():
+        qnn(cali[:bsz])  # first quantised forward initialises every step size
+    block = qnn.model.decoder[block_idx]
+    conv = [m for m in block.modules() if isinstance(m, QuantModule)][0]
+
+    idx_log, mask_log, traj, cache = [], [], [], {}
+    _randperm, _rand_like, _call, _save = torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data
+
+    def randperm(n, *a, **k):
+        r = _randperm(n, *a, **k)
+        idx_log.append(r[:bsz].clone())
+        return r
+
+    def rand_like(x, *a, **k):
+        r = _rand_like(x, *a, **k)
+        mask_log.append(r.clone())
+        return r
+
+    def rec_call(self, pred, tgt, grad=None):
+        tot = _call(self, pred, tgt, grad)
+        traj.append((self.count, float(tot), float(cb.lp_loss(pred, tgt, p=self.p)), float(self.round_loss)))
+        return tot
+
+    def save(*a, **k):
+        r = _save(*a, **k)
+        cache["inp"], cache["sym"], cache["out"] = r[0][0], r[0][1], r[1]
+        return r
+
+    import logging
+    logging.getLogger().setLevel(logging.WARNING)
+    torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data = randperm, rand_like, rec_call, save
+    try:
+        torch.manual_seed(5)
+        cb.block_reconstruction(qnn, block, cali, batch_size=bsz, iters=iters, weight=0.01, opt_mode="mse", asym=asym,
+                                b_range=(20, 2), warmup=0.2, input_prob=input_prob, p=2.0, lr=0.003)
+    finally:
+        torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data = _randperm, _rand_like, _call, _save
+    out["idx"] = np.stack([npy(i) for i in idx_log])
+    if mask_log:
+        out["masks"] = np.stack([npy(m) for m in mask_log]).astype(np.float32)
+    out["traj"] = np.array(traj, dtype=np.float64)
+    out["cache_inp"], out["cache_sym"], out["cache_out"] = npy(cache["inp"]), npy(cache["sym"]), npy(cache["out"])
+    wq, bq = conv.weight_quantizer, conv.bias_quantizer
+    out["final/alpha_w"], out["final/alpha_b"] = npy(wq.alpha), npy(bq.alpha)
+    out["final/delta_w"], out["final/zp_w"] = npy(wq.delta), npy(wq.zero_point)
+    out["final/delta_b"], out["final/zp_b"] = npy(bq.delta), npy(bq.zero_point)
+    assert wq.soft_targets is False and bq.soft_targets is False  # calib_block.py:180-183: both go hard
+    with torch.no_grad():
+        y = block(cache["inp"][:bsz])
+    out["final/block_out"] = npy(y)
+    out["final/codes_w"], out["final/codes_b"] = npy(wq.x_quant), npy(bq.x_quant)
+    np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **out)
+    print(tag, "block", type(block).__name__, tuple(conv.weight.shape), "iters", len(traj), "first/last rec",
+          traj[0][2], traj[-1][2], "masks", len(mask_log))
+
+
+if __name__ == "__main__":
+    run_block_case("block_tiny_hnerv", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 3, False, 1.0)
+    run_block_case("block_tiny_hnerv_qdrop", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 2, True, 0.5)
+    # (hadamard=True cannot run in the reference: calib_block.py:125 builds alpha from the UNROTATED org_weight while the
+    #  forward quantises the rotated, channel-padded copy -- shape mismatch at quantizer.py:291)
+    run_block_case("block_tiny_nerv", "nerv", TINY_NERV, [5, 6, 3, 4, 5, 4, 3], False, 2, False, 1.0)

@@ -26,6 +26,21 @@ CASES = {
 }
 
 
+# block-wise reconstruction fixtures (tests/golden/make_block_golden.py)
+BLOCK_CASES = {
+    "block_tiny_hnerv": ("hnerv", TINY_HNERV),
+    "block_tiny_hnerv_qdrop": ("hnerv", TINY_HNERV),
+    "block_tiny_nerv": ("nerv", TINY_NERV),
+}
+
+
+def block_case(tag):
+    arch, cfg = BLOCK_CASES[tag]
+    g = load(tag)
+    sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
+    return g, arch, cfg, O.stages_from_state_dict(sd, cfg, arch)
+
+
 def load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import nq_oracle as O
-from tests.helpers import CASES, case_stages, load, t
+from tests.helpers import CASES, case_stages, load, t, BLOCK_CASES, block_case
 
 
 def test_fwht_matches_scipy():
@@ -163,3 +163,32 @@ def test_calibration_golden(tag):
         assert torch.equal(q.codes_w, q.codes_w.round())
         assert np.allclose(q.codes_b.numpy(), g[f"final/{i}/codes_b"], atol=5e-2)  # biases stay soft (Q3)
     assert n_diff / n_tot < 5e-3
+
+
+@pytest.mark.parametrize("tag", list(BLOCK_CASES))
+def test_block_reconstruction_oracle_matches_reference(tag):
+    """oracle.block_reconstruction against the reference's calib_block.block_reconstruction run on the same tiny
+    decoder with its randperm / rand_like draws replayed: cached block inputs / outputs, the loss trajectory, the final
+    rounding variables and the hard-rounded codes of the block."""
+    g, arch, cfg, stages = block_case(tag)
+    k = int(g["block_idx"])
+    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]))
+    log = []
+    masks = [t(m) for m in g["masks"]] if "masks" in g.files else None
+    inp, sym, out = O.block_reconstruction(qd, k, t(g["cali"]), g["idx"].tolist(), int(g["iters"]), weight=0.01,
+                                           asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2,
+                                           input_prob=float(g["input_prob"]), p=2.0, lr=0.003, masks=masks, log=log)
+    assert np.abs(inp.numpy() - g["cache_inp"]).max() < 1e-5
+    assert np.abs(sym.numpy() - g["cache_sym"]).max() < 1e-5
+    assert np.abs(out.numpy() - g["cache_out"]).max() < 1e-5
+    traj = np.array(log)
+    assert traj.shape == g["traj"].shape
+    assert np.allclose(traj[:, 2], g["traj"][:, 2], rtol=2e-3, atol=1e-9)   # reconstruction loss
+    assert np.allclose(traj[:, 3], g["traj"][:, 3], rtol=1e-4, atol=1e-6)   # rounding regulariser
+    q = qd.q[k]
+    assert np.array_equal(q.delta_w.numpy(), g["final/delta_w"]) and np.array_equal(q.zp_w.numpy(), g["final/zp_w"])
+    assert np.array_equal(q.delta_b.numpy(), g["final/delta_b"]) and np.array_equal(q.zp_b.numpy(), g["final/zp_b"])
+    far = (np.abs(q.alpha_w.numpy() - g["final/alpha_w"]) > 1e-3).mean()
+    assert far < 0.01, far
+    codes, _ = O.adaround_quant(q.stage.weight, q.alpha_w, q.delta_w, q.zp_w, q.n_bits, soft=False)
+    assert (codes.numpy() != g["final/codes_w"]).mean() < 1e-3
