@@ -1,4 +1,5 @@
 // Rotation (FWHT), weight packing, layout edges, loss / dot / PSNR reductions, library plumbing.
+#include <cuda_bf16.h>
 #include "nq_common.cuh"
 
 namespace nq {
@@ -302,6 +303,62 @@ extern "C" int nq_unpack_wgrad(const nq_conv_desc* d, const float* dwk, int cin_
   if (!dwk || cin_dst < d->cin) return NQ_ERR_BAD_ARG;
   const int64_t total = (int64_t)d->cout * cin_dst * d->ksize * d->ksize;
   unpack_wgrad_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(*d, dwk, cin_dst, dw_ref, db_ref);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wise reconstruction (calib_block.py:62-63,168-170): lp_loss of ONE stage's output against its full-precision
+// output, with the backward through the activation and the up-shuffle fused -- the block's output gradient goes
+// straight into the split-bf16 dZ the weight-gradient kernel consumes.  One pass, 16 bytes per element.
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) block_loss_bwd_kernel(const uint16_t* __restrict__ y_hi, const uint16_t* __restrict__ y_lo,
+                                                             const float* __restrict__ tgt, const float* __restrict__ gprime,
+                                                             int n, int h, int w, int rh, int rw, int cg, float p,
+                                                             float grad_scale, float* __restrict__ loss_sum,
+                                                             uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo) {
+  __shared__ float red[32];
+  const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  const int W2 = w * rw, H2 = h * rh;
+  float loss = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const float y = __uint_as_float((uint32_t)y_hi[e] << 16) + __uint_as_float((uint32_t)y_lo[e] << 16);
+    const float d = y - tgt[e];
+    const float a = fabsf(d);
+    float g;
+    if (p == 2.0f) {
+      loss += d * d;
+      g = 2.0f * d;
+    } else {
+      loss += powf(a, p);
+      g = p * powf(a, p - 1.0f) * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+    }
+    g *= grad_scale;
+    if (gprime != nullptr) g *= gprime[e];
+    const int c = (int)(e % cg);
+    const int64_t pix = e / cg;
+    const int x = (int)(pix % W2), yy = (int)((pix / W2) % H2), b = (int)(pix / ((int64_t)W2 * H2));
+    const int qh = yy / rh, si = yy - qh * rh, qw = x / rw, sj = x - qw * rw;
+    const int64_t o = (((int64_t)b * h + qh) * w + qw) * ((int64_t)rh * rw * cg) + (int64_t)(si * rw + sj) * cg + c;
+    const __nv_bfloat16 hv = __float2bfloat16_rn(g);
+    dz_hi[o] = __bfloat16_as_ushort(hv);
+    dz_lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(g - __bfloat162float(hv)));
+  }
+  loss = block_sum(loss, red);
+  if (threadIdx.x == 0 && loss_sum != nullptr) atomicAdd(loss_sum, loss);
+}
+}  // namespace nq
+
+extern "C" int nq_block_loss_bwd(const void* y_split, const float* tgt, const float* gprime, int n, int h, int w, int rh, int rw,
+                                 int cg, float p, float grad_scale, float* loss_sum, void* dz_split, void* stream) {
+  if (!y_split || !tgt || !dz_split || n <= 0 || h <= 0 || w <= 0 || rh <= 0 || rw <= 0 || cg <= 0 || !(p > 0.f)) return NQ_ERR_BAD_ARG;
+  if ((rh * rw * cg) % 8) return NQ_ERR_BAD_SHAPE;  // dZ rows are read in 16-byte chunks
+  const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  const uint16_t* yh = reinterpret_cast<const uint16_t*>(y_split);
+  uint16_t* dh = reinterpret_cast<uint16_t*>(dz_split);
+  block_loss_bwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(yh, yh + total, tgt, gprime, n, h, w, rh, rw, cg, p, grad_scale,
+                                                                       loss_sum, dh, dh + total);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

@@ -245,6 +245,7 @@ class DecoderEngine:
         if self.device.type != "cuda":
             raise L.NqError("DecoderEngine needs CUDA tensors (no CPU fallback)")
         self.mode = "uaq"
+        self.stage_state = None  # optional per-stage (mode, soft_w, soft_b) override, see _round_modes
         self.soft_w = False
         self.soft_b = False
         # Convolution path: tcgen05 tensor cores (default) or the exact-fp32 FFMA kernels (NQ_CONV=simt).
@@ -387,13 +388,9 @@ class DecoderEngine:
             self._fwd_bpl = [2] * len(self.stages)
         if self.mode != "off":
             # every weight and bias quantiser of the decoder in one multi-tensor launch
-            if self.mode == "uaq":
-                mw = mb = ROUND_NEAREST
-            else:
-                mw = ROUND_SOFT if self.soft_w else ROUND_HARD
-                mb = ROUND_SOFT if self.soft_b else ROUND_HARD
             tasks = []
-            for s, (_, _, _, deq_w, deq_b) in zip(self.stages, self._packed):
+            for i, (s, (_, _, _, deq_w, deq_b)) in enumerate(zip(self.stages, self._packed)):
+                mw, mb = self._round_modes(i)
                 tasks.append(self._fq_task(s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, mw, s.codes_w, deq_w,
                                            reg_b is not None and mw == ROUND_SOFT))
                 tasks.append(self._fq_task(s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, mb, s.codes_b, deq_b, False))
@@ -430,7 +427,7 @@ class DecoderEngine:
             # is applied per output channel in the epilogue.  Otherwise the de-quantised fp32 weights,
             # split into two bf16 planes.
             integer = self.mode != "off" and not s.hadamard
-            exact1 = integer and (self.mode == "uaq" or not self.soft_w)
+            exact1 = integer and self._round_modes(i)[0] != ROUND_SOFT
             bpl = 1 if exact1 else 2
             self._fwd_bpl[i] = bpl
             # forward operand + per-column epilogue vectors: one task; data-gradient operand: another; all stages'
@@ -451,6 +448,14 @@ class DecoderEngine:
             self.launches += (len(packs) + L.MULTI_MAX - 1) // L.MULTI_MAX
         self._weights_valid = True
         self._wt_valid = need_wt
+
+    def _round_modes(self, i: int):
+        """(weight, bias) rounding mode of stage i.  `stage_state` (set by the module binding when a decoder mixes
+        plain and AdaRound quantisers, e.g. after block-wise reconstruction of some blocks) overrides the global mode."""
+        st = self.stage_state[i] if getattr(self, "stage_state", None) else (self.mode, self.soft_w, self.soft_b)
+        if st[0] == "uaq":
+            return ROUND_NEAREST, ROUND_NEAREST
+        return (ROUND_SOFT if st[1] else ROUND_HARD), (ROUND_SOFT if st[2] else ROUND_HARD)
 
     @staticmethod
     def _fq_task(x, alpha, delta, zp, n_bits, mode, codes, deq, want_reg) -> "L.FqTask":

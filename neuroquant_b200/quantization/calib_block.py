@@ -1,0 +1,207 @@
+"""Block-wise calibration (reference: quantization/calib_block.py:91-183, data_utils.py:45-86,146-196).
+
+One decoder block (conv -> PixelShuffle -> GELU, one engine stage) learns its rounding variables against the block's
+own full-precision output.  Per iteration, on the GPU: fake-quant of the block's weight and bias (one launch), operand
+pack (one launch), tcgen05 forward with the activation derivative saved, ONE fused kernel for lp_loss + activation
+backward + un-shuffle (nq_block_loss_bwd), tcgen05 weight gradient + finish, and the fused quantiser Jacobian + Adam
+(nq_adaround_step_multi).  No data gradient is needed: nothing upstream of the block learns.
+
+Differences from the network-wise variant that the reference has and this keeps: only this block's quantisers become
+AdaRound quantisers; the regulariser covers the block's weight only; BOTH its weight and bias quantisers end
+hard-rounded (calib_block.py:180-183); the cached inputs / outputs drop the last len(cali) % 10 samples
+(data_utils.py:67).  `opt_mode` 'fisher_diag' / 'fisher_full' and hadamard blocks are not supported (the reference's own
+block_reconstruction cannot run on a rotated layer: calib_block.py:125 initialises alpha from the unrotated weight).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from ..calibration import LinearTempDecay
+from ..engine import AdamState, ROUND_SOFT, _ACT, _ACT_SAVED_GRAD, _pad
+from ..runner import DecoderRunner
+from .quant_block import BaseQuantBlock
+from .quant_layer import QuantModule
+from .quantizer import AdaRoundQuantizer
+
+
+class BlockStep:
+    """Buffers, plans and the launch sequence of one block iteration for a fixed (batch, input grid)."""
+
+    def __init__(self, stage, n: int, h: int, w: int, lr: float):
+        g = stage.geom
+        dev = stage.weight.device
+        self.stage, self.n, self.h, self.w = stage, n, h, w
+        cin_p = _pad(g.cin, 16)
+        cg = _pad(g.c_grp, 16)
+        if (g.rh * g.rw * cg) % 16:
+            raise NotImplementedError("block output channels cannot be padded to a multiple of 16 GEMM columns")
+        act = _ACT[g.act]
+        self.d = L.ConvDesc(n, h, w, g.cin, cin_p, g.k, g.cout, g.rh, g.rw, g.c_grp, cg, _ACT_SAVED_GRAD if act == 1 else act)
+        self.H, self.W, self.cg, self.cin_p = h * g.rh, w * g.rw, cg, cin_p
+        self.fwd = L.TcPlan()
+        L.check(L.lib.nq_tc_plan_conv(C.byref(self.d), 0, 2, 2, C.byref(self.fwd)), "nq_tc_plan_conv")
+        self.wg = L.TcWgradPlan()
+        L.check(L.lib.nq_tc_plan_wgrad(C.byref(self.d), 2, 2, C.byref(self.wg)), "nq_tc_plan_wgrad")
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.x = torch.zeros(2, n, h, w, cin_p, **bf)
+        self.y = torch.zeros(2, n, self.H, self.W, cg, **bf)
+        self.z = torch.zeros(n, self.H, self.W, cg, device=dev) if act != 0 else None
+        self.tgt = torch.zeros(n, self.H, self.W, cg, device=dev)
+        self.dz = torch.zeros(2, n, h, w, self.d.nout_p, **bf)
+        self.wpk = torch.empty(int(self.fwd.wpk_bytes), device=dev, dtype=torch.uint8)
+        self.scale = torch.empty(self.d.nout_p, device=dev)
+        self.bias_p = torch.empty(self.d.nout_p, device=dev)
+        self.deq_w, self.deq_b = torch.empty_like(stage.weight), torch.empty_like(stage.bias)
+        self.ws = torch.empty(int(self.wg.workspace_floats), device=dev)
+        self.gw, self.gb = torch.zeros_like(stage.weight), torch.zeros_like(stage.bias)
+        self.loss = torch.zeros(1, device=dev)
+        self.reg = torch.zeros(1, device=dev)
+        self.hyper = torch.zeros(4, device=dev)
+        self.opt = AdamState([stage.alpha_w, stage.alpha_b], lr=lr)
+        self.launches = 0
+
+    def run(self, x_nchw: torch.Tensor, tgt_nchw: torch.Tensor, reg_w: float, reg_b: float, p: float, want_reg: bool = False):
+        s, d, st = self.stage, self.d, L.stream()
+        g = s.geom
+        cw = lambda dl: int(dl.numel() > 1)  # noqa: E731
+        rows = lambda x, dl: (dl.numel(), x.numel() // dl.numel()) if dl.numel() > 1 else (1, x.numel())  # noqa: E731
+        # 1. soft fake-quant of weight and bias (quantizer.py:278-300)
+        rw_, rl_ = rows(s.w_src, s.delta_w)
+        rb_, bl_ = rows(s.bias, s.delta_b)
+        fq = (L.FqTask * 2)(
+            L.FqTask(L.ptr(s.w_src), L.ptr(s.alpha_w), L.ptr(s.delta_w), L.ptr(s.zp_w), L.ptr(s.codes_w), L.ptr(self.deq_w), rw_, rl_,
+                     cw(s.delta_w), s.n_bits, ROUND_SOFT, int(want_reg)),
+            L.FqTask(L.ptr(s.bias), L.ptr(s.alpha_b), L.ptr(s.delta_b), L.ptr(s.zp_b), L.ptr(s.codes_b), L.ptr(self.deq_b), rb_, bl_,
+                     cw(s.delta_b), s.n_bits, ROUND_SOFT, 0))
+        if want_reg:
+            self.reg.zero_()
+        L.check(L.lib.nq_fakequant_fwd_multi(fq, 2, L.ptr(self.reg) if want_reg else None, float(reg_b), st), "nq_fakequant_fwd_multi")
+        # 2. operand pack + epilogue vectors
+        pk = (L.TcPackTask * 1)(L.TcPackTask(C.pointer(d), C.pointer(self.fwd), L.ptr(self.deq_w), None, self.wpk.data_ptr(), None,
+                                             L.ptr(self.deq_b), L.ptr(self.scale), L.ptr(self.bias_p), g.cin, 0, 0, 0))
+        L.check(L.lib.nq_tc_pack_multi(pk, 1, st), "nq_tc_pack_multi")
+        # 3. inputs into the engine's layouts
+        L.check(L.lib.nq_nchw_to_split(L.ptr(x_nchw), self.x.data_ptr(), self.n, g.cin, self.h, self.w, self.cin_p, st), "nq_nchw_to_split")
+        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(tgt_nchw), L.ptr(self.tgt), self.n, g.c_grp, self.H, self.W, self.cg, st), "nq_nchw_to_nhwc")
+        # 4. forward (activation derivative kept in z)
+        L.check(L.lib.nq_tc_conv_fwd(C.byref(d), C.byref(self.fwd), self.x.data_ptr(), self.wpk.data_ptr(), L.ptr(self.scale),
+                                     L.ptr(self.bias_p), L.ptr(self.z), self.y.data_ptr(), st), "nq_tc_conv_fwd")
+        # 5. loss + backward through activation / up-shuffle: mean over n*H*W of sum_c |y - tgt|^p (quantizer.py:66-73)
+        self.loss.zero_()
+        L.check(L.lib.nq_block_loss_bwd(self.y.data_ptr(), L.ptr(self.tgt), L.ptr(self.z), self.n, self.h, self.w, g.rh, g.rw, self.cg,
+                                        float(p), 1.0 / float(self.n * self.H * self.W), L.ptr(self.loss), self.dz.data_ptr(), st),
+                "nq_block_loss_bwd")
+        # 6. weight / bias gradient
+        L.check(L.lib.nq_tc_conv_wgrad(C.byref(d), C.byref(self.wg), self.x.data_ptr(), self.dz.data_ptr(), None, L.ptr(self.ws),
+                                       self.ws.numel(), st), "nq_tc_conv_wgrad")
+        fin = (L.WgFinishTask * 1)(L.WgFinishTask(C.pointer(d), L.ptr(self.ws), L.ptr(self.gw), L.ptr(self.gb), self.wg.psplits,
+                                                  self.wg.N, g.cin, 0))
+        L.check(L.lib.nq_tc_wgrad_finish_multi(fin, 1, st), "nq_tc_wgrad_finish_multi")
+        # 7. quantiser Jacobian + Adam on (alpha_w, alpha_b); the regulariser acts on the weight only (calib_block.py:38-47)
+        step_size, bc2 = self.opt.hyper_of_next_step()
+        self.hyper.copy_(torch.tensor([reg_w, reg_b, step_size, bc2], dtype=torch.float32))
+        ad = (L.AdaTask * 2)(
+            L.AdaTask(L.ptr(self.gw), L.ptr(s.w_src), L.ptr(s.alpha_w), L.ptr(s.delta_w), L.ptr(s.zp_w), L.ptr(self.opt.m[0]),
+                      L.ptr(self.opt.v[0]), rw_, rl_, cw(s.delta_w), s.n_bits, 1, 0),
+            L.AdaTask(L.ptr(self.gb), L.ptr(s.bias), L.ptr(s.alpha_b), L.ptr(s.delta_b), L.ptr(s.zp_b), L.ptr(self.opt.m[1]),
+                      L.ptr(self.opt.v[1]), rb_, bl_, cw(s.delta_b), s.n_bits, 0, 0))
+        L.check(L.lib.nq_adaround_step_multi(ad, 2, 1.0, 0.9, 0.999, 1e-8, L.ptr(self.hyper), st), "nq_adaround_step_multi")
+        self.launches += 10
+
+    def rec_loss(self) -> float:
+        return float(self.loss) / float(self.n * self.H * self.W)
+
+
+def _features(runner: DecoderRunner, model, embed: torch.Tensor, weight_quant: bool):
+    model.set_quant_state(weight_quant)
+    return runner.features(embed)
+
+
+def save_inp_oup_data(model, runner: DecoderRunner, k: int, cali_data: torch.Tensor, asym: bool, batch_size: int = 10):
+    """data_utils.py:45-86 with input_prob=True: (block input the optimisation sees, full-precision block input,
+    full-precision block output) over the calibration set, kept in HBM."""
+    inps, syms, outs = [], [], []
+    for i in range(int(cali_data.size(0) / batch_size)):
+        e = cali_data[i * batch_size:(i + 1) * batch_size].cuda()
+        feats = _features(runner, model, e, False)
+        syms.append(feats[k - 1].clone())
+        outs.append(feats[k].clone())
+        if asym:  # input recomputed with the whole network quantised (data_utils.py:172-180)
+            inps.append(_features(runner, model, e, True)[k - 1].clone())
+        else:
+            inps.append(syms[-1])
+    model.set_quant_state(False)
+    return (torch.cat(inps), torch.cat(syms)), torch.cat(outs)
+
+
+def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, batch_size: int = 8, iters: int = 20000,
+                         weight: float = 0.01, opt_mode: str = "mse", asym: bool = False, b_range: tuple = (20, 2),
+                         warmup: float = 0.0, input_prob: float = 1.0, p: float = 2.0, lr: float = 0.0015):
+    """Block-wise calibration (calib_block.py:91-183); same arguments as the reference."""
+    if opt_mode != "mse":
+        raise NotImplementedError("opt_mode 'fisher_diag' / 'fisher_full' need the cached output gradients (data_utils.py:89-116)")
+    if not isinstance(block, BaseQuantBlock):
+        raise ValueError("block_reconstruction expects a QuantNeRVBlock of the model's decoder")
+    convs = [m for m in block.modules() if isinstance(m, QuantModule)]
+    if len(convs) != 1:
+        raise NotImplementedError("blocks with other than one quantised convolution")
+    conv = convs[0]
+    if conv.hadamard:
+        raise NotImplementedError("block_reconstruction on a rotated layer (the reference cannot run it either: calib_block.py:125)")
+    runner = DecoderRunner.of(model.model)
+    k = [i for i, l in enumerate(runner.layers) if l is conv]
+    if not k or k[0] == 0 or k[0] == len(runner.layers) - 1:
+        raise ValueError("block is not one of this model's decoder blocks")
+    k = k[0]
+    # the caches depend on the predecessors only; take them before this block's quantisers are swapped
+    model.eval()
+    model.set_quant_state(True)
+    runner.sync()  # initialises step sizes that no forward has initialised yet
+    (cached_inps, cached_sym), cached_outs = save_inp_oup_data(model, runner, k, cali_data, asym)
+    model.set_quant_state(False)
+    block.set_quant_state(True)
+    round_mode = "learned_hard_sigmoid"
+    conv.weight_quantizer = AdaRoundQuantizer(uaq=conv.weight_quantizer, round_mode=round_mode, weight_tensor=conv.org_weight.data)
+    conv.weight_quantizer.soft_targets = True
+    conv.bias_quantizer = AdaRoundQuantizer(uaq=conv.bias_quantizer, round_mode=round_mode, weight_tensor=conv.bias.data)
+    conv.bias_quantizer.soft_targets = True
+    wq, bq = conv.weight_quantizer, conv.bias_quantizer
+    wq.alpha, bq.alpha = nn.Parameter(wq.alpha.data.contiguous()), nn.Parameter(bq.alpha.data.contiguous())
+    st = runner.engine.stages[k]
+    st.weight, st.bias, st.w_src = conv.weight.data, conv.bias.data, conv.weight.data
+    st.set_bits(wq.n_bits)
+    st.delta_w, st.zp_w = wq.delta.data.contiguous(), wq.zero_point.contiguous()
+    st.delta_b, st.zp_b = bq.delta.data.contiguous(), bq.zero_point.contiguous()
+    st.alpha_w, st.alpha_b = wq.alpha.data, bq.alpha.data
+    n_cached = cached_inps.size(0)
+    bsz = min(batch_size, n_cached)
+    step = BlockStep(st, bsz, cached_inps.shape[2], cached_inps.shape[3], lr)
+    decay = LinearTempDecay(iters, rel_start_decay=warmup + (1 - warmup) * 0.0, start_b=b_range[0], end_b=b_range[1])
+    loss_start = iters * warmup
+    model.train()
+    for i in range(iters):
+        idx = torch.randperm(n_cached)[:batch_size].to(cached_inps.device)
+        cur_inp, cur_sym = cached_inps[idx], cached_sym[idx]
+        if input_prob < 1.0:  # QDrop (calib_block.py:163-164)
+            cur_inp = torch.where(torch.rand_like(cur_inp) < input_prob, cur_inp, cur_sym)
+        count = i + 1
+        b = decay(count)
+        reg_on = not (count < loss_start)
+        want_log = count % 500 == 0
+        step.run(cur_inp.contiguous(), cached_outs[idx].contiguous(), weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
+                 want_reg=want_log and reg_on)
+        if want_log:  # calib_block.py:85-87
+            rec = step.rec_loss()
+            rnd = float(step.reg) * weight if reg_on else 0.0
+            logging.info('Total loss:\t{:.4f} (rec:{:.4f}, round:{:.4f})\tb={:.2f}\tcount={}'.format(
+                rec + rnd, rec, rnd, b if reg_on else 0, count))
+    torch.cuda.empty_cache()
+    wq.soft_targets = False  # calib_block.py:180-183: both quantisers of the block go hard
+    bq.soft_targets = False
+    runner._key = None
+    return step

@@ -130,12 +130,18 @@ class DecoderRunner:
                 key += [src.data_ptr(), src._version, srb.data_ptr(), srb._version]
         else:
             ada = [isinstance(l.weight_quantizer, AdaRoundQuantizer) for l in self.layers]
-            if any(ada) and not all(ada):
-                raise NotImplementedError("mixed UAQ / AdaRound quantisers in one decoder pass")
             eng.mode = "ada" if all(ada) else "uaq"
+            eng.stage_state = None
             if all(ada):
                 eng.soft_w = bool(self.layers[0].weight_quantizer.soft_targets)
                 eng.soft_b = bool(self.layers[0].bias_quantizer.soft_targets)
+            if any(ada):
+                # per-stage rounding state: layers calibrated block by block carry AdaRound quantisers next to plain ones,
+                # and the block-wise variant leaves both quantisers of a block hard (calib_block.py:180-183)
+                eng.stage_state = [("ada", bool(l.weight_quantizer.soft_targets), bool(l.bias_quantizer.soft_targets)) if a
+                                   else ("uaq", False, False) for l, a in zip(self.layers, ada)]
+                if all(ada) and len(set(eng.stage_state)) == 1:
+                    eng.stage_state = None
             for l, st in zip(self.layers, eng.stages):
                 wq, bq = l.weight_quantizer, l.bias_quantizer
                 st.weight, st.bias = l.weight.data, l.bias.data
@@ -151,11 +157,12 @@ class DecoderRunner:
                     bq.delta, bq.zero_point, bq.inited = nn.Parameter(d), z, True
                 st.delta_w, st.zp_w = wq.delta.data, wq.zero_point
                 st.delta_b, st.zp_b = bq.delta.data, bq.zero_point
-                st.alpha_w = wq.alpha.data if all(ada) else None
-                st.alpha_b = bq.alpha.data if all(ada) else None
+                is_ada = isinstance(wq, AdaRoundQuantizer)
+                st.alpha_w = wq.alpha.data if is_ada else None
+                st.alpha_b = bq.alpha.data if is_ada else None
                 for tns in (st.w_src, st.bias, st.delta_w, st.zp_w, st.delta_b, st.zp_b, st.alpha_w, st.alpha_b):
                     key += [None] if tns is None else [tns.data_ptr(), tns._version]
-                key += [wq.n_bits, eng.soft_w, eng.soft_b]
+                key += [wq.n_bits, eng.soft_w, eng.soft_b, is_ada, getattr(wq, "soft_targets", None), getattr(bq, "soft_targets", None)]
         if key != self._key:
             eng.invalidate()
             self._key = key

@@ -1,0 +1,105 @@
+"""GPU parity of block-wise reconstruction (neuroquant_b200.quantization.block_reconstruction)
+against the unmodified reference's calib_block.block_reconstruction: fixtures from tests/golden/make_block_golden.py, the
+reference's unseeded torch.randperm / torch.rand_like draws replayed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nq_oracle as O
+from tests.helpers import BLOCK_CASES, load, t
+
+pytestmark = pytest.mark.gpu
+
+
+def build(tag):
+    from neuroquant_b200.models import HNeRV, NeRV
+    from neuroquant_b200.quantization import QuantModel
+    arch, cfg = BLOCK_CASES[tag]
+    g = load(tag)
+    model = (HNeRV if arch == "hnerv" else NeRV)(cfg)
+    sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if "encoder" not in k] and not unexpected
+    qnn = QuantModel(model.cuda(), hadamard=bool(g["hadamard"]),
+                     weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"}).cuda()
+    qnn.set_bitwidth(g["bits"].tolist())
+    qnn.eval()
+    qnn.set_quant_state(True)
+    qnn(t(g["cali"])[:2].cuda())
+    return g, qnn
+
+
+@pytest.mark.parametrize("tag", list(BLOCK_CASES))
+def test_block_reconstruction_matches_reference(tag, monkeypatch):
+    from neuroquant_b200.quantization import QuantModule, block_reconstruction
+    import neuroquant_b200.quantization.calib_block as cb
+    g, qnn = build(tag)
+    block = qnn.model.decoder[int(g["block_idx"])]
+    conv = [m for m in block.modules() if isinstance(m, QuantModule)][0]
+    idx_seq = [torch.as_tensor(r) for r in g["idx"]]
+    masks = [t(m) for m in g["masks"]] if "masks" in g.files else []
+    calls = {"perm": 0, "rand": 0}
+    n_cached = g["cache_inp"].shape[0]
+
+    def randperm(n, *a, **k):
+        assert n == n_cached
+        r = idx_seq[calls["perm"]]
+        calls["perm"] += 1
+        rest = torch.tensor([v for v in range(n) if v not in r.tolist()])
+        return torch.cat([r, rest])
+
+    def rand_like(x, *a, **k):
+        r = masks[calls["rand"]].to(x.device)
+        calls["rand"] += 1
+        return r
+
+    caches = {}
+    _save = cb.save_inp_oup_data
+
+    def save(*a, **k):
+        r = _save(*a, **k)
+        caches["inp"], caches["sym"], caches["out"] = r[0][0], r[0][1], r[1]
+        return r
+
+    traj = []
+    _run = cb.BlockStep.run
+
+    def run(self, *a, **k):
+        _run(self, *a, **k)
+        traj.append(self.rec_loss())
+
+    monkeypatch.setattr(torch, "randperm", randperm)
+    monkeypatch.setattr(torch, "rand_like", rand_like)
+    monkeypatch.setattr(cb, "save_inp_oup_data", save)
+    monkeypatch.setattr(cb.BlockStep, "run", run)
+    block_reconstruction(qnn, block, t(g["cali"]).cuda(), batch_size=int(g["bsz"]), iters=int(g["iters"]), weight=0.01,
+                         opt_mode="mse", asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2, input_prob=float(g["input_prob"]),
+                         p=2.0, lr=0.003)
+    monkeypatch.undo()
+    assert calls["perm"] == int(g["iters"]) and calls["rand"] == len(masks)
+    # cached block inputs / outputs: full-precision and (asym) quantised-predecessor activations
+    for name in ("inp", "sym", "out"):
+        ref = g["cache_" + name]
+        assert np.abs(caches[name].cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
+    # loss trajectory of the block output
+    assert np.allclose(np.array(traj), g["traj"][:, 2], rtol=5e-3, atol=1e-9)
+    wq, bq = conv.weight_quantizer, conv.bias_quantizer
+    assert wq.soft_targets is False and bq.soft_targets is False
+    assert np.array_equal(wq.delta.detach().cpu().numpy(), g["final/delta_w"]) and np.array_equal(wq.zero_point.cpu().numpy(), g["final/zp_w"])
+    assert np.array_equal(bq.delta.detach().cpu().numpy(), g["final/delta_b"]) and np.array_equal(bq.zero_point.cpu().numpy(), g["final/zp_b"])
+    far = (np.abs(wq.alpha.detach().cpu().numpy() - g["final/alpha_w"]) > 2e-3).mean()
+    assert far < 0.02, far
+    # identical alpha / scales -> bit-exact hard codes: re-derive on the oracle from OUR alpha
+    want, _ = O.adaround_quant(conv.org_weight.cpu(), wq.alpha.detach().cpu(), wq.delta.detach().cpu(), wq.zero_point.cpu(),
+                               wq.n_bits, soft=False)
+    with torch.no_grad():
+        y = block(caches["inp"][:2])
+    assert torch.equal(wq.x_quant.cpu(), want)
+    assert (wq.x_quant.cpu().numpy() != g["final/codes_w"]).mean() < 1e-2
+    ref = g["final/block_out"]
+    assert np.abs(y.cpu().numpy() - ref).max() <= 0.02 * np.abs(ref).max()
+    # the whole decoder still runs with this block AdaRound-hard and every other layer on plain rounding
+    qnn.eval()
+    qnn.set_quant_state(True)
+    out, _, _ = qnn(t(g["cali"])[:2].cuda())
+    assert torch.isfinite(out).all()
