@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=8, help="synthetic frames resident per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-steps", type=int, default=10)
-    ap.add_argument("--mode", default="calib", choices=["calib", "decode"],
+    ap.add_argument("--stage", type=int, default=5, help="--mode block: decoder stage (block) to reconstruct")
+    ap.add_argument("--mode", default="calib", choices=["calib", "decode", "block"],
                     help="decode: quantised-decode throughput only (any workload, e.g. hnerv-1080p-12m)")
     return ap.parse_args()
 
@@ -194,6 +195,8 @@ def run_b200(args):
     c, h0, w0 = embed_shape(cfg, arch)
     if args.mode == "decode":
         return run_decode_only(args, eng, cfg, arch, geoms, world, rank, local)
+    if args.mode == "block":
+        return run_block(args, eng, cfg, arch, geoms, world, rank)
     H, W = cfg["crop_h"], cfg["crop_w"]
     gen = torch.Generator().manual_seed(903 + rank)
     F = max(args.frames, args.batch)
@@ -416,6 +419,66 @@ def run_decode_only(args, eng, cfg, arch, geoms, world, rank, local):
                           "tflops_effective": fps * gf / 1e3}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_block(args, eng, cfg, arch, geoms, world, rank):
+    """Block-wise reconstruction (calib_block.py): iterations/s of ONE decoder block learning its
+    rounding against cached full-precision outputs -- per iteration a random mini-batch gather from the HBM-resident
+    cache, QDrop mixing (input_prob 0.5), then quantization/calib_block.BlockStep (soft fake-quant, tcgen05 forward, fused
+    loss + activation backward, tcgen05 weight gradient, fused Jacobian + Adam).  Single GPU: blocks are calibrated one
+    after the other and a block has no exchange step."""
+    from neuroquant_b200.quantization.calib_block import BlockStep
+    from neuroquant_b200.workloads import embed_shape
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "block_recon_iters_per_s", "unavailable": "block-wise reconstruction is a single-GPU loop (replicas only)"}))
+        return
+    k = args.stage
+    if not 1 <= k < len(geoms) - 1:
+        raise SystemExit("--stage must be a decoder block (1 .. n_stages - 2)")
+    _, h, w = embed_shape(cfg, arch)
+    for g in geoms[:k]:
+        h, w = h * g.rh, w * g.rw
+    g = geoms[k]
+    st = eng.stages[k]
+    B, F = args.batch, max(args.frames, args.batch)
+    gen = torch.Generator().manual_seed(903)
+    inp = torch.randn(F, g.cin, h, w, generator=gen).cuda()
+    sym = inp + 0.01 * torch.randn(F, g.cin, h, w, generator=gen).cuda()
+    out = torch.randn(F, g.c_grp, h * g.rh, w * g.rw, generator=gen).cuda() * 0.3
+    from neuroquant_b200.quantization.calib_block import cache_to_engine_layout
+    step = BlockStep(st, B, h, w, lr=HYPER["lr"])
+    inp_s, sym_s, out_c = cache_to_engine_layout(step, inp, sym, out)
+
+    from neuroquant_b200.quantization.calib_block import gather_frames
+    cur, alt = torch.empty_like(inp_s[:, :B]), torch.empty_like(inp_s[:, :B])
+
+    def it(i):  # exactly the loop body of quantization/calib_block.block_reconstruction
+        idx_h = torch.randperm(F)[:B]
+        gather_frames(inp_s, idx_h, cur)
+        keep = torch.rand_like(cur[0], dtype=torch.float32) < 0.5
+        gather_frames(sym_s, idx_h, alt)
+        torch.where(keep.unsqueeze(0), cur, alt, out=cur)
+        step.run_cached(cur, out_c, idx_h.cuda().int(), HYPER["weight"], 10.0, HYPER["p"])
+
+    for i in range(max(args.warmup, 3)):
+        it(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        it(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    flops = 2.0 * B * h * w * g.cout * g.cin * g.k * g.k * 2  # forward + weight gradient
+    print(json.dumps({"metric": "block_recon_iters_per_s", "value": 1e3 / ms, "unit": f"it/s (batch-{B} iterations of one block)",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": eng.dtype_name, "data": "synthetic",
+                      "config": {"workload": f"{args.workload} block {k}: {g.cin}->{g.cout} k{g.k} at {h}x{w}, batch {B}, QDrop 0.5",
+                                 "cache_frames": F},
+                      "gpu_launches": 8 * args.steps, "tflops_algorithmic": flops / (ms * 1e-3) / 1e12}))
 
 
 if __name__ == "__main__":

@@ -382,10 +382,11 @@ int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int h, int w, i
 /* Block-wise reconstruction (calib_block.py:62-63,168-170): lp_loss of one stage's output y against its
  * full-precision output tgt, fused with the backward through activation + up-shuffle.  y_split (n, h*rh, w*rw, cg)
  * split-bf16 as nq_tc_conv_fwd writes it, tgt the same grid in fp32 NHWC (pad channels zero), gprime the saved
- * GELU'(pre-activation) (nq_conv_desc.act = 2; NULL for a linear stage).  *loss_sum += sum |y - tgt|^p;
+ * GELU'(pre-activation) (nq_conv_desc.act = 2; NULL for a linear stage).  frame_idx (device, n entries, may be NULL):
+ * batch entry b compares against frame frame_idx[b] of a target cache (N, h*rh, w*rw, cg).  *loss_sum += sum |y - tgt|^p;
  * dz_split (n, h, w, rh*rw*cg) = unshuffle(grad_scale * p |d|^(p-1) sign(d) * gprime), ready for nq_tc_conv_wgrad. */
-int nq_block_loss_bwd(const void* y_split, const float* tgt, const float* gprime, int n, int h, int w, int rh, int rw, int cg,
-                      float p, float grad_scale, float* loss_sum, void* dz_split, void* stream);
+int nq_block_loss_bwd(const void* y_split, const float* tgt, const int32_t* frame_idx, const float* gprime, int n, int h, int w,
+                      int rh, int rw, int cg, float p, float grad_scale, float* loss_sum, void* dz_split, void* stream);
 
 /* lp_loss (quantizer.py:66-73) standalone: *loss_sum += sum |pred - tgt|^p; grad (may be NULL) receives
  * grad_scale * p * |d|^(p-1) * sign(d). */

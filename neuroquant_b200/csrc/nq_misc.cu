@@ -313,52 +313,79 @@ extern "C" int nq_unpack_wgrad(const nq_conv_desc* d, const float* dwk, int cin_
 // straight into the split-bf16 dZ the weight-gradient kernel consumes.  One pass, 16 bytes per element.
 // ---------------------------------------------------------------------------------------------
 namespace nq {
-__global__ void __launch_bounds__(256) block_loss_bwd_kernel(const uint16_t* __restrict__ y_hi, const uint16_t* __restrict__ y_lo,
-                                                             const float* __restrict__ tgt, const float* __restrict__ gprime,
+// one thread = 8 consecutive channels of one output pixel: 16-byte accesses on every operand, 32-bit index math
+__global__ void __launch_bounds__(256) block_loss_bwd_kernel(const uint4* __restrict__ y_hi, const uint4* __restrict__ y_lo,
+                                                             const float4* __restrict__ tgt, const int* __restrict__ frame_idx,
+                                                             const float4* __restrict__ gprime,
                                                              int n, int h, int w, int rh, int rw, int cg, float p,
                                                              float grad_scale, float* __restrict__ loss_sum,
-                                                             uint16_t* __restrict__ dz_hi, uint16_t* __restrict__ dz_lo) {
+                                                             uint4* __restrict__ dz_hi, uint4* __restrict__ dz_lo) {
   __shared__ float red[32];
-  const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  const int c8n = cg >> 3;
   const int W2 = w * rw, H2 = h * rh;
+  const int total = n * H2 * W2 * c8n;       // 8-channel groups (checked < 2^31 on the host)
+  const int frame8 = H2 * W2 * c8n;
   float loss = 0.f;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const float y = __uint_as_float((uint32_t)y_hi[e] << 16) + __uint_as_float((uint32_t)y_lo[e] << 16);
-    const float d = y - tgt[e];
-    const float a = fabsf(d);
-    float g;
-    if (p == 2.0f) {
-      loss += d * d;
-      g = 2.0f * d;
-    } else {
-      loss += powf(a, p);
-      g = p * powf(a, p - 1.0f) * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c8 = e % c8n;
+    const int pix = e / c8n;
+    const int x = pix % W2, t = pix / W2;
+    const int yy = t % H2, b = t / H2;
+    const int te = frame_idx != nullptr ? e + (frame_idx[b] - b) * frame8 : e;  // target cache of many frames
+    const uint4 yh = y_hi[e], yl = y_lo[e];
+    const float4 t0 = tgt[2 * (size_t)te], t1 = tgt[2 * (size_t)te + 1];
+    float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+    if (gprime != nullptr) { g0 = gprime[2 * (size_t)e]; g1 = gprime[2 * (size_t)e + 1]; }
+    const uint32_t hw[4] = {yh.x, yh.y, yh.z, yh.w}, lw[4] = {yl.x, yl.y, yl.z, yl.w};
+    const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t hb = q ? (hw[k] & 0xFFFF0000u) : (hw[k] << 16), lb = q ? (lw[k] & 0xFFFF0000u) : (lw[k] << 16);
+        const float d = (__uint_as_float(hb) + __uint_as_float(lb)) - tv[2 * k + q];
+        float g;
+        if (p == 2.0f) {
+          loss += d * d;
+          g = 2.0f * d;
+        } else {
+          const float a = fabsf(d);
+          loss += powf(a, p);
+          g = p * powf(a, p - 1.0f) * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        }
+        gr[q] = g * grad_scale * gv[2 * k + q];
+      }
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(gr[0]), h1 = __float2bfloat16_rn(gr[1]);
+      oh[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      ol[k] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gr[0] - __bfloat162float(h0))) |
+              ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gr[1] - __bfloat162float(h1))) << 16);
     }
-    g *= grad_scale;
-    if (gprime != nullptr) g *= gprime[e];
-    const int c = (int)(e % cg);
-    const int64_t pix = e / cg;
-    const int x = (int)(pix % W2), yy = (int)((pix / W2) % H2), b = (int)(pix / ((int64_t)W2 * H2));
     const int qh = yy / rh, si = yy - qh * rh, qw = x / rw, sj = x - qw * rw;
-    const int64_t o = (((int64_t)b * h + qh) * w + qw) * ((int64_t)rh * rw * cg) + (int64_t)(si * rw + sj) * cg + c;
-    const __nv_bfloat16 hv = __float2bfloat16_rn(g);
-    dz_hi[o] = __bfloat16_as_ushort(hv);
-    dz_lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(g - __bfloat162float(hv)));
+    const size_t o = ((size_t)((b * h + qh) * w + qw) * (rh * rw) + (si * rw + sj)) * c8n + c8;
+    dz_hi[o] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    dz_lo[o] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
   }
   loss = block_sum(loss, red);
   if (threadIdx.x == 0 && loss_sum != nullptr) atomicAdd(loss_sum, loss);
 }
 }  // namespace nq
 
-extern "C" int nq_block_loss_bwd(const void* y_split, const float* tgt, const float* gprime, int n, int h, int w, int rh, int rw,
-                                 int cg, float p, float grad_scale, float* loss_sum, void* dz_split, void* stream) {
+extern "C" int nq_block_loss_bwd(const void* y_split, const float* tgt, const int32_t* frame_idx, const float* gprime, int n, int h,
+                                 int w, int rh, int rw, int cg, float p, float grad_scale, float* loss_sum, void* dz_split,
+                                 void* stream) {
   if (!y_split || !tgt || !dz_split || n <= 0 || h <= 0 || w <= 0 || rh <= 0 || rw <= 0 || cg <= 0 || !(p > 0.f)) return NQ_ERR_BAD_ARG;
-  if ((rh * rw * cg) % 8) return NQ_ERR_BAD_SHAPE;  // dZ rows are read in 16-byte chunks
+  if (cg % 8) return NQ_ERR_BAD_SHAPE;  // 16-byte channel groups (tensor-core stages pad cg to 16)
   const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  if (total / 8 >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
   const uint16_t* yh = reinterpret_cast<const uint16_t*>(y_split);
   uint16_t* dh = reinterpret_cast<uint16_t*>(dz_split);
-  block_loss_bwd_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(yh, yh + total, tgt, gprime, n, h, w, rh, rw, cg, p, grad_scale,
-                                                                       loss_sum, dh, dh + total);
+  block_loss_bwd_kernel<<<grid_for(total / 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(yh), reinterpret_cast<const uint4*>(yh + total), reinterpret_cast<const float4*>(tgt), frame_idx,
+      reinterpret_cast<const float4*>(gprime), n, h, w, rh, rw, cg, p, grad_scale, loss_sum, reinterpret_cast<uint4*>(dh),
+      reinterpret_cast<uint4*>(dh + total));
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

@@ -62,10 +62,26 @@ class BlockStep:
         self.loss = torch.zeros(1, device=dev)
         self.reg = torch.zeros(1, device=dev)
         self.hyper = torch.zeros(4, device=dev)
+        # the host runs ahead of the device: pinned staging ring for the per-iteration scalars (as GraphedStep)
+        self.hyper_host = [torch.zeros(4).pin_memory() for _ in range(8)]
+        self.hyper_done = [None] * 8
+        self.n_run = 0
         self.opt = AdamState([stage.alpha_w, stage.alpha_b], lr=lr)
         self.launches = 0
 
     def run(self, x_nchw: torch.Tensor, tgt_nchw: torch.Tensor, reg_w: float, reg_b: float, p: float, want_reg: bool = False):
+        """One iteration from NCHW fp32 inputs (converted into the engine's layouts here)."""
+        g, st = self.stage.geom, L.stream()
+        L.check(L.lib.nq_nchw_to_split(L.ptr(x_nchw), self.x.data_ptr(), self.n, g.cin, self.h, self.w, self.cin_p, st), "nq_nchw_to_split")
+        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(tgt_nchw), L.ptr(self.tgt), self.n, g.c_grp, self.H, self.W, self.cg, st), "nq_nchw_to_nhwc")
+        self.launches += 2
+        self.run_cached(self.x, self.tgt, None, reg_w, reg_b, p, want_reg)
+
+    def run_cached(self, x_split: torch.Tensor, tgt_cache: torch.Tensor, frame_idx, reg_w: float, reg_b: float, p: float,
+                   want_reg: bool = False):
+        """One iteration from inputs already in the engine's layouts: x_split (2, n, h, w, cin_p) bf16 planes; tgt_cache
+        (N, H, W, cg) fp32 NHWC with frame_idx (int32 device tensor of n entries) selecting the batch's frames, or a
+        (n, H, W, cg) batch with frame_idx None."""
         s, d, st = self.stage, self.d, L.stream()
         g = s.geom
         cw = lambda dl: int(dl.numel() > 1)  # noqa: E731
@@ -85,36 +101,67 @@ class BlockStep:
         pk = (L.TcPackTask * 1)(L.TcPackTask(C.pointer(d), C.pointer(self.fwd), L.ptr(self.deq_w), None, self.wpk.data_ptr(), None,
                                              L.ptr(self.deq_b), L.ptr(self.scale), L.ptr(self.bias_p), g.cin, 0, 0, 0))
         L.check(L.lib.nq_tc_pack_multi(pk, 1, st), "nq_tc_pack_multi")
-        # 3. inputs into the engine's layouts
-        L.check(L.lib.nq_nchw_to_split(L.ptr(x_nchw), self.x.data_ptr(), self.n, g.cin, self.h, self.w, self.cin_p, st), "nq_nchw_to_split")
-        L.check(L.lib.nq_nchw_to_nhwc(L.ptr(tgt_nchw), L.ptr(self.tgt), self.n, g.c_grp, self.H, self.W, self.cg, st), "nq_nchw_to_nhwc")
-        # 4. forward (activation derivative kept in z)
-        L.check(L.lib.nq_tc_conv_fwd(C.byref(d), C.byref(self.fwd), self.x.data_ptr(), self.wpk.data_ptr(), L.ptr(self.scale),
+        # 3. forward (activation derivative kept in z)
+        L.check(L.lib.nq_tc_conv_fwd(C.byref(d), C.byref(self.fwd), x_split.data_ptr(), self.wpk.data_ptr(), L.ptr(self.scale),
                                      L.ptr(self.bias_p), L.ptr(self.z), self.y.data_ptr(), st), "nq_tc_conv_fwd")
-        # 5. loss + backward through activation / up-shuffle: mean over n*H*W of sum_c |y - tgt|^p (quantizer.py:66-73)
+        # 4. loss + backward through activation / up-shuffle: mean over n*H*W of sum_c |y - tgt|^p (quantizer.py:66-73)
         self.loss.zero_()
-        L.check(L.lib.nq_block_loss_bwd(self.y.data_ptr(), L.ptr(self.tgt), L.ptr(self.z), self.n, self.h, self.w, g.rh, g.rw, self.cg,
+        L.check(L.lib.nq_block_loss_bwd(self.y.data_ptr(), L.ptr(tgt_cache), frame_idx.data_ptr() if frame_idx is not None else None,
+                                        L.ptr(self.z), self.n, self.h, self.w, g.rh, g.rw, self.cg,
                                         float(p), 1.0 / float(self.n * self.H * self.W), L.ptr(self.loss), self.dz.data_ptr(), st),
                 "nq_block_loss_bwd")
-        # 6. weight / bias gradient
-        L.check(L.lib.nq_tc_conv_wgrad(C.byref(d), C.byref(self.wg), self.x.data_ptr(), self.dz.data_ptr(), None, L.ptr(self.ws),
+        # 5. weight / bias gradient
+        L.check(L.lib.nq_tc_conv_wgrad(C.byref(d), C.byref(self.wg), x_split.data_ptr(), self.dz.data_ptr(), None, L.ptr(self.ws),
                                        self.ws.numel(), st), "nq_tc_conv_wgrad")
         fin = (L.WgFinishTask * 1)(L.WgFinishTask(C.pointer(d), L.ptr(self.ws), L.ptr(self.gw), L.ptr(self.gb), self.wg.psplits,
                                                   self.wg.N, g.cin, 0))
         L.check(L.lib.nq_tc_wgrad_finish_multi(fin, 1, st), "nq_tc_wgrad_finish_multi")
-        # 7. quantiser Jacobian + Adam on (alpha_w, alpha_b); the regulariser acts on the weight only (calib_block.py:38-47)
+        # 6. quantiser Jacobian + Adam on (alpha_w, alpha_b); the regulariser acts on the weight only (calib_block.py:38-47)
         step_size, bc2 = self.opt.hyper_of_next_step()
-        self.hyper.copy_(torch.tensor([reg_w, reg_b, step_size, bc2], dtype=torch.float32))
+        kk = self.n_run % len(self.hyper_host)
+        self.n_run += 1
+        if self.hyper_done[kk] is not None:
+            self.hyper_done[kk].synchronize()
+        hh = self.hyper_host[kk]
+        hh[0], hh[1], hh[2], hh[3] = reg_w, reg_b, step_size, bc2
+        self.hyper.copy_(hh, non_blocking=True)
+        if self.hyper_done[kk] is None:
+            self.hyper_done[kk] = torch.cuda.Event()
+        self.hyper_done[kk].record()
         ad = (L.AdaTask * 2)(
             L.AdaTask(L.ptr(self.gw), L.ptr(s.w_src), L.ptr(s.alpha_w), L.ptr(s.delta_w), L.ptr(s.zp_w), L.ptr(self.opt.m[0]),
                       L.ptr(self.opt.v[0]), rw_, rl_, cw(s.delta_w), s.n_bits, 1, 0),
             L.AdaTask(L.ptr(self.gb), L.ptr(s.bias), L.ptr(s.alpha_b), L.ptr(s.delta_b), L.ptr(s.zp_b), L.ptr(self.opt.m[1]),
                       L.ptr(self.opt.v[1]), rb_, bl_, cw(s.delta_b), s.n_bits, 0, 0))
         L.check(L.lib.nq_adaround_step_multi(ad, 2, 1.0, 0.9, 0.999, 1e-8, L.ptr(self.hyper), st), "nq_adaround_step_multi")
-        self.launches += 10
+        self.launches += 8
 
     def rec_loss(self) -> float:
         return float(self.loss) / float(self.n * self.H * self.W)
+
+
+def cache_to_engine_layout(step: BlockStep, inps: torch.Tensor, syms, outs: torch.Tensor):
+    """NCHW fp32 caches of N frames -> (2, N, h, w, cin_p) split-bf16 inputs and (N, H, W, cg) fp32 NHWC targets."""
+    g, st = step.stage.geom, L.stream()
+    N = inps.shape[0]
+    dev = inps.device
+
+    def split(t_):
+        o = torch.zeros(2, N, step.h, step.w, step.cin_p, device=dev, dtype=torch.bfloat16)
+        L.check(L.lib.nq_nchw_to_split(L.ptr(t_.contiguous()), o.data_ptr(), N, g.cin, step.h, step.w, step.cin_p, st), "nq_nchw_to_split")
+        return o
+
+    out_c = torch.zeros(N, step.H, step.W, step.cg, device=dev)
+    L.check(L.lib.nq_nchw_to_nhwc(L.ptr(outs.contiguous()), L.ptr(out_c), N, g.c_grp, step.H, step.W, step.cg, st), "nq_nchw_to_nhwc")
+    return split(inps), (split(syms) if syms is not None else None), out_c
+
+
+def gather_frames(cache: torch.Tensor, idx_host, out: torch.Tensor):
+    """out[:, b] = cache[:, idx[b]]: whole frames are contiguous, so this is one plain copy per plane and frame (advanced
+    indexing would run an element-wise gather kernel over 2-byte elements)."""
+    for b, i in enumerate(idx_host.tolist()):
+        out[:, b].copy_(cache[:, i])
+    return out
 
 
 def _features(runner: DecoderRunner, model, embed: torch.Tensor, weight_quant: bool):
@@ -184,17 +231,25 @@ def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, 
     decay = LinearTempDecay(iters, rel_start_decay=warmup + (1 - warmup) * 0.0, start_b=b_range[0], end_b=b_range[1])
     loss_start = iters * warmup
     model.train()
+    # the caches go into the engine's own layouts ONCE (split-bf16 NHWC inputs, fp32 NHWC targets): an iteration then
+    # only gathers its frames (contiguous per frame) and never transposes
+    inp_s, sym_s, out_c = cache_to_engine_layout(step, cached_inps, cached_sym if input_prob < 1.0 else None, cached_outs)
+    cur = torch.empty_like(inp_s[:, :bsz])
+    alt = torch.empty_like(cur) if input_prob < 1.0 else None
     for i in range(iters):
-        idx = torch.randperm(n_cached)[:batch_size].to(cached_inps.device)
-        cur_inp, cur_sym = cached_inps[idx], cached_sym[idx]
-        if input_prob < 1.0:  # QDrop (calib_block.py:163-164)
-            cur_inp = torch.where(torch.rand_like(cur_inp) < input_prob, cur_inp, cur_sym)
+        idx_h = torch.randperm(n_cached)[:batch_size]
+        idx = idx_h.to(cached_inps.device)
+        gather_frames(inp_s, idx_h, cur)
+        if input_prob < 1.0:  # QDrop (calib_block.py:163-164); one draw per element, shared by the hi and lo planes
+            keep = torch.rand_like(cur[0], dtype=torch.float32) < input_prob
+            gather_frames(sym_s, idx_h, alt)
+            torch.where(keep.unsqueeze(0), cur, alt, out=cur)
         count = i + 1
         b = decay(count)
         reg_on = not (count < loss_start)
         want_log = count % 500 == 0
-        step.run(cur_inp.contiguous(), cached_outs[idx].contiguous(), weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
-                 want_reg=want_log and reg_on)
+        step.run_cached(cur, out_c, idx.int(), weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
+                        want_reg=want_log and reg_on)
         if want_log:  # calib_block.py:85-87
             rec = step.rec_loss()
             rnd = float(step.reg) * weight if reg_on else 0.0

@@ -49,9 +49,12 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
         return torch.cat([r, rest])
 
     def rand_like(x, *a, **k):
-        r = masks[calls["rand"]].to(x.device)
+        # the product draws its QDrop mask in the engine's NHWC layout (n, h, w, cin_p); the recorded draw is NCHW
+        r = masks[calls["rand"]].to(x.device).permute(0, 2, 3, 1)
         calls["rand"] += 1
-        return r
+        full = torch.ones(x.shape, device=x.device)
+        full[..., :r.shape[-1]] = r
+        return full
 
     caches = {}
     _save = cb.save_inp_oup_data
@@ -62,7 +65,7 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
         return r
 
     traj = []
-    _run = cb.BlockStep.run
+    _run = cb.BlockStep.run_cached
 
     def run(self, *a, **k):
         _run(self, *a, **k)
@@ -71,7 +74,7 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
     monkeypatch.setattr(torch, "randperm", randperm)
     monkeypatch.setattr(torch, "rand_like", rand_like)
     monkeypatch.setattr(cb, "save_inp_oup_data", save)
-    monkeypatch.setattr(cb.BlockStep, "run", run)
+    monkeypatch.setattr(cb.BlockStep, "run_cached", run)
     block_reconstruction(qnn, block, t(g["cali"]).cuda(), batch_size=int(g["bsz"]), iters=int(g["iters"]), weight=0.01,
                          opt_mode="mse", asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2, input_prob=float(g["input_prob"]),
                          p=2.0, lr=0.003)

@@ -62,3 +62,44 @@ def test_tensor_core_engine_matches_fp32_engine_at_full_size(monkeypatch, worklo
             tol = gtol * float(b.abs().max()) + 1e-12
             assert float((a - b).abs().max()) <= tol, (workload, i, name, float((a - b).abs().max()), tol)
     assert torch.isfinite(tc[2]).all()
+
+
+@pytest.mark.parametrize("workload,k", [("hnerv-bunny-3m", 5), ("hnerv-bunny-3m", 3), ("nerv-bunny-3m", 4)])
+def test_block_step_matches_torch_autograd_at_full_size(workload, k):
+    """One block-wise reconstruction step (quantization/calib_block.BlockStep: soft fake-quant, tcgen05 forward, fused
+    loss + activation backward, tcgen05 weight gradient) of a full-size decoder block against plain PyTorch fp32 autograd
+    of the same block (conv2d -> PixelShuffle -> exact GELU -> lp_loss), TF32 off."""
+    import torch.nn.functional as F
+    import neuroquant_b200 as nq
+    from neuroquant_b200.quantization.calib_block import BlockStep
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape, random_decoder
+    from oracle import nq_oracle as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    arch, cfg = WORKLOADS[workload]
+    geoms, params = random_decoder(cfg, arch, 903)
+    _, h, w = embed_shape(cfg, arch)
+    for g in geoms[:k]:
+        h, w = h * g.rh, w * g.rw
+    g = geoms[k]
+    wt, bs = params[k][0].cuda(), params[k][1].cuda()
+    st = nq.QuantStage(g, wt, bs, 5, False)
+    st.init_scales()
+    st.start_adaround()
+    gen = torch.Generator().manual_seed(23)
+    n = 2
+    x = torch.randn(n, g.cin, h, w, generator=gen).cuda()
+    tgt = torch.randn(n, g.c_grp, h * g.rh, w * g.rw, generator=gen).cuda() * 0.3
+    # checker: the oracle's soft fake-quant (pure torch, runs on the GPU tensors) + torch autograd
+    _, wq = O.adaround_quant(wt, st.alpha_w, st.delta_w, st.zp_w, st.n_bits, True)
+    _, bq = O.adaround_quant(bs, st.alpha_b, st.delta_b, st.zp_b, st.n_bits, True)
+    wq, bq = wq.detach().requires_grad_(True), bq.detach().requires_grad_(True)
+    y = F.gelu(F.pixel_shuffle(F.conv2d(x, wq, bq, padding=g.k // 2), g.rh))
+    loss = (y - tgt).abs().pow(2.0).sum(1).mean()
+    loss.backward()
+    step = BlockStep(st, n, h, w, lr=1e-3)
+    step.run(x, tgt, 0.0, 0.0, 2.0)
+    assert step.rec_loss() == pytest.approx(float(loss), rel=2e-5)
+    for name, a, b in (("dW", step.gw, wq.grad), ("db", step.gb, bq.grad)):
+        tol = 2e-4 * float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= tol, (name, float((a - b).abs().max()), tol)
