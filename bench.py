@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=8, help="synthetic frames resident per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-steps", type=int, default=10)
+    ap.add_argument("--artefact", action="store_true", help="--mode decode: decode from the packed artefact written by this run")
     ap.add_argument("--stage", type=int, default=5, help="--mode block: decoder stage (block) to reconstruct")
     ap.add_argument("--mode", default="calib", choices=["calib", "decode", "block"],
                     help="decode: quantised-decode throughput only (any workload, e.g. hnerv-1080p-12m)")
@@ -390,6 +391,15 @@ def run_decode_only(args, eng, cfg, arch, geoms, world, rank, local):
     eng.soft_w = False
     eng.invalidate()
     eng.forward(embeds[:B])
+    artefact_bytes = None
+    if args.artefact:  # write the packed artefact of this decoder, drop the live model, decode from the file
+        import tempfile
+        from neuroquant_b200.artefact import PackedDecoder, save_artefact
+        path = os.path.join(tempfile.mkdtemp(), f"{args.workload}.nqb")
+        artefact_bytes = save_artefact(eng, path)
+        want = eng.forward(embeds[:B], reuse_weights=True).clone()
+        eng = PackedDecoder(path).engine
+        assert torch.equal(eng.forward(embeds[:B]), want), "decode from the artefact differs from the live model"
     for _ in range(max(args.warmup, 3)):
         eng.forward(embeds[:B], reuse_weights=True)
     torch.cuda.synchronize()
@@ -416,7 +426,9 @@ def run_decode_only(args, eng, cfg, arch, geoms, world, rank, local):
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": eng.dtype_name,
                           "data": "synthetic", "config": {"workload": args.workload + " quantised decode", "batch": B},
                           "gpu_launches": eng.launches - l0, "gflop_per_frame": gf,
-                          "tflops_effective": fps * gf / 1e3}))
+                          "tflops_effective": fps * gf / 1e3,
+                          **({"artefact_bytes": artefact_bytes, "artefact": "decoded from the packed artefact (bit-identical to the live model)"}
+                             if artefact_bytes else {})}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -370,6 +370,15 @@ int nq_jet_head(const float* z, const float* zd1, const float* zd2, const float*
 /* ------------------------------------------------------------------------------------------------
  * Layout edges and reductions
  * ------------------------------------------------------------------------------------------------ */
+/* Packed weight codes of the quantised artefact (readme.md:125-127: the hand-off to entropy coding; the reference keeps
+ * the codes as fp32, quantizer.py:297 / quant_model.py:74-80).  Integer codes 0 .. 2^n_bits - 1 <-> a dense little-endian
+ * bit stream: element i occupies bits [i * n_bits, (i + 1) * n_bits); the stream is padded to whole groups of eight
+ * elements, nq_packed_bytes(numel, n_bits) = ceil(numel / 8) * n_bits bytes.  nq_pack_codes sets *not_integer_flag (device
+ * int, may be NULL) when an input is not an integer in range (e.g. soft-rounded codes) and stores 0 for it. */
+int64_t nq_packed_bytes(int64_t numel, int n_bits);
+int nq_pack_codes(const float* codes, int64_t numel, int n_bits, void* packed, int* not_integer_flag, void* stream);
+int nq_unpack_codes(const void* packed, int64_t numel, int n_bits, float* codes, void* stream);
+
 /* NCHW (n, c, h, w) <-> NHWC (n, h, w, c_p); pad channels are written as zero / ignored. */
 int nq_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream);
 int nq_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream);

@@ -130,6 +130,9 @@ def _load():
         "nq_split_to_nchw": (I, [P, P, I, I, I, I, I, P]),
         "nq_f32_to_split": (I, [P, P, L, P]),
         "nq_split_to_f32": (I, [P, P, L, P]),
+        "nq_packed_bytes": (L, [L, I]),
+        "nq_pack_codes": (I, [P, L, I, P, P, P]),
+        "nq_unpack_codes": (I, [P, L, I, P, P]),
         "nq_nchw_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
         "nq_nhwc_to_nchw": (I, [P, P, I, I, I, I, I, P]),
         "nq_act_bwd_unshuffle": (I, [P, P, I, I, I, I, I, I, I, P, P]),

@@ -390,6 +390,63 @@ extern "C" int nq_block_loss_bwd(const void* y_split, const float* tgt, const in
   return NQ_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed weight codes (the quantised artefact, readme.md:125-127 "implementation-agnostic" step 4): integer codes
+// 0 .. 2^bits - 1 (held in fp32 by the quantisers, quantizer.py:297) <-> a dense little-endian bit stream, element i in
+// bits [i * bits, (i + 1) * bits).  Eight elements fill exactly `bits` bytes: one thread per group of eight.
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) pack_codes_kernel(const float* __restrict__ codes, int64_t numel, int bits,
+                                                         uint8_t* __restrict__ out, int* __restrict__ bad) {
+  const int64_t groups = (numel + 7) / 8;
+  const float qmax = (float)((1 << bits) - 1);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long acc = 0ull;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t e = g * 8 + k;
+      float v = e < numel ? codes[e] : 0.f;
+      if (!(v >= 0.f && v <= qmax && v == rintf(v))) { if (bad) atomicOr(bad, 1); v = 0.f; }  // not an integer code
+      acc |= (unsigned long long)(unsigned)v << (k * bits);
+    }
+    for (int b = 0; b < bits; ++b) out[g * bits + b] = (uint8_t)(acc >> (8 * b));
+  }
+}
+__global__ void __launch_bounds__(256) unpack_codes_kernel(const uint8_t* __restrict__ in, int64_t numel, int bits,
+                                                           float* __restrict__ codes) {
+  const int64_t groups = (numel + 7) / 8;
+  const unsigned mask = (1u << bits) - 1u;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long acc = 0ull;
+    for (int b = 0; b < bits; ++b) acc |= (unsigned long long)in[g * bits + b] << (8 * b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t e = g * 8 + k;
+      if (e < numel) codes[e] = (float)((unsigned)(acc >> (k * bits)) & mask);
+    }
+  }
+}
+}  // namespace nq
+
+extern "C" int64_t nq_packed_bytes(int64_t numel, int n_bits) {
+  if (numel < 0 || n_bits < 2 || n_bits > 8) return -1;
+  return (numel + 7) / 8 * n_bits;
+}
+extern "C" int nq_pack_codes(const float* codes, int64_t numel, int n_bits, void* packed, int* not_integer_flag, void* stream) {
+  if (!codes || !packed || numel <= 0 || n_bits < 2 || n_bits > 8) return NQ_ERR_BAD_ARG;
+  pack_codes_kernel<<<grid_for((numel + 7) / 8), 256, 0, as_stream(stream)>>>(codes, numel, n_bits, reinterpret_cast<uint8_t*>(packed),
+                                                                             not_integer_flag);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+extern "C" int nq_unpack_codes(const void* packed, int64_t numel, int n_bits, float* codes, void* stream) {
+  if (!codes || !packed || numel <= 0 || n_bits < 2 || n_bits > 8) return NQ_ERR_BAD_ARG;
+  unpack_codes_kernel<<<grid_for((numel + 7) / 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), numel, n_bits,
+                                                                               codes);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
 extern "C" int nq_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, int c_p, void* stream) {
   if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_p < c) return NQ_ERR_BAD_ARG;
   nchw_to_nhwc_kernel<<<grid_for((int64_t)n * h * w * c_p), 256, 0, as_stream(stream)>>>(src, dst, n, c, h, w, c_p);

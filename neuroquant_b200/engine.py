@@ -386,7 +386,13 @@ class DecoderEngine:
             self.reg_sum.zero_()
         if not hasattr(self, "_fwd_bpl"):
             self._fwd_bpl = [2] * len(self.stages)
-        if self.mode != "off":
+        if self.mode == "packed":
+            # decoder rebuilt from a packed artefact: the integer codes ARE the state (no weights, no rounding); the
+            # de-quantised copies serve the rotated stages and the FFMA head, the tensor-core stages pack the codes
+            for s, (_, _, _, deq_w, deq_b) in zip(self.stages, self._packed):
+                deq_b.copy_(s.bias)
+                torch.mul(s.codes_w - s.zp_w, s.delta_w, out=deq_w)  # quantizer.py:299 (same two roundings as the kernel)
+        elif self.mode != "off":
             # every weight and bias quantiser of the decoder in one multi-tensor launch
             tasks = []
             for i, (s, (_, _, _, deq_w, deq_b)) in enumerate(zip(self.stages, self._packed)):
@@ -453,6 +459,8 @@ class DecoderEngine:
         """(weight, bias) rounding mode of stage i.  `stage_state` (set by the module binding when a decoder mixes
         plain and AdaRound quantisers, e.g. after block-wise reconstruction of some blocks) overrides the global mode."""
         st = self.stage_state[i] if getattr(self, "stage_state", None) else (self.mode, self.soft_w, self.soft_b)
+        if st[0] == "packed":
+            return ROUND_HARD, ROUND_HARD
         if st[0] == "uaq":
             return ROUND_NEAREST, ROUND_NEAREST
         return (ROUND_SOFT if st[1] else ROUND_HARD), (ROUND_SOFT if st[2] else ROUND_HARD)

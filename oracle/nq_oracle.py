@@ -513,3 +513,23 @@ def omega(stages: Sequence[Stage], vec: Sequence[torch.Tensor], embeds: Sequence
         hv = [a + b for a, b in zip(hv, h)]
     per = [float((h * v).sum()) for h, v in zip(hv, vec)]
     return sum(per), per
+
+
+# --------------------------------------------------------------------------------------------
+# Packed codes of the quantised artefact (include/neuroquant_b200.h: nq_pack_codes): numpy statement of the bit stream
+# --------------------------------------------------------------------------------------------
+def pack_codes_np(codes, n_bits: int):
+    """Integer codes -> little-endian bit stream, element i in bits [i*b, (i+1)*b), padded to groups of eight."""
+    import numpy as np
+    c = np.asarray(codes).reshape(-1).astype(np.uint64)
+    pad = (-len(c)) % 8
+    c = np.concatenate([c, np.zeros(pad, dtype=np.uint64)])
+    bits = ((c[:, None] >> np.arange(n_bits, dtype=np.uint64)[None, :]) & 1).astype(np.uint8).reshape(-1)
+    return np.packbits(bits, bitorder="little")
+
+
+def unpack_codes_np(packed, numel: int, n_bits: int):
+    import numpy as np
+    bits = np.unpackbits(np.asarray(packed, dtype=np.uint8), bitorder="little")[: ((numel + 7) // 8) * 8 * n_bits]
+    vals = (bits.reshape(-1, n_bits).astype(np.uint32) << np.arange(n_bits, dtype=np.uint32)[None, :]).sum(1)
+    return vals[:numel].astype(np.float32)

@@ -192,3 +192,16 @@ def test_block_reconstruction_oracle_matches_reference(tag):
     assert far < 0.01, far
     codes, _ = O.adaround_quant(q.stage.weight, q.alpha_w, q.delta_w, q.zp_w, q.n_bits, soft=False)
     assert (codes.numpy() != g["final/codes_w"]).mean() < 1e-3
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4, 5, 6, 7, 8])
+def test_packed_code_stream_statement(bits):
+    """The numpy statement of the artefact's bit stream: round trip, size, and a hand-checked vector."""
+    rng = np.random.default_rng(bits)
+    for n in (1, 7, 8, 9, 1000):
+        c = rng.integers(0, 2 ** bits, n)
+        p = O.pack_codes_np(c, bits)
+        assert len(p) == (n + 7) // 8 * bits
+        assert np.array_equal(O.unpack_codes_np(p, n, bits), c.astype(np.float32))
+    if bits == 3:  # codes 1,2,3,4,5,6,7,0 -> bits 100 010 110 001 101 011 111 000 (LSB first) -> bytes 0xD1 0x58 0x1F
+        assert O.pack_codes_np([1, 2, 3, 4, 5, 6, 7, 0], 3).tolist() == [0xD1, 0x58, 0x1F]
