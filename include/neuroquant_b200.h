@@ -229,6 +229,12 @@ int nq_head_fwd_loss(const nq_conv_desc* d, const float* x, const float* w_head,
 int nq_head_fwd_loss_split(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
                            int out_bias, const float* target, float p, float mean_pixels,
                            float* img, float* loss_sum, void* dz_head_split, void* stream);
+/* Same contract on the tensor cores, "tap-expanded": the 9 taps become GEMM columns (N = 27, K = C, no halo in the
+ * activation operand) and the convolution is finished by nine shifted adds per output -- 9 MMAs per 128 input pixels
+ * instead of 81 (nq_tc_head_fwd_loss) or 1080 FMAs per pixel (nq_head_fwd_loss_split).  cin_p <= 64. */
+int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                            int out_bias, const float* target, float p, float mean_pixels, float* img,
+                            float* loss_sum, void* dz_head_split, void* stream);
 
 /* Head weight/bias gradient: dwk_head [(9*cin_p + 4)][4] as nq_conv_wgrad; workspace >= blocks*(9*cin_p+4)*4
  * floats with blocks = nq_head_wgrad_blocks(d). */

@@ -262,6 +262,8 @@ class DecoderEngine:
         # head forward: the HBM-bound FFMA kernel (default, measured faster: 0.27 vs 0.36 ms at 2 x 640 x 1280) or
         # the tensor-core kernel with the OutImg/loss epilogue (NQ_HEAD=tc)
         self.head_tc = os.environ.get("NQ_HEAD", "simt").lower() == "tc"
+        # NQ_HEAD=tapexp: tensor cores with the taps as GEMM columns + nine shifted adds (nq_head_tc.cu)
+        self.head_tapexp = os.environ.get("NQ_HEAD", "simt").lower() == "tapexp"
         self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
@@ -523,7 +525,8 @@ class DecoderEngine:
             mp = 1.0
         want_dz = train and target is not None
         if self.use_tc and not self.head_tc:
-            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss_split, C.byref(p.desc[last]),
+            head_fn = L.lib.nq_head_fwd_loss_tapexp if (self.head_tapexp and p.desc[last].cin_p <= 64) else L.lib.nq_head_fwd_loss_split
+            L.check(self._run("head_fwd_loss", p.desc[last], head_fn, C.byref(p.desc[last]),
                               p.x[last].data_ptr(), L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target),
                               float(p_norm), mp, L.ptr(p.img) if (want_img or target is None) else None,
                               L.ptr(p.loss) if target is not None else None,
