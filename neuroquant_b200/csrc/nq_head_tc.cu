@@ -8,9 +8,10 @@
 // and the convolution is finished by nine shifted adds   y[p][o] = sum_t D[p + offset(t)][(t, o)].
 // 9 MMAs (3 channel blocks x 3 split passes) of N = 32 per 128 INPUT pixels instead of 81; the adds are 27 per pixel.
 //
-// A CTA step: a 16 x 32 block of input pixels (4 MMA tiles; linear pixel order, so the 8-row groups of the K-major
-// no-swizzle operand are simply contiguous) -> the 14 x 30 outputs inside it.  Roles (576 threads): warps 0-7 move
-// the accumulators TMEM -> shared staging [pixel][33] and then finish the outputs (bias, OutImg, loss, dL/dz), warps
+// A CTA step: a 16 x 32 block of input pixels (4 MMA tiles of 4 rows; linear pixel order, so the 8-row groups of the
+// K-major no-swizzle operand are simply contiguous) -> the 14 x 30 outputs inside it.  The tiles stream through a ring
+// of six 128-pixel buffers, so the copies of the next tiles (and of the next block) run under the MMAs of this one.
+// Roles (576 threads): warps 0-7 move the accumulators TMEM -> shared staging [pixel][33] and then finish the outputs (bias, OutImg, loss, dL/dz), warps
 // 8-15 copy the split-bf16 activations with cp.async, warp 16 issues the MMAs, warp 17 owns the TMEM allocation.
 // Accumulators are double buffered in TMEM (2 x 128 columns): the epilogue of block i overlaps the loads and MMAs of
 // block i+1.  Weights (5.8 KB fp32) are split into bf16 hi / lo planes in shared memory once per CTA.
@@ -24,7 +25,8 @@ constexpr int HT_RH = 16, HT_RW = 32;             // input block (with the 1-pix
 constexpr int HT_NPIX = HT_RH * HT_RW;            // 512 = 4 MMA tiles
 constexpr int HT_OH = HT_RH - 2, HT_OW = HT_RW - 2;
 constexpr int HT_THREADS = 576;
-constexpr int HT_CGS = HT_NPIX * 16 + 64;         // bytes per 8-channel group of the A buffer (+64: lane-pair stores conflict free)
+constexpr int HT_NB = 6;                          // ring of 128-pixel activation buffers (one MMA tile each)
+constexpr int HT_CGS = 128 * 16 + 64;             // bytes per 8-channel group of a tile buffer (+64: lane-pair stores conflict free)
 constexpr int HT_STG = 33;                        // floats per staged pixel row (27 used; odd stride: conflict-free scalar access)
 constexpr int HT_MAXC = 64;
 
@@ -82,21 +84,24 @@ __device__ __forceinline__ void hcommit(uint32_t bar) {
 
 __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid_constant__ HeadTcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // [0,128) barriers + TMEM pointer | A buffer (2 planes) | B planes | staging
+  // [0,256) barriers + TMEM pointer | HT_NB activation tile buffers (2 planes each) | B planes | staging
   const uint32_t bar0 = hsm(smem);
-  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 8, T_FULL = bar0 + 16, T_EMPTY = bar0 + 32;  // T_*: two slots each
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + HT_NB * 8, T_FULL = bar0 + 2 * HT_NB * 8, T_EMPTY = T_FULL + 16;  // T_*: two slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 240);
   const int ncg = p.C16 / 8;
   const int a_plane = ncg * HT_CGS;
+  const int a_tile = 2 * a_plane;
   const int b_plane = ncg * 32 * 16;
-  uint8_t* a_buf = smem + 128;
-  uint8_t* b_buf = a_buf + 2 * a_plane;
+  uint8_t* a_buf = smem + 256;
+  uint8_t* b_buf = a_buf + HT_NB * a_tile;
   float* stg = reinterpret_cast<float*>(b_buf + 2 * b_plane);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    hbar_init(A_FULL, 256);
-    hbar_init(A_EMPTY, 1);
+    for (int i = 0; i < HT_NB; ++i) {
+      hbar_init(A_FULL + i * 8, 256);
+      hbar_init(A_EMPTY + i * 8, 1);
+    }
     for (int i = 0; i < 2; ++i) {
       hbar_init(T_FULL + i * 8, 1);
       hbar_init(T_EMPTY + i * 8, 8);
@@ -117,8 +122,8 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
     reinterpret_cast<__nv_bfloat16*>(b_buf + b_plane)[e] = __float2bfloat16_rn(v - __bfloat162float(hv));
   }
   // channel groups beyond the stored channels (C16 > Cs) are never copied: zero them once
-  for (int e = threadIdx.x; e < (p.C16 - p.Cs) / 8 * (HT_CGS / 16) * 2; e += HT_THREADS) {
-    const int per = HT_CGS / 16, pl = e / ((p.C16 - p.Cs) / 8 * per), r = e % ((p.C16 - p.Cs) / 8 * per);
+  for (int e = threadIdx.x; e < (p.C16 - p.Cs) / 8 * (HT_CGS / 16) * 2 * HT_NB; e += HT_THREADS) {
+    const int per = (p.C16 - p.Cs) / 8 * (HT_CGS / 16), pl = e / per, r = e % per;  // pl = (buffer, plane)
     reinterpret_cast<uint4*>(a_buf + pl * a_plane + (p.Cs / 8) * HT_CGS)[r] = make_uint4(0u, 0u, 0u, 0u);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -137,20 +142,22 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
     const uint32_t b0 = ((hsm(b_buf) & 0x3FFFFu) >> 4) | ((uint32_t)(32 * 16 >> 4) << 16);
     const uint32_t a_plane16 = (uint32_t)a_plane >> 4, b_plane16 = (uint32_t)b_plane >> 4;
     const int nk = p.C16 / 16;
-    uint32_t it = 0;
+    uint32_t it = 0, ab = 0, aph = 0;
     for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       hbar_wait(T_EMPTY + acc * 8, ((it >> 1) & 1) ^ 1);
-      hbar_wait(A_FULL, it & 1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        hbar_wait(A_FULL + ab * 8, aph);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem_base + acc * 128 + j * 32;
+        const uint32_t at = a0 + ab * ((uint32_t)a_tile >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k >= nk) break;
-          const uint32_t a = a0 + (uint32_t)(j * 128 * 16 >> 4) + (uint32_t)k * 2u * (HT_CGS >> 4);
+          const uint32_t a = at + (uint32_t)k * 2u * (HT_CGS >> 4);
           const uint32_t b = b0 + (uint32_t)k * 2u * (32 * 16 >> 4);
           if (leader) {
             hmma(d, a, a_hi32, b, b_hi32, idesc, k ? 1u : 0u);
@@ -158,36 +165,39 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
             hmma(d, a, a_hi32, b + b_plane16, b_hi32, idesc, 1);
           }
         }
+        if (leader) hcommit(A_EMPTY + ab * 8);
+        if (++ab == HT_NB) { ab = 0; aph ^= 1; }
       }
-      if (leader) {
-        hcommit(A_EMPTY);
-        hcommit(T_FULL + acc * 8);
-      }
+      if (leader) hcommit(T_FULL + acc * 8);
     }
   } else if (warp >= 8 && warp < 16) {
     // ===================== loaders: split-bf16 NHWC -> [channel group][pixel][8] =====================
     const int ltid = threadIdx.x - 256;
-    const int ncs = p.Cs / 8, npair = (ncs + 1) >> 1, tasks = HT_NPIX * npair;
+    const int ncs = p.Cs / 8, npair = (ncs + 1) >> 1, tasks = 128 * npair;
     const uint32_t a_sm = hsm(a_buf);
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+    uint32_t ab = 0, aph = 0;
+    for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, img = t / (p.tiles_x * p.tiles_y);
       const int y0 = ty * HT_OH - 1, x0 = tx * HT_OW - 1;
-      hbar_wait(A_EMPTY, (it & 1) ^ 1);
-      for (int j = ltid >> 1; j < tasks; j += 128) {
-        const int cpi = j / HT_NPIX, pix = j - cpi * HT_NPIX;
-        const int cg = 2 * cpi + (ltid & 1);
-        if (cg < ncs) {
-          const int ry = pix / HT_RW, rx = pix - ry * HT_RW;
-          const int gy = y0 + ry, gx = x0 + rx;
-          const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
-          const uint8_t* src = ok ? p.x + ((size_t)((img * p.h + gy) * p.w + gx) * p.Cs + cg * 8) * 2 : p.x;
-          const uint32_t d = a_sm + cg * HT_CGS + pix * 16;
-          hcp16(d, src, ok ? 16u : 0u);
-          hcp16(d + a_plane, src + p.x_plane_bytes, ok ? 16u : 0u);
+      for (int mt = 0; mt < 4; ++mt) {  // MMA tile mt = block rows 4 mt .. 4 mt + 3
+        hbar_wait(A_EMPTY + ab * 8, aph ^ 1);
+        const uint32_t dst = a_sm + ab * a_tile;
+        for (int j = ltid >> 1; j < tasks; j += 128) {
+          const int cpi = j >> 7, pix = j & 127;
+          const int cg = 2 * cpi + (ltid & 1);
+          if (cg < ncs) {
+            const int ry = 4 * mt + (pix >> 5), rx = pix & 31;
+            const int gy = y0 + ry, gx = x0 + rx;
+            const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
+            const uint8_t* src = ok ? p.x + ((size_t)((img * p.h + gy) * p.w + gx) * p.Cs + cg * 8) * 2 : p.x;
+            const uint32_t d = dst + cg * HT_CGS + pix * 16;
+            hcp16(d, src, ok ? 16u : 0u);
+            hcp16(d + a_plane, src + p.x_plane_bytes, ok ? 16u : 0u);
+          }
         }
+        hcp_arrive(A_FULL + ab * 8);
+        if (++ab == HT_NB) { ab = 0; aph ^= 1; }
       }
-      hcp_arrive(A_FULL);
     }
   } else if (warp < 8) {
     // ===================== epilogue: TMEM -> staging, then the nine shifted adds per output =====================
@@ -324,7 +334,8 @@ extern "C" int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_spli
   q.total = (int)total;
   q.out_bias = out_bias; q.p = p; q.inv_mean = target ? 1.0f / mean_pixels : 0.f;
   const int ncg = q.C16 / 8;
-  const int smem = 128 + 2 * ncg * HT_CGS + 2 * ncg * 32 * 16 + HT_NPIX * HT_STG * 4;
+  const int smem = 256 + HT_NB * 2 * ncg * HT_CGS + 2 * ncg * 32 * 16 + HT_NPIX * HT_STG * 4;
+  if (smem > 227 * 1024) return NQ_ERR_UNSUPPORTED;
   NQ_CUDA_CHECK(cudaFuncSetAttribute(head_tapexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = sm_count();
   if (grid > q.total) grid = q.total;
