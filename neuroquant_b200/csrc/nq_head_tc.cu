@@ -209,6 +209,19 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
     for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, img = t / (p.tiles_x * p.tiles_y);
+      // the target pixels of this thread's (at most two) outputs are requested before the accumulator wait: the loss
+      // epilogue otherwise pays the DRAM latency of these loads once per output round
+      float tg[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int o = threadIdx.x + 256 * r;
+        const int oy = o / HT_OW, ox = o - oy * HT_OW;
+        const int py = ty * HT_OH + oy, px = tx * HT_OW + ox;
+        const bool ok = p.target != nullptr && o < HT_OH * HT_OW && py < p.h && px < p.w;
+        const int64_t off = (int64_t)img * 3 * plane + (int64_t)py * p.w + px;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tg[r][c] = ok ? __ldg(p.target + off + c * plane) : 0.f;
+      }
       hbar_wait(T_FULL + acc * 8, (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -233,7 +246,10 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
       __syncwarp();
       if (lane == 0) hbar_arrive(T_EMPTY + acc * 8);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // staging complete (epilogue warps only)
-      for (int o = threadIdx.x; o < HT_OH * HT_OW; o += 256) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int o = threadIdx.x + 256 * r;
+        if (o >= HT_OH * HT_OW) continue;
         const int oy = o / HT_OW, ox = o - oy * HT_OW;
         const int py = ty * HT_OH + oy, px = tx * HT_OW + ox;
         if (py >= p.h || px >= p.w) continue;
@@ -261,7 +277,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
           }
           if (p.img) p.img[off + c * plane] = outv;
           if (p.target) {
-            const float dlt = outv - __ldg(p.target + off + c * plane);
+            const float dlt = outv - tg[r][c];
             const float a = fabsf(dlt);
             if (p.p == 2.0f) {
               loss += dlt * dlt;

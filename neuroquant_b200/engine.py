@@ -259,11 +259,13 @@ class DecoderEngine:
         # weight-gradient operand planes (input activations, output gradients): default = the backward setting
         self.wg_a_planes = int(os.environ.get("NQ_WG_A_PLANES", str(self.bwd_a_planes)))
         self.wg_b_planes = int(os.environ.get("NQ_WG_B_PLANES", str(self.bwd_b_planes)))
-        # head forward: the HBM-bound FFMA kernel (default, measured faster: 0.27 vs 0.36 ms at 2 x 640 x 1280) or
-        # the tensor-core kernel with the OutImg/loss epilogue (NQ_HEAD=tc)
-        self.head_tc = os.environ.get("NQ_HEAD", "simt").lower() == "tc"
-        # NQ_HEAD=tapexp: tensor cores with the taps as GEMM columns + nine shifted adds (nq_head_tc.cu)
-        self.head_tapexp = os.environ.get("NQ_HEAD", "simt").lower() == "tapexp"
+        # head forward (measured at 2 x 640 x 1280 in a calibration step): tap-expanded tensor-core kernel 0.115 ms,
+        # FFMA strip kernel 0.26 ms, generic tensor-core kernel with the head epilogue 0.29 ms
+        head = os.environ.get("NQ_HEAD", "tapexp").lower()
+        self.head_tc = head == "tc"
+        # default: tensor cores with the taps as GEMM columns + nine shifted adds (nq_head_tc.cu, heads of <= 64 input
+        # channels); NQ_HEAD=simt: the FFMA kernels; NQ_HEAD=tc: the generic tensor-core kernel with the head epilogue
+        self.head_tapexp = head == "tapexp"
         self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)

@@ -347,13 +347,13 @@ def test_graph_replay_equals_eager(nq, monkeypatch):
 
 
 def test_tensor_core_head_variant(nq, monkeypatch):
-    """NQ_HEAD=tc: the head's forward + OutImg + loss + dL/dz as a tcgen05 GEMM epilogue gives the same frames,
-    loss and gradients as the default HBM-bound FFMA head."""
+    """The three head forward kernels (FFMA strip kernel, generic tcgen05 kernel with the head epilogue, tap-expanded
+    tcgen05 kernel = default) give the same frames, loss and gradients."""
     outs = {}
-    for mode in ("simt", "tc"):
+    for mode in ("simt", "tc", "tapexp"):
         monkeypatch.setenv("NQ_HEAD", mode)
         g, arch, cfg, stages, eng = make_engine(nq, "tiny_hnerv", "uaq")
-        assert eng.head_tc == (mode == "tc")
+        assert eng.head_tc == (mode == "tc") and eng.head_tapexp == (mode == "tapexp")
         eng.init_scales()
         eng.start_adaround()
         cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
@@ -362,10 +362,11 @@ def test_tensor_core_head_variant(nq, monkeypatch):
         eng.backward()
         grads = [x.clone() for pair in eng.param_grads() for x in pair]
         outs[mode] = (img, loss, grads)
-    assert (outs["tc"][0] - outs["simt"][0]).abs().max() < 2e-6
-    assert outs["tc"][1] == pytest.approx(outs["simt"][1], rel=1e-5)
-    for a, b in zip(outs["tc"][2], outs["simt"][2]):
-        assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-10
+    for mode in ("tc", "tapexp"):
+        assert (outs[mode][0] - outs["simt"][0]).abs().max() < 2e-6
+        assert outs[mode][1] == pytest.approx(outs["simt"][1], rel=1e-5)
+        for a, b in zip(outs[mode][2], outs["simt"][2]):
+            assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-10
 
 
 def test_saved_activation_derivative_equals_recomputed(nq, monkeypatch, conv_path):
