@@ -357,6 +357,14 @@ typedef struct nq_wgrad_finish_task {
 } nq_wgrad_finish_task;
 int nq_tc_wgrad_finish_multi(const nq_wgrad_finish_task* tasks, int n_tasks, void* stream);
 
+/* Head weight gradient, tap-expanded (the backward counterpart of nq_head_fwd_loss_tapexp): input pixels as GEMM-K, the
+ * 27 (tap, channel) pairs as columns of a dZ operand assembled with the nine shifts, one extra row of ones for the bias
+ * gradient.  Writes nq_head_wgrad_tapexp_splits(d) partial sums of (9 * cin_p + 4) x 16 floats into `workspace`, in the
+ * layout nq_tc_wgrad_finish_multi reads (psplits = that count, n_cols = 16, d with cg = 16).  cin_p <= 64. */
+int nq_head_wgrad_tapexp_splits(const nq_conv_desc* d);
+int nq_head_wgrad_tapexp(const nq_conv_desc* d, const void* x_split, const void* dz_split, float* workspace,
+                         int64_t workspace_floats, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Omega = dw^T H dw (methods/bit_assign.py:57-118,171-203) by second-order FORWARD propagation:
  * every stage carries (y, y', y'') = value and first/second directional derivative along the weight

@@ -123,6 +123,8 @@ def _load():
         "nq_tc_plan_wgrad": (I, [DP, I, I, C.POINTER(TcWgradPlan)]),
         "nq_tc_conv_wgrad": (I, [DP, C.POINTER(TcWgradPlan), P, P, P, P, L, P]),
         "nq_tc_wgrad_finish_multi": (I, [C.POINTER(WgFinishTask), I, P]),
+        "nq_head_wgrad_tapexp_splits": (I, [DP]),
+        "nq_head_wgrad_tapexp": (I, [DP, P, P, P, L, P]),
         "nq_jet_act": (I, [P, P, P, P, P, L, I, P, P, P, I, P]),
         "nq_head_fwd_loss_split": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_head_fwd_loss_tapexp": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),

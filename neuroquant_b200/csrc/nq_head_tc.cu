@@ -359,3 +359,241 @@ extern "C" int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_spli
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }
+
+// ================================================================================================
+// Head weight gradient, tap-expanded:   dW[t][c][o] = sum_p x[p + off(t)][c] * dz[p][o]
+//                                                   = sum_q x[q][c] * dzs[q][(t, o)],   dzs[q][(t, o)] = dz[q - off(t)][o]
+// One GEMM with the INPUT pixels q as K, the channels as M (plain copy of the activation tile: no shifted copies, no
+// halo rows) and the 27 (tap, channel) pairs as N; the nine shifts move to the tiny dZ operand (3 channels), which eight
+// warps assemble in shared memory from a raw halo tile.  Per 16 pixels: 2 MMAs (x_hi x [dzs_hi | dzs_lo], x_lo x dzs_hi)
+// instead of 6 in wgrad_tc_kernel, and 4x less shared-memory traffic.  One extra row of ones gives the bias gradient
+// (column of the centre tap).  Persistent CTAs over row segments of 128 pixels; accumulators stay in TMEM; every CTA
+// writes one partial in the layout nq_tc_wgrad_finish_multi reads ((9 * cin_p + 4) rows x 16 columns).
+// ================================================================================================
+namespace nq {
+
+constexpr int WT_TW = 128, WT_THREADS = 576, WT_NB = 2;
+constexpr int WT_CGS = WT_TW * 16 + 64;          // bytes per 8-row group (A: 8 channels, B: 8 columns) of a tile buffer
+constexpr int WT_RAW_ROW = (WT_TW + 2) * 16;     // raw dZ halo row: 130 pixels x (8 channels bf16)
+constexpr int WT_A_PLANE = 16 * WT_CGS, WT_B_PLANE = 4 * WT_CGS, WT_RAW_PLANE = 3 * WT_RAW_ROW;
+
+struct HeadWgParams {
+  const uint8_t* x; size_t x_plane_bytes;     // split-bf16 (n, h, w, Cs)
+  const uint8_t* dz; size_t dz_plane_bytes;   // split-bf16 (n, h, w, 8)
+  float* ws;                                  // (grid, 9 * Cs + 4, 16) partial sums
+  int n, h, w, Cs;
+  int tiles_x, total, tiles_per_cta;
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1) head_wgrad_tapexp_kernel(const __grid_constant__ HeadWgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t bar0 = hsm(smem);
+  const uint32_t LOAD_FULL = bar0, B_FULL = bar0 + 16, SLOT_EMPTY = bar0 + 32, DONE = bar0 + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+  uint8_t* a_buf = smem + 256;                                  // [slot][plane][16 groups][WT_CGS]
+  uint8_t* b_buf = a_buf + WT_NB * 2 * WT_A_PLANE;              // [slot][plane][4 groups][WT_CGS]
+  uint8_t* raw = b_buf + WT_NB * 2 * WT_B_PLANE;                // [slot][plane][3 rows][130 px][16 B]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncs = p.Cs / 8;
+  const int t_begin = blockIdx.x * p.tiles_per_cta, t_end = min(p.total, t_begin + p.tiles_per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WT_NB; ++i) {
+      hbar_init(LOAD_FULL + i * 8, 256);
+      hbar_init(B_FULL + i * 8, 8);
+      hbar_init(SLOT_EMPTY + i * 8, 1);
+    }
+    hbar_init(DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hsm(tmem_slot)), "r"(64) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // constant rows of the activation operand: group ncs = ones in channel 0 (bias gradient), groups above = zero
+  for (int e = threadIdx.x; e < WT_NB * 2 * (16 - ncs) * (WT_CGS / 16); e += WT_THREADS) {
+    const int per = (16 - ncs) * (WT_CGS / 16), sp = e / per, r = e % per;  // sp = (slot, plane)
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((sp & 1) == 0 && r < WT_CGS / 16) v.x = 0x3F80u;  // bf16 1.0, hi plane, first constant group
+    reinterpret_cast<uint4*>(a_buf + sp * WT_A_PLANE + ncs * WT_CGS)[r] = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ===================== MMA issuer =====================
+    const bool leader = helect();
+    const uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);   // D fp32, A/B bf16 both MN-major, M = 128
+    const uint32_t idesc64 = (idesc32 & ~(0x3Fu << 17)) | ((uint32_t)(64 >> 3) << 17);
+    const uint32_t hi32 = ((uint32_t)WT_CGS >> 4) | (1u << 14);  // SBO: next 8-row group
+    const uint32_t lbo = (128u >> 4) << 16;                       // LBO: second 8-pixel half of a K = 16 step
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t s = it % WT_NB, ph = (it / WT_NB) & 1;
+      hbar_wait(LOAD_FULL + s * 8, ph);
+      hbar_wait(B_FULL + s * 8, ph);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a16 = ((hsm(a_buf + s * 2 * WT_A_PLANE) & 0x3FFFFu) >> 4) | lbo;
+      const uint32_t b16 = ((hsm(b_buf + s * 2 * WT_B_PLANE) & 0x3FFFFu) >> 4) | lbo;
+#pragma unroll
+      for (int k = 0; k < WT_TW / 16; ++k) {
+        const uint32_t a = a16 + k * 16, b = b16 + k * 16;  // 16 pixels = 256 bytes
+        if (leader) {
+          hmma(tmem_base, a, hi32, b, hi32, idesc64, (it | k) ? 1u : 0u);
+          hmma(tmem_base, a + (WT_A_PLANE >> 4), hi32, b, hi32, idesc32, 1);
+        }
+      }
+      if (leader) hcommit(SLOT_EMPTY + s * 8);
+    }
+    if (leader) hcommit(DONE);
+  } else if (warp >= 8 && warp < 16) {
+    // ===================== loaders: activation tile + raw dZ halo =====================
+    const int ltid = threadIdx.x - 256;
+    const int npair = (ncs + 1) >> 1;
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t s = it % WT_NB, ph = (it / WT_NB) & 1;
+      const int tx = t % p.tiles_x, row = t / p.tiles_x;  // row = img * h + y
+      const int y = row % p.h, x0 = tx * WT_TW;
+      hbar_wait(SLOT_EMPTY + s * 8, ph ^ 1);
+      const uint32_t a_sm = hsm(a_buf + s * 2 * WT_A_PLANE);
+      for (int j = ltid >> 1; j < WT_TW * npair; j += 128) {
+        const int cpi = j >> 7, px = j & 127;
+        const int cg = 2 * cpi + (ltid & 1);
+        if (cg < ncs) {
+          const bool ok = x0 + px < p.w;
+          const uint8_t* src = ok ? p.x + ((size_t)(row * p.w + x0 + px) * p.Cs + cg * 8) * 2 : p.x;
+          const uint32_t d = a_sm + cg * WT_CGS + px * 16;
+          hcp16(d, src, ok ? 16u : 0u);
+          hcp16(d + WT_A_PLANE, src + p.x_plane_bytes, ok ? 16u : 0u);
+        }
+      }
+      const uint32_t r_sm = hsm(raw + s * 2 * WT_RAW_PLANE);
+      for (int j = ltid; j < 3 * (WT_TW + 2); j += 256) {
+        const int ry = j / (WT_TW + 2), rx = j - ry * (WT_TW + 2);
+        const int gy = y + ry - 1, gx = x0 + rx - 1;
+        const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
+        const uint8_t* src = ok ? p.dz + (size_t)((row + ry - 1) * p.w + gx) * 16 : p.dz;
+        const uint32_t d = r_sm + ry * WT_RAW_ROW + rx * 16;
+        hcp16(d, src, ok ? 16u : 0u);
+        hcp16(d + WT_RAW_PLANE, src + p.dz_plane_bytes, ok ? 16u : 0u);
+      }
+      hcp_arrive(LOAD_FULL + s * 8);
+    }
+  } else if (warp < 8) {
+    // ===================== dZ operand builders: dzs[q][(t, o)] = dz[q - off(t)][o], columns n = 3 t + o =====================
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t s = it % WT_NB, ph = (it / WT_NB) & 1;
+      hbar_wait(LOAD_FULL + s * 8, ph);
+      const uint16_t* rw = reinterpret_cast<const uint16_t*>(raw + s * 2 * WT_RAW_PLANE);
+      uint8_t* bb = b_buf + s * 2 * WT_B_PLANE;
+      for (int e = threadIdx.x; e < WT_TW * 4 * 2; e += 256) {
+        const int px = e & 127, gi = (e >> 7) & 3, pl = e >> 9;
+        uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int nn = gi * 8 + j;
+          if (nn < 27) {
+            const int tt = nn / 3, o = nn - tt * 3, kh = tt / 3, kw = tt - kh * 3;
+            const uint32_t v = rw[(pl * WT_RAW_PLANE + (2 - kh) * WT_RAW_ROW + (px + 2 - kw) * 16) / 2 + o];
+            w4[j >> 1] |= v << (16 * (j & 1));
+          }
+        }
+        *reinterpret_cast<uint4*>(bb + pl * WT_B_PLANE + gi * WT_CGS + px * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) hbar_arrive(B_FULL + s * 8);
+    }
+    // ===================== epilogue (warps 0-3): accumulator -> this CTA's partial =====================
+    const int rows_total = 9 * p.Cs + 4;
+    float* out = p.ws + (size_t)blockIdx.x * rows_total * 16;
+    if (warp < 4) {
+      for (int e = threadIdx.x; e < rows_total * 4; e += 128) reinterpret_cast<float4*>(out)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t_end > t_begin) {
+        hbar_wait(DONE, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int rowm = warp * 32 + lane;  // accumulator row = channel (or the ones row)
+        uint32_t v[32], v2[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+            "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+            "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]), "=r"(v2[8]),
+              "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15]), "=r"(v2[16]),
+              "=r"(v2[17]), "=r"(v2[18]), "=r"(v2[19]), "=r"(v2[20]), "=r"(v2[21]), "=r"(v2[22]), "=r"(v2[23]), "=r"(v2[24]),
+              "=r"(v2[25]), "=r"(v2[26]), "=r"(v2[27]), "=r"(v2[28]), "=r"(v2[29]), "=r"(v2[30]), "=r"(v2[31])
+            : "r"(taddr + 32)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const bool is_ch = rowm < p.Cs, is_ones = rowm == p.Cs;
+        if (is_ch || is_ones) {
+#pragma unroll
+          for (int nn = 0; nn < 27; ++nn) {
+            const float val = __uint_as_float(v[nn]) + __uint_as_float(v2[nn]);
+            const int tt = nn / 3, o = nn - tt * 3;
+            if (is_ch) out[((size_t)tt * p.Cs + rowm) * 16 + o] = val;
+            else if (tt == 4) out[(size_t)9 * p.Cs * 16 + o] = val;  // bias gradient: unshifted (centre-tap) column
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 17) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+  }
+}
+
+}  // namespace nq
+
+extern "C" int nq_head_wgrad_tapexp_splits(const nq_conv_desc* d) {
+  if (check_conv_desc(d)) return 0;
+  const long long total = (long long)d->n * d->h * ((d->w + WT_TW - 1) / WT_TW);
+  return (int)(total < sm_count() ? total : sm_count());
+}
+
+extern "C" int nq_head_wgrad_tapexp(const nq_conv_desc* d, const void* x_split, const void* dz_split, float* workspace,
+                                    int64_t workspace_floats, void* stream) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  if (d->ksize != 3 || d->rh != 1 || d->rw != 1 || d->cout != 3) return NQ_ERR_BAD_SHAPE;
+  if (!x_split || !dz_split || !workspace) return NQ_ERR_BAD_ARG;
+  if (d->cin_p % 8 || d->cin_p > HT_MAXC) return NQ_ERR_UNSUPPORTED;
+  const int grid = nq_head_wgrad_tapexp_splits(d);
+  const int rows_total = 9 * d->cin_p + 4;
+  if (workspace_floats < (int64_t)grid * rows_total * 16) return NQ_ERR_WORKSPACE;
+  const size_t pix = (size_t)d->n * d->h * d->w;
+  if (pix >= (1ULL << 31)) return NQ_ERR_BAD_SHAPE;
+  HeadWgParams q{};
+  q.x = reinterpret_cast<const uint8_t*>(x_split); q.x_plane_bytes = pix * d->cin_p * 2;
+  q.dz = reinterpret_cast<const uint8_t*>(dz_split); q.dz_plane_bytes = pix * 16;
+  q.ws = workspace; q.n = d->n; q.h = d->h; q.w = d->w; q.Cs = d->cin_p;
+  q.tiles_x = (d->w + WT_TW - 1) / WT_TW;
+  q.total = d->n * d->h * q.tiles_x;
+  q.tiles_per_cta = (q.total + grid - 1) / grid;
+  const int smem = 256 + WT_NB * 2 * (WT_A_PLANE + WT_B_PLANE + WT_RAW_PLANE);
+  NQ_CUDA_CHECK(cudaFuncSetAttribute(head_wgrad_tapexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  head_wgrad_tapexp_kernel<<<grid, WT_THREADS, smem, as_stream(stream)>>>(q);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}

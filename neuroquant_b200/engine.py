@@ -266,6 +266,8 @@ class DecoderEngine:
         # default: tensor cores with the taps as GEMM columns + nine shifted adds (nq_head_tc.cu, heads of <= 64 input
         # channels); NQ_HEAD=simt: the FFMA kernels; NQ_HEAD=tc: the generic tensor-core kernel with the head epilogue
         self.head_tapexp = head == "tapexp"
+        # head weight gradient: tap-expanded kernel (default, 0.18 ms) or the generic tensor-core wgrad kernel (NQ_HEAD_WG=generic, 0.22 ms)
+        self.head_wg_tapexp = os.environ.get("NQ_HEAD_WG", "tapexp").lower() == "tapexp"
         self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
@@ -622,7 +624,20 @@ class DecoderEngine:
             d = p.desc[i]
             _, wt, _, _, _ = self._packed[i]
             ws, sp = p.ws[i]
-            if isinstance(sp, L.TcWgradPlan):
+            if isinstance(sp, L.TcWgradPlan) and i == last and self.head_wg_tapexp and d.cin_p <= 64 and p.head_desc16 is not None \
+                    and p.head_desc16.cg == 16 and not self.stages[i].hadamard:
+                # head: tap-expanded weight gradient (nq_head_tc.cu); same partial layout, finished with the others
+                if not hasattr(p, "head_wg_ws"):
+                    n_sp = int(L.lib.nq_head_wgrad_tapexp_splits(C.byref(d)))
+                    p.head_wg_ws = (torch.empty(n_sp * (9 * d.cin_p + 4) * 16, device=self.device), n_sp)
+                hws, n_sp = p.head_wg_ws
+                L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_head_wgrad_tapexp, C.byref(d), p.x[i].data_ptr(), p.dz[i].data_ptr(),
+                                  L.ptr(hws), hws.numel(), st), "nq_head_wgrad_tapexp")
+                self.launches += 1
+                gw_, gb_ = views[i]
+                finish.append(L.WgFinishTask(C.pointer(p.head_desc16), L.ptr(hws), L.ptr(gw_), L.ptr(gb_), n_sp, 16,
+                                             self.stages[i].cin_src, 0))
+            elif isinstance(sp, L.TcWgradPlan):
                 # partial sums only (dwk = NULL): one multi-stage launch after the loop reduces and unpacks them all
                 L.check(self._run(f"conv_wgrad[{i}]", d, L.lib.nq_tc_conv_wgrad, C.byref(d), C.byref(sp), p.x[i].data_ptr(),
                                   p.dz[i].data_ptr(), None, L.ptr(ws), ws.numel(), st), "nq_tc_conv_wgrad")

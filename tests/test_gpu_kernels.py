@@ -456,3 +456,22 @@ def test_host_batch_pipe_orders_and_reuses_slots(nq):
     assert float(acc) == want
     with pytest.raises(RuntimeError):
         pipe.get()
+
+
+def test_head_weight_gradient_variants_agree(nq, monkeypatch):
+    """Tap-expanded head weight gradient (default, nq_head_wgrad_tapexp) against the generic tensor-core wgrad kernel: same
+    gradient for every tensor (only the head's path differs; the tolerance is fp32 summation order)."""
+    outs = {}
+    for mode in ("generic", "tapexp"):
+        monkeypatch.setenv("NQ_HEAD_WG", mode)
+        g, arch, cfg, stages, eng = make_engine(nq, "tiny_hnerv", "uaq")
+        assert eng.head_wg_tapexp == (mode == "tapexp")
+        eng.init_scales()
+        eng.start_adaround()
+        cali, frames = dev(t(g["cali"])), dev(t(g["frames"]))
+        eng.forward(cali[:2], train=True, target=frames[:2])
+        eng.backward()
+        outs[mode] = [(gw.clone(), gb.clone()) for gw, gb in eng._grad_buffers()[1]]
+    for (gw_a, gb_a), (gw_b, gb_b) in zip(outs["tapexp"], outs["generic"]):
+        assert (gw_a - gw_b).abs().max() <= 1e-5 * gw_b.abs().max() + 1e-12
+        assert (gb_a - gb_b).abs().max() <= 1e-5 * gb_b.abs().max() + 1e-12
