@@ -493,19 +493,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) head_wgrad_tapexp_kernel(const 
       hbar_wait(LOAD_FULL + s * 8, ph);
       const uint16_t* rw = reinterpret_cast<const uint16_t*>(raw + s * 2 * WT_RAW_PLANE);
       uint8_t* bb = b_buf + s * 2 * WT_B_PLANE;
-      for (int e = threadIdx.x; e < WT_TW * 4 * 2; e += 256) {
-        const int px = e & 127, gi = (e >> 7) & 3, pl = e >> 9;
-        uint32_t w4[4] = {0u, 0u, 0u, 0u};
+      {  // one thread = one pixel of one plane: all 27 (tap, channel) columns, every index a compile-time constant
+        const int px = threadIdx.x & 127, pl = threadIdx.x >> 7;
+        const uint16_t* rp = rw + (pl * WT_RAW_PLANE + (px + 2) * 16) / 2;
+        uint8_t* dst = bb + pl * WT_B_PLANE + px * 16;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int nn = gi * 8 + j;
-          if (nn < 27) {
-            const int tt = nn / 3, o = nn - tt * 3, kh = tt / 3, kw = tt - kh * 3;
-            const uint32_t v = rw[(pl * WT_RAW_PLANE + (2 - kh) * WT_RAW_ROW + (px + 2 - kw) * 16) / 2 + o];
-            w4[j >> 1] |= v << (16 * (j & 1));
+        for (int gi = 0; gi < 4; ++gi) {
+          uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int nn = gi * 8 + j;
+            if (nn < 27) {
+              const int tt = nn / 3, o = nn - tt * 3, kh = tt / 3, kw = tt - kh * 3;
+              const uint32_t v = rp[((2 - kh) * WT_RAW_ROW - kw * 16) / 2 + o];
+              w4[j >> 1] |= v << (16 * (j & 1));
+            }
           }
+          *reinterpret_cast<uint4*>(dst + gi * WT_CGS) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
-        *reinterpret_cast<uint4*>(bb + pl * WT_B_PLANE + gi * WT_CGS + px * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
