@@ -266,7 +266,7 @@ class DecoderEngine:
         # default: tensor cores with the taps as GEMM columns + nine shifted adds (nq_head_tc.cu, heads of <= 64 input
         # channels); NQ_HEAD=simt: the FFMA kernels; NQ_HEAD=tc: the generic tensor-core kernel with the head epilogue
         self.head_tapexp = head == "tapexp"
-        # head weight gradient: tap-expanded kernel (default, 0.18 ms) or the generic tensor-core wgrad kernel (NQ_HEAD_WG=generic, 0.22 ms)
+        # head weight gradient: tap-expanded kernel (default, 0.14 ms) or the generic tensor-core wgrad kernel (NQ_HEAD_WG=generic, 0.22 ms)
         self.head_wg_tapexp = os.environ.get("NQ_HEAD_WG", "tapexp").lower() == "tapexp"
         self.cluster = int(os.environ.get("NQ_CLUSTER", "2"))  # CTAs sharing a weight stream by TMA multicast
         self._plans: Dict[Tuple[int, int, int, bool], _Plan] = {}
@@ -625,7 +625,7 @@ class DecoderEngine:
             _, wt, _, _, _ = self._packed[i]
             ws, sp = p.ws[i]
             if isinstance(sp, L.TcWgradPlan) and i == last and self.head_wg_tapexp and d.cin_p <= 64 and p.head_desc16 is not None \
-                    and p.head_desc16.cg == 16 and not self.stages[i].hadamard:
+                    and p.head_desc16.cg == 16:
                 # head: tap-expanded weight gradient (nq_head_tc.cu); same partial layout, finished with the others
                 if not hasattr(p, "head_wg_ws"):
                     n_sp = int(L.lib.nq_head_wgrad_tapexp_splits(C.byref(d)))
