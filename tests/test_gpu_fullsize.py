@@ -103,3 +103,77 @@ def test_block_step_matches_torch_autograd_at_full_size(workload, k):
     for name, a, b in (("dW", step.gw, wq.grad), ("db", step.gb, bq.grad)):
         tol = 2e-4 * float(b.abs().max()) + 1e-12
         assert float((a - b).abs().max()) <= tol, (name, float((a - b).abs().max()), tol)
+
+
+def _calibrate(monkeypatch, conv, iters, perturb=0.0):
+    monkeypatch.setenv("NQ_CONV", conv)
+    import neuroquant_b200 as nq
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape, random_decoder
+    arch, cfg = WORKLOADS["hnerv-bunny-3m"]
+    geoms, params = random_decoder(cfg, arch, 903)
+    stages = [nq.QuantStage(g, w.cuda(), b.cuda(), nb, False) for g, (w, b), nb in zip(geoms, params, [6, 5, 4, 5, 5, 6, 6])]
+    eng = nq.DecoderEngine(stages)
+    c, h0, w0 = embed_shape(cfg, arch)
+    gen = torch.Generator().manual_seed(29)
+    embeds = torch.randn(8, c, h0, w0, generator=gen).cuda()
+    # targets = ground-truth frames the full-precision decoder fits at ~35 dB, as in the reference, whose calibration
+    # loss and PSNR are both taken against the data set's frames (calib_model.py:150-160, :211-221)
+    eng.mode = "off"
+    frames = torch.cat([eng.forward(embeds[i:i + 2]).clone() for i in range(0, 8, 2)])
+    frames = (frames + 0.0178 * torch.randn(frames.shape, generator=gen).cuda()).contiguous()
+    if perturb:  # tools/chaos_check.py: how far do two runs of the SAME engine drift on inputs one rounding apart?
+        embeds = embeds * (1 + perturb * torch.randn(embeds.shape, generator=gen).cuda())
+    eng.mode = "uaq"
+    eng.init_scales()
+    order = [[0, 5], [3, 6], [1, 4], [7, 2]]
+
+    def fetch(idx):
+        idx = torch.as_tensor(idx, device="cuda")
+        return embeds[idx], frames[idx]
+
+    log = []
+    loop = nq.CalibrationLoop(eng, fetch, len(order), iters=iters, weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003, log=log)
+    loop.run(lambda: order)
+    out = torch.cat([eng.forward(embeds[i:i + 2]).clone() for i in range(0, 8, 2)])  # hard-rounded weights
+    mse = ((out - frames) ** 2).flatten(1).mean(1)
+    psnr = (-10 * torch.log10(mse + 1e-9)).cpu()
+    codes = [s.codes_w.clone() for s in eng.stages]
+    state = [(s.w_src.clone(), s.alpha_w.clone(), s.delta_w.clone(), s.zp_w.clone(), s.n_bits) for s in eng.stages]
+    del eng
+    torch.cuda.empty_cache()
+    return psnr, log, codes, state
+
+
+def test_full_size_calibration_psnr_parity(monkeypatch):
+    """North-star bar at the benchmark's own size: a (shortened) two-phase calibration of HNeRV-Bunny-3M, W 6 5 4 5 5 6 6,
+    on the tensor-core engine and on the exact-fp32 engine in the same batch order ends at the same quality -- per-frame
+    PSNR of the hard-rounded decode within 0.01 dB (mean) -- with matching loss trajectories, and its final integer codes
+    are the reference quantiser's for the V and scales it learned."""
+    iters = 240
+    from oracle import nq_oracle as O
+    p_tc, log_tc, codes_tc, state_tc = _calibrate(monkeypatch, "tc", iters)
+    p_ff, log_ff, codes_ff, _ = _calibrate(monkeypatch, "simt", iters)
+    # integer codes: bit-exact with the reference quantiser for the run's own final V and (fp16-rounded) scales
+    for (w, alpha, delta, zp, nb), got in zip(state_tc, codes_tc):
+        want, _ = O.adaround_quant(w, alpha, delta.half().float(), zp.half().float(), nb, False)
+        assert torch.equal(got, want)
+    assert len(log_tc) == len(log_ff) > 200
+    rec_tc = torch.tensor([r[2] for r in log_tc]); rec_ff = torch.tensor([r[2] for r in log_ff])
+    # Adam's first steps are sign-like (g / sqrt(v) ~ +-1), so an element whose gradient is at rounding level moves by
+    # +-lr depending on the summation order: the early transient differs by tens of percent between ANY two correct
+    # implementations (the reference on two cuDNN algorithms included).  What must agree is where the run settles.
+    ratio = rec_tc / rec_ff
+    late = slice(iters // 2, None)
+    mism = sum(int((a != b).sum()) for a, b in zip(codes_tc, codes_ff)) / sum(a.numel() for a in codes_tc)
+    report = dict(ratio_all=(float(ratio.min()), float(ratio.max())), ratio_late=(float(ratio[late].min()), float(ratio[late].max())),
+                  psnr_tc=float(p_tc.mean()), psnr_ff=float(p_ff.mean()), psnr_frame=float((p_tc - p_ff).abs().max()), code_mismatch=mism)
+    print(report)
+    assert 0.5 < float(ratio.min()) and float(ratio.max()) < 2.0, report
+    assert 0.95 < float(ratio[late].min()) and float(ratio[late].max()) < 1.05, report
+    assert abs(float(p_tc.mean() - p_ff.mean())) < 0.01, report           # dB, the north-star bar
+    assert float((p_tc - p_ff).abs().max()) < 0.03, report
+    # `code_mismatch` BETWEEN the two runs is reported, not asserted: the fp16 rounding of the learned step size and the
+    # floor make the dynamics discontinuous, so two correct engines end phase 1 on step sizes an fp16 ulp or two apart
+    # and from there on different (equally good) codes -- 21 % of them in this run, at 2e-5 dB PSNR difference.  The
+    # yardstick: the exact-fp32 engine against ITSELF with the embeddings perturbed by 1e-7 ends 17 % of the codes apart
+    # (tools/chaos_check.py, measured on a B200).
