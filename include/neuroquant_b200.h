@@ -411,6 +411,17 @@ int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int h, int w, i
 int nq_block_loss_bwd(const void* y_split, const float* tgt, const int32_t* frame_idx, const float* gprime, int n, int h, int w,
                       int rh, int rw, int cg, float p, float grad_scale, float* loss_sum, void* dz_split, void* stream);
 
+/* Fisher-weighted block losses (LossFunction.__call__, calib_block.py:66-72) on the layouts of nq_block_loss_bwd.
+ * fisher: the cached |dL/d(block output)| + 1 (save_grad_data, data_utils.py:91-119), fp32 NHWC (N, h*rh, w*rw, cg) like
+ * the target cache and addressed through the same frame_idx.
+ *   mode 1 'fisher_diag': *loss_sum += sum d^2 F^2 (caller divides by n*H*W);  dy = grad_scale * 2 d F^2
+ *   mode 2 'fisher_full': frame_dot[b] = sum_{c,h,w} |d| F (n floats, overwritten); dy = grad_scale * 2 frame_dot[b] F sign(d)
+ *                         (the loss is sum_b frame_dot[b]^2 / (n*C*H*W*100), formed by the caller; loss_sum is not touched)
+ * dz_split as nq_block_loss_bwd: dy * gprime, un-shuffled, split-bf16. */
+int nq_block_loss_bwd_fisher(const void* y_split, const float* tgt, const float* fisher, const int32_t* frame_idx,
+                             const float* gprime, int n, int h, int w, int rh, int rw, int cg, int mode, float grad_scale,
+                             float* loss_sum, float* frame_dot, void* dz_split, void* stream);
+
 /* lp_loss (quantizer.py:66-73) standalone: *loss_sum += sum |pred - tgt|^p; grad (may be NULL) receives
  * grad_scale * p * |d|^(p-1) * sign(d). */
 int nq_lp_loss(const float* pred, const float* tgt, int64_t numel, float p, float grad_scale,

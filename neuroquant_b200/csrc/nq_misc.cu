@@ -373,6 +373,121 @@ __global__ void __launch_bounds__(256) block_loss_bwd_kernel(const uint4* __rest
 }
 }  // namespace nq
 
+// ---------------------------------------------------------------------------------------------
+// Fisher-weighted block losses (calib_block.py:66-72) on the same layouts.  F = cached |dL/dy| + 1 (data_utils.py:113),
+// fp32 NHWC like the target cache and addressed through the same frame_idx.
+//   MODE 1  fisher_diag : loss += sum d^2 F^2,               dy = 2 d F^2
+//   MODE 2  fisher_full, pass A : frame_dot[b] += sum |d| F  (no gradient)
+//   MODE 3  fisher_full, pass B : dy = 2 frame_dot[b] F sign(d)         (loss = sum_b frame_dot[b]^2, formed by the caller)
+// blockIdx.y = batch entry, so that pass A reduces one frame per block.
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+template <int MODE>
+__global__ void __launch_bounds__(256) block_fisher_kernel(const uint4* __restrict__ y_hi, const uint4* __restrict__ y_lo,
+                                                           const float4* __restrict__ tgt, const float4* __restrict__ fisher,
+                                                           const int* __restrict__ frame_idx, const float4* __restrict__ gprime,
+                                                           int h, int w, int rh, int rw, int cg, float grad_scale,
+                                                           float* __restrict__ loss_sum, float* __restrict__ frame_dot,
+                                                           uint4* __restrict__ dz_hi, uint4* __restrict__ dz_lo) {
+  __shared__ float red[32];
+  const int c8n = cg >> 3;
+  const int W2 = w * rw, H2 = h * rh;
+  const int frame8 = H2 * W2 * c8n;
+  const int b = blockIdx.y;
+  const int src = frame_idx != nullptr ? frame_idx[b] : b;
+  const float dot = MODE == 3 ? frame_dot[b] : 0.f;
+  float acc = 0.f;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < frame8; f += gridDim.x * blockDim.x) {
+    const size_t e = (size_t)b * frame8 + f, te = (size_t)src * frame8 + f;
+    const int c8 = f % c8n;
+    const int pix = f / c8n;
+    const int x = pix % W2, yy = pix / W2;
+    const uint4 yh = y_hi[e], yl = y_lo[e];
+    const float4 t0 = tgt[2 * te], t1 = tgt[2 * te + 1];
+    const float4 f0 = fisher[2 * te], f1 = fisher[2 * te + 1];
+    float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+    if (MODE != 2 && gprime != nullptr) { g0 = gprime[2 * e]; g1 = gprime[2 * e + 1]; }
+    const uint32_t hw[4] = {yh.x, yh.y, yh.z, yh.w}, lw[4] = {yl.x, yl.y, yl.z, yl.w};
+    const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t hb = q ? (hw[k] & 0xFFFF0000u) : (hw[k] << 16), lb = q ? (lw[k] & 0xFFFF0000u) : (lw[k] << 16);
+        const float d = (__uint_as_float(hb) + __uint_as_float(lb)) - tv[2 * k + q];
+        const float F = fabsf(fv[2 * k + q]);
+        float g = 0.f;
+        if (MODE == 1) {
+          acc += d * d * F * F;
+          g = 2.0f * d * F * F;
+        } else if (MODE == 2) {
+          acc += fabsf(d) * F;
+        } else {
+          g = 2.0f * dot * F * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        }
+        gr[q] = g * grad_scale * gv[2 * k + q];
+      }
+      if (MODE != 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(gr[0]), h1 = __float2bfloat16_rn(gr[1]);
+        oh[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        ol[k] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gr[0] - __bfloat162float(h0))) |
+                ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gr[1] - __bfloat162float(h1))) << 16);
+      }
+    }
+    if (MODE != 2) {
+      const int qh = yy / rh, si = yy - qh * rh, qw = x / rw, sj = x - qw * rw;
+      const size_t o = ((size_t)((b * h + qh) * w + qw) * (rh * rw) + (si * rw + sj)) * c8n + c8;
+      dz_hi[o] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      dz_lo[o] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    }
+  }
+  if (MODE != 3) {
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      if (MODE == 1 && loss_sum != nullptr) atomicAdd(loss_sum, acc);
+      if (MODE == 2) atomicAdd(frame_dot + b, acc);
+    }
+  }
+}
+}  // namespace nq
+
+extern "C" int nq_block_loss_bwd_fisher(const void* y_split, const float* tgt, const float* fisher, const int32_t* frame_idx,
+                                        const float* gprime, int n, int h, int w, int rh, int rw, int cg, int mode,
+                                        float grad_scale, float* loss_sum, float* frame_dot, void* dz_split, void* stream) {
+  if (!y_split || !tgt || !fisher || !dz_split || n <= 0 || h <= 0 || w <= 0 || rh <= 0 || rw <= 0 || cg <= 0) return NQ_ERR_BAD_ARG;
+  if (mode != 1 && mode != 2) return NQ_ERR_BAD_ARG;
+  if (mode == 2 && !frame_dot) return NQ_ERR_BAD_ARG;
+  if (cg % 8 || n > 65535) return NQ_ERR_BAD_SHAPE;
+  const int64_t total = (int64_t)n * h * rh * w * rw * cg;
+  if (total / 8 >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
+  const int64_t frame8 = total / 8 / n;
+  const uint16_t* yh = reinterpret_cast<const uint16_t*>(y_split);
+  uint16_t* dh = reinterpret_cast<uint16_t*>(dz_split);
+  // about two waves of 256-thread blocks over the batch
+  int per_frame = (int)std::min<int64_t>((frame8 + 255) / 256, std::max<int64_t>(1, (2LL * 8 * sm_count()) / n));
+  dim3 grid(per_frame, n);
+  cudaStream_t st = as_stream(stream);
+#define NQ_FISHER_ARGS                                                                                                         \
+  reinterpret_cast<const uint4*>(yh), reinterpret_cast<const uint4*>(yh + total), reinterpret_cast<const float4*>(tgt),        \
+      reinterpret_cast<const float4*>(fisher), frame_idx, reinterpret_cast<const float4*>(gprime), h, w, rh, rw, cg, grad_scale, \
+      loss_sum, frame_dot, reinterpret_cast<uint4*>(dh), reinterpret_cast<uint4*>(dh + total)
+  if (mode == 1) {
+    block_fisher_kernel<1><<<grid, 256, 0, st>>>(NQ_FISHER_ARGS);
+  } else {
+    if (cudaMemsetAsync(frame_dot, 0, sizeof(float) * n, st) != cudaSuccess) return NQ_ERR_CUDA;
+    block_fisher_kernel<2><<<grid, 256, 0, st>>>(NQ_FISHER_ARGS);
+    NQ_LAUNCH_CHECK();
+    block_fisher_kernel<3><<<grid, 256, 0, st>>>(NQ_FISHER_ARGS);
+  }
+#undef NQ_FISHER_ARGS
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
 extern "C" int nq_block_loss_bwd(const void* y_split, const float* tgt, const int32_t* frame_idx, const float* gprime, int n, int h,
                                  int w, int rh, int rw, int cg, float p, float grad_scale, float* loss_sum, void* dz_split,
                                  void* stream) {

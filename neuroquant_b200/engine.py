@@ -402,17 +402,20 @@ class DecoderEngine:
             # every weight and bias quantiser of the decoder in one multi-tensor launch
             tasks = []
             for i, (s, (_, _, _, deq_w, deq_b)) in enumerate(zip(self.stages, self._packed)):
+                if self._stage_off(i):
+                    continue
                 mw, mb = self._round_modes(i)
                 tasks.append(self._fq_task(s.w_src, s.alpha_w, s.delta_w, s.zp_w, s.n_bits, mw, s.codes_w, deq_w,
                                            reg_b is not None and mw == ROUND_SOFT))
                 tasks.append(self._fq_task(s.bias, s.alpha_b, s.delta_b, s.zp_b, s.n_bits, mb, s.codes_b, deq_b, False))
-            arr = (L.FqTask * len(tasks))(*tasks)
-            L.check(L.lib.nq_fakequant_fwd_multi(arr, len(tasks), L.ptr(self.reg_sum) if reg_b is not None else None,
-                                                 float(reg_b or 0.0), st), "nq_fakequant_fwd_multi")
-            self.launches += (len(tasks) + L.MULTI_MAX - 1) // L.MULTI_MAX
+            if tasks:
+                arr = (L.FqTask * len(tasks))(*tasks)
+                L.check(L.lib.nq_fakequant_fwd_multi(arr, len(tasks), L.ptr(self.reg_sum) if reg_b is not None else None,
+                                                     float(reg_b or 0.0), st), "nq_fakequant_fwd_multi")
+                self.launches += (len(tasks) + L.MULTI_MAX - 1) // L.MULTI_MAX
         packs = []
         for i, (s, d, (wk, wt, bp, deq_w, deq_b)) in enumerate(zip(self.stages, p.desc, self._packed)):
-            if self.mode == "off":
+            if self._stage_off(i):
                 w_for_conv, b_for_conv, cin_src = s.weight, s.bias, s.geom.cin
             else:
                 if s.hadamard:  # quant_layer.py:71: rotate back, keep the first C_in channels
@@ -438,7 +441,7 @@ class DecoderEngine:
             # codes are integers and are what the conv multiplies (no rotation in between); the step size
             # is applied per output channel in the epilogue.  Otherwise the de-quantised fp32 weights,
             # split into two bf16 planes.
-            integer = self.mode != "off" and not s.hadamard
+            integer = not self._stage_off(i) and not s.hadamard
             exact1 = integer and self._round_modes(i)[0] != ROUND_SOFT
             bpl = 1 if exact1 else 2
             self._fwd_bpl[i] = bpl
@@ -460,6 +463,14 @@ class DecoderEngine:
             self.launches += (len(packs) + L.MULTI_MAX - 1) // L.MULTI_MAX
         self._weights_valid = True
         self._wt_valid = need_wt
+
+    def _stage_off(self, i: int) -> bool:
+        """Stage i runs on its full-precision weights: the whole decoder (mode 'off') or this stage alone ('off' in
+        `stage_state`: quantize_model_till, data_utils.py:261-272, quantises a prefix of the decoder only)."""
+        if self.mode == "off":
+            return True
+        ss = getattr(self, "stage_state", None)
+        return bool(ss) and ss[i][0] == "off"
 
     def _round_modes(self, i: int):
         """(weight, bias) rounding mode of stage i.  `stage_state` (set by the module binding when a decoder mixes
@@ -681,6 +692,32 @@ class DecoderEngine:
             L.check(L.lib.nq_tc_wgrad_finish_multi(arr, len(finish), st), "nq_tc_wgrad_finish_multi")
             self.launches += (len(finish) + L.MULTI_MAX - 1) // L.MULTI_MAX
         return flat
+
+    def stage_input_grad(self, i: int) -> torch.Tensor:
+        """dL/d(input of stage i) = dL/d(output of block i-1, after its activation and up-shuffle) of the last
+        forward(train=True, target=...) + backward(), as (n, C, H, W) fp32.  backward() itself only keeps that gradient
+        multiplied by the activation derivative (dz[i-1]); this re-runs stage i's data gradient with a linear
+        predecessor.  Used for the output-gradient cache of the Fisher block losses (data_utils.py:209-258)."""
+        p = self._last_plan
+        assert p.train and hasattr(p, "dwk") and 0 < i < len(self.stages)
+        st = L.stream()
+        d, g_prev = p.desc[i], self.geoms[i - 1]
+        last = len(self.stages) - 1
+        out = torch.empty_like(p.dz[i - 1])
+        if self.use_tc:
+            pl, wpk = (p.tc_head_dgrad, self._head_dgrad) if i == last else (p.tc_dgrad[i], self._tcw[i][1])
+            dws = p.dgrad_ws if pl.ksplit > 1 else None
+            L.check(L.lib.nq_tc_conv_dgrad(C.byref(d), C.byref(pl), p.dz[i].data_ptr(), wpk.data_ptr(), None, g_prev.rh, g_prev.rw, 0,
+                                           out.data_ptr(), L.ptr(dws), dws.numel() if dws is not None else 0, st), "nq_tc_conv_dgrad")
+            out = out[0].float() + out[1].float()
+        else:
+            _, wt, _, _, _ = self._packed[i]
+            L.check(L.lib.nq_conv_dgrad(C.byref(d), L.ptr(p.dz[i]), L.ptr(wt), None, g_prev.rh, g_prev.rw, 0, L.ptr(out), st),
+                    "nq_conv_dgrad")
+        n, h, w = out.shape[0], out.shape[1], out.shape[2]
+        cg = out.shape[3] // (g_prev.rh * g_prev.rw)
+        out = out.view(n, h, w, g_prev.rh, g_prev.rw, cg).permute(0, 5, 1, 3, 2, 4)
+        return out.reshape(n, cg, h * g_prev.rh, w * g_prev.rw)[:, :g_prev.c_grp].contiguous()
 
     def param_grads(self, grad_scale: float = 1.0, reg_w: float = 0.0, reg_b: float = 0.0, hyper: Optional[torch.Tensor] = None):
         """Chain the (possibly all-reduced) weight gradients through the rotation and the quantiser

@@ -9,8 +9,11 @@ backward + un-shuffle (nq_block_loss_bwd), tcgen05 weight gradient + finish, and
 Differences from the network-wise variant that the reference has and this keeps: only this block's quantisers become
 AdaRound quantisers; the regulariser covers the block's weight only; BOTH its weight and bias quantisers end
 hard-rounded (calib_block.py:180-183); the cached inputs / outputs drop the last len(cali) % 10 samples
-(data_utils.py:67).  `opt_mode` 'fisher_diag' / 'fisher_full' and hadamard blocks are not supported (the reference's own
-block_reconstruction cannot run on a rotated layer: calib_block.py:125 initialises alpha from the unrotated weight).
+(data_utils.py:67).  `opt_mode` 'fisher_diag' / 'fisher_full' (calib_block.py:66-72) weight the loss with the cached
+output gradients of save_grad_data (data_utils.py:91-119): taken here with the engine's own backward, kept in HBM in the
+target cache's layout, applied inside the fused loss kernel (nq_block_loss_bwd_fisher).  Hadamard blocks are not
+supported (the reference's own block_reconstruction cannot run on a rotated layer: calib_block.py:125 initialises alpha
+from the unrotated weight).
 """
 from __future__ import annotations
 
@@ -60,6 +63,8 @@ class BlockStep:
         self.ws = torch.empty(int(self.wg.workspace_floats), device=dev)
         self.gw, self.gb = torch.zeros_like(stage.weight), torch.zeros_like(stage.bias)
         self.loss = torch.zeros(1, device=dev)
+        self.frame_dot = torch.zeros(n, device=dev)  # 'fisher_full': per-frame sum |d| F
+        self.opt_mode = "mse"
         self.reg = torch.zeros(1, device=dev)
         self.hyper = torch.zeros(4, device=dev)
         # the host runs ahead of the device: pinned staging ring for the per-iteration scalars (as GraphedStep)
@@ -78,7 +83,7 @@ class BlockStep:
         self.run_cached(self.x, self.tgt, None, reg_w, reg_b, p, want_reg)
 
     def run_cached(self, x_split: torch.Tensor, tgt_cache: torch.Tensor, frame_idx, reg_w: float, reg_b: float, p: float,
-                   want_reg: bool = False):
+                   want_reg: bool = False, opt_mode: str = "mse", fisher_cache: torch.Tensor = None):
         """One iteration from inputs already in the engine's layouts: x_split (2, n, h, w, cin_p) bf16 planes; tgt_cache
         (N, H, W, cg) fp32 NHWC with frame_idx (int32 device tensor of n entries) selecting the batch's frames, or a
         (n, H, W, cg) batch with frame_idx None."""
@@ -106,10 +111,24 @@ class BlockStep:
                                      L.ptr(self.bias_p), L.ptr(self.z), self.y.data_ptr(), st), "nq_tc_conv_fwd")
         # 4. loss + backward through activation / up-shuffle: mean over n*H*W of sum_c |y - tgt|^p (quantizer.py:66-73)
         self.loss.zero_()
-        L.check(L.lib.nq_block_loss_bwd(self.y.data_ptr(), L.ptr(tgt_cache), frame_idx.data_ptr() if frame_idx is not None else None,
-                                        L.ptr(self.z), self.n, self.h, self.w, g.rh, g.rw, self.cg,
-                                        float(p), 1.0 / float(self.n * self.H * self.W), L.ptr(self.loss), self.dz.data_ptr(), st),
-                "nq_block_loss_bwd")
+        self.opt_mode = opt_mode
+        fi = frame_idx.data_ptr() if frame_idx is not None else None
+        if opt_mode == "mse":
+            L.check(L.lib.nq_block_loss_bwd(self.y.data_ptr(), L.ptr(tgt_cache), fi, L.ptr(self.z), self.n, self.h, self.w, g.rh, g.rw,
+                                            self.cg, float(p), 1.0 / float(self.n * self.H * self.W), L.ptr(self.loss),
+                                            self.dz.data_ptr(), st), "nq_block_loss_bwd")
+        elif opt_mode in ("fisher_diag", "fisher_full"):
+            # calib_block.py:66-72: sum_c d^2 F^2 averaged over n*H*W, or mean over n*C*H*W of (sum |d| F) |d| F / 100
+            if fisher_cache is None or fisher_cache.shape[1:] != tgt_cache.shape[1:]:
+                raise L.NqError("Fisher block loss needs the cached output gradients in the target cache's layout")
+            diag = opt_mode == "fisher_diag"
+            scale = 1.0 / float(self.n * self.H * self.W) if diag else 1.0 / (100.0 * self.n * g.c_grp * self.H * self.W)
+            L.check(L.lib.nq_block_loss_bwd_fisher(self.y.data_ptr(), L.ptr(tgt_cache), L.ptr(fisher_cache), fi, L.ptr(self.z), self.n,
+                                                   self.h, self.w, g.rh, g.rw, self.cg, 1 if diag else 2, scale, L.ptr(self.loss),
+                                                   L.ptr(self.frame_dot), self.dz.data_ptr(), st), "nq_block_loss_bwd_fisher")
+            self.launches += 0 if diag else 2
+        else:
+            raise ValueError('Not supported reconstruction loss function: {}'.format(opt_mode))  # calib_block.py:73-74
         # 5. weight / bias gradient
         L.check(L.lib.nq_tc_conv_wgrad(C.byref(d), C.byref(self.wg), x_split.data_ptr(), self.dz.data_ptr(), None, L.ptr(self.ws),
                                        self.ws.numel(), st), "nq_tc_conv_wgrad")
@@ -137,6 +156,8 @@ class BlockStep:
         self.launches += 8
 
     def rec_loss(self) -> float:
+        if self.opt_mode == "fisher_full":
+            return float((self.frame_dot.double() ** 2).sum()) / (100.0 * self.n * self.stage.geom.c_grp * self.H * self.W)
         return float(self.loss) / float(self.n * self.H * self.W)
 
 
@@ -151,9 +172,16 @@ def cache_to_engine_layout(step: BlockStep, inps: torch.Tensor, syms, outs: torc
         L.check(L.lib.nq_nchw_to_split(L.ptr(t_.contiguous()), o.data_ptr(), N, g.cin, step.h, step.w, step.cin_p, st), "nq_nchw_to_split")
         return o
 
-    out_c = torch.zeros(N, step.H, step.W, step.cg, device=dev)
-    L.check(L.lib.nq_nchw_to_nhwc(L.ptr(outs.contiguous()), L.ptr(out_c), N, g.c_grp, step.H, step.W, step.cg, st), "nq_nchw_to_nhwc")
+    out_c = nhwc_cache(step, outs)
     return split(inps), (split(syms) if syms is not None else None), out_c
+
+
+def nhwc_cache(step: BlockStep, t_: torch.Tensor) -> torch.Tensor:
+    """(N, c_grp, H, W) fp32 -> (N, H, W, cg) fp32, pad channels zero: the layout of the target and Fisher caches."""
+    g, N = step.stage.geom, t_.shape[0]
+    o = torch.zeros(N, step.H, step.W, step.cg, device=t_.device)
+    L.check(L.lib.nq_nchw_to_nhwc(L.ptr(t_.contiguous()), L.ptr(o), N, g.c_grp, step.H, step.W, step.cg, L.stream()), "nq_nchw_to_nhwc")
+    return o
 
 
 def gather_frames(cache: torch.Tensor, idx_host, out: torch.Tensor):
@@ -186,12 +214,51 @@ def save_inp_oup_data(model, runner: DecoderRunner, k: int, cali_data: torch.Ten
     return (torch.cat(inps), torch.cat(syms)), torch.cat(outs)
 
 
+def quantize_model_till(model, layer):
+    """data_utils.py:261-272: quantise every layer / block up to and including `layer`, in module order."""
+    model.set_quant_state(False)
+    for _, module in model.named_modules():
+        if isinstance(module, (QuantModule, BaseQuantBlock)):
+            module.set_quant_state(True)
+        if module is layer:
+            break
+
+
+def block_output_grads(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor) -> torch.Tensor:
+    """GetLayerGrad (data_utils.py:222-258) over the calibration set, one sample at a time: the gradient of
+    mean((out_fp - out_q)^2) -- out_q with the decoder quantised up to and including the block -- w.r.t. the block's
+    output in the QUANTISED pass (the call the reference's backward hook keeps; pinned in tests/golden/block_*_f*.npz).
+    The engine runs the partly quantised decoder forward with out_fp as the target, back-propagates, and re-runs the
+    data gradient of stage k+1 without the activation derivative."""
+    eng = runner.engine
+    out = []
+    for i in range(cali_data.size(0)):
+        e = cali_data[i:i + 1].cuda()
+        model.set_quant_state(False)
+        runner.sync()
+        out_fp = eng.forward(e, reuse_weights=True).clone()
+        quantize_model_till(model, block)
+        runner.sync()
+        _, _, hh, ww = out_fp.shape
+        eng.forward(e, train=True, target=out_fp, p_norm=2.0, mean_pixels=float(out_fp[0].numel()), reuse_weights=True, want_img=False)
+        eng.backward()
+        out.append(eng.stage_input_grad(k + 1))
+    model.set_quant_state(False)
+    block.set_quant_state(True)
+    return torch.cat(out)
+
+
+def save_grad_data(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor) -> torch.Tensor:
+    """data_utils.py:91-119 (batch_size=1): |g| + 1, kept in HBM."""
+    return block_output_grads(model, runner, block, k, cali_data).abs() + 1.0
+
+
 def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, batch_size: int = 8, iters: int = 20000,
                          weight: float = 0.01, opt_mode: str = "mse", asym: bool = False, b_range: tuple = (20, 2),
                          warmup: float = 0.0, input_prob: float = 1.0, p: float = 2.0, lr: float = 0.0015):
     """Block-wise calibration (calib_block.py:91-183); same arguments as the reference."""
-    if opt_mode != "mse":
-        raise NotImplementedError("opt_mode 'fisher_diag' / 'fisher_full' need the cached output gradients (data_utils.py:89-116)")
+    if opt_mode not in ("mse", "fisher_diag", "fisher_full"):
+        raise ValueError('Not supported reconstruction loss function: {}'.format(opt_mode))
     if not isinstance(block, BaseQuantBlock):
         raise ValueError("block_reconstruction expects a QuantNeRVBlock of the model's decoder")
     convs = [m for m in block.modules() if isinstance(m, QuantModule)]
@@ -225,6 +292,9 @@ def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, 
     st.delta_w, st.zp_w = wq.delta.data.contiguous(), wq.zero_point.contiguous()
     st.delta_b, st.zp_b = bq.delta.data.contiguous(), bq.zero_point.contiguous()
     st.alpha_w, st.alpha_b = wq.alpha.data, bq.alpha.data
+    runner._key = None
+    # calib_block.py:154-157: the output gradients are taken AFTER the block's quantisers were swapped (AdaRound, soft)
+    cached_grads = save_grad_data(model, runner, block, k, cali_data) if opt_mode != "mse" else None
     n_cached = cached_inps.size(0)
     bsz = min(batch_size, n_cached)
     step = BlockStep(st, bsz, cached_inps.shape[2], cached_inps.shape[3], lr)
@@ -234,6 +304,7 @@ def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, 
     # the caches go into the engine's own layouts ONCE (split-bf16 NHWC inputs, fp32 NHWC targets): an iteration then
     # only gathers its frames (contiguous per frame) and never transposes
     inp_s, sym_s, out_c = cache_to_engine_layout(step, cached_inps, cached_sym if input_prob < 1.0 else None, cached_outs)
+    grad_c = nhwc_cache(step, cached_grads) if cached_grads is not None else None
     cur = torch.empty_like(inp_s[:, :bsz])
     alt = torch.empty_like(cur) if input_prob < 1.0 else None
     for i in range(iters):
@@ -249,7 +320,7 @@ def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, 
         reg_on = not (count < loss_start)
         want_log = count % 500 == 0
         step.run_cached(cur, out_c, idx.int(), weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
-                        want_reg=want_log and reg_on)
+                        want_reg=want_log and reg_on, opt_mode=opt_mode, fisher_cache=grad_c)
         if want_log:  # calib_block.py:85-87
             rec = step.rec_loss()
             rnd = float(step.reg) * weight if reg_on else 0.0

@@ -118,10 +118,8 @@ class DecoderRunner:
 
         eng = self.engine
         on = [q and l.use_weight_quant for l, q in zip(self.layers, self._quant)]
-        if any(on) and not all(on):
-            raise NotImplementedError("mixed quantised / full-precision layers in one decoder pass")
-        key = [all(on)]
-        if not all(on):
+        key = [tuple(on)]
+        if not any(on):
             eng.mode = "off"
             for l, st in zip(self.layers, eng.stages):
                 src = l.org_weight if hasattr(l, "org_weight") else l.weight.data
@@ -129,20 +127,28 @@ class DecoderRunner:
                 st.weight, st.bias = src, srb
                 key += [src.data_ptr(), src._version, srb.data_ptr(), srb._version]
         else:
-            ada = [isinstance(l.weight_quantizer, AdaRoundQuantizer) for l in self.layers]
+            ada = [o and isinstance(l.weight_quantizer, AdaRoundQuantizer) for l, o in zip(self.layers, on)]
             eng.mode = "ada" if all(ada) else "uaq"
             eng.stage_state = None
             if all(ada):
                 eng.soft_w = bool(self.layers[0].weight_quantizer.soft_targets)
                 eng.soft_b = bool(self.layers[0].bias_quantizer.soft_targets)
-            if any(ada):
+            if any(ada) or not all(on):
                 # per-stage rounding state: layers calibrated block by block carry AdaRound quantisers next to plain ones,
-                # and the block-wise variant leaves both quantisers of a block hard (calib_block.py:180-183)
-                eng.stage_state = [("ada", bool(l.weight_quantizer.soft_targets), bool(l.bias_quantizer.soft_targets)) if a
-                                   else ("uaq", False, False) for l, a in zip(self.layers, ada)]
+                # the block-wise variant leaves both quantisers of a block hard (calib_block.py:180-183), and
+                # quantize_model_till (data_utils.py:261-272) quantises a prefix of the decoder only
+                eng.stage_state = [("off", False, False) if not o else
+                                   ("ada", bool(l.weight_quantizer.soft_targets), bool(l.bias_quantizer.soft_targets)) if a
+                                   else ("uaq", False, False) for l, a, o in zip(self.layers, ada, on)]
                 if all(ada) and len(set(eng.stage_state)) == 1:
                     eng.stage_state = None
-            for l, st in zip(self.layers, eng.stages):
+            for l, st, o in zip(self.layers, eng.stages, on):
+                if not o:  # full-precision stage inside a partly quantised decoder
+                    src = l.org_weight if hasattr(l, "org_weight") else l.weight.data
+                    srb = l.org_bias if hasattr(l, "org_bias") else l.bias.data
+                    st.weight, st.bias = src, srb
+                    key += [src.data_ptr(), src._version, srb.data_ptr(), srb._version]
+                    continue
                 wq, bq = l.weight_quantizer, l.bias_quantizer
                 st.weight, st.bias = l.weight.data, l.bias.data
                 if not st.hadamard:

@@ -447,11 +447,50 @@ def block_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, asym: bool, cache_
     return torch.cat(inps), torch.cat(syms), torch.cat(outs)
 
 
+def block_grad_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, branch: str = "q", raw: bool = False):
+    """save_grad_data(model, block, cali_data, batch_size=1) (data_utils.py:91-119) with GetLayerGrad (:222-258): per
+    sample, loss = mean((out_fp - out_q)^2) where out_q has stages 0..k quantised in their current state
+    (quantize_model_till, :261-272) and the rest full precision; the hook on the block keeps the gradient w.r.t. the
+    block's output; the cache is |g| + 1.  The block is traversed by BOTH passes; the (non-full) backward hook keeps
+    the gradient of the QUANTISED pass (`branch` 'q'; pinned bit-exactly against the reference's raw gradients in
+    tests/golden/block_tiny_hnerv_f*.npz -- 'fp' is off by a factor of -1 and the activations' difference).  For any
+    frame of more than a few thousand values |g| < 6e-8 and the cache is exactly 1.0 in fp32."""
+    outs = []
+    for i in range(cali.size(0)):
+        e = cali[i:i + 1]
+        ws, bs = [], []
+        for j, q in enumerate(qd.q):
+            if j < k:
+                w, b = qd.quantised_params(q)  # predecessors: whatever state they are in
+            elif j == k:  # the block itself: AdaRound, soft (calib_block.py:123-130 ran before save_grad_data)
+                _, w = adaround_quant(q.stage.weight, q.alpha_w, q.delta_w, q.zp_w, q.n_bits, True)
+                _, b = adaround_quant(q.stage.bias, q.alpha_b, q.delta_b, q.zp_b, q.n_bits, True)
+            else:
+                w, b = q.stage.weight, q.stage.bias
+            ws.append(w.detach()); bs.append(b.detach())
+        x_fp, x_q = e, e
+        y_fp = y_q = None
+        for j, st in enumerate(qd.stages):
+            x_fp = apply_act(up_shuffle(F.conv2d(x_fp, st.weight, st.bias, stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
+            x_q = apply_act(up_shuffle(F.conv2d(x_q, ws[j], bs[j], stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
+            if j == k:
+                x_fp = x_fp.detach().requires_grad_(True)
+                x_q = x_q.detach().requires_grad_(True)
+                y_fp, y_q = x_fp, x_q
+        loss = F.mse_loss(x_fp, x_q, reduction="none").flatten(1).mean(1)
+        g_fp, g_q = torch.autograd.grad(loss.sum(), [y_fp, y_q])
+        outs.append(g_fp if branch == "fp" else g_q)
+    g = torch.cat(outs)
+    return g if raw else g.abs() + 1.0
+
+
 def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: Sequence[Sequence[int]], iters: int,
                          weight: float = 0.01, asym: bool = False, b_range=(20, 2), warmup: float = 0.0,
                          input_prob: float = 1.0, p: float = 2.0, lr: float = 0.0015,
-                         masks: Optional[Sequence[torch.Tensor]] = None, log: Optional[list] = None):
-    """calib_block.py:91-183, opt_mode 'mse', for the block that is decoder stage k, with the reference's random draws
+                         masks: Optional[Sequence[torch.Tensor]] = None, log: Optional[list] = None,
+                         opt_mode: str = "mse", grads_out: Optional[list] = None):
+    """calib_block.py:91-183 for the block that is decoder stage k (opt_mode 'mse' | 'fisher_diag' | 'fisher_full',
+    calib_block.py:62-72 with the output-gradient cache of data_utils.py:91-119), with the reference's random draws
     injected: idx_seq[i] = torch.randperm(N)[:batch_size] of iteration i, masks[i] = its torch.rand_like (QDrop).
     Only this stage's quantisers become AdaRound (fp16-rounded scales, quantizer.py:264-265); both its weight and bias
     quantisers end hard-rounded (calib_block.py:180-183, unlike the network-wise variant)."""
@@ -470,6 +509,9 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
     # the cache is taken AFTER the block's quantisers were swapped (calib_block.py:151), but predecessors only matter
     q.alpha_w, q.alpha_b = alpha_w.detach(), alpha_b.detach()
     inp, sym, out_fp = block_cache(qd, k, cali, asym)
+    grads = block_grad_cache(qd, k, cali) if opt_mode != "mse" else None
+    if grads_out is not None:
+        grads_out.append(grads)
     for it in range(iters):
         idx = torch.as_tensor(idx_seq[it])
         cur_inp, cur_sym, cur_out = inp[idx], sym[idx], out_fp[idx]
@@ -480,7 +522,15 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
         _, bq = adaround_quant(st.bias, alpha_b, q.delta_b, q.zp_b, q.n_bits, True)
         y = apply_act(up_shuffle(F.conv2d(cur_inp, wq, bq, stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
         count = it + 1
-        rec = lp_loss(y, cur_out, p=p)
+        if opt_mode == "mse":
+            rec = lp_loss(y, cur_out, p=p)
+        elif opt_mode == "fisher_diag":  # calib_block.py:66-67
+            rec = ((y - cur_out).pow(2) * grads[idx].pow(2)).sum(1).mean()
+        elif opt_mode == "fisher_full":  # calib_block.py:68-72
+            a, gr = (y - cur_out).abs(), grads[idx].abs()
+            rec = (torch.sum(a * gr, (1, 2, 3)).view(-1, 1, 1, 1) * a * gr).mean() / 100
+        else:
+            raise ValueError(opt_mode)
         b = decay(count)
         if count < loss_start:
             b, rnd = 0, torch.zeros(())

@@ -26,7 +26,7 @@ from make_golden import TINY_HNERV, TINY_NERV, npy  # noqa: E402
 torch.set_num_threads(8)
 
 
-def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters=60, n_frames=20, bsz=2):
+def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters=60, n_frames=20, bsz=2, opt_mode="mse"):
     torch.manual_seed(903)
     model = (models.HNeRV if arch == "hnerv" else models.NeRV)(cfg)
     with torch.no_grad():
@@ -54,6 +54,20 @@ def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, 
 
     idx_log, mask_log, traj, cache = [], [], [], {}
     _randperm, _rand_like, _call, _save = torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data
+    _save_grad = cb.save_grad_data
+    import quantization.data_utils as du
+    _get_grad = du.GetLayerGrad.__call__
+    raw = []
+
+    def get_grad(self, x):
+        r = _get_grad(self, x)
+        raw.append(r.detach().cpu().clone())  # before |g| + 1 swallows it (data_utils.py:113)
+        return r
+
+    def save_grad(*a, **k):
+        r = _save_grad(*a, **k)
+        cache["grad"] = r.detach().cpu().clone()
+        return r
 
     def randperm(n, *a, **k):
         r = _randperm(n, *a, **k)
@@ -66,8 +80,13 @@ def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, 
         return r
 
     def rec_call(self, pred, tgt, grad=None):
+        saved = (self.count, self.round)
+        self.round = "none"  # the reference's own reconstruction term alone (total = 0 + rec_loss, calib_block.py:75-85)
+        with torch.no_grad():
+            rec = float(_call(self, pred, tgt, grad))
+        self.count, self.round = saved
         tot = _call(self, pred, tgt, grad)
-        traj.append((self.count, float(tot), float(cb.lp_loss(pred, tgt, p=self.p)), float(self.round_loss)))
+        traj.append((self.count, float(tot), rec, float(self.round_loss)))
         return tot
 
     def save(*a, **k):
@@ -78,12 +97,21 @@ def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, 
     import logging
     logging.getLogger().setLevel(logging.WARNING)
     torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data = randperm, rand_like, rec_call, save
+    cb.save_grad_data = save_grad
+    du.GetLayerGrad.__call__ = get_grad
     try:
         torch.manual_seed(5)
-        cb.block_reconstruction(qnn, block, cali, batch_size=bsz, iters=iters, weight=0.01, opt_mode="mse", asym=asym,
+        cb.block_reconstruction(qnn, block, cali, batch_size=bsz, iters=iters, weight=0.01, opt_mode=opt_mode, asym=asym,
                                 b_range=(20, 2), warmup=0.2, input_prob=input_prob, p=2.0, lr=0.003)
     finally:
         torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data = _randperm, _rand_like, _call, _save
+        cb.save_grad_data = _save_grad
+        du.GetLayerGrad.__call__ = _get_grad
+    out["opt_mode"] = np.array(opt_mode)
+    if "grad" in cache:
+        # |g| + 1 in fp32 keeps ~3 digits of g; store the cache as the reference holds it
+        out["cache_grad"] = npy(cache["grad"])
+        out["raw_grad"] = npy(torch.cat(raw))
     out["idx"] = np.stack([npy(i) for i in idx_log])
     if mask_log:
         out["masks"] = np.stack([npy(m) for m in mask_log]).astype(np.float32)
@@ -104,8 +132,15 @@ def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, 
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:
+        _all = run_block_case
+        run_block_case = lambda tag, *a, **k: _all(tag, *a, **k) if tag in only else None  # noqa: E731
     run_block_case("block_tiny_hnerv", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 3, False, 1.0)
     run_block_case("block_tiny_hnerv_qdrop", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 2, True, 0.5)
     # (hadamard=True cannot run in the reference: calib_block.py:125 builds alpha from the UNROTATED org_weight while the
     #  forward quantises the rotated, channel-padded copy -- shape mismatch at quantizer.py:291)
     run_block_case("block_tiny_nerv", "nerv", TINY_NERV, [5, 6, 3, 4, 5, 4, 3], False, 2, False, 1.0)
+    # coarse predecessors so that the output gradients reach the resolution of fp32 (|g| + 1): at 5-6 bits the cache is 1.0
+    run_block_case("block_tiny_hnerv_fdiag", "hnerv", TINY_HNERV, [2, 2, 2, 3, 5, 6, 6], False, 3, False, 1.0, opt_mode="fisher_diag")
+    run_block_case("block_tiny_hnerv_ffull", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 2, True, 0.5, opt_mode="fisher_full")

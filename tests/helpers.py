@@ -31,6 +31,8 @@ BLOCK_CASES = {
     "block_tiny_hnerv": ("hnerv", TINY_HNERV),
     "block_tiny_hnerv_qdrop": ("hnerv", TINY_HNERV),
     "block_tiny_nerv": ("nerv", TINY_NERV),
+    "block_tiny_hnerv_fdiag": ("hnerv", TINY_HNERV),   # opt_mode 'fisher_diag'
+    "block_tiny_hnerv_ffull": ("hnerv", TINY_HNERV),   # opt_mode 'fisher_full', asym, QDrop 0.5
 }
 
 

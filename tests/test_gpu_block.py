@@ -58,6 +58,11 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
 
     caches = {}
     _save = cb.save_inp_oup_data
+    _grads = cb.block_output_grads
+
+    def grads(*a, **k):
+        caches["raw_grad"] = _grads(*a, **k)
+        return caches["raw_grad"]
 
     def save(*a, **k):
         r = _save(*a, **k)
@@ -74,9 +79,10 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
     monkeypatch.setattr(torch, "randperm", randperm)
     monkeypatch.setattr(torch, "rand_like", rand_like)
     monkeypatch.setattr(cb, "save_inp_oup_data", save)
+    monkeypatch.setattr(cb, "block_output_grads", grads)
     monkeypatch.setattr(cb.BlockStep, "run_cached", run)
     block_reconstruction(qnn, block, t(g["cali"]).cuda(), batch_size=int(g["bsz"]), iters=int(g["iters"]), weight=0.01,
-                         opt_mode="mse", asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2, input_prob=float(g["input_prob"]),
+                         opt_mode=str(g["opt_mode"]) if "opt_mode" in g.files else "mse", asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2, input_prob=float(g["input_prob"]),
                          p=2.0, lr=0.003)
     monkeypatch.undo()
     assert calls["perm"] == int(g["iters"]) and calls["rand"] == len(masks)
@@ -84,6 +90,15 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
     for name in ("inp", "sym", "out"):
         ref = g["cache_" + name]
         assert np.abs(caches[name].cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
+    if "raw_grad" in g.files:
+        # Fisher modes: the cached output gradients (GetLayerGrad), raw -- |g| + 1 is 1.0 in fp32 at these magnitudes
+        ref = g["raw_grad"]
+        got = caches["raw_grad"].cpu().numpy()
+        assert got.shape == ref.shape
+        # g is the back-propagated DIFFERENCE of two nearly equal frames (out_q - out_fp ~ 1e-4 at 5-6 bits): fp32
+        # cancellation leaves about three digits in either implementation
+        assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max(), (np.abs(got - ref).max(), np.abs(ref).max())
+        assert np.array_equal(np.abs(got) + np.float32(1.0), g["cache_grad"])
     # loss trajectory of the block output
     assert np.allclose(np.array(traj), g["traj"][:, 2], rtol=5e-3, atol=1e-9)
     wq, bq = conv.weight_quantizer, conv.bias_quantizer
@@ -106,3 +121,48 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
     qnn.set_quant_state(True)
     out, _, _ = qnn(t(g["cali"])[:2].cuda())
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("mode", ["fisher_diag", "fisher_full"])
+@pytest.mark.parametrize("conv", ["tc"])
+def test_fisher_block_step_against_autograd(mode, conv):
+    """One block iteration with a NON-trivial Fisher cache (the reference's own is 1.0 everywhere): loss and weight /
+    bias gradients of calib_block.py:66-72 against PyTorch autograd of the oracle's soft fake-quant."""
+    import torch.nn.functional as F
+    import neuroquant_b200 as nq
+    from neuroquant_b200.quantization.calib_block import BlockStep, nhwc_cache
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator().manual_seed(5)
+    g = nq.StageGeom(14, 12 * 4, 3, 2, 2, "gelu")
+    wt = (torch.randn(g.cout, g.cin, 3, 3, generator=gen) * 0.1).cuda()
+    bs = (torch.randn(g.cout, generator=gen) * 0.05).cuda()
+    st = nq.QuantStage(g, wt, bs, 5, False)
+    st.init_scales()
+    st.start_adaround()
+    n, h, w = 3, 9, 20
+    x = torch.randn(n, g.cin, h, w, generator=gen).cuda()
+    n_cache = 5
+    tgt = (torch.randn(n_cache, g.c_grp, h * 2, w * 2, generator=gen) * 0.3).cuda()
+    fis = (1.0 + torch.rand(n_cache, g.c_grp, h * 2, w * 2, generator=gen)).cuda()
+    idx = torch.tensor([4, 0, 2], dtype=torch.int32).cuda()
+    _, wq = O.adaround_quant(wt, st.alpha_w, st.delta_w, st.zp_w, st.n_bits, True)
+    _, bq = O.adaround_quant(bs, st.alpha_b, st.delta_b, st.zp_b, st.n_bits, True)
+    wq, bq = wq.detach().requires_grad_(True), bq.detach().requires_grad_(True)
+    y = F.gelu(F.pixel_shuffle(F.conv2d(x, wq, bq, padding=1), 2))
+    cur_t, cur_f = tgt[idx.long()], fis[idx.long()]
+    if mode == "fisher_diag":
+        loss = ((y - cur_t).pow(2) * cur_f.pow(2)).sum(1).mean()
+    else:
+        a = (y - cur_t).abs()
+        loss = (torch.sum(a * cur_f, (1, 2, 3)).view(-1, 1, 1, 1) * a * cur_f).mean() / 100
+    loss.backward()
+    step = BlockStep(st, n, h, w, lr=1e-3)
+    step.run(x, tgt[:n], 0.0, 0.0, 2.0)  # fills step.x with the split-bf16 input (and runs one plain iteration)
+    st.start_adaround()
+    step2 = BlockStep(st, n, h, w, lr=1e-3)
+    step2.run_cached(step.x, nhwc_cache(step2, tgt), idx, 0.0, 0.0, 2.0, opt_mode=mode, fisher_cache=nhwc_cache(step2, fis))
+    assert step2.rec_loss() == pytest.approx(float(loss), rel=3e-5)
+    for name, a_, b_ in (("dW", step2.gw, wq.grad), ("db", step2.gb, bq.grad)):
+        tol = 2e-4 * float(b_.abs().max()) + 1e-12
+        assert float((a_ - b_).abs().max()) <= tol, (name, float((a_ - b_).abs().max()), tol)

@@ -177,7 +177,16 @@ def test_block_reconstruction_oracle_matches_reference(tag):
     masks = [t(m) for m in g["masks"]] if "masks" in g.files else None
     inp, sym, out = O.block_reconstruction(qd, k, t(g["cali"]), g["idx"].tolist(), int(g["iters"]), weight=0.01,
                                            asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2,
-                                           input_prob=float(g["input_prob"]), p=2.0, lr=0.003, masks=masks, log=log)
+                                           input_prob=float(g["input_prob"]), p=2.0, lr=0.003, masks=masks, log=log,
+                                           opt_mode=str(g["opt_mode"]) if "opt_mode" in g.files else "mse")
+    if "cache_grad" in g.files:  # Fisher modes: the cached output gradients, as the reference holds them (|g| + 1) and raw
+        q = qd.q[k]
+        a_w, a_b = q.alpha_w, q.alpha_b
+        q.alpha_w, q.alpha_b = O.adaround_init_alpha(q.stage.weight, q.delta_w), O.adaround_init_alpha(q.stage.bias, q.delta_b)
+        raw = O.block_grad_cache(qd, k, t(g["cali"]), raw=True).numpy()
+        q.alpha_w, q.alpha_b = a_w, a_b
+        assert np.abs(raw - g["raw_grad"]).max() <= 1e-3 * np.abs(g["raw_grad"]).max()
+        assert np.array_equal(np.abs(raw) + np.float32(1.0), g["cache_grad"])
     assert np.abs(inp.numpy() - g["cache_inp"]).max() < 1e-5
     assert np.abs(sym.numpy() - g["cache_sym"]).max() < 1e-5
     assert np.abs(out.numpy() - g["cache_out"]).max() < 1e-5
