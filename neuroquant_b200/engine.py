@@ -719,6 +719,21 @@ class DecoderEngine:
         out = out.view(n, h, w, g_prev.rh, g_prev.rw, cg).permute(0, 5, 1, 3, 2, 4)
         return out.reshape(n, cg, h * g_prev.rh, w * g_prev.rw)[:, :g_prev.c_grp].contiguous()
 
+    def stage_output_grad(self, i: int) -> torch.Tensor:
+        """dL/d(convolution output of stage i), before its up-shuffle and activation, of the last forward(train=True,
+        target=...) + backward(): the engine's own dz[i], returned as (n, C_out, h, w) fp32 in the reference's channel
+        order (the engine's GEMM columns are sub-pixel major: column = s * cg + c, reference channel = c * rh*rw + s)."""
+        p = self._last_plan
+        assert p.train and hasattr(p, "dwk")
+        g = self.geoms[i]
+        dz = p.dz[i]
+        dz = dz[0].float() + dz[1].float() if self.use_tc else dz
+        n, h, w, ncol = dz.shape
+        r2 = g.rh * g.rw
+        cg = ncol // r2
+        out = dz[..., :r2 * cg].view(n, h, w, r2, cg)[..., :g.c_grp].permute(0, 4, 3, 1, 2)
+        return out.reshape(n, g.c_grp * r2, h, w).contiguous()
+
     def param_grads(self, grad_scale: float = 1.0, reg_w: float = 0.0, reg_b: float = 0.0, hyper: Optional[torch.Tensor] = None):
         """Chain the (possibly all-reduced) weight gradients through the rotation and the quantiser
         Jacobian.  Returns per stage (g_w, g_b): d_alpha (mode 'ada', soft) or d_delta (mode 'uaq').

@@ -3,5 +3,4 @@ from .quant_layer import QuantModule  # noqa: F401
 from .quant_model import QuantModel  # noqa: F401
 from .calib_model import model_reconstruction  # noqa: F401
 from .calib_block import block_reconstruction  # noqa: F401
-# layer_reconstruction (reference calib_layer.py) is imported by the reference package but called by no command line and
-# crashes there (calib_layer.py:130); it is not provided.
+from .calib_layer import layer_reconstruction  # noqa: F401  (the reference's, repaired: see calib_layer.py)

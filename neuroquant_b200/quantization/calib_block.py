@@ -17,6 +17,7 @@ from the unrotated weight).
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 import logging
 
@@ -25,7 +26,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from ..calibration import LinearTempDecay
-from ..engine import AdamState, ROUND_SOFT, _ACT, _ACT_SAVED_GRAD, _pad
+from ..engine import AdamState, ROUND_SOFT, StageGeom, _ACT, _ACT_SAVED_GRAD, _pad
 from ..runner import DecoderRunner
 from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule
@@ -197,16 +198,22 @@ def _features(runner: DecoderRunner, model, embed: torch.Tensor, weight_quant: b
     return runner.features(embed)
 
 
-def save_inp_oup_data(model, runner: DecoderRunner, k: int, cali_data: torch.Tensor, asym: bool, batch_size: int = 10):
+def save_inp_oup_data(model, runner: DecoderRunner, k: int, cali_data: torch.Tensor, asym: bool, batch_size: int = 10,
+                      layer=None):
     """data_utils.py:45-86 with input_prob=True: (block input the optimisation sees, full-precision block input,
-    full-precision block output) over the calibration set, kept in HBM."""
+    full-precision block output) over the calibration set, kept in HBM.  `layer` (a QuantModule): the hooked module is
+    the convolution alone -- its output is taken before the up-shuffle and the activation (layer_reconstruction)."""
     inps, syms, outs = [], [], []
     for i in range(int(cali_data.size(0) / batch_size)):
         e = cali_data[i * batch_size:(i + 1) * batch_size].cuda()
         feats = _features(runner, model, e, False)
-        syms.append(feats[k - 1].clone())
-        outs.append(feats[k].clone())
-        if asym:  # input recomputed with the whole network quantised (data_utils.py:172-180)
+        syms.append(feats[k - 1].clone() if k > 0 else e.float().clone())
+        if layer is not None:
+            with torch.no_grad():
+                outs.append(layer(syms[-1]))  # quant state is off: the module's own full-precision convolution
+        else:
+            outs.append(feats[k].clone())
+        if asym and k > 0:  # input recomputed with the whole network quantised (data_utils.py:172-180)
             inps.append(_features(runner, model, e, True)[k - 1].clone())
         else:
             inps.append(syms[-1])
@@ -224,7 +231,7 @@ def quantize_model_till(model, layer):
             break
 
 
-def block_output_grads(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor) -> torch.Tensor:
+def block_output_grads(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor, layer: bool = False) -> torch.Tensor:
     """GetLayerGrad (data_utils.py:222-258) over the calibration set, one sample at a time: the gradient of
     mean((out_fp - out_q)^2) -- out_q with the decoder quantised up to and including the block -- w.r.t. the block's
     output in the QUANTISED pass (the call the reference's backward hook keeps; pinned in tests/golden/block_*_f*.npz).
@@ -242,41 +249,48 @@ def block_output_grads(model, runner: DecoderRunner, block, k: int, cali_data: t
         _, _, hh, ww = out_fp.shape
         eng.forward(e, train=True, target=out_fp, p_norm=2.0, mean_pixels=float(out_fp[0].numel()), reuse_weights=True, want_img=False)
         eng.backward()
-        out.append(eng.stage_input_grad(k + 1))
+        out.append(eng.stage_output_grad(k) if layer else eng.stage_input_grad(k + 1))
     model.set_quant_state(False)
     block.set_quant_state(True)
     return torch.cat(out)
 
 
-def save_grad_data(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor) -> torch.Tensor:
+def save_grad_data(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor, layer: bool = False) -> torch.Tensor:
     """data_utils.py:91-119 (batch_size=1): |g| + 1, kept in HBM."""
-    return block_output_grads(model, runner, block, k, cali_data).abs() + 1.0
+    return block_output_grads(model, runner, block, k, cali_data, layer).abs() + 1.0
 
 
 def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, batch_size: int = 8, iters: int = 20000,
                          weight: float = 0.01, opt_mode: str = "mse", asym: bool = False, b_range: tuple = (20, 2),
                          warmup: float = 0.0, input_prob: float = 1.0, p: float = 2.0, lr: float = 0.0015):
     """Block-wise calibration (calib_block.py:91-183); same arguments as the reference."""
-    if opt_mode not in ("mse", "fisher_diag", "fisher_full"):
-        raise ValueError('Not supported reconstruction loss function: {}'.format(opt_mode))
     if not isinstance(block, BaseQuantBlock):
         raise ValueError("block_reconstruction expects a QuantNeRVBlock of the model's decoder")
     convs = [m for m in block.modules() if isinstance(m, QuantModule)]
     if len(convs) != 1:
         raise NotImplementedError("blocks with other than one quantised convolution")
-    conv = convs[0]
+    return _reconstruct(model, block, convs[0], False, cali_data, batch_size, iters, weight, opt_mode, asym, b_range, warmup,
+                        input_prob, p, lr)
+
+
+def _reconstruct(model, block, conv, layer_mode: bool, cali_data, batch_size, iters, weight, opt_mode, asym, b_range, warmup,
+                 input_prob, p, lr):
+    """Shared body of block_reconstruction and layer_reconstruction (calib_layer.py:89-179 is calib_block.py:91-183 on a
+    lone QuantModule): layer_mode compares the convolution's own output and never applies the rounding regulariser."""
+    if opt_mode not in ("mse", "fisher_diag", "fisher_full"):
+        raise ValueError('Not supported reconstruction loss function: {}'.format(opt_mode))
     if conv.hadamard:
         raise NotImplementedError("block_reconstruction on a rotated layer (the reference cannot run it either: calib_block.py:125)")
     runner = DecoderRunner.of(model.model)
     k = [i for i, l in enumerate(runner.layers) if l is conv]
-    if not k or k[0] == 0 or k[0] == len(runner.layers) - 1:
+    if not k or (not layer_mode and (k[0] == 0 or k[0] == len(runner.layers) - 1)):
         raise ValueError("block is not one of this model's decoder blocks")
     k = k[0]
     # the caches depend on the predecessors only; take them before this block's quantisers are swapped
     model.eval()
     model.set_quant_state(True)
     runner.sync()  # initialises step sizes that no forward has initialised yet
-    (cached_inps, cached_sym), cached_outs = save_inp_oup_data(model, runner, k, cali_data, asym)
+    (cached_inps, cached_sym), cached_outs = save_inp_oup_data(model, runner, k, cali_data, asym, layer=conv if layer_mode else None)
     model.set_quant_state(False)
     block.set_quant_state(True)
     round_mode = "learned_hard_sigmoid"
@@ -294,9 +308,13 @@ def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, 
     st.alpha_w, st.alpha_b = wq.alpha.data, bq.alpha.data
     runner._key = None
     # calib_block.py:154-157: the output gradients are taken AFTER the block's quantisers were swapped (AdaRound, soft)
-    cached_grads = save_grad_data(model, runner, block, k, cali_data) if opt_mode != "mse" else None
+    cached_grads = save_grad_data(model, runner, block, k, cali_data, layer_mode) if opt_mode != "mse" else None
     n_cached = cached_inps.size(0)
     bsz = min(batch_size, n_cached)
+    if layer_mode:
+        # the layer alone: same quantiser state, but the compared output is the convolution's (no up-shuffle, no activation)
+        st = copy.copy(st)
+        st.geom = StageGeom(st.geom.cin, st.geom.cout, st.geom.k, 1, 1, "none")
     step = BlockStep(st, bsz, cached_inps.shape[2], cached_inps.shape[3], lr)
     decay = LinearTempDecay(iters, rel_start_decay=warmup + (1 - warmup) * 0.0, start_b=b_range[0], end_b=b_range[1])
     loss_start = iters * warmup
@@ -317,7 +335,9 @@ def block_reconstruction(model, block: BaseQuantBlock, cali_data: torch.Tensor, 
             torch.where(keep.unsqueeze(0), cur, alt, out=cur)
         count = i + 1
         b = decay(count)
-        reg_on = not (count < loss_start)
+        # calib_layer.py:38-46: collect_round_loss walks the CHILDREN of the module it is given; a lone QuantModule has
+        # none that is a QuantModule, so the layer-wise variant never sees the regulariser
+        reg_on = not (count < loss_start) and not layer_mode
         want_log = count % 500 == 0
         step.run_cached(cur, out_c, idx.int(), weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
                         want_reg=want_log and reg_on, opt_mode=opt_mode, fisher_cache=grad_c)

@@ -419,7 +419,7 @@ def model_reconstruction(qd: QuantDecoder, cali: torch.Tensor, frames: torch.Ten
 # --------------------------------------------------------------------------------------------
 # Block-wise reconstruction (calib_block.py:91-183, data_utils.py:45-86,146-196)
 # --------------------------------------------------------------------------------------------
-def block_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, asym: bool, cache_bs: int = 10):
+def block_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, asym: bool, cache_bs: int = 10, layer: bool = False):
     """save_inp_oup_data(model, block, cali_data, asym, batch_size=10, input_prob=True) for the block that is stage k:
     (input the optimisation sees, full-precision input, full-precision output) over the calibration set; the last
     cali.size(0) % 10 samples are dropped as in data_utils.py:67.  With asym the input comes from a pass with EVERY
@@ -434,7 +434,12 @@ def block_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, asym: bool, cache_
             _, feats = decode(qd.stages, e, keep=True)
         x_fp = e if k == 0 else feats[k - 1]
         syms.append(x_fp)
-        outs.append(feats[k])
+        if layer:  # hook on the QuantModule itself (layer_reconstruction): the convolution's own output
+            st = qd.stages[k]
+            with torch.no_grad():
+                outs.append(F.conv2d(x_fp, st.weight, st.bias, stride=1, padding=st.k // 2))
+        else:
+            outs.append(feats[k])
         if asym:
             qd.mode = mode
             with torch.no_grad():
@@ -447,7 +452,7 @@ def block_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, asym: bool, cache_
     return torch.cat(inps), torch.cat(syms), torch.cat(outs)
 
 
-def block_grad_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, branch: str = "q", raw: bool = False):
+def block_grad_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, branch: str = "q", raw: bool = False, layer: bool = False):
     """save_grad_data(model, block, cali_data, batch_size=1) (data_utils.py:91-119) with GetLayerGrad (:222-258): per
     sample, loss = mean((out_fp - out_q)^2) where out_q has stages 0..k quantised in their current state
     (quantize_model_till, :261-272) and the rest full precision; the hook on the block keeps the gradient w.r.t. the
@@ -471,9 +476,14 @@ def block_grad_cache(qd: QuantDecoder, k: int, cali: torch.Tensor, branch: str =
         x_fp, x_q = e, e
         y_fp = y_q = None
         for j, st in enumerate(qd.stages):
-            x_fp = apply_act(up_shuffle(F.conv2d(x_fp, st.weight, st.bias, stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
-            x_q = apply_act(up_shuffle(F.conv2d(x_q, ws[j], bs[j], stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
-            if j == k:
+            x_fp = F.conv2d(x_fp, st.weight, st.bias, stride=1, padding=st.k // 2)
+            x_q = F.conv2d(x_q, ws[j], bs[j], stride=1, padding=st.k // 2)
+            if j == k and layer:  # `layer`: the hooked module is the convolution alone
+                x_fp, x_q = x_fp.detach().requires_grad_(True), x_q.detach().requires_grad_(True)
+                y_fp, y_q = x_fp, x_q
+            x_fp = apply_act(up_shuffle(x_fp, st.rh, st.rw), st.act)
+            x_q = apply_act(up_shuffle(x_q, st.rh, st.rw), st.act)
+            if j == k and not layer:
                 x_fp = x_fp.detach().requires_grad_(True)
                 x_q = x_q.detach().requires_grad_(True)
                 y_fp, y_q = x_fp, x_q
@@ -488,12 +498,18 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
                          weight: float = 0.01, asym: bool = False, b_range=(20, 2), warmup: float = 0.0,
                          input_prob: float = 1.0, p: float = 2.0, lr: float = 0.0015,
                          masks: Optional[Sequence[torch.Tensor]] = None, log: Optional[list] = None,
-                         opt_mode: str = "mse", grads_out: Optional[list] = None):
+                         opt_mode: str = "mse", grads_out: Optional[list] = None, layer: bool = False):
     """calib_block.py:91-183 for the block that is decoder stage k (opt_mode 'mse' | 'fisher_diag' | 'fisher_full',
     calib_block.py:62-72 with the output-gradient cache of data_utils.py:91-119), with the reference's random draws
     injected: idx_seq[i] = torch.randperm(N)[:batch_size] of iteration i, masks[i] = its torch.rand_like (QDrop).
     Only this stage's quantisers become AdaRound (fp16-rounded scales, quantizer.py:264-265); both its weight and bias
-    quantisers end hard-rounded (calib_block.py:180-183, unlike the network-wise variant)."""
+    quantisers end hard-rounded (calib_block.py:180-183, unlike the network-wise variant).
+
+    layer=True: layer_reconstruction (calib_layer.py:89-179) REPAIRED -- as shipped it stops at :130 (`opt_params +=`
+    before any assignment); with `opt_params = []` it is this function on the convolution alone: the cached / compared
+    output is the conv's own (before up-shuffle and activation), and the rounding regulariser is never applied, because
+    LossFunction.collect_round_loss (calib_layer.py:38-46) walks the CHILDREN of the given module and a QuantModule's
+    children are its two quantisers, not a QuantModule."""
     q = qd.q[k]
     if q.hadamard:
         raise NotImplementedError("the reference's block_reconstruction cannot run with hadamard=True (calib_block.py:125)")
@@ -508,8 +524,8 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
     loss_start = iters * warmup
     # the cache is taken AFTER the block's quantisers were swapped (calib_block.py:151), but predecessors only matter
     q.alpha_w, q.alpha_b = alpha_w.detach(), alpha_b.detach()
-    inp, sym, out_fp = block_cache(qd, k, cali, asym)
-    grads = block_grad_cache(qd, k, cali) if opt_mode != "mse" else None
+    inp, sym, out_fp = block_cache(qd, k, cali, asym, layer=layer)
+    grads = block_grad_cache(qd, k, cali, layer=layer) if opt_mode != "mse" else None
     if grads_out is not None:
         grads_out.append(grads)
     for it in range(iters):
@@ -520,7 +536,9 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
         opt.zero_grad()
         _, wq = adaround_quant(st.weight, alpha_w, q.delta_w, q.zp_w, q.n_bits, True)
         _, bq = adaround_quant(st.bias, alpha_b, q.delta_b, q.zp_b, q.n_bits, True)
-        y = apply_act(up_shuffle(F.conv2d(cur_inp, wq, bq, stride=1, padding=st.k // 2), st.rh, st.rw), st.act)
+        y = F.conv2d(cur_inp, wq, bq, stride=1, padding=st.k // 2)
+        if not layer:
+            y = apply_act(up_shuffle(y, st.rh, st.rw), st.act)
         count = it + 1
         if opt_mode == "mse":
             rec = lp_loss(y, cur_out, p=p)
@@ -532,7 +550,7 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
         else:
             raise ValueError(opt_mode)
         b = decay(count)
-        if count < loss_start:
+        if count < loss_start or layer:
             b, rnd = 0, torch.zeros(())
         else:
             rnd = weight * round_reg(alpha_w, b)

@@ -26,7 +26,36 @@ from make_golden import TINY_HNERV, TINY_NERV, npy  # noqa: E402
 torch.set_num_threads(8)
 
 
-def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters=60, n_frames=20, bsz=2, opt_mode="mse"):
+def repaired_layer_reconstruction():
+    """calib_layer.layer_reconstruction stops at calib_layer.py:130 (`opt_params +=` with no prior assignment).  Compile
+    the reference's OWN source with the one missing statement inserted, in the module's namespace, in memory only."""
+    import inspect
+    import quantization.calib_layer as cl
+    src = inspect.getsource(cl.layer_reconstruction)
+    needle = "    opt_params += [layer.weight_quantizer.alpha]"
+    assert src.count(needle) == 1
+    src = src.replace(needle, "    opt_params = []\n" + needle)
+    ns = {}
+    exec(compile(src, "<calib_layer.layer_reconstruction + opt_params = []>", "exec"), cl.__dict__, ns)
+    return cl, ns["layer_reconstruction"]
+
+
+def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters=60, n_frames=20, bsz=2, opt_mode="mse",
+                   layer=None):
+    """layer: None = block_reconstruction on decoder[block_idx]; 'conv' = the repaired layer_reconstruction on that
+    block's convolution; 'head' / 'stem' = on the head layer / decoder[0]."""
+    global cb
+    cb_block = cb
+    if layer is not None:
+        cb, layer_fn = repaired_layer_reconstruction()
+    try:
+        _run_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters, n_frames, bsz, opt_mode, layer,
+                  layer_fn if layer is not None else None)
+    finally:
+        cb = cb_block
+
+
+def _run_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, iters, n_frames, bsz, opt_mode, layer, layer_fn):
     torch.manual_seed(903)
     model = (models.HNeRV if arch == "hnerv" else models.NeRV)(cfg)
     with torch.no_grad():
@@ -49,8 +78,12 @@ def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, 
     qnn.set_quant_state(True)
     with torch.no_grad():
         qnn(cali[:bsz])  # first quantised forward initialises every step size
-    block = qnn.model.decoder[block_idx]
+    block = {None: lambda: qnn.model.decoder[block_idx], "conv": lambda: qnn.model.decoder[block_idx].conv,
+             "head": lambda: qnn.model.head_layer, "stem": lambda: qnn.model.decoder[0]}[layer]()
     conv = [m for m in block.modules() if isinstance(m, QuantModule)][0]
+    assert layer is None or block is conv
+    out["layer"] = np.array(layer or "")
+    out["stage"] = np.array([i for i, m in enumerate(x for x in qnn.model.modules() if isinstance(x, QuantModule)) if m is conv][0])
 
     idx_log, mask_log, traj, cache = [], [], [], {}
     _randperm, _rand_like, _call, _save = torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data
@@ -101,8 +134,8 @@ def run_block_case(tag, arch, cfg, bits, hadamard, block_idx, asym, input_prob, 
     du.GetLayerGrad.__call__ = get_grad
     try:
         torch.manual_seed(5)
-        cb.block_reconstruction(qnn, block, cali, batch_size=bsz, iters=iters, weight=0.01, opt_mode=opt_mode, asym=asym,
-                                b_range=(20, 2), warmup=0.2, input_prob=input_prob, p=2.0, lr=0.003)
+        (layer_fn or cb.block_reconstruction)(qnn, block, cali, batch_size=bsz, iters=iters, weight=0.01, opt_mode=opt_mode,
+                                              asym=asym, b_range=(20, 2), warmup=0.2, input_prob=input_prob, p=2.0, lr=0.003)
     finally:
         torch.randperm, torch.rand_like, cb.LossFunction.__call__, cb.save_inp_oup_data = _randperm, _rand_like, _call, _save
         cb.save_grad_data = _save_grad
@@ -144,3 +177,8 @@ if __name__ == "__main__":
     # coarse predecessors so that the output gradients reach the resolution of fp32 (|g| + 1): at 5-6 bits the cache is 1.0
     run_block_case("block_tiny_hnerv_fdiag", "hnerv", TINY_HNERV, [2, 2, 2, 3, 5, 6, 6], False, 3, False, 1.0, opt_mode="fisher_diag")
     run_block_case("block_tiny_hnerv_ffull", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 2, True, 0.5, opt_mode="fisher_full")
+    # layer_reconstruction, repaired in memory (see repaired_layer_reconstruction)
+    run_block_case("layer_tiny_hnerv_conv", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, 3, True, 0.5, layer="conv", n_frames=10)
+    run_block_case("layer_tiny_hnerv_head", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 4], False, 0, False, 1.0, layer="head",
+                   opt_mode="fisher_diag", n_frames=10)
+    run_block_case("layer_tiny_nerv_stem", "nerv", TINY_NERV, [4, 6, 3, 4, 5, 4, 3], False, 0, False, 1.0, layer="stem")

@@ -34,10 +34,16 @@ BLOCK_CASES = {
     "block_tiny_hnerv_fdiag": ("hnerv", TINY_HNERV),   # opt_mode 'fisher_diag'
     "block_tiny_hnerv_ffull": ("hnerv", TINY_HNERV),   # opt_mode 'fisher_full', asym, QDrop 0.5
 }
+# layer_reconstruction (calib_layer.py:89-179), the reference's own source with its missing `opt_params = []` inserted in memory
+LAYER_CASES = {
+    "layer_tiny_hnerv_conv": ("hnerv", TINY_HNERV),    # a block's convolution, asym, QDrop 0.5
+    "layer_tiny_hnerv_head": ("hnerv", TINY_HNERV),    # head layer, fisher_diag
+    "layer_tiny_nerv_stem": ("nerv", TINY_NERV),       # stem (1x1), input = the embedding
+}
 
 
 def block_case(tag):
-    arch, cfg = BLOCK_CASES[tag]
+    arch, cfg = (BLOCK_CASES[tag] if tag in BLOCK_CASES else LAYER_CASES[tag])
     g = load(tag)
     sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
     return g, arch, cfg, O.stages_from_state_dict(sd, cfg, arch)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import nq_oracle as O
-from tests.helpers import BLOCK_CASES, load, t
+from tests.helpers import BLOCK_CASES, LAYER_CASES, load, t
 
 pytestmark = pytest.mark.gpu
 
@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def build(tag):
     from neuroquant_b200.models import HNeRV, NeRV
     from neuroquant_b200.quantization import QuantModel
-    arch, cfg = BLOCK_CASES[tag]
+    arch, cfg = BLOCK_CASES[tag] if tag in BLOCK_CASES else LAYER_CASES[tag]
     g = load(tag)
     model = (HNeRV if arch == "hnerv" else NeRV)(cfg)
     sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
@@ -29,12 +29,17 @@ def build(tag):
     return g, qnn
 
 
-@pytest.mark.parametrize("tag", list(BLOCK_CASES))
+@pytest.mark.parametrize("tag", list(BLOCK_CASES) + list(LAYER_CASES))
 def test_block_reconstruction_matches_reference(tag, monkeypatch):
-    from neuroquant_b200.quantization import QuantModule, block_reconstruction
+    """layer_* cases: layer_reconstruction against the reference's own function with its missing `opt_params = []`
+    inserted in memory (tests/golden/make_block_golden.py)."""
+    from neuroquant_b200.quantization import QuantModule, block_reconstruction, layer_reconstruction
     import neuroquant_b200.quantization.calib_block as cb
     g, qnn = build(tag)
-    block = qnn.model.decoder[int(g["block_idx"])]
+    which = str(g["layer"]) if "layer" in g.files else ""
+    block = {"": lambda: qnn.model.decoder[int(g["block_idx"])], "conv": lambda: qnn.model.decoder[int(g["block_idx"])].conv,
+             "head": lambda: qnn.model.head_layer, "stem": lambda: qnn.model.decoder[0]}[which]()
+    reconstruct = layer_reconstruction if which else block_reconstruction
     conv = [m for m in block.modules() if isinstance(m, QuantModule)][0]
     idx_seq = [torch.as_tensor(r) for r in g["idx"]]
     masks = [t(m) for m in g["masks"]] if "masks" in g.files else []
@@ -81,7 +86,7 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
     monkeypatch.setattr(cb, "save_inp_oup_data", save)
     monkeypatch.setattr(cb, "block_output_grads", grads)
     monkeypatch.setattr(cb.BlockStep, "run_cached", run)
-    block_reconstruction(qnn, block, t(g["cali"]).cuda(), batch_size=int(g["bsz"]), iters=int(g["iters"]), weight=0.01,
+    reconstruct(qnn, block, t(g["cali"]).cuda(), batch_size=int(g["bsz"]), iters=int(g["iters"]), weight=0.01,
                          opt_mode=str(g["opt_mode"]) if "opt_mode" in g.files else "mse", asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2, input_prob=float(g["input_prob"]),
                          p=2.0, lr=0.003)
     monkeypatch.undo()
@@ -98,7 +103,9 @@ def test_block_reconstruction_matches_reference(tag, monkeypatch):
         # g is the back-propagated DIFFERENCE of two nearly equal frames (out_q - out_fp ~ 1e-4 at 5-6 bits): fp32
         # cancellation leaves about three digits in either implementation
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max(), (np.abs(got - ref).max(), np.abs(ref).max())
-        assert np.array_equal(np.abs(got) + np.float32(1.0), g["cache_grad"])
+        # the cache itself: |g| + 1 in fp32 -- 1.0 or 1.0000001 (the head's gradients straddle half an ulp of 1)
+        cache = np.abs(got) + np.float32(1.0)
+        assert np.abs(cache - g["cache_grad"]).max() <= 1.2e-7 and (cache != g["cache_grad"]).mean() < 0.01
     # loss trajectory of the block output
     assert np.allclose(np.array(traj), g["traj"][:, 2], rtol=5e-3, atol=1e-9)
     wq, bq = conv.weight_quantizer, conv.bias_quantizer

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import nq_oracle as O
-from tests.helpers import CASES, case_stages, load, t, BLOCK_CASES, block_case
+from tests.helpers import CASES, case_stages, load, t, BLOCK_CASES, LAYER_CASES, block_case
 
 
 def test_fwht_matches_scipy():
@@ -165,25 +165,29 @@ def test_calibration_golden(tag):
     assert n_diff / n_tot < 5e-3
 
 
-@pytest.mark.parametrize("tag", list(BLOCK_CASES))
+@pytest.mark.parametrize("tag", list(BLOCK_CASES) + list(LAYER_CASES))
 def test_block_reconstruction_oracle_matches_reference(tag):
     """oracle.block_reconstruction against the reference's calib_block.block_reconstruction run on the same tiny
     decoder with its randperm / rand_like draws replayed: cached block inputs / outputs, the loss trajectory, the final
-    rounding variables and the hard-rounded codes of the block."""
+    rounding variables and the hard-rounded codes of the block.  layer_* cases: the layer-wise variant against the
+    reference's layer_reconstruction with its missing statement inserted (tests/golden/make_block_golden.py)."""
     g, arch, cfg, stages = block_case(tag)
-    k = int(g["block_idx"])
+    layer = tag in LAYER_CASES
+    k = int(g["stage"]) if layer else int(g["block_idx"])
     qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]))
     log = []
     masks = [t(m) for m in g["masks"]] if "masks" in g.files else None
     inp, sym, out = O.block_reconstruction(qd, k, t(g["cali"]), g["idx"].tolist(), int(g["iters"]), weight=0.01,
                                            asym=bool(g["asym"]), b_range=(20, 2), warmup=0.2,
                                            input_prob=float(g["input_prob"]), p=2.0, lr=0.003, masks=masks, log=log,
-                                           opt_mode=str(g["opt_mode"]) if "opt_mode" in g.files else "mse")
+                                           opt_mode=str(g["opt_mode"]) if "opt_mode" in g.files else "mse", layer=layer)
+    if layer:
+        assert not g["traj"][:, 3].any()  # the regulariser never reaches a lone QuantModule (calib_layer.py:38-46)
     if "cache_grad" in g.files:  # Fisher modes: the cached output gradients, as the reference holds them (|g| + 1) and raw
         q = qd.q[k]
         a_w, a_b = q.alpha_w, q.alpha_b
         q.alpha_w, q.alpha_b = O.adaround_init_alpha(q.stage.weight, q.delta_w), O.adaround_init_alpha(q.stage.bias, q.delta_b)
-        raw = O.block_grad_cache(qd, k, t(g["cali"]), raw=True).numpy()
+        raw = O.block_grad_cache(qd, k, t(g["cali"]), raw=True, layer=layer).numpy()
         q.alpha_w, q.alpha_b = a_w, a_b
         assert np.abs(raw - g["raw_grad"]).max() <= 1e-3 * np.abs(g["raw_grad"]).max()
         assert np.array_equal(np.abs(raw) + np.float32(1.0), g["cache_grad"])
