@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--decode-steps", type=int, default=10)
     ap.add_argument("--artefact", action="store_true", help="--mode decode: decode from the packed artefact written by this run")
     ap.add_argument("--stage", type=int, default=5, help="--mode block: decoder stage (block) to reconstruct")
-    ap.add_argument("--mode", default="calib", choices=["calib", "decode", "block"],
+    ap.add_argument("--mode", default="calib", choices=["calib", "decode", "block", "train"],
                     help="decode: quantised-decode throughput only (any workload, e.g. hnerv-1080p-12m)")
     return ap.parse_args()
 
@@ -198,6 +198,9 @@ def run_b200(args):
         return run_decode_only(args, eng, cfg, arch, geoms, world, rank, local)
     if args.mode == "block":
         return run_block(args, eng, cfg, arch, geoms, world, rank)
+    if args.mode == "train":
+        del eng
+        return run_train(args, cfg, arch, world, rank)
     H, W = cfg["crop_h"], cfg["crop_w"]
     gen = torch.Generator().manual_seed(903 + rank)
     F = max(args.frames, args.batch)
@@ -491,6 +494,59 @@ def run_block(args, eng, cfg, arch, geoms, world, rank):
                       "config": {"workload": f"{args.workload} block {k}: {g.cin}->{g.cout} k{g.k} at {h}x{w}, batch {B}, QDrop 0.5",
                                  "cache_frames": F},
                       "gpu_launches": 8 * args.steps, "tflops_algorithmic": flops / (ms * 1e-3) / 1e12}))
+
+
+def run_train(args, cfg, arch, world, rank):
+    """FP32 regression training (methods/regress.py): iterations/s of the reference's training step --
+    adjust_lr, forward, 'l2' loss, backward, Adam on every parameter -- with the decoder on the engine's tcgen05 kernels
+    in full-precision mode (methods/regress.DecoderTrainer) and, for HNeRV, the stock-PyTorch ConvNeXt encoder in front.
+    Frames resident in HBM; single GPU as in the reference."""
+    from types import SimpleNamespace
+    from neuroquant_b200.methods.regress import DecoderTrainer
+    from neuroquant_b200.models import HNeRV, NeRV
+    from neuroquant_b200.utils import adjust_lr
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "fp_train_iters_per_s", "unavailable": "regression training is single-GPU, as in the reference"}))
+        return
+    torch.manual_seed(903)
+    cfg = dict(cfg)
+    cfg.setdefault("diff_enc", False)
+    model = (HNeRV if arch == "hnerv" else NeRV)(cfg).cuda().train()
+    B, F = args.batch, max(args.frames, args.batch)
+    gen = torch.Generator().manual_seed(903)
+    frames = torch.rand(F, 3, cfg["crop_h"], cfg["crop_w"], generator=gen).cuda()
+    norm_idx = (torch.arange(F).float() / F).cuda()
+    targs = SimpleNamespace(lr=float(cfg.get("learning_rate", 1e-3)), lr_type="cosine_0.1_1_0.1")
+    trainer = DecoderTrainer(model, arch, targs.lr)
+    total = max(args.warmup, 3) + args.steps
+
+    def it(i):
+        adjust_lr(trainer, i / total, targs)
+        idx = torch.arange(i * B, i * B + B, device="cuda") % F
+        img = frames[idx]
+        return trainer.step(img if arch == "hnerv" else norm_idx[idx], img)
+
+    for i in range(max(args.warmup, 3)):
+        first, _ = it(i)
+    torch.cuda.synchronize()
+    l0 = trainer.launches + trainer.runner.engine.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        last, _ = it(max(args.warmup, 3) + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    eng = trainer.runner.engine
+    print(json.dumps({"metric": "fp_train_iters_per_s", "value": 1e3 / ms, "unit": f"it/s (batch-{B} training iterations)",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": eng.dtype_name, "data": "synthetic",
+                      "config": {"workload": f"{args.workload} FP32 regression step, batch {B}, loss l2, Adam, cosine lr",
+                                 "encoder": "stock PyTorch ConvNeXt (autograd), fed by the engine's d_embed" if arch == "hnerv" else "none",
+                                 "l2_inputs": "frames resident in HBM"},
+                      "gpu_launches": (eng.launches + trainer.launches - l0), "loss_first": float(first), "loss_last": float(last)}))
 
 
 if __name__ == "__main__":

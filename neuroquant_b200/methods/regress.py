@@ -1,0 +1,171 @@
+"""FP32 regression training of the decoder on the engine's convolution kernels (reference: methods/regress.py:151-322;
+SURVEY 8(f) rank 4 -- the step that produces the `epoch300.pth` the calibration starts from).
+
+Per iteration (regress.py:249-261): learning rate from adjust_lr, forward, loss_fn 'l2' (utils.py:115-116: per-frame
+mean over C*H*W, batch mean), backward, Adam on every parameter.  Here the decoder -- stem, blocks, head: the
+convolutions that hold all of NeRV's and nearly all of HNeRV's training FLOPs -- runs on the same tcgen05 forward / data
+gradient / weight gradient kernels as the calibration loop, with the engine in full-precision mode, and its Adam steps are
+CUDA kernels of the library.  HNeRV's ConvNeXt frame encoder stays stock PyTorch (as everywhere in this package): the
+engine hands back dL/d(embedding) and autograd carries it through the encoder, whose parameters step in a torch Adam
+at the same learning rate.  Losses other than 'l2' (SSIM mixtures) are not provided.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+import time
+from datetime import datetime
+
+import torch
+import torch.nn.functional as F
+from torch.utils.data import Subset
+
+from ..engine import AdamState
+from ..runner import DecoderRunner
+from ..utils import RoundTensor, adjust_lr, data_split, get_config, psnr_fn_single, setup_logger, worker_init_fn
+
+
+class DecoderTrainer:
+    """One model's training state: the engine binding, a fused Adam over the decoder's (weight, bias) tensors and, for
+    HNeRV, a torch Adam over the encoder.  `param_groups` makes it acceptable to utils.adjust_lr."""
+
+    def __init__(self, model, arch: str, lr: float):
+        self.model, self.arch = model, arch
+        self.runner = DecoderRunner.of(model)
+        if any(self.runner._quant):
+            raise ValueError("regression training takes the full-precision model, not a QuantModel")
+        self.params = [t for l in self.runner.layers for t in (l.weight.data, l.bias.data)]
+        self.opt = AdamState(self.params, lr)
+        enc = [p for n, p in model.named_parameters() if n.startswith("encoder")] if arch == "hnerv" else []
+        self.enc_opt = torch.optim.Adam(enc, weight_decay=0.) if enc else None
+        self.param_groups = [{"lr": lr}] + (self.enc_opt.param_groups if self.enc_opt else [])
+        self.launches = 0
+
+    def step(self, inputs: torch.Tensor, frames: torch.Tensor):
+        """inputs: the frames themselves (hnerv) or their normalised indices (nerv).  Returns (loss, img_out), both on
+        the device; the loss is the value BEFORE the update, as regress.py:260 logs it."""
+        eng = self.runner.engine
+        if self.enc_opt is not None:
+            embed = self.model.encode(inputs)
+        else:
+            with torch.no_grad():
+                embed = self.model.encode(inputs)
+        self.runner.sync()
+        n, _, hh, ww = frames.shape
+        img = eng.forward(embed.detach(), train=True, target=frames, p_norm=2.0, mean_pixels=float(n * 3 * hh * ww),
+                          reuse_weights=True)
+        loss = eng.last_loss().clone()
+        flat = eng.backward()
+        _, views = eng._grad_buffers()
+        if self.enc_opt is not None:
+            # dL/d(embedding): the stem's data gradient, a k x k (1 x 1 in every shipped config) transposed convolution of
+            # a (n, C, h0, w0) map of a few hundred values -- left to torch, like the encoder it feeds
+            st0 = eng.stages[0]
+            d_embed = F.conv_transpose2d(eng.stage_output_grad(0), st0.weight, padding=st0.geom.k // 2)
+            self.enc_opt.zero_grad()
+            embed.backward(d_embed)
+            self.enc_opt.step()
+        self.opt.lr = float(self.param_groups[0]["lr"])
+        self.launches += self.opt.step([g for pair in views for g in pair])
+        eng.invalidate()  # the kernels updated the weights in place
+        return loss, img
+
+
+def train(args, cfg):
+    """regress.py:151-322 without TensorBoard: data set, model, per-epoch training + evaluation, checkpoints
+    (`model_latest.pth`, `epoch<N>.pth`: plain state_dicts, loadable by the reference)."""
+    from ..videosets import VideoDataSet
+    from .common import build_model, evaluate, init_distributed
+    rank, world, _ = init_distributed()
+    if world > 1:
+        raise NotImplementedError("regression training is single-GPU, as in the reference")
+    if cfg["loss"] != "l2":
+        raise NotImplementedError(f"loss {cfg['loss']!r}: only 'l2' runs on the fused head kernel")
+    device = "cuda"
+    full_dataset = VideoDataSet(cfg, args)
+    full_loader = torch.utils.data.DataLoader(full_dataset, batch_size=cfg["batch_size"], shuffle=False, num_workers=cfg["workers"],
+                                              pin_memory=True, drop_last=False, worker_init_fn=worker_init_fn)
+    args.final_size = full_dataset.final_size
+    args.full_data_length = len(full_dataset)
+    split = [int(x) for x in args.data_split.split("_")]
+    train_idx, args.val_ind_list = data_split(list(range(args.full_data_length)), split, False, 0)
+    gen = torch.Generator()
+    gen.manual_seed(args.seed)
+    train_loader = torch.utils.data.DataLoader(Subset(full_dataset, train_idx), batch_size=cfg["batch_size"], shuffle=True,
+                                               num_workers=cfg["workers"], pin_memory=True, drop_last=True,
+                                               worker_init_fn=worker_init_fn, generator=gen)
+    model = build_model(args, cfg).to(device)
+    args.outf = os.path.join(args.outf, f"Encoder_{round(args.encoder_param, 2)}M_Decoder_{round(args.decoder_param, 2)}M_"
+                                        f"Total_{round(args.total_param, 2)}M")
+    os.makedirs(args.outf, exist_ok=True)
+    setup_logger(args.outf + "/" + time.strftime("%Y%m%d_%H%M%S") + ".log")
+    logging.info("[PID] %s" % os.getpid())
+    logging.info(str(model))
+    if args.weight != "None":
+        logging.info("=> loading checkpoint '{}'".format(args.weight))
+        model.load_state_dict(torch.load(args.weight, map_location="cpu"), strict=False)
+        model.to(device)
+    if args.eval_only:
+        results, _, _ = evaluate(model, full_loader, args, cfg, args.dump_vis)
+        logging.info(f"best_pred_seen_psnr: {RoundTensor(results[0].max(), 2)} | ")
+        return
+    args.lr = cfg["learning_rate"]
+    trainer = DecoderTrainer(model, args.arch, args.lr)
+    start = datetime.now()
+    for epoch in range(cfg["epoch"]):
+        model.train()
+        epoch_start, psnrs = datetime.now(), []
+        for i, sample in enumerate(train_loader):
+            cur_epoch = (epoch + float(i) / len(train_loader)) / cfg["epoch"]
+            lr = adjust_lr(trainer, cur_epoch, args)
+            img = sample["img"].to(device, non_blocking=True)
+            inputs = img if args.arch == "hnerv" else sample["norm_idx"].to(device)
+            _, img_out = trainer.step(inputs, img)
+            psnrs.append(psnr_fn_single(img_out, img))
+            if i % args.print_freq == 0 or i == len(train_loader) - 1:
+                logging.info("[{}], Epoch[{}/{}], Step [{}/{}], lr:{:.2e} pred_PSNR: {}".format(
+                    datetime.now().strftime("%Y/%m/%d %H:%M:%S"), epoch + 1, cfg["epoch"], i + 1, len(train_loader), lr,
+                    RoundTensor(torch.cat(psnrs).mean(), 2)))
+        logging.info("Time/epoch: \tCurrent:{:.2f} \tAverage:{:.2f}".format(
+            (datetime.now() - epoch_start).total_seconds(), (datetime.now() - start).total_seconds() / (epoch + 1)))
+        if (epoch + 1) % cfg["eval_freq"] == 0 or (cfg["epoch"] - epoch) in [1, 3, 5]:
+            results, hw, _ = evaluate(model, full_loader, args, cfg, args.dump_vis if epoch == cfg["epoch"] - 1 else False)
+            logging.info(f"Eval at epoch {epoch + 1} for {hw}: pred_seen_psnr: {RoundTensor(results[0], 2)} | ")
+        torch.save(model.state_dict(), "{}/model_latest.pth".format(args.outf))
+        if (epoch + 1) % cfg["epoch"] == 0:
+            torch.save(model.state_dict(), f"{args.outf}/epoch{epoch + 1}.pth")
+    logging.info(f"Training complete in: {str(datetime.now() - start)}")
+
+
+def parse_args(argv):
+    import argparse
+    parser = argparse.ArgumentParser()  # regress.py:33-55
+    parser.add_argument("--seed", default=903, type=int)
+    parser.add_argument("--outf", default="unify")
+    parser.add_argument("--config", type=str)
+    parser.add_argument("--arch", type=str)
+    parser.add_argument("--data_path", type=str)
+    parser.add_argument("--vid", type=str)
+    parser.add_argument("--data_split", type=str, default="1_1_1")
+    parser.add_argument("-p", "--print-freq", default=50, type=int)
+    parser.add_argument("--lr_type", type=str, default="cosine_0.1_1_0.1")
+    parser.add_argument("--weight", default="None", type=str)
+    parser.add_argument("--eval_only", action="store_true", default=False)
+    parser.add_argument("--dump_vis", action="store_true", default=False)
+    parser.add_argument("--eval_fps", action="store_true", default=False)
+    return parser.parse_args(argv)
+
+
+def main(argv):
+    args = parse_args(argv)
+    cfg = get_config(args.config)
+    torch.manual_seed(args.seed)
+    args.outf = os.path.join("results", args.outf)
+    args.exp_id = f"{args.vid}_e{cfg['epoch']}_b{cfg['batch_size']}_lr{cfg['learning_rate']}_{cfg['loss']}"
+    args.outf = os.path.join(args.outf, args.exp_id)
+    train(args, cfg)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

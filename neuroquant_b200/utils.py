@@ -1,7 +1,7 @@
-"""Helpers with the reference's names (utils.py): YAML config, logger, data split, PSNR.
-MS-SSIM, the FP-training loss zoo and LR schedule are eval cosmetics / FP training:
-not part of the calibration path."""
+"""Helpers with the reference's names (utils.py): YAML config, logger, data split, PSNR, the LR schedule of the FP
+regression (methods/regress.py).  MS-SSIM and the SSIM-mixing training losses are not provided."""
 import logging
+import math
 import random
 import sys
 
@@ -67,3 +67,25 @@ def psnr_fn_batch(output_list, gt):
 
 def msssim_fn_single(output, gt):
     raise NotImplementedError("MS-SSIM is an evaluation cosmetic outside the calibration path (SURVEY row 14)")
+
+
+def adjust_lr(optimizer, cur_epoch, args, eta_min=0.05):
+    """utils.py:79-99: 'cosine_<up_ratio>_<up_pow>_<min_lr>' / 'hybrid_...' multiplier applied to every param group of
+    `optimizer` (anything with a `param_groups` list of dicts, e.g. methods.regress.DecoderTrainer)."""
+    if "hybrid" in args.lr_type:
+        up_ratio, up_pow, down_pow, min_lr, final_lr = [float(x) for x in args.lr_type.split("_")[1:]]
+        if cur_epoch < up_ratio:
+            lr_mult = min_lr + (1. - min_lr) * (cur_epoch / up_ratio) ** up_pow
+        else:
+            lr_mult = 1 - (1 - final_lr) * ((cur_epoch - up_ratio) / (1. - up_ratio)) ** down_pow
+    elif "cosine" in args.lr_type:
+        up_ratio, up_pow, min_lr = [float(x) for x in args.lr_type.split("_")[1:]]
+        if cur_epoch < up_ratio:
+            lr_mult = min_lr + (1. - min_lr) * (cur_epoch / up_ratio) ** up_pow
+        else:
+            lr_mult = max(0.5 * (math.cos(math.pi * (cur_epoch - up_ratio) / (1 - up_ratio)) + 1.0), eta_min)
+    else:
+        raise NotImplementedError
+    for param_group in optimizer.param_groups:
+        param_group["lr"] = args.lr * lr_mult
+    return args.lr * lr_mult

@@ -563,6 +563,54 @@ def block_reconstruction(qd: QuantDecoder, k: int, cali: torch.Tensor, idx_seq: 
 
 
 # --------------------------------------------------------------------------------------------
+# FP32 regression of the decoder (regress.py:239-271, utils.py:79-99,112-116): SURVEY 8(f) rank 4
+# --------------------------------------------------------------------------------------------
+def adjust_lr(base_lr: float, cur_epoch: float, lr_type: str, eta_min: float = 0.05) -> float:
+    """utils.py:79-99."""
+    if "hybrid" in lr_type:
+        up_ratio, up_pow, down_pow, min_lr, final_lr = [float(x) for x in lr_type.split("_")[1:]]
+        if cur_epoch < up_ratio:
+            mult = min_lr + (1. - min_lr) * (cur_epoch / up_ratio) ** up_pow
+        else:
+            mult = 1 - (1 - final_lr) * ((cur_epoch - up_ratio) / (1. - up_ratio)) ** down_pow
+    elif "cosine" in lr_type:
+        up_ratio, up_pow, min_lr = [float(x) for x in lr_type.split("_")[1:]]
+        if cur_epoch < up_ratio:
+            mult = min_lr + (1. - min_lr) * (cur_epoch / up_ratio) ** up_pow
+        else:
+            mult = max(0.5 * (math.cos(math.pi * (cur_epoch - up_ratio) / (1 - up_ratio)) + 1.0), eta_min)
+    else:
+        raise NotImplementedError(lr_type)
+    return base_lr * mult
+
+
+def regress_decoder(stages: Sequence[Stage], embeds: torch.Tensor, frames: torch.Tensor, order: Sequence[Sequence[int]],
+                    epochs: int, lr: float, lr_type: str = "cosine_0.1_1_0.1", log: Optional[list] = None):
+    """The training loop of regress.py:249-271 for a decoder fed with FIXED embeddings (NeRV: positional encoding), loss
+    'l2' (utils.py:115-116: per-frame mean over C*H*W, then the batch mean), Adam defaults, lr set per step by adjust_lr.
+    order: the mini-batches of all epochs, in sequence (len(order) / epochs steps per epoch).  Updates `stages` in place."""
+    ws = [s.weight.clone().requires_grad_(True) for s in stages]
+    bs = [s.bias.clone().requires_grad_(True) for s in stages]
+    opt = torch.optim.Adam([t for pair in zip(ws, bs) for t in pair], weight_decay=0.)
+    per_epoch = len(order) // epochs
+    for it, idx in enumerate(order):
+        epoch, i = divmod(it, per_epoch)
+        cur_lr = adjust_lr(lr, (epoch + float(i) / per_epoch) / epochs, lr_type)
+        for gr in opt.param_groups:
+            gr["lr"] = cur_lr
+        idx = torch.as_tensor(idx)
+        out = decode(stages, embeds[idx], ws, bs)
+        loss = F.mse_loss(out, frames[idx], reduction="none").flatten(1).mean(1).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if log is not None:
+            log.append((float(loss), cur_lr))
+    for s, w, b in zip(stages, ws, bs):
+        s.weight, s.bias = w.detach(), b.detach()
+
+
+# --------------------------------------------------------------------------------------------
 # Omega = dw^T H dw sensitivity (bit_assign.py:57-118,171-203)
 # --------------------------------------------------------------------------------------------
 def omega(stages: Sequence[Stage], vec: Sequence[torch.Tensor], embeds: Sequence[torch.Tensor],

@@ -218,3 +218,20 @@ def test_packed_code_stream_statement(bits):
         assert np.array_equal(O.unpack_codes_np(p, n, bits), c.astype(np.float32))
     if bits == 3:  # codes 1,2,3,4,5,6,7,0 -> bits 100 010 110 001 101 011 111 000 (LSB first) -> bytes 0xD1 0x58 0x1F
         assert O.pack_codes_np([1, 2, 3, 4, 5, 6, 7, 0], 3).tolist() == [0xD1, 0x58, 0x1F]
+
+
+def test_regress_decoder_oracle_matches_reference():
+    """oracle.regress_decoder / adjust_lr against the reference's model, loss_fn, adjust_lr and torch Adam replayed on
+    seeded frames (tests/golden/make_regress_golden.py): learning rates, loss per step, final decoder weights."""
+    from tests.helpers import TINY_NERV
+    g = load("regress_tiny_nerv")
+    sd = {k[4:]: t(g[k]) for k in g.files if k.startswith("sd0/")}
+    stages = O.stages_from_state_dict(sd, TINY_NERV, "nerv")
+    log = []
+    O.regress_decoder(stages, t(g["embed"]), t(g["frames"]), g["order"].tolist(), int(g["epochs"]), float(g["lr"]),
+                      str(g["lr_type"]), log=log)
+    assert np.allclose([r[1] for r in log], g["lr_seq"], rtol=1e-12)
+    assert np.allclose([r[0] for r in log], g["loss"], rtol=1e-5)
+    sd1 = {k[4:]: t(g[k]) for k in g.files if k.startswith("sd1/")}
+    for st, ref in zip(stages, O.stages_from_state_dict(sd1, TINY_NERV, "nerv")):
+        assert float((st.weight - ref.weight).abs().max()) < 2e-6 and float((st.bias - ref.bias).abs().max()) < 2e-6
