@@ -19,7 +19,7 @@ import torch
 from ..parallel import candidates_of_rank, gather_scores
 from ..quantization import QuantModel
 from ..runner import DecoderRunner
-from ..sensitivity import OmegaEvaluator, fisher_diag
+from ..sensitivity import fisher_diag, omega, omega_layers
 from ..utils import data_split, get_config, setup_logger, worker_init_fn
 from ..videosets import VideoDataSet
 from .common import build_model, evaluate, init_distributed
@@ -29,9 +29,11 @@ hnerv_candidate = {"candidate1": [2, 3, 4, 6, 4, 4, 2], "candidate2": [6, 5, 4, 
 nerv_candidate = {"candidate1": [5, 6, 3, 4, 5, 4, 3], "candidate2": [6, 5, 5, 6, 7, 6, 7]}
 
 
-def sensitivity_criterion(mode, arch, net, qnn, dataloader, use_cuda=True, max_batches=10):
+def sensitivity_criterion(mode, arch, net, qnn, dataloader, use_cuda=True, max_batches=10, per_layer=True):
     """bit_assign.py:171-217.  `net` is the full-precision model, `qnn` the QuantModel whose perturbation
-    W - Q(W) is scored; the first 10 batches of `dataloader` are used (:115-117)."""
+    W - Q(W) is scored; the first 10 batches of `dataloader` are used (:115-117).  per_layer: also log the reference's
+    "[i-th layer]" terms (:194-200, :208-214); for 'omega' they cost 2 extra jets per layer (sensitivity.omega_layers) --
+    pass False when only the score matters (candidate search)."""
     vec = qnn.get_perturbation()
     runner = DecoderRunner.of(net)
     for l in runner.layers:
@@ -48,16 +50,16 @@ def sensitivity_criterion(mode, arch, net, qnn, dataloader, use_cuda=True, max_b
             if len(batches) >= max_batches:
                 break
     if mode == "omega":
-        ev = OmegaEvaluator(runner.engine)
-        n, _, h0, w0 = batches[0][0].shape
-        for embed, img in batches:
-            if embed.shape[0] != n:  # a ragged last batch gets its own plan
-                n = embed.shape[0]
-            ev.set_direction(vec, embed.shape[0], h0, w0) if ev._v is None or embed.shape[0] != n else None
-            ev.add_batch(embed, img)
-        return torch.tensor(ev.value())
+        if per_layer:
+            for count, cur in enumerate(omega_layers(runner.engine, vec, batches)):
+                logging.info(f"[{count:d}-th layer] {cur:.3e}")
+        return torch.tensor(omega(runner.engine, vec, batches))
     if mode == "fisher_diag":
-        return torch.tensor(fisher_diag(runner.engine, vec, batches))
+        per = fisher_diag(runner.engine, vec, batches, per_layer=True)
+        if per_layer:
+            for count, cur in enumerate(per):
+                logging.info(f"[{count:d}-th layer] {cur:.3e}")
+        return torch.tensor(sum(per))
     raise ValueError("Not implemented sensitivity criteria: {}".format(mode))
 
 

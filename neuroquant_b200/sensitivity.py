@@ -5,8 +5,9 @@ omega        Omega = sum_batches v^T H_b v, H_b the Hessian of nn.MSELoss(decode
              v^T H v = d^2/d eps^2 L(w + eps v)|_0 is propagated FORWARD as a second-order jet
              (y, y', y'') through the decoder: 5 forward convolutions per stage on the tensor-core kernel
              (y*w, y'*w, y*v, y''*w, y'*v), the elementwise chain rule (nq_jet_act) and the MSE head
-             (nq_jet_head).  No backward pass, no graph.  The per-layer split of Omega that the reference
-             also logs needs the full H v and is not produced.
+             (nq_jet_head).  No backward pass, no graph.  The per-layer terms the reference also logs,
+             Omega_l = v_l^T (H v)_l (bit_assign.py:194-200), follow from the same kernel by polarisation:
+             v_l^T H v = (Omega(v + v_l) - Omega(v - v_l)) / 4, two more jets per layer (omega_layers).
 fisher_diag  sum_l sum (v_l^2 * g_l^2) with g the gradient accumulated over the batches: one engine
              forward/backward per batch and one fused multi-tensor reduction (nq_multi_dot).
 """
@@ -135,9 +136,33 @@ class OmegaEvaluator:
         return float(self.acc)
 
 
-def fisher_diag(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches) -> float:
+def omega(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches) -> float:
+    """Omega over `batches` of (embedding, frames); one direction, all batches."""
+    ev = OmegaEvaluator(engine)
+    shape = None
+    for embed, img in batches:
+        if tuple(embed.shape) != shape:  # a ragged last batch gets its own plan
+            shape = tuple(embed.shape)
+            ev.set_direction(vecs, embed.shape[0], embed.shape[2], embed.shape[3])
+        ev.add_batch(embed, img)
+    return ev.value()
+
+
+def omega_layers(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches) -> List[float]:
+    """The per-layer terms of Omega the reference logs (bit_assign.py:194-200): [v_l^T (H v)_l for every layer l], whose
+    sum is Omega.  H is symmetric, so v_l^T H v = (Q(v + v_l) - Q(v - v_l)) / 4 with Q(u) = u^T H u the quantity the jet
+    kernels evaluate; v +- v_l doubles / zeroes layer l's perturbation.  2 * n_layers evaluations."""
+    out = []
+    for l in range(len(vecs)):
+        plus = [v * 2.0 if i == l else v for i, v in enumerate(vecs)]
+        minus = [torch.zeros_like(v) if i == l else v for i, v in enumerate(vecs)]
+        out.append(0.25 * (omega(engine, plus, batches) - omega(engine, minus, batches)))
+    return out
+
+
+def fisher_diag(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches, per_layer: bool = False):
     """bit_assign.py:122-168, :205-214: gradients of the MSE-mean loss accumulated over the batches,
-    then sum v^2 g^2."""
+    then sum v^2 g^2 (per_layer: the list of per-layer sums the reference logs, :208-214)."""
     if engine.mode != "off":
         raise L.NqError("fisher_diag is defined on the full-precision decoder")
     total = None
@@ -150,4 +175,5 @@ def fisher_diag(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches) ->
     _, views = engine._grad_buffers()
     g = [gw.contiguous() for gw, _ in views]
     v = [x.detach().contiguous().float() for x in vecs]
-    return float(L.multi_dot(v, g, 1).sum())
+    per = L.multi_dot(v, g, 1)
+    return [float(x) for x in per] if per_layer else float(per.sum())

@@ -118,7 +118,7 @@ class ListLoader(list):
     """Stand-in for the DataLoader `gt` of model_reconstruction: len() + iteration of dicts."""
 
 
-def run_model_case(tag, arch, cfg, bits, hadamard, iters, n_frames=8, bsz=2, omega=True):
+def run_model_case(tag, arch, cfg, bits, hadamard, iters, n_frames=8, bsz=2, omega=True, only_layers=False):
     torch.manual_seed(903)
     model = (models.HNeRV if arch == "hnerv" else models.NeRV)(cfg)
     with torch.no_grad():  # non-degenerate random decoder weights (default init is fine) + biases
@@ -173,13 +173,23 @@ def run_model_case(tag, arch, cfg, bits, hadamard, iters, n_frames=8, bsz=2, ome
             spec.loader.exec_module(ba)
             loader = [{"img": frames[i:i + bsz], "norm_idx": torch.arange(i, i + bsz).float() / n_frames,
                        "idx": torch.arange(i, i + bsz)} for i in range(0, n_frames, bsz)]
-            om = ba.sensitivity_criterion("omega", arch, copy.deepcopy(fp_model), qnn, loader, use_cuda=False)
+            net_o, net_f = copy.deepcopy(fp_model), copy.deepcopy(fp_model)
+            om = ba.sensitivity_criterion("omega", arch, net_o, qnn, loader, use_cuda=False)
             out["omega"] = np.array(float(om), dtype=np.float64)
-            fd = ba.sensitivity_criterion("fisher_diag", arch, copy.deepcopy(fp_model), qnn, loader, use_cuda=False)
+            fd = ba.sensitivity_criterion("fisher_diag", arch, net_f, qnn, loader, use_cuda=False)
             out["fisher_diag"] = np.array(float(fd), dtype=np.float64)
+            # the per-layer terms the reference logs (bit_assign.py:194-200, :208-214), at full precision: H v and the
+            # accumulated gradient are still in the nets' .grad (gradtensor_to_vec, :38-55)
+            side = {"omega": out["omega"], "fisher_diag": out["fisher_diag"],
+                    "omega_layers": np.array([float((gg * v).sum()) for gg, v in zip(ba.gradtensor_to_vec(net_o), pert)]),
+                    "fisher_layers": np.array([float((v.pow(2) * gg.pow(2)).sum()) for gg, v in zip(ba.gradtensor_to_vec(net_f), pert)])}
+            np.savez_compressed(os.path.join(HERE, f"{tag}_sens_layers.npz"), **side)
+            print(tag, "omega layers", side["omega_layers"], "sum", side["omega_layers"].sum(), "omega", float(om))
         finally:
             torch.Tensor.cuda = _cuda
 
+    if only_layers:
+        return
     # calibration with an injected, fixed batch order
     order = [[(2 * j + 3 * k) % n_frames for k in range(bsz)] for j in range(n_frames // bsz)]
     order = [[0, 5], [3, 6], [1, 4], [7, 2]][: n_frames // bsz]
@@ -248,6 +258,11 @@ def bookkeeping():
 if __name__ == "__main__":
     quantizer_kats()
     bookkeeping()
+    if sys.argv[1:] == ["sens_layers"]:  # only the per-layer sensitivity side files (tiny_*_sens_layers.npz)
+        run_model_case("tiny_hnerv", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, iters=80, only_layers=True)
+        run_model_case("tiny_hnerv_had", "hnerv", TINY_HNERV, [4, 5, 4, 6, 5, 6, 8], True, iters=80, only_layers=True)
+        run_model_case("tiny_nerv", "nerv", TINY_NERV, [6, 5, 4, 5, 5, 6, 6], False, iters=80, only_layers=True)
+        sys.exit(0)
     run_model_case("tiny_hnerv", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, iters=80)
     run_model_case("tiny_hnerv_had", "hnerv", TINY_HNERV, [4, 5, 4, 6, 5, 6, 8], True, iters=80)
     run_model_case("tiny_nerv", "nerv", TINY_NERV, [6, 5, 4, 5, 5, 6, 6], False, iters=80)

@@ -169,6 +169,14 @@ def test_omega_golden(tag):
     for i in range(0, 8, 2):
         ev.add_batch(cali[i:i + 2], frames[i:i + 2])
     assert ev.value() == pytest.approx(float(g["omega"]), rel=5e-3, abs=1e-12)
+    # the per-layer terms the reference logs (bit_assign.py:194-200), here by polarisation of the same jet
+    from neuroquant_b200.sensitivity import omega, omega_layers
+    gl = load(tag + "_sens_layers")
+    batches = [(cali[i:i + 2], frames[i:i + 2]) for i in range(0, 8, 2)]
+    assert omega(runner.engine, vec, batches) == pytest.approx(float(g["omega"]), rel=5e-3, abs=1e-12)
+    per = np.array(omega_layers(runner.engine, vec, batches))
+    assert np.abs(per - gl["omega_layers"]).max() <= 5e-3 * np.abs(gl["omega_layers"]).max(), (per, gl["omega_layers"])
+    assert per.sum() == pytest.approx(float(g["omega"]), rel=2e-2)  # the terms cancel: several are negative
     # fisher_diag against autograd of the oracle
     _, _, _, stages = __import__("tests.helpers", fromlist=["case_stages"]).case_stages(tag)
     ws = [s.weight.clone().requires_grad_(True) for s in stages]
@@ -178,5 +186,7 @@ def test_omega_golden(tag):
         gr = torch.autograd.grad(torch.nn.functional.mse_loss(out, frames[i:i + 2].cpu()), ws)
         tot = [a + b for a, b in zip(tot, gr)]
     want = sum(float((v.cpu() ** 2 * gg ** 2).sum()) for v, gg in zip(vec, tot))
-    got = fisher_diag(runner.engine, vec, [(cali[i:i + 2], frames[i:i + 2]) for i in range(0, 8, 2)])
+    got = fisher_diag(runner.engine, vec, batches)
     assert got == pytest.approx(want, rel=2e-3)
+    assert got == pytest.approx(float(g["fisher_diag"]), rel=5e-3)
+    assert np.allclose(fisher_diag(runner.engine, vec, batches, per_layer=True), gl["fisher_layers"], rtol=5e-3, atol=1e-4 * gl["fisher_layers"].max())
