@@ -56,6 +56,11 @@ int nq_sm_count(void);
 int nq_uaq_init_max(const float* x, int64_t rows, int64_t row_len, int n_bits,
                     float* delta, float* zero_point, void* stream);
 
+/* The other asymmetric initialisers of init_quantization_scale: method 1 'mse' (ten shrinking ranges scored by the L_3.5
+ * norm, quantizer.py:170-187), 2 'l1' (:204-220), 3 'gaussian' (mu +- 6 var, :189-202).  Same layout as nq_uaq_init_max. */
+int nq_uaq_init_search(const float* x, int64_t rows, int64_t row_len, int n_bits, int method,
+                       float* delta, float* zero_point, void* stream);
+
 typedef enum nq_round_mode {
   NQ_ROUND_NEAREST = 0, /* UAQ forward, round-half-even + STE   (quantizer.py:117-119, :53-57) */
   NQ_ROUND_SOFT = 1,    /* AdaRound floor + h(alpha)           (quantizer.py:288-291, :302-303) */

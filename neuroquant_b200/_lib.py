@@ -96,6 +96,7 @@ def _load():
         "nq_abi_version": (I, []),
         "nq_sm_count": (I, []),
         "nq_uaq_init_max": (I, [P, L, L, I, P, P, P]),
+        "nq_uaq_init_search": (I, [P, L, L, I, I, P, P, P]),
         "nq_fakequant_fwd": (I, [P, P, P, P, L, L, I, I, I, P, P, P, F, P]),
         "nq_fakequant_bwd": (I, [P, P, P, P, P, L, L, I, I, I, F, F, F, P, P, P]),
         "nq_adaround_init_alpha": (I, [P, P, L, L, I, P, P]),
@@ -193,6 +194,21 @@ def uaq_init_max(x, n_bits, channel_wise=True):
     delta = torch.empty(rows, device=x.device, dtype=torch.float32)
     zp = torch.empty_like(delta)
     check(lib.nq_uaq_init_max(ptr(x), rows, row_len, n_bits, ptr(delta), ptr(zp), stream()), "nq_uaq_init_max")
+    if x.dim() == 4 and channel_wise:
+        return delta.view(-1, 1, 1, 1), zp.view(-1, 1, 1, 1)
+    return delta.view(-1), zp.view(-1)
+
+
+SCALE_METHODS = {"mse": 1, "l1": 2, "gaussian": 3}
+
+
+def uaq_init_search(x, n_bits, channel_wise, method: str):
+    """'mse' / 'l1' / 'gaussian' initialisers (quantizer.py:170-222), asymmetric; same shapes as uaq_init_max."""
+    rows, row_len, _ = rows_of(x, channel_wise)
+    delta = torch.empty(rows, device=x.device, dtype=torch.float32)
+    zp = torch.empty_like(delta)
+    check(lib.nq_uaq_init_search(ptr(x), rows, row_len, n_bits, SCALE_METHODS[method], ptr(delta), ptr(zp), stream()),
+          "nq_uaq_init_search")
     if x.dim() == 4 and channel_wise:
         return delta.view(-1, 1, 1, 1), zp.view(-1, 1, 1, 1)
     return delta.view(-1), zp.view(-1)

@@ -38,6 +38,105 @@ __global__ void __launch_bounds__(256) uaq_init_max_kernel(const float* __restri
   }
 }
 
+// 'mse' (L_3.5) / 'l1' range search and the 'gaussian' initialiser (quantizer.py:170-222), one block per row.  The ten
+// candidate ranges are scored in ONE pass over the row; every operation the reference performs on fp32 tensors is a
+// separately rounded fp32 operation here (no contraction), so the step sizes are the reference's bit for bit -- only the
+// summation order of the score differs, which matters when two candidates tie to ~1e-7.
+template <int METHOD>  // 1 mse, 2 l1, 3 gaussian
+__global__ void __launch_bounds__(256) uaq_init_search_kernel(const float* __restrict__ x, int64_t row_len, int n_bits,
+                                                              float* __restrict__ delta, float* __restrict__ zp) {
+  __shared__ float smin[8], smax[8];
+  __shared__ double ssum[8][10];
+  __shared__ float bc[2];
+  const float* row = x + (int64_t)blockIdx.x * row_len;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float qmax = (float)((1 << n_bits) - 1);
+  if (METHOD == 3) {
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < row_len; i += blockDim.x) acc += (double)row[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) ssum[wid][0] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < nw; ++i) t += ssum[i][0];
+      bc[0] = (float)(t / (double)row_len);
+    }
+    __syncthreads();
+    const double mean = (double)bc[0];
+    acc = 0.0;
+    for (int64_t i = threadIdx.x; i < row_len; i += blockDim.x) { const double dlt = (double)row[i] - mean; acc += dlt * dlt; }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) ssum[wid][1] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < nw; ++i) t += ssum[i][1];
+      const float mu = bc[0], var = (float)(t / (double)(row_len - 1));      // torch.var: unbiased
+      const float six = __fmul_rn(6.0f, var);
+      const float lo = fminf(__fsub_rn(mu, six), 0.0f), hi = fmaxf(__fadd_rn(mu, six), 0.0f);
+      const float d = fmaxf(__fdiv_rn(__fsub_rn(hi, lo), qmax), 1e-8f);
+      delta[blockIdx.x] = d;
+      zp[blockIdx.x] = rintf(__fdiv_rn(-lo, d));
+    }
+    return;
+  }
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = threadIdx.x; i < row_len; i += blockDim.x) {
+    const float v = row[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < nw; ++i) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+    bc[0] = mn; bc[1] = mx;
+  }
+  __syncthreads();
+  mn = bc[0]; mx = bc[1];
+  float d[10], z[10];
+  double sc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float f = (float)(1.0 - (double)i * 0.05);            // python float, cast when it meets the fp32 tensor
+    const float hi = __fmul_rn(mx, f), lo = __fmul_rn(mn, f);
+    d[i] = fmaxf(__fdiv_rn(__fsub_rn(hi, lo), qmax), 1e-8f);
+    z[i] = rintf(__fdiv_rn(-lo, d[i]));
+    sc[i] = 0.0;
+  }
+  for (int64_t e = threadIdx.x; e < row_len; e += blockDim.x) {
+    const float v = row[e];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const float q = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(v, d[i])), z[i]), 0.0f), qmax);
+      const float err = fabsf(__fsub_rn(v, __fmul_rn(__fsub_rn(q, z[i]), d[i])));
+      sc[i] += (double)(METHOD == 1 ? powf(err, 3.5f) : err);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    double a = sc[i];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) ssum[wid][i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float best = 1e+10f;
+    int pick = 0;
+    for (int i = 0; i < 10; ++i) {
+      double t = 0.0;
+      for (int w = 0; w < nw; ++w) t += ssum[w][i];
+      const float score = (float)(t / (double)row_len);
+      if (score < best) { best = score; pick = i; }            // strict: the first of equal scores wins
+    }
+    delta[blockIdx.x] = d[pick];
+    zp[blockIdx.x] = z[pick];
+  }
+}
+
 __device__ __forceinline__ float soft_target_raw(float alpha, float& sig) {
   sig = sigmoid_f(alpha);
   return __fadd_rn(__fmul_rn(sig, kZeta - kGamma), kGamma);  // two roundings, as torch (no FMA)
@@ -292,6 +391,18 @@ extern "C" int nq_uaq_init_max(const float* x, int64_t rows, int64_t row_len, in
   if (!x || !delta || !zero_point || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
   if (n_bits < 2 || n_bits > 8) return NQ_ERR_BAD_ARG;
   uaq_init_max_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, row_len, 1 << n_bits, delta, zero_point);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+extern "C" int nq_uaq_init_search(const float* x, int64_t rows, int64_t row_len, int n_bits, int method, float* delta,
+                                  float* zero_point, void* stream) {
+  if (!x || !delta || !zero_point || rows <= 0 || row_len <= 0) return NQ_ERR_BAD_ARG;
+  if (n_bits < 2 || n_bits > 8 || method < 1 || method > 3) return NQ_ERR_BAD_ARG;
+  cudaStream_t s = as_stream(stream);
+  if (method == 1) uaq_init_search_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, row_len, n_bits, delta, zero_point);
+  else if (method == 2) uaq_init_search_kernel<2><<<(unsigned)rows, 256, 0, s>>>(x, row_len, n_bits, delta, zero_point);
+  else uaq_init_search_kernel<3><<<(unsigned)rows, 256, 0, s>>>(x, row_len, n_bits, delta, zero_point);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

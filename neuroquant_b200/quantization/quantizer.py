@@ -110,13 +110,17 @@ class UniformAffineQuantizer(nn.Module):
         return deq
 
     def init_quantization_scale(self, x: torch.Tensor, channel_wise: bool = False):
-        if self.sym or "max" not in self.scale_method or "scale" in self.scale_method:
-            raise NotImplementedError(f"scale_method={self.scale_method!r} symmetric={self.sym}: only the asymmetric "
-                                      "'max' initialiser is on the calibrate/bit_assign path (readme: --init max)")
+        if self.sym or self.scale_method not in ("max", "mse", "l1", "gaussian"):
+            raise NotImplementedError(f"scale_method={self.scale_method!r} symmetric={self.sym}: the asymmetric 'max', "
+                                      "'mse', 'l1' and 'gaussian' initialisers are provided (quantizer.py:160-222)")
+        if self.scale_method == "max":
+            init = lambda t_, cw: L.uaq_init_max(t_, self.n_bits, cw)  # noqa: E731
+        else:
+            init = lambda t_, cw: L.uaq_init_search(t_, self.n_bits, cw, self.scale_method)  # noqa: E731
         if not channel_wise:
-            d, z = L.uaq_init_max(x.detach().contiguous().float().view(-1), self.n_bits, False)
+            d, z = init(x.detach().contiguous().float().view(-1), False)
             return d.view(()), z.view(())
-        return L.uaq_init_max(x.detach().contiguous().float(), self.n_bits, True)
+        return init(x.detach().contiguous().float(), True)
 
     def bitwidth_refactor(self, refactored_bit: int):
         assert 2 <= refactored_bit <= 8, "bitwidth not supported"

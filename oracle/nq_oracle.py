@@ -91,6 +91,48 @@ def uaq_init_max(x: torch.Tensor, n_bits: int, channel_wise: bool = True):
     return d, z
 
 
+def _scale_search_1(x: torch.Tensor, n_bits: int, method: str):
+    """quantizer.py:170-187 ('mse': L_3.5) and :204-220 ('l1') for one channel / tensor: ten shrinking ranges, the first
+    strictly better score wins; all arithmetic in fp32 tensors (no clamp of the range to zero, unlike 'max')."""
+    eps = torch.tensor(1e-8)
+    n_levels = 2 ** n_bits
+    x_max, x_min = x.max(), x.min()
+    best, delta, zp = 1e+10, None, None
+    for i in range(10):
+        new_max = x_max * (1.0 - (i * 0.05))
+        new_min = x_min * (1.0 - (i * 0.05))
+        d = torch.max((new_max - new_min) / (2 ** n_bits - 1), eps)      # quantize(), quantizer.py:224-231
+        z = (-new_min / d).round()
+        x_q = (torch.clamp(torch.round(x / d) + z, 0, n_levels - 1) - z) * d
+        score = (x - x_q).abs().pow(3.5).mean() if method == "mse" else (x - x_q).abs().mean()
+        if score < best:
+            best, delta, zp = score, d, z
+    return delta, zp
+
+
+def _scale_gaussian_1(x: torch.Tensor, n_bits: int):
+    """quantizer.py:189-202: range mu +- 6 * VARIANCE (sic), clamped to contain zero."""
+    n_levels = 2 ** n_bits
+    mu, sigma = torch.mean(x), torch.var(x)
+    x_min = min(mu - 6 * sigma, 0)
+    x_max = max(mu + 6 * sigma, 0)
+    delta = torch.max(torch.as_tensor((x_max - x_min) / (n_levels - 1), dtype=torch.float32), torch.tensor(1e-8))
+    zp = torch.as_tensor(-x_min / delta, dtype=torch.float32).round()
+    return delta, zp
+
+
+def uaq_init(x: torch.Tensor, n_bits: int, channel_wise: bool, method: str):
+    """init_quantization_scale for scale_method 'max' | 'mse' | 'l1' | 'gaussian', asymmetric (quantizer.py:127-222)."""
+    if method == "max":
+        return uaq_init_max(x, n_bits, channel_wise)
+    one = (lambda t: _scale_gaussian_1(t, n_bits)) if method == "gaussian" else (lambda t: _scale_search_1(t, n_bits, method))
+    if channel_wise and x.dim() == 4:
+        pairs = [one(x[c]) for c in range(x.shape[0])]
+        return (torch.stack([p[0] for p in pairs]).view(-1, 1, 1, 1), torch.stack([p[1] for p in pairs]).view(-1, 1, 1, 1))
+    d, z = one(x)
+    return (d.view(-1), z.view(-1)) if channel_wise else (d, z)
+
+
 def round_ste(x: torch.Tensor) -> torch.Tensor:
     """quantizer.py:53-57."""
     return (x.round() - x).detach() + x

@@ -53,6 +53,49 @@ def test_uaq_kernels_golden(nq, bits, name):
     assert np.abs(dd.cpu().numpy().reshape(want.shape) - want).max() <= tol
 
 
+@pytest.mark.parametrize("method", ["mse", "l1", "gaussian"])
+@pytest.mark.parametrize("bits", [2, 4, 6, 8])
+def test_scale_search_initialisers_golden(nq, method, bits):
+    """'mse' / 'l1' / 'gaussian' scale initialisers (quantizer.py:170-222) against the reference's own
+    UniformAffineQuantizer(scale_method=...) (tests/golden/make_init_golden.py): the search picks the reference's range
+    and the step sizes are bit-exact; the gaussian one within an ulp or two (its mean / variance are reductions)."""
+    L = nq._lib
+    g = load("scale_inits")
+    for name in ("w", "b"):
+        x = dev(t(g[name]))
+        delta, zp = L.uaq_init_search(x, bits, True, method)
+        ref_d, ref_z = g[f"{method}{bits}_{name}_delta"], g[f"{method}{bits}_{name}_zp"]
+        got_d, got_z = delta.cpu().numpy().reshape(ref_d.shape), zp.cpu().numpy().reshape(ref_z.shape)
+        if method == "gaussian":
+            assert np.allclose(got_d, ref_d, rtol=1e-6, atol=0) and np.abs(got_z - ref_z).max() <= 1
+        else:
+            assert np.array_equal(got_d, ref_d), (name, np.abs(got_d - ref_d).max())
+            assert np.array_equal(got_z, ref_z)
+            _, deq = L.fakequant_fwd(x, None, delta, zp, bits, 0)
+            assert np.array_equal(deq.cpu().numpy(), g[f"{method}{bits}_{name}_deq"])
+
+
+def test_quantmodel_with_mse_init(nq):
+    """--init mse end to end: the module binding initialises every layer through the quantiser's own scale_method."""
+    from neuroquant_b200.models import HNeRV
+    from neuroquant_b200.quantization import QuantModel, QuantModule
+    from tests.helpers import TINY_HNERV
+    torch.manual_seed(3)
+    model = HNeRV(TINY_HNERV).cuda()
+    qnn = QuantModel(model, hadamard=False, weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "mse"}).cuda()
+    qnn.set_bitwidth([4] * 7)
+    qnn.eval()
+    qnn.set_quant_state(True)
+    embed = torch.randn(2, 4, 2, 4).cuda()
+    out, _, _ = qnn(embed)
+    assert torch.isfinite(out).all()
+    for m in qnn.model.modules():
+        if isinstance(m, QuantModule):
+            w = m.weight.detach().cpu()
+            d, z = O.uaq_init(w, 4, True, "mse")
+            assert torch.equal(m.weight_quantizer.delta.detach().cpu(), d) and torch.equal(m.weight_quantizer.zero_point.cpu(), z)
+
+
 @pytest.mark.parametrize("bits", [2, 4, 6, 8])
 @pytest.mark.parametrize("name", ["w", "b"])
 def test_adaround_kernels_golden(nq, bits, name):

@@ -235,3 +235,20 @@ def test_regress_decoder_oracle_matches_reference():
     sd1 = {k[4:]: t(g[k]) for k in g.files if k.startswith("sd1/")}
     for st, ref in zip(stages, O.stages_from_state_dict(sd1, TINY_NERV, "nerv")):
         assert float((st.weight - ref.weight).abs().max()) < 2e-6 and float((st.bias - ref.bias).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("method", ["mse", "l1", "gaussian"])
+def test_scale_initialisers_oracle_matches_reference(method):
+    """oracle.uaq_init for the searching / gaussian initialisers against UniformAffineQuantizer(scale_method=...) of the
+    reference (tests/golden/make_init_golden.py): step sizes and zero points of every channel, and the fake-quantised
+    tensor."""
+    g = load("scale_inits")
+    for bits in (2, 4, 6, 8):
+        for name in ("w", "b"):
+            x = t(g[name])
+            d, z = O.uaq_init(x, bits, True, method)
+            ref_d, ref_z = g[f"{method}{bits}_{name}_delta"], g[f"{method}{bits}_{name}_zp"]
+            assert np.array_equal(d.numpy().reshape(ref_d.shape), ref_d), (method, bits, name)
+            assert np.array_equal(z.numpy().reshape(ref_z.shape), ref_z)
+            _, deq = O.uaq_quant(x, d, z, bits)
+            assert np.array_equal(deq.numpy(), g[f"{method}{bits}_{name}_deq"])
