@@ -2,9 +2,10 @@
 (quantization/quantizer.py), backed by the fused libnq_sm100 kernels.
 
 Scope: the uniform-affine quantiser with the 'max' scale initialisation the
-documented commands use (`--init max`), its straight-through forward/backward, and the AdaRound
-'learned_hard_sigmoid' quantiser.  The 'mse' / 'gaussian' / 'l1' initialisers, QATQuantizer, qfn and
-round_noise_ste are not on the path named by the north star and raise NotImplementedError here.
+documented commands use (`--init max`) and the 'mse' / 'l1' / 'gaussian' alternatives (quantizer.py:170-222,
+nq_uaq_init_search), its straight-through forward/backward, and the AdaRound 'learned_hard_sigmoid'
+quantiser.  Symmetric quantisation, QATQuantizer, qfn and round_noise_ste are not on the path named by the
+north star and raise NotImplementedError here.
 """
 import logging
 import time
