@@ -156,10 +156,11 @@ class DecoderRunner:
                 st.set_bits(wq.n_bits)
                 if not wq.inited if hasattr(wq, "inited") else False:
                     # first quantised forward: UniformAffineQuantizer.init_quantization_scale (quantizer.py:112-115)
-                    d, z = wq.init_quantization_scale(st.w_src, True)  # 'max' | 'mse' | 'l1' | 'gaussian' (--init)
+                    # 'max' | 'mse' | 'l1' | 'gaussian' (--init); per channel or per tensor (--channel_wise)
+                    d, z = wq.init_quantization_scale(st.w_src, wq.channel_wise)
                     wq.delta, wq.zero_point, wq.inited = nn.Parameter(d), z, True
                 if not bq.inited if hasattr(bq, "inited") else False:
-                    d, z = bq.init_quantization_scale(st.bias, True)
+                    d, z = bq.init_quantization_scale(st.bias, bq.channel_wise)
                     bq.delta, bq.zero_point, bq.inited = nn.Parameter(d), z, True
                 st.delta_w, st.zp_w = wq.delta.data, wq.zero_point
                 st.delta_b, st.zp_b = bq.delta.data, bq.zero_point

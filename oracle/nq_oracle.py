@@ -326,10 +326,12 @@ class QStage:
 
 
 class QuantDecoder:
-    """Functional stand-in for QuantModel(model, hadamard, {'channel_wise': True, 'max'})."""
+    """Functional stand-in for QuantModel(model, hadamard, {'channel_wise': channel_wise, 'max'}).  channel_wise=False
+    (the command line without --channel_wise): one scalar step size per tensor, shape () as quantizer.py:160-168 makes it."""
 
-    def __init__(self, stages: Sequence[Stage], bits: Sequence[int], hadamard: bool):
+    def __init__(self, stages: Sequence[Stage], bits: Sequence[int], hadamard: bool, channel_wise: bool = True):
         assert len(bits) == len(stages)
+        self.channel_wise = channel_wise
         self.q: List[QStage] = []
         for st, nb in zip(stages, bits):
             assert 2 <= nb <= 8  # quantizer.py:96,237
@@ -353,8 +355,8 @@ class QuantDecoder:
     def init_scales(self):
         """First quantised forward: quantizer.py:112-115 on what quant_layer.py:70-74 feeds it."""
         for q in self.q:
-            q.delta_w, q.zp_w = uaq_init_max(q.w_src, q.n_bits, True)
-            q.delta_b, q.zp_b = uaq_init_max(q.stage.bias, q.n_bits, True)
+            q.delta_w, q.zp_w = uaq_init_max(q.w_src, q.n_bits, self.channel_wise)
+            q.delta_b, q.zp_b = uaq_init_max(q.stage.bias, q.n_bits, self.channel_wise)
 
     def start_adaround(self):
         """calib_model.py:169-184 + quantizer.py:259-319."""

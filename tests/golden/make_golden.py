@@ -118,7 +118,7 @@ class ListLoader(list):
     """Stand-in for the DataLoader `gt` of model_reconstruction: len() + iteration of dicts."""
 
 
-def run_model_case(tag, arch, cfg, bits, hadamard, iters, n_frames=8, bsz=2, omega=True, only_layers=False):
+def run_model_case(tag, arch, cfg, bits, hadamard, iters, n_frames=8, bsz=2, omega=True, only_layers=False, channel_wise=True):
     torch.manual_seed(903)
     model = (models.HNeRV if arch == "hnerv" else models.NeRV)(cfg)
     with torch.no_grad():  # non-degenerate random decoder weights (default init is fine) + biases
@@ -145,7 +145,8 @@ def run_model_case(tag, arch, cfg, bits, hadamard, iters, n_frames=8, bsz=2, ome
 
     fp_model = copy.deepcopy(model)
     qnn = quantization.QuantModel(model=model, hadamard=hadamard,
-                                  weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"})
+                                  weight_quant_params={"n_bits": 8, "channel_wise": channel_wise, "scale_method": "max"})
+    out["channel_wise"] = np.array(channel_wise)
     out["avg_bits"] = np.array(qnn.set_bitwidth(bits), dtype=np.float64)
     qnn.eval()
     qnn.set_quant_state(True)
@@ -256,8 +257,12 @@ def bookkeeping():
 
 
 if __name__ == "__main__":
-    quantizer_kats()
-    bookkeeping()
+    if not sys.argv[1:]:
+        quantizer_kats()
+        bookkeeping()
+    if sys.argv[1:] == ["layerwise"]:  # per-tensor scales (the command line without --channel_wise): tiny_hnerv_lw.npz only
+        run_model_case("tiny_hnerv_lw", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, iters=80, omega=False, channel_wise=False)
+        sys.exit(0)
     if sys.argv[1:] == ["sens_layers"]:  # only the per-layer sensitivity side files (tiny_*_sens_layers.npz)
         run_model_case("tiny_hnerv", "hnerv", TINY_HNERV, [6, 5, 4, 5, 5, 6, 6], False, iters=80, only_layers=True)
         run_model_case("tiny_hnerv_had", "hnerv", TINY_HNERV, [4, 5, 4, 6, 5, 6, 8], True, iters=80, only_layers=True)

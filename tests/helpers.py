@@ -27,6 +27,15 @@ CASES = {
 
 
 # block-wise reconstruction fixtures (tests/golden/make_block_golden.py)
+# per-tensor scales (the command line without --channel_wise); fixture from `make_golden.py layerwise`
+LW_CASES = {"tiny_hnerv_lw": ("hnerv", TINY_HNERV)}
+
+
+def cw(g) -> bool:
+    """channel_wise flag of a model fixture (older fixtures predate the key: per-channel)."""
+    return bool(g["channel_wise"]) if "channel_wise" in g.files else True
+
+
 BLOCK_CASES = {
     "block_tiny_hnerv": ("hnerv", TINY_HNERV),
     "block_tiny_hnerv_qdrop": ("hnerv", TINY_HNERV),
@@ -58,7 +67,7 @@ def t(a):
 
 
 def case_stages(tag):
-    arch, cfg = CASES[tag]
+    arch, cfg = CASES[tag] if tag in CASES else LW_CASES[tag]
     g = load(tag)
     sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
     return g, arch, cfg, O.stages_from_state_dict(sd, cfg, arch)

@@ -7,14 +7,14 @@ import pytest
 import torch
 
 from oracle import nq_oracle as O
-from tests.helpers import CASES, load, t
+from tests.helpers import CASES, LW_CASES, cw, load, t
 
 pytestmark = pytest.mark.gpu
 
 
 def build_model(tag):
     from neuroquant_b200.models import HNeRV, NeRV
-    arch, cfg = CASES[tag]
+    arch, cfg = CASES[tag] if tag in CASES else LW_CASES[tag]
     g = load(tag)
     model = (HNeRV if arch == "hnerv" else NeRV)(cfg)
     sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}
@@ -34,14 +34,14 @@ def loader_for(g):
                        for idx in g["order"].tolist()])
 
 
-@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("tag", list(CASES) + list(LW_CASES))
 def test_quantmodel_matches_reference(tag):
     from neuroquant_b200.quantization import QuantModel, QuantModule
     g, arch, cfg, model = build_model(tag)
     cali = t(g["cali"]).cuda()
     out, embed_list, dec_time = model.decode(cali[:2])
     assert np.abs(out.cpu().numpy() - g["fp_out"]).max() < 2e-5 and dec_time > 0 and embed_list[0] is cali[:2] or True
-    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": True,
+    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": cw(g),
                                                                                 "scale_method": "max"}).cuda()
     assert qnn.set_bitwidth(g["bits"].tolist()) == float(g["avg_bits"])
     qnn.set_quant_state(True)
@@ -105,7 +105,7 @@ def test_standalone_module_and_quantizer_autograd():
         QuantModule(torch.nn.Linear(3, 3))
 
 
-@pytest.mark.parametrize("tag", ["tiny_hnerv", "tiny_nerv_had"])
+@pytest.mark.parametrize("tag", ["tiny_hnerv", "tiny_nerv_had", "tiny_hnerv_lw"])
 def test_model_reconstruction_and_checkpoint(tag, tmp_path):
     """calibrate_network.py flow on the golden tiny net: quantised forward initialises scales, then
     model_reconstruction (80 iterations in the injected batch order), then the whole-object checkpoint."""
@@ -113,7 +113,7 @@ def test_model_reconstruction_and_checkpoint(tag, tmp_path):
     from neuroquant_b200.quantization.quantizer import AdaRoundQuantizer
     g, arch, cfg, model = build_model(tag)
     cali, frames = t(g["cali"]).cuda(), t(g["frames"])
-    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": True,
+    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": cw(g),
                                                                                 "scale_method": "max"}).cuda()
     qnn.set_bitwidth(g["bits"].tolist())
     qnn.set_quant_state(True)

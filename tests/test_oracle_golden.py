@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import nq_oracle as O
-from tests.helpers import CASES, case_stages, load, t, BLOCK_CASES, LAYER_CASES, block_case
+from tests.helpers import CASES, LW_CASES, case_stages, cw, load, t, BLOCK_CASES, LAYER_CASES, block_case
 
 
 def test_fwht_matches_scipy():
@@ -101,13 +101,13 @@ def test_bookkeeping_golden():
         assert num / den == float(g[key])
 
 
-@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("tag", list(CASES) + list(LW_CASES))
 def test_decode_and_init_golden(tag):
     g, arch, cfg, stages = case_stages(tag)
     cali = t(g["cali"])
     out, feats = O.decode(stages, cali[:2], keep=True)
     assert np.allclose(out.numpy(), g["fp_out"], atol=1e-6)
-    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]))
+    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]), channel_wise=cw(g))
     assert qd.avg_bits() == float(g["avg_bits"])
     for i, q in enumerate(qd.q):
         assert np.array_equal(q.delta_w.numpy(), g[f"init/{i}/delta_w"])
@@ -133,11 +133,11 @@ def test_omega_golden(tag):
     assert om == pytest.approx(float(g["omega"]), rel=2e-3, abs=1e-12)
 
 
-@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("tag", list(CASES) + list(LW_CASES))
 def test_calibration_golden(tag):
     """80 iterations (4 step-size + 76 AdaRound... per calib_model.py:144,205) on the fixed batch order."""
     g, arch, cfg, stages = case_stages(tag)
-    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]))
+    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]), channel_wise=cw(g))
     log = []
     O.model_reconstruction(qd, t(g["cali"]), t(g["frames"]), g["order"].tolist(), iters=80, weight=0.01,
                            b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003, log=log)
