@@ -41,9 +41,11 @@ class BlockStep:
         dev = stage.weight.device
         self.stage, self.n, self.h, self.w = stage, n, h, w
         cin_p = _pad(g.cin, 16)
-        cg = _pad(g.c_grp, 16)
+        # nothing consumes the block's output as a K operand here, so its channel group only needs 16-byte stores (8)
+        # as long as the GEMM's N = sub-pixels x group stays a multiple of 16 (HNeRV-3M block 5: 37 -> 40, N = 160)
+        cg = _pad(g.c_grp, 8)
         if (g.rh * g.rw * cg) % 16:
-            raise NotImplementedError("block output channels cannot be padded to a multiple of 16 GEMM columns")
+            cg = _pad(g.c_grp, 16)
         act = _ACT[g.act]
         self.d = L.ConvDesc(n, h, w, g.cin, cin_p, g.k, g.cout, g.rh, g.rw, g.c_grp, cg, _ACT_SAVED_GRAD if act == 1 else act)
         self.H, self.W, self.cg, self.cin_p = h * g.rh, w * g.rw, cg, cin_p
