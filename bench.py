@@ -32,8 +32,8 @@ HYPER = dict(weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003, iters=21
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hnerv-bunny-3m")
     ap.add_argument("--batch", type=int, default=2, help="frames per GPU per iteration")
