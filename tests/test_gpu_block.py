@@ -173,3 +173,43 @@ def test_fisher_block_step_against_autograd(mode, conv):
     for name, a_, b_ in (("dW", step2.gw, wq.grad), ("db", step2.gb, bq.grad)):
         tol = 2e-4 * float(b_.abs().max()) + 1e-12
         assert float((a_ - b_).abs().max()) <= tol, (name, float((a_ - b_).abs().max()), tol)
+
+
+@pytest.mark.parametrize("conv", ["tc", "simt"])
+def test_output_gradient_cache_every_block_and_layer(conv, monkeypatch):
+    """GetLayerGrad (data_utils.py:222-258) for EVERY block (the last one's consumer is the head) and every lone layer
+    (stem and head included) against the oracle's block_grad_cache, which is pinned to the reference's raw hook
+    gradients on the fixtures."""
+    monkeypatch.setenv("NQ_CONV", conv)
+    import neuroquant_b200.quantization.calib_block as cb
+    from neuroquant_b200.quantization import QuantModule
+    from neuroquant_b200.quantization.quantizer import AdaRoundQuantizer
+    from neuroquant_b200.runner import DecoderRunner
+    from tests.helpers import block_case
+    tag = "block_tiny_hnerv"
+    g, arch, cfg, stages = block_case(tag)
+    cali = t(g["cali"])[:3]
+    n_stage = len(stages)
+    for k, layer in [(k, False) for k in range(1, n_stage - 1)] + [(k, True) for k in (0, 2, n_stage - 1)]:
+        _, qnn = build(tag)
+        runner = DecoderRunner.of(qnn.model)
+        convs = [m for m in qnn.model.modules() if isinstance(m, QuantModule)]
+        conv_k = convs[k]
+        block = conv_k if layer else qnn.model.decoder[k]
+        qnn.set_quant_state(False)
+        block.set_quant_state(True)
+        conv_k.weight_quantizer = AdaRoundQuantizer(uaq=conv_k.weight_quantizer, round_mode="learned_hard_sigmoid",
+                                                    weight_tensor=conv_k.org_weight.data)
+        conv_k.bias_quantizer = AdaRoundQuantizer(uaq=conv_k.bias_quantizer, round_mode="learned_hard_sigmoid",
+                                                  weight_tensor=conv_k.bias.data)
+        conv_k.weight_quantizer.soft_targets = conv_k.bias_quantizer.soft_targets = True
+        runner._key = None
+        got = cb.block_output_grads(qnn, runner, block, k, cali.cuda(), layer).cpu()
+        qd = O.QuantDecoder(stages, g["bits"].tolist(), False)
+        q = qd.q[k]
+        q.delta_w, q.zp_w = O.fp16_round(q.delta_w), O.fp16_round(q.zp_w)
+        q.delta_b, q.zp_b = O.fp16_round(q.delta_b), O.fp16_round(q.zp_b)
+        q.alpha_w, q.alpha_b = O.adaround_init_alpha(q.stage.weight, q.delta_w), O.adaround_init_alpha(q.stage.bias, q.delta_b)
+        want = O.block_grad_cache(qd, k, cali, raw=True, layer=layer)
+        assert got.shape == want.shape, (k, layer)
+        assert float((got - want).abs().max()) <= 1e-2 * float(want.abs().max()), (k, layer, float((got - want).abs().max()), float(want.abs().max()))
