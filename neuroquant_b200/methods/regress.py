@@ -7,7 +7,7 @@ convolutions that hold all of NeRV's and nearly all of HNeRV's training FLOPs --
 gradient / weight gradient kernels as the calibration loop, with the engine in full-precision mode, and its Adam steps are
 CUDA kernels of the library.  HNeRV's ConvNeXt frame encoder stays stock PyTorch (as everywhere in this package): the
 engine hands back dL/d(embedding) and autograd carries it through the encoder, whose parameters step in a torch Adam
-at the same learning rate.  Losses other than 'l2' (SSIM mixtures) are not provided.
+at the same learning rate.  Losses: 'l2' and 'l1'; the SSIM mixtures are not provided.
 """
 from __future__ import annotations
 
@@ -30,8 +30,12 @@ class DecoderTrainer:
     """One model's training state: the engine binding, a fused Adam over the decoder's (weight, bias) tensors and, for
     HNeRV, a torch Adam over the encoder.  `param_groups` makes it acceptable to utils.adjust_lr."""
 
-    def __init__(self, model, arch: str, lr: float):
+    def __init__(self, model, arch: str, lr: float, loss: str = "l2"):
+        if loss not in ("l2", "l1"):
+            raise NotImplementedError(f"loss {loss!r}: 'l2' and 'l1' run on the fused head kernel (utils.py:115-118); the "
+                                      "SSIM mixtures are not provided")
         self.model, self.arch = model, arch
+        self.p_norm = 2.0 if loss == "l2" else 1.0
         self.runner = DecoderRunner.of(model)
         if any(self.runner._quant):
             raise ValueError("regression training takes the full-precision model, not a QuantModel")
@@ -53,7 +57,7 @@ class DecoderTrainer:
                 embed = self.model.encode(inputs)
         self.runner.sync()
         n, _, hh, ww = frames.shape
-        img = eng.forward(embed.detach(), train=True, target=frames, p_norm=2.0, mean_pixels=float(n * 3 * hh * ww),
+        img = eng.forward(embed.detach(), train=True, target=frames, p_norm=self.p_norm, mean_pixels=float(n * 3 * hh * ww),
                           reuse_weights=True)
         loss = eng.last_loss().clone()
         flat = eng.backward()
@@ -80,8 +84,8 @@ def train(args, cfg):
     rank, world, _ = init_distributed()
     if world > 1:
         raise NotImplementedError("regression training is single-GPU, as in the reference")
-    if cfg["loss"] != "l2":
-        raise NotImplementedError(f"loss {cfg['loss']!r}: only 'l2' runs on the fused head kernel")
+    if cfg["loss"] not in ("l2", "l1"):
+        raise NotImplementedError(f"loss {cfg['loss']!r}: only 'l2' / 'l1' run on the fused head kernel")
     device = "cuda"
     full_dataset = VideoDataSet(cfg, args)
     full_loader = torch.utils.data.DataLoader(full_dataset, batch_size=cfg["batch_size"], shuffle=False, num_workers=cfg["workers"],
@@ -111,7 +115,7 @@ def train(args, cfg):
         logging.info(f"best_pred_seen_psnr: {RoundTensor(results[0].max(), 2)} | ")
         return
     args.lr = cfg["learning_rate"]
-    trainer = DecoderTrainer(model, args.arch, args.lr)
+    trainer = DecoderTrainer(model, args.arch, args.lr, cfg["loss"])
     start = datetime.now()
     for epoch in range(cfg["epoch"]):
         model.train()

@@ -629,7 +629,7 @@ def adjust_lr(base_lr: float, cur_epoch: float, lr_type: str, eta_min: float = 0
 
 
 def regress_decoder(stages: Sequence[Stage], embeds: torch.Tensor, frames: torch.Tensor, order: Sequence[Sequence[int]],
-                    epochs: int, lr: float, lr_type: str = "cosine_0.1_1_0.1", log: Optional[list] = None):
+                    epochs: int, lr: float, lr_type: str = "cosine_0.1_1_0.1", log: Optional[list] = None, loss_type: str = "l2"):
     """The training loop of regress.py:249-271 for a decoder fed with FIXED embeddings (NeRV: positional encoding), loss
     'l2' (utils.py:115-116: per-frame mean over C*H*W, then the batch mean), Adam defaults, lr set per step by adjust_lr.
     order: the mini-batches of all epochs, in sequence (len(order) / epochs steps per epoch).  Updates `stages` in place."""
@@ -644,7 +644,8 @@ def regress_decoder(stages: Sequence[Stage], embeds: torch.Tensor, frames: torch
             gr["lr"] = cur_lr
         idx = torch.as_tensor(idx)
         out = decode(stages, embeds[idx], ws, bs)
-        loss = F.mse_loss(out, frames[idx], reduction="none").flatten(1).mean(1).mean()
+        per = F.mse_loss if loss_type == "l2" else F.l1_loss     # utils.py:115-118
+        loss = per(out, frames[idx], reduction="none").flatten(1).mean(1).mean()
         opt.zero_grad()
         loss.backward()
         opt.step()

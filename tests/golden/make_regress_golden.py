@@ -26,14 +26,14 @@ from make_golden import TINY_HNERV, TINY_NERV, npy  # noqa: E402
 torch.set_num_threads(8)
 
 
-def run_case(tag, arch, cfg, epochs=3, n_frames=6, bsz=2, lr=2e-3, lr_type="cosine_0.1_1_0.1"):
+def run_case(tag, arch, cfg, epochs=3, n_frames=6, bsz=2, lr=2e-3, lr_type="cosine_0.1_1_0.1", loss="l2"):
     torch.manual_seed(903)
     model = (models.HNeRV if arch == "hnerv" else models.NeRV)(cfg)
     g = torch.Generator().manual_seed(11)
     frames = torch.rand(n_frames, 3, cfg["crop_h"], cfg["crop_w"], generator=g)
     norm_idx = torch.arange(n_frames).float() / n_frames
     out = {"frames": npy(frames), "norm_idx": npy(norm_idx), "epochs": np.array(epochs), "bsz": np.array(bsz), "lr": np.array(lr),
-           "lr_type": np.array(lr_type)}
+           "lr_type": np.array(lr_type), "loss_type": np.array(loss)}
     for k, v in model.state_dict().items():
         out["sd0/" + k] = npy(v)
     if arch == "nerv":
@@ -51,7 +51,7 @@ def run_case(tag, arch, cfg, epochs=3, n_frames=6, bsz=2, lr=2e-3, lr_type="cosi
             cur_lr = adjust_lr(optimizer, cur_epoch, args)
             img = frames[idx]
             img_out, _, _ = model(img) if arch == "hnerv" else model(norm_idx[idx])
-            final_loss = loss_fn(img_out, img, "l2")
+            final_loss = loss_fn(img_out, img, loss)
             optimizer.zero_grad()
             final_loss.backward()
             optimizer.step()
@@ -67,3 +67,4 @@ def run_case(tag, arch, cfg, epochs=3, n_frames=6, bsz=2, lr=2e-3, lr_type="cosi
 if __name__ == "__main__":
     run_case("regress_tiny_nerv", "nerv", TINY_NERV)
     run_case("regress_tiny_hnerv", "hnerv", TINY_HNERV)
+    run_case("regress_tiny_nerv_l1", "nerv", TINY_NERV, loss="l1", lr_type="hybrid_0.2_1_2_0.1_0.05")

@@ -12,7 +12,8 @@ from tests.helpers import TINY_HNERV, TINY_NERV, load, t
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("tag,arch,cfg", [("regress_tiny_nerv", "nerv", TINY_NERV), ("regress_tiny_hnerv", "hnerv", TINY_HNERV)])
+@pytest.mark.parametrize("tag,arch,cfg", [("regress_tiny_nerv", "nerv", TINY_NERV), ("regress_tiny_hnerv", "hnerv", TINY_HNERV),
+                                          ("regress_tiny_nerv_l1", "nerv", TINY_NERV)])
 @pytest.mark.parametrize("conv", ["tc", "simt"])
 def test_regression_training_matches_reference(tag, arch, cfg, conv, monkeypatch):
     monkeypatch.setenv("NQ_CONV", conv)
@@ -29,7 +30,7 @@ def test_regression_training_matches_reference(tag, arch, cfg, conv, monkeypatch
     epochs, order = int(g["epochs"]), g["order"]
     per_epoch = len(order) // epochs
     args = SimpleNamespace(lr=float(g["lr"]), lr_type=str(g["lr_type"]))
-    trainer = DecoderTrainer(model, arch, args.lr)
+    trainer = DecoderTrainer(model, arch, args.lr, str(g["loss_type"]) if "loss_type" in g.files else "l2")
     losses, lrs, psnrs = [], [], []
     for it, idx in enumerate(order):
         epoch, i = divmod(it, per_epoch)

@@ -220,16 +220,17 @@ def test_packed_code_stream_statement(bits):
         assert O.pack_codes_np([1, 2, 3, 4, 5, 6, 7, 0], 3).tolist() == [0xD1, 0x58, 0x1F]
 
 
-def test_regress_decoder_oracle_matches_reference():
+@pytest.mark.parametrize("tag", ["regress_tiny_nerv", "regress_tiny_nerv_l1"])
+def test_regress_decoder_oracle_matches_reference(tag):
     """oracle.regress_decoder / adjust_lr against the reference's model, loss_fn, adjust_lr and torch Adam replayed on
     seeded frames (tests/golden/make_regress_golden.py): learning rates, loss per step, final decoder weights."""
     from tests.helpers import TINY_NERV
-    g = load("regress_tiny_nerv")
+    g = load(tag)
     sd = {k[4:]: t(g[k]) for k in g.files if k.startswith("sd0/")}
     stages = O.stages_from_state_dict(sd, TINY_NERV, "nerv")
     log = []
     O.regress_decoder(stages, t(g["embed"]), t(g["frames"]), g["order"].tolist(), int(g["epochs"]), float(g["lr"]),
-                      str(g["lr_type"]), log=log)
+                      str(g["lr_type"]), log=log, loss_type=str(g["loss_type"]))
     assert np.allclose([r[1] for r in log], g["lr_seq"], rtol=1e-12)
     assert np.allclose([r[0] for r in log], g["loss"], rtol=1e-5)
     sd1 = {k[4:]: t(g[k]) for k in g.files if k.startswith("sd1/")}
