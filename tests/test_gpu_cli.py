@@ -70,3 +70,40 @@ def _args(mod, cfg_path, data, ckpt, mode):
     cfg = get_config(cfg_path)
     args.outf = os.path.join("results", args.outf, "x_" + mode)
     return args, cfg
+
+
+def test_calibrate_network_cli_mse_init_layerwise_scales(tmp_path, monkeypatch):
+    """--init mse without --channel_wise: per-tensor scales from the range search, checkpoint suffix LW."""
+    from neuroquant_b200.methods import calibrate_network
+    data, cfg_path, ckpt = make_clip(tmp_path, TINY_HNERV, "hnerv")
+    monkeypatch.chdir(tmp_path)
+    calibrate_network.main(["--config", cfg_path, "--arch", "hnerv", "--data_path", data, "--vid", "Clip", "--batch_size", "2",
+                            "--precision", "6", "5", "4", "5", "5", "6", "6", "--init", "mse", "--iters_w", "40", "--weight", "0.01",
+                            "--b_start", "20", "--b_end", "2", "--warmup", "0.2", "--lr", "0.003", "--ckpt", ckpt, "--outf", "t"])
+    files = glob.glob(os.path.join("results", "t", "**", "hnerv_W*_prob1.0_mse-init_LW.pth"), recursive=True)
+    assert len(files) == 1
+    qnn = torch.load(files[0], weights_only=False)
+    from neuroquant_b200.quantization import QuantModule
+    mods = [m for m in qnn.modules() if isinstance(m, QuantModule)]
+    assert all(m.weight_quantizer.delta.numel() == 1 for m in mods)  # one step size per tensor
+    assert all(torch.equal(c, c.round()) for c in qnn.get_quantized_param()[0::2])
+
+
+@pytest.mark.parametrize("arch,cfg", [("nerv", TINY_NERV), ("hnerv", TINY_HNERV)])
+def test_regress_cli_trains_and_writes_reference_checkpoints(tmp_path, monkeypatch, arch, cfg):
+    """methods/regress.py: three epochs on the tiny clip; the loss falls, the checkpoints are plain state_dicts with the
+    reference's keys, and the calibration command line starts from them."""
+    from neuroquant_b200.methods import regress
+    data, cfg_path, _ = make_clip(tmp_path, cfg, arch)
+    monkeypatch.chdir(tmp_path)
+    regress.main(["--config", cfg_path, "--arch", arch, "--data_path", data, "--vid", "Clip", "--outf", "r", "-p", "1"])
+    ck = glob.glob(os.path.join("results", "r", "**", "epoch3.pth"), recursive=True)
+    latest = glob.glob(os.path.join("results", "r", "**", "model_latest.pth"), recursive=True)
+    assert len(ck) == 1 and len(latest) == 1
+    sd = torch.load(ck[0], map_location="cpu")
+    assert "decoder.0.weight" in sd and "decoder.1.conv.0.weight" in sd and "head_layer.bias" in sd
+    assert ("encoder.downsample_layers.0.0.weight" in sd) == (arch == "hnerv") or arch == "nerv"
+    text = open(glob.glob(os.path.join(os.path.dirname(ck[0]), "*.log"))[0]).read()
+    psnrs = [float(l.split("pred_PSNR:")[1].split()[0].strip(",")) for l in text.splitlines() if "pred_PSNR:" in l]
+    assert len(psnrs) >= 6 and psnrs[-1] > psnrs[0]          # it learns
+    assert "Training complete in" in text
