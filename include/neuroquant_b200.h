@@ -416,6 +416,13 @@ int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int h, int w, i
 int nq_block_loss_bwd(const void* y_split, const float* tgt, const int32_t* frame_idx, const float* gprime, int n, int h, int w,
                       int rh, int rw, int cg, float p, float grad_scale, float* loss_sum, void* dz_split, void* stream);
 
+/* Mini-batch assembly of block_reconstruction (calib_block.py:160-164: cached_inps[0][idx], cached_inps[1][idx] and
+ * torch.where(torch.rand_like(cur_inp) < input_prob, cur_inp, cur_sym)) on the HBM-resident caches.  inp_split / sym_split:
+ * (2, n_cache, frame_elems) split-bf16 caches (sym_split and rnd NULL: plain gather, input_prob = 1); frame_idx: n device
+ * ints; rnd: (n, frame_elems) uniform draws in the batch's own layout; out_split (2, n, frame_elems). */
+int nq_qdrop_gather(const void* inp_split, const void* sym_split, const int32_t* frame_idx, const float* rnd, float input_prob,
+                    int n, int n_cache, int64_t frame_elems, void* out_split, void* stream);
+
 /* Fisher-weighted block losses (LossFunction.__call__, calib_block.py:66-72) on the layouts of nq_block_loss_bwd.
  * fisher: the cached |dL/d(block output)| + 1 (save_grad_data, data_utils.py:91-119), fp32 NHWC (N, h*rh, w*rw, cg) like
  * the target cache and addressed through the same frame_idx.

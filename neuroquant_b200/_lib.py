@@ -143,6 +143,7 @@ def _load():
         "nq_lp_loss": (I, [P, P, L, F, F, P, P, P]),
         "nq_block_loss_bwd": (I, [P, P, P, P, I, I, I, I, I, I, F, F, P, P, P]),
         "nq_block_loss_bwd_fisher": (I, [P, P, P, P, P, I, I, I, I, I, I, I, F, P, P, P, P]),
+        "nq_qdrop_gather": (I, [P, P, P, P, F, I, I, L, P, P]),
         "nq_multi_dot": (I, [P, P, P, I, I, P, P]),
         "nq_psnr": (I, [P, P, I, L, P, P]),
     }

@@ -374,6 +374,62 @@ __global__ void __launch_bounds__(256) block_loss_bwd_kernel(const uint4* __rest
 }  // namespace nq
 
 // ---------------------------------------------------------------------------------------------
+// Mini-batch assembly of block-wise reconstruction (calib_block.py:160-164): gather the batch's frames from the
+// HBM-resident split-bf16 input cache and, with QDrop, take each element from the quantised-predecessor cache or the
+// full-precision one according to a uniform draw -- one pass instead of four frame copies + compare + where.
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) qdrop_gather_kernel(const uint4* __restrict__ inp_hi, const uint4* __restrict__ inp_lo,
+                                                           const uint4* __restrict__ sym_hi, const uint4* __restrict__ sym_lo,
+                                                           const int* __restrict__ frame_idx, const float4* __restrict__ rnd,
+                                                           float prob, int n, int frame8, uint4* __restrict__ out_hi,
+                                                           uint4* __restrict__ out_lo) {
+  const int total = n * frame8;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int b = e / frame8, f = e - b * frame8;
+    const size_t src = (size_t)frame_idx[b] * frame8 + f;
+    uint4 h = inp_hi[src], l = inp_lo[src];
+    if (sym_hi != nullptr) {
+      const float4 r0 = rnd[2 * (size_t)e], r1 = rnd[2 * (size_t)e + 1];
+      const uint4 sh = sym_hi[src], sl = sym_lo[src];
+      const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+      const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w}, slw[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // torch.where(rand < input_prob, cur_inp, cur_sym): per 16-bit half of each word
+        const uint32_t m = (rv[2 * k] < prob ? 0x0000FFFFu : 0u) | (rv[2 * k + 1] < prob ? 0xFFFF0000u : 0u);
+        hw[k] = (hw[k] & m) | (shw[k] & ~m);
+        lw[k] = (lw[k] & m) | (slw[k] & ~m);
+      }
+      h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    out_hi[e] = h;
+    out_lo[e] = l;
+  }
+}
+}  // namespace nq
+
+extern "C" int nq_qdrop_gather(const void* inp_split, const void* sym_split, const int32_t* frame_idx, const float* rnd,
+                               float input_prob, int n, int n_cache, int64_t frame_elems, void* out_split, void* stream) {
+  if (!inp_split || !frame_idx || !out_split || n <= 0 || n_cache <= 0 || frame_elems <= 0) return NQ_ERR_BAD_ARG;
+  if ((sym_split != nullptr) != (rnd != nullptr)) return NQ_ERR_BAD_ARG;
+  if (frame_elems % 8 || (int64_t)n * frame_elems / 8 >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;
+  const uint16_t* ih = reinterpret_cast<const uint16_t*>(inp_split);
+  const uint16_t* sh = reinterpret_cast<const uint16_t*>(sym_split);
+  uint16_t* oh = reinterpret_cast<uint16_t*>(out_split);
+  const int64_t cache_plane = (int64_t)n_cache * frame_elems, out_plane = (int64_t)n * frame_elems;
+  qdrop_gather_kernel<<<grid_for(out_plane / 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(ih), reinterpret_cast<const uint4*>(ih + cache_plane),
+      sh ? reinterpret_cast<const uint4*>(sh) : nullptr, sh ? reinterpret_cast<const uint4*>(sh + cache_plane) : nullptr, frame_idx,
+      reinterpret_cast<const float4*>(rnd), input_prob, n, (int)(frame_elems / 8), reinterpret_cast<uint4*>(oh),
+      reinterpret_cast<uint4*>(oh + out_plane));
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fisher-weighted block losses (calib_block.py:66-72) on the same layouts.  F = cached |dL/dy| + 1 (data_utils.py:113),
 // fp32 NHWC like the target cache and addressed through the same frame_idx.
 //   MODE 1  fisher_diag : loss += sum d^2 F^2,               dy = 2 d F^2

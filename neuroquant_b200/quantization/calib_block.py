@@ -187,6 +187,20 @@ def nhwc_cache(step: BlockStep, t_: torch.Tensor) -> torch.Tensor:
     return o
 
 
+def assemble_batch(inp_s: torch.Tensor, sym_s, idx_dev: torch.Tensor, input_prob: float, out: torch.Tensor) -> int:
+    """calib_block.py:160-164 in one launch: out[:, b] = inp_s[:, idx[b]], and with QDrop (input_prob < 1) each element is
+    taken from inp_s where torch.rand_like(cur_inp) < input_prob, else from sym_s.  The uniform draw stays torch's (one
+    call per iteration, as in the reference), in the batch's own (n, h, w, cin_p) layout."""
+    n = out.shape[1]
+    frame = out[0, 0].numel()
+    rnd = None
+    if input_prob < 1.0:
+        rnd = torch.rand_like(out[0], dtype=torch.float32)
+    L.check(L.lib.nq_qdrop_gather(inp_s.data_ptr(), sym_s.data_ptr() if rnd is not None else None, idx_dev.data_ptr(), L.ptr(rnd),
+                                  float(input_prob), n, inp_s.shape[1], frame, out.data_ptr(), L.stream()), "nq_qdrop_gather")
+    return 2 if rnd is not None else 1
+
+
 def gather_frames(cache: torch.Tensor, idx_host, out: torch.Tensor):
     """out[:, b] = cache[:, idx[b]]: whole frames are contiguous, so this is one plain copy per plane and frame (advanced
     indexing would run an element-wise gather kernel over 2-byte elements)."""
@@ -326,22 +340,18 @@ def _reconstruct(model, block, conv, layer_mode: bool, cali_data, batch_size, it
     inp_s, sym_s, out_c = cache_to_engine_layout(step, cached_inps, cached_sym if input_prob < 1.0 else None, cached_outs)
     grad_c = nhwc_cache(step, cached_grads) if cached_grads is not None else None
     cur = torch.empty_like(inp_s[:, :bsz])
-    alt = torch.empty_like(cur) if input_prob < 1.0 else None
     for i in range(iters):
         idx_h = torch.randperm(n_cached)[:batch_size]
-        idx = idx_h.to(cached_inps.device)
-        gather_frames(inp_s, idx_h, cur)
-        if input_prob < 1.0:  # QDrop (calib_block.py:163-164); one draw per element, shared by the hi and lo planes
-            keep = torch.rand_like(cur[0], dtype=torch.float32) < input_prob
-            gather_frames(sym_s, idx_h, alt)
-            torch.where(keep.unsqueeze(0), cur, alt, out=cur)
+        idx = idx_h.to(cached_inps.device).int()
+        # gather + QDrop (calib_block.py:160-164); one draw per element, shared by the hi and lo planes
+        assemble_batch(inp_s, sym_s, idx, input_prob, cur)
         count = i + 1
         b = decay(count)
         # calib_layer.py:38-46: collect_round_loss walks the CHILDREN of the module it is given; a lone QuantModule has
         # none that is a QuantModule, so the layer-wise variant never sees the regulariser
         reg_on = not (count < loss_start) and not layer_mode
         want_log = count % 500 == 0
-        step.run_cached(cur, out_c, idx.int(), weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
+        step.run_cached(cur, out_c, idx, weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
                         want_reg=want_log and reg_on, opt_mode=opt_mode, fisher_cache=grad_c)
         if want_log:  # calib_block.py:85-87
             rec = step.rec_loss()
