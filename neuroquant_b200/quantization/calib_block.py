@@ -1,7 +1,8 @@
 """Block-wise calibration (reference: quantization/calib_block.py:91-183, data_utils.py:45-86,146-196).
 
 One decoder block (conv -> PixelShuffle -> GELU, one engine stage) learns its rounding variables against the block's
-own full-precision output.  Per iteration, on the GPU: fake-quant of the block's weight and bias (one launch), operand
+own full-precision output.  Per iteration, on the GPU: mini-batch gather + QDrop mixing from the HBM-resident caches
+(nq_qdrop_gather), fake-quant of the block's weight and bias (one launch), operand
 pack (one launch), tcgen05 forward with the activation derivative saved, ONE fused kernel for lp_loss + activation
 backward + un-shuffle (nq_block_loss_bwd), tcgen05 weight gradient + finish, and the fused quantiser Jacobian + Adam
 (nq_adaround_step_multi).  No data gradient is needed: nothing upstream of the block learns.
@@ -199,14 +200,6 @@ def assemble_batch(inp_s: torch.Tensor, sym_s, idx_dev: torch.Tensor, input_prob
     L.check(L.lib.nq_qdrop_gather(inp_s.data_ptr(), sym_s.data_ptr() if rnd is not None else None, idx_dev.data_ptr(), L.ptr(rnd),
                                   float(input_prob), n, inp_s.shape[1], frame, out.data_ptr(), L.stream()), "nq_qdrop_gather")
     return 2 if rnd is not None else 1
-
-
-def gather_frames(cache: torch.Tensor, idx_host, out: torch.Tensor):
-    """out[:, b] = cache[:, idx[b]]: whole frames are contiguous, so this is one plain copy per plane and frame (advanced
-    indexing would run an element-wise gather kernel over 2-byte elements)."""
-    for b, i in enumerate(idx_host.tolist()):
-        out[:, b].copy_(cache[:, i])
-    return out
 
 
 def _features(runner: DecoderRunner, model, embed: torch.Tensor, weight_quant: bool):

@@ -4,8 +4,6 @@ tensor-core-vs-fp32 `code_mismatch` that tests/test_gpu_fullsize.py reports.  GP
 import os
 import sys
 
-import torch
-
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from tests.test_gpu_fullsize import _calibrate  # noqa: E402
 
