@@ -117,14 +117,29 @@ def train(args, cfg):
     args.lr = cfg["learning_rate"]
     trainer = DecoderTrainer(model, args.arch, args.lr, cfg["loss"])
     start = datetime.now()
+    # The loader decodes every PNG once (first epoch); the frames then stay resident in HBM and later epochs only draw the
+    # loader's shuffled index batches -- at several hundred iterations/s four decoding workers cannot keep up
+    # (same scheme as quantization/calib_model._FrameSource).
+    n_full = args.full_data_length
+    train_pos = torch.as_tensor(train_idx, device=device)
+    frames, have = None, torch.zeros(n_full, dtype=torch.bool, device=device)
     for epoch in range(cfg["epoch"]):
         model.train()
         epoch_start, psnrs = datetime.now(), []
-        for i, sample in enumerate(train_loader):
+        resident = frames is not None and bool(have[train_pos].all())
+        for i, sample in enumerate(train_loader.batch_sampler if resident else train_loader):
             cur_epoch = (epoch + float(i) / len(train_loader)) / cfg["epoch"]
             lr = adjust_lr(trainer, cur_epoch, args)
-            img = sample["img"].to(device, non_blocking=True)
-            inputs = img if args.arch == "hnerv" else sample["norm_idx"].to(device)
+            if resident:
+                idx = train_pos[torch.as_tensor(sample, device=device)]     # positions in the Subset -> frame numbers
+                img, norm_idx = frames[idx], idx.double() / n_full                # float(idx) / len(video), as the data set
+            else:
+                img = sample["img"].to(device, non_blocking=True).float()
+                idx, norm_idx = sample["idx"].to(device).view(-1), sample["norm_idx"].to(device)
+                if frames is None:
+                    frames = torch.empty((n_full,) + tuple(img.shape[1:]), device=device)
+                frames[idx], have[idx] = img, True
+            inputs = img if args.arch == "hnerv" else norm_idx
             _, img_out = trainer.step(inputs, img)
             psnrs.append(psnr_fn_single(img_out, img))
             if i % args.print_freq == 0 or i == len(train_loader) - 1:
