@@ -213,3 +213,27 @@ def test_output_gradient_cache_every_block_and_layer(conv, monkeypatch):
         want = O.block_grad_cache(qd, k, cali, raw=True, layer=layer)
         assert got.shape == want.shape, (k, layer)
         assert float((got - want).abs().max()) <= 1e-2 * float(want.abs().max()), (k, layer, float((got - want).abs().max()), float(want.abs().max()))
+
+
+def test_batch_assembly_kernel_equals_torch_where():
+    """nq_qdrop_gather (calib_block.py:160-164) against advanced indexing + torch.where on the split-bf16 planes, with and
+    without QDrop, and its argument checks."""
+    import neuroquant_b200._lib as L
+    from neuroquant_b200.quantization.calib_block import assemble_batch
+    gen = torch.Generator().manual_seed(9)
+    N, n, h, w, c = 7, 3, 5, 6, 16
+    inp = torch.randn(2, N, h, w, c, generator=gen).cuda().bfloat16()
+    sym = torch.randn(2, N, h, w, c, generator=gen).cuda().bfloat16()
+    idx = torch.tensor([6, 0, 3], dtype=torch.int32).cuda()
+    out = torch.empty(2, n, h, w, c, device="cuda", dtype=torch.bfloat16)
+    assemble_batch(inp, sym, idx, 1.0, out)
+    assert torch.equal(out, inp[:, idx.long()])
+    torch.manual_seed(4)
+    assemble_batch(inp, sym, idx, 0.3, out)
+    torch.manual_seed(4)
+    keep = torch.rand_like(out[0], dtype=torch.float32) < 0.3
+    want = torch.where(keep.unsqueeze(0), inp[:, idx.long()], sym[:, idx.long()])
+    assert torch.equal(out, want) and 0.2 < float(keep.float().mean()) < 0.4
+    st = L.stream()
+    assert L.lib.nq_qdrop_gather(inp.data_ptr(), sym.data_ptr(), idx.data_ptr(), None, 0.5, n, N, h * w * c, out.data_ptr(), st) != 0
+    assert L.lib.nq_qdrop_gather(inp.data_ptr(), None, idx.data_ptr(), None, 1.0, n, N, h * w * c + 4, out.data_ptr(), st) != 0
