@@ -468,11 +468,13 @@ def run_block(args, eng, cfg, arch, geoms, world, rank):
 
     from neuroquant_b200.quantization.calib_block import assemble_batch
     cur = torch.empty_like(inp_s[:, :B])
+    idx = torch.zeros(B, dtype=torch.int32, device="cuda")
+    use_graph = os.environ.get("NQ_GRAPH", "1") != "0"
 
     def it(i):  # exactly the loop body of quantization/calib_block.block_reconstruction
-        idx = torch.randperm(F)[:B].cuda().int()
+        idx.copy_(torch.randperm(F)[:B])
         assemble_batch(inp_s, sym_s, idx, 0.5, cur)
-        step.run_cached(cur, out_c, idx, HYPER["weight"], 10.0, HYPER["p"])
+        step.run_cached(cur, out_c, idx, HYPER["weight"], 10.0, HYPER["p"], graph=use_graph)
 
     for i in range(max(args.warmup, 3)):
         it(i)

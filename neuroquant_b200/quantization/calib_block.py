@@ -21,6 +21,7 @@ from __future__ import annotations
 import copy
 import ctypes as C
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -75,6 +76,7 @@ class BlockStep:
         self.hyper_host = [torch.zeros(4).pin_memory() for _ in range(8)]
         self.hyper_done = [None] * 8
         self.n_run = 0
+        self._graphs = {}
         self.opt = AdamState([stage.alpha_w, stage.alpha_b], lr=lr)
         self.launches = 0
 
@@ -87,10 +89,51 @@ class BlockStep:
         self.run_cached(self.x, self.tgt, None, reg_w, reg_b, p, want_reg)
 
     def run_cached(self, x_split: torch.Tensor, tgt_cache: torch.Tensor, frame_idx, reg_w: float, reg_b: float, p: float,
-                   want_reg: bool = False, opt_mode: str = "mse", fisher_cache: torch.Tensor = None):
+                   want_reg: bool = False, opt_mode: str = "mse", fisher_cache: torch.Tensor = None, graph: bool = False):
         """One iteration from inputs already in the engine's layouts: x_split (2, n, h, w, cin_p) bf16 planes; tgt_cache
         (N, H, W, cg) fp32 NHWC with frame_idx (int32 device tensor of n entries) selecting the batch's frames, or a
-        (n, H, W, cg) batch with frame_idx None."""
+        (n, H, W, cg) batch with frame_idx None.  graph=True: the launch sequence is captured once per set of buffers as
+        a CUDA graph and replayed (the caller keeps x_split / frame_idx in the same buffers); the per-iteration scalars
+        travel through the 16-byte device array either way."""
+        self._set_hyper(reg_w, reg_b)
+        if not graph or want_reg:
+            self._body(x_split, tgt_cache, frame_idx, reg_b, p, want_reg, opt_mode, fisher_cache)
+            return
+        key = (x_split.data_ptr(), tgt_cache.data_ptr(), frame_idx.data_ptr() if frame_idx is not None else 0, float(p), opt_mode,
+               fisher_cache.data_ptr() if fisher_cache is not None else 0)
+        g = self._graphs.get(key)
+        if g is None:
+            self._body(x_split, tgt_cache, frame_idx, reg_b, p, False, opt_mode, fisher_cache)  # this iteration's real work
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            state = self.opt.params + self.opt.m + self.opt.v
+            saved = [t.clone() for t in state]  # capture must not advance the state
+            n0 = self.launches
+            with torch.cuda.graph(g):
+                self._body(x_split, tgt_cache, frame_idx, reg_b, p, False, opt_mode, fisher_cache)
+            self.launches = n0
+            for t, sv in zip(state, saved):
+                t.copy_(sv)
+            self._graphs[key] = g
+        else:
+            g.replay()
+            self.launches += 8
+
+    def _set_hyper(self, reg_w: float, reg_b: float):
+        """(reg_w, reg_b, Adam step size, sqrt bias correction) of the step about to run -> the device array."""
+        step_size, bc2 = self.opt.hyper_of_next_step()
+        kk = self.n_run % len(self.hyper_host)
+        self.n_run += 1
+        if self.hyper_done[kk] is not None:
+            self.hyper_done[kk].synchronize()
+        hh = self.hyper_host[kk]
+        hh[0], hh[1], hh[2], hh[3] = reg_w, reg_b, step_size, bc2
+        self.hyper.copy_(hh, non_blocking=True)
+        if self.hyper_done[kk] is None:
+            self.hyper_done[kk] = torch.cuda.Event()
+        self.hyper_done[kk].record()
+
+    def _body(self, x_split, tgt_cache, frame_idx, reg_b, p, want_reg, opt_mode, fisher_cache):
         s, d, st = self.stage, self.d, L.stream()
         g = s.geom
         cw = lambda dl: int(dl.numel() > 1)  # noqa: E731
@@ -140,17 +183,6 @@ class BlockStep:
                                                   self.wg.N, g.cin, 0))
         L.check(L.lib.nq_tc_wgrad_finish_multi(fin, 1, st), "nq_tc_wgrad_finish_multi")
         # 6. quantiser Jacobian + Adam on (alpha_w, alpha_b); the regulariser acts on the weight only (calib_block.py:38-47)
-        step_size, bc2 = self.opt.hyper_of_next_step()
-        kk = self.n_run % len(self.hyper_host)
-        self.n_run += 1
-        if self.hyper_done[kk] is not None:
-            self.hyper_done[kk].synchronize()
-        hh = self.hyper_host[kk]
-        hh[0], hh[1], hh[2], hh[3] = reg_w, reg_b, step_size, bc2
-        self.hyper.copy_(hh, non_blocking=True)
-        if self.hyper_done[kk] is None:
-            self.hyper_done[kk] = torch.cuda.Event()
-        self.hyper_done[kk].record()
         ad = (L.AdaTask * 2)(
             L.AdaTask(L.ptr(self.gw), L.ptr(s.w_src), L.ptr(s.alpha_w), L.ptr(s.delta_w), L.ptr(s.zp_w), L.ptr(self.opt.m[0]),
                       L.ptr(self.opt.v[0]), rw_, rl_, cw(s.delta_w), s.n_bits, 1, 0),
@@ -333,9 +365,11 @@ def _reconstruct(model, block, conv, layer_mode: bool, cali_data, batch_size, it
     inp_s, sym_s, out_c = cache_to_engine_layout(step, cached_inps, cached_sym if input_prob < 1.0 else None, cached_outs)
     grad_c = nhwc_cache(step, cached_grads) if cached_grads is not None else None
     cur = torch.empty_like(inp_s[:, :bsz])
+    idx = torch.zeros(bsz, dtype=torch.int32, device=cached_inps.device)
+    use_graph = os.environ.get("NQ_GRAPH", "1") != "0"
     for i in range(iters):
         idx_h = torch.randperm(n_cached)[:batch_size]
-        idx = idx_h.to(cached_inps.device).int()
+        idx.copy_(idx_h)                       # static device buffer: the graphed step reads the same address every time
         # gather + QDrop (calib_block.py:160-164); one draw per element, shared by the hi and lo planes
         assemble_batch(inp_s, sym_s, idx, input_prob, cur)
         count = i + 1
@@ -345,7 +379,7 @@ def _reconstruct(model, block, conv, layer_mode: bool, cali_data, batch_size, it
         reg_on = not (count < loss_start) and not layer_mode
         want_log = count % 500 == 0
         step.run_cached(cur, out_c, idx, weight if reg_on else 0.0, float(b) if reg_on else 0.0, p,
-                        want_reg=want_log and reg_on, opt_mode=opt_mode, fisher_cache=grad_c)
+                        want_reg=want_log and reg_on, opt_mode=opt_mode, fisher_cache=grad_c, graph=use_graph)
         if want_log:  # calib_block.py:85-87
             rec = step.rec_loss()
             rnd = float(step.reg) * weight if reg_on else 0.0
