@@ -1,0 +1,59 @@
+"""Host-side logic that needs no GPU: the learning-rate schedule, the prefix quantisation of the Fisher gradient pass,
+the runner's per-stage state, the packed-stream size arithmetic."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nq_oracle as O
+from tests.helpers import TINY_HNERV, load
+
+
+def test_adjust_lr_matches_reference_sequences():
+    """utils.adjust_lr (product) against the learning rates the reference's adjust_lr produced (regress fixtures) and
+    against the oracle's restatement, for the cosine and the hybrid schedule."""
+    from neuroquant_b200.utils import adjust_lr
+    for tag in ("regress_tiny_nerv", "regress_tiny_nerv_l1"):
+        g = load(tag)
+        args = SimpleNamespace(lr=float(g["lr"]), lr_type=str(g["lr_type"]))
+        opt = SimpleNamespace(param_groups=[{"lr": 0.0}, {"lr": 0.0}])
+        epochs, n = int(g["epochs"]), len(g["lr_seq"])
+        per = n // epochs
+        got = []
+        for it in range(n):
+            e, i = divmod(it, per)
+            got.append(adjust_lr(opt, (e + float(i) / per) / epochs, args))
+            assert opt.param_groups[0]["lr"] == opt.param_groups[1]["lr"] == got[-1]
+            assert got[-1] == O.adjust_lr(args.lr, (e + float(i) / per) / epochs, args.lr_type)
+        assert np.allclose(got, g["lr_seq"], rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        adjust_lr(SimpleNamespace(param_groups=[]), 0.5, SimpleNamespace(lr=1.0, lr_type="step_0.1"))
+
+
+def test_quantize_model_till_quantises_a_prefix():
+    """data_utils.py:261-272: every layer / block up to and including the given one, in module order."""
+    from neuroquant_b200.models import HNeRV
+    from neuroquant_b200.quantization import QuantModel, QuantModule
+    from neuroquant_b200.quantization.calib_block import quantize_model_till
+    torch.manual_seed(0)
+    qnn = QuantModel(HNeRV(TINY_HNERV), hadamard=False, weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"})
+    mods = [m for m in qnn.model.modules() if isinstance(m, QuantModule)]
+    assert len(mods) == 7
+    for target, n_on in ((qnn.model.decoder[3], 4), (qnn.model.decoder[3].conv, 4), (qnn.model.decoder[0], 1), (qnn.model.head_layer, 7)):
+        qnn.set_quant_state(True)
+        quantize_model_till(qnn, target)
+        assert [m.use_weight_quant for m in mods] == [True] * n_on + [False] * (7 - n_on)
+
+
+def test_layer_and_block_entry_points_reject_wrong_modules():
+    from neuroquant_b200.models import HNeRV
+    from neuroquant_b200.quantization import QuantModel, block_reconstruction, layer_reconstruction
+    qnn = QuantModel(HNeRV(TINY_HNERV), hadamard=False, weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"})
+    cali = torch.zeros(10, 4, 2, 4)
+    with pytest.raises(ValueError):
+        block_reconstruction(qnn, qnn.model.head_layer, cali)          # a lone layer is not a block
+    with pytest.raises(ValueError):
+        layer_reconstruction(qnn, qnn.model.decoder[2], cali)          # a block is not a layer
+    with pytest.raises(ValueError):
+        block_reconstruction(qnn, qnn.model.decoder[2], cali, opt_mode="hessian")
