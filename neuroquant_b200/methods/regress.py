@@ -45,6 +45,66 @@ class DecoderTrainer:
         self.enc_opt = torch.optim.Adam(enc, weight_decay=0.) if enc else None
         self.param_groups = [{"lr": lr}] + (self.enc_opt.param_groups if self.enc_opt else [])
         self.launches = 0
+        # decoder-only models (NeRV): the whole step -- weight pack, forward + loss, backward, Adam -- is one CUDA graph,
+        # replayed with the batch in static buffers and the learning rate in a 16-byte device array (NQ_GRAPH=0: eager)
+        self.use_graph = self.enc_opt is None and os.environ.get("NQ_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._hyper_host = [torch.zeros(4).pin_memory() for _ in range(8)] if self.use_graph else []
+        self._hyper_done = [None] * 8
+        self._n_run = 0
+
+    def _step_graphed(self, embed: torch.Tensor, frames: torch.Tensor):
+        eng = self.runner.engine
+        key = (tuple(embed.shape), tuple(frames.shape))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = {"embed": torch.empty_like(embed, dtype=torch.float32), "frames": torch.empty_like(frames),
+                                      "hyper": torch.zeros(4, device=frames.device), "graph": None, "launches": 0}
+        st["embed"].copy_(embed)
+        st["frames"].copy_(frames)
+        self.opt.lr = float(self.param_groups[0]["lr"])
+        step_size, bc2 = self.opt.hyper_of_next_step()
+        k = self._n_run % len(self._hyper_host)
+        self._n_run += 1
+        if self._hyper_done[k] is not None:
+            self._hyper_done[k].synchronize()
+        hh = self._hyper_host[k]
+        hh[2], hh[3] = step_size, bc2
+        st["hyper"].copy_(hh, non_blocking=True)
+        if self._hyper_done[k] is None:
+            self._hyper_done[k] = torch.cuda.Event()
+        self._hyper_done[k].record()
+        n, _, hh_, ww_ = frames.shape
+
+        def body():
+            eng.forward(st["embed"], train=True, target=st["frames"], p_norm=self.p_norm, mean_pixels=float(n * 3 * hh_ * ww_))
+            eng.backward()
+            _, views = eng._grad_buffers()
+            return self.opt.step_dev([g for pair in views for g in pair], st["hyper"])
+
+        if st["graph"] is None:
+            l0 = eng.launches
+            body()                              # eager once: this iteration's real work, and every lazy allocation
+            st["launches"] = eng.launches - l0
+            torch.cuda.synchronize()
+            loss, img = eng.last_loss().clone(), eng._last_plan.img.clone()
+            g = torch.cuda.CUDAGraph()
+            state = self.opt.params + self.opt.m + self.opt.v
+            saved = [t.clone() for t in state]  # capture must not advance the state
+            eng.invalidate()
+            with torch.cuda.graph(g):
+                body()
+            eng.launches = l0 + st["launches"]
+            for t, sv in zip(state, saved):
+                t.copy_(sv)
+            st["graph"] = g
+        else:
+            st["graph"].replay()
+            eng.launches += st["launches"]
+            loss, img = eng.last_loss().clone(), eng._last_plan.img
+        self.launches += len(self.opt.params)  # the Adam kernels (the engine counts its own)
+        eng.invalidate()
+        return loss, img
 
     def step(self, inputs: torch.Tensor, frames: torch.Tensor):
         """inputs: the frames themselves (hnerv) or their normalised indices (nerv).  Returns (loss, img_out), both on
@@ -56,6 +116,8 @@ class DecoderTrainer:
             with torch.no_grad():
                 embed = self.model.encode(inputs)
         self.runner.sync()
+        if self.use_graph:
+            return self._step_graphed(embed, frames)
         n, _, hh, ww = frames.shape
         img = eng.forward(embed.detach(), train=True, target=frames, p_norm=self.p_norm, mean_pixels=float(n * 3 * hh * ww),
                           reuse_weights=True)
