@@ -102,7 +102,7 @@ def test_regress_cli_trains_and_writes_reference_checkpoints(tmp_path, monkeypat
     assert len(ck) == 1 and len(latest) == 1
     sd = torch.load(ck[0], map_location="cpu")
     assert "decoder.0.weight" in sd and "decoder.1.conv.0.weight" in sd and "head_layer.bias" in sd
-    assert ("encoder.downsample_layers.0.0.weight" in sd) == (arch == "hnerv") or arch == "nerv"
+    assert any(k.startswith("encoder.") for k in sd) == (arch == "hnerv")
     text = open(glob.glob(os.path.join(os.path.dirname(ck[0]), "*.log"))[0]).read()
     psnrs = [float(l.split("pred_PSNR:")[1].split()[0].strip(",")) for l in text.splitlines() if "pred_PSNR:" in l]
     assert len(psnrs) >= 6 and psnrs[-1] > psnrs[0]          # it learns
