@@ -6,10 +6,15 @@ legs may.  It is a plain PyTorch-CPU (fp32) restatement of the reference's algor
 as pure functions over explicit tensors (no nn.Module surgery), each citing the reference
 file:line it follows (paths relative to /root/reference).
 
-Pinning: `tests/golden/make_golden.py` imports the UNMODIFIED reference from
-/root/reference (with the three shim modules under `oracle/ref_shims/`) in the build container
-and stores its outputs in `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks every
-function below against those fixtures.  The only un-pinned piece is the third-party
+Pinning: `tests/golden/make_golden.py` (and make_block_golden.py, make_init_golden.py,
+make_regress_golden.py next to it) import the UNMODIFIED reference from /root/reference (with the
+three shim modules under `oracle/ref_shims/`) in the build container and store its outputs in
+`tests/golden/*.npz`; `tests/test_oracle_golden.py` checks every function below against those
+fixtures.  Two fixtures are not plain calls of a reference entry point and say so in their
+generators: layer_reconstruction is the reference's own source compiled in memory with its missing
+`opt_params = []` inserted (it cannot run as shipped), and the FP32 training loop replays
+regress.py:249-271 with the reference's model, loss_fn and adjust_lr (its train() needs a PNG data
+set, worker processes and TensorBoard).  The only un-pinned piece is the third-party
 `hadamard_transform` package (PyPI `hadamard-transform`, version not pinned by the reference,
 absent from /root/reference): restated as the orthonormal Sylvester-ordered Walsh-Hadamard
 transform and checked against `scipy.linalg.hadamard(n)/sqrt(n)`; the ordering of codes along
