@@ -21,37 +21,40 @@ def hadamard_along_channel_weight(x: torch.Tensor, normalize: bool = True):
     return L.fwht_channel(x.detach().contiguous().float())
 
 
+def _same_conv_or_raise(conv: nn.Conv2d):
+    """The engine's kernels cover what the decoders use: odd square kernels, stride 1, 'same' padding, no groups."""
+    k = conv.kernel_size
+    ok = (conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and k[0] == k[1] and k[0] % 2 == 1
+          and conv.padding == (k[0] // 2, k[0] // 2))
+    if not ok:
+        raise ValueError("QuantModule kernels cover the decoders' stride-1 'same' convolutions only: {}".format(conv))
+
+
 class QuantModule(nn.Module):
+    """Attribute names are the reference's (quant_layer.py:29-65): pickled QuantModels carry them and the runner reads
+    them -- weight / org_weight / bias / org_bias, hadamard + C + hadamard_weight, use_weight_quant, the two quantisers,
+    fwd_kwargs / fwd_func."""
+
     def __init__(self, org_module: Union[nn.Conv2d,], hadamard: bool = True, weight_quant_params: dict = {}):
         super().__init__()
-        if isinstance(org_module, nn.Conv2d):
-            self.fwd_kwargs = dict(stride=org_module.stride, padding=org_module.padding, dilation=org_module.dilation,
-                                   groups=org_module.groups)
-            self.fwd_func = F.conv2d  # kept for layout compatibility; the forward below runs libnq_sm100 kernels
-        else:
+        if not isinstance(org_module, nn.Conv2d):
             raise ValueError("Not supported modules: {}".format(org_module))
-        k = org_module.kernel_size
-        if org_module.stride != (1, 1) or org_module.dilation != (1, 1) or org_module.groups != 1 or k[0] != k[1] or \
-                k[0] % 2 == 0 or org_module.padding != (k[0] // 2, k[0] // 2):
-            raise ValueError("QuantModule kernels cover the decoders' stride-1 'same' convolutions only: {}".format(org_module))
-        self.weight = org_module.weight
-        self.org_weight = org_module.weight.data.clone()
+        _same_conv_or_raise(org_module)
+        self.fwd_kwargs = {k: getattr(org_module, k) for k in ("stride", "padding", "dilation", "groups")}
+        self.fwd_func = F.conv2d  # kept for layout compatibility; the forward below runs libnq_sm100 kernels
+        # the learnable tensors stay the module's own Parameters; full-precision copies serve the un-quantised state
+        self.weight, self.org_weight = org_module.weight, org_module.weight.data.clone()
+        has_bias = org_module.bias is not None
+        self.bias = org_module.bias if has_bias else None
+        self.org_bias = org_module.bias.data.clone() if has_bias else None
         self.hadamard = hadamard
-        if self.hadamard:
-            C_out, C_in, KH, KW = self.weight.shape
-            self.C = C_in
-            pad_channels = _next_power_of_two(self.C) - self.C
-            x_padded = F.pad(org_module.weight.data.clone(), (0, 0, 0, 0, 0, pad_channels))
-            self.hadamard_weight = hadamard_along_channel_weight(x_padded)
-        if org_module.bias is not None:
-            self.bias = org_module.bias
-            self.org_bias = org_module.bias.data.clone()
-        else:
-            self.bias = None
-            self.org_bias = None
+        if hadamard:
+            # rotated copy of the weight: input channels zero-padded to a power of two, then the orthonormal WHT
+            self.C = self.weight.shape[1]
+            grow = _next_power_of_two(self.C) - self.C
+            self.hadamard_weight = hadamard_along_channel_weight(F.pad(self.org_weight, (0, 0, 0, 0, 0, grow)))
         self.use_weight_quant = False
-        self.weight_quantizer = UniformAffineQuantizer(**weight_quant_params)
-        self.bias_quantizer = UniformAffineQuantizer(**weight_quant_params)
+        self.weight_quantizer, self.bias_quantizer = (UniformAffineQuantizer(**weight_quant_params) for _ in range(2))
         self.extra_repr = org_module.extra_repr
 
     def quantized_weight_bias(self):

@@ -16,20 +16,26 @@ class QuantModel(nn.Module):
         self.hadamard = hadamard
         self.quant_module_refactor(self.model, weight_quant_params)
 
+    def _wrapped(self, child: nn.Module, params: dict):
+        """The quantised stand-in of one child, or None when the child is kept and searched instead."""
+        wrapper = specials.get(type(child))
+        if wrapper is not None:
+            return wrapper(child, self.hadamard, params)
+        if isinstance(child, nn.Conv2d):
+            return QuantModule(child, self.hadamard, params)
+        return None
+
     def quant_module_refactor(self, module: nn.Module, weight_quant_params: dict = {}):
-        """Recursively replace Conv2d -> QuantModule and NeRVBlock -> QuantNeRVBlock, skipping every child
-        whose name contains 'encoder' (quant_model.py:19-41)."""
-        for name, child in module.named_children():
-            if "encoder" in name:
+        """Module surgery of quant_model.py:19-41: NeRVBlock -> QuantNeRVBlock, bare Conv2d -> QuantModule, depth first;
+        children whose name contains 'encoder' (never quantised) and StraightThrough placeholders are left alone."""
+        for name, child in list(module.named_children()):
+            if "encoder" in name or isinstance(child, StraightThrough):
                 continue
-            elif type(child) in specials:
-                setattr(module, name, specials[type(child)](child, self.hadamard, weight_quant_params))
-            elif isinstance(child, nn.Conv2d):
-                setattr(module, name, QuantModule(child, self.hadamard, weight_quant_params))
-            elif isinstance(child, StraightThrough):
-                continue
-            else:
+            repl = self._wrapped(child, weight_quant_params)
+            if repl is None:
                 self.quant_module_refactor(child, weight_quant_params)
+            else:
+                setattr(module, name, repl)
 
     def quant_modules(self):
         return [m for m in self.model.modules() if isinstance(m, QuantModule)]
@@ -49,20 +55,17 @@ class QuantModel(nn.Module):
         return self.model.decode(input)
 
     def set_bitwidth(self, bit, init=False):
-        """Per-layer bit-widths; returns the average bits per parameter (quant_model.py:58-72)."""
-        count = 0
-        bits = 0.0
-        num_param = 0.0
-        for m in self.model.modules():
-            if isinstance(m, QuantModule):
-                m.weight_quantizer.bitwidth_refactor(bit[count])
-                m.weight_quantizer.inited = init
-                m.bias_quantizer.bitwidth_refactor(bit[count])
-                m.bias_quantizer.inited = init
-                bits += m.weight_quantizer.n_bits * m.weight.numel() + m.bias_quantizer.n_bits * m.bias.numel()
-                num_param += m.weight.numel() + m.bias.numel()
-                count += 1
-        return bits / num_param
+        """Give layer i (weight and bias quantiser alike) bit[i] bits and mark the scales (un)initialised; returns the
+        average bits per decoder parameter (quant_model.py:58-72).  Integer sums: exact, so the ratio is the reference's."""
+        total_bits = total_params = 0
+        for i, m in enumerate(self.quant_modules()):
+            for q in (m.weight_quantizer, m.bias_quantizer):
+                q.bitwidth_refactor(bit[i])
+                q.inited = init
+            n_w, n_b = m.weight.numel(), m.bias.numel()
+            total_bits += m.weight_quantizer.n_bits * n_w + m.bias_quantizer.n_bits * n_b
+            total_params += n_w + n_b
+        return float(total_bits) / float(total_params)
 
     def get_quantized_param(self):
         """Codes cached by the last forward, W and b interleaved per layer (quant_model.py:74-80)."""
