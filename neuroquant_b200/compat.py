@@ -14,7 +14,7 @@ import sys
 def install_reference_aliases():
     from . import models, quantization, utils, videosets
     from .models import _layers
-    from .quantization import calib_model, data_utils, quant_block, quant_layer, quant_model, quantizer
+    from .quantization import calib_block, calib_layer, calib_model, data_utils, quant_block, quant_layer, quant_model, quantizer
 
     table = {
         "models": models, "models.HNeRV": sys.modules[models.__name__ + ".HNeRV"],
@@ -22,6 +22,7 @@ def install_reference_aliases():
         "quantization": quantization, "quantization.quantizer": quantizer, "quantization.quant_layer": quant_layer,
         "quantization.quant_block": quant_block, "quantization.quant_model": quant_model,
         "quantization.calib_model": calib_model, "quantization.data_utils": data_utils,
+        "quantization.calib_block": calib_block, "quantization.calib_layer": calib_layer,
         "utils": utils, "videosets": videosets,
     }
     for name, mod in table.items():

@@ -57,3 +57,25 @@ def test_layer_and_block_entry_points_reject_wrong_modules():
         layer_reconstruction(qnn, qnn.model.decoder[2], cali)          # a block is not a layer
     with pytest.raises(ValueError):
         block_reconstruction(qnn, qnn.model.decoder[2], cali, opt_mode="hessian")
+
+
+def test_reference_module_paths_resolve_after_aliasing():
+    """compat.install_reference_aliases: the reference's import paths, the block- and layer-wise modules included.  Run
+    in a subprocess so that the aliases do not leak into this test session."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from neuroquant_b200.compat import install_reference_aliases\n"
+            "install_reference_aliases()\n"
+            "from quantization import QuantModel, model_reconstruction, block_reconstruction, layer_reconstruction\n"
+            "from quantization.calib_layer import layer_reconstruction as a\n"
+            "from quantization.calib_block import block_reconstruction as b\n"
+            "from quantization.quantizer import AdaRoundQuantizer, UniformAffineQuantizer\n"
+            "from models import HNeRV, NeRV\n"
+            "assert a is layer_reconstruction and b is block_reconstruction\n"
+            "assert QuantModel.__module__ == 'quantization.quant_model' and HNeRV.__module__ == 'models.HNeRV'\n"
+            "print('aliases ok')\n") % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert out.returncode == 0 and "aliases ok" in out.stdout, out.stderr[-2000:]
