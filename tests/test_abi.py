@@ -146,3 +146,18 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
             (C.sizeof(L.WgFinishTask), L.WgFinishTask.cin_dst.offset),
             (C.sizeof(L.TcPackTask), L.TcPackTask.cin_src.offset)]
     assert got == want
+
+
+def test_tensor_core_kernels_compile_without_spills():
+    """ptxas -v logs written by the build (neuroquant_b200/csrc/Makefile): no tensor-core kernel spills registers -- a
+    spill in the single issuing warp or in an epilogue warp costs more than any tuning in DESIGN.md section 4 gains."""
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neuroquant_b200", "csrc")
+    seen = 0
+    for name in ("nq_conv_tc.o.ptxas.log", "nq_wgrad_tc.o.ptxas.log", "nq_head_tc.o.ptxas.log"):
+        text = open(os.path.join(csrc, name)).read()
+        for stores, loads in re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", text):
+            assert (stores, loads) == ("0", "0"), (name, stores, loads)
+            seen += 1
+    assert seen >= 15
