@@ -240,6 +240,12 @@ int nq_head_fwd_loss_split(const nq_conv_desc* d, const void* x_split, const flo
 int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
                             int out_bias, const float* target, float p, float mean_pixels, float* img,
                             float* loss_sum, void* dz_head_split, void* stream);
+/* Same, with the target frames as the data set stores them: uint8 (n, 3, h, w); the kernel evaluates value / 255 in fp32
+ * (IEEE division: bit-identical to the reference's `read_image(...) / 255.0`, videosets/datasets.py:8-54, consumed at
+ * calib_model.py:150).  A quarter of the bytes over PCIe and out of HBM per iteration. */
+int nq_head_fwd_loss_tapexp_u8(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                               int out_bias, const uint8_t* target_u8, float p, float mean_pixels,
+                               float* img, float* loss_sum, void* dz_head_split, void* stream);
 
 /* Head weight/bias gradient: dwk_head [(9*cin_p + 4)][4] as nq_conv_wgrad; workspace >= blocks*(9*cin_p+4)*4
  * floats with blocks = nq_head_wgrad_blocks(d). */
@@ -330,6 +336,9 @@ int nq_nchw_to_split(const float* src, void* dst_split, int n, int c, int h, int
 int nq_split_to_nchw(const void* src_split, float* dst, int n, int c, int h, int w, int c_p, void* stream);
 int nq_f32_to_split(const float* src, void* dst_split, int64_t numel, void* stream);
 int nq_split_to_f32(const void* src_split, float* dst, int64_t numel, void* stream);
+/* Frame ingest (videosets/datasets.py:8-54: `read_image(path) / 255.0`): uint8 -> fp32 value / 255, IEEE division, so the
+ * result is bit-identical to the reference's host-side conversion.  16-byte aligned pointers. */
+int nq_u8_to_f32(const uint8_t* src, float* dst, int64_t numel, void* stream);
 
 /* Weight + bias gradient on the tensor cores; output contract identical to nq_conv_wgrad (dwk
  * [(kdim + 4)][nout_p], bias gradient in row kdim).  cin_p % 8 == 0, rh*rw*cg % 16 == 0. */

@@ -129,6 +129,8 @@ def _load():
         "nq_jet_act": (I, [P, P, P, P, P, L, I, P, P, P, I, P]),
         "nq_head_fwd_loss_split": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
         "nq_head_fwd_loss_tapexp": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
+        "nq_head_fwd_loss_tapexp_u8": (I, [DP, P, P, P, I, P, F, F, P, P, P, P]),
+        "nq_u8_to_f32": (I, [P, P, L, P]),
         "nq_jet_head": (I, [P, P, P, P, P, P, I, I, I, I, P, P]),
         "nq_nchw_to_split": (I, [P, P, I, I, I, I, I, P]),
         "nq_split_to_nchw": (I, [P, P, I, I, I, I, I, P]),

@@ -46,8 +46,9 @@ class GraphedStep:
     all-reduce into the graph hung on the test box: opt-in with NQ_GRAPH_DP=1)."""
 
     def __init__(self, eng: DecoderEngine, opt: AdamState, embed: torch.Tensor, frames: torch.Tensor, p_norm: float,
-                 mean_pixels: float, group=None, world: int = 1, capture: bool = True):
+                 mean_pixels: float, group=None, world: int = 1, capture: bool = True, phase: str = "alpha"):
         self.eng, self.opt, self.p_norm, self.mean_pixels = eng, opt, p_norm, mean_pixels
+        self.phase = phase  # 'alpha': AdaRound phase (one fused Jacobian + Adam launch); 'delta': step-size phase
         self.group, self.world = group, world
         self.capture = capture  # False: the same fused kernel sequence launched eagerly (data-parallel default)
         self.embed = torch.empty_like(embed)
@@ -66,7 +67,12 @@ class GraphedStep:
         flat = eng.backward()
         if self.world > 1:  # the NCCL all-reduce is captured into the graph with the kernels around it
             torch.distributed.all_reduce(flat, group=self.group)
-        adaround_step_multi(eng, self.opt, self.hyper)  # quantiser Jacobian + Adam for all 14 tensors: one launch
+        if self.phase == "alpha":
+            adaround_step_multi(eng, self.opt, self.hyper)  # quantiser Jacobian + Adam for all 14 tensors: one launch
+        else:  # step-size phase (5 % of a run): straight-through d_delta per tensor, Adam with the device-side step size
+            grads = eng.param_grads(1.0)
+            self.opt.step_dev([g for pair in grads for g in pair], self.hyper)
+            eng.launches += len(self.opt.params)
 
     def run(self, embed, frames, reg_w: float, reg_b: float):
         self.embed.copy_(embed)
@@ -104,33 +110,54 @@ class GraphedStep:
 
 
 class HostBatchPipe:
-    """Double-buffered host -> device input pipe for calibration batches that live in (pinned) host memory.
+    """Host -> device input pipe for calibration batches that live in host memory (quantization/calib_model._FrameSource
+    feeds the loop through it while frames are not resident in HBM).
 
-    `put(embed_h, frames_h)` starts the copy of the NEXT batch on a side stream; `get()` makes the compute stream
-    wait for the oldest pending batch and returns its device tensors.  With one batch in flight the PCIe copy of
-    batch k+1 (19.7 MB for two 1280x640 frames) runs under the kernels of batch k instead of in front of them.
-    A slot is refilled only after the compute stream has consumed it (event recorded by `get()` of the next batch or
-    by `release()`)."""
+    `put(*host_tensors)` starts the copy of the NEXT batch on a side stream -- straight from the source when it is pinned
+    (a DataLoader with pin_memory=True), else through a pinned staging slot; `get()` makes the compute stream wait for the
+    oldest pending batch and returns its device tensors.  With one batch in flight the PCIe copy of batch k+1 (4.9 MB for
+    two 1280x640 uint8 frames, 19.7 MB as fp32) runs under the kernels of batch k instead of in front of them.  A slot is
+    refilled only after the compute stream has consumed it (event recorded by the next `get()` or by `release()`).
 
-    def __init__(self, embed_shape, frames_shape, device="cuda", depth: int = 2):
+    specs: one (shape, dtype) per tensor of a batch."""
+
+    def __init__(self, specs, device="cuda", depth: int = 2):
         self.stream = torch.cuda.Stream(device=device)
-        self.slots = [(torch.empty(embed_shape, device=device), torch.empty(frames_shape, device=device)) for _ in range(depth)]
+        self.specs = [(tuple(sh), dt) for sh, dt in specs]
+        self.slots = [tuple(torch.empty(sh, device=device, dtype=dt) for sh, dt in self.specs) for _ in range(depth)]
+        self.pinned = [None] * depth  # staging for unpinned sources, allocated on first use
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [None] * depth  # event after which the slot may be overwritten
         self.head = self.tail = 0   # next slot to fill / next slot to hand out
         self.depth = depth
         self._last = None
 
-    def put(self, embed_h: torch.Tensor, frames_h: torch.Tensor):
+    def pending(self) -> int:
+        return self.head - self.tail
+
+    def put(self, *host_tensors):
         if self.head - self.tail >= self.depth:
             raise RuntimeError("HostBatchPipe: all slots are pending; call get() first")
+        if len(host_tensors) != len(self.specs):
+            raise ValueError(f"HostBatchPipe: expected {len(self.specs)} tensors per batch, got {len(host_tensors)}")
         k = self.head % self.depth
-        e, f = self.slots[k]
         with torch.cuda.stream(self.stream):
             if self.free[k] is not None:
                 self.stream.wait_event(self.free[k])
-            e.copy_(embed_h, non_blocking=True)
-            f.copy_(frames_h, non_blocking=True)
+            for j, (dst, src) in enumerate(zip(self.slots[k], host_tensors)):
+                if tuple(src.shape) != tuple(dst.shape) or src.dtype != dst.dtype:
+                    raise ValueError(f"HostBatchPipe: batch tensor {j} is {tuple(src.shape)} {src.dtype}, slot is {tuple(dst.shape)} {dst.dtype}")
+                if src.is_cuda:
+                    dst.copy_(src, non_blocking=True)
+                    continue
+                if not src.is_pinned():
+                    if self.pinned[k] is None:
+                        self.pinned[k] = [torch.empty(sh, dtype=dt).pin_memory() for sh, dt in self.specs]
+                    if self.free[k] is not None:
+                        self.free[k].synchronize()  # the staging buffer's previous copy has left the host
+                    self.pinned[k][j].copy_(src)
+                    src = self.pinned[k][j]
+                dst.copy_(src.contiguous(), non_blocking=True)
             self.ready[k].record(self.stream)
         self.head += 1
 
@@ -159,7 +186,8 @@ class CalibrationLoop:
 
     def __init__(self, engine: DecoderEngine, fetch: Callable, n_batches: int, iters: int, weight: float = 0.01,
                  b_range=(20, 2), warmup: float = 0.0, p: float = 2.0, lr: float = 0.0015,
-                 group=None, global_batch: Optional[int] = None, log: Optional[list] = None):
+                 group=None, global_batch: Optional[int] = None, log: Optional[list] = None,
+                 on_iteration: Optional[Callable] = None):
         self.eng, self.fetch, self.n_batches, self.iters = engine, fetch, n_batches, iters
         self.weight, self.b_range, self.warmup, self.p, self.lr = weight, b_range, warmup, p, lr
         self.group = group
@@ -168,6 +196,7 @@ class CalibrationLoop:
             self.world = torch.distributed.get_world_size(group)
         self.global_batch = global_batch
         self.log = log
+        self.on_iteration = on_iteration  # (phase, count, device loss scalar) after every iteration; no sync
         # one GPU: CUDA-graph replay; data parallel: the same fused sequence launched eagerly around the NCCL all-reduce
         # (capturing the all-reduce hung on the test box: opt-in with NQ_GRAPH_DP=1); NQ_GRAPH=0: per-tensor eager path
         self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0"
@@ -180,15 +209,18 @@ class CalibrationLoop:
     # -- one iteration: forward + loss + backward + (all-reduce) + Jacobian + Adam
     def iteration(self, idx, opt: AdamState, reg_w: float, reg_b: float, want_log: bool):
         eng = self.eng
-        embed, frames = self.fetch(idx)
+        res = self.fetch(idx)
+        embed, frames = res[0], res[1]
         n, _, H, W = frames.shape
-        gb = self.global_batch if self.global_batch is not None else n * self.world
-        if self.use_graph and eng.mode == "ada" and not want_log:
-            key = (tuple(embed.shape), tuple(frames.shape), id(opt))
+        # lp_loss is a mean over the frames ACTUALLY in the (global) mini-batch (quantizer.py:71): a loader with
+        # drop_last=False ends an epoch on a ragged batch, whose size `fetch` reports as a third value
+        gb = res[2] if len(res) > 2 else (self.global_batch if self.global_batch is not None else n * self.world)
+        if self.use_graph and eng.mode in ("ada", "uaq") and eng.stage_state is None and not want_log:
+            key = (tuple(embed.shape), tuple(frames.shape), id(opt), gb)
             gs = self._graphed.get(key)
             if gs is None:
                 gs = self._graphed[key] = GraphedStep(eng, opt, embed, frames, self.p, float(gb * H * W), self.group, self.world,
-                                                      capture=self.capture)
+                                                      capture=self.capture, phase="alpha" if eng.mode == "ada" else "delta")
             gs.run(embed, frames, reg_w, reg_b)
             return
         eng.forward(embed, train=True, target=frames, p_norm=self.p, mean_pixels=float(gb * H * W),
@@ -212,7 +244,9 @@ class CalibrationLoop:
         for _ in range(self.ep1):
             for idx in batches():
                 count += 1
-                self.iteration(idx, opt, 0.0, 0.0, False)
+                self.iteration(idx, opt, 0.0, 0.0, self.log is not None)
+                if self.on_iteration is not None:
+                    self.on_iteration("delta", count, self.eng.last_loss())
                 if self.log is not None:
                     self.log.append(("delta", count, float(self._global_loss()), 0.0, 0.0))
         return count
@@ -236,6 +270,8 @@ class CalibrationLoop:
                 reg_on = not (count < loss_start)
                 want_log = self.log is not None or count % 500 == 0
                 self.iteration(idx, opt, self.weight if reg_on else 0.0, float(b) if reg_on else 0.0, want_log)
+                if self.on_iteration is not None:
+                    self.on_iteration("alpha", count, self.eng.last_loss())
                 if want_log:
                     rec = float(self._global_loss())
                     rnd = float(eng.reg_sum) * self.weight if reg_on else 0.0

@@ -336,123 +336,9 @@ __device__ __forceinline__ uint16_t f_to_bf16_bits(float v) {  // round to neare
   return (uint16_t)(u >> 16);
 }
 
-__global__ void __launch_bounds__(HT_H * HT_W) head_fwd_loss_kernel(const HeadParams q) {
-  __shared__ __align__(16) float xs[(HT_H + 2) * (HT_W + 2) * H_PS];
-  __shared__ __align__(16) float ws[9 * H_CH * 4];
-  __shared__ float red[32];
-  const int tid = threadIdx.x;
-  const int lx = tid % HT_W, ly = tid / HT_W;
-  const int tiles_w = (q.w_ + HT_W - 1) / HT_W, tiles_h = (q.h + HT_H - 1) / HT_H;
-  int b = blockIdx.x;
-  const int tw = b % tiles_w; b /= tiles_w;
-  const int th = b % tiles_h;
-  const int bn = b / tiles_h;
-  const int x0 = tw * HT_W, y0 = th * HT_H;
-  const int px = x0 + lx, py = y0 + ly;
-
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-  for (int c0 = 0; c0 < q.C; c0 += H_CH) {
-    const int cw = min(H_CH, q.C - c0);  // 8 or 4
-    const int c4n = cw >> 2;
-    __syncthreads();
-    // stage the halo tile: (HT_H+2) x (HT_W+2) pixels x cw channels
-    for (int i = tid; i < (HT_H + 2) * (HT_W + 2) * 2; i += HT_H * HT_W) {
-      const int c4 = i & 1, pix = i >> 1;
-      const int sx = pix % (HT_W + 2), sy = pix / (HT_W + 2);
-      const int gx = x0 + sx - 1, gy = y0 + sy - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c4 < c4n && (unsigned)gx < (unsigned)q.w_ && (unsigned)gy < (unsigned)q.h) {
-        const int64_t o = ((int64_t)(bn * q.h + gy) * q.w_ + gx) * q.C + c0 + c4 * 4;
-        if (q.x_hi) {
-          const uint2 hb = __ldg(reinterpret_cast<const uint2*>(q.x_hi + o)), lb = __ldg(reinterpret_cast<const uint2*>(q.x_lo + o));
-          v.x = bf16_bits_to_f(hb.x & 0xFFFFu) + bf16_bits_to_f(lb.x & 0xFFFFu);
-          v.y = bf16_bits_to_f(hb.x >> 16) + bf16_bits_to_f(lb.x >> 16);
-          v.z = bf16_bits_to_f(hb.y & 0xFFFFu) + bf16_bits_to_f(lb.y & 0xFFFFu);
-          v.w = bf16_bits_to_f(hb.y >> 16) + bf16_bits_to_f(lb.y >> 16);
-        } else {
-          v = ldg4(q.x + o);
-        }
-      }
-      *reinterpret_cast<float4*>(&xs[pix * H_PS + c4 * 4]) = v;
-    }
-    for (int i = tid; i < 9 * H_CH; i += HT_H * HT_W) {
-      const int tap = i / H_CH, c = i % H_CH;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < cw) v = ldg4(q.w + ((int64_t)tap * q.C + c0 + c) * 4);
-      *reinterpret_cast<float4*>(&ws[i * 4]) = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float* xp = &xs[((ly + kh) * (HT_W + 2) + (lx + kw)) * H_PS];
-        const float4 xa = *reinterpret_cast<const float4*>(xp);
-        const float4 xb = *reinterpret_cast<const float4*>(xp + 4);
-        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        const float* wp = &ws[(kh * 3 + kw) * H_CH * 4];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 wv = *reinterpret_cast<const float4*>(wp + c * 4);
-          acc0 = fmaf(xv[c], wv.x, acc0);
-          acc1 = fmaf(xv[c], wv.y, acc1);
-          acc2 = fmaf(xv[c], wv.z, acc2);
-        }
-      }
-  }
-  float loss = 0.f;
-  if (px < q.w_ && py < q.h) {
-    const float v[3] = {acc0 + q.bias[0], acc1 + q.bias[1], acc2 + q.bias[2]};
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    const int64_t plane = (int64_t)q.h * q.w_;
-    const int64_t o = (int64_t)bn * 3 * plane + (int64_t)py * q.w_ + px;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float outv, dout;
-      if (q.out_bias == 0) {
-        const float t = tanhf(v[c]);
-        outv = t * 0.5f + 0.5f;
-        dout = 0.5f * (1.0f - t * t);
-      } else {
-        outv = sigmoid_f(v[c]);
-        dout = outv * (1.0f - outv);
-      }
-      if (q.img) q.img[o + c * plane] = outv;
-      if (q.target) {
-        const float dlt = outv - q.target[o + c * plane];
-        const float a = fabsf(dlt);
-        if (q.p == 2.0f) {
-          loss += dlt * dlt;
-          g[c] = 2.0f * dlt * q.inv_mean * dout;
-        } else {
-          loss += powf(a, q.p);
-          const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
-          g[c] = q.p * powf(a, q.p - 1.0f) * sgn * q.inv_mean * dout;
-        }
-      }
-    }
-    if (q.dz) *reinterpret_cast<float4*>(q.dz + ((int64_t)(bn * q.h + py) * q.w_ + px) * 4) = make_float4(g[0], g[1], g[2], 0.f);
-    if (q.dz_hi) {
-      uint16_t hb[3], lb[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        hb[c] = f_to_bf16_bits(g[c]);
-        lb[c] = f_to_bf16_bits(g[c] - bf16_bits_to_f(hb[c]));
-      }
-      const int64_t o = ((int64_t)(bn * q.h + py) * q.w_ + px) * 8;
-      *reinterpret_cast<uint4*>(q.dz_hi + o) = make_uint4((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), hb[2], 0u, 0u);
-      *reinterpret_cast<uint4*>(q.dz_lo + o) = make_uint4((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), lb[2], 0u, 0u);
-    }
-  }
-  if (q.target && q.loss_sum) {
-    loss = block_sum(loss, red);
-    if (tid == 0) atomicAdd(q.loss_sum, loss);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Head forward, 4 pixels per thread.  The kernel above issues 16 shared-memory wavefronts (2 input float4 + 8
-// broadcast weight float4) per 24 FMAs and is bound by the shared-memory pipe (92 % busy, 0.27 ms).  Here a thread
+// Head forward, 4 pixels per thread.  (A one-pixel-per-thread kernel issued 16 shared-memory wavefronts -- 2 input
+// float4 + 8 broadcast weight float4 -- per 24 FMAs and was bound by the shared-memory pipe: 92 % busy, 0.27 ms; removed.)  Here a thread
 // owns a 4-row strip of one column: the 8 weight loads of a (tap, channel quad) feed 4 pixels, and the 6 input rows
 // of a strip are loaded once per kernel column -- 72 wavefronts per 288 FMAs, balanced with the FMA pipe.
 // Same staging (pixel-major, 8-channel chunks), same per-pixel epilogue.
@@ -753,12 +639,7 @@ static inline int64_t hcdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // 0.31 ms against 0.27 ms for this kernel at 1280x640x2: with 44 KB of staging per CTA its synchronous tile loads are
 // exposed, and the head's input arrives as split-bf16 NHWC, which needs a converting transpose.  Not kept.)
 static int launch_head_fwd(const HeadParams& q, cudaStream_t s) {
-  static const bool v1 = getenv("NQ_HEAD_V1") != nullptr;  // A/B switch: the one-pixel-per-thread kernel
-  static const bool v2 = getenv("NQ_HEAD_V2") != nullptr;  // A/B switch: the synchronous 4-row-strip kernel
-  if (v1) {
-    const int64_t blocks = hcdiv(q.w_, HT_W) * hcdiv(q.h, HT_H) * q.n;
-    head_fwd_loss_kernel<<<(unsigned)blocks, HT_H * HT_W, 0, s>>>(q);
-  } else if (q.x_hi && !q.target && !v2 && q.C % 8 == 0 && q.C <= HA_MAXC) {
+  if (q.x_hi && !q.target && q.C % 8 == 0 && q.C <= HA_MAXC) {
     // decode (no target): the asynchronous kernel; with the loss epilogue its 8 warps per SM cannot hide the target
     // loads and gradient stores, and the synchronous strip kernel below is faster (0.26 vs 0.29 ms at 1280x640x2)
     const int smem = HA_STAGES * HA_STAGE_BYTES + 9 * q.C * 16;

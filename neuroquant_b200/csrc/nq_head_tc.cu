@@ -36,6 +36,7 @@ struct HeadTcParams {
   const float* wk;           // [9][Cs][4] fp32 head weights as nq_pack_weight lays them out
   const float* bias;         // [>= 3]
   const float* target;       // (n, 3, h, w) or null
+  const uint8_t* target_u8;  // (n, 3, h, w) uint8 frames (value / 255, datasets.py:8-54) or null; at most one of the two
   float* img;                // (n, 3, h, w) or null
   float* loss_sum;
   uint8_t* dz;               // split-bf16 planes (n, h, w, 8) or null
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
     // ===================== epilogue: TMEM -> staging, then the nine shifted adds per output =====================
     const int q = warp & 3, half = warp >> 2;
     const int64_t plane = (int64_t)p.h * p.w;
+    const bool has_target = p.target != nullptr || p.target_u8 != nullptr;
     const float b0 = p.bias[0], b1 = p.bias[1], b2 = p.bias[2];
     float loss = 0.f;
     uint32_t it = 0;
@@ -217,10 +219,12 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
         const int o = threadIdx.x + 256 * r;
         const int oy = o / HT_OW, ox = o - oy * HT_OW;
         const int py = ty * HT_OH + oy, px = tx * HT_OW + ox;
-        const bool ok = p.target != nullptr && o < HT_OH * HT_OW && py < p.h && px < p.w;
+        const bool ok = has_target && o < HT_OH * HT_OW && py < p.h && px < p.w;
         const int64_t off = (int64_t)img * 3 * plane + (int64_t)py * p.w + px;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tg[r][c] = ok ? __ldg(p.target + off + c * plane) : 0.f;
+        for (int c = 0; c < 3; ++c)
+          tg[r][c] = !ok ? 0.f : (p.target ? __ldg(p.target + off + c * plane)
+                                           : __fdiv_rn((float)__ldg(p.target_u8 + off + c * plane), 255.0f));
       }
       hbar_wait(T_FULL + acc * 8, (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
             dout = outv * (1.0f - outv);
           }
           if (p.img) p.img[off + c * plane] = outv;
-          if (p.target) {
+          if (has_target) {
             const float dlt = outv - tg[r][c];
             const float a = fabsf(dlt);
             if (p.p == 2.0f) {
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // staging free for the next block
     }
-    if (p.target && p.loss_sum) {
+    if (has_target && p.loss_sum) {
       loss = warp_sum(loss);
       if (lane == 0 && loss != 0.f) atomicAdd(p.loss_sum, loss);
     }
@@ -325,9 +329,10 @@ int check_conv_desc(const nq_conv_desc* d);
 using namespace nq;
 
 // Same contract as nq_head_fwd_loss_split (include/neuroquant_b200.h).
-extern "C" int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
-                                       int out_bias, const float* target, float p, float mean_pixels, float* img,
-                                       float* loss_sum, void* dz_head_split, void* stream) {
+static int head_tapexp_launch(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                              int out_bias, const float* target_f32, const uint8_t* target_u8, float p, float mean_pixels, float* img,
+                              float* loss_sum, void* dz_head_split, void* stream) {
+  const void* target = target_f32 ? (const void*)target_f32 : (const void*)target_u8;
   int st = check_conv_desc(d);
   if (st) return st;
   if (d->ksize != 3 || d->rh != 1 || d->rw != 1 || d->cout != 3 || d->cg != 4) return NQ_ERR_BAD_SHAPE;
@@ -340,7 +345,7 @@ extern "C" int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_spli
   const size_t pix = (size_t)d->n * d->h * d->w;
   q.x = reinterpret_cast<const uint8_t*>(x_split);
   q.x_plane_bytes = pix * d->cin_p * 2;
-  q.wk = w_head; q.bias = bias_head; q.target = target; q.img = img; q.loss_sum = loss_sum;
+  q.wk = w_head; q.bias = bias_head; q.target = target_f32; q.target_u8 = target_u8; q.img = img; q.loss_sum = loss_sum;
   q.dz = reinterpret_cast<uint8_t*>(dz_head_split);
   q.dz_plane_bytes = pix * 16;
   q.n = d->n; q.h = d->h; q.w = d->w; q.Cs = d->cin_p; q.C16 = (d->cin_p + 15) / 16 * 16;
@@ -358,6 +363,22 @@ extern "C" int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_spli
   head_tapexp_kernel<<<grid, HT_THREADS, smem, as_stream(stream)>>>(q);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
+}
+
+extern "C" int nq_head_fwd_loss_tapexp(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                                       int out_bias, const float* target, float p, float mean_pixels, float* img,
+                                       float* loss_sum, void* dz_head_split, void* stream) {
+  return head_tapexp_launch(d, x_split, w_head, bias_head, out_bias, target, nullptr, p, mean_pixels, img, loss_sum, dz_head_split, stream);
+}
+
+// Same with the target frames as the data set stores them: uint8 (n, 3, h, w); the kernel evaluates value / 255 in fp32
+// (IEEE division, bit-identical to `read_image(...) / 255.0`, videosets/datasets.py:8-54) -- a quarter of the bytes over
+// PCIe and out of HBM.
+extern "C" int nq_head_fwd_loss_tapexp_u8(const nq_conv_desc* d, const void* x_split, const float* w_head, const float* bias_head,
+                                          int out_bias, const uint8_t* target_u8, float p, float mean_pixels, float* img,
+                                          float* loss_sum, void* dz_head_split, void* stream) {
+  if (!target_u8) return NQ_ERR_BAD_ARG;
+  return head_tapexp_launch(d, x_split, w_head, bias_head, out_bias, nullptr, target_u8, p, mean_pixels, img, loss_sum, dz_head_split, stream);
 }
 
 // ================================================================================================

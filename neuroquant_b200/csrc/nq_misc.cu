@@ -30,9 +30,11 @@ static inline int grid_for(int64_t numel, int block = 256) {
 // lane `lane` (n <= 256 -> R <= 8).  Butterflies over bits 0-4 are lane exchanges, over bits 5-7 are
 // register exchanges.  Same stage order (h = 1, 2, 4, ...) and operand order (a+b, a-b) as the
 // Sylvester butterfly the reference's hadamard_transform package performs.
+// src and dst MAY ALIAS (the engine rotates in place): neither is __restrict__, and a warp reads its whole vector
+// into registers before it stores any of it, so in-place operation is well defined.
 // ---------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(256) fwht_kernel(const float* __restrict__ src, float* __restrict__ dst,
+__global__ void __launch_bounds__(256) fwht_kernel(const float* src, float* dst,
                                                    int64_t n_vectors, int n, int64_t inner,
                                                    int64_t outer_stride, float norm) {
   const int lane = threadIdx.x & 31;
@@ -711,6 +713,42 @@ extern "C" int nq_act_bwd_unshuffle(const float* dy, const float* z, int n, int 
   if (act != 0 && !z) return NQ_ERR_BAD_ARG;
   const int64_t total = (int64_t)n * h * rh * w * rw * cg;
   act_bwd_unshuffle_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(dy, z, n, h, w, rh, rw, cg, act, dz);
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame ingest: uint8 frames as the data set stores them -> fp32 in [0, 1], value / 255 with an IEEE fp32 division
+// (bit-identical to `read_image(...) / 255.0`, videosets/datasets.py:8-54).  16 values per thread: one 16-byte load,
+// four 16-byte stores.  Used where a kernel wants fp32 targets (FFMA head, wide heads, PSNR); the default head kernel
+// reads the uint8 frames directly (nq_head_fwd_loss_tapexp_u8).
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t numel) {
+  const int64_t n16 = numel >> 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(dst) + i * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = make_float4(__fdiv_rn((float)(w[k] & 0xffu), 255.0f), __fdiv_rn((float)((w[k] >> 8) & 0xffu), 255.0f),
+                         __fdiv_rn((float)((w[k] >> 16) & 0xffu), 255.0f), __fdiv_rn((float)(w[k] >> 24), 255.0f));
+  }
+  for (int64_t i = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    dst[i] = __fdiv_rn((float)src[i], 255.0f);
+}
+}  // namespace nq
+
+extern "C" int nq_u8_to_f32(const uint8_t* src, float* dst, int64_t numel, void* stream) {
+  if (!src || !dst || numel <= 0) return NQ_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return NQ_ERR_BAD_ARG;
+  int64_t blocks = ((numel >> 4) + 255) / 256;
+  const int64_t cap = (int64_t)nq::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  nq::u8_to_f32_kernel<<<(unsigned)blocks, 256, 0, nq::as_stream(stream)>>>(src, dst, numel);
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }

@@ -11,8 +11,11 @@ quant_model.py:28-29):
   * lp_loss + LossFunction.collect_round_loss (quantizer.py:66-73, calib_model.py:39-47)
   * autograd of all of the above + torch.optim.Adam.step (calib_model.py:145-165, :206-226)
 
-Data layout in HBM (all fp32 in this revision):
-  activations  NHWC, channels padded to a multiple of 4, pads kept at zero
+Data layout in HBM:
+  activations  tensor-core engine (default): "split-bf16" NHWC -- two bf16 planes hi = bf16(v), lo = bf16(v - hi), channels
+               padded to 16 (8 for the head's input), pads kept at zero; exact-fp32 FFMA engine (NQ_CONV=simt): fp32 NHWC,
+               channels padded to 4
+  targets      (n, 3, H, W) fp32 in [0, 1], or uint8 as the data set stores them (value / 255 evaluated on the device)
   weights      reference layout (C_out, C_in[pow2 if rotated], k, k) for everything the quantiser
                touches (weight, alpha, delta, zero_point, codes);  "packed" GEMM layouts
                (include/neuroquant_b200.h) for what the convolutions read
@@ -530,17 +533,39 @@ class DecoderEngine:
                                   L.ptr(bp), L.ptr(z), p.x[i + 1].data_ptr(), st), "nq_tc_conv_fwd")
             self.launches += 1
         wk, _, bp, _, _ = self._packed[last]
+        tapexp = self.use_tc and not self.head_tc and self.head_tapexp and p.desc[last].cin_p <= 64
+        target_u8 = None
         if target is not None:
-            target = target.detach().contiguous().float()
+            target = target.detach().contiguous()
             if tuple(target.shape) != (n, 3, p.H, p.W):
                 raise L.NqError(f"target shape {tuple(target.shape)} != {(n, 3, p.H, p.W)}")
+            if target.dtype == torch.uint8:
+                # frames as the data set stores them (videosets/datasets.py:8-54): value / 255 is evaluated on the device,
+                # inside the head kernel where it has a uint8 variant, else by the ingest kernel into a plan buffer
+                if not target.is_cuda:
+                    raise L.NqError("neuroquant_b200 kernels need CUDA tensors (there is no CPU fallback)")
+                if tapexp:
+                    target_u8 = target
+                else:
+                    if not hasattr(p, "tgt_f32"):
+                        p.tgt_f32 = torch.empty(n, 3, p.H, p.W, device=self.device)
+                    L.check(L.lib.nq_u8_to_f32(target.data_ptr(), L.ptr(p.tgt_f32), target.numel(), st), "nq_u8_to_f32")
+                    self.launches += 1
+                    target = p.tgt_f32
+            else:
+                target = target.float()
             p.loss.zero_()
             mp = float(mean_pixels if mean_pixels is not None else n * p.H * p.W)
         else:
             mp = 1.0
         want_dz = train and target is not None
-        if self.use_tc and not self.head_tc:
-            head_fn = L.lib.nq_head_fwd_loss_tapexp if (self.head_tapexp and p.desc[last].cin_p <= 64) else L.lib.nq_head_fwd_loss_split
+        if target_u8 is not None:
+            L.check(self._run("head_fwd_loss", p.desc[last], L.lib.nq_head_fwd_loss_tapexp_u8, C.byref(p.desc[last]),
+                              p.x[last].data_ptr(), L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], target_u8.data_ptr(),
+                              float(p_norm), mp, L.ptr(p.img) if want_img else None, L.ptr(p.loss),
+                              p.dz[last].data_ptr() if want_dz else None, st), "nq_head_fwd_loss_tapexp_u8")
+        elif self.use_tc and not self.head_tc:
+            head_fn = L.lib.nq_head_fwd_loss_tapexp if tapexp else L.lib.nq_head_fwd_loss_split
             L.check(self._run("head_fwd_loss", p.desc[last], head_fn, C.byref(p.desc[last]),
                               p.x[last].data_ptr(), L.ptr(wk), L.ptr(bp), _HEAD[self.geoms[last].act], L.ptr(target),
                               float(p_norm), mp, L.ptr(p.img) if (want_img or target is None) else None,
@@ -616,8 +641,8 @@ class DecoderEngine:
                     pl = self._wg_plan(d)
                     if pl is None:
                         raise NotImplementedError(
-                            f"stage {i}: cin_p * k = {d.cin_p * d.ksize} > 504 accumulator rows -- no tensor-core wgrad plan "
-                            "(12M-class decoders); train such models with NQ_CONV=simt")
+                            f"stage {i}: no tensor-core weight-gradient plan for cin_p = {d.cin_p}, k = {d.ksize} "
+                            "(nq_tc_plan_wgrad slices the input channels until the accumulators fit TMEM and found no slicing)")
                     p.dwk.append(torch.empty(d.kdim + 4, pl.N, device=self.device))
                     p.ws.append((torch.empty(pl.workspace_floats, device=self.device), pl))
                     if i == last:

@@ -6,8 +6,9 @@ output-directory naming, same checkpoint file name and whole-object pickle layou
         --iters_w 21000 --weight 0.01 --b_start 20 --b_end 2 --warmup 0.2 --lr 0.003 --ckpt epoch300.pth
     torchrun --nproc-per-node 8 -m neuroquant_b200.methods.calibrate_network ...   # frame-sharded data parallel
 
-Flags the reference parses but ignores are kept and ignored the same way: --seed
-(seed_all is never called), --opt_mode (kwargs hard-code 'mse'), --input_prob (logged / file name only).
+Flags the reference parses but ignores are kept and ignored the same way: --opt_mode (kwargs
+hard-code 'mse'), --input_prob (logged / file name only).  --seed: the reference never calls seed_all, so its shuffle is
+unseeded; here it seeds the mini-batch shuffle, because data-parallel ranks must draw the same batches.
 """
 import argparse
 import logging
@@ -74,7 +75,10 @@ def calibrate(args, cfg):
     train_idx, args.val_ind_list = data_split(list(range(args.full_data_length)), split, False, 0)
     gen = torch.Generator()
     gen.manual_seed(args.seed)  # every rank must draw the same shuffled batches; the reference is unseeded (Q7)
-    train_loader = torch.utils.data.DataLoader(Subset(full_dataset, train_idx), batch_size=args.batch_size, shuffle=True,
+    # the calibration loader hands out uint8 frames (value / 255 happens inside the head-loss kernel): a quarter of the
+    # PCIe bytes in the first epoch and of the resident clip in HBM afterwards
+    train_dataset = VideoDataSet(cfg, args, as_uint8=True)
+    train_loader = torch.utils.data.DataLoader(Subset(train_dataset, train_idx), batch_size=args.batch_size, shuffle=True,
                                                num_workers=cfg["workers"], pin_memory=True, drop_last=True,
                                                worker_init_fn=worker_init_fn, persistent_workers=cfg["workers"] > 0,
                                                generator=gen)

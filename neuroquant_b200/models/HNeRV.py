@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from ._layers import ConvNeXt, NeRVBlock
-from ..runner import DecoderRunner
+from ..runner import DecoderRunner, EmbedList
 
 
 class HNeRV(nn.Module):
@@ -39,14 +39,14 @@ class HNeRV(nn.Module):
         return self.encoder(img)
 
     def decode(self, img_embed):
-        """Returns (img_out, embed_list, dec_time) as HNeRV.py:49-71.  embed_list holds only the input
-        embedding: the intermediate feature maps live in the engine's NHWC buffers (nothing on the hot
-        path consumes them; DecoderRunner.features() materialises them on request)."""
+        """Returns (img_out, embed_list, dec_time) as HNeRV.py:49-71.  embed_list[0] is the input embedding; the stem's and
+        the blocks' outputs (entries 1..) live in the engine's NHWC buffers and are converted on first access
+        (runner.EmbedList) -- nothing on the hot path consumes them."""
         dec_start = time.time()
         img_out = DecoderRunner.of(self).decode(img_embed)
         if torch.cuda.is_available():
             torch.cuda.synchronize()  # HNeRV.py:67-68: dec_time is a host wall-clock measurement
-        return img_out, [img_embed], time.time() - dec_start
+        return img_out, EmbedList(DecoderRunner.of(self), img_embed, True), time.time() - dec_start
 
     def forward(self, input):
         return self.decode(self.encode(input))

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from ._layers import NeRVBlock, PositionEncoding
-from ..runner import DecoderRunner
+from ..runner import DecoderRunner, EmbedList
 
 
 class NeRV(nn.Module):
@@ -39,7 +39,7 @@ class NeRV(nn.Module):
         img_out = DecoderRunner.of(self).decode(img_embed)
         if torch.cuda.is_available():
             torch.cuda.synchronize()  # NeRV.py:61-62
-        return img_out, [img_embed], time.time() - dec_start
+        return img_out, EmbedList(DecoderRunner.of(self), img_embed, False), time.time() - dec_start
 
     def forward(self, input):
         return self.decode(self.encode(input))

@@ -30,6 +30,7 @@ from .. import _lib as L
 from ..calibration import LinearTempDecay
 from ..engine import AdamState, ROUND_SOFT, StageGeom, _ACT, _ACT_SAVED_GRAD, _pad
 from ..runner import DecoderRunner
+from .data_utils import quantize_model_till  # noqa: F401  (data_utils.py:261-272)
 from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule
 from .quantizer import AdaRoundQuantizer
@@ -260,16 +261,6 @@ def save_inp_oup_data(model, runner: DecoderRunner, k: int, cali_data: torch.Ten
             inps.append(syms[-1])
     model.set_quant_state(False)
     return (torch.cat(inps), torch.cat(syms)), torch.cat(outs)
-
-
-def quantize_model_till(model, layer):
-    """data_utils.py:261-272: quantise every layer / block up to and including `layer`, in module order."""
-    model.set_quant_state(False)
-    for _, module in model.named_modules():
-        if isinstance(module, (QuantModule, BaseQuantBlock)):
-            module.set_quant_state(True)
-        if module is layer:
-            break
 
 
 def block_output_grads(model, runner: DecoderRunner, block, k: int, cali_data: torch.Tensor, layer: bool = False) -> torch.Tensor:

@@ -6,7 +6,7 @@ import logging
 import torch
 import torch.nn as nn
 
-from ..calibration import CalibrationLoop, LinearTempDecay
+from ..calibration import CalibrationLoop, HostBatchPipe, LinearTempDecay
 from ..parallel import shard_indices, world_info
 from ..runner import DecoderRunner
 from .quant_layer import QuantModule
@@ -60,39 +60,121 @@ class LossFunction:
         return total
 
 
-class _FrameSource:
-    """Feeds the loop from the reference's `gt` DataLoader.  Frames are decoded by the loader ONCE (first
-    epoch) and kept resident in HBM; later epochs only draw index batches from `gt.batch_sampler`, so
-    the PNG decode + 20 MB host-to-device copy per iteration of calib_model.py:150 leaves the loop."""
+# facts about the last model_reconstruction() of this process (bench.py reports the host -> device bytes per step)
+LAST_RUN = {}
 
-    def __init__(self, gt, cali_data: torch.Tensor, rank: int, world: int):
-        self.gt, self.cali, self.rank, self.world = gt, cali_data, rank, world
+
+class _Staged:
+    """One mini-batch whose host -> device copy is in flight (HostBatchPipe slot)."""
+    __slots__ = ("idx", "n_global", "resident")
+
+    def __init__(self, idx, n_global, resident):
+        self.idx, self.n_global, self.resident = idx, n_global, resident
+
+
+class _FrameSource:
+    """Feeds the loop from the reference's `gt` loader (dicts with 'img' and 'idx', calib_model.py:147-151).
+
+    Frames may arrive as fp32 in [0, 1] (the reference's `read_image / 255`) or as uint8 (VideoDataSet(as_uint8=True):
+    a quarter of the bytes over PCIe and in HBM; value / 255 is evaluated inside the head kernel).  Batches coming from
+    the loader go through a HostBatchPipe: the copy of batch k+1 runs on a side stream under the kernels of batch k.
+
+    residency 'hbm'    frames are decoded by the loader ONCE (first epoch) and kept resident in HBM; later epochs only
+                       draw index batches from `gt.batch_sampler`, so the PNG decode + host-to-device copy per
+                       iteration of calib_model.py:150 leaves the loop.  Every rank copies the whole global batch.
+              'stream' every iteration takes its frames from the loader (clips that do not fit in HBM); a rank copies
+                       only its own shard of the global batch.
+              'auto'   'hbm' when the clip takes less than a quarter of the free device memory."""
+
+    def __init__(self, gt, cali_data: torch.Tensor, rank: int, world: int, residency: str = "auto", device=None):
+        self.gt, self.rank, self.world = gt, rank, world
+        self.dev = torch.device(device) if device is not None else (cali_data.device if cali_data.is_cuda else torch.device("cuda"))
+        self.cali_host = None if cali_data.is_cuda else cali_data
+        self.cali = cali_data if cali_data.is_cuda else None
+        if residency not in ("auto", "hbm", "stream"):
+            raise ValueError(f"residency {residency!r}: expected 'auto', 'hbm' or 'stream'")
+        self.residency = residency
         self.frames = None
         self.have = None
+        self.pipe = None
+        self.h2d_bytes = 0  # bytes this rank copied host -> device (bench.py reports it per step)
+
+    # -- host side ---------------------------------------------------------------------------------------------------
+    def _decide(self, img: torch.Tensor):
+        n_frames = (self.cali if self.cali is not None else self.cali_host).shape[0]
+        if self.residency == "auto":
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            self.residency = "hbm" if n_frames * img[0].numel() * img.element_size() < free // 4 else "stream"
+        if self.residency == "hbm":
+            if self.cali is None:
+                self.cali = self.cali_host.to(self.dev)
+            self.frames = torch.empty((n_frames,) + tuple(img.shape[1:]), device=self.dev, dtype=img.dtype)
+            self.have = torch.zeros(n_frames, dtype=torch.bool)
+
+    def _stage(self, sample) -> _Staged:
+        img = sample["img"]
+        idx = torch.as_tensor(sample["idx"]).view(-1).cpu()
+        if img.dtype not in (torch.uint8, torch.float32):
+            img = img.float()
+        if self.frames is None and self.residency != "stream":
+            self._decide(img)
+        resident = self.residency == "hbm"
+        mine = idx if resident else shard_indices(idx, self.rank, self.world)
+        img_m = img if (resident or self.world == 1) else img[self.rank::self.world]
+        tensors = [img_m]
+        if self.cali is None:  # embeddings on the host as well: this batch's rows travel with the frames
+            tensors.append(self.cali_host[mine].contiguous())
+        specs = [(tuple(t.shape), t.dtype) for t in tensors]
+        if self.pipe is None or self.pipe.specs != specs:
+            if self.pipe is not None:  # ragged last batch (drop_last=False): drain, then a pipe of the new shape
+                torch.cuda.current_stream().synchronize()
+                self.pipe.stream.synchronize()
+            self.pipe = HostBatchPipe(specs, device=self.dev, depth=3)
+        self.pipe.put(*tensors)
+        self.h2d_bytes += sum(t.numel() * t.element_size() for t in tensors if not t.is_cuda)
+        return _Staged(idx, int(idx.numel()), resident)
 
     def batches(self):
-        if self.have is not None and bool(self.have.all()) and hasattr(self.gt, "batch_sampler") and \
-                self.gt.batch_sampler is not None:
-            for idx in self.gt.batch_sampler:
-                yield list(idx)
-        else:
-            for sample in self.gt:
-                yield sample
+        if self.have is not None and bool(self.have.all()):
+            sampler = getattr(self.gt, "batch_sampler", None)
+            if sampler is not None:
+                for idx in sampler:
+                    yield list(idx)
+            else:  # a plain sequence of sample dicts: its index batches, without touching the frames again
+                for sample in self.gt:
+                    yield torch.as_tensor(sample["idx"]).view(-1).tolist()
+            return
+        it = iter(self.gt)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = self._stage(next(it))  # batch k+1 starts its copy before batch k is consumed
+            except StopIteration:
+                nxt = None
+            yield cur
 
+    # -- device side -------------------------------------------------------------------------------------------------
     def fetch(self, item):
-        dev = self.cali.device
-        if isinstance(item, dict):
-            idx = torch.as_tensor(item["idx"]).view(-1).to(dev)
-            img = item["img"].to(dev, non_blocking=True).float()
-            if self.frames is None:
-                self.frames = torch.empty((self.cali.shape[0],) + tuple(img.shape[1:]), device=dev)
-                self.have = torch.zeros(self.cali.shape[0], dtype=torch.bool, device=dev)
-            self.frames[idx] = img
-            self.have[idx] = True
-        else:
-            idx = torch.as_tensor(item, device=dev).view(-1)
+        if isinstance(item, _Staged):
+            got = self.pipe.get()
+            img = got[0]
+            if item.resident:
+                idx_d = item.idx.to(self.dev)
+                self.frames[idx_d] = img
+                self.have[item.idx] = True
+                mine = shard_indices(idx_d, self.rank, self.world)
+                return self.cali[mine], self.frames[mine], item.n_global
+            if self.cali is None:
+                return got[1], img, item.n_global
+            mine = shard_indices(item.idx, self.rank, self.world).to(self.dev)
+            return self.cali[mine], img, item.n_global
+        idx = torch.as_tensor(item, device=self.dev).view(-1)
         mine = shard_indices(idx, self.rank, self.world)
-        return self.cali[mine], self.frames[mine]
+        return self.cali[mine], self.frames[mine], int(idx.numel())
 
 
 def _install_adaround(runner: DecoderRunner, round_mode: str):
@@ -115,11 +197,17 @@ def _install_adaround(runner: DecoderRunner, round_mode: str):
 
 def model_reconstruction(model, cali_data: torch.Tensor, gt, arch: str = "hnerv", batch_size: int = 8,
                          iters: int = 20000, weight: float = 0.01, opt_mode: str = "mse", hadamard: bool = True,
-                         b_range: tuple = (20, 2), warmup: float = 0.0, p: float = 2.0, lr: float = 0.0015):
+                         b_range: tuple = (20, 2), warmup: float = 0.0, p: float = 2.0, lr: float = 0.0015, *,
+                         frame_residency: str = "auto", on_iteration=None):
     """Network-wise calibration (calib_model.py:92-240).  `model` is a QuantModel; `cali_data` the decoder
-    inputs of every frame; `gt` the frame loader (dicts with 'img' and 'idx').  Under torch.distributed
-    every rank calls this with the same arguments: mini-batches are sharded by frame and the weight
-    gradients are all-reduced (neuroquant_b200/calibration.py)."""
+    inputs of every frame; `gt` the frame loader (dicts with 'img' -- fp32 in [0, 1] or uint8 -- and 'idx').  Under
+    torch.distributed every rank calls this with the same arguments: mini-batches are sharded by frame and the weight
+    gradients are all-reduced (neuroquant_b200/calibration.py).
+
+    Additive, keyword-only: `frame_residency` ('auto' | 'hbm' | 'stream', see _FrameSource) and
+    `on_iteration(phase, count, loss)` -- called after every iteration with the reconstruction loss of that iteration as
+    a DEVICE scalar (no synchronisation; this rank's share under data parallelism): progress reporting / loss read-back
+    without waiting for the reference's one log line per 500 iterations."""
     if arch not in ("hnerv", "nerv"):
         raise ValueError
     if opt_mode != "mse":
@@ -130,11 +218,13 @@ def model_reconstruction(model, cali_data: torch.Tensor, gt, arch: str = "hnerv"
     runner.sync()  # initialises the step sizes if no quantised forward has run yet
     eng = runner.engine
     rank, world, group = world_info()
-    src = _FrameSource(gt, cali_data, rank, world)
+    src = _FrameSource(gt, cali_data, rank, world, residency=frame_residency, device=eng.device)
+    LAST_RUN.clear()
+    LAST_RUN["_src"] = src  # live during the run (bench.py samples its byte counter from the iteration callback)
     n_batches = len(gt)
     gb = getattr(gt, "batch_size", None) or batch_size
     loop = CalibrationLoop(eng, src.fetch, n_batches, iters, weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr,
-                           group=group, global_batch=gb)
+                           group=group, global_batch=gb, on_iteration=on_iteration)
     model.train()
     loop.run_phase1(src.batches)
     torch.cuda.empty_cache()
@@ -143,3 +233,5 @@ def model_reconstruction(model, cali_data: torch.Tensor, gt, arch: str = "hnerv"
     for l in runner.layers:  # calib_model.py:231-240: weight quantisers go hard, bias quantisers stay soft (Q3)
         l.weight_quantizer.soft_targets = False
     runner._key = None
+    LAST_RUN.pop("_src", None)
+    LAST_RUN.update(h2d_bytes=src.h2d_bytes, residency=src.residency, launches=eng.launches)

@@ -48,6 +48,47 @@ def conv2d_nchw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     return out
 
 
+class EmbedList(list):
+    """`embed_list` of HNeRV.decode / NeRV.decode (HNeRV.py:50-61, NeRV.py:45-56): [input embedding, output of the stem,
+    output of every block].  Only entry 0 is consumed anywhere in the reference (calibrate_network.py:104: the calibration
+    inputs), so the feature maps -- which live in the engine's NHWC buffers -- are converted to NCHW tensors on first
+    access beyond entry 0 (one more decode of the same embedding + one layout kernel per stage)."""
+
+    def __init__(self, runner: "DecoderRunner", embed: torch.Tensor, unfold_stem: bool):
+        super().__init__([embed])
+        self._runner, self._unfold, self._full = runner, unfold_stem, False
+        self._n = len(runner.layers)  # input + stem + blocks (the head's output is not listed)
+
+    def _fill(self):
+        if self._full:
+            return
+        self._full = True
+        r = self._runner
+        feats = r.features(list.__getitem__(self, 0))[: self._n - 1]
+        if self._unfold and (r.geoms[0].rh, r.geoms[0].rw) != (1, 1):  # HNeRV lists the stem output before the fold
+            g = r.geoms[0]
+            n, c, hh, ww = feats[0].shape
+            feats[0] = feats[0].view(n, c, hh // g.rh, g.rh, ww // g.rw, g.rw).permute(0, 1, 3, 5, 2, 4).reshape(
+                n, c * g.rh * g.rw, hh // g.rh, ww // g.rw)
+        list.extend(self, feats)
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if not (isinstance(i, int) and (i == 0 or i == -self._n)):
+            self._fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+    def __reduce__(self):
+        self._fill()
+        return (list, (list(list.__iter__(self)),))
+
+
 class DecoderRunner:
     """One per model instance (cached in the model's __dict__, never pickled)."""
 
@@ -99,7 +140,7 @@ class DecoderRunner:
         for l, g, q, had in zip(layers, geoms, self._quant, hadamard):
             if l.bias is None:
                 raise NotImplementedError("decoder convolutions without bias")
-            st = QuantStage(g, l.weight.data, l.bias.data, 8, had and q)
+            st = QuantStage(g, l.weight.detach(), l.bias.detach(), 8, had and q)
             if q and had:
                 st.w_src = l.hadamard_weight  # the module's own rotated copy (quant_layer.py:49)
                 st.codes_w = torch.empty_like(st.w_src)
@@ -114,6 +155,10 @@ class DecoderRunner:
 
     # ------------------------------------------------------------------ module state -> engine state
     def sync(self):
+        """Module state -> engine state.  The packed-weight cache is keyed on (data_ptr, version counter) of every tensor
+        the engine aliases; the aliases are `.detach()` views, which SHARE the owning Parameter's version counter (a
+        `.data` alias would get a fresh one that never moves), so `load_state_dict` / in-place updates by torch invalidate
+        the cache.  Kernels of this library that update tensors in place (Adam) call `engine.invalidate()` themselves."""
         from .quantization.quantizer import AdaRoundQuantizer
 
         eng = self.engine
@@ -122,8 +167,8 @@ class DecoderRunner:
         if not any(on):
             eng.mode = "off"
             for l, st in zip(self.layers, eng.stages):
-                src = l.org_weight if hasattr(l, "org_weight") else l.weight.data
-                srb = l.org_bias if hasattr(l, "org_bias") else l.bias.data
+                src = l.org_weight if hasattr(l, "org_weight") else l.weight.detach()
+                srb = l.org_bias if hasattr(l, "org_bias") else l.bias.detach()
                 st.weight, st.bias = src, srb
                 key += [src.data_ptr(), src._version, srb.data_ptr(), srb._version]
         else:
@@ -144,13 +189,13 @@ class DecoderRunner:
                     eng.stage_state = None
             for l, st, o in zip(self.layers, eng.stages, on):
                 if not o:  # full-precision stage inside a partly quantised decoder
-                    src = l.org_weight if hasattr(l, "org_weight") else l.weight.data
-                    srb = l.org_bias if hasattr(l, "org_bias") else l.bias.data
+                    src = l.org_weight if hasattr(l, "org_weight") else l.weight.detach()
+                    srb = l.org_bias if hasattr(l, "org_bias") else l.bias.detach()
                     st.weight, st.bias = src, srb
                     key += [src.data_ptr(), src._version, srb.data_ptr(), srb._version]
                     continue
                 wq, bq = l.weight_quantizer, l.bias_quantizer
-                st.weight, st.bias = l.weight.data, l.bias.data
+                st.weight, st.bias = l.weight.detach(), l.bias.detach()
                 if not st.hadamard:
                     st.w_src = st.weight
                 st.set_bits(wq.n_bits)
@@ -162,11 +207,11 @@ class DecoderRunner:
                 if not bq.inited if hasattr(bq, "inited") else False:
                     d, z = bq.init_quantization_scale(st.bias, bq.channel_wise)
                     bq.delta, bq.zero_point, bq.inited = nn.Parameter(d), z, True
-                st.delta_w, st.zp_w = wq.delta.data, wq.zero_point
-                st.delta_b, st.zp_b = bq.delta.data, bq.zero_point
+                st.delta_w, st.zp_w = wq.delta.detach(), wq.zero_point
+                st.delta_b, st.zp_b = bq.delta.detach(), bq.zero_point
                 is_ada = isinstance(wq, AdaRoundQuantizer)
-                st.alpha_w = wq.alpha.data if is_ada else None
-                st.alpha_b = bq.alpha.data if is_ada else None
+                st.alpha_w = wq.alpha.detach() if is_ada else None
+                st.alpha_b = bq.alpha.detach() if is_ada else None
                 for tns in (st.w_src, st.bias, st.delta_w, st.zp_w, st.delta_b, st.zp_b, st.alpha_w, st.alpha_b):
                     key += [None] if tns is None else [tns.data_ptr(), tns._version]
                 key += [wq.n_bits, eng.soft_w, eng.soft_b, is_ada, getattr(wq, "soft_targets", None), getattr(bq, "soft_targets", None)]

@@ -41,7 +41,13 @@ def test_quantmodel_matches_reference(tag):
     cali = t(g["cali"]).cuda()
     out, embed_list, dec_time = model.decode(cali[:2])
     assert np.abs(out.cpu().numpy() - g["fp_out"]).max() < 2e-5 and dec_time > 0
-    assert len(embed_list) == 1 and torch.equal(embed_list[0], cali[:2])  # only the input embedding is returned
+    # embed_list as the reference returns it: the input embedding, then the stem's and every block's output
+    assert torch.equal(embed_list[0], cali[:2])
+    n_feat = sum(1 for k in g.files if k.startswith("fp_embed"))
+    assert len(embed_list) == n_feat
+    for i in range(n_feat):
+        want = g[f"fp_embed{i}"]
+        assert tuple(embed_list[i].shape) == want.shape and np.abs(embed_list[i].cpu().numpy() - want).max() < 2e-5, i
     qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": cw(g),
                                                                                 "scale_method": "max"}).cuda()
     assert qnn.set_bitwidth(g["bits"].tolist()) == float(g["avg_bits"])
@@ -191,3 +197,62 @@ def test_omega_golden(tag):
     assert got == pytest.approx(want, rel=2e-3)
     assert got == pytest.approx(float(g["fisher_diag"]), rel=5e-3)
     assert np.allclose(fisher_diag(runner.engine, vec, batches, per_layer=True), gl["fisher_layers"], rtol=5e-3, atol=1e-4 * gl["fisher_layers"].max())
+
+
+def test_packed_weight_cache_follows_load_state_dict():
+    """the runner's packed-weight cache is keyed on the owning Parameters' version counters, so
+    decode -> load_state_dict(other weights) -> decode uses the NEW weights (a `.data` alias never changes version)."""
+    from neuroquant_b200.quantization import QuantModel
+    g, arch, cfg, model = build_model("tiny_hnerv")
+    cali = t(g["cali"]).cuda()
+    out0, _, _ = model.decode(cali[:2])
+    other = {k: v + 0.01 * torch.randn_like(v) for k, v in model.state_dict().items() if "encoder" not in k}
+    model.load_state_dict(other, strict=False)
+    out1, _, _ = model.decode(cali[:2])
+    assert (out1 - out0).abs().max() > 1e-4, "decode after load_state_dict still used the stale packed weights"
+    g2, _, _, fresh = build_model("tiny_hnerv")
+    fresh.load_state_dict(other, strict=False)
+    want, _, _ = fresh.decode(cali[:2])
+    assert torch.equal(out1, want)
+    # the quantised model too: in-place change of a weight through torch invalidates the cache
+    qnn = QuantModel(model, hadamard=False, weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"}).cuda()
+    qnn.set_bitwidth([6] * 7)
+    qnn.set_quant_state(True)
+    a, _, _ = qnn(cali[:2])
+    with torch.no_grad():
+        qnn.model.head_layer.weight.mul_(1.05)
+    b, _, _ = qnn(cali[:2])
+    assert (a - b).abs().max() > 1e-5
+
+
+def test_data_utils_surface():
+    """quantization.data_utils under the reference's import path and signatures (data_utils.py:45-272)."""
+    from neuroquant_b200.compat import install_reference_aliases
+    install_reference_aliases()
+    from quantization.data_utils import GetLayerGrad, GetLayerInpOut, quantize_model_till, save_grad_data, save_inp_oup_data
+    from neuroquant_b200.quantization import QuantModel
+    from tests.helpers import block_case
+    g, arch, cfg, model = build_model("tiny_hnerv")
+    cali = t(g["cali"]).cuda()
+    qnn = QuantModel(model, hadamard=False, weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"}).cuda()
+    qnn.set_bitwidth(g["bits"].tolist())
+    qnn.set_quant_state(True)
+    qnn(cali[:2])
+    block = qnn.model.decoder[3]
+    (inps, syms), outs = save_inp_oup_data(qnn, block, cali, asym=True, batch_size=4, keep_gpu=True, input_prob=True)
+    assert inps.shape == syms.shape and inps.shape[0] == outs.shape[0] == 8
+    (inps1,), outs1 = save_inp_oup_data(qnn, block, cali, asym=False, batch_size=4)
+    assert torch.equal(inps1, syms) and torch.equal(outs1, outs)
+    # the same numbers through the per-batch callable
+    inp_b, out_b, sym_b = GetLayerInpOut(qnn, block, cali.device, asym=True, input_prob=True)(cali[:4])
+    assert torch.equal(inp_b, inps[:4]) and torch.equal(out_b, outs[:4]) and torch.equal(sym_b, syms[:4])
+    feats = qnn.model.decode(cali[:4])[1]
+    qnn.set_quant_state(False)
+    feats = qnn.model.decode(cali[:4])[1]
+    assert (feats[3] - syms[:4]).abs().max() < 1e-6 and (feats[4] - outs[:4]).abs().max() < 1e-6
+    grads = save_grad_data(qnn, block, cali, batch_size=4)
+    raw = GetLayerGrad(qnn, block, cali.device)(cali[:2])
+    assert grads.shape == outs.shape and torch.allclose(grads[:2], raw.abs() + 1.0)
+    quantize_model_till(qnn, block)
+    states = [m.use_weight_quant for m in qnn.quant_modules()]
+    assert states == [True, True, True, True, False, False, False]

@@ -79,3 +79,38 @@ def test_reference_module_paths_resolve_after_aliasing():
             "print('aliases ok')\n") % root
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
     assert out.returncode == 0 and "aliases ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_oracle_workloads_agree_with_the_package():
+    """bench.py's CPU legs take their configurations and seeded weights from oracle/workloads.py (so that the reference arm
+    maps no product library); they must be the package's."""
+    import torch
+    from neuroquant_b200 import workloads as P
+    from oracle import workloads as W
+    assert set(P.WORKLOADS) == set(W.WORKLOADS)
+    for name in P.WORKLOADS:
+        assert P.WORKLOADS[name] == W.WORKLOADS[name]
+        arch, cfg = P.WORKLOADS[name]
+        assert P.embed_shape(cfg, arch) == W.embed_shape(cfg, arch)
+        geoms, _ = (P.geometry_from_cfg(cfg, arch), None)
+        _, h0, w0 = P.embed_shape(cfg, arch)
+        assert P.conv_flops(geoms, h0, w0, 2) == W.conv_flops(cfg, arch, 2)
+    arch, cfg = P.WORKLOADS["nerv-bunny-3m"]
+    _, params = P.random_decoder(cfg, arch, 903)
+    for (w, b), st in zip(params, W.random_stages(cfg, arch, 903)):
+        assert torch.equal(w, st.weight) and torch.equal(b, st.bias)
+
+
+def test_reference_staging_recipe_is_byte_exact():
+    """oracle/make_ref.py copies the reference's product Python byte for byte (MANIFEST.json holds both hashes); the
+    staged tree is what bench.py's `--impl reference` runs on the GPU box.  Skipped where nothing was staged."""
+    import hashlib, json, os
+    import pytest
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    man = os.path.join(root, "MANIFEST.json")
+    if not os.path.exists(man):
+        pytest.skip("oracle/_ref not staged (no /root/reference at build time)")
+    files = json.load(open(man))["files"]
+    assert "quantization/calib_model.py" in files and "models/HNeRV.py" in files
+    for rel, h in files.items():
+        assert hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest() == h["sha256"] == h["source_sha256"], rel
