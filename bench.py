@@ -58,7 +58,7 @@ def config_of(args, world):
             "frames_per_gpu_per_step": args.batch, "global_batch": args.batch * world, "hadamard": bool(args.hadamard),
             "parallelism": f"dp{world} (frame-sharded, NCCL all-reduce of dW)" if world > 1 else "single GPU",
             "l2": "no explicit flush: each step streams >2 GB of activations, far above the 126 MB L2",
-            "launch": "CUDA graph replay of the iteration on 1 GPU; the same fused launch sequence issued eagerly around the NCCL all-reduce when N > 1",
+            "launch": "CUDA graph replay of the iteration; when N > 1 the NCCL all-reduce of dW is a node of the same graph",
             **{k: v for k, v in HYPER.items()}}
 
 
@@ -486,6 +486,149 @@ def run_b200(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_omega(args, cfg, arch, geoms, params, world, rank):
+    """BASELINE.json configs[3]: bit_assign's Omega search.  A step = one search over ALL 7^L per-layer bit-width
+    configurations (bits 2..8) under an average-bit budget: the perturbation of every layer at every bit-width
+    (QuantModel + get_perturbation), the Gram table of Omega from 49 + 1029 forward jets over 10 mini-batches of 2 frames
+    (farmed over the ranks, one all-reduce of 1078 doubles), and the table search kernel.  metric: candidate
+    configurations scored per second, whole job; the reference scores ONE candidate per Hessian-vector product pass."""
+    import torch.distributed as dist
+    from neuroquant_b200.methods.bit_assign import search_bit_assignment
+    from neuroquant_b200.workloads import embed_shape
+
+    H, W = cfg["crop_h"], cfg["crop_w"]
+    c, h0, w0 = embed_shape(cfg, arch)
+    from neuroquant_b200.models import HNeRV, NeRV
+    torch.manual_seed(1)
+    fp = (HNeRV if arch == "hnerv" else NeRV)(dict(cfg)).cuda()
+    convs = [fp.decoder[0]] + [blk.conv[0] for blk in list(fp.decoder)[1:]] + [fp.head_layer]
+    with torch.no_grad():
+        for conv, (w, b) in zip(convs, params):
+            conv.weight.copy_(w.cuda())
+            conv.bias.copy_(b.cuda())
+    gen = torch.Generator().manual_seed(903)
+    n_b, B = 10, args.batch
+    frames = torch.rand(n_b * B, 3, H, W, generator=gen).cuda()
+    embeds = torch.randn(n_b * B, c, h0, w0, generator=gen).cuda()
+    # the loader hands out frames; the embeddings of a random-init encoder carry no information, so the decoder inputs
+    # are the seeded embeddings above (as in the calibration benchmark)
+    loader = [{"img": frames[i:i + B], "norm_idx": torch.arange(i, i + B).float().cuda() / (n_b * B), "idx": torch.arange(i, i + B)}
+              for i in range(0, n_b * B, B)]
+    lookup = {int(s["idx"][0]): embeds[int(s["idx"][0]):int(s["idx"][0]) + B] for s in loader}
+    state = {"i": 0}
+
+    def encode(x):
+        k = (state["i"] % n_b) * B
+        state["i"] += 1
+        return lookup[k]
+    fp.encode = encode
+    options = [2, 3, 4, 5, 6, 7, 8]
+    budget = 4.8
+
+    def one():
+        state["i"] = 0
+        return search_bit_assignment(arch, fp, loader, embeds, options, budget, batch_size=B)
+
+    if world > 1:
+        dist.barrier()
+    for _ in range(min(args.warmup, 1)):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    t0 = time.perf_counter()
+    e0.record()
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        bits, score, avg_bits, table = one()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms) / steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_cfg = len(options) ** table.L
+    out = {"metric": "omega_candidates_per_s", "value": n_cfg / (ms * 1e-3), "unit": "bit-width configurations scored / s",
+           "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "bf16x2 split operands, fp32 accumulate (tcgen05); table in f64",
+           "data": "synthetic",
+           "config": {"workload": f"{args.workload} bit_assign Omega search: {table.L} layers x bits {options}, average bits <= {budget}, "
+                                  f"{n_b} mini-batches of {B} frames", "configurations": n_cfg, "forward_jets": len(table.directions()),
+                      "parallelism": f"jets farmed over {world} GPU(s), one all-reduce of {len(table.directions())} doubles"},
+           "clocks": sampler.stop(t0, t1) if sampler else None, "gpu_launches": table.eng.launches,
+           "best": {"bits": bits, "omega": score, "avg_bits": avg_bits},
+           "reference_candidates": {"[6,5,4,5,5,6,6]": table.score([6, 5, 4, 5, 5, 6, 6]), "[2,3,4,6,4,4,2]": table.score([2, 3, 4, 6, 4, 4, 2])},
+           "seconds_per_jet": ms * 1e-3 / len(table.directions()) * world,
+           "e2e": {"value": n_cfg / (ms * 1e-3), "unit": "bit-width configurations scored / s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * len(table.directions()),
+                   "note": "the search starts from HBM-resident frames (20 frames); the table travels to the host once per search"}}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_omega_reference(args):
+    """The reference's own sensitivity_criterion('omega') (bit_assign.py:171-203: double-backward Hessian-vector product)
+    on the host cores, bounded: ONE candidate over `n_b` mini-batches of 2 frames instead of 10 (a full candidate takes
+    minutes on CPU); candidates/s is scaled to the full 10 batches."""
+    import copy
+    import importlib.util
+    from oracle import ref_runner
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if not ref_runner.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not staged: the Omega arm needs the reference's bit_assign.py"}))
+        return
+    from oracle import workloads as W
+    qnn, arch, cfg, _ = ref_runner.build(args.workload, [6, 5, 4, 5, 5, 6, 6], False)
+    spec = importlib.util.spec_from_file_location("ref_bit_assign", os.path.join(ref_runner.REF, "methods", "bit_assign.py"))
+    ba = importlib.util.module_from_spec(spec)
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self   # bit_assign.py:110 hard-codes .cuda(); this arm is the CPU path
+    try:
+        spec.loader.exec_module(ba)
+        gen = torch.Generator().manual_seed(903)
+        c, h, w = W.embed_shape(cfg, arch)
+        n_b = max(1, min(args.steps, 2))
+        frames = torch.rand(n_b * 2, 3, cfg["crop_h"], cfg["crop_w"], generator=gen)
+        embeds = torch.randn(n_b * 2, c, h, w, generator=gen)
+        with torch.no_grad():
+            qnn(embeds[:2])
+        net = ref_runner.build.fp_model   # the full-precision network (bit_assign.py:364 passes a copy of it)
+        loader = [{"img": frames[i:i + 2], "norm_idx": torch.arange(i, i + 2).float() / (2 * n_b), "idx": torch.arange(i, i + 2)}
+                  for i in range(0, 2 * n_b, 2)]
+        if arch == "hnerv":  # decoder inputs = the seeded embeddings (the random-init encoder is not part of the path timed)
+            calls = {"n": 0}
+
+            def encode(x):
+                k = 2 * (calls["n"] % n_b)
+                calls["n"] += 1
+                return embeds[k:k + 2]
+            net.encode = encode
+        t0 = time.perf_counter()
+        om = ba.sensitivity_criterion("omega", arch, net, qnn, loader, use_cuda=False)
+        dt = time.perf_counter() - t0
+    finally:
+        torch.Tensor.cuda = _cuda
+    per_candidate = dt / n_b * 10
+    val = 1.0 / per_candidate
+    unit = "bit-width configurations scored / s"
+    print(json.dumps({"impl": "reference", "metric": "omega_candidates_per_s", "value": val, "unit": unit, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_candidate, "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{args.workload} bit_assign Omega: one candidate = Hessian-vector product over 10 mini-batches of 2 frames"},
+                      "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "reference",
+                                       "sample": f"the reference's sensitivity_criterion('omega') over {n_b} of the 10 mini-batches "
+                                                 f"({dt:.1f} s), scaled to 10; omega = {float(om):.3e}"},
+                      "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def run_decode_only(args, eng, cfg, arch, geoms, world, rank, local):

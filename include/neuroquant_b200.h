@@ -454,6 +454,18 @@ int nq_lp_loss(const float* pred, const float* tgt, int64_t numel, float p, floa
 int nq_multi_dot(const float* const* a_ptrs, const float* const* b_ptrs, const int64_t* sizes,
                  int n_tensors, int mode, float* out, void* stream);
 
+/* bit_assign as a search (the reference scores a hand-written candidate list, methods/bit_assign.py:343-372, one
+ * Hessian-vector product each).  Omega is quadratic in the perturbation, so with the Gram table
+ * gram[(l, b), (m, b')] = v_l(b)^T H_lm v_m(b') (row-major (L * nb)^2 doubles, symmetric; option index fastest within a
+ * layer) the score of configuration (c_0 .. c_{L-1}) is sum_l gram[(l,c_l),(l,c_l)] + 2 sum_{l<m} gram[(l,c_l),(m,c_m)].
+ * Scores all nb^L configurations (index = sum_l c_l * nb^l) and returns the admissible one -- sum_l bits_weight[l * nb + c_l]
+ * <= budget -- of smallest score (ties: smallest index); best_index = -1 when none is admissible.  `scores` (optional,
+ * nb^L doubles) receives every admissible configuration's score, +inf elsewhere.  n_layers <= 8, n_options <= 16. */
+int nq_omega_search_workspace(int n_layers, int n_options, int64_t* n_configs, int64_t* workspace_bytes);
+int nq_omega_search(const double* gram, const double* bits_weight, int n_layers, int n_options, double budget,
+                    double* scores, void* workspace, int64_t workspace_bytes, double* best_score, int64_t* best_index,
+                    void* stream);
+
 /* PSNR per frame (utils.py:148-151): psnr[i] = -10 log10(mean((a_i - b_i)^2) + 1e-9), frames of
  * `frame_numel` elements. */
 int nq_psnr(const float* a, const float* b, int n_frames, int64_t frame_numel, float* psnr, void* stream);

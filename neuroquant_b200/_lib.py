@@ -148,6 +148,8 @@ def _load():
         "nq_qdrop_gather": (I, [P, P, P, P, F, I, I, L, P, P]),
         "nq_multi_dot": (I, [P, P, P, I, I, P, P]),
         "nq_psnr": (I, [P, P, I, L, P, P]),
+        "nq_omega_search_workspace": (I, [I, I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "nq_omega_search": (I, [P, P, I, I, D, P, P, L, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header/library drift: fail loudly

@@ -41,9 +41,11 @@ class LinearTempDecay:
 class GraphedStep:
     """One calibration iteration (forward, loss, backward, quantiser Jacobian, Adam) captured ONCE as a CUDA graph
     and replayed: ~100 kernel launches become one graph launch.  Inputs are copied into static buffers; the four
-    scalars that change per iteration go through a 16-byte device array (nq_*_dev kernels).  Single-GPU AdaRound
-    phase; the eager path stays for iterations that log and, by default, for data-parallel runs (capturing the NCCL
-    all-reduce into the graph hung on the test box: opt-in with NQ_GRAPH_DP=1)."""
+    scalars that change per iteration go through a 16-byte device array (nq_*_dev kernels).  Both phases; the eager
+    path stays for iterations that log.  Data parallel: the NCCL all-reduce of the flat dW buffer is captured INTO the
+    graph between the backward kernels and the fused Jacobian + Adam launch (the communicator is created and warmed up
+    by the eager first iteration; capture runs in thread-local error mode, so the NCCL watchdog thread's event queries
+    do not invalidate it).  NQ_GRAPH_DP=0 falls back to the eager launch sequence around an eager all-reduce."""
 
     def __init__(self, eng: DecoderEngine, opt: AdamState, embed: torch.Tensor, frames: torch.Tensor, p_norm: float,
                  mean_pixels: float, group=None, world: int = 1, capture: bool = True, phase: str = "alpha"):
@@ -97,7 +99,8 @@ class GraphedStep:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             saved = [t.clone() for t in self.opt.params + self.opt.m + self.opt.v]  # capture must not advance the state
-            with torch.cuda.graph(g):
+            # thread_local: other threads (NCCL's watchdog, bench.py's clock sampler) may call the CUDA API meanwhile
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._body()
             self.eng.launches -= self.launches_per_replay  # launches issued during capture do not execute
             for t, s in zip(self.opt.params + self.opt.m + self.opt.v, saved):
@@ -197,10 +200,10 @@ class CalibrationLoop:
         self.global_batch = global_batch
         self.log = log
         self.on_iteration = on_iteration  # (phase, count, device loss scalar) after every iteration; no sync
-        # one GPU: CUDA-graph replay; data parallel: the same fused sequence launched eagerly around the NCCL all-reduce
-        # (capturing the all-reduce hung on the test box: opt-in with NQ_GRAPH_DP=1); NQ_GRAPH=0: per-tensor eager path
+        # CUDA-graph replay of the iteration, the NCCL all-reduce included when data parallel (NQ_GRAPH_DP=0: the same
+        # fused sequence launched eagerly around an eager all-reduce); NQ_GRAPH=0: per-tensor eager path
         self.use_graph = os.environ.get("NQ_GRAPH", "1") != "0"
-        self.capture = self.world == 1 or os.environ.get("NQ_GRAPH_DP", "0") != "0"
+        self.capture = self.world == 1 or os.environ.get("NQ_GRAPH_DP", "1") != "0"
         self._graphed = {}
         self.ep1 = int(0.05 * iters / n_batches)  # calib_model.py:144
         self.ep2 = int(iters / n_batches) - self.ep1  # calib_model.py:205

@@ -85,6 +85,9 @@ __device__ __forceinline__ void hcommit(uint32_t bar) {
 
 __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid_constant__ HeadTcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  // uint8 targets: v / 255 with an IEEE fp32 division (bit-identical to the reference's `read_image / 255.0`), tabulated once
+  __shared__ float u8lut[256];
+  if (threadIdx.x < 256) u8lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
   // [0,256) barriers + TMEM pointer | HT_NB activation tile buffers (2 planes each) | B planes | staging
   const uint32_t bar0 = hsm(smem);
   const uint32_t A_FULL = bar0, A_EMPTY = bar0 + HT_NB * 8, T_FULL = bar0 + 2 * HT_NB * 8, T_EMPTY = T_FULL + 16;  // T_*: two slots
@@ -213,7 +216,8 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
       const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, img = t / (p.tiles_x * p.tiles_y);
       // the target pixels of this thread's (at most two) outputs are requested before the accumulator wait: the loss
       // epilogue otherwise pays the DRAM latency of these loads once per output round
-      float tg[2][3];
+      // (uint8 targets stay raw bytes here -- converting would wait for the load -- and go through the table below)
+      uint32_t tgraw[2][3];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int o = threadIdx.x + 256 * r;
@@ -223,11 +227,16 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_tapexp_kernel(const __grid
         const int64_t off = (int64_t)img * 3 * plane + (int64_t)py * p.w + px;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          tg[r][c] = !ok ? 0.f : (p.target ? __ldg(p.target + off + c * plane)
-                                           : __fdiv_rn((float)__ldg(p.target_u8 + off + c * plane), 255.0f));
+          tgraw[r][c] = !ok ? 0u : (p.target ? __float_as_uint(__ldg(p.target + off + c * plane))
+                                             : (uint32_t)__ldg(p.target_u8 + off + c * plane));
       }
       hbar_wait(T_FULL + acc * 8, (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float tg[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tg[r][c] = p.target_u8 ? u8lut[tgraw[r][c] & 255u] : __uint_as_float(tgraw[r][c]);
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = half + 2 * jj;
@@ -356,7 +365,7 @@ static int head_tapexp_launch(const nq_conv_desc* d, const void* x_split, const 
   q.out_bias = out_bias; q.p = p; q.inv_mean = target ? 1.0f / mean_pixels : 0.f;
   const int ncg = q.C16 / 8;
   const int smem = 256 + HT_NB * 2 * ncg * HT_CGS + 2 * ncg * 32 * 16 + HT_NPIX * HT_STG * 4;
-  if (smem > 227 * 1024) return NQ_ERR_UNSUPPORTED;
+  if (smem + 1024 > 227 * 1024) return NQ_ERR_UNSUPPORTED;  // + the static 1 KB uint8 table
   NQ_CUDA_CHECK(cudaFuncSetAttribute(head_tapexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = sm_count();
   if (grid > q.total) grid = q.total;

@@ -752,3 +752,108 @@ extern "C" int nq_u8_to_f32(const uint8_t* src, float* dst, int64_t numel, void*
   NQ_LAUNCH_CHECK();
   return NQ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// bit_assign as a SEARCH (methods/bit_assign.py:343-372 scores a hand-written candidate list one 15 s Hessian-vector
+// product at a time).  Omega is a quadratic form, so for perturbations v_l(b) = W_l - Q_b(W_l) of layer l at b bits
+//     Omega(b_0 .. b_{L-1}) = sum_l G[(l, b_l), (l, b_l)] + 2 sum_{l < m} G[(l, b_l), (m, b_m)]
+// with the Gram table G[(l, b), (m, b')] = v_l(b)^T H_lm v_m(b') measured once (sensitivity.OmegaTable).  This kernel
+// scores EVERY configuration -- nb^L of them, 7^7 = 823 543 for 7 layers x {2 .. 8} bits -- by table lookup, one thread
+// each, and returns the admissible one (average bits <= budget) of smallest Omega; ties go to the smaller index, so the
+// result does not depend on the launch geometry.
+// ---------------------------------------------------------------------------------------------
+namespace nq {
+struct OmegaSearchParams {
+  const double* G;        // (L * nb) x (L * nb), row-major, symmetric
+  const double* bits_w;   // [L * nb]: n_params(l) * bits(b) / total_params  (contribution of the choice to the average bit-width)
+  double budget;
+  long long total;        // nb^L
+  int L, nb;
+  double* scores;         // optional: Omega of every configuration (total entries) or null
+  double* block_best; long long* block_idx;
+};
+
+__device__ __forceinline__ double omega_of(const OmegaSearchParams& q, long long idx, double& avg_bits) {
+  int c[8];
+  for (int l = 0; l < q.L; ++l) { c[l] = (int)(idx % q.nb); idx /= q.nb; }
+  double s = 0.0, ab = 0.0;
+  const int n = q.L * q.nb;
+  for (int l = 0; l < q.L; ++l) {
+    const int a = l * q.nb + c[l];
+    ab += q.bits_w[a];
+    s += q.G[(size_t)a * n + a];
+    for (int m = l + 1; m < q.L; ++m) s += 2.0 * q.G[(size_t)a * n + m * q.nb + c[m]];
+  }
+  avg_bits = ab;
+  return s;
+}
+
+__global__ void __launch_bounds__(256) omega_search_kernel(const OmegaSearchParams q) {
+  __shared__ double sb[256];
+  __shared__ long long si[256];
+  double best = INFINITY;
+  long long bi = -1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < q.total; i += (long long)gridDim.x * blockDim.x) {
+    double ab;
+    const double s = omega_of(q, i, ab);
+    if (q.scores) q.scores[i] = ab <= q.budget ? s : INFINITY;
+    if (ab <= q.budget && (s < best || (s == best && i < bi))) { best = s; bi = i; }
+  }
+  sb[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double s2 = sb[threadIdx.x + o]; const long long i2 = si[threadIdx.x + o];
+      if (i2 >= 0 && (si[threadIdx.x] < 0 || s2 < sb[threadIdx.x] || (s2 == sb[threadIdx.x] && i2 < si[threadIdx.x]))) {
+        sb[threadIdx.x] = s2; si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { q.block_best[blockIdx.x] = sb[0]; q.block_idx[blockIdx.x] = si[0]; }
+}
+
+__global__ void omega_search_final_kernel(const double* block_best, const long long* block_idx, int nblocks, double* out_score,
+                                          long long* out_idx) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double best = INFINITY; long long bi = -1;
+  for (int b = 0; b < nblocks; ++b) {
+    const long long i2 = block_idx[b];
+    if (i2 >= 0 && (bi < 0 || block_best[b] < best || (block_best[b] == best && i2 < bi))) { best = block_best[b]; bi = i2; }
+  }
+  *out_score = best; *out_idx = bi;
+}
+}  // namespace nq
+
+extern "C" int nq_omega_search_workspace(int n_layers, int n_options, int64_t* n_configs, int64_t* workspace_bytes) {
+  if (n_layers < 1 || n_layers > 8 || n_options < 1 || n_options > 16 || !n_configs || !workspace_bytes) return NQ_ERR_BAD_ARG;
+  long long total = 1;
+  for (int l = 0; l < n_layers; ++l) total *= n_options;
+  *n_configs = total;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)nq::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  *workspace_bytes = blocks * 16;
+  return NQ_OK;
+}
+
+extern "C" int nq_omega_search(const double* gram, const double* bits_weight, int n_layers, int n_options, double budget,
+                               double* scores, void* workspace, int64_t workspace_bytes, double* best_score,
+                               int64_t* best_index, void* stream) {
+  int64_t total = 0, need = 0;
+  const int st = nq_omega_search_workspace(n_layers, n_options, &total, &need);
+  if (st) return st;
+  if (!gram || !bits_weight || !workspace || !best_score || !best_index) return NQ_ERR_BAD_ARG;
+  if (workspace_bytes < need) return NQ_ERR_WORKSPACE;
+  const int blocks = (int)(need / 16);
+  nq::OmegaSearchParams q{};
+  q.G = gram; q.bits_w = bits_weight; q.budget = budget; q.total = total; q.L = n_layers; q.nb = n_options; q.scores = scores;
+  q.block_best = reinterpret_cast<double*>(workspace);
+  q.block_idx = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)blocks * 8);
+  nq::omega_search_kernel<<<blocks, 256, 0, nq::as_stream(stream)>>>(q);
+  NQ_LAUNCH_CHECK();
+  nq::omega_search_final_kernel<<<1, 32, 0, nq::as_stream(stream)>>>(q.block_best, q.block_idx, blocks, best_score,
+                                                                    reinterpret_cast<long long*>(best_index));
+  NQ_LAUNCH_CHECK();
+  return NQ_OK;
+}

@@ -177,3 +177,113 @@ def fisher_diag(engine: DecoderEngine, vecs: Sequence[torch.Tensor], batches, pe
     v = [x.detach().contiguous().float() for x in vecs]
     per = L.multi_dot(v, g, 1)
     return [float(x) for x in per] if per_layer else float(per.sum())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# bit_assign as a search: the Gram table of Omega and its exhaustive evaluation (BASELINE.json configs[3])
+# ------------------------------------------------------------------------------------------------------------------
+class OmegaTable:
+    """Omega of EVERY per-layer bit-width configuration from one table.
+
+    The reference scores a candidate by one Hessian-vector product over 10 mini-batches (bit_assign.py:57-118, ~15.6 s on
+    its GPU) and therefore ships two hand-written candidates per architecture (:28-36).  Omega(v) = v^T H v is quadratic:
+    with v_l(b) = W_l - Q_b(W_l), the perturbation of layer l alone at bit-width b,
+
+        Omega(b_0 .. b_{L-1}) = sum_l G[(l,b_l),(l,b_l)] + 2 sum_{l<m} G[(l,b_l),(m,b_m)],
+        G[(l,b),(m,b')] = v_l(b)^T H_lm v_m(b')
+
+    so L*nb single-layer directions and C(L,2)*nb^2 two-layer directions, each ONE forward jet (OmegaEvaluator: no
+    backward pass), give the whole table by polarisation, G[a,b] = (Q(a+b) - Q(a) - Q(b)) / 2 -- 49 + 1029 jets for 7
+    layers x {2..8} bits -- after which all nb^L = 823 543 configurations are scored by table lookup on the device
+    (nq_omega_search).  The jets are independent: under torch.distributed rank r evaluates directions r, r + world, ...
+    and one all-reduce of the result vector assembles the table on every rank (candidate farming)."""
+
+    def __init__(self, engine: DecoderEngine, perturbations, options: Sequence[int], n_params: Sequence[int]):
+        """perturbations[l][k]: (C_out, C_in, k, k) perturbation of stage l at options[k] bits; n_params[l]: parameters
+        of stage l counted in the average bit-width (weights + bias, quant_model.py:58-72)."""
+        self.eng, self.pert, self.options = engine, perturbations, list(options)
+        self.L, self.nb = len(perturbations), len(options)
+        if self.L > 8 or self.nb > 16:
+            raise L.NqError("OmegaTable: at most 8 layers x 16 options")
+        self.n_params = [float(x) for x in n_params]
+        self.gram = None
+        self.jets = 0
+
+    def directions(self):
+        """The jets to evaluate: ('s', l, k) single-layer and ('p', l, k, m, k2) two-layer directions, in a fixed order."""
+        d = [("s", l, k) for l in range(self.L) for k in range(self.nb)]
+        d += [("p", l, k, m, k2) for l in range(self.L) for m in range(l + 1, self.L) for k in range(self.nb) for k2 in range(self.nb)]
+        return d
+
+    def _vecs(self, d):
+        zero = [torch.zeros_like(self.pert[l][0]) for l in range(self.L)]
+        zero[d[1]] = self.pert[d[1]][d[2]]
+        if d[0] == "p":
+            zero[d[3]] = self.pert[d[3]][d[4]]
+        return zero
+
+    def build(self, batches, rank: int = 0, world: int = 1, group=None):
+        dirs = self.directions()
+        q = torch.zeros(len(dirs), dtype=torch.float64, device=self.eng.device)
+        for i in range(rank, len(dirs), world):
+            q[i] = omega(self.eng, self._vecs(dirs[i]), batches)
+            self.jets += 1
+        if world > 1:
+            torch.distributed.all_reduce(q, group=group)
+        q = q.cpu()
+        n = self.L * self.nb
+        g = torch.zeros(n, n, dtype=torch.float64)
+        single = {}
+        for i, d in enumerate(dirs):
+            if d[0] == "s":
+                a = d[1] * self.nb + d[2]
+                g[a, a] = q[i]
+                single[a] = float(q[i])
+        for i, d in enumerate(dirs):
+            if d[0] == "p":
+                a, b = d[1] * self.nb + d[2], d[3] * self.nb + d[4]
+                g[a, b] = g[b, a] = 0.5 * (float(q[i]) - single[a] - single[b])
+        self.gram = g
+        return g
+
+    def score(self, bits: Sequence[int]) -> float:
+        """Omega of one configuration from the table (host arithmetic; the search kernel does the same sums)."""
+        c = [self.options.index(b) for b in bits]
+        s = 0.0
+        for l in range(self.L):
+            a = l * self.nb + c[l]
+            s += float(self.gram[a, a])
+            for m in range(l + 1, self.L):
+                s += 2.0 * float(self.gram[a, m * self.nb + c[m]])
+        return s
+
+    def bits_weight(self) -> torch.Tensor:
+        tot = sum(self.n_params)
+        return torch.tensor([self.n_params[l] * b / tot for l in range(self.L) for b in self.options], dtype=torch.float64)
+
+    def search(self, avg_bits_budget: float, want_scores: bool = False):
+        """(best bits, its Omega, its average bit-width[, all scores]) over all nb^L configurations whose average
+        bit-width does not exceed the budget."""
+        dev = self.eng.device
+        g = self.gram.to(dev).contiguous()
+        bw = self.bits_weight().to(dev)
+        n_cfg, ws_bytes = C.c_int64(0), C.c_int64(0)
+        L.check(L.lib.nq_omega_search_workspace(self.L, self.nb, C.byref(n_cfg), C.byref(ws_bytes)), "nq_omega_search_workspace")
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        scores = torch.empty(n_cfg.value, dtype=torch.float64, device=dev) if want_scores else None
+        best = torch.zeros(1, dtype=torch.float64, device=dev)
+        idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        L.check(L.lib.nq_omega_search(g.data_ptr(), bw.data_ptr(), self.L, self.nb, float(avg_bits_budget),
+                                      scores.data_ptr() if want_scores else None, ws.data_ptr(), ws.numel(), best.data_ptr(),
+                                      idx.data_ptr(), L.stream()), "nq_omega_search")
+        self.eng.launches += 2
+        i = int(idx)
+        if i < 0:
+            return None, float("inf"), float("nan"), scores
+        bits, ab = [], 0.0
+        for l in range(self.L):
+            k = i % self.nb
+            i //= self.nb
+            bits.append(self.options[k])
+            ab += float(bw[l * self.nb + k])
+        return bits, float(best), ab, scores

@@ -58,6 +58,8 @@ def build(workload: str, bits, hadamard: bool, seed: int = 903):
         for c, st in zip(convs, W.random_stages(cfg_dict, arch, seed)):
             c.weight.copy_(st.weight)
             c.bias.copy_(st.bias)
+    import copy
+    build.fp_model = copy.deepcopy(model)  # the full-precision network, before the (in-place) module surgery
     qnn = quantization.QuantModel(model=model, hadamard=hadamard,
                                   weight_quant_params={"n_bits": 8, "channel_wise": True, "scale_method": "max"})
     qnn.set_bitwidth(list(bits))

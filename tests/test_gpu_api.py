@@ -256,3 +256,46 @@ def test_data_utils_surface():
     quantize_model_till(qnn, block)
     states = [m.use_weight_quant for m in qnn.quant_modules()]
     assert states == [True, True, True, True, False, False, False]
+
+
+@pytest.mark.parametrize("tag", ["tiny_hnerv", "tiny_nerv"])
+def test_omega_table_reproduces_reference_scores_of_arbitrary_configurations(tag):
+    """bit_assign as a search (BASELINE configs[3]): the Gram table of Omega, measured once with forward jets, reproduces
+    the UNMODIFIED reference's sensitivity_criterion (double-backward HVP, bit_assign.py:171-203) on nine configurations
+    it was not built around (tests/golden/make_omega_golden.py) -- negative scores included -- and the device search over
+    all 7^7 configurations returns the true minimum of the table under the average-bit budget."""
+    from neuroquant_b200.methods.bit_assign import search_bit_assignment
+    g, arch, cfg, model = build_model(tag)
+    gc = load(tag + "_omega_configs")
+    cali, frames = t(g["cali"]).cuda(), t(g["frames"]).cuda()
+    # the loader's frames must map to the fixture's embeddings (bit_assign re-encodes them with the encoder, whose random
+    # weights the fixture does not store)
+    embeds = cali / 3.0 if arch == "hnerv" else cali
+    loader = [{"img": frames[i:i + 2], "norm_idx": torch.arange(i, i + 2).float() / 8, "idx": torch.arange(i, i + 2)} for i in range(0, 8, 2)]
+    table_embeds = {int(s["idx"][0]): embeds[int(s["idx"][0]):int(s["idx"][0]) + 2] for s in loader}
+    model.encode = lambda x, _m=model: (table_embeds[min(table_embeds, key=lambda k: float((frames[k:k + 2] - x).abs().sum()))]
+                                        if arch == "hnerv" else type(model).encode(_m, x))
+    options = [2, 3, 4, 5, 6, 7, 8]
+    bits, score, avg_bits, table = search_bit_assignment(arch, model, loader, cali, options, 4.5, batch_size=2)
+    assert len(table.directions()) == 49 + 21 * 49 and table.jets == len(table.directions())
+    want = gc["omega"]
+    got = np.array([table.score(c) for c in gc["configs"].tolist()])
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 5e-3 * scale, (got, want)
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * scale)
+    assert rel.max() < 2e-2, (got, want)
+    # the search: exhaustive on the host over the same table
+    bw = table.bits_weight().numpy().reshape(7, 7)
+    gm = table.gram.numpy()
+    idx = np.arange(7 ** 7)
+    c = np.stack([(idx // 7 ** l) % 7 for l in range(7)], 1)            # c[i, l] = option index of layer l (index = sum c_l 7^l)
+    a = c + 7 * np.arange(7)[None, :]
+    sc = sum(gm[a[:, l], a[:, l]] for l in range(7)) + 2 * sum(gm[a[:, l], a[:, m]] for l in range(7) for m in range(l + 1, 7))
+    ok = sum(bw[l, c[:, l]] for l in range(7)) <= 4.5
+    sc = np.where(ok, sc, np.inf)
+    best_i = int(np.argmin(sc))
+    best, best_c = float(sc[best_i]), c[best_i].tolist()
+    assert bits == [options[k] for k in best_c] and score == pytest.approx(best, rel=1e-12)
+    assert avg_bits <= 4.5 and score == pytest.approx(table.score(bits), rel=1e-12)
+    none, sc, _, _ = table.search(1.9)                     # nothing fits below 2 bits on average
+    assert none is None and sc == float("inf")

@@ -30,15 +30,17 @@ def build(hadamard):
     return eng, cfg, arch
 
 
-def run(eng, embeds, frames, order, rank, world, group, iters):
+def run(eng, embeds, frames, order, rank, world, group, iters, want_log=True):
     def fetch(idx):
         idx = shard_indices(torch.as_tensor(idx), rank, world).cuda()
         return embeds[idx], frames[idx]
-    log = []
+    log = [] if want_log else None     # a log forces the eager launch sequence; without it the iteration replays as a CUDA graph
     loop = nq.CalibrationLoop(eng, fetch, len(order), iters=iters, weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003,
                               group=group, global_batch=len(order[0]), log=log)
     loop.world = world
     loop.run_phase2(lambda: order)
+    if not want_log:
+        assert loop._graphed and all(g.graph is not None or not g.capture for g in loop._graphed.values())
     return log
 
 
@@ -61,6 +63,14 @@ if __name__ == "__main__":
     alpha_dp = [s.alpha_w.clone() for s in eng.stages]
     dist.barrier()
     del eng
+    # the same iterations replayed as ONE CUDA graph per step with the NCCL all-reduce captured inside it: the kernels and
+    # the reduction are the eager run's, so the rounding variables must come out bit-identical
+    eng_g, _, _ = build(hadamard)
+    run(eng_g, embeds, frames, order, rank, world, None, iters, want_log=False)
+    graph_equal = all(torch.equal(a, s.alpha_w) for a, s in zip(alpha_dp, eng_g.stages))
+    graph_far = max(float(((a - s.alpha_w).abs() > 1e-3).float().mean()) for a, s in zip(alpha_dp, eng_g.stages))
+    dist.barrier()
+    del eng_g
     dist.destroy_process_group()     # the single-GPU run below must see no process group (CalibrationLoop would all-reduce)
     if rank == 0:
         eng1, _, _ = build(hadamard)
@@ -69,4 +79,5 @@ if __name__ == "__main__":
         far = [float(((a - s.alpha_w).abs() > 1e-3).float().mean()) for a, s in zip(alpha_dp, eng1.stages)]
         print(json.dumps({"check": "dp_equivalence", "n_gpus": world, "hadamard": hadamard, "iterations": len(log_dp),
                           "loss_rel_diff_max": float(((rec_dp - rec_1).abs() / rec_1).max()),
-                          "alpha_far_fraction_max": max(far), "loss_first": float(rec_1[0]), "loss_last": float(rec_1[-1])}))
+                          "alpha_far_fraction_max": max(far), "graph_with_nccl_bit_identical_to_eager": graph_equal,
+                          "graph_alpha_far_fraction_max": graph_far, "loss_first": float(rec_1[0]), "loss_last": float(rec_1[-1])}))
