@@ -85,6 +85,7 @@ def main():
     ap.add_argument("--precision", type=int, nargs="+", default=[6, 5, 4, 5, 5, 6, 6])
     ap.add_argument("--hadamard", action="store_true")
     ap.add_argument("--skip-train", action="store_true", help="reuse the clip and checkpoint under --work")
+    ap.add_argument("--train-only", action="store_true", help="make the clip and the full-precision checkpoint, then stop")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -96,7 +97,16 @@ def main():
     os.makedirs(work, exist_ok=True)
     rec = {"arch": a.arch, "gpus": world, "iters_w": a.iters, "precision": a.precision, "hadamard": a.hadamard, "batch_size": a.batch}
     os.chdir(work)
-    if not a.skip_train and rank == 0:
+    if not a.skip_train and rank == 0 and world > 1:
+        # the regression script is single-GPU (as in the reference): run it in a child process outside the process group
+        import subprocess
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                                                                  "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID")}
+        t0 = time.time()
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--arch", a.arch, "--work", a.work, "--fp-epochs", str(a.fp_epochs),
+                        "--train-only"], check=True, env=env, cwd=ROOT)
+        rec["fp_training_seconds"] = time.time() - t0
+    elif not a.skip_train and rank == 0:
         t0 = time.time()
         if not os.path.isdir(clip) or len(os.listdir(clip)) != 132:
             make_clip(clip)
@@ -106,6 +116,8 @@ def main():
         t0 = time.time()
         regress.main(["--config", cfg_path, "--arch", a.arch, "--data_path", clip, "--vid", "Synth", "--outf", "fp", "-p", "1000"])
         rec["fp_training_seconds"] = time.time() - t0
+    if a.train_only:
+        return
     if world > 1:
         from neuroquant_b200.methods.common import init_distributed
         init_distributed()
