@@ -30,6 +30,7 @@
 // stages whose epilogue is the longest role), warps n_epi..15 activation loaders
 // (fp32 -> bf16 hi/lo), warp 16 weight-stage producer, warp 17 MMA issuer, warp 18 TMEM allocator.
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "nq_common.cuh"
@@ -99,6 +100,9 @@ struct TcParams {
   int bcat;              // weight stage stores the planes side by side per k-group ([k-group][plane][n][8]): A_hi x [B_hi | B_lo]
                          // is ONE MMA of 2 * nt columns (hi*hi in columns [0, nt), hi*lo in [nt, 2 nt)) + A_lo x B_hi
   int mt;                // 16x8 pixel tiles (side by side in x) per CTA step: they share every weight stage (NT <= 256 / mt)
+  int n_prod;            // lanes of the producer warp issuing weight-stage copies (stages round robin)
+  int skip;              // NQ_TC_SKIP (debug): bit 0 epilogue body, bit 2 activation copies
+  long long* dbg;        // NQ_TC_DBG: {SM cycles, nanoseconds} of CTA 0 (the SM clock this launch really ran at), or null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +209,54 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2): one MMA of M = 256 spans the two CTAs of a cluster; each holds its 128 A rows and HALF of
+// the B rows at the same shared-memory offsets; the leader CTA issues, tcgen05.commit signals both CTAs' barriers.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): what this arrival publishes was
+  // written by the async proxy (TMA) or already ordered by fence.proxy.async; a cluster-scope release costs a full fence per stage
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // a remote CTA arrives on this barrier
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+#define NQ_UMMA2(NAME, QUAL)                                                                                              \
+  __device__ __forceinline__ void NAME(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,          \
+                                       uint32_t idesc, uint32_t accum) {                                                    \
+    asm volatile(                                                                                                           \
+        "{\n\t"                                                                                                             \
+        ".reg .pred p;\n\t"                                                                                                 \
+        ".reg .b64 da, db;\n\t"                                                                                             \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                                         \
+        "mov.b64 da, {%1, %2};\n\t"                                                                                         \
+        "mov.b64 db, {%3, %4};\n\t"                                                                                         \
+        "tcgen05.mma.cta_group::2.kind::f16" QUAL " [%0], da, db, %5, p;\n\t"                                              \
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)                               \
+        : "memory");                                                                                                        \
+  }
+NQ_UMMA2(umma2_w, "")
+// the A operand stays in the collector for the next MMA (same A, other B): its 4 KB are read from shared memory once
+NQ_UMMA2(umma2_w_keep, ".collector::a::fill")
+NQ_UMMA2(umma2_w_reuse, ".collector::a::lastuse")
+#undef NQ_UMMA2
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -222,8 +274,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, int m = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -299,9 +351,28 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int group, in
   return c;
 }
 
+// MMAs of one weight stage (k16 K steps of 16 channels), fully unrolled.  PASSES bit 0: activation lo plane, bit 1: weight lo
+// plane; BCAT: both weight planes as one operand of 2 nt columns (idesc2).  Only the elected lane issues; the block is one
+// reconvergence scope, the descriptor low words are independent adds.
+// tcgen05.commit of a weight stage's B_EMPTY barrier: pair / single CTA / every CTA of a multicast cluster
+template <int CG>
+__device__ __forceinline__ void commit_stage(uint32_t bar, int cs, uint16_t mc_mask) {
+  if (CG == 2) umma2_commit_mc(bar, 3);
+  else if (cs == 1) umma_commit(bar);
+  else umma_commit_mc(bar, mc_mask);
+}
+
 // MT / BCAT / RES are compile-time copies of TcParams::mt / bcat / resident: the common (1, 0, 0) variant carries
 // none of their code.
-template <int MT, int BCAT, int RES>
+// CG = 2: CTA-pair MMAs (cta_group::2, M = 256).  The two CTAs of a cluster work on neighbouring pixel tiles of the same N
+// tile; each stages its own halo tile and HALF of every weight stage (N / 2 rows of B); the leader (rank 0) issues every MMA
+// for both.  What the leader must know about its peer -- activation tile landed, weight half landed, accumulator drained --
+// reaches it as one extra arrival on ITS OWN barriers (remote mbarrier.arrive from the peer's relay warps 17 / 19 and
+// epilogue warps); what the peer must know -- operands consumed, accumulator ready -- is the multicast tcgen05.commit.
+// Per MMA instruction the issuing thread now moves twice the work (these kernels are bound by that one thread's
+// instruction stream, profiles/r02h_issue_bound.md), every weight byte is read from L2 once per pair, written to shared
+// memory once per pair and read by each tensor core from ONE of the two shared memories.
+template <int MT, int BCAT, int RES, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // [0, TC_HDR_BYTES): barriers + tmem pointer; then A buffers, then B stages
@@ -322,34 +393,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_MAX_RING; ++i) {
-      mbar_init(A_FULL + i * 8, (TC_WORK_WARPS - p.n_epi) * 32);  // one deferred arrival per loader thread
+      // one deferred arrival per loader thread (+ the peer's relay on the pair leader)
+      mbar_init(A_FULL + i * 8, (TC_WORK_WARPS - p.n_epi) * 32 + (CG == 2 && rank == 0 ? 1 : 0));
       mbar_init(A_EMPTY + i * 8, 1);
       mbar_init(T_FULL + i * 8, 1);
-      mbar_init(T_EMPTY + i * 8, p.n_epi);
+      mbar_init(T_EMPTY + i * 8, CG == 2 ? 2 * p.n_epi : p.n_epi);  // pair: both CTAs' epilogue warps arrive on the leader's
     }
     for (int i = 0; i < p.n_bstages; ++i) {
-      mbar_init(B_FULL + i * 8, 1);
-      mbar_init(B_EMPTY + i * 8, p.cs);  // every CTA of the cluster must have consumed the slot
+      mbar_init(B_FULL + i * 8, CG == 2 && rank == 0 ? 2 : 1);  // pair leader: own producer + the peer's relay
+      mbar_init(B_EMPTY + i * 8, CG == 2 ? 1 : p.cs);  // multicast: every CTA of the cluster must have consumed the slot
     }
     fence_barrier_init();
   }
   if (warp == 18) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {  // both CTAs of the pair, the same warp
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long dbg_c0 = 0, dbg_t0 = 0;
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   const int taps = p.ks * p.ks;
   const int ncb = (p.C + p.KC - 1) / p.KC;
 
   if (warp == 16) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
-    if (lane == 0) {
+    // n_prod lanes take the stages round robin.  One thread sustains only about one bulk copy per 650-1200 SM cycles
+    // however small the copy (tools/tma_bulk_bench.cu: 15 KB copies land at 22 B/clk/SM from one thread, 49 from four
+    // lanes); with a single producer every weight stage cost ~900 cycles and the convolutions ran at the producer's pace,
+    // not the tensor pipe's (profiles/r02m_weight_stream.md).
+    if (lane < p.n_prod) {
+      int turn = 0;
       const int nsb_full = p.KC / p.SBC;
       const int stages_per_ntile = (p.C / p.SBC) * taps;
       const size_t ntile_stride = (size_t)stages_per_ntile * p.NT * p.SBC * 2 * p.b_planes;
@@ -357,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
         const TileCoord tc = tile_coord(p, t, rank);
         const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * 2 * p.b_planes;
-        const uint32_t part = stage_bytes / p.cs;
+        const uint32_t part = stage_bytes / p.cs;  // pair (CG == 2): this CTA's half of the stage = its N / 2 rows of B
         const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride + (size_t)tc.cb0 * taps * nsb_full * stage_bytes;
         for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
           const int nsb = cb == ncb - 1 ? p.nsb_last : nsb_full;
@@ -365,16 +453,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int sb = 0; sb < nsb; ++sb, ++sc) {
               const uint32_t s = bs, ph = bph;
               if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
-              mbar_wait(B_EMPTY + s * 8, ph ^ 1);
-              mbar_arrive_expect_tx(B_FULL + s * 8, stage_bytes);
-              if (p.cs == 1)
-                bulk_g2s(b_base + s * p.b_stage_bytes, src, stage_bytes, B_FULL + s * 8);
-              else  // this CTA fetches its 1/cs of the stage and multicasts it to every CTA of the cluster
-                bulk_g2s_mc(b_base + s * p.b_stage_bytes + rank * part, src + rank * part, part, B_FULL + s * 8, mc_mask);
+              if (turn == lane) {
+                mbar_wait(B_EMPTY + s * 8, ph ^ 1);
+                mbar_arrive_expect_tx(B_FULL + s * 8, CG == 2 ? part : stage_bytes);
+                if (CG == 2)  // own half only, at the base of the slot (packed per half: [half][plane][k-group][n / 2][8])
+                  bulk_g2s(b_base + s * p.b_stage_bytes, src + rank * part, part, B_FULL + s * 8);
+                else if (p.cs == 1)
+                  bulk_g2s(b_base + s * p.b_stage_bytes, src, stage_bytes, B_FULL + s * 8);
+                else  // this CTA fetches its 1/cs of the stage and multicasts it to every CTA of the cluster
+                  bulk_g2s_mc(b_base + s * p.b_stage_bytes + rank * part, src + rank * part, part, B_FULL + s * 8, mc_mask);
+              }
+              if (++turn == p.n_prod) turn = 0;
               src += stage_bytes;
             }
         }
         if (RES) break;  // the ring now holds every stage of the (single) N tile for the rest of the kernel
+      }
+    }
+  } else if (CG == 2 && warp == 17 && rank != 0) {
+    // ===================== pair, peer CTA: weight-stage relay =====================
+    // follows the leader's issue order; each landed half-stage of this CTA becomes one arrival on the LEADER's B_FULL
+    if (lane == 0) {
+      const int nsb_full = p.KC / p.SBC;
+      const uint32_t lead_full = mapa_u32(B_FULL, 0);
+      uint32_t bs = 0, bph = 0;
+      for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
+        const TileCoord tc = tile_coord(p, t, rank);
+        for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
+          const int nst = (cb == ncb - 1 ? p.nsb_last : nsb_full) * taps;
+          for (int i = 0; i < nst; ++i) {
+            mbar_wait(B_FULL + bs * 8, bph);
+            mbar_arrive_cluster(lead_full + bs * 8);
+            if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (CG == 2 && warp == 19 && rank != 0) {
+    // ===================== pair, peer CTA: activation-tile relay =====================
+    if (lane == 0) {
+      const uint32_t lead_full = mapa_u32(A_FULL, 0);
+      uint32_t abuf = 0, aph = 0;
+      for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
+        const TileCoord tc = tile_coord(p, t, rank);
+        for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
+          mbar_wait(A_FULL + abuf * 8, aph);
+          fence_proxy_async();  // this CTA's cp.async writes (generic proxy) -> the pair's MMA reads (async proxy)
+          mbar_arrive_cluster(lead_full + abuf * 8);
+          if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
+        }
       }
     }
   } else if (warp == 17) {
@@ -397,17 +524,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int passes = (p.a_planes == 2 ? 1 : 0) | (p.b_planes == 2 ? 2 : 0);
     for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
       const TileCoord tc = tile_coord(p, t, rank);
-      mbar_wait(T_EMPTY + acc * 8, tph ^ 1);
+      if (CG == 2) mbar_wait_cluster(T_EMPTY + acc * 8, tph ^ 1); else mbar_wait(T_EMPTY + acc * 8, tph ^ 1);
       tc_fence_after();
       if (RES) bs = 0;  // stage i of the tile lives in ring slot i
       const bool b_wait = !RES || t == cluster_id;
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       const uint32_t d_tmem1 = d_tmem + p.sub_stride;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
       constexpr bool two = MT == 2;
-      const uint32_t idesc = make_idesc(tc.nt);
+      const uint32_t idesc = make_idesc(tc.nt, 128 * CG);
       const uint32_t idesc2 = make_idesc(2 * tc.nt);  // bcat: both weight planes as one operand
-      const uint32_t b_lbo16 = (uint32_t)tc.nt << BCAT;  // k-group stride: nt (or 2 nt) * 16 bytes >> 4
-      const uint32_t b_plane16 = (uint32_t)(tc.nt * p.SBC * 2) >> 4;
+      // k-group stride: nt (bcat: 2 nt; pair: this CTA's nt / 2) rows * 16 bytes >> 4
+      const uint32_t b_lbo16 = CG == 2 ? (uint32_t)tc.nt >> 1 : (uint32_t)tc.nt << BCAT;
+      const uint32_t b_plane16 = (uint32_t)((tc.nt / CG) * p.SBC * 2) >> 4;
       const uint32_t b_step16 = 2 * b_lbo16;
       uint32_t accum = 0;
       if (RES) {
@@ -449,7 +577,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
       } else
       for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
-        mbar_wait(A_FULL + abuf * 8, aph);
+        if (CG == 2) mbar_wait_cluster(A_FULL + abuf * 8, aph); else mbar_wait(A_FULL + abuf * 8, aph);
         fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
         tc_fence_after();
         const uint32_t a_buf16 = (((a_base + abuf * p.a_buf_bytes) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
@@ -460,13 +588,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           uint32_t a_lo = a_tap;
           for (int sb = 0; sb < nsb; ++sb) {
             if (b_wait) {
-              mbar_wait(B_FULL + bs * 8, bph);
+              if (CG == 2) mbar_wait_cluster(B_FULL + bs * 8, bph); else mbar_wait(B_FULL + bs * 8, bph);
               tc_fence_after();
             }
             uint32_t b_lo = (((b_base + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
             // uniform loops; only the MMA itself is predicated on the leader lane, so that ptxas keeps the
             // descriptors in uniform registers instead of broadcasting them per instruction
-            if (BCAT) {
+            if (CG == 2) {
+              // pair MMAs; where one A tile meets both weight planes it is read from shared memory once (A collector)
+#pragma unroll 1
+              for (int j = 0; j < k16_per_stage; ++j) {
+                if (leader) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m) {
+                    const uint32_t d = m == 0 ? d_tmem : d_tmem1, am = a_lo + 8 * m;
+                    if (passes & 2) {
+                      umma2_w_keep(d, am, a_hi32, b_lo, b_hi32, idesc, accum);
+                      umma2_w_reuse(d, am, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+                    } else {
+                      umma2_w(d, am, a_hi32, b_lo, b_hi32, idesc, accum);
+                    }
+                    if (passes & 1) umma2_w(d, am + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+                  }
+                }
+                accum = 1;
+                a_lo += a_step16;
+                b_lo += b_step16;
+              }
+            } else if (BCAT) {
               // 2 MMAs per k16 instead of 3: the A tile (4 KB of shared-memory reads per MMA, the binding resource
               // at narrow N) is fetched twice, not three times
 #pragma unroll 1
@@ -532,18 +681,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             }
             // stage free once these MMAs have read it -- signalled to every CTA that multicasts into it
-            if (leader && !RES) {
-              if (p.cs == 1) umma_commit(B_EMPTY + bs * 8);
-              else umma_commit_mc(B_EMPTY + bs * 8, mc_mask);
-            }
+            if (leader && !RES) commit_stage<CG>(B_EMPTY + bs * 8, p.cs, mc_mask);
             if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
           }
           if (++kw == p.ks) { kw = 0; a_tap += row_skip16; } else { ++a_tap; }
         }
-        if (leader) umma_commit(A_EMPTY + abuf * 8);
+        if (leader) { if (CG == 2) umma2_commit_mc(A_EMPTY + abuf * 8, 3); else umma_commit(A_EMPTY + abuf * 8); }
         if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
       }
-      if (leader) umma_commit(T_FULL + acc * 8);
+      if (leader) { if (CG == 2) umma2_commit_mc(T_FULL + acc * 8, 3); else umma_commit(T_FULL + acc * 8); }
       if (++acc == (uint32_t)p.n_acc) { acc = 0; tph ^= 1; }
     }
   } else if (warp >= p.n_epi && warp < TC_WORK_WARPS) {
@@ -576,8 +722,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool ok = tc.real && (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w && ch < p.c_valid;
             const uint8_t* src = ok ? img + ((size_t)(gy * p.w + gx) * p.in_stride + ch) * 2 : p.in;
             const uint32_t d = dst + cgi * p.CGS + pix * 16;
+            if (!(p.skip & 4)) {
             cp_async16(d, src, ok ? 16u : 0u);
             if (p.a_planes == 2) cp_async16(d + p.a_plane_bytes, src + p.in_plane_bytes, ok ? 16u : 0u);  // plane 1 of the dummy address is valid
+            }
           }
           pix += nload / 2;
           while (pix >= npix) { pix -= npix; ++cpi; }
@@ -694,7 +842,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(T_FULL + acc * 8, tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + sub * p.sub_stride + ((uint32_t)(q * 32) << 16);
-      for (int c0 = half * 16; c0 < tc.nt; c0 += (p.n_epi >> 2) * 16) {
+      for (int c0 = half * 16; c0 < tc.nt && !(p.skip & 1); c0 += (p.n_epi >> 2) * 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         if (BCAT) {  // hi*lo partial sums live nt columns further
@@ -771,7 +919,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (MT > 1 && ++sub < MT) goto next_sub;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(T_EMPTY + acc * 8);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(T_EMPTY + acc * 8, 0));  // the pair leader issues for both CTAs
+        else mbar_arrive(T_EMPTY + acc * 8);
+      }
     }
     if (p.epi == 2 && p.head_loss != nullptr) {
       head_loss_acc = warp_sum(head_loss_acc);
@@ -781,10 +932,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.dbg[0] = clock64() - dbg_c0;
+    p.dbg[1] = t1 - dbg_t0;
+  }
   if (p.cs > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / signal its barriers
   if (warp == 18) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -802,6 +960,7 @@ struct TcPackParams {
   int rh, rw, c_grp, cg;  // packed output-channel order (up-shuffle groups)
   int dir;                // 0 forward (K = input channels, N = packed output channels), 1 dgrad (swapped, flipped)
   int C, N, NT, KC, SBC, b_planes, bcat;
+  int cg2;                // CTA-pair plan: every stage stored per half of its columns, [half][plane][k-group][n / 2][8]
 };
 
 __device__ __forceinline__ int unpack_cout(int np, int rh, int rw, int c_grp, int cg) {
@@ -869,7 +1028,13 @@ __device__ __forceinline__ void tc_pack_body(const TcPackParams& q, long long e_
     const size_t stage_bytes = (size_t)nt * q.SBC * 2 * q.b_planes;
     const size_t ntile_stride = (size_t)stages_per_ntile * q.NT * q.SBC * 2 * q.b_planes;
     uint8_t* st = q.out + (size_t)tn * ntile_stride + (size_t)s * stage_bytes;
-    if (q.bcat) {  // [k-group][plane][n][8]
+    if (q.cg2) {  // [half][plane][k-group][n in half][8]: each CTA of the pair fetches one contiguous half-stage
+      const int nh = nt >> 1, h = nn >= nh ? 1 : 0, nl = nn - h * nh;
+      uint8_t* hb = st + (size_t)h * (stage_bytes >> 1);
+      const size_t o = ((size_t)g * nh + nl) * 16;
+      *reinterpret_cast<uint4*>(hb + o) = hi;
+      if (q.b_planes == 2) *reinterpret_cast<uint4*>(hb + (size_t)nh * q.SBC * 2 + o) = lo;
+    } else if (q.bcat) {  // [k-group][plane][n][8]
       const size_t o = ((size_t)g * 2 * nt + nn) * 16;
       *reinterpret_cast<uint4*>(st + o) = hi;
       *reinterpret_cast<uint4*>(st + o + (size_t)nt * 16) = lo;
@@ -955,10 +1120,22 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   // Planes side by side (see TcParams::bcat) when both operands are split, the doubled tile fits the accumulator
   // slot (256 columns, 128 per pixel tile when mt == 2) and K is long enough to amortise the second TMEM read of
   // the epilogue.
-  pl->bcat = (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256 && d->ksize * d->ksize * C >= 512) ? 1 : 0;
+  // CTA pairs (cta_group::2, see conv_tc_kernel): whenever the weights of an N tile are too large to stay resident in the
+  // ring (the small stages keep the single-CTA resident / multicast forms) and there are pixel-tile pairs to form.
+  {
+    const long long w_tile_bytes = (long long)d->ksize * d->ksize * C * pl->NT * 2 * b_planes;
+    const long long tiles_m = (long long)((d->w + TILE_W * pl->mt - 1) / (TILE_W * pl->mt)) * ((d->h + TILE_H - 1) / TILE_H) * d->n;
+    // ... and every SM has a pair's worth of pixel tiles: with fewer tiles (the deep, split-K stages) the relay hop between
+    // the two CTAs is exposed and the multicast form measured faster (HNeRV-3M stage 3 data gradient: 147k against 176k cycles)
+    pl->cg2 = (w_tile_bytes > 96 * 1024 && tiles_m >= (long long)sm_count()) ? 1 : 0;
+    if (const char* e = getenv("NQ_TC_CG2")) {  // tuning override
+      if (atoi(e) == 0) pl->cg2 = 0;
+    }
+  }
+  pl->bcat = (!pl->cg2 && a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256 && d->ksize * d->ksize * C >= 512) ? 1 : 0;
   if (const char* e = getenv("NQ_TC_BCAT")) {  // tuning override
     if (atoi(e) == 0) pl->bcat = 0;
-    else if (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256) pl->bcat = 1;
+    else if (!pl->cg2 && a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256) pl->bcat = 1;
   }
   const int tile_w = TILE_W * pl->mt;
   pl->PW = tile_w + d->ksize - 1;
@@ -974,7 +1151,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   int best = 0, best_kc = 0;
   for (int sbc = (C < 128 ? C : 128) / 16 * 16; sbc >= 16 && !best; sbc -= 16) {
     if (C % sbc) continue;
-    const int stage = pl->NT * sbc * 2 * b_planes;
+    const int stage = pl->NT * sbc * 2 * b_planes >> pl->cg2;  // pair: each CTA stages half of the columns
     if (stage > 32 * 1024 && sbc > 16) continue;
     // activation unit: ~64 channels (a multiple of the stage), fewer when the (16x16-pixel) halo is large
     for (int kc = sbc >= 64 ? sbc : sbc * (64 / sbc); kc >= sbc; kc -= sbc) {
@@ -993,7 +1170,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->KC = best_kc;
   pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
   pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
-  pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes;
+  pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes >> pl->cg2;
   // Ring depths: as many activation buffers (<= 8) as fit next to ~48 KB of weight stages, and as many accumulator
   // slots as the 512 TMEM columns hold, so that several short-K tiles can be in flight.
   const int total = 227 * 1024 - TC_HDR_BYTES - EPI_STAGE_BYTES;
@@ -1032,7 +1209,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
     if (v == 8 || v == 12) pl->n_epi = v;
   }
   // Weights that fit the ring whole (the head: 9 stages of 3 KB) are loaded once per CTA and stay resident.
-  pl->resident = (N <= pl->NT && pl->mt == 1 && !pl->bcat && d->ksize <= 3 && pl->KC == C && sbc == C && sbc <= 96 && (C / sbc) * d->ksize * d->ksize <= pl->n_bstages) ? 1 : 0;
+  pl->resident = (!pl->cg2 && N <= pl->NT && pl->mt == 1 && !pl->bcat && d->ksize <= 3 && pl->KC == C && sbc == C && sbc <= 96 && (C / sbc) * d->ksize * d->ksize <= pl->n_bstages) ? 1 : 0;
   pl->tiles_x = (d->w + tile_w - 1) / tile_w;
   pl->tiles_y = (d->h + TILE_H - 1) / TILE_H;
   pl->tiles_n = (N + pl->NT - 1) / pl->NT;
@@ -1082,7 +1259,7 @@ static int fill_pack(const nq_conv_desc* d, const nq_tc_plan* pl, const float* w
   q.w = w_ref; q.zp = zero_point; q.zp_stride = zp_stride; q.out = reinterpret_cast<uint8_t*>(wpk);
   q.cout = d->cout; q.cin = d->cin; q.cin_src = cin_src; q.ks = d->ksize;
   q.rh = d->rh; q.rw = d->rw; q.c_grp = d->c_grp; q.cg = d->cg;
-  q.dir = pl->dir; q.C = pl->C; q.N = pl->N; q.NT = pl->NT; q.KC = pl->KC; q.SBC = pl->SBC; q.b_planes = pl->b_planes; q.bcat = pl->bcat;
+  q.dir = pl->dir; q.C = pl->C; q.N = pl->N; q.NT = pl->NT; q.KC = pl->KC; q.SBC = pl->SBC; q.b_planes = pl->b_planes; q.bcat = pl->bcat; q.cg2 = pl->cg2;
   const long long total = (long long)(pl->C / pl->SBC) * d->ksize * d->ksize * (pl->SBC / 8) * pl->NT * pl->tiles_n;
   blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
@@ -1163,6 +1340,7 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
     return NQ_ERR_BAD_ARG;
   if (p.mt < 1 || p.mt > 2 || (p.mt == 2 && (pl->NT > 128 || p.epi == 2))) return NQ_ERR_BAD_ARG;
   if (p.bcat && (p.epi == 2 || pl->a_planes != 2 || pl->b_planes != 2 || 2 * pl->NT * pl->mt > 256)) return NQ_ERR_BAD_ARG;
+  if (pl->cg2 && (p.bcat || pl->resident || p.epi == 2 || (pl->NT & 15))) return NQ_ERR_BAD_ARG;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
@@ -1174,9 +1352,10 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.fd_tiles_x = make_fastdiv(pl->tiles_x); p.fd_tiles_y = make_fastdiv(pl->tiles_y);
   p.fd_rh = make_fastdiv(p.rh); p.fd_rw = make_fastdiv(p.rw); p.fd_PW = make_fastdiv(pl->PW);
   p.fd_npix = make_fastdiv(pl->PW * pl->PH); p.fd_cg = make_fastdiv(p.cg);
-  void (*kern)(const TcParams) = p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1, 0> : conv_tc_kernel<2, 0, 0>)
-                                 : p.bcat  ? conv_tc_kernel<1, 1, 0>
-                                           : (p.resident ? conv_tc_kernel<1, 0, 1> : conv_tc_kernel<1, 0, 0>);
+  void (*kern)(const TcParams) = pl->cg2   ? (p.mt == 2 ? conv_tc_kernel<2, 0, 0, 2> : conv_tc_kernel<1, 0, 0, 2>)
+                                 : p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1, 0, 1> : conv_tc_kernel<2, 0, 0, 1>)
+                                 : p.bcat    ? conv_tc_kernel<1, 1, 0, 1>
+                                             : (p.resident ? conv_tc_kernel<1, 0, 1, 1> : conv_tc_kernel<1, 0, 0, 1>);
   NQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // cluster size: CTAs working on neighbouring pixel tiles of the same N tile share the weight stream
   int cs = pl->cluster;
@@ -1188,6 +1367,10 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   }
   p.tiles_m = pl->tiles_x * pl->tiles_y * d->n;
   if (cs < 1 || p.tiles_m < 2 * cs) cs = 1;
+  if (pl->cg2) {  // the pair IS the cluster
+    if (p.tiles_m < 4) return NQ_ERR_BAD_ARG;
+    cs = 2;
+  }
   p.cs = cs;
   p.tiles_m_pad = (p.tiles_m + cs - 1) / cs * cs;
   p.ncb = (pl->C + pl->KC - 1) / pl->KC;
@@ -1207,7 +1390,26 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static const int n_prod_env = getenv("NQ_TC_PROD") ? atoi(getenv("NQ_TC_PROD")) : 0;  // tuning override
+  p.n_prod = n_prod_env >= 1 && n_prod_env <= 32 ? n_prod_env : 4;
+  if (p.n_prod > pl->n_bstages) p.n_prod = pl->n_bstages;
+  static const int skip_flags = getenv("NQ_TC_SKIP") ? atoi(getenv("NQ_TC_SKIP")) : 0;
+  p.skip = skip_flags;
+  static const bool dbg_on = getenv("NQ_TC_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {  // debugging aid: synchronises after every launch and prints the SM clock the kernel saw
+    if (!dbg_buf) NQ_CUDA_CHECK(cudaMalloc(&dbg_buf, 8 * sizeof(long long)));
+    NQ_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), s));
+    p.dbg = dbg_buf;
+  }
   NQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  if (dbg_on) {
+    long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    NQ_CUDA_CHECK(cudaStreamSynchronize(s));
+    NQ_CUDA_CHECK(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[NQ_TC_DBG] epi=%d hw=%dx%d C=%d N=%d ks=%d mt=%d bcat=%d: %lld cycles, %lld ns, SM clock %.0f MHz\n", p.epi, p.h, p.w,
+            p.C, p.N, p.ks, p.mt, p.bcat, h[0], h[1], h[1] > 0 ? (double)h[0] / (double)h[1] * 1e3 : 0.0);
+  }
   return NQ_OK;
 }
 
