@@ -39,7 +39,7 @@ class TcPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("dir", "C", "N", "NT", "KC", "SBC", "a_planes", "b_planes", "PW", "PH", "CGS", "a_plane_bytes",
                  "a_buf_bytes", "b_stage_bytes", "n_bstages", "smem_bytes", "tiles_x", "tiles_y", "tiles_n",
-                 "total_tiles", "cluster", "mt", "bcat", "n_abuf", "n_acc", "acc_stride", "n_epi", "resident", "ksplit", "cg2")] + [("wpk_bytes", C.c_int64), ("workspace_floats", C.c_int64)]
+                 "total_tiles", "cluster", "mt", "bcat", "n_abuf", "n_acc", "acc_stride", "n_epi", "resident", "ksplit", "cg2", "gst", "reserved")] + [("wpk_bytes", C.c_int64), ("workspace_floats", C.c_int64)]
 
 
 class TcWgradPlan(C.Structure):

@@ -81,7 +81,8 @@ struct TcParams {
   int rh, rw, cg, act;   // fwd: up-shuffle of this stage's output; dgrad: previous stage's (un-shuffle)
   int tiles_x, tiles_y, tiles_n, total_tiles;
   int PW, PH, CGS;       // halo width/height (pixels), channel-group stride (bytes)
-  int a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages;
+  int a_plane_bytes, a_buf_bytes, b_stage_bytes, n_bstages;  // n_bstages ring slots of gst weight stages each
+  int gst, b_slot_bytes;  // weight stages per ring slot (one bulk copy, one barrier round trip), bytes per slot
   int in_stride, c_valid;  // channels per pixel stored in `in` (<= C) : channels >= c_valid are read as zero
   int n_store;           // dgrad: columns actually stored / row stride of zprev and out (<= N, N padded to 16)
   int epi_stage_off;     // byte offset of the epilogue staging tiles in shared memory
@@ -441,31 +442,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int nsb_full = p.KC / p.SBC;
       const int stages_per_ntile = (p.C / p.SBC) * taps;
       const size_t ntile_stride = (size_t)stages_per_ntile * p.NT * p.SBC * 2 * p.b_planes;
-      uint32_t sc = 0, bs = 0, bph = 0;
+      uint32_t bs = 0, bph = 0;
       for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
         const TileCoord tc = tile_coord(p, t, rank);
         const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * 2 * p.b_planes;
         const uint32_t part = stage_bytes / p.cs;  // pair (CG == 2): this CTA's half of the stage = its N / 2 rows of B
-        const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride + (size_t)tc.cb0 * taps * nsb_full * stage_bytes;
-        for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
-          const int nsb = cb == ncb - 1 ? p.nsb_last : nsb_full;
-          for (int tap = 0; tap < taps; ++tap)
-            for (int sb = 0; sb < nsb; ++sb, ++sc) {
-              const uint32_t s = bs, ph = bph;
-              if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
-              if (turn == lane) {
-                mbar_wait(B_EMPTY + s * 8, ph ^ 1);
-                mbar_arrive_expect_tx(B_FULL + s * 8, CG == 2 ? part : stage_bytes);
-                if (CG == 2)  // own half only, at the base of the slot (packed per half: [half][plane][k-group][n / 2][8])
-                  bulk_g2s(b_base + s * p.b_stage_bytes, src + rank * part, part, B_FULL + s * 8);
-                else if (p.cs == 1)
-                  bulk_g2s(b_base + s * p.b_stage_bytes, src, stage_bytes, B_FULL + s * 8);
-                else  // this CTA fetches its 1/cs of the stage and multicasts it to every CTA of the cluster
-                  bulk_g2s_mc(b_base + s * p.b_stage_bytes + rank * part, src + rank * part, part, B_FULL + s * 8, mc_mask);
-              }
-              if (++turn == p.n_prod) turn = 0;
-              src += stage_bytes;
+        // the tile's stages are contiguous in issue order (pair: each half of the columns is, [N tile][half][stage]);
+        // a ring slot takes up to gst of them in ONE copy
+        int rem = taps * (nsb_full * (tc.cb1 - tc.cb0) - (tc.cb1 == ncb ? nsb_full - p.nsb_last : 0));
+        const size_t s0 = (size_t)tc.cb0 * taps * nsb_full;
+        const uint32_t unit = CG == 2 ? part : stage_bytes;  // bytes per stage in this CTA's stream
+        const uint8_t* src = p.wpk + (size_t)(tc.n0 / p.NT) * ntile_stride + s0 * unit +
+                             (CG == 2 ? (size_t)rank * stages_per_ntile * part : (size_t)0);
+        while (rem > 0) {
+          const int g = rem < p.gst ? rem : p.gst;
+          const uint32_t s = bs, ph = bph, bytes = (uint32_t)g * unit;
+          if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
+          if (turn == lane) {
+            mbar_wait(B_EMPTY + s * 8, ph ^ 1);
+            mbar_arrive_expect_tx(B_FULL + s * 8, bytes);
+            if (CG == 2 || p.cs == 1) {
+              bulk_g2s(b_base + s * p.b_slot_bytes, src, bytes, B_FULL + s * 8);
+            } else {  // this CTA fetches its 1/cs of the slot's bytes and multicasts it to every CTA of the cluster
+              const uint32_t gp = bytes / p.cs;
+              bulk_g2s_mc(b_base + s * p.b_slot_bytes + rank * gp, src + rank * gp, gp, B_FULL + s * 8, mc_mask);
             }
+          }
+          if (++turn == p.n_prod) turn = 0;
+          src += bytes;
+          rem -= g;
         }
         if (RES) break;  // the ring now holds every stage of the (single) N tile for the rest of the kernel
       }
@@ -479,13 +484,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t bs = 0, bph = 0;
       for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
         const TileCoord tc = tile_coord(p, t, rank);
-        for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
-          const int nst = (cb == ncb - 1 ? p.nsb_last : nsb_full) * taps;
-          for (int i = 0; i < nst; ++i) {
-            mbar_wait(B_FULL + bs * 8, bph);
-            mbar_arrive_cluster(lead_full + bs * 8);
-            if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
-          }
+        int rem = taps * (nsb_full * (tc.cb1 - tc.cb0) - (tc.cb1 == ncb ? nsb_full - p.nsb_last : 0));
+        for (; rem > 0; rem -= p.gst) {  // one arrival per ring slot
+          mbar_wait(B_FULL + bs * 8, bph);
+          mbar_arrive_cluster(lead_full + bs * 8);
+          if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -575,7 +578,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         if (leader) umma_commit(A_EMPTY + abuf * 8);
         if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
-      } else
+      } else {
+      // weight stages left in this tile / in the current ring slot, position inside the slot
+      int rem = taps * (nsb_full * (tc.cb1 - tc.cb0) - (tc.cb1 == ncb ? nsb_full - p.nsb_last : 0));
+      int glen = 0, gi = 0;
+      const uint32_t stage16 = (uint32_t)((tc.nt / CG) * p.SBC * 2 * p.b_planes) >> 4;  // this tile's bytes per stage / 16
+      uint32_t b_grp = 0;
       for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
         if (CG == 2) mbar_wait_cluster(A_FULL + abuf * 8, aph); else mbar_wait(A_FULL + abuf * 8, aph);
         fence_proxy_async();  // cp.async wrote the tile through the generic proxy; the MMA reads it through the async proxy
@@ -587,11 +595,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int tap = 0; tap < taps; ++tap) {
           uint32_t a_lo = a_tap;
           for (int sb = 0; sb < nsb; ++sb) {
-            if (b_wait) {
+            if (gi == 0) {  // a new ring slot: up to gst stages behind one barrier
+              glen = rem < p.gst ? rem : p.gst;
               if (CG == 2) mbar_wait_cluster(B_FULL + bs * 8, bph); else mbar_wait(B_FULL + bs * 8, bph);
               tc_fence_after();
+              b_grp = (((b_base + bs * p.b_slot_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
             }
-            uint32_t b_lo = (((b_base + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+            uint32_t b_lo = b_grp;
+            b_grp += stage16;
             // uniform loops; only the MMA itself is predicated on the leader lane, so that ptxas keeps the
             // descriptors in uniform registers instead of broadcasting them per instruction
             if (CG == 2) {
@@ -680,14 +691,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 b_lo += b_step16;
               }
             }
-            // stage free once these MMAs have read it -- signalled to every CTA that multicasts into it
-            if (leader && !RES) commit_stage<CG>(B_EMPTY + bs * 8, p.cs, mc_mask);
-            if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
+            // slot free once these MMAs have read it -- signalled to every CTA that multicasts into it
+            if (++gi == glen) {
+              if (leader) commit_stage<CG>(B_EMPTY + bs * 8, p.cs, mc_mask);
+              if (++bs == (uint32_t)p.n_bstages) { bs = 0; bph ^= 1; }
+              rem -= glen;
+              gi = 0;
+            }
           }
           if (++kw == p.ks) { kw = 0; a_tap += row_skip16; } else { ++a_tap; }
         }
         if (leader) { if (CG == 2) umma2_commit_mc(A_EMPTY + abuf * 8, 3); else umma_commit(A_EMPTY + abuf * 8); }
         if (++abuf == (uint32_t)p.n_abuf) { abuf = 0; aph ^= 1; }
+      }
       }
       if (leader) { if (CG == 2) umma2_commit_mc(T_FULL + acc * 8, 3); else umma_commit(T_FULL + acc * 8); }
       if (++acc == (uint32_t)p.n_acc) { acc = 0; tph ^= 1; }
@@ -1028,9 +1044,9 @@ __device__ __forceinline__ void tc_pack_body(const TcPackParams& q, long long e_
     const size_t stage_bytes = (size_t)nt * q.SBC * 2 * q.b_planes;
     const size_t ntile_stride = (size_t)stages_per_ntile * q.NT * q.SBC * 2 * q.b_planes;
     uint8_t* st = q.out + (size_t)tn * ntile_stride + (size_t)s * stage_bytes;
-    if (q.cg2) {  // [half][plane][k-group][n in half][8]: each CTA of the pair fetches one contiguous half-stage
+    if (q.cg2) {  // [half of the columns][stage][plane][k-group][n in half][8]: each CTA of the pair streams ONE contiguous region
       const int nh = nt >> 1, h = nn >= nh ? 1 : 0, nl = nn - h * nh;
-      uint8_t* hb = st + (size_t)h * (stage_bytes >> 1);
+      uint8_t* hb = q.out + (size_t)tn * ntile_stride + ((size_t)h * stages_per_ntile + s) * (stage_bytes >> 1);
       const size_t o = ((size_t)g * nh + nl) * 16;
       *reinterpret_cast<uint4*>(hb + o) = hi;
       if (q.b_planes == 2) *reinterpret_cast<uint4*>(hb + (size_t)nh * q.SBC * 2 + o) = lo;
@@ -1184,13 +1200,35 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
     const int v = atoi(e);
     if (v >= 2 && v <= TC_MAX_RING && total - v * pl->a_buf_bytes >= 2 * pl->b_stage_bytes) n_abuf = v;
   }
+  // Weight stages per ring slot.  Every slot costs the issuing thread one barrier wait, one tcgen05.commit and the ring
+  // arithmetic, ~250 cycles that the one-or-two-deep MMA queue hides only in part (HNeRV-3M stage 5: 720 cycles of MMAs per
+  // stage, 970 per stage measured); slots of several stages amortise them, and one bulk copy moves the whole slot (a copy costs
+  // its issuing lane ~1000 cycles whatever its size, tools/tma_bulk_bench.cu).  Largest slot <= 32 KB that leaves >= 3 slots,
+  // trading activation buffers beyond the second for it.
+  int gst = 1;
+  if ((long long)d->ksize * d->ksize * C * pl->NT * 2 * b_planes > 96 * 1024) {  // not a candidate for resident weights
+    const int stages_tile = (C / sbc) * d->ksize * d->ksize;
+    for (int na = n_abuf; na >= 2; --na) {
+      const int bud = total - na * pl->a_buf_bytes;
+      int g = bud / 3 / pl->b_stage_bytes;
+      if (g * pl->b_stage_bytes > 32 * 1024) g = 32 * 1024 / pl->b_stage_bytes;
+      if (g > 8) g = 8;
+      if (g > stages_tile) g = stages_tile;
+      if (g > gst) { gst = g; n_abuf = na; }
+    }
+  }
+  if (const char* e = getenv("NQ_TC_GST")) {  // tuning override
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8 && (total - n_abuf * pl->a_buf_bytes) / (v * pl->b_stage_bytes) >= 2) gst = v;
+  }
+  pl->gst = gst;
   pl->n_abuf = n_abuf;
   const int budget = total - n_abuf * pl->a_buf_bytes;
-  int nst = budget / pl->b_stage_bytes;
+  int nst = budget / (gst * pl->b_stage_bytes);
   if (nst > TC_MAX_BSTAGES) nst = TC_MAX_BSTAGES;
   if (nst < 2) return NQ_ERR_UNSUPPORTED;
   pl->n_bstages = nst;
-  pl->smem_bytes = TC_HDR_BYTES + n_abuf * pl->a_buf_bytes + nst * pl->b_stage_bytes + EPI_STAGE_BYTES;
+  pl->smem_bytes = TC_HDR_BYTES + n_abuf * pl->a_buf_bytes + nst * gst * pl->b_stage_bytes + EPI_STAGE_BYTES;
   int sub_cols = pl->NT * (pl->bcat ? 2 : 1), sub_stride = 32;
   while (sub_stride < sub_cols) sub_stride *= 2;
   pl->acc_stride = sub_stride * pl->mt;
@@ -1343,7 +1381,10 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   if (pl->cg2 && (p.bcat || pl->resident || p.epi == 2 || (pl->NT & 15))) return NQ_ERR_BAD_ARG;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
-  p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * pl->b_stage_bytes;
+  p.gst = pl->gst < 1 ? 1 : pl->gst;
+  if (p.gst > 1 && pl->resident) return NQ_ERR_BAD_ARG;
+  p.b_slot_bytes = p.gst * pl->b_stage_bytes;
+  p.epi_stage_off = TC_HDR_BYTES + pl->n_abuf * pl->a_buf_bytes + pl->n_bstages * p.b_slot_bytes;
   if (p.epi == 1 || p.epi == 3) { p.out_h = p.h / p.rh; p.out_w = p.w / p.rw; p.quad_stride = p.rh * p.rw * p.n_store; }
   else { p.out_h = p.h * p.rh; p.out_w = p.w * p.rw; p.quad_stride = 0; }
   if ((long long)p.n * p.out_h * p.out_w >= (1LL << 31) || (long long)p.n * p.h * p.w >= (1LL << 31)) return NQ_ERR_BAD_SHAPE;

@@ -95,6 +95,25 @@ __device__ __forceinline__ void wmma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t 
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+// same MMA, keeping the A operand in the collector for the next MMA (same A, other B) / taking it from there: the 4 KB
+// A tile is read from shared memory once for both
+#define NQ_WMMA(NAME, QUAL)                                                                                               \
+  __device__ __forceinline__ void NAME(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,          \
+                                       uint32_t idesc, uint32_t accum) {                                                    \
+    asm volatile(                                                                                                           \
+        "{\n\t"                                                                                                             \
+        ".reg .pred p;\n\t"                                                                                                 \
+        ".reg .b64 da, db;\n\t"                                                                                             \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                                         \
+        "mov.b64 da, {%1, %2};\n\t"                                                                                         \
+        "mov.b64 db, {%3, %4};\n\t"                                                                                         \
+        "tcgen05.mma.cta_group::1.kind::f16" QUAL " [%0], da, db, %5, p;\n\t"                                              \
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)                               \
+        : "memory");                                                                                                        \
+  }
+NQ_WMMA(wmma_w_keep, ".collector::a::fill")
+NQ_WMMA(wmma_w_reuse, ".collector::a::lastuse")
+#undef NQ_WMMA
 __device__ __forceinline__ void wcp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -133,6 +152,10 @@ __device__ __forceinline__ void wsplit8(const float4& a, const float4& b, uint4&
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// BCAT / PASSES are compile-time copies of WgParams::bcat and of (a_planes == 2) | (b_planes == 2) << 1: the issue loop is
+// bound by the instruction stream of its one thread (~13 cycles per instruction), and the per-MMA tests of runtime flags were
+// a third of it (22 instructions per 3 MMAs, profiles/r02p_wgrad.md)
+template <int BCAT, int PASSES>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t bar0 = wsmem_u32(smem);
@@ -201,12 +224,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * nc) >> 3) << 17);  // N = 2 nc
-    const uint32_t acc_cols = (uint32_t)p.NC << p.bcat;
+    const uint32_t acc_cols = (uint32_t)p.NC << BCAT;
     const uint32_t a_hi32 = ((uint32_t)p.CGS_A >> 4) | (1u << 14), b_hi32 = ((uint32_t)p.CGS_B >> 4) | (1u << 14);
     const uint32_t lbo_bits = (128u >> 4) << 16;
     const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)p.b_plane_bytes >> 4;
     const uint32_t mb_step16 = (uint32_t)(16 * p.CGS_A) >> 4, row16 = (WG_TW * 16) >> 4;
-    const int passes = (p.a_planes == 2 ? 1 : 0) | (p.b_planes == 2 ? 2 : 0);
+    constexpr int passes = PASSES;
     uint32_t accum = 0, bi = 0, ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       wbar_wait(FULL + bi * 8, ph);
@@ -227,13 +250,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             if (khl >= nkh) break;
             const uint32_t a_lo = a16 + (r + khl) * row16, b_lo = b16 + r * row16, d = tmem_base + khl * acc_cols;
             if (leader) {
-              if (p.bcat) {  // x_hi * [dz_hi | dz_lo] in one MMA of 2 NC columns, then x_lo * dz_hi: 2 A-tile reads, not 3
+              if (BCAT) {  // x_hi * [dz_hi | dz_lo] in one MMA of 2 NC columns, then x_lo * dz_hi: 2 A-tile reads, not 3
                 wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc2, r == 0 ? accum : 1u);
                 wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
+              } else if (passes & 2) {  // x_hi meets both dz planes: fetched once (A collector)
+                wmma_w_keep(d, a_lo, a_hi32, b_lo, b_hi32, idesc, r == 0 ? accum : 1u);
+                wmma_w_reuse(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+                if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
               } else {
                 wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, r == 0 ? accum : 1u);
                 if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
-                if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
               }
             }
           }
@@ -248,9 +274,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll 1
           for (int mb = 0; mb < p.MB; ++mb) {
             if (leader) {
-              wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
+              if (passes & 2) {
+                wmma_w_keep(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
+                wmma_w_reuse(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
+              } else {
+                wmma_w(d, a_lo, a_hi32, b_lo, b_hi32, idesc, accum);
+              }
               if (passes & 1) wmma_w(d, a_lo + a_plane16, a_hi32, b_lo, b_hi32, idesc, 1);
-              if (passes & 2) wmma_w(d, a_lo, a_hi32, b_lo + b_plane16, b_hi32, idesc, 1);
             }
             a_lo += mb_step16;
             d += acc_cols;
@@ -392,7 +422,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           } else if (g == Gc && ch < 4 && kh == 0 && cg0 == 0) {
             orow = p.ks * p.ks * p.C + ch;  // bias gradient row (+ 3 zero rows)
           }
-          const uint32_t taddr = tmem_base + (khl * p.MB + mb) * (p.NC << p.bcat) + ((uint32_t)(q * 32) << 16);
+          const uint32_t taddr = tmem_base + (khl * p.MB + mb) * (p.NC << BCAT) + ((uint32_t)(q * 32) << 16);
           for (int c0 = 0; c0 < nc; c0 += 16) {
             uint32_t v[16];
             asm volatile(
@@ -402,7 +432,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 : "r"(taddr + c0)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (p.bcat) {  // + the x_hi * dz_lo partial sums, NC columns further
+            if (BCAT) {  // + the x_hi * dz_lo partial sums, NC columns further
               uint32_t v2[16];
               asm volatile(
                   "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -642,9 +672,16 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   p.x_plane_bytes = (size_t)d->n * d->h * d->w * pl->C * 2;
   p.dz_plane_bytes = (size_t)d->n * d->h * d->w * p.dz_stride * 2;
   cudaStream_t s = as_stream(stream);
-  NQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int passes = (p.a_planes == 2 ? 1 : 0) | (p.b_planes == 2 ? 2 : 0);
+  if (p.bcat && passes != 3) return NQ_ERR_BAD_ARG;
+  void (*kern)(const WgParams) = p.bcat      ? wgrad_tc_kernel<1, 3>
+                                 : passes == 3 ? wgrad_tc_kernel<0, 3>
+                                 : passes == 2 ? wgrad_tc_kernel<0, 2>
+                                 : passes == 1 ? wgrad_tc_kernel<0, 1>
+                                               : wgrad_tc_kernel<0, 0>;
+  NQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int grid = pl->psplits * pl->msplit * pl->nsplits * pl->khg;
-  wgrad_tc_kernel<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
+  kern<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
   NQ_LAUNCH_CHECK();
   if (!dwk) return NQ_OK;
   const int64_t n4 = (int64_t)(d->ksize * d->ksize * pl->C + 4) * pl->N / 4;

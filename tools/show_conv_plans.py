@@ -22,4 +22,4 @@ for name in names:
                 print(f"  {tag}[{i}]: status {st}")
                 continue
             print(f"  {tag}[{i}]: {d.h}x{d.w} ks={d.ksize} C={p.C} N={p.N} NT={p.NT} mt={p.mt} bcat={p.bcat} cg2={p.cg2} ks={p.ksplit} res={p.resident} epi={p.n_epi} abuf={p.n_abuf} acc={p.n_acc}x{p.acc_stride} KC={p.KC} SBC={p.SBC} PW={p.PW} "
-                  f"a_buf={p.a_buf_bytes} stage={p.b_stage_bytes} x{p.n_bstages} smem={p.smem_bytes} tiles={p.total_tiles}")
+                  f"a_buf={p.a_buf_bytes} stage={p.b_stage_bytes} x{p.gst} x{p.n_bstages} smem={p.smem_bytes} tiles={p.total_tiles}")
