@@ -332,7 +332,7 @@ def run_b200(args):
     value = args.steps * world / (ms * 1e-3)
 
     # ---- per-kernel timing of the convolution launches (CUDA events on the launch stream)
-    kern = eng.kernel_profile(lambda: step(0, *resident(0), eager=True), reps=3)
+    kern = eng.kernel_profile(lambda: step(0, *resident(0), eager=True), reps=5)
 
     # ---- quantised decode (hard rounding, weights static -> packed once, Q9)
     eng.soft_w = False
@@ -342,7 +342,7 @@ def run_b200(args):
         eng.forward(embeds_d[:B], reuse_weights=True)
     ms_d, _, _ = timed(lambda i: eng.forward(resident(i)[0], reuse_weights=True), args.decode_steps)
     decode_fps = args.decode_steps * B * world / (ms_d * 1e-3)
-    kern_dec = eng.kernel_profile(lambda: eng.forward(embeds_d[:B], reuse_weights=True), reps=3)
+    kern_dec = eng.kernel_profile(lambda: eng.forward(embeds_d[:B], reuse_weights=True), reps=5)
     eng.soft_w = True
     eng.invalidate()
 

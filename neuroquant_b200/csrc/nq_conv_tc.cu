@@ -370,9 +370,11 @@ __device__ __forceinline__ void commit_stage(uint32_t bar, int cs, uint16_t mc_m
 // for both.  What the leader must know about its peer -- activation tile landed, weight half landed, accumulator drained --
 // reaches it as one extra arrival on ITS OWN barriers (remote mbarrier.arrive from the peer's relay warps 17 / 19 and
 // epilogue warps); what the peer must know -- operands consumed, accumulator ready -- is the multicast tcgen05.commit.
-// Per MMA instruction the issuing thread now moves twice the work (these kernels are bound by that one thread's
-// instruction stream, profiles/r02h_issue_bound.md), every weight byte is read from L2 once per pair, written to shared
-// memory once per pair and read by each tensor core from ONE of the two shared memories.
+// Every weight byte is read from L2 once per pair, written to shared memory once per pair, and each tensor core fetches
+// half of B from its neighbour: operand reads per MMA drop from 128 x 32 + N x 32 bytes to 128 x 32 + N x 16 per SM
+// (tools/umma_bench2.cu: the operand fetch runs at 128 B/clk/SM and binds below N = 128).  Measured on HNeRV-3M
+// (profiles/r02h_conv_analysis.md): conv_fwd[5] 537k -> 476k SM cycles, conv_dgrad[5] 914k -> 843k, stage 4 likewise;
+// the deep split-K stages (few tiles per SM) keep the multicast form, where the relay hop is not exposed.
 template <int MT, int BCAT, int RES, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -433,10 +435,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 16) {
     // ===================== weight-stage producer (TMA bulk copies) =====================
-    // n_prod lanes take the stages round robin.  One thread sustains only about one bulk copy per 650-1200 SM cycles
+    // n_prod lanes take the ring slots round robin.  One thread sustains only about one bulk copy per 650-1200 SM cycles
     // however small the copy (tools/tma_bulk_bench.cu: 15 KB copies land at 22 B/clk/SM from one thread, 49 from four
-    // lanes); with a single producer every weight stage cost ~900 cycles and the convolutions ran at the producer's pace,
-    // not the tensor pipe's (profiles/r02m_weight_stream.md).
+    // lanes, 3 KB copies at 2.6 / 8.8), which would bind plans with small slots; on HNeRV-3M one lane or four measure the
+    // same (profiles/r02h_conv_analysis.md: the stage time is set by the issuing thread, not by the stream).
     if (lane < p.n_prod) {
       int turn = 0;
       const int nsb_full = p.KC / p.SBC;

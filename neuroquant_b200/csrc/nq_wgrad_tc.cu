@@ -152,9 +152,11 @@ __device__ __forceinline__ void wsplit8(const float4& a, const float4& b, uint4&
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// BCAT / PASSES are compile-time copies of WgParams::bcat and of (a_planes == 2) | (b_planes == 2) << 1: the issue loop is
-// bound by the instruction stream of its one thread (~13 cycles per instruction), and the per-MMA tests of runtime flags were
-// a third of it (22 instructions per 3 MMAs, profiles/r02p_wgrad.md)
+// BCAT / PASSES are compile-time copies of WgParams::bcat and of (a_planes == 2) | (b_planes == 2) << 1: the per-MMA tests
+// of runtime flags were a third of the unrolled issue sequence (22 -> 15 instructions per 3 MMAs).  Measured effect on
+// conv_wgrad[5] of this and of fetching x_hi once for both dz planes (A collector): none (0.480 -> 0.477 ms) -- that kernel
+// sits at the shared-memory wavefront limit, tensor-core operand reads 50 % + cp.async writes 53 % of the SM's wavefront
+// slots (profiles/r02r_wgrad.md); the collector moved the first share from 86 M to 63 M wavefronts.
 template <int BCAT, int PASSES>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];

@@ -299,7 +299,7 @@ class DecoderEngine:
 
     def kernel_profile(self, step_fn, reps: int = 3):
         """Per-kernel device time of the convolution launches of `step_fn` (CUDA events on the launch
-        stream, averaged over `reps` runs).  Returns a list of dicts sorted by total time."""
+        stream, median of `reps` runs).  Returns a list of dicts sorted by total time."""
         step_fn()
         torch.cuda.synchronize()
         self._prof = []
@@ -309,11 +309,12 @@ class DecoderEngine:
         rows, self._prof = self._prof, None
         agg = {}
         for name, flops, e0, e1 in rows:
-            a = agg.setdefault(name, [0.0, 0, flops])
-            a[0] += e0.elapsed_time(e1)
-            a[1] += 1
-        out = [{"kernel": k, "ms": v[0] / v[1], "flops": v[2], "tflops": v[2] / (v[0] / v[1] * 1e-3) / 1e12}
-               for k, v in agg.items()]
+            agg.setdefault(name, ([], flops))[0].append(e0.elapsed_time(e1))
+        out = []
+        for k, (ts, flops) in agg.items():
+            ts.sort()
+            ms = ts[len(ts) // 2]  # median: one slow repetition (a first-touch page fault, a clock dip) must not pick the "dominant" kernel
+            out.append({"kernel": k, "ms": ms, "flops": flops, "tflops": flops / (ms * 1e-3) / 1e12})
         out.sort(key=lambda r: -r["ms"])
         return out
 
