@@ -37,7 +37,8 @@ def main():
     starts = [k for k, d in enumerate(rows) if first in d["name"]]
     # the last complete pair of consecutive starts whose distance equals the most common distance = one replayed iteration
     gaps = [b - a for a, b in zip(starts, starts[1:])]
-    common = max(set(gaps), key=gaps.count)
+    # the graph replays the multi-tensor sequence (fewest launches); eager warm-up iterations are longer
+    common = min(g for g in set(gaps) if g >= 20)
     a = [s for s, g in zip(starts, gaps) if g == common][-1]
     it = rows[a:a + common]
     peak = 6536.0
