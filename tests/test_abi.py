@@ -92,7 +92,16 @@ def test_tc_plans_fit_for_every_workload():
                 cols = pl.NT * (2 if pl.bcat else 1)
                 assert cols <= 256 and pl.mt in (1, 2) and pl.acc_stride >= cols * pl.mt and pl.n_acc * pl.acc_stride <= 512
                 assert 2 <= pl.n_abuf <= 8 and 2 <= pl.n_acc <= 8 and pl.n_epi in (8, 12) and pl.n_bstages <= 16
-                assert pl.smem_bytes >= 1024 + pl.n_abuf * pl.a_buf_bytes + pl.n_bstages * pl.b_stage_bytes
+                assert 1 <= pl.gst <= 8
+                assert pl.smem_bytes >= 1024 + pl.n_abuf * pl.a_buf_bytes + pl.n_bstages * pl.gst * pl.b_stage_bytes
+                if pl.gst > 1:  # several weight stages per ring slot: one bulk copy <= 32 KB, >= 3 slots in flight
+                    assert pl.gst * pl.b_stage_bytes <= 32 * 1024 and pl.n_bstages >= 3 and not pl.resident
+                if pl.cg2:  # CTA pairs: each CTA stages half of the columns; no side-by-side planes, no resident weights
+                    assert not pl.bcat and not pl.resident and pl.NT % 16 == 0
+                    assert pl.b_stage_bytes == pl.NT * pl.SBC * 2 * bp // 2
+                    assert pl.tiles_x * pl.tiles_y * 2 >= 148  # a pair's worth of pixel tiles for every SM
+                else:
+                    assert pl.b_stage_bytes == pl.NT * pl.SBC * 2 * bp
                 if pl.bcat:
                     assert ap == 2 and bp == 2
                 if pl.resident:

@@ -177,3 +177,34 @@ def test_full_size_calibration_psnr_parity(monkeypatch):
     # and from there on different (equally good) codes -- 21 % of them in this run, at 2e-5 dB PSNR difference.  The
     # yardstick: the exact-fp32 engine against ITSELF with the embeddings perturbed by 1e-7 ends 17 % of the codes apart
     # (tools/chaos_check.py, measured on a B200).
+
+
+@pytest.mark.parametrize("workload", ["hnerv-bunny-3m", "nerv-bunny-3m"])
+def test_cta_pair_plans_match_the_multicast_plans(monkeypatch, workload):
+    """Round 2: stages 4-5 run as CTA pairs (tcgen05.mma.cta_group::2, A collector, several weight stages per ring slot).
+    NQ_TC_CG2=0 / NQ_TC_GST=1 select round 1's multicast plans (side-by-side planes, one stage per slot): same products,
+    same fp32 accumulators, another summation order -- frames, loss and every gradient must agree to fp32 rounding."""
+    import ctypes as C
+    import neuroquant_b200 as nq
+    from neuroquant_b200 import _lib as L
+    from neuroquant_b200.engine import stage_descs
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape
+    arch, cfg = WORKLOADS[workload]
+    geoms = nq.geometry_from_cfg(cfg, arch)
+    _, h0, w0 = embed_shape(cfg, arch)
+    d5 = stage_descs(geoms, 2, h0, w0, True)[5]
+    pl = L.TcPlan()
+    assert L.lib.nq_tc_plan_conv(C.byref(d5), 1, 2, 2, C.byref(pl)) == 0
+    assert pl.cg2 == 1 and pl.gst > 1 and pl.bcat == 0, "stage 5 is expected to take a CTA-pair plan"
+    pair = _run(monkeypatch, "tc", workload, 2, False)
+    monkeypatch.setenv("NQ_TC_CG2", "0")
+    monkeypatch.setenv("NQ_TC_GST", "1")
+    assert L.lib.nq_tc_plan_conv(C.byref(d5), 1, 2, 2, C.byref(pl)) == 0
+    assert pl.cg2 == 0 and pl.gst == 1
+    mc = _run(monkeypatch, "tc", workload, 2, False)
+    assert (pair[0] - mc[0]).abs().max() < 2e-6 and (pair[4] - mc[4]).abs().max() < 2e-6
+    assert pair[1] == pytest.approx(mc[1], rel=1e-6)
+    for i, ((gw_p, gb_p), (gw_m, gb_m)) in enumerate(zip(pair[3], mc[3])):
+        for name, a, b in (("dW", gw_p, gw_m), ("db", gb_p, gb_m)):
+            tol = 2e-5 * float(b.abs().max()) + 1e-12
+            assert float((a - b).abs().max()) <= tol, (workload, i, name, float((a - b).abs().max()), tol)
