@@ -48,6 +48,9 @@ struct WgParams {
   int a_planes, b_planes;
   int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
   int dz_stride, n_valid;  // channels per pixel stored in dz (<= N); columns >= n_valid are zero
+  int a_sts;               // shifted input copies staged through registers (one global load, <= ks st.shared) instead of ks cp.async
+  int skip;                // NQ_WG_SKIP (debug): bit 0 shifted-input copies, bit 1 dZ copies, bit 2 MMAs
+  long long* dbg;          // NQ_TC_DBG: {SM cycles, ns} of CTA 0
 };
 
 // ---- PTX helpers (same conventions as nq_conv_tc.cu) ----
@@ -216,12 +219,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  long long dbg_c0 = 0, dbg_t0 = 0;
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 17) {
     // ===================== MMA issuer =====================
     // Highest warp id of its scheduler partition; warp-uniform loop with an elect.sync leader so that the
     // descriptors stay in uniform registers (see nq_conv_tc.cu).
-    const bool leader = welect_one();
+    const bool leader = welect_one() && !(p.skip & 4);
     // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128, N = nc
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nc >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // The (input row, kw, group) items a thread copies are the same for every tile: decode them ONCE into
     // registers (source offset relative to the tile origin, destination offset, dy, dx); the per-tile work is then
     // a bounds test and two adds per copy.  (The decode loop per tile made this kernel issue bound.)
-    constexpr int MAXI = 8;
+    constexpr int MAXI = 4;  // (the register-staged path below covers the 3x3 and 5x5 stages; this one the 1x1 stages)
     int a_so[MAXI], a_do[MAXI], a_dyx[MAXI];  // source element offset, destination byte offset, (dy << 16) | (dx & 0xffff)
     int na = 0;
     bool a_table = true;
@@ -341,6 +349,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         while (cpi >= npair) { cpi -= npair; if (++kw == p.ks) { kw = 0; ++ar; } }
       }
     }
+    // Register-staged input copies (p.a_sts): every source 16 bytes is loaded from global memory ONCE (before the buffer is
+    // even free) and written to its <= ks shifted destinations with st.shared.  The ks cp.async.ca copies per source cost 8
+    // shared-memory / L1 wavefronts per warp instruction each and took 28-35 % of this kernel (profiles/r02r_wgrad.md: with
+    // the input copies skipped conv_wgrad[5] drops from 819 k to 591 k cycles); a 16-lane st.shared run costs 2-3.
+    // Warp items: phase 0 = (staged row, group pair) x source columns 0..15; phase 1 = (block of 4 staged rows, group pair) x
+    // the ks - 1 halo columns 16.. of each row.
+    constexpr int MAXS = 2;
+    int s_so[MAXS], s_do[MAXS], s_dyx[MAXS];  // source element offset, destination of the kw = 0 copy, (dy + 64) << 16 | (dx + 64), or -1: lane unused
+    int ns = 0;
+    const int q0n = p.AR * npair, q1n = ((p.AR + 3) >> 2) * npair;
+    // one decision for the whole CTA: every warp's share of the items fits the registers
+    const bool a_sts = p.a_sts != 0 && (q0n + q1n + nlgrp - 1) / nlgrp <= MAXS;
+    if (a_sts) {
+      for (int q = lgrp; q < q0n + q1n; q += nlgrp) {
+        int ar, xs, cpi;
+        bool ok;
+        if (q < q0n) {
+          ar = q / npair; cpi = q - ar * npair; xs = xl; ok = true;
+        } else {
+          const int q1 = q - q0n, arb = q1 / npair;
+          cpi = q1 - arb * npair; ar = arb * 4 + (xl >> 2); xs = WG_TW + (xl & 3);
+          ok = ar < p.AR && (xl & 3) < p.ks - 1;
+        }
+        const int cg = 2 * cpi + cgp;
+        ok = ok && cg < ncg_c;
+        const int dy = ar + kh0 - p.pad, dx = xs - p.pad;
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k)
+          if (k == ns) {
+            s_so[k] = (dy * p.w + dx) * p.C + (cg0 + cg) * 8;
+            s_do[k] = cg * p.CGS_A + ar * (WG_TW * 16) + xs * 16;
+            s_dyx[k] = ok ? (((dy + 64) << 16) | (dx + 64)) : -1;  // both biased by 64 (|dy|, |dx| < 64): a valid item is >= 0
+          }
+        ++ns;
+      }
+    }
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(p.x);
     const uint16_t* zh = reinterpret_cast<const uint16_t*>(p.dz);
     uint32_t bi = 0, ph = 0;
@@ -349,11 +393,47 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     for (int t = t_begin; t < t_end; ++t) {
       const int y0 = ty * p.TR, x0 = tx * WG_TW, img = img_next;
       if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img_next; } }
+      uint4 s_hi[MAXS], s_lo[MAXS];
+      if (a_sts && !(p.skip & 1)) {  // sources into registers while the MMAs may still be reading the buffer
+        const uint16_t* origin = xh + (ptrdiff_t)((img * p.h + y0) * p.w + x0) * p.C;
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) {
+          s_hi[k] = make_uint4(0u, 0u, 0u, 0u);
+          s_lo[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (k < ns && s_dyx[k] >= 0) {
+            const int gy = y0 + (s_dyx[k] >> 16) - 64, gx = x0 + (s_dyx[k] & 0xffff) - 64;
+            if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
+              const uint16_t* src = origin + s_so[k];
+              s_hi[k] = __ldg(reinterpret_cast<const uint4*>(src));
+              if (p.a_planes == 2) s_lo[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + p.x_plane_bytes));
+            }
+          }
+        }
+      }
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
       const uint32_t buf = buf0 + bi * p.buf_bytes;
       // ---- shifted input copies: staged row ar holds image row y0 + ar + kh0 - pad; copy kw holds source column
       //      x0 + xl + kw - pad; the kw copies of one source sector come from L1 (cp.async.ca)
-      if (a_table) {
+      if (p.skip & 1) {
+      } else if (a_sts) {
+        const uint32_t kw_step = (uint32_t)(ncg_c * p.CGS_A) - 16u;  // next shift: next (kw, group) block, one pixel to the left
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) {
+          if (k < ns && s_dyx[k] >= 0) {
+            uint32_t d = buf + (uint32_t)s_do[k];
+            const int xs = (s_dyx[k] & 0xffff) - 64 + p.pad;  // source column within the staged row: 0 .. 15 + ks - 1
+            for (int kw = 0; kw < p.ks; ++kw, d += kw_step) {
+              const int xd = xs - kw;                          // its destination column in shift kw
+              if ((unsigned)xd < (unsigned)WG_TW) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(s_hi[k].x), "r"(s_hi[k].y), "r"(s_hi[k].z), "r"(s_hi[k].w) : "memory");
+                if (p.a_planes == 2)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + p.a_plane_bytes), "r"(s_lo[k].x), "r"(s_lo[k].y), "r"(s_lo[k].z), "r"(s_lo[k].w) : "memory");
+              }
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared (generic proxy) -> MMA operand reads (async proxy)
+      } else if (a_table) {
         const uint16_t* origin = xh + (ptrdiff_t)((img * p.h + y0) * p.w + x0) * p.C;
 #pragma unroll
         for (int k = 0; k < MAXI; ++k) {
@@ -386,7 +466,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
       }
       // ---- output-gradient tile
-      {
+      if (!(p.skip & 2)) {
         const uint32_t b_dst = buf + p.a_planes * p.a_plane_bytes + bslot * 16;
         const int oy = y0 + br, ox = x0 + bxl;
         const bool pix_ok = oy < p.h && ox < p.w;
@@ -461,6 +541,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.dbg[0] = clock64() - dbg_c0;
+    p.dbg[1] = t1 - dbg_t0;
+  }
   if (warp == 18) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -683,7 +769,24 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
                                                : wgrad_tc_kernel<0, 0>;
   NQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int grid = pl->psplits * pl->msplit * pl->nsplits * pl->khg;
+  static const int sts_env = getenv("NQ_WG_STS") ? atoi(getenv("NQ_WG_STS")) : 1;  // tuning override (0: cp.async copies)
+  p.a_sts = sts_env != 0 && p.ks > 1 && p.ks <= 5;
+  static const int skip_flags = getenv("NQ_WG_SKIP") ? atoi(getenv("NQ_WG_SKIP")) : 0;
+  p.skip = skip_flags;
+  static const bool dbg_on = getenv("NQ_TC_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {  // debugging aid: synchronises after the launch and prints the SM cycles / clock the kernel saw
+    if (!dbg_buf) NQ_CUDA_CHECK(cudaMalloc(&dbg_buf, 2 * sizeof(long long)));
+    p.dbg = dbg_buf;
+  }
   kern<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
+  if (dbg_on) {
+    long long h[2] = {0, 0};
+    NQ_CUDA_CHECK(cudaStreamSynchronize(s));
+    NQ_CUDA_CHECK(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[NQ_TC_DBG] wgrad hw=%dx%d C=%d N=%d ks=%d msplit=%d nkh=%d NC=%d TR=%d nbuf=%d: %lld cycles, %lld ns, SM clock %.0f MHz\n", p.h, p.w,
+            p.C, p.N, p.ks, p.msplit, p.nkh, p.NC, p.TR, p.nbuf, h[0], h[1], h[1] > 0 ? (double)h[0] / (double)h[1] * 1e3 : 0.0);
+  }
   NQ_LAUNCH_CHECK();
   if (!dwk) return NQ_OK;
   const int64_t n4 = (int64_t)(d->ksize * d->ksize * pl->C + 4) * pl->N / 4;
