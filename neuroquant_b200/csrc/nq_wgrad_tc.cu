@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // the input copies skipped conv_wgrad[5] drops from 819 k to 591 k cycles); a 16-lane st.shared run costs 2-3.
     // Warp items: phase 0 = (staged row, group pair) x source columns 0..15; phase 1 = (block of 4 staged rows, group pair) x
     // the ks - 1 halo columns 16.. of each row.
-    constexpr int MAXS = 2;
+    constexpr int MAXS = 4;
     int s_so[MAXS], s_do[MAXS], s_dyx[MAXS];  // source element offset, destination of the kw = 0 copy, (dy + 64) << 16 | (dx + 64), or -1: lane unused
     int ns = 0;
     const int q0n = p.AR * npair, q1n = ((p.AR + 3) >> 2) * npair;
@@ -393,23 +393,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     for (int t = t_begin; t < t_end; ++t) {
       const int y0 = ty * p.TR, x0 = tx * WG_TW, img = img_next;
       if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img_next; } }
-      uint4 s_hi[MAXS], s_lo[MAXS];
-      if (a_sts && !(p.skip & 1)) {  // sources into registers while the MMAs may still be reading the buffer
-        const uint16_t* origin = xh + (ptrdiff_t)((img * p.h + y0) * p.w + x0) * p.C;
+      // register-staged copies go in rounds of two items per thread: round 0 is loaded while the MMAs may still be reading the
+      // buffer (before the wait below), later rounds (wide channel slices only) after it
+      uint4 s_hi[2], s_lo[2];
+      const uint16_t* s_origin = xh + (ptrdiff_t)((img * p.h + y0) * p.w + x0) * p.C;
+      auto s_load = [&](int base) {
 #pragma unroll
-        for (int k = 0; k < MAXS; ++k) {
+        for (int k = 0; k < 2; ++k) {
           s_hi[k] = make_uint4(0u, 0u, 0u, 0u);
           s_lo[k] = make_uint4(0u, 0u, 0u, 0u);
-          if (k < ns && s_dyx[k] >= 0) {
-            const int gy = y0 + (s_dyx[k] >> 16) - 64, gx = x0 + (s_dyx[k] & 0xffff) - 64;
+          const int dyx = k + base < ns ? (k + base == 0 ? s_dyx[0] : k + base == 1 ? s_dyx[1] : k + base == 2 ? s_dyx[2] : s_dyx[3]) : -1;
+          if (dyx >= 0) {
+            const int gy = y0 + (dyx >> 16) - 64, gx = x0 + (dyx & 0xffff) - 64;
             if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w) {
-              const uint16_t* src = origin + s_so[k];
+              const int so = k + base == 0 ? s_so[0] : k + base == 1 ? s_so[1] : k + base == 2 ? s_so[2] : s_so[3];
+              const uint16_t* src = s_origin + so;
               s_hi[k] = __ldg(reinterpret_cast<const uint4*>(src));
               if (p.a_planes == 2) s_lo[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + p.x_plane_bytes));
             }
           }
         }
-      }
+      };
+      if (a_sts && !(p.skip & 1)) s_load(0);
       wbar_wait(EMPTY + bi * 8, ph ^ 1);
       const uint32_t buf = buf0 + bi * p.buf_bytes;
       // ---- shifted input copies: staged row ar holds image row y0 + ar + kh0 - pad; copy kw holds source column
@@ -417,17 +422,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (p.skip & 1) {
       } else if (a_sts) {
         const uint32_t kw_step = (uint32_t)(ncg_c * p.CGS_A) - 16u;  // next shift: next (kw, group) block, one pixel to the left
+        for (int base = 0; base < ns; base += 2) {
+          if (base > 0) s_load(base);
 #pragma unroll
-        for (int k = 0; k < MAXS; ++k) {
-          if (k < ns && s_dyx[k] >= 0) {
-            uint32_t d = buf + (uint32_t)s_do[k];
-            const int xs = (s_dyx[k] & 0xffff) - 64 + p.pad;  // source column within the staged row: 0 .. 15 + ks - 1
-            for (int kw = 0; kw < p.ks; ++kw, d += kw_step) {
-              const int xd = xs - kw;                          // its destination column in shift kw
-              if ((unsigned)xd < (unsigned)WG_TW) {
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(s_hi[k].x), "r"(s_hi[k].y), "r"(s_hi[k].z), "r"(s_hi[k].w) : "memory");
-                if (p.a_planes == 2)
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + p.a_plane_bytes), "r"(s_lo[k].x), "r"(s_lo[k].y), "r"(s_lo[k].z), "r"(s_lo[k].w) : "memory");
+          for (int k = 0; k < 2; ++k) {
+            const int dyx = k + base < ns ? (k + base == 0 ? s_dyx[0] : k + base == 1 ? s_dyx[1] : k + base == 2 ? s_dyx[2] : s_dyx[3]) : -1;
+            if (dyx >= 0) {
+              const int dof = k + base == 0 ? s_do[0] : k + base == 1 ? s_do[1] : k + base == 2 ? s_do[2] : s_do[3];
+              uint32_t d = buf + (uint32_t)dof;
+              const int xs = (dyx & 0xffff) - 64 + p.pad;  // source column within the staged row: 0 .. 15 + ks - 1
+              for (int kw = 0; kw < p.ks; ++kw, d += kw_step) {
+                const int xd = xs - kw;                    // its destination column in shift kw
+                if ((unsigned)xd < (unsigned)WG_TW) {
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(s_hi[k].x), "r"(s_hi[k].y), "r"(s_hi[k].z), "r"(s_hi[k].w) : "memory");
+                  if (p.a_planes == 2)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + p.a_plane_bytes), "r"(s_lo[k].x), "r"(s_lo[k].y), "r"(s_lo[k].z), "r"(s_lo[k].w) : "memory");
+                }
               }
             }
           }
