@@ -443,11 +443,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       int turn = 0;
       const int nsb_full = p.KC / p.SBC;
       const int stages_per_ntile = (p.C / p.SBC) * taps;
-      const size_t ntile_stride = (size_t)stages_per_ntile * p.NT * p.SBC * 2 * p.b_planes;
+      // pair plans with side-by-side planes (CG == 2 && BCAT) store 3 nt SBC bytes per stage and CTA, see pack
+      const size_t ntile_stride = (size_t)stages_per_ntile * p.NT * p.SBC * (CG == 2 && BCAT ? 6 : 2 * p.b_planes);
       uint32_t bs = 0, bph = 0;
       for (int t = cluster_id; t < p.total_groups; t += n_clusters) {
         const TileCoord tc = tile_coord(p, t, rank);
-        const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * 2 * p.b_planes;
+        const uint32_t stage_bytes = (uint32_t)tc.nt * p.SBC * (CG == 2 && BCAT ? 6 : 2 * p.b_planes);
         const uint32_t part = stage_bytes / p.cs;  // pair (CG == 2): this CTA's half of the stage = its N / 2 rows of B
         // the tile's stages are contiguous in issue order (pair: each half of the columns is, [N tile][half][stage]);
         // a ring slot takes up to gst of them in ONE copy
@@ -537,9 +538,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t d_tmem1 = d_tmem + p.sub_stride;  // second pixel tile (mt == 2): 8 pixels = 8 16-byte rows further in the halo
       constexpr bool two = MT == 2;
       const uint32_t idesc = make_idesc(tc.nt, 128 * CG);
-      const uint32_t idesc2 = make_idesc(2 * tc.nt);  // bcat: both weight planes as one operand
-      // k-group stride: nt (bcat: 2 nt; pair: this CTA's nt / 2) rows * 16 bytes >> 4
-      const uint32_t b_lbo16 = CG == 2 ? (uint32_t)tc.nt >> 1 : (uint32_t)tc.nt << BCAT;
+      const uint32_t idesc2 = make_idesc(2 * tc.nt, 128 * CG);  // bcat: both weight planes as one operand
+      // k-group stride: nt (bcat: 2 nt; pair: this CTA's nt / 2, pair + bcat: nt, see below) rows * 16 bytes >> 4
+      const uint32_t b_lbo16 = CG == 2 ? (uint32_t)tc.nt >> (BCAT ? 0 : 1) : (uint32_t)tc.nt << BCAT;
       const uint32_t b_plane16 = (uint32_t)((tc.nt / CG) * p.SBC * 2) >> 4;
       const uint32_t b_step16 = 2 * b_lbo16;
       uint32_t accum = 0;
@@ -584,7 +585,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // weight stages left in this tile / in the current ring slot, position inside the slot
       int rem = taps * (nsb_full * (tc.cb1 - tc.cb0) - (tc.cb1 == ncb ? nsb_full - p.nsb_last : 0));
       int glen = 0, gi = 0;
-      const uint32_t stage16 = (uint32_t)((tc.nt / CG) * p.SBC * 2 * p.b_planes) >> 4;  // this tile's bytes per stage / 16
+      const uint32_t stage16 = CG == 2 && BCAT ? (uint32_t)(tc.nt * p.SBC * 3) >> 4
+                                               : (uint32_t)((tc.nt / CG) * p.SBC * 2 * p.b_planes) >> 4;  // this tile's bytes per stage / 16
       uint32_t b_grp = 0;
       for (int cb = tc.cb0; cb < tc.cb1; ++cb) {
         if (CG == 2) mbar_wait_cluster(A_FULL + abuf * 8, aph); else mbar_wait(A_FULL + abuf * 8, aph);
@@ -607,7 +609,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             b_grp += stage16;
             // uniform loops; only the MMA itself is predicated on the leader lane, so that ptxas keeps the
             // descriptors in uniform registers instead of broadcasting them per instruction
-            if (CG == 2) {
+            if (CG == 2 && BCAT) {
+              // Pair MMAs with the weight planes side by side: A_hi x [B_hi | B_lo] is ONE MMA of 2 nt columns -- the leader's
+              // shared memory holds B_hi (nt rows per k-group), the peer's B_lo at the same offsets -- then A_lo x B_hi with
+              // B_hi split in halves between the CTAs, stored a second time behind the first region (k-group stride nt / 2).
+              // 2 MMA instructions per K step and pixel tile instead of 3 (narrow N: 41 cycles per N = 48 pair MMA against a
+              // pipe time of 24, tools/umma_bench2.cu) for 1.5x the weight bytes.
+              const uint32_t y_off16 = (uint32_t)(tc.nt * p.SBC * 2) >> 4;  // region X: SBC / 8 k-groups x nt rows x 16 bytes
+              uint32_t by = ((b_lo + y_off16) & 0xFFFFu) | ((uint32_t)(tc.nt >> 1) << 16);
+#pragma unroll 1
+              for (int j = 0; j < k16_per_stage; ++j) {
+                if (leader) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m) {
+                    const uint32_t d = m == 0 ? d_tmem : d_tmem1, am = a_lo + 8 * m;
+                    umma2_w(d, am, a_hi32, b_lo, b_hi32, idesc2, accum);
+                    umma2_w(d, am + a_plane16, a_hi32, by, b_hi32, idesc, 1);
+                  }
+                }
+                accum = 1;
+                a_lo += a_step16;
+                b_lo += b_step16;
+                by += (uint32_t)tc.nt;  // two k-groups of nt / 2 rows
+              }
+            } else if (CG == 2) {
               // pair MMAs; where one A tile meets both weight planes it is read from shared memory once (A collector)
 #pragma unroll 1
               for (int j = 0; j < k16_per_stage; ++j) {
@@ -1046,7 +1071,18 @@ __device__ __forceinline__ void tc_pack_body(const TcPackParams& q, long long e_
     const size_t stage_bytes = (size_t)nt * q.SBC * 2 * q.b_planes;
     const size_t ntile_stride = (size_t)stages_per_ntile * q.NT * q.SBC * 2 * q.b_planes;
     uint8_t* st = q.out + (size_t)tn * ntile_stride + (size_t)s * stage_bytes;
-    if (q.cg2) {  // [half of the columns][stage][plane][k-group][n in half][8]: each CTA of the pair streams ONE contiguous region
+    if (q.cg2 && q.bcat) {
+      // pair plan with side-by-side planes, per CTA and stage: region X [k-group][nt][8] (leader: hi plane, peer: lo plane),
+      // then region Y [k-group][nt / 2][8] = this CTA's half of the hi plane's columns
+      const int nh = nt >> 1, h = nn >= nh ? 1 : 0, nl = nn - h * nh;
+      const size_t part = (size_t)nt * q.SBC * 3, xbytes = (size_t)nt * q.SBC * 2;
+      const size_t nts = (size_t)stages_per_ntile * q.NT * q.SBC * 6;
+      uint8_t* r0 = q.out + (size_t)tn * nts + (size_t)s * part;
+      uint8_t* r1 = r0 + (size_t)stages_per_ntile * part;
+      *reinterpret_cast<uint4*>(r0 + ((size_t)g * nt + nn) * 16) = hi;
+      *reinterpret_cast<uint4*>(r1 + ((size_t)g * nt + nn) * 16) = lo;
+      *reinterpret_cast<uint4*>((h ? r1 : r0) + xbytes + ((size_t)g * nh + nl) * 16) = hi;
+    } else if (q.cg2) {  // [half of the columns][stage][plane][k-group][n in half][8]: each CTA of the pair streams ONE contiguous region
       const int nh = nt >> 1, h = nn >= nh ? 1 : 0, nl = nn - h * nh;
       uint8_t* hb = q.out + (size_t)tn * ntile_stride + ((size_t)h * stages_per_ntile + s) * (stage_bytes >> 1);
       const size_t o = ((size_t)g * nh + nl) * 16;
@@ -1150,10 +1186,10 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
       if (atoi(e) == 0) pl->cg2 = 0;
     }
   }
-  pl->bcat = (!pl->cg2 && a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256 && d->ksize * d->ksize * C >= 512) ? 1 : 0;
+  pl->bcat = (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256 && d->ksize * d->ksize * C >= 512) ? 1 : 0;
   if (const char* e = getenv("NQ_TC_BCAT")) {  // tuning override
     if (atoi(e) == 0) pl->bcat = 0;
-    else if (!pl->cg2 && a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256) pl->bcat = 1;
+    else if (a_planes == 2 && b_planes == 2 && 2 * pl->NT * pl->mt <= 256) pl->bcat = 1;
   }
   const int tile_w = TILE_W * pl->mt;
   pl->PW = tile_w + d->ksize - 1;
@@ -1169,7 +1205,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   int best = 0, best_kc = 0;
   for (int sbc = (C < 128 ? C : 128) / 16 * 16; sbc >= 16 && !best; sbc -= 16) {
     if (C % sbc) continue;
-    const int stage = pl->NT * sbc * 2 * b_planes >> pl->cg2;  // pair: each CTA stages half of the columns
+    const int stage = pl->cg2 && pl->bcat ? pl->NT * sbc * 3 : pl->NT * sbc * 2 * b_planes >> pl->cg2;  // pair: each CTA stages half of the columns (+ half a plane again when side by side)
     if (stage > 32 * 1024 && sbc > 16) continue;
     // activation unit: ~64 channels (a multiple of the stage), fewer when the (16x16-pixel) halo is large
     for (int kc = sbc >= 64 ? sbc : sbc * (64 / sbc); kc >= sbc; kc -= sbc) {
@@ -1188,7 +1224,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   pl->KC = best_kc;
   pl->a_plane_bytes = pl->CGS * (pl->KC / 8);
   pl->a_buf_bytes = pl->a_plane_bytes * a_planes;
-  pl->b_stage_bytes = pl->NT * sbc * 2 * b_planes >> pl->cg2;
+  pl->b_stage_bytes = pl->cg2 && pl->bcat ? pl->NT * sbc * 3 : pl->NT * sbc * 2 * b_planes >> pl->cg2;
   // Ring depths: as many activation buffers (<= 8) as fit next to ~48 KB of weight stages, and as many accumulator
   // slots as the 512 TMEM columns hold, so that several short-K tiles can be in flight.
   const int total = 227 * 1024 - TC_HDR_BYTES - EPI_STAGE_BYTES;
@@ -1260,7 +1296,7 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   // bytes of the packed weight buffer: full-width stages for all but the last N tile
   const long long stages = (long long)(C / sbc) * taps;
   const int last_nt = N - (pl->tiles_n - 1) * pl->NT;
-  pl->wpk_bytes = stages * sbc * 2 * b_planes * ((long long)(pl->tiles_n - 1) * pl->NT + last_nt);
+  pl->wpk_bytes = stages * sbc * (pl->cg2 && pl->bcat ? 6 : 2 * b_planes) * ((long long)(pl->tiles_n - 1) * pl->NT + last_nt);
   // weight-stream sharing: 2 CTAs per cluster pack all 148 SMs (74 TPCs); every stage splits evenly
   // (nt * SBC * 2 * planes is a multiple of 512 bytes)
   pl->cluster = 2;
@@ -1380,7 +1416,7 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
     return NQ_ERR_BAD_ARG;
   if (p.mt < 1 || p.mt > 2 || (p.mt == 2 && (pl->NT > 128 || p.epi == 2))) return NQ_ERR_BAD_ARG;
   if (p.bcat && (p.epi == 2 || pl->a_planes != 2 || pl->b_planes != 2 || 2 * pl->NT * pl->mt > 256)) return NQ_ERR_BAD_ARG;
-  if (pl->cg2 && (p.bcat || pl->resident || p.epi == 2 || (pl->NT & 15))) return NQ_ERR_BAD_ARG;
+  if (pl->cg2 && (pl->resident || p.epi == 2 || (pl->NT & 15))) return NQ_ERR_BAD_ARG;
   p.a_plane_bytes = pl->a_plane_bytes; p.a_buf_bytes = pl->a_buf_bytes; p.b_stage_bytes = pl->b_stage_bytes;
   p.n_bstages = pl->n_bstages;
   p.gst = pl->gst < 1 ? 1 : pl->gst;
@@ -1395,7 +1431,8 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   p.fd_tiles_x = make_fastdiv(pl->tiles_x); p.fd_tiles_y = make_fastdiv(pl->tiles_y);
   p.fd_rh = make_fastdiv(p.rh); p.fd_rw = make_fastdiv(p.rw); p.fd_PW = make_fastdiv(pl->PW);
   p.fd_npix = make_fastdiv(pl->PW * pl->PH); p.fd_cg = make_fastdiv(p.cg);
-  void (*kern)(const TcParams) = pl->cg2   ? (p.mt == 2 ? conv_tc_kernel<2, 0, 0, 2> : conv_tc_kernel<1, 0, 0, 2>)
+  void (*kern)(const TcParams) = pl->cg2   ? (p.bcat ? (p.mt == 2 ? conv_tc_kernel<2, 1, 0, 2> : conv_tc_kernel<1, 1, 0, 2>)
+                                                      : (p.mt == 2 ? conv_tc_kernel<2, 0, 0, 2> : conv_tc_kernel<1, 0, 0, 2>))
                                  : p.mt == 2 ? (p.bcat ? conv_tc_kernel<2, 1, 0, 1> : conv_tc_kernel<2, 0, 0, 1>)
                                  : p.bcat    ? conv_tc_kernel<1, 1, 0, 1>
                                              : (p.resident ? conv_tc_kernel<1, 0, 1, 1> : conv_tc_kernel<1, 0, 0, 1>);

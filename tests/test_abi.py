@@ -97,8 +97,9 @@ def test_tc_plans_fit_for_every_workload():
                 if pl.gst > 1:  # several weight stages per ring slot: one bulk copy <= 32 KB, >= 3 slots in flight
                     assert pl.gst * pl.b_stage_bytes <= 32 * 1024 and pl.n_bstages >= 3 and not pl.resident
                 if pl.cg2:  # CTA pairs: each CTA stages half of the columns; no side-by-side planes, no resident weights
-                    assert not pl.bcat and not pl.resident and pl.NT % 16 == 0
-                    assert pl.b_stage_bytes == pl.NT * pl.SBC * 2 * bp // 2
+                    assert not pl.resident and pl.NT % 16 == 0
+                    # side-by-side planes in a pair plan: a full plane + half of the hi plane again per CTA
+                    assert pl.b_stage_bytes == (pl.NT * pl.SBC * 3 if pl.bcat else pl.NT * pl.SBC * 2 * bp // 2)
                     assert pl.tiles_x * pl.tiles_y * 2 >= 148  # a pair's worth of pixel tiles for every SM
                 else:
                     assert pl.b_stage_bytes == pl.NT * pl.SBC * 2 * bp

@@ -181,7 +181,8 @@ def test_full_size_calibration_psnr_parity(monkeypatch):
 
 @pytest.mark.parametrize("workload", ["hnerv-bunny-3m", "nerv-bunny-3m"])
 def test_cta_pair_plans_match_the_multicast_plans(monkeypatch, workload):
-    """Round 2: stages 4-5 run as CTA pairs (tcgen05.mma.cta_group::2, A collector, several weight stages per ring slot).
+    """Round 2: stages 4-5 run as CTA pairs (tcgen05.mma.cta_group::2; A collector in the forward, side-by-side planes split
+    between the two CTAs in the data gradient; several weight stages per ring slot).
     NQ_TC_CG2=0 / NQ_TC_GST=1 select round 1's multicast plans (side-by-side planes, one stage per slot): same products,
     same fp32 accumulators, another summation order -- frames, loss and every gradient must agree to fp32 rounding."""
     import ctypes as C
@@ -195,7 +196,7 @@ def test_cta_pair_plans_match_the_multicast_plans(monkeypatch, workload):
     d5 = stage_descs(geoms, 2, h0, w0, True)[5]
     pl = L.TcPlan()
     assert L.lib.nq_tc_plan_conv(C.byref(d5), 1, 2, 2, C.byref(pl)) == 0
-    assert pl.cg2 == 1 and pl.gst > 1 and pl.bcat == 0, "stage 5 is expected to take a CTA-pair plan"
+    assert pl.cg2 == 1 and pl.gst > 1, "stage 5 is expected to take a CTA-pair plan"
     pair = _run(monkeypatch, "tc", workload, 2, False)
     monkeypatch.setenv("NQ_TC_CG2", "0")
     monkeypatch.setenv("NQ_TC_GST", "1")
@@ -203,7 +204,7 @@ def test_cta_pair_plans_match_the_multicast_plans(monkeypatch, workload):
     assert pl.cg2 == 0 and pl.gst == 1
     mc = _run(monkeypatch, "tc", workload, 2, False)
     assert (pair[0] - mc[0]).abs().max() < 2e-6 and (pair[4] - mc[4]).abs().max() < 2e-6
-    assert pair[1] == pytest.approx(mc[1], rel=1e-6)
+    assert pair[1] == pytest.approx(mc[1], rel=1e-5)  # the loss is an fp32 atomicAdd of ~1e5 partial sums: its order varies run to run
     for i, ((gw_p, gb_p), (gw_m, gb_m)) in enumerate(zip(pair[3], mc[3])):
         for name, a, b in (("dW", gw_p, gw_m), ("db", gb_p, gb_m)):
             tol = 2e-5 * float(b.abs().max()) + 1e-12
