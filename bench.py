@@ -27,7 +27,7 @@ METRIC = "adaround_calib_iters_per_s"
 UNIT = "it/s (batch-2 iterations; frame-sharded DP processes N of them per step)"
 DEFAULT_BITS = [6, 5, 4, 5, 5, 6, 6]
 HYPER = dict(weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003, iters=21000)
-TRAFFIC_FILE = "r02t_traffic.json"   # dram bytes per launch of the dominant kernels, from the committed `ncu --set full` capture
+TRAFFIC_FILE = "r02x_traffic.json"   # dram bytes per launch of the dominant kernels, from the committed `ncu --set full` capture
 MMA_PASSES = {"conv_fwd": 3, "conv_dgrad": 3, "conv_wgrad": 3, "head_fwd_loss": 3}  # bf16 MMAs per fp32-equivalent product
 
 
