@@ -1179,9 +1179,9 @@ static int fill_plan(const nq_conv_desc* d, int dir, int a_planes, int b_planes,
   {
     const long long w_tile_bytes = (long long)d->ksize * d->ksize * C * pl->NT * 2 * b_planes;
     const long long tiles_m = (long long)((d->w + TILE_W * pl->mt - 1) / (TILE_W * pl->mt)) * ((d->h + TILE_H - 1) / TILE_H) * d->n;
-    // ... and every SM has a pair's worth of pixel tiles: with fewer tiles (the deep, split-K stages) the relay hop between
-    // the two CTAs is exposed and the multicast form measured faster (HNeRV-3M stage 3 data gradient: 147k against 176k cycles)
-    pl->cg2 = (w_tile_bytes > 96 * 1024 && tiles_m >= (long long)sm_count()) ? 1 : 0;
+    // ... and there are enough pixel tiles for the relay hop between the two CTAs to stay hidden (measured, HNeRV-3M stage 3 with
+    // 50 tiles: forward 110 k -> 102 k cycles, split-K data gradient 162 k -> 135 k; stage 2 with 6 tiles: no difference)
+    pl->cg2 = (w_tile_bytes > 96 * 1024 && tiles_m >= 32) ? 1 : 0;
     if (const char* e = getenv("NQ_TC_CG2")) {  // tuning override
       if (atoi(e) == 0) pl->cg2 = 0;
     }

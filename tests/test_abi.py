@@ -100,7 +100,7 @@ def test_tc_plans_fit_for_every_workload():
                     assert not pl.resident and pl.NT % 16 == 0
                     # side-by-side planes in a pair plan: a full plane + half of the hi plane again per CTA
                     assert pl.b_stage_bytes == (pl.NT * pl.SBC * 3 if pl.bcat else pl.NT * pl.SBC * 2 * bp // 2)
-                    assert pl.tiles_x * pl.tiles_y * 2 >= 148  # a pair's worth of pixel tiles for every SM
+                    assert pl.tiles_x * pl.tiles_y * 2 >= 32  # enough pixel tiles to hide the relay hop of a pair
                 else:
                     assert pl.b_stage_bytes == pl.NT * pl.SBC * 2 * bp
                 if pl.bcat:
