@@ -209,3 +209,49 @@ def test_cta_pair_plans_match_the_multicast_plans(monkeypatch, workload):
         for name, a, b in (("dW", gw_p, gw_m), ("db", gb_p, gb_m)):
             tol = 2e-5 * float(b.abs().max()) + 1e-12
             assert float((a - b).abs().max()) <= tol, (workload, i, name, float((a - b).abs().max()), tol)
+
+
+def _run_custom(monkeypatch, conv, geoms, n, h0, w0, bits):
+    monkeypatch.setenv("NQ_CONV", conv)
+    import neuroquant_b200 as nq
+    gen = torch.Generator().manual_seed(31)
+    stages = []
+    for g, nb in zip(geoms, bits):
+        w = torch.randn(g.cout, g.cin, g.k, g.k, generator=gen) * (1.5 / (g.cin * g.k * g.k) ** 0.5)
+        b = torch.randn(g.cout, generator=gen) * 0.05
+        stages.append(nq.QuantStage(g, w.cuda(), b.cuda(), nb, False))
+    eng = nq.DecoderEngine(stages)
+    eng.init_scales()
+    eng.start_adaround()
+    embed = torch.randn(n, geoms[0].cin, h0, w0, generator=gen).cuda()
+    H, W = h0, w0
+    for g in geoms:
+        H, W = H * g.rh, W * g.rw
+    frames = torch.rand(n, 3, H, W, generator=gen).cuda()
+    img = eng.forward(embed, train=True, target=frames, p_norm=2.0).clone()
+    loss = float(eng.last_loss())
+    eng.backward()
+    views = [(gw.clone(), gb.clone()) for gw, gb in eng._grad_buffers()[1]]
+    plans = eng._last_plan
+    info = [(int(plans.tc_fwd[(1, 2)].cg2), int(plans.tc_dgrad[1].cg2), int(plans.tc_dgrad[1].bcat),
+             int(plans.tc_fwd[(1, 2)].tiles_x * plans.tc_fwd[(1, 2)].tiles_y * n))] if conv == "tc" else None
+    del eng
+    torch.cuda.empty_cache()
+    return img, loss, views, info
+
+
+def test_cta_pair_plans_with_an_odd_number_of_pixel_tiles(monkeypatch):
+    """A pair plan whose pixel tiles do not pair up (45 tiles: the last cluster's second CTA runs a padding slot that feeds
+    zeros into the pair's MMAs and stores nothing) and whose image edge cuts tiles (w = 24 = 3 x 8, h = 48 = 3 x 16 are exact;
+    the up-shuffled head sees 96 x 48): tensor-core engine against the exact-fp32 engine."""
+    from neuroquant_b200.engine import StageGeom
+    geoms = [StageGeom(16, 64, 1, 1, 1, "none"), StageGeom(64, 128, 3, 2, 2, "gelu"), StageGeom(32, 3, 3, 1, 1, "tanh")]
+    tc = _run_custom(monkeypatch, "tc", geoms, 5, 48, 24, [6, 5, 6])
+    assert tc[3][0] == (1, 1, 1, 45), tc[3]  # forward and data gradient of the block are pair plans over 45 tiles
+    ff = _run_custom(monkeypatch, "simt", geoms, 5, 48, 24, [6, 5, 6])
+    assert (tc[0] - ff[0]).abs().max() < 1e-4  # pre-activations of O(1) here: 2^-17 relative per product (north-star bar: 1e-3)
+    assert tc[1] == pytest.approx(ff[1], rel=1e-5)
+    for i, ((gw_t, gb_t), (gw_f, gb_f)) in enumerate(zip(tc[2], ff[2])):
+        for name, a, b in (("dW", gw_t, gw_f), ("db", gb_t, gb_f)):
+            tol = 2e-4 * float(b.abs().max()) + 1e-12
+            assert float((a - b).abs().max()) <= tol, (i, name, float((a - b).abs().max()), tol)
