@@ -275,7 +275,8 @@ typedef struct nq_tc_plan {
   int32_t resident;            /* 1: all weight stages of a tile fit the ring; loaded once per CTA */
   int32_t ksplit;              /* data gradient: CTAs sharing the K range of one tile (1 = off; the caller may set 1) */
   int32_t cg2;                 /* 1: CTA-pair MMAs (tcgen05 cta_group::2, M = 256): two pixel tiles per MMA, each CTA stages half of
-                                  every weight stage; needs cluster = 2 (forced at launch) and excludes bcat / resident */
+                                  every weight stage; needs cluster = 2 (forced at launch), excludes resident; with bcat the leader
+                                  stages the hi plane, the peer the lo plane, both also their half of the hi plane's columns */
   int32_t gst;                 /* weight stages per ring slot (one bulk copy and one barrier round trip for all of them); the ring has
                                   n_bstages slots of gst * b_stage_bytes bytes */
   int32_t reserved;
