@@ -96,6 +96,7 @@ class GraphedStep:
             l0 = self.eng.launches
             self._body()  # eager once: allocates every lazily-created buffer, and is this iteration's real work
             self.launches_per_replay = self.eng.launches - l0
+            self._plan_of_body, self._mean_of_body = self.eng._last_plan, self.eng._mean_pixels
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             saved = [t.clone() for t in self.opt.params + self.opt.m + self.opt.v]  # capture must not advance the state
@@ -109,6 +110,10 @@ class GraphedStep:
         else:
             self.graph.replay()
             self.eng.launches += self.launches_per_replay
+            # what the Python side of forward() would have noted (last_loss() reads it): with a ragged last batch the loop
+            # alternates between the graphs of two batch sizes
+            self.eng._last_plan, self.eng._mean_pixels = self._plan_of_body, self._mean_of_body
+            self.eng._packed_for = (self._plan_of_body.n, self._plan_of_body.h0, self._plan_of_body.w0)
         self.eng.invalidate()
 
 

@@ -276,6 +276,8 @@ class DecoderEngine:
         self._packed = None  # per-stage (wk, wt, bias_packed, deq_w scratch, deq_b scratch)
         self._weights_valid = False
         self._wt_valid = False
+        self._packed_for = None  # (n, h0, w0) of the plan whose operand layouts the packed weights currently have
+        self._retired = []  # outgrown packed-operand buffers: captured graphs may still pack into / read from them
         self.reg_sum = torch.zeros(1, device=self.device)
         self._grad = None
         self.sm = L.lib.nq_sm_count()
@@ -385,12 +387,38 @@ class DecoderEngine:
                 self._tcw.append(None)
         self._head_dgrad = self._tcw[last][1] if (self.use_tc and last > 0) else None
 
+    def _fit_packed(self, p: _Plan):
+        """The packed-operand buffers were sized by the first plan of this engine.  The layout the C library chooses
+        depends on the number of pixel tiles, i.e. on the batch size: CTA pairs with the two weight planes side by side
+        take 1.5x the bytes of the plain layout (nq_tc_plan.wpk_bytes), so a later plan of a LARGER batch can need more
+        than a smaller first one reserved (decode one frame, then calibrate on two).  Grow what is too small; the old
+        buffer stays alive because a captured graph of another plan packs into it and reads from it."""
+        last = len(self.stages) - 1
+        for i, tcw in enumerate(self._tcw):
+            if tcw is None:
+                continue
+            wpk_f, wpk_d, scale_p = tcw
+            need_f = max(p.tc_fwd[(i, 1)].wpk_bytes, p.tc_fwd[(i, 2)].wpk_bytes)
+            need_d = p.tc_dgrad[i].wpk_bytes if (p.train and i > 0) else 0
+            if need_f <= wpk_f.numel() and need_d <= wpk_d.numel():
+                continue
+            self._retired.append(tcw)
+            if need_f > wpk_f.numel():
+                wpk_f = torch.zeros(need_f, dtype=torch.uint8, device=self.device)
+            if need_d > wpk_d.numel():
+                wpk_d = torch.zeros(need_d, dtype=torch.uint8, device=self.device)
+            self._tcw[i] = (wpk_f, wpk_d, scale_p)
+            if i == last and last > 0:
+                self._head_dgrad = wpk_d
+
     # ------------------------------------------------------------------ weights
     def prepare_weights(self, p: _Plan, need_wt: bool, reg_b: Optional[float] = None):
         """Fake-quantise every stage's weight and bias and pack them for the convolutions
         (quant_layer.py:68-78).  reg_b: also accumulate sum(1 - |2h-1|^b) over the WEIGHT alphas into
         self.reg_sum (calib_model.py:39-47; bias alphas are excluded there)."""
         self._alloc_packed(p)
+        if self.use_tc:
+            self._fit_packed(p)
         st = L.stream()
         if reg_b is not None:
             self.reg_sum.zero_()
@@ -467,6 +495,7 @@ class DecoderEngine:
             self.launches += (len(packs) + L.MULTI_MAX - 1) // L.MULTI_MAX
         self._weights_valid = True
         self._wt_valid = need_wt
+        self._packed_for = (p.n, p.h0, p.w0)
 
     def _stage_off(self, i: int) -> bool:
         """Stage i runs on its full-precision weights: the whole decoder (mode 'off') or this stage alone ('off' in
@@ -512,7 +541,9 @@ class DecoderEngine:
         p = self.plan(n, h0, w0, train)
         self._last_plan = p
         st = L.stream()
-        if not (reuse_weights and self._weights_valid and (self._wt_valid or not train)):
+        # packed operands are reusable only by a plan of the same geometry: the layout (stage size, CTA pairs, planes side
+        # by side) is chosen per plan and depends on the number of pixel tiles, hence on the batch size
+        if not (reuse_weights and self._weights_valid and (self._wt_valid or not train) and self._packed_for == (n, h0, w0)):
             self.prepare_weights(p, need_wt=train, reg_b=reg_b)
         embed = embed.detach().contiguous().float()
         if self.use_tc:

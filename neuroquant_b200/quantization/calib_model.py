@@ -66,10 +66,10 @@ LAST_RUN = {}
 
 class _Staged:
     """One mini-batch whose host -> device copy is in flight (HostBatchPipe slot)."""
-    __slots__ = ("idx", "n_global", "resident")
+    __slots__ = ("idx", "n_global", "resident", "pipe")
 
-    def __init__(self, idx, n_global, resident):
-        self.idx, self.n_global, self.resident = idx, n_global, resident
+    def __init__(self, idx, n_global, resident, pipe):
+        self.idx, self.n_global, self.resident, self.pipe = idx, n_global, resident, pipe
 
 
 class _FrameSource:
@@ -96,7 +96,8 @@ class _FrameSource:
         self.residency = residency
         self.frames = None
         self.have = None
-        self.pipe = None
+        self.pipe = None  # the pipe staged into last
+        self.pipes = {}
         self.h2d_bytes = 0  # bytes this rank copied host -> device (bench.py reports it per step)
 
     # -- host side ---------------------------------------------------------------------------------------------------
@@ -124,15 +125,16 @@ class _FrameSource:
         tensors = [img_m]
         if self.cali is None:  # embeddings on the host as well: this batch's rows travel with the frames
             tensors.append(self.cali_host[mine].contiguous())
-        specs = [(tuple(t.shape), t.dtype) for t in tensors]
-        if self.pipe is None or self.pipe.specs != specs:
-            if self.pipe is not None:  # ragged last batch (drop_last=False): drain, then a pipe of the new shape
-                torch.cuda.current_stream().synchronize()
-                self.pipe.stream.synchronize()
-            self.pipe = HostBatchPipe(specs, device=self.dev, depth=3)
-        self.pipe.put(*tensors)
+        # one pipe per batch shape: a loader with drop_last=False ends its epoch on a short batch, which is staged while
+        # the batch before it is still pending in the pipe of the full shape (the staged batch remembers its pipe)
+        specs = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        pipe = self.pipes.get(specs)
+        if pipe is None:
+            pipe = self.pipes[specs] = HostBatchPipe(specs, device=self.dev, depth=3)
+        self.pipe = pipe
+        pipe.put(*tensors)
         self.h2d_bytes += sum(t.numel() * t.element_size() for t in tensors if not t.is_cuda)
-        return _Staged(idx, int(idx.numel()), resident)
+        return _Staged(idx, int(idx.numel()), resident, pipe)
 
     def batches(self):
         if self.have is not None and bool(self.have.all()):
@@ -160,7 +162,7 @@ class _FrameSource:
     # -- device side -------------------------------------------------------------------------------------------------
     def fetch(self, item):
         if isinstance(item, _Staged):
-            got = self.pipe.get()
+            got = item.pipe.get()
             img = got[0]
             if item.resident:
                 idx_d = item.idx.to(self.dev)

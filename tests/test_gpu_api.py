@@ -299,3 +299,46 @@ def test_omega_table_reproduces_reference_scores_of_arbitrary_configurations(tag
     assert avg_bits <= 4.5 and score == pytest.approx(table.score(bits), rel=1e-12)
     none, sc, _, _ = table.search(1.9)                     # nothing fits below 2 bits on average
     assert none is None and sc == float("inf")
+
+
+def test_model_reconstruction_with_a_ragged_last_batch():
+    """A loader with drop_last=False ends every epoch on a short batch (here 2 + 2 + 1 frames).  lp_loss is a mean over the
+    frames actually in the batch (quantizer.py:66-73), so loss and gradients of that iteration are normalised by 1, not by
+    the nominal batch size of 2; the loop alternates between the captured graphs of the two batch sizes.  Checked against
+    the CPU oracle in the same batch order: per-iteration losses through `on_iteration`, then frames and PSNR."""
+    from neuroquant_b200.quantization import QuantModel, model_reconstruction
+    from neuroquant_b200.utils import psnr_fn_single
+    tag = "tiny_hnerv"
+    g, arch, cfg, model = build_model(tag)
+    cali, frames = t(g["cali"]), t(g["frames"])
+    batches = [[0, 5], [3, 6], [1]]
+    iters = 60  # 1 epoch of step sizes (3 iterations) + 19 epochs of AdaRound (57)
+    # oracle
+    stages = O.stages_from_state_dict({k[3:]: t(g[k]) for k in g.files if k.startswith("sd/")}, cfg, arch)
+    qd = O.QuantDecoder(stages, g["bits"].tolist(), bool(g["hadamard"]), channel_wise=cw(g))
+    qd.init_scales()
+    want_log = []
+    O.model_reconstruction(qd, cali, frames, batches, iters, weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003, log=want_log)
+    with torch.no_grad():
+        want_out = qd.forward(cali[:2])
+    # product
+    qnn = QuantModel(model, hadamard=bool(g["hadamard"]), weight_quant_params={"n_bits": 8, "channel_wise": cw(g),
+                                                                                "scale_method": "max"}).cuda()
+    qnn.set_bitwidth(g["bits"].tolist())
+    qnn.set_quant_state(True)
+    qnn(cali[:2].cuda())
+    loader = ListLoader([{"img": frames[idx], "idx": torch.as_tensor(idx), "norm_idx": torch.as_tensor(idx).float()}
+                         for idx in batches])
+    got = []
+    model_reconstruction(qnn, cali_data=cali.cuda(), gt=loader, arch=arch, batch_size=2, iters=iters, weight=0.01,
+                         opt_mode="mse", hadamard=bool(g["hadamard"]), b_range=(20, 2), warmup=0.2, p=2.0, lr=0.003,
+                         on_iteration=lambda phase, count, loss: got.append((phase, count, loss.clone())))
+    assert [(ph, c) for ph, c, _ in got] == [(r[0], r[1]) for r in want_log]
+    got_rec = np.array([float(l) for _, _, l in got])
+    want_rec = np.array([r[2] for r in want_log])
+    # three epochs, the short batch three times; a loss normalised by the nominal batch size would be off by a factor of 2
+    assert np.allclose(got_rec[:9], want_rec[:9], rtol=1e-3, atol=1e-7)
+    assert np.allclose(got_rec, want_rec, rtol=2e-2, atol=1e-6)  # later iterations: the trajectory is chaotic (DESIGN 2)
+    out, _, _ = qnn(cali[:2].cuda())
+    assert (out.cpu() - want_out).abs().max() < 5e-3
+    assert (psnr_fn_single(out, frames[:2].cuda()).cpu() - O.psnr(want_out, frames[:2])).abs().max() < 0.01

@@ -255,3 +255,64 @@ def test_cta_pair_plans_with_an_odd_number_of_pixel_tiles(monkeypatch):
         for name, a, b in (("dW", gw_t, gw_f), ("db", gb_t, gb_f)):
             tol = 2e-4 * float(b.abs().max()) + 1e-12
             assert float((a - b).abs().max()) <= tol, (i, name, float((a - b).abs().max()), tol)
+
+
+def test_packed_operands_follow_the_batch_size(monkeypatch):
+    """The packed weight layout is chosen per plan and depends on the number of pixel tiles, i.e. on the batch size: stage 3
+    of HNeRV-3M has 25 tiles per frame, so one frame runs the single-CTA plan and two frames the CTA-pair plan, whose data
+    gradient operand is 1.5x as large.  An engine that decodes ONE frame first (its operand buffers are sized by that plan),
+    then takes a calibration step on TWO, then decodes two and one with `reuse_weights` must give at every point what an
+    engine that only ever saw that batch size gives."""
+    monkeypatch.setenv("NQ_CONV", "tc")
+    import neuroquant_b200 as nq
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape, random_decoder
+    arch, cfg = WORKLOADS["hnerv-bunny-3m"]
+    geoms, params = random_decoder(cfg, arch, 903)
+    bits = [6, 5, 4, 5, 5, 6, 6]
+
+    def make():
+        eng = nq.DecoderEngine([nq.QuantStage(g, w.cuda(), b.cuda(), nb, False) for g, (w, b), nb in zip(geoms, params, bits)])
+        eng.init_scales()
+        eng.start_adaround()
+        return eng
+
+    c, h0, w0 = embed_shape(cfg, arch)
+    gen = torch.Generator().manual_seed(19)
+    embed = torch.randn(2, c, h0, w0, generator=gen).cuda()
+    frames = torch.rand(2, 3, cfg["crop_h"], cfg["crop_w"], generator=gen).cuda()
+
+    a = make()
+    one_first = a.forward(embed[:1]).clone()
+    p1, p2 = a.plan(1, h0, w0, False), a.plan(2, h0, w0, True)
+    assert (p1.tc_fwd[(3, 2)].cg2, p2.tc_fwd[(3, 2)].cg2) == (0, 1)  # the premise: the layout changes with the batch
+    small = a._tcw[3][1].numel()
+    assert p2.tc_dgrad[3].wpk_bytes > small  # ... and the two-frame data gradient needs more than one frame reserved
+    img = a.forward(embed, train=True, target=frames, p_norm=2.0).clone()
+    assert a._tcw[3][1].numel() >= p2.tc_dgrad[3].wpk_bytes
+    loss = float(a.last_loss())
+    a.backward()
+    grads = [(gw.clone(), gb.clone()) for gw, gb in a._grad_buffers()[1]]
+    two = a.forward(embed, reuse_weights=True).clone()       # same geometry as the step: packed weights are reused
+    one = a.forward(embed[:1], reuse_weights=True).clone()   # other geometry: they must be packed again
+    del a
+    torch.cuda.empty_cache()
+
+    b = make()
+    ref_img = b.forward(embed, train=True, target=frames, p_norm=2.0).clone()
+    ref_loss = float(b.last_loss())
+    b.backward()
+    ref_grads = [(gw.clone(), gb.clone()) for gw, gb in b._grad_buffers()[1]]
+    del b
+    torch.cuda.empty_cache()
+    ref_one = make().forward(embed[:1]).clone()
+
+    # same kernels on the same plans: expected bit-identical, asserted to 1e-6 (a wrong layout gives garbage)
+    assert (one_first - ref_one).abs().max() < 1e-6 and (one - ref_one).abs().max() < 1e-6
+    assert (img - ref_img).abs().max() < 1e-6
+    assert (two - ref_img).abs().max() < 2e-5  # the training epilogue evaluates GELU next to GELU', decode evaluates GELU alone
+    assert (two[:1] - one).abs().max() < 2e-5  # the same frame through the pair plan and through the single-CTA plan
+    assert loss == pytest.approx(ref_loss, rel=1e-5)
+    for i, ((gw, gb), (rw, rb)) in enumerate(zip(grads, ref_grads)):
+        for name, x, y in (("dW", gw, rw), ("db", gb, rb)):
+            tol = 1e-5 * float(y.abs().max()) + 1e-12  # same kernels, same plans: only the order of fp32 atomics differs
+            assert float((x - y).abs().max()) <= tol, (i, name, float((x - y).abs().max()), tol)
