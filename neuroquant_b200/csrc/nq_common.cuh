@@ -1,6 +1,7 @@
 // Shared device/host helpers for libnq_sm100.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <math.h>
 #include "../../include/neuroquant_b200.h"
@@ -25,6 +26,18 @@ inline int cuda_fail(cudaError_t e) {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached per device
+
+// Programmatic dependent launch.  The persistent tensor-core kernels spend their first microseconds on chip only (barrier
+// initialisation, TMEM allocation, constant operand fill); launched with the programmatic-serialisation attribute their
+// CTAs take over an SM as soon as a CTA of the kernel before them exits and do that part under its tail.  pdl_wait()
+// returns when the preceding kernel has completed and its writes are visible -- nothing before it may touch global
+// memory; without the attribute it returns at once.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {  // NQ_PDL=0: plain stream order
+  static const bool on = !(getenv("NQ_PDL") && atoi(getenv("NQ_PDL")) == 0);
+  return on;
+}
 
 constexpr float kZeta = 1.1f, kGamma = -0.1f;  // quantizer.py:274
 

@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
+  pdl_wait();     // everything above ran under the tail of the kernel before this one (nq_common.cuh)
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
   long long dbg_c0 = 0, dbg_t0 = 0;
   if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1463,13 +1465,15 @@ static int launch_tc(const nq_conv_desc* d, const nq_tc_plan* pl, TcParams& p, c
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   static const int n_prod_env = getenv("NQ_TC_PROD") ? atoi(getenv("NQ_TC_PROD")) : 0;  // tuning override
   p.n_prod = n_prod_env >= 1 && n_prod_env <= 32 ? n_prod_env : 4;
   if (p.n_prod > pl->n_bstages) p.n_prod = pl->n_bstages;

@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();     // everything above ran under the tail of the kernel before this one (nq_common.cuh)
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
   long long dbg_c0 = 0, dbg_t0 = 0;
   if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -789,7 +791,17 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
     if (!dbg_buf) NQ_CUDA_CHECK(cudaMalloc(&dbg_buf, 2 * sizeof(long long)));
     p.dbg = dbg_buf;
   }
-  kern<<<grid, WG_THREADS, pl->smem_bytes, s>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WG_THREADS);
+  cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  NQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   if (dbg_on) {
     long long h[2] = {0, 0};
     NQ_CUDA_CHECK(cudaStreamSynchronize(s));
