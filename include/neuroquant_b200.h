@@ -280,7 +280,10 @@ typedef struct nq_tc_plan {
   int32_t gst;                 /* weight stages per ring slot (one bulk copy and one barrier round trip for all of them); the ring has
                                   n_bstages slots of gst * b_stage_bytes bytes */
   int32_t reserved;
-  int64_t wpk_bytes;           /* size of the packed weight buffer the caller allocates */
+  int64_t wpk_bytes;           /* size of the packed weight buffer the caller allocates.  The order AND the size of the packed
+                                  operand belong to this plan, and the plan depends on every field of the descriptor, d->n included
+                                  (CTA pairs are chosen from 32 pixel tiles on; cg2 with bcat packs 6 instead of 4 bytes per weight):
+                                  pack with the plan the convolution is launched with, re-pack when the batch size changes */
   int64_t workspace_floats;    /* fp32 partial sums nq_tc_conv_dgrad needs when ksplit > 1 */
 } nq_tc_plan;
 
