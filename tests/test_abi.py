@@ -126,6 +126,35 @@ def test_tc_plans_fit_for_every_workload():
                 assert wp.psplits * wp.nsplits * wp.khg * wp.msplit <= max(148, wp.nsplits * wp.khg * wp.msplit)
 
 
+def test_packed_operand_depends_on_the_batch_size():
+    """Host-only statement of what DecoderEngine._fit_packed / the geometry check of `reuse_weights` exist for: the plan of a
+    stage, hence order and size of its packed weights, changes with the batch size.  Stage 3 of HNeRV-Bunny-3M (40 x 80
+    pixels = 25 tiles per frame): one frame stays below the 32 tiles CTA pairs need, two frames pair up, and the pair plan
+    of the data gradient holds the hi plane twice (6 instead of 4 bytes per weight).  The GPU counterpart is
+    tests/test_gpu_fullsize.py::test_packed_operands_follow_the_batch_size."""
+    import ctypes as C
+    import neuroquant_b200 as nq
+    from neuroquant_b200 import _lib as L
+    from neuroquant_b200.engine import stage_descs
+    from neuroquant_b200.workloads import WORKLOADS, embed_shape
+    arch, cfg = WORKLOADS["hnerv-bunny-3m"]
+    _, h0, w0 = embed_shape(cfg, arch)
+    geo = nq.geometry_from_cfg(cfg, arch)
+    plans = {}
+    for n in (1, 2):
+        d = stage_descs(geo, n, h0, w0, True)[3]
+        for direction in (0, 1):
+            pl = L.TcPlan()
+            assert L.lib.nq_tc_plan_conv(C.byref(d), direction, 2, 2, C.byref(pl)) == 0
+            plans[(n, direction)] = pl
+    assert (d.h, d.w) == (40, 80)
+    for direction in (0, 1):
+        assert (plans[(1, direction)].cg2, plans[(2, direction)].cg2) == (0, 1)
+    assert plans[(1, 1)].bcat == 1 and plans[(2, 1)].bcat == 1
+    assert plans[(2, 1)].wpk_bytes * 2 == plans[(1, 1)].wpk_bytes * 3
+    assert plans[(2, 0)].wpk_bytes == plans[(1, 0)].wpk_bytes  # same bytes, another order (each CTA of a pair streams its half)
+
+
 def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     """Every struct the Python side mirrors has the size and trailing-field offset the C header gives it
     (compiled here with gcc: the header is plain C)."""
