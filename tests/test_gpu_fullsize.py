@@ -306,7 +306,8 @@ def test_packed_operands_follow_the_batch_size(monkeypatch):
     torch.cuda.empty_cache()
     ref_one = make().forward(embed[:1]).clone()
 
-    # same kernels on the same plans: expected bit-identical, asserted to 1e-6 (a wrong layout gives garbage)
+    # same kernels on the same plans: expected bit-identical, asserted to 1e-6 (a wrong layout gives garbage).  Measured on
+    # B200, three repetitions: frames and every gradient identical, the loss (fp32 atomics) within 5e-7 relative
     assert (one_first - ref_one).abs().max() < 1e-6 and (one - ref_one).abs().max() < 1e-6
     assert (img - ref_img).abs().max() < 1e-6
     assert (two - ref_img).abs().max() < 2e-5  # the training epilogue evaluates GELU next to GELU', decode evaluates GELU alone
