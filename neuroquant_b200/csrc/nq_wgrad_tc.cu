@@ -49,7 +49,7 @@ struct WgParams {
   int CGS_A, CGS_B, a_plane_bytes, b_plane_bytes, buf_bytes, nbuf;
   int dz_stride, n_valid;  // channels per pixel stored in dz (<= N); columns >= n_valid are zero
   int a_sts;               // shifted input copies staged through registers (one global load, <= ks st.shared) instead of ks cp.async
-  int skip;                // NQ_WG_SKIP (debug): bit 0 shifted-input copies, bit 1 dZ copies, bit 2 MMAs
+  int skip;                // NQ_WG_SKIP (debug): bit 0 shifted-input copies, bit 1 dZ copies (bit 2, MMAs, is masked off at launch)
   long long* dbg;          // NQ_TC_DBG: {SM cycles, ns} of CTA 0
 };
 
@@ -784,7 +784,7 @@ extern "C" int nq_tc_conv_wgrad(const nq_conv_desc* d, const nq_tc_wgrad_plan* p
   static const int sts_env = getenv("NQ_WG_STS") ? atoi(getenv("NQ_WG_STS")) : 1;  // tuning override (0: cp.async copies)
   p.a_sts = sts_env != 0 && p.ks > 1 && p.ks <= 5;
   static const int skip_flags = getenv("NQ_WG_SKIP") ? atoi(getenv("NQ_WG_SKIP")) : 0;
-  p.skip = skip_flags;
+  p.skip = skip_flags & 3;  // bit 2 (no MMAs) leaves the commits out as well and never finishes: not accepted
   static const bool dbg_on = getenv("NQ_TC_DBG") != nullptr;
   static long long* dbg_buf = nullptr;
   if (dbg_on) {  // debugging aid: synchronises after the launch and prints the SM cycles / clock the kernel saw
