@@ -204,7 +204,9 @@ def model_reconstruction(model, cali_data: torch.Tensor, gt, arch: str = "hnerv"
     """Network-wise calibration (calib_model.py:92-240).  `model` is a QuantModel; `cali_data` the decoder
     inputs of every frame; `gt` the frame loader (dicts with 'img' -- fp32 in [0, 1] or uint8 -- and 'idx').  Under
     torch.distributed every rank calls this with the same arguments: mini-batches are sharded by frame and the weight
-    gradients are all-reduced (neuroquant_b200/calibration.py).
+    gradients are all-reduced (neuroquant_b200/calibration.py).  `gt` must then yield the SAME index batches on every rank
+    (a shuffling loader needs an identically seeded generator, as methods/calibrate_network.py builds it; the reference
+    itself is unseeded) and every global batch must split evenly over the ranks (parallel.shard_indices raises).
 
     Additive, keyword-only: `frame_residency` ('auto' | 'hbm' | 'stream', see _FrameSource) and
     `on_iteration(phase, count, loss)` -- called after every iteration with the reconstruction loss of that iteration as
